@@ -1,0 +1,208 @@
+/*
+ * mininf_b200 — C-ABI of the B200-native ELBO engine.
+ *
+ * The reference (tillahoffmann/mininf) has no FFI: its ELBO hot path is
+ * `EvidenceLowerBoundLoss.forward` (mininf/nn.py:212-228), which re-executes the Python model
+ * under a `LogProbTracer` (mininf/core.py:207-277) and lets torch autograd differentiate it.
+ * This header is the boundary a maintainer would bind instead (ctypes stub in INTEGRATION.md):
+ * the host traces the model ONCE into flat tables of plain-old-data and hands them, together
+ * with borrowed device pointers, to the entry points below. Every function
+ *   - is `extern "C"`, takes only pointers / integers / POD structs (no torch types),
+ *   - only ENQUEUES work on `stream` (a cudaStream_t passed as void*), never synchronises,
+ *   - returns 0 on success or a negative MNF_E_* code; `mnf_last_error()` has the text,
+ *   - borrows every pointer for the duration of the enqueued work; it owns no user memory.
+ *
+ * Vocabulary (the reference's): a *site* is one `mininf.sample(name, dist, shape)` statement
+ * (mininf/core.py:300-328); a *latent* site is one the approximation draws
+ * (mininf/nn.py:133-145), an *observed* site is one `condition` pinned (mininf/core.py:331-387);
+ * a *particle* is one reparameterised draw of all latent sites (the reference uses exactly one,
+ * mininf/nn.py:217; S particles := mean over S reference evaluations).
+ *
+ * Packed layouts (all row-major fp32 unless stated):
+ *   z     [S][D]  particle values of all *global* latent sites, D = sum of their element counts
+ *   noise [S][D]  the reparameterisation noise of z: eps ~ N(0,1) for Normal sites, the standard
+ *                 gamma draw for Gamma sites, the drawn value itself for Beta sites
+ *   acc   [S][1+D] fp64 step accumulator: column 0 = sum of scaled log-densities of particle s,
+ *                 column 1+d = d(that sum)/d z[s][d]
+ */
+#ifndef MININF_B200_H_
+#define MININF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNF_ABI_VERSION 3
+
+/* error codes */
+#define MNF_OK 0
+#define MNF_E_INVALID (-1)      /* bad argument (null pointer, unsupported enum, bad shape)   */
+#define MNF_E_UNSUPPORTED (-2)  /* a shape/family combination this build has no kernel for     */
+#define MNF_E_CUDA (-3)         /* a CUDA runtime call failed; text in mnf_last_error()        */
+
+/* distribution families; log-densities restate torch.distributions */
+#define MNF_NORMAL 0            /* params: loc, scale            torch/distributions/normal.py:87-103    */
+#define MNF_GAMMA 1             /* params: concentration, rate   torch/distributions/gamma.py:89-98      */
+#define MNF_BETA 2              /* params: concentration1, concentration0   beta.py:87-91 -> dirichlet.py:90-97 */
+#define MNF_BERNOULLI_PROBS 3   /* params: probs                 bernoulli.py:121-125 + utils.py:101-137 */
+#define MNF_BERNOULLI_LOGITS 4  /* params: logits                bernoulli.py:121-125                    */
+#define MNF_POISSON 5           /* params: rate                  poisson.py:75-79                        */
+#define MNF_NUM_FAMILIES 6
+
+/* inverse links applied to a linear predictor */
+#define MNF_T_ID 0
+#define MNF_T_EXP 1
+
+/* device status bits, OR-ed into `status[0]` by kernels (checked by the host at its sync point) */
+#define MNF_ST_BAD_PARAM 1u     /* a distribution parameter left its arg constraint (e.g. scale<=0, NaN) */
+#define MNF_ST_BAD_VALUE 2u     /* an unmasked value left the support of its distribution      */
+#define MNF_ST_NONFINITE 4u     /* the loss or a gradient is NaN/Inf                           */
+
+/*
+ * One distribution parameter as a scalar link:  value_i = T(A_i + B_i * x_i)  with
+ *   A_i = a_lat < 0 ? a_const : z[s][a_lat + a_stride * i]
+ *   B_i = b_lat < 0 ? b_const : z[s][b_lat + b_stride * i]
+ *   x_i = x == NULL ? 1       : x[x_stride * i]
+ * This closed form covers the user link code of SURVEY §8a row a10 short of matrix products:
+ * constants, data tensors, a latent itself (prior sites), `c + d*x`, `exp(a + b*x)`.
+ */
+typedef struct mnf_link {
+  float a_const;
+  float b_const;
+  int32_t a_lat;
+  int32_t b_lat;
+  int32_t a_stride;
+  int32_t b_stride;
+  const float* x;
+  int32_t x_stride;
+  int32_t transform; /* MNF_T_* */
+} mnf_link_t;
+
+/* A latent site of the approximation (mininf/nn.py:100-159); parameters are the CONSTRAINED
+ * tensors of the torch distribution, already expanded to `numel` elements. */
+typedef struct mnf_latent {
+  int32_t family;  /* MNF_NORMAL | MNF_GAMMA | MNF_BETA */
+  int32_t numel;
+  int32_t offset;  /* first column in z / noise */
+  int32_t reserved;
+  const float* p0; /* Normal loc   | Gamma concentration | Beta concentration1 */
+  const float* p1; /* Normal scale | Gamma rate          | Beta concentration0 */
+} mnf_latent_t;
+
+/* A model site evaluated element-wise (everything LogProbTracer.sample records,
+ * mininf/core.py:211-245, except matrix-product links). */
+typedef struct mnf_site {
+  int32_t family;
+  int32_t value_lat;    /* >= 0: the value is z[s][value_lat + i] (prior of a latent site)     */
+  const float* value;   /* else: observed data, numel elements                                 */
+  const uint8_t* mask;  /* optional torch.bool mask (MaskedTensor sites, core.py:231-239,265)  */
+  int64_t numel;
+  double scale;         /* batch rescaling declared/actual (core.py:267-271), 1 otherwise      */
+  mnf_link_t param[2];
+} mnf_site_t;
+
+/* A site whose first parameter is a dense linear predictor  eta_i = a + X[i,:] . theta
+ * (`X @ theta`, tests/test_mininf.py:11, examples/minibatch.md:33). */
+typedef struct mnf_dense_site {
+  int32_t family;       /* MNF_NORMAL (loc=eta) | MNF_BERNOULLI_LOGITS (logits=eta) | MNF_POISSON (rate=exp(eta)) */
+  int32_t p;            /* features */
+  int64_t n_rows;       /* rows held by THIS rank */
+  int64_t ldx;          /* row stride of X in elements (>= p) */
+  const float* X;       /* [n_rows][ldx] */
+  const float* y;       /* [n_rows] observed values */
+  const uint8_t* mask;  /* optional row mask */
+  int32_t theta_lat;    /* column of theta[0] in z */
+  int32_t icpt_lat;     /* column of a latent scalar intercept, or -1 */
+  float icpt_const;     /* constant intercept when icpt_lat < 0 */
+  int32_t reserved;
+  mnf_link_t scale;     /* MNF_NORMAL only: the scale parameter as a scalar link with x == NULL  */
+  double weight;        /* batch rescaling (core.py:267-271) */
+} mnf_dense_site_t;
+
+/* precision modes of the dense sweep */
+#define MNF_DENSE_FP32 0   /* SIMT fp32 FMA, any p / S                                          */
+#define MNF_DENSE_TF32 1   /* tcgen05 kind::tf32, operands rounded-to-nearest to TF32 in-kernel, */
+                           /* fp32 accumulate in TMEM; needs p in {32,64,96,128}, S in {16..64} %16==0 */
+
+typedef struct mnf_device_info {
+  int32_t sm_count;
+  int32_t cc_major;
+  int32_t cc_minor;
+  int32_t max_smem_optin;
+  int64_t total_mem;
+} mnf_device_info_t;
+
+int mnf_abi_version(void);
+const char* mnf_last_error(void);
+int mnf_device_info(int device, mnf_device_info_t* out);
+
+/* Bytes of scratch `mnf_dense_sweep` / `mnf_site_sweep` need for their per-CTA partial sums. */
+size_t mnf_workspace_bytes(int n_particles, int n_latent_total, int device);
+
+/*
+ * Reparameterised draw of every global latent site for S particles
+ * (FactorizedDistribution.rsample, mininf/nn.py:133-145; Normal.rsample torch normal.py:82-85;
+ * Gamma.rsample gamma.py:79-87; Beta.rsample beta.py:84-85).
+ *   noise_in != NULL : external noise [S][D] (parity mode: the host drew it with the torch
+ *                      generator in the reference's order) and is copied to noise_out;
+ *   noise_in == NULL : Normal sites draw eps from Philox4x32-10 (key = seed, counter =
+ *                      (offset, particle*D + column)); Gamma/Beta sites require external noise.
+ * Also zeroes `acc` [S][1+D] for the step and clears nothing else.
+ */
+int mnf_rsample(const mnf_latent_t* latents_dev, int n_latents, int n_particles, int n_latent_total,
+                const float* noise_in, uint64_t seed, uint64_t offset,
+                float* z, float* noise_out, double* acc, uint32_t* status, void* stream);
+
+/*
+ * Dense-link sweep: for every local row i and particle s evaluates the site's log-density at
+ * eta = a_s + X[i,:].theta_s and its score, and accumulates
+ *   acc[s][0]               += weight * sum_i log p(y_i | eta_is, ...)
+ *   acc[s][1+theta_lat+j]   += weight * sum_i dlogp/deta * X[i,j]
+ *   (+ intercept / scale latent columns)
+ * X and y are read exactly once per call for all particles and both directions
+ * (replaces aten::mv + MvBackward + the elementwise log_prob chain).
+ */
+int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int n_particles,
+                    int n_latent_total, double* acc, void* workspace, size_t workspace_bytes,
+                    uint32_t* status, void* stream);
+
+/*
+ * Element-wise sweep over up to MNF_MAX_FUSED_SITES sites of equal numel whose values are
+ * observed data and whose links reference only scalar latents (stride 0): one pass over the
+ * data for all particles (LogProbTracer.sample + contribution, core.py:211-273).
+ */
+#define MNF_MAX_FUSED_SITES 4
+int mnf_site_sweep(const mnf_site_t* sites, int n_sites, const float* z, int n_particles,
+                   int n_latent_total, double* acc, void* workspace, size_t workspace_bytes,
+                   uint32_t* status, void* stream);
+
+/*
+ * Small sites (priors of global latents, short observed vectors): any link stride, any value
+ * kind; accumulates into acc with fp64 atomics. `sites_dev` is a DEVICE array.
+ */
+int mnf_small_sites(const mnf_site_t* sites_dev, int n_sites, int64_t max_numel, const float* z,
+                    int n_particles, int n_latent_total, double* acc, uint32_t* status,
+                    void* stream);
+
+/*
+ * Combine: loss = -( mean_s acc[s][0] + entropy(q) )   (mininf/nn.py:226-228, entropy
+ * nn.py:124-131) and its gradient w.r.t. the constrained parameters of every latent site through
+ * the reparameterisation (pathwise) derivative, plus the analytic entropy gradient.
+ *   out[0] = loss; out[1 + offset + i] = dloss/dp0_i; out[1 + D + offset + i] = dloss/dp1_i.
+ */
+int mnf_finalize(const mnf_latent_t* latents_dev, int n_latents, int n_particles,
+                 int n_latent_total, const float* z, const float* noise, const double* acc,
+                 int with_entropy, float* out, uint32_t* status, void* stream);
+
+/* Counting scan used by the integer-exact parity checks: out[0]=sum(mask), out[1]=sum(mask*value)
+ * as int64 (value must hold integers); mask may be NULL (all ones). */
+int mnf_masked_count(const float* value, const uint8_t* mask, int64_t numel, int64_t* out,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MININF_B200_H_ */

@@ -1,0 +1,309 @@
+// C-ABI entry points of the mininf_b200 engine (declared in include/mininf_b200.h).
+// Every entry validates its arguments, enqueues kernels on the caller's stream and returns;
+// nothing here synchronises, allocates user-visible memory or throws.
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+#include "dense_simt.cuh"
+#include "dense_tc.cuh"
+#include "site_sweep.cuh"
+#include "small.cuh"
+
+using namespace mnf;
+
+namespace {
+
+struct DeviceCache {
+  bool ready = false;
+  int sm_count = 0;
+  int cc_major = 0;
+  int cc_minor = 0;
+  int max_smem_optin = 0;
+  size_t total_mem = 0;
+};
+
+DeviceCache g_dev[64];
+std::mutex g_dev_mutex;
+
+int device_cache(int device, DeviceCache** out) {
+  if (device < 0) MNF_CUDA_CHECK(cudaGetDevice(&device));
+  if (device >= 64) return fail(MNF_E_INVALID, "device index out of range%s%s");
+  std::lock_guard<std::mutex> lock(g_dev_mutex);
+  DeviceCache& c = g_dev[device];
+  if (!c.ready) {
+    cudaDeviceProp prop;
+    MNF_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    c.sm_count = prop.multiProcessorCount;
+    c.cc_major = prop.major;
+    c.cc_minor = prop.minor;
+    c.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    c.total_mem = prop.totalGlobalMem;
+    c.ready = true;
+  }
+  *out = &c;
+  return MNF_OK;
+}
+
+inline int max_ctas(const DeviceCache& c) { return 4 * c.sm_count; }
+
+int launch_reduce(const float* partial, int n_cta, int S, int ncol, const ColMap& map, double weight,
+                  int D, double* acc, cudaStream_t stream) {
+  const int total = S * ncol;
+  reduce_partials_kernel<<<(total + 255) / 256, 256, 0, stream>>>(partial, n_cta, S, ncol, map,
+                                                                  weight, D, acc);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+template <int FAMILY>
+int launch_dense_tc(const mnf_dense_site_t& site, const float* z, int S, int D, float* partial,
+                    uint32_t* status, int grid, cudaStream_t stream) {
+  auto kernel = tc::dense_tc_kernel<FAMILY>;
+  MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)tc::kSmemBytes));
+  kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(site, z, S, D, partial, status);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+template <int NSITES>
+int launch_site_sweep(const mnf_site_t* sites, const float* z, int S, int D, float* partial,
+                      uint32_t* status, int grid, cudaStream_t stream) {
+  SweepArgs<NSITES> args;
+  for (int i = 0; i < NSITES; ++i) args.site[i] = sites[i];
+  if (S <= 32) {
+    auto kernel = site_sweep_kernel<NSITES, 1>;
+    const size_t smem = site_sweep_smem_bytes<NSITES, 1>();
+    MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, kSweepThreads, smem, stream>>>(args, z, S, D, partial, status);
+  } else if (S <= 64) {
+    auto kernel = site_sweep_kernel<NSITES, 2>;
+    const size_t smem = site_sweep_smem_bytes<NSITES, 2>();
+    MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, kSweepThreads, smem, stream>>>(args, z, S, D, partial, status);
+  } else {
+    auto kernel = site_sweep_kernel<NSITES, 4>;
+    const size_t smem = site_sweep_smem_bytes<NSITES, 4>();
+    MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, kSweepThreads, smem, stream>>>(args, z, S, D, partial, status);
+  }
+  MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+bool family_has_two_params(int family) { return family <= MNF_BETA; }
+
+}  // namespace
+
+extern "C" {
+
+int mnf_abi_version(void) { return MNF_ABI_VERSION; }
+
+const char* mnf_last_error(void) { return g_last_error; }
+
+int mnf_device_info(int device, mnf_device_info_t* out) {
+  if (out == nullptr) return fail(MNF_E_INVALID, "mnf_device_info: out is null%s%s");
+  DeviceCache* c;
+  if (int rc = device_cache(device, &c)) return rc;
+  out->sm_count = c->sm_count;
+  out->cc_major = c->cc_major;
+  out->cc_minor = c->cc_minor;
+  out->max_smem_optin = c->max_smem_optin;
+  out->total_mem = (int64_t)c->total_mem;
+  return MNF_OK;
+}
+
+size_t mnf_workspace_bytes(int n_particles, int n_latent_total, int device) {
+  DeviceCache* c;
+  if (device_cache(device, &c) != MNF_OK) return 0;
+  const size_t ncol = (size_t)std::max(n_latent_total + 3, 1 + 4 * MNF_MAX_FUSED_SITES);
+  return (size_t)max_ctas(*c) * (size_t)n_particles * ncol * sizeof(float);
+}
+
+int mnf_rsample(const mnf_latent_t* latents_dev, int n_latents, int n_particles, int n_latent_total,
+                const float* noise_in, uint64_t seed, uint64_t offset, float* z, float* noise_out,
+                double* acc, uint32_t* status, void* stream) {
+  if (!latents_dev || !z || !noise_out || !acc || !status || n_latents <= 0 || n_particles <= 0 ||
+      n_latent_total <= 0)
+    return fail(MNF_E_INVALID, "mnf_rsample: null pointer or empty latent table%s%s");
+  const int64_t total = (int64_t)n_particles * (n_latent_total + 1);
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, 1024);
+  rsample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(latents_dev, n_latents, n_particles,
+                                                         n_latent_total, noise_in, seed, offset, z,
+                                                         noise_out, acc, status);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int n_particles,
+                    int n_latent_total, double* acc, void* workspace, size_t workspace_bytes,
+                    uint32_t* status, void* stream_) {
+  if (!site || !z || !acc || !workspace || !status)
+    return fail(MNF_E_INVALID, "mnf_dense_sweep: null pointer%s%s");
+  const mnf_dense_site_t s = *site;
+  const int S = n_particles, D = n_latent_total, p = s.p;
+  if (!s.X || !s.y || p <= 0 || s.n_rows < 0 || s.ldx < p || S <= 0)
+    return fail(MNF_E_INVALID, "mnf_dense_sweep: bad site shape%s%s");
+  if (s.family != MNF_NORMAL && s.family != MNF_BERNOULLI_LOGITS && s.family != MNF_POISSON)
+    return fail(MNF_E_UNSUPPORTED, "mnf_dense_sweep: family has no dense-link kernel%s%s");
+  if (s.theta_lat < 0 || s.theta_lat + p > D || s.icpt_lat >= D)
+    return fail(MNF_E_INVALID, "mnf_dense_sweep: latent columns out of range%s%s");
+  if (s.family == MNF_NORMAL && s.scale.x != nullptr)
+    return fail(MNF_E_UNSUPPORTED, "mnf_dense_sweep: per-row scale is not supported%s%s");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DeviceCache* c;
+  if (int rc = device_cache(-1, &c)) return rc;
+  if (s.n_rows == 0) return MNF_OK;
+
+  const int ncol = 1 + p + 2;
+  float* partial = static_cast<float*>(workspace);
+  int grid = 0;
+
+  if (mode == MNF_DENSE_TF32) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(s.X) % 16 == 0) && (s.ldx % 4 == 0);
+    const bool has_icpt = s.icpt_lat >= 0 || s.icpt_const != 0.0f;
+    if (p != tc::kP || S > tc::kNS || !aligned || has_icpt || c->cc_major != 10)
+      return fail(MNF_E_UNSUPPORTED,
+                  "mnf_dense_sweep: TF32 mode needs p == 64, S <= 64, no intercept, 16-byte aligned "
+                  "rows and an sm_100 device%s%s");
+    const int64_t n_tiles = (s.n_rows + tc::kTileM - 1) / tc::kTileM;
+    grid = (int)std::min<int64_t>(n_tiles, c->sm_count);
+    if ((size_t)grid * S * ncol * sizeof(float) > workspace_bytes)
+      return fail(MNF_E_INVALID, "mnf_dense_sweep: workspace too small%s%s");
+    int rc;
+    if (s.family == MNF_NORMAL) rc = launch_dense_tc<MNF_NORMAL>(s, z, S, D, partial, status, grid, stream);
+    else if (s.family == MNF_BERNOULLI_LOGITS) rc = launch_dense_tc<MNF_BERNOULLI_LOGITS>(s, z, S, D, partial, status, grid, stream);
+    else rc = launch_dense_tc<MNF_POISSON>(s, z, S, D, partial, status, grid, stream);
+    if (rc) return rc;
+  } else if (mode == MNF_DENSE_FP32) {
+    const size_t smem = dense_simt_smem_bytes(S, p);
+    if (smem > (size_t)c->max_smem_optin)
+      return fail(MNF_E_UNSUPPORTED, "mnf_dense_sweep: p x S too large for the fp32 kernel%s%s");
+    const int64_t n_tiles = (s.n_rows + kSimtRows - 1) / kSimtRows;
+    grid = (int)std::min<int64_t>(n_tiles, 2 * c->sm_count);
+    if ((size_t)grid * S * ncol * sizeof(float) > workspace_bytes)
+      return fail(MNF_E_INVALID, "mnf_dense_sweep: workspace too small%s%s");
+    MNF_CUDA_CHECK(cudaFuncSetAttribute(dense_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dense_simt_kernel<<<grid, kSimtThreads, smem, stream>>>(s, z, S, D, partial, status);
+    MNF_CUDA_CHECK(cudaGetLastError());
+  } else {
+    return fail(MNF_E_INVALID, "mnf_dense_sweep: unknown mode%s%s");
+  }
+
+  ColMap map;
+  map.n_vec = p;
+  map.vec_lat = s.theta_lat;
+  map.n_scalar = 2;
+  for (int i = 0; i < 16; ++i) map.scalar_lat[i] = -1;
+  map.scalar_lat[0] = s.icpt_lat;
+  // gradient w.r.t. the scale link's pre-transform value u goes to its latent scalar
+  map.scalar_lat[1] = s.family == MNF_NORMAL ? s.scale.a_lat : -1;
+  return launch_reduce(partial, grid, S, ncol, map, s.weight, D, acc, stream);
+}
+
+int mnf_site_sweep(const mnf_site_t* sites, int n_sites, const float* z, int n_particles,
+                   int n_latent_total, double* acc, void* workspace, size_t workspace_bytes,
+                   uint32_t* status, void* stream_) {
+  if (!sites || !z || !acc || !workspace || !status)
+    return fail(MNF_E_INVALID, "mnf_site_sweep: null pointer%s%s");
+  if (n_sites < 1 || n_sites > MNF_MAX_FUSED_SITES)
+    return fail(MNF_E_INVALID, "mnf_site_sweep: 1..MNF_MAX_FUSED_SITES sites per call%s%s");
+  const int S = n_particles, D = n_latent_total;
+  if (S <= 0 || S > 128) return fail(MNF_E_UNSUPPORTED, "mnf_site_sweep: 1..128 particles%s%s");
+  for (int i = 0; i < n_sites; ++i) {
+    const mnf_site_t& st = sites[i];
+    if (st.numel != sites[0].numel || st.value == nullptr || st.value_lat >= 0)
+      return fail(MNF_E_INVALID, "mnf_site_sweep: fused sites need observed values of equal length%s%s");
+    if (st.family < 0 || st.family >= MNF_NUM_FAMILIES)
+      return fail(MNF_E_INVALID, "mnf_site_sweep: unknown family%s%s");
+    for (int p = 0; p < 2; ++p) {
+      const mnf_link_t& L = st.param[p];
+      if ((L.a_lat >= 0 && L.a_stride != 0) || (L.b_lat >= 0 && L.b_stride != 0))
+        return fail(MNF_E_UNSUPPORTED, "mnf_site_sweep: links must reference scalar latents%s%s");
+      if (L.a_lat >= D || L.b_lat >= D)
+        return fail(MNF_E_INVALID, "mnf_site_sweep: latent column out of range%s%s");
+    }
+  }
+  if (sites[0].numel == 0) return MNF_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DeviceCache* c;
+  if (int rc = device_cache(-1, &c)) return rc;
+  const int64_t n_chunks = (sites[0].numel + 31) / 32;
+  const int grid = (int)std::min<int64_t>((n_chunks + kSweepWarps - 1) / kSweepWarps, 2 * c->sm_count);
+  const int n_templ = n_sites == 1 ? 1 : (n_sites == 2 ? 2 : 4);
+  const int ncol = 1 + 4 * n_templ;
+  if ((size_t)grid * S * ncol * sizeof(float) > workspace_bytes)
+    return fail(MNF_E_INVALID, "mnf_site_sweep: workspace too small%s%s");
+  float* partial = static_cast<float*>(workspace);
+
+  // pad the site list to the template width with inert duplicates of zero weight
+  mnf_site_t padded[MNF_MAX_FUSED_SITES];
+  for (int i = 0; i < n_templ; ++i) {
+    padded[i] = sites[i < n_sites ? i : 0];
+    if (i >= n_sites) {
+      padded[i].scale = 0.0;
+      for (int p = 0; p < 2; ++p) { padded[i].param[p].a_lat = -1; padded[i].param[p].b_lat = -1; }
+    }
+  }
+  int rc;
+  if (n_templ == 1) rc = launch_site_sweep<1>(padded, z, S, D, partial, status, grid, stream);
+  else if (n_templ == 2) rc = launch_site_sweep<2>(padded, z, S, D, partial, status, grid, stream);
+  else rc = launch_site_sweep<4>(padded, z, S, D, partial, status, grid, stream);
+  if (rc) return rc;
+
+  ColMap map;
+  map.n_vec = 0;
+  map.vec_lat = 0;
+  map.n_scalar = 4 * n_templ;
+  for (int i = 0; i < 16; ++i) map.scalar_lat[i] = -1;
+  for (int i = 0; i < n_sites; ++i) {
+    const bool two = family_has_two_params(sites[i].family);
+    map.scalar_lat[4 * i + 0] = sites[i].param[0].a_lat;
+    map.scalar_lat[4 * i + 1] = sites[i].param[0].b_lat;
+    map.scalar_lat[4 * i + 2] = two ? sites[i].param[1].a_lat : -1;
+    map.scalar_lat[4 * i + 3] = two ? sites[i].param[1].b_lat : -1;
+  }
+  return launch_reduce(partial, grid, S, ncol, map, 1.0, D, acc, stream);
+}
+
+int mnf_small_sites(const mnf_site_t* sites_dev, int n_sites, int64_t max_numel, const float* z,
+                    int n_particles, int n_latent_total, double* acc, uint32_t* status,
+                    void* stream) {
+  if (n_sites == 0) return MNF_OK;
+  if (!sites_dev || !z || !acc || !status || n_sites < 0 || max_numel < 0)
+    return fail(MNF_E_INVALID, "mnf_small_sites: null pointer or negative size%s%s");
+  if (max_numel == 0) return MNF_OK;
+  const int bx = (int)std::min<int64_t>((max_numel + kSmallThreads - 1) / kSmallThreads, 1024);
+  dim3 grid(bx, n_sites);
+  small_sites_kernel<<<grid, kSmallThreads, 0, (cudaStream_t)stream>>>(sites_dev, z, n_particles,
+                                                                       n_latent_total, acc, status);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+int mnf_finalize(const mnf_latent_t* latents_dev, int n_latents, int n_particles, int n_latent_total,
+                 const float* z, const float* noise, const double* acc, int with_entropy, float* out,
+                 uint32_t* status, void* stream) {
+  if (!latents_dev || !z || !noise || !acc || !out || !status || n_latents <= 0)
+    return fail(MNF_E_INVALID, "mnf_finalize: null pointer or empty latent table%s%s");
+  finalize_kernel<<<1, kFinalThreads, 0, (cudaStream_t)stream>>>(latents_dev, n_latents, n_particles,
+                                                                 n_latent_total, z, noise, acc,
+                                                                 with_entropy, out, status);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+int mnf_masked_count(const float* value, const uint8_t* mask, int64_t numel, int64_t* out,
+                     void* stream) {
+  if (!value || !out || numel < 0) return fail(MNF_E_INVALID, "mnf_masked_count: bad argument%s%s");
+  MNF_CUDA_CHECK(cudaMemsetAsync(out, 0, 2 * sizeof(int64_t), (cudaStream_t)stream));
+  if (numel == 0) return MNF_OK;
+  const int grid = (int)std::min<int64_t>((numel + 255) / 256, 2048);
+  masked_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      value, mask, numel, reinterpret_cast<unsigned long long*>(out));
+  MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,281 @@
+// O(S*D) kernels of the ELBO step: the reparameterised draw of the global latent sites, the
+// element-wise evaluation of short sites (priors, small observed vectors), the fixed-order
+// reduction of sweep partials into the step accumulator, and the final combine with entropy and
+// pathwise gradients. None of these touches the big observed arrays.
+#pragma once
+
+#include "common.cuh"
+#include "implicit_grad.cuh"
+
+namespace mnf {
+
+__device__ __forceinline__ int find_latent(const mnf_latent_t* lat, int n, int col) {
+  int k = 0;
+  for (int i = 1; i < n; ++i)
+    if (col >= lat[i].offset) k = i;
+  return k;
+}
+
+// -------------------------------------------------------------------------------------------
+// rsample: z[s][d] from noise, FactorizedDistribution.rsample (mininf/nn.py:133-145)
+// -------------------------------------------------------------------------------------------
+__global__ void rsample_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
+                               const float* __restrict__ noise_in, uint64_t seed, uint64_t offset,
+                               float* __restrict__ z, float* __restrict__ noise_out,
+                               double* __restrict__ acc, uint32_t* __restrict__ status) {
+  const int64_t n_z = (int64_t)S * D;
+  const int64_t n_acc = (int64_t)S * (D + 1);
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n_acc; i += nth) acc[i] = 0.0;
+  uint32_t bad = 0;
+  for (int64_t i = tid; i < n_z; i += nth) {
+    const int d = (int)(i % D);
+    const mnf_latent_t L = lat[find_latent(lat, n_lat, d)];
+    const int e = d - L.offset;
+    const float p0 = L.p0[e], p1 = L.p1[e];
+    float nz, val;
+    if (L.family == MNF_NORMAL) {
+      // Normal.rsample: loc + eps * scale                       TORCH normal.py:82-85
+      if (noise_in != nullptr) {
+        nz = noise_in[i];
+      } else {
+        Philox rng(seed, offset, (uint64_t)i);
+        const uint4 r = rng.next();
+        nz = box_muller(r.x, r.y).x;
+      }
+      val = fmaf(nz, p1, p0);
+      if (!(p1 > 0.0f) || p0 != p0) bad |= MNF_ST_BAD_PARAM;
+    } else if (L.family == MNF_GAMMA) {
+      // Gamma.rsample: standard_gamma(alpha) / rate, clamped at tiny   TORCH gamma.py:79-87
+      nz = noise_in != nullptr ? noise_in[i] : NAN;
+      val = fmaxf(nz / p1, kFloatTiny);
+      if (!(p0 > 0.0f) || !(p1 > 0.0f)) bad |= MNF_ST_BAD_PARAM;
+    } else {
+      // Beta.rsample: first component of a 2-simplex Dirichlet draw    TORCH beta.py:84-85
+      nz = noise_in != nullptr ? noise_in[i] : NAN;
+      val = nz;
+      if (!(p0 > 0.0f) || !(p1 > 0.0f)) bad |= MNF_ST_BAD_PARAM;
+    }
+    z[i] = val;
+    noise_out[i] = nz;
+  }
+  if (bad) atomicOr(status, bad);
+}
+
+// -------------------------------------------------------------------------------------------
+// small sites: LogProbTracer.sample + contribution (mininf/core.py:211-273) for short sites.
+// grid = (blocks over elements, n_sites); every thread owns elements, loops over particles.
+// -------------------------------------------------------------------------------------------
+constexpr int kSmallThreads = 128;
+
+__global__ void __launch_bounds__(kSmallThreads)
+small_sites_kernel(const mnf_site_t* __restrict__ sites, const float* __restrict__ z, int S, int D,
+                   double* __restrict__ acc, uint32_t* __restrict__ status) {
+  const mnf_site_t site = sites[blockIdx.y];
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if ((int64_t)blockIdx.x * blockDim.x >= site.numel) return;
+  const bool g0 = link_has_latent(site.param[0]);
+  const bool g1 = link_has_latent(site.param[1]);
+  const bool two = site.family <= MNF_BETA;  // families with a second parameter
+  const float w = (float)site.scale;
+  __shared__ double s_lp[kSmallThreads / 32];
+  uint32_t bad = 0;
+
+  for (int s = 0; s < S; ++s) {
+    const float* zs = z + (int64_t)s * D;
+    double* as = acc + (int64_t)s * (D + 1);
+    double lp_sum = 0.0;
+    // scalar-latent gradient sums of this thread (stride-0 targets)
+    float gA0 = 0.f, gB0 = 0.f, gA1 = 0.f, gB1 = 0.f;
+    for (int64_t i = i0; i < site.numel; i += stride) {
+      if (site.mask != nullptr && site.mask[i] == 0) continue;
+      const float v = site.value_lat >= 0 ? zs[site.value_lat + i] : site.value[i];
+      const LinkVal l0 = eval_link(site.param[0], zs, i);
+      LinkVal l1; l1.value = 0.f; l1.du = 0.f; l1.x = 1.f;
+      if (two) l1 = eval_link(site.param[1], zs, i);
+      const Dens dn = density(site.family, v, l0.value, l1.value, g0 || g1);
+      if (dn.bad_param) bad |= MNF_ST_BAD_PARAM;
+      if (dn.bad_value) bad |= MNF_ST_BAD_VALUE;
+      lp_sum += (double)dn.lp;
+      if (site.value_lat >= 0) atomicAdd(as + 1 + site.value_lat + i, (double)(w * dn.dv));
+      if (g0) {
+        const float du = dn.d0 * l0.du;
+        const mnf_link_t& L = site.param[0];
+        if (L.a_lat >= 0) { if (L.a_stride) atomicAdd(as + 1 + L.a_lat + L.a_stride * i, (double)(w * du)); else gA0 += du; }
+        if (L.b_lat >= 0) { if (L.b_stride) atomicAdd(as + 1 + L.b_lat + L.b_stride * i, (double)(w * du * l0.x)); else gB0 += du * l0.x; }
+      }
+      if (two && g1) {
+        const float du = dn.d1 * l1.du;
+        const mnf_link_t& L = site.param[1];
+        if (L.a_lat >= 0) { if (L.a_stride) atomicAdd(as + 1 + L.a_lat + L.a_stride * i, (double)(w * du)); else gA1 += du; }
+        if (L.b_lat >= 0) { if (L.b_stride) atomicAdd(as + 1 + L.b_lat + L.b_stride * i, (double)(w * du * l1.x)); else gB1 += du * l1.x; }
+      }
+    }
+    // block-reduce the log-density and the scalar-latent gradient sums, one atomic per block
+    lp_sum = warp_sum(lp_sum);
+    gA0 = warp_sum(gA0); gB0 = warp_sum(gB0); gA1 = warp_sum(gA1); gB1 = warp_sum(gB1);
+    if ((threadIdx.x & 31) == 0) {
+      s_lp[threadIdx.x >> 5] = lp_sum;
+      const mnf_link_t& L0 = site.param[0];
+      const mnf_link_t& L1 = site.param[1];
+      if (g0 && L0.a_lat >= 0 && L0.a_stride == 0 && gA0 != 0.f) atomicAdd(as + 1 + L0.a_lat, (double)(w * gA0));
+      if (g0 && L0.b_lat >= 0 && L0.b_stride == 0 && gB0 != 0.f) atomicAdd(as + 1 + L0.b_lat, (double)(w * gB0));
+      if (two && g1 && L1.a_lat >= 0 && L1.a_stride == 0 && gA1 != 0.f) atomicAdd(as + 1 + L1.a_lat, (double)(w * gA1));
+      if (two && g1 && L1.b_lat >= 0 && L1.b_stride == 0 && gB1 != 0.f) atomicAdd(as + 1 + L1.b_lat, (double)(w * gB1));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int k = 0; k < kSmallThreads / 32; ++k) t += s_lp[k];
+      atomicAdd(as, (double)site.scale * t);
+    }
+    __syncthreads();
+  }
+  if (bad) atomicOr(status, bad);
+}
+
+// -------------------------------------------------------------------------------------------
+// Fixed-order reduction of per-CTA sweep partials [n_cta][S][ncol] (fp32) into acc (fp64).
+// Column c of a partial goes to acc column colmap(c): 0 -> log-density, 1+k -> latent column.
+// -------------------------------------------------------------------------------------------
+struct ColMap {
+  // partial column 0 is the log-density; then `n_vec` consecutive latent columns starting at
+  // vec_lat (theta of a dense site), then up to 16 individually mapped scalar latent columns.
+  int32_t n_vec;
+  int32_t vec_lat;
+  int32_t n_scalar;
+  int32_t scalar_lat[16];
+};
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_cta, int S, int ncol,
+                                       ColMap map, double weight, int D,
+                                       double* __restrict__ acc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= S * ncol) return;
+  const int s = idx / ncol, c = idx % ncol;
+  int target;
+  if (c == 0) target = 0;
+  else if (c <= map.n_vec) target = 1 + map.vec_lat + (c - 1);
+  else {
+    const int k = c - 1 - map.n_vec;
+    if (k >= map.n_scalar || map.scalar_lat[k] < 0) return;
+    target = 1 + map.scalar_lat[k];
+  }
+  double t = 0.0;
+  for (int b = 0; b < n_cta; ++b) t += (double)partial[((int64_t)b * S + s) * ncol + c];
+  // several partial columns may map to one latent column (e.g. the same scalar latent used by
+  // two fused sites), hence the atomic; launches are stream-ordered.
+  atomicAdd(acc + (int64_t)s * (D + 1) + target, weight * t);
+}
+
+// -------------------------------------------------------------------------------------------
+// finalize: loss = -(mean_s acc[s][0] + H[q]) (mininf/nn.py:226-228) and gradients w.r.t. the
+// constrained parameters via the pathwise derivative of each family's rsample.
+// -------------------------------------------------------------------------------------------
+constexpr int kFinalThreads = 256;
+
+__global__ void __launch_bounds__(kFinalThreads)
+finalize_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
+                const float* __restrict__ z, const float* __restrict__ noise,
+                const double* __restrict__ acc, int with_entropy, float* __restrict__ out,
+                uint32_t* __restrict__ status) {
+  __shared__ double red[kFinalThreads];
+  const double invS = 1.0 / (double)S;
+  double ent = 0.0;
+  bool nonfinite = false;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const mnf_latent_t L = lat[find_latent(lat, n_lat, d)];
+    const int e = d - L.offset;
+    const double p0 = (double)L.p0[e], p1 = (double)L.p1[e];
+    double g0 = 0.0, g1 = 0.0, h = 0.0, dh0 = 0.0, dh1 = 0.0;
+    if (L.family == MNF_NORMAL) {
+      // z = loc + eps*scale; H = 0.5 + 0.5 log(2 pi) + log(scale)   TORCH normal.py:114-115
+      for (int s = 0; s < S; ++s) {
+        const double g = acc[(int64_t)s * (D + 1) + 1 + d];
+        g0 += g;
+        g1 += g * (double)noise[(int64_t)s * D + d];
+      }
+      h = 0.5 + 0.91893853320467274178 + log(p1);
+      dh1 = 1.0 / p1;
+    } else if (L.family == MNF_GAMMA) {
+      // z = g/rate: dz/dalpha = standard_gamma_grad(alpha, g)/rate, dz/drate = -g/rate^2
+      // H = alpha - log(rate) + lgamma(alpha) + (1-alpha) digamma(alpha)   TORCH gamma.py:100-106
+      for (int s = 0; s < S; ++s) {
+        const double g = acc[(int64_t)s * (D + 1) + 1 + d];
+        const double gam = (double)noise[(int64_t)s * D + d];
+        const bool clamped = gam / p1 < (double)kFloatTiny;  // clamp_ is outside autograd: grads as if unclamped
+        (void)clamped;
+        g0 += g * standard_gamma_grad(p0, gam) / p1;
+        g1 += g * (-gam / (p1 * p1));
+      }
+      h = p0 - log(p1) + lgamma(p0) + (1.0 - p0) * digamma_d(p0);
+      dh0 = 1.0 + (1.0 - p0) * trigamma_d(p0);
+      dh1 = -1.0 / p1;
+    } else {
+      // Beta(c1 = p0, c0 = p1) as a 2-simplex Dirichlet; _Dirichlet backward dirichlet.py:16-35:
+      // grad_k = dirichlet_grad(x_k, c_k, total) * (go_k - sum_j x_j go_j) with go = (g, 0).
+      const double tot = p0 + p1;
+      for (int s = 0; s < S; ++s) {
+        const double g = acc[(int64_t)s * (D + 1) + 1 + d];
+        const double x = (double)noise[(int64_t)s * D + d];
+        g0 += dirichlet_grad(x, p0, tot) * g * (1.0 - x);
+        g1 += dirichlet_grad(1.0 - x, p1, tot) * (-x * g);
+      }
+      // Dirichlet entropy with k = 2                                TORCH dirichlet.py:122-130
+      const double dt = digamma_d(tot);
+      h = lgamma(p0) + lgamma(p1) - lgamma(tot) - (p0 - 1.0) * digamma_d(p0) -
+          (p1 - 1.0) * digamma_d(p1) + (tot - 2.0) * dt;
+      const double tt = trigamma_d(tot);
+      dh0 = -(p0 - 1.0) * trigamma_d(p0) + (tot - 2.0) * tt;
+      dh1 = -(p1 - 1.0) * trigamma_d(p1) + (tot - 2.0) * tt;
+    }
+    if (!with_entropy) { h = 0.0; dh0 = 0.0; dh1 = 0.0; }
+    ent += h;
+    const double o0 = -(g0 * invS + dh0);
+    const double o1 = -(g1 * invS + dh1);
+    if (!isfinite(o0) || !isfinite(o1)) nonfinite = true;
+    out[1 + d] = (float)o0;
+    out[1 + D + d] = (float)o1;
+  }
+  // total log joint over particles
+  double lj = 0.0;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) lj += acc[(int64_t)s * (D + 1)];
+  red[threadIdx.x] = ent + lj * invS;
+  __syncthreads();
+  for (int o = kFinalThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double loss = -red[0];
+    out[0] = (float)loss;
+    if (!isfinite(loss)) nonfinite = true;
+  }
+  if (nonfinite) atomicOr(status, MNF_ST_NONFINITE);
+}
+
+// -------------------------------------------------------------------------------------------
+// integer-exact counting scan (parity checks on masks and count data)
+// -------------------------------------------------------------------------------------------
+__global__ void masked_count_kernel(const float* __restrict__ value, const uint8_t* __restrict__ mask,
+                                    int64_t n, unsigned long long* __restrict__ out) {
+  unsigned long long cnt = 0, tot = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const bool m = mask == nullptr || mask[i] != 0;
+    if (m) {
+      cnt += 1;
+      tot += (unsigned long long)(long long)llrintf(value[i]);
+    }
+  }
+  cnt = warp_sum(cnt);
+  tot = warp_sum(tot);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out, cnt);
+    atomicAdd(out + 1, tot);
+  }
+}
+
+}  // namespace mnf
