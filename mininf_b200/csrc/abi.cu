@@ -56,13 +56,55 @@ int launch_reduce(const float* partial, int n_cta, int S, int ncol, const ColMap
   return MNF_OK;
 }
 
+// cuTensorMapEncodeTiled is resolved through the runtime so the library has no link-time
+// dependency on libcuda.
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                      const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int tensor_map_encoder(TensorMapEncodeFn* out) {
+  static TensorMapEncodeFn fn = nullptr;
+  static std::mutex m;
+  std::lock_guard<std::mutex> lock(m);
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MNF_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || ptr == nullptr)
+      return fail(MNF_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver%s%s");
+    fn = reinterpret_cast<TensorMapEncodeFn>(ptr);
+  }
+  *out = fn;
+  return MNF_OK;
+}
+
+// X [n_rows][ldx] fp32 as a 2-D tensor (features fastest), boxes of 32 features x 128 rows,
+// data type TFLOAT32: the TMA unit rounds to tf32 (nearest even) while copying.
+int make_x_map(const mnf_dense_site_t& site, CUtensorMapSwizzle swizzle, CUtensorMap* map) {
+  TensorMapEncodeFn encode;
+  if (int rc = tensor_map_encoder(&encode)) return rc;
+  const cuuint64_t dims[2] = {(cuuint64_t)site.p, (cuuint64_t)site.n_rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)site.ldx * sizeof(float)};
+  const cuuint32_t box[2] = {32, (cuuint32_t)tc::kTileM};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(site.X), dims,
+                            strides, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MNF_E_CUDA, "cuTensorMapEncodeTiled failed%s%s");
+  return MNF_OK;
+}
+
 template <int FAMILY>
 int launch_dense_tc(const mnf_dense_site_t& site, const float* z, int S, int D, float* partial,
                     uint32_t* status, int grid, cudaStream_t stream) {
+  CUtensorMap map_k, map_mn;
+  if (int rc = make_x_map(site, CU_TENSOR_MAP_SWIZZLE_128B, &map_k)) return rc;
+  if (int rc = make_x_map(site, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, &map_mn)) return rc;
   auto kernel = tc::dense_tc_kernel<FAMILY>;
   MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)tc::kSmemBytes));
-  kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(site, z, S, D, partial, status);
+  kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_k, map_mn, site, z, S, D, partial, status);
   MNF_CUDA_CHECK(cudaGetLastError());
   return MNF_OK;
 }
@@ -161,7 +203,8 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
   int grid = 0;
 
   if (mode == MNF_DENSE_TF32) {
-    const bool aligned = (reinterpret_cast<uintptr_t>(s.X) % 16 == 0) && (s.ldx % 4 == 0);
+    const bool aligned = (reinterpret_cast<uintptr_t>(s.X) % 16 == 0) && (s.ldx % 4 == 0) &&
+                         s.n_rows < (int64_t)1 << 31;
     const bool has_icpt = s.icpt_lat >= 0 || s.icpt_const != 0.0f;
     if (p != tc::kP || S > tc::kNS || !aligned || has_icpt || c->cc_major != 10)
       return fail(MNF_E_UNSUPPORTED,
@@ -305,5 +348,13 @@ int mnf_masked_count(const float* value, const uint8_t* mask, int64_t numel, int
   MNF_CUDA_CHECK(cudaGetLastError());
   return MNF_OK;
 }
+
+#ifdef MNF_TC_DEBUG
+int mnf_debug_buffer(void* ptr) {
+  float* p = static_cast<float*>(ptr);
+  MNF_CUDA_CHECK(cudaMemcpyToSymbol(tc::g_tc_debug, &p, sizeof(p)));
+  return MNF_OK;
+}
+#endif
 
 }  // extern "C"

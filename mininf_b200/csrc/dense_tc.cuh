@@ -1,31 +1,61 @@
 // Dense-link sweep, tcgen05 variant (MNF_DENSE_TF32) for sm_100a.
 //
-// One persistent CTA per SM streams 128-row tiles of X exactly once and runs BOTH matrix products
-// of the step on the 5th-generation tensor cores, with the X tile shared between them in smem:
+// One persistent CTA per SM streams 128-row tiles of X from HBM exactly once and runs BOTH matrix
+// products of the ELBO step on the 5th-generation tensor cores, in the transposed orientation
+// that keeps every intermediate in tensor memory:
 //
-//   eta[128 x S]  = Xtile[128 x p] . Theta^T[p x S]       tcgen05.mma kind::tf32, M=128 N=S K=p
-//                   A = Xtile as a K-major  SWIZZLE_128B operand, B = Theta K-major, D in TMEM
-//   R  [128 x S]  = score(y, eta)                          epilogue warps: tcgen05.ld -> registers
-//   G  [p x S]   += Xtile^T[p x 128] . R[128 x S]          tcgen05.mma kind::tf32, M=p N=S K=128
-//                   A = the SAME smem tile read as an MN-major operand, B = R MN-major,
-//                   D accumulates in TMEM across every tile the CTA owns
+//   eta^T[S x 128] = Theta[S x p] . Xtile^T[p x 128]      tcgen05.mma kind::tf32, M=64 N=128 K=p
+//                    A = Theta resident in TMEM (TS mode), B = X tile, K-major SWIZZLE_128B
+//   R^T  [S x 128] = score(y, eta)                        epilogue warps, IN PLACE in TMEM:
+//                    tcgen05.ld -> registers -> log-density / score -> tcgen05.st
+//   G^T  [S x p]  += R^T[S x 128] . Xtile[128 x p]        tcgen05.mma kind::tf32, M=64 N=p K=128
+//                    A = the eta accumulator columns themselves (TS mode), B = X tile, MN-major
 //
-// Precision mode (stated): operands are rounded to nearest to TF32 (10-bit mantissa)
-// IN THE KERNEL — X by the producer warps on its way from HBM to shared memory, Theta and R before
-// they are stored — products are exact, accumulation is fp32 in TMEM. The tensor core itself
-// truncates fp32 inputs, which would bias eta by ~2^-11 relative; rounding first removes the bias
-// (measured effect in DESIGN.md). Log-densities, residual statistics and all reductions are fp32
-// / fp64 SIMT.
+// so the residual matrix never touches shared memory, and an epilogue thread owns one particle:
+// its per-particle statistics are single registers.
 //
-// Warp roles (416 threads): warps 0-3 epilogue (TMEM lane quadrant == warp id), warps 4-11 two
-// producer groups that alternate tiles (coalesced 128-bit LDG -> round -> swizzled STS.128 ->
-// fence.proxy.async -> mbarrier), warp 12 allocates TMEM and one elected lane issues every MMA.
-// Pipelines: X ring (kStages), double-buffered eta accumulator and R tile, all mbarrier based.
+// Facts measured on B200 that shape this kernel (tools/umma_probe.cu, umma_time.cu,
+// umma_ts_probe.cu; numbers in DESIGN.md):
+//  * kind::tf32 accepts MN-major operands ONLY in the SWIZZLE_128B_BASE32B layout and K-major
+//    operands only in the 16-byte-atom layouts, so the X tile is kept in shared memory as two
+//    images written from the same registers (HBM is still read once).
+//  * one tf32 MMA costs about N/2 + 11 cycles, plus M/4 when A is fetched from shared memory;
+//    A-in-TMEM removes that term, and MN-major costs the same as K-major.
+//  * MMAs must be issued by an `elect.sync`-elected lane under warp-uniform control flow; a
+//    `threadIdx.x == 0` guard makes the compiler wrap every UTCHMMA in a vote loop (~90 cycles).
+//  * the tensor core accumulates with truncation: ~1e4 chained accumulations into one TMEM tile
+//    bias the sum by ~3e-4 relative. The gradient accumulator is therefore ping-ponged between two
+//    TMEM tiles and drained into fp32 registers every kFlush tiles.
+//
+// Precision mode (stated): X, Theta and R are rounded to nearest to TF32 (10-bit
+// mantissa) before they reach the tensor core - X by the TMA unit on its way from HBM to shared
+// memory (ties to even), Theta and R by the epilogue warps (ties away) - products are exact,
+// accumulation is fp32 in TMEM; log-densities, residual statistics and reductions are fp32 / fp64
+// SIMT.
+//
+//  * register-staged loads cannot stream X fast enough: a warp sustains only ~4-5 outstanding
+//    LDG.128, so HBM rate is set by the NUMBER OF WARPS issuing loads (tools/ldg_probe.cu: 8
+//    warps/SM 4.0 TB/s, 16 -> 6.6, 32 -> 7.3 TB/s). TMA has no such limit and needs no registers.
+//  * TMA with tensor-map data type TFLOAT32 rounds fp32 to tf32 to-nearest-EVEN on its way into
+//    shared memory, and SWIZZLE_128B / SWIZZLE_128B_ATOM_32B produce exactly the two operand
+//    images, zero-filling rows past the end (tools/tma_probe.cu: 8192/8192 elements incl. ties).
+//
+// Data movement: one elected lane per ring issues cp.async.bulk.tensor loads. The MN-major ring is
+// kMnStages deep and is what keeps HBM requests in flight; the K-major image of a tile is only
+// needed until its eta product has retired, so that ring is kKStages deep and its loads hit L2
+// (the same rows were fetched moments earlier for the MN-major image). X is read from HBM once.
+//
+// Warp roles (256 threads): warps 0-3 epilogue (TMEM lane quadrant == warp id; lanes 0-15 of each
+// quadrant carry the 64 particle rows of an M=64 accumulator), warp 4 MN-ring TMA producer,
+// warp 5 K-ring TMA producer, warp 6 stages (y, live) pairs of each tile, warp 7 allocates TMEM
+// and issues every MMA.
 //
 // Replaces: aten::mv / addmv_ and MvBackward of `X @ theta` (tests/test_mininf.py:11,
 // examples/minibatch.md:33) plus the element-wise Normal / Bernoulli / Poisson log_prob chains
 // and their autograd twins (mininf/core.py:241), for all S particles in one pass.
 #pragma once
+
+#include <cuda.h>
 
 #include "common.cuh"
 #include "dense_simt.cuh"
@@ -34,31 +64,36 @@ namespace mnf {
 namespace tc {
 
 constexpr int kP = 64;          // features handled by this instantiation
-constexpr int kNS = 64;         // particle slots (MMA N); S <= kNS, spare slots carry theta = 0
-constexpr int kTileM = 128;     // rows per tile
-constexpr int kStages = 4;      // X ring depth
+constexpr int kNS = 64;         // particle slots (MMA M); S <= kNS, spare slots carry theta = 0
+constexpr int kTileM = 128;     // rows per tile (MMA N of the eta product, K of the gradient product)
+constexpr int kKStages = 2;     // K-major image ring (live until the eta product retires)
+constexpr int kMnStages = 4;    // MN-major image ring (live until the gradient product retires)
+constexpr int kFlush = 8;       // tiles accumulated in TMEM before the gradient tile is drained
 constexpr int kEpiWarps = 4;
-constexpr int kProdWarps = 8;   // two groups of four
-constexpr int kThreads = (kEpiWarps + kProdWarps + 1) * 32;
-constexpr int kMmaWarp = kEpiWarps + kProdWarps;
+constexpr int kWarpMnTma = 4, kWarpKTma = 5, kWarpY = 6, kMmaWarp = 7;
+constexpr int kThreads = 8 * 32;
 
-constexpr uint32_t kAtomBytes = kTileM * 128;                 // one K-atom of the X tile: 128 rows x 128 B
-constexpr uint32_t kXStageBytes = (kP / 32) * kAtomBytes;     // 32 KB
-constexpr uint32_t kRStageBytes = (kNS / 32) * kAtomBytes;    // 32 KB
-constexpr uint32_t kThetaAtomBytes = kNS * 128;               // 8 KB
-constexpr uint32_t kThetaBytes = (kP / 32) * kThetaAtomBytes; // 16 KB
+constexpr uint32_t kAtomBytes = kTileM * 128;                 // 128 rows x 128 B (32 fp32)
+constexpr uint32_t kXImageBytes = (kP / 32) * kAtomBytes;     // 32 KB per image
+constexpr uint32_t kYBytes = 2 * kTileM * 4;                  // interleaved (y, live) pairs per row
 
-constexpr uint32_t kOffX = 0;
-constexpr uint32_t kOffR = kOffX + kStages * kXStageBytes;
-constexpr uint32_t kOffTheta = kOffR + 2 * kRStageBytes;
-constexpr uint32_t kOffBar = kOffTheta + kThetaBytes;
-constexpr uint32_t kNumBars = 2 * kStages + 4 * 2 + 1;
-constexpr uint32_t kOffMisc = kOffBar + 8 * kNumBars;         // tmem address + per-particle params
-constexpr uint32_t kSmemBytes = kOffMisc + 16 + kNS * 16 + 1024 /* alignment slack */;
+constexpr uint32_t kOffK = 0;
+constexpr uint32_t kOffMN = kOffK + kKStages * kXImageBytes;
+constexpr uint32_t kOffY = kOffMN + kMnStages * kXImageBytes;
+constexpr uint32_t kOffBar = kOffY + kMnStages * kYBytes;
+constexpr uint32_t kNumBars = 2 * kKStages + 2 * kMnStages + 8;  // + eta_full, r_ready, g_full, g_empty (x2 each)
+constexpr uint32_t kOffMisc = kOffBar + 8 * kNumBars;         // tmem slot, counters, per-particle params
+constexpr uint32_t kOffGrad = kOffMisc + 64 + kNS * 16;         // drained gradient [kNS][kP + 1] fp32
+constexpr uint32_t kOffStat = kOffGrad + kNS * (kP + 1) * 4;    // per-particle statistic exchange [kNS]
+constexpr uint32_t kSmemBytes = kOffStat + kNS * 4 + 1024 /* alignment slack */;
+static_assert(kOffMisc % 16 == 0, "misc block alignment");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
-constexpr uint32_t kTmemCols = 256;   // eta0 [0,64) eta1 [64,128) G [128,192)
-constexpr uint32_t kColEta = 0;
-constexpr uint32_t kColG = 2 * kNS;
+// tensor memory map (512 columns allocated): two eta^T / R^T tiles, two gradient tiles, Theta
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColEta = 0;               // + b * kTileM
+constexpr uint32_t kColG = 2 * kTileM;        // + gb * kP
+constexpr uint32_t kColTheta = kColG + 2 * kP;
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -79,6 +114,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+      "@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -92,16 +135,28 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                            uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 2-D tiled TMA load: box (32 features x 128 rows) at (feature c0, row c1) -> shared memory
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
-// 32 lanes x 16 consecutive fp32 columns of TMEM -> 16 registers per thread
+// D[tmem] (+)= A[tmem] . B[smem descriptor given as two 32-bit words]
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns of TMEM <-> 16 registers per thread
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -110,27 +165,67 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tc_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+      "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+      "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+// 16 lanes x 32 columns spread over all 32 threads (measured mapping, tools/tmem_shape_probe.cu):
+// register 4g+j of thread t holds lane t/4 + 8*(j>>1), column 8g + 2*(t%4) + (j&1)
+__device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_st_16x256b_x4(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- descriptors (cute/arch/mma_sm100_desc.hpp, cute/atom/mma_traits_sm100.hpp) -------------
-// Shared-memory matrix descriptor, SWIZZLE_128B, version 1 (Blackwell):
+// Shared-memory matrix descriptor, version 1 (Blackwell):
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
-//   [46,48) version = 1 | [61,64) layout type (2 = SWIZZLE_128B)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   [46,48) version = 1 | [61,64) layout type (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout) {
   uint64_t d = 0;
   d |= (uint64_t)((addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
-}
-// K-major operand: rows of 128 B (32 fp32 of K), 8-row groups 1024 B apart (SBO); LBO unused.
-__device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr) { return smem_desc(addr, 16, 1024); }
-// MN-major operand: 32 fp32 of M/N contiguous (128 B), K rows 128 B apart, 8-row K groups 1024 B
-// apart (SBO), next 32-element M/N chunk one atom (128 rows x 128 B) further (LBO).
-__device__ __forceinline__ uint64_t desc_mnmajor(uint32_t addr) {
-  return smem_desc(addr, kAtomBytes, 1024);
 }
 // Instruction descriptor, kind::tf32, fp32 accumulate:
 //   [4,6) D format 1=F32 | [7,10) A format 2=TF32 | [10,13) B format 2=TF32 | [15] A MN-major
@@ -140,10 +235,6 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// Swizzle<3,4,3>: XOR the 16-byte chunk index (bits 4-6) with the 128-byte row index (bits 7-9).
-__device__ __forceinline__ uint32_t swz128(uint32_t byte_off) {
-  return byte_off ^ (((byte_off >> 7) & 7u) << 4);
-}
 // round-to-nearest (ties away) to TF32: the tensor core then only drops zero bits
 __device__ __forceinline__ uint32_t rn_tf32(float x) {
   return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
@@ -158,33 +249,54 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
                : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
 
-struct ParticleParam {
-  float icpt;
-  float scale;
-  float dscale;
+#ifdef MNF_TC_DEBUG
+// Debug builds only: per-role cycle counters kept in registers and flushed once per thread.
+__device__ float* g_tc_debug = nullptr;   // [16384 floats scratch][int64 cycle counters]
+#define TC_DECL() long long tc_cnt__[4] = {0, 0, 0, 0}; long long t0__ = clock64(); const long long tstart__ = t0__
+#define TC_T0() t0__ = clock64()
+#define TC_ACC(i) do { const long long n__ = clock64(); tc_cnt__[i] += n__ - t0__; t0__ = n__; } while (0)
+#define TC_FLUSH(slot0, n, cond) do { if (blockIdx.x == 0 && g_tc_debug && (cond)) { \
+    for (int i__ = 0; i__ < (n); ++i__) ((long long*)(g_tc_debug + 16384))[(slot0) + i__] = tc_cnt__[i__]; \
+    ((long long*)(g_tc_debug + 16384))[15] = clock64() - tstart__; } } while (0)
+#else
+#define TC_DECL() do {} while (0)
+#define TC_T0() do {} while (0)
+#define TC_ACC(i) do {} while (0)
+#define TC_FLUSH(slot0, n, cond) do {} while (0)
+#endif
+
+struct TileCounters {   // particle-independent sums over the live rows this CTA handled
+  float n_live;
   float pad;
+  double lgamma_sum;    // Poisson: sum lgamma(y + 1)
 };
 
 // partial layout per CTA: [S][ncol], ncol = 1 + kP + 2 (same as the SIMT variant)
 template <int FAMILY>
 __global__ void __launch_bounds__(kThreads, 1)
-dense_tc_kernel(mnf_dense_site_t site, const float* __restrict__ z, int S, int D,
+dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_mn,
+                mnf_dense_site_t site, const float* __restrict__ z, int S, int D,
                 float* __restrict__ partial, uint32_t* __restrict__ status) {
   extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operands need 1024-byte alignment
+  // swizzled operand images need 1024-byte alignment
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
-  const uint32_t sX = base + kOffX, sR = base + kOffR, sTheta = base + kOffTheta;
+  const uint32_t sK = base + kOffK, sMN = base + kOffMN, sY = base + kOffY;
   const uint32_t bars = base + kOffBar;
-  // barrier map
-  const uint32_t bXFull = bars, bXEmpty = bars + 8 * kStages;
-  const uint32_t bEtaFull = bars + 16 * kStages, bEtaEmpty = bEtaFull + 16;
-  const uint32_t bRFull = bEtaEmpty + 16, bREmpty = bRFull + 16;
-  const uint32_t bGFull = bREmpty + 16;
+  const uint32_t bKFull = bars, bKEmpty = bKFull + 8 * kKStages;
+  const uint32_t bMnFull = bKEmpty + 8 * kKStages, bMnEmpty = bMnFull + 8 * kMnStages;
+  const uint32_t bEtaFull = bMnEmpty + 8 * kMnStages, bRReady = bEtaFull + 16;
+  const uint32_t bGFull = bRReady + 16, bGEmpty = bGFull + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + kOffMisc);
-  ParticleParam* sPar = reinterpret_cast<ParticleParam*>(gbase + kOffMisc + 16);
+  TileCounters* counters = reinterpret_cast<TileCounters*>(gbase + kOffMisc + 16);
+  DenseParticle* sPar = reinterpret_cast<DenseParticle*>(gbase + kOffMisc + 64);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -195,17 +307,22 @@ dense_tc_kernel(mnf_dense_site_t site, const float* __restrict__ z, int S, int D
 
   // ---- one-time setup ----------------------------------------------------------------------
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) {
-      mbar_init(bXFull + 8 * i, 4);   // four producer warps of the owning group
-      mbar_init(bXEmpty + 8 * i, 1);  // tcgen05.commit
+    for (int i = 0; i < kKStages; ++i) {
+      mbar_init(bKFull + 8 * i, 1);    // arrive.expect_tx of the K-ring producer
+      mbar_init(bKEmpty + 8 * i, 1);   // tcgen05.commit after the eta product
+    }
+    for (int i = 0; i < kMnStages; ++i) {
+      mbar_init(bMnFull + 8 * i, 2);   // arrive.expect_tx of the MN-ring producer + the y warp
+      mbar_init(bMnEmpty + 8 * i, 1);  // tcgen05.commit after the gradient product
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bEtaFull + 8 * i, 1);
-      mbar_init(bEtaEmpty + 8 * i, kEpiWarps * 32);
-      mbar_init(bRFull + 8 * i, kEpiWarps * 32);
-      mbar_init(bREmpty + 8 * i, 1);
+      mbar_init(bRReady + 8 * i, kEpiWarps * 32);
+      mbar_init(bGFull + 8 * i, 1);
+      mbar_init(bGEmpty + 8 * i, kEpiWarps * 32);
     }
-    mbar_init(bGFull, 1);
+    counters->n_live = 0.f;
+    counters->lgamma_sum = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
@@ -213,254 +330,358 @@ dense_tc_kernel(mnf_dense_site_t site, const float* __restrict__ z, int S, int D
                      smem_u32(tmem_slot)), "n"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // Theta -> smem, K-major SWIZZLE_128B, rounded to TF32; spare particle slots are zero
-  for (int i = tid; i < kNS * kP; i += kThreads) {
-    const int s = i / kP, j = i % kP;
-    const float v = s < S ? z[(int64_t)s * D + site.theta_lat + j] : 0.0f;
-    const uint32_t off = (uint32_t)(j >> 5) * kThetaAtomBytes + swz128((uint32_t)s * 128u + (uint32_t)(j & 31) * 4u);
-    *reinterpret_cast<uint32_t*>(gbase + kOffTheta + off) = rn_tf32(v);
+  if (warp == kWarpMnTma && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_mn) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
   }
   for (int s = tid; s < kNS; s += kThreads) {
-    ParticleParam pp;
-    pp.icpt = 0.f; pp.scale = 1.f; pp.dscale = 0.f; pp.pad = 0.f;
+    DenseParticle dp;
+    dp.icpt = 0.f; dp.scale = 1.f; dp.dscale = 0.f;
     if (s < S) {
-      const DenseParticle dp = dense_particle(site, z + (int64_t)s * D);
-      pp.icpt = dp.icpt; pp.scale = dp.scale; pp.dscale = dp.dscale;
+      dp = dense_particle(site, z + (int64_t)s * D);
       if (FAMILY == MNF_NORMAL && !(dp.scale > 0.0f)) atomicOr(status, MNF_ST_BAD_PARAM);
     }
-    sPar[s] = pp;
+    sPar[s] = dp;
   }
-  fence_proxy_async();  // Theta was written through the generic proxy, tcgen05.mma reads it async
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp >= kEpiWarps && warp < kMmaWarp) {
-    // ================= producers: HBM -> registers -> TF32 round -> swizzled smem ============
-    const int group = (warp - kEpiWarps) >> 2;           // 0 or 1
-    const int gtid = ((warp - kEpiWarps) & 3) * 32 + lane;  // 0..127 within the group
-    const bool vec_ok = true;
-    (void)vec_ok;
-    for (int64_t k = group; k < my_tiles; k += 2) {
-      const int64_t tile = blockIdx.x + k * gridDim.x;
-      const int64_t row0 = tile * kTileM;
-      const int st = (int)(k % kStages);
-      const uint32_t use = (uint32_t)(k / kStages);
-      float4 v[16];
+  if (warp < kEpiWarps) {
+    // Theta -> TMEM as the A operand of the eta product: particle s on lane (s%16)+32*(s/16),
+    // feature j in column kColTheta + j, rounded to TF32. Spare particle slots are zero.
+    const int s = warp * 16 + lane;
+    const bool owner = lane < 16 && s < S;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int f = it * 128 + gtid;   // float4 index in the tile: 16 per row
-        const int r = f >> 4, c = f & 15;
-        const int64_t row = row0 + r;
-        if (row < site.n_rows) v[it] = ldg_stream(reinterpret_cast<const float4*>(site.X + row * site.ldx) + c);
-        else v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      mbar_wait(bXEmpty + 8 * st, (use & 1u) ^ 1u);
-      const uint32_t stage = sX + (uint32_t)st * kXStageBytes;
+    for (int ch = 0; ch < kP / 16; ++ch) {
+      uint32_t v[16];
 #pragma unroll
-      for (int it = 0; it < 16; ++it) {
-        const int f = it * 128 + gtid;
-        const uint32_t r = (uint32_t)(f >> 4), c = (uint32_t)(f & 15);
-        const uint32_t off = (c >> 3) * kAtomBytes + r * 128u + (((c & 7u) ^ (r & 7u)) << 4);
-        sts128(stage + off, rn_tf32(v[it].x), rn_tf32(v[it].y), rn_tf32(v[it].z), rn_tf32(v[it].w));
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bXFull + 8 * st);
+      for (int c = 0; c < 16; ++c)
+        v[c] = owner ? rn_tf32(z[(int64_t)s * D + site.theta_lat + ch * 16 + c]) : 0u;
+      tc_st16(tmem + lane_base + kColTheta + ch * 16, v);
     }
-  } else if (warp == kMmaWarp) {
-    // ================= MMA issuer (one elected lane) ==========================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_eta = idesc_tf32(kTileM, kNS, 0, 0);
-      constexpr uint32_t idesc_g = idesc_tf32(kP, kNS, 1, 1);
-      for (int64_t k = 0; k <= my_tiles; ++k) {
-        if (k < my_tiles) {
-          const int st = (int)(k % kStages);
-          const uint32_t b = (uint32_t)(k & 1);
-          mbar_wait(bXFull + 8 * st, (uint32_t)((k / kStages) & 1));
-          mbar_wait(bEtaEmpty + 8 * b, (uint32_t)(((k >> 1) & 1) ^ 1));
-          tc_fence_after();
-          const uint32_t xs = sX + (uint32_t)st * kXStageBytes;
+    tc_wait_st();
+    tc_fence_before();
+  }
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == kWarpMnTma) {
+    // ================= MN-major ring: TMA producer (one elected lane) =========================
+    if (elect_one()) {
+      for (int64_t k = 0; k < my_tiles; ++k) {
+        const int st = (int)(k % kMnStages);
+        const int row0 = (int)((blockIdx.x + k * gridDim.x) * kTileM);
+        mbar_wait(bMnEmpty + 8 * st, (uint32_t)(((k / kMnStages) & 1) ^ 1));
+        mbar_arrive_expect_tx(bMnFull + 8 * st, kXImageBytes);
 #pragma unroll
-          for (int a = 0; a < kP / 32; ++a) {
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              tc_mma_tf32(tmem + kColEta + b * kNS, desc_kmajor(xs + a * kAtomBytes + ks * 32),
-                          desc_kmajor(sTheta + a * kThetaAtomBytes + ks * 32), idesc_eta,
-                          (a | ks) != 0 ? 1u : 0u);
-            }
-          }
-          tc_commit(bEtaFull + 8 * b);
-        }
-        if (k >= 1) {
-          const int64_t kk = k - 1;
-          const int st = (int)(kk % kStages);
-          const uint32_t b = (uint32_t)(kk & 1);
-          mbar_wait(bRFull + 8 * b, (uint32_t)((kk >> 1) & 1));
-          tc_fence_after();
-          const uint32_t xs = sX + (uint32_t)st * kXStageBytes;
-          const uint32_t rs = sR + b * kRStageBytes;
-#pragma unroll
-          for (int ks = 0; ks < kTileM / 8; ++ks) {
-            tc_mma_tf32(tmem + kColG, desc_mnmajor(xs + ks * 1024), desc_mnmajor(rs + ks * 1024),
-                        idesc_g, (kk > 0 || ks > 0) ? 1u : 0u);
-          }
-          tc_commit(bXEmpty + 8 * st);
-          tc_commit(bREmpty + 8 * b);
-        }
+        for (int a = 0; a < kP / 32; ++a)
+          tma_load_2d(sMN + (uint32_t)st * kXImageBytes + a * kAtomBytes, &map_mn, a * 32, row0, bMnFull + 8 * st);
       }
-      tc_commit(bGFull);
     }
     __syncwarp();
-  } else {
-    // ================= epilogue warps: eta -> log-density, score R ============================
-    const int row_in_tile = tid;  // TMEM lane == tile row
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    float st0[kNS];  // Normal: sum r^2            | others: sum log-density
+  } else if (warp == kWarpKTma) {
+    // ================= K-major ring: TMA producer (one elected lane) ==========================
+    if (elect_one()) {
+      for (int64_t k = 0; k < my_tiles; ++k) {
+        const int st = (int)(k % kKStages);
+        const int row0 = (int)((blockIdx.x + k * gridDim.x) * kTileM);
+        mbar_wait(bKEmpty + 8 * st, (uint32_t)(((k / kKStages) & 1) ^ 1));
+        mbar_arrive_expect_tx(bKFull + 8 * st, kXImageBytes);
 #pragma unroll
-    for (int s = 0; s < kNS; ++s) st0[s] = 0.f;
-    float n_live = 0.f;
-    double lgam = 0.0;   // Poisson: sum lgamma(y+1) over live rows (particle independent)
-    bool bad_value = false;
-
-    // prefetch y / mask of the first tile
-    float y_next = 0.f; bool live_next = false;
-    {
-      const int64_t row = (int64_t)blockIdx.x * kTileM + row_in_tile;
-      live_next = row < site.n_rows && (site.mask == nullptr || site.mask[row] != 0);
-      if (live_next) y_next = __ldg(site.y + row);
+        for (int a = 0; a < kP / 32; ++a)
+          tma_load_2d(sK + (uint32_t)st * kXImageBytes + a * kAtomBytes, &map_k, a * 32, row0, bKFull + 8 * st);
+      }
     }
-    for (int64_t k = 0; k < my_tiles; ++k) {
-      const uint32_t b = (uint32_t)(k & 1);
-      const float y = y_next;
-      const bool live = live_next;
-      if (k + 1 < my_tiles) {
-        const int64_t row = (blockIdx.x + (k + 1) * gridDim.x) * kTileM + row_in_tile;
-        live_next = row < site.n_rows && (site.mask == nullptr || site.mask[row] != 0);
-        y_next = live_next ? __ldg(site.y + row) : 0.f;
-      }
-      if (live) {
-        n_live += 1.f;
-        if (y != y) bad_value = true;
-        if (FAMILY == MNF_POISSON) lgam += (double)lgammaf(y + 1.0f);
-      }
-      mbar_wait(bEtaFull + 8 * b, (uint32_t)((k >> 1) & 1));
-      tc_fence_after();
-      mbar_wait(bREmpty + 8 * b, (uint32_t)(((k >> 1) & 1) ^ 1));
-      const uint32_t rs = sR + b * kRStageBytes;
-      const uint32_t r = (uint32_t)row_in_tile;
-#pragma unroll
-      for (int ch = 0; ch < kNS / 16; ++ch) {
-        uint32_t v[16];
-        tc_ld16(tmem + lane_base + kColEta + b * kNS + ch * 16, v);
-        tc_wait_ld();
-        uint32_t out[16];
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const int s = ch * 16 + c;
-          const float eta = __uint_as_float(v[c]);
-          float score;
-          if (FAMILY == MNF_NORMAL) {
-            score = live ? y - eta : 0.f;          // unit-scale residual; 1/sigma^2 applied at the end
-            st0[s] = fmaf(score, score, st0[s]);
-          } else if (FAMILY == MNF_BERNOULLI_LOGITS) {
-            const float e = __expf(-fabsf(eta));
-            const float inv = __fdividef(1.0f, 1.0f + e);
-            const float sig = eta >= 0.f ? inv : e * inv;
-            const float lp = y * eta - (fmaxf(eta, 0.f) + log1pf(e));
-            score = live ? y - sig : 0.f;
-            st0[s] += live ? lp : 0.f;
-          } else {
-            const float rate = expf(eta);
-            score = live ? y - rate : 0.f;
-            st0[s] += live ? fmaf(y, eta, -rate) : 0.f;
-          }
-          out[c] = rn_tf32(score);
-        }
-        // R tile, MN-major SWIZZLE_128B: row r holds 32 particles per 128-byte line
-        const uint32_t half = (uint32_t)(ch >> 1) * kAtomBytes + r * 128u;
+    __syncwarp();
+  } else if (warp == kWarpY) {
+    // ================= y warp: (y, live) pairs of each tile, four rows per lane ===============
+    // Values of the next kMnStages tiles are kept in registers so their latency is off the path.
+    const bool y_vec = (reinterpret_cast<uintptr_t>(site.y) % 16 == 0) &&
+                       (site.mask == nullptr || reinterpret_cast<uintptr_t>(site.mask) % 4 == 0);
+    float4 yq[kMnStages];
+    uint32_t mq[kMnStages];
+    auto fetch = [&](int64_t k, float4& yraw, uint32_t& mraw) {
+      const int64_t row = (blockIdx.x + k * gridDim.x) * kTileM + lane * 4;
+      if (y_vec && row + 4 <= site.n_rows) {
+        yraw = __ldg(reinterpret_cast<const float4*>(site.y + row));
+        mraw = site.mask == nullptr ? 0x01010101u : __ldg(reinterpret_cast<const uint32_t*>(site.mask + row));
+      } else {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        mraw = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const uint32_t c16 = (uint32_t)((ch & 1) * 4 + q);
-          sts128(rs + half + ((c16 ^ (r & 7u)) << 4), out[4 * q], out[4 * q + 1], out[4 * q + 2], out[4 * q + 3]);
+          if (row + q < site.n_rows) {
+            t[q] = __ldg(site.y + row + q);
+            const uint32_t m = site.mask == nullptr ? 1u : (uint32_t)__ldg(site.mask + row + q);
+            mraw |= (m != 0 ? 1u : 0u) << (8 * q);
+          }
         }
+        yraw = make_float4(t[0], t[1], t[2], t[3]);
       }
-      tc_fence_before();
-      mbar_arrive(bEtaEmpty + 8 * b);
-      fence_proxy_async();
-      mbar_arrive(bRFull + 8 * b);
-    }
-
-    // ---- CTA-level reduction of the per-particle statistics and the gradient read-out -------
-    mbar_wait(bGFull, 0);
-    tc_fence_after();
-    // every MMA has retired: X stage 0 is free to serve as reduction scratch [128][kNS+1]
-    float* scratch = reinterpret_cast<float*>(gbase + kOffX);
-    const int ncol = 1 + kP + 2;
-    float* out = partial + (size_t)blockIdx.x * S * ncol;
-    __shared__ float s_nlive[kEpiWarps];
-    __shared__ double s_lgam[kEpiWarps];
-    {
-      const float nl = warp_sum(n_live);
-      const double lg = warp_sum(lgam);
-      if (lane == 0) { s_nlive[warp] = nl; s_lgam[warp] = lg; }
-    }
-    // pass 1: st0
+    };
 #pragma unroll
-    for (int s = 0; s < kNS; ++s) scratch[tid * (kNS + 1) + s] = st0[s];
-    epi_bar_sync();
-    float tot0 = 0.f;
-    const float tot1 = 0.f;  // intercept gradient: intercepts are routed to the fp32 kernel for now
-    if (tid < kNS) for (int rr = 0; rr < kTileM; ++rr) tot0 += scratch[rr * (kNS + 1) + tid];
-    const float cnt = s_nlive[0] + s_nlive[1] + s_nlive[2] + s_nlive[3];
-    const double lgsum = s_lgam[0] + s_lgam[1] + s_lgam[2] + s_lgam[3];
-    if (tid < S) {
-      const int s = tid;
-      const ParticleParam pp = sPar[s];
-      float lp, dicpt, dscale = 0.f;
-      if (FAMILY == MNF_NORMAL) {
-        const float inv = 1.0f / pp.scale, iv = inv * inv;
-        lp = -0.5f * iv * tot0 - cnt * (logf(pp.scale) + kLogSqrt2Pi);
-        dicpt = iv * tot1;
-        dscale = (tot0 * iv * inv - cnt * inv) * pp.dscale;
-      } else if (FAMILY == MNF_BERNOULLI_LOGITS) {
-        lp = tot0;
-        dicpt = tot1;
-      } else {
-        lp = tot0 - (float)lgsum;
-        dicpt = tot1;
-      }
-      out[s * ncol + 0] = lp;
-      out[s * ncol + 1 + kP] = dicpt;
-      out[s * ncol + 2 + kP] = dscale;
+    for (int i = 0; i < kMnStages; ++i) {
+      yq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      mq[i] = 0;
+      if (i < my_tiles) fetch(i, yq[i], mq[i]);
     }
-    // G: M = kP = 64 accumulator layout puts feature j on TMEM lane (j % 16) + 32 * (j / 16)
-    // (cute tmem_frg_1sm, M_MMA == 64), i.e. lanes 0-15 of each epilogue warp's quadrant.
-    {
-      const int j = warp * 16 + lane;
+    bool bad_value = false;
+    for (int64_t k0 = 0; k0 < my_tiles; k0 += kMnStages) {
 #pragma unroll
-      for (int ch = 0; ch < kNS / 16; ++ch) {
-        uint32_t v[16];
-        tc_ld16(tmem + lane_base + kColG + ch * 16, v);
-        tc_wait_ld();
-        if (lane < 16) {
+      for (int i = 0; i < kMnStages; ++i) {
+        const int64_t k = k0 + i;
+        if (k < my_tiles) {
+          mbar_wait(bMnEmpty + 8 * i, (uint32_t)(((k / kMnStages) & 1) ^ 1));
+          const float yr[4] = {yq[i].x, yq[i].y, yq[i].z, yq[i].w};
+          float yv[4], lv[4];
+          float live_cnt = 0.f;
+          double lgam = 0.0;
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const int s = ch * 16 + c;
-            if (s < S) {
-              float g = __uint_as_float(v[c]);
-              if (FAMILY == MNF_NORMAL) {
-                const float inv = 1.0f / sPar[s].scale;
-                g *= inv * inv;
-              }
-              out[s * ncol + 1 + j] = g;
+          for (int q = 0; q < 4; ++q) {
+            const bool live = ((mq[i] >> (8 * q)) & 0xFFu) != 0;
+            yv[q] = live ? yr[q] : 0.f;
+            lv[q] = live ? 1.f : 0.f;
+            if (live) {
+              live_cnt += 1.f;
+              if (yr[q] != yr[q]) bad_value = true;
+              if (FAMILY == MNF_POISSON) lgam += (double)lgammaf(yr[q] + 1.0f);
             }
           }
+          const uint32_t dst = sY + (uint32_t)i * kYBytes + lane * 32;
+          sts128(dst, __float_as_uint(yv[0]), __float_as_uint(lv[0]), __float_as_uint(yv[1]), __float_as_uint(lv[1]));
+          sts128(dst + 16, __float_as_uint(yv[2]), __float_as_uint(lv[2]), __float_as_uint(yv[3]), __float_as_uint(lv[3]));
+          // particle-independent tile sums; ordered before the consumers by the mn_full barrier chain
+          live_cnt = warp_sum(live_cnt);
+          if (FAMILY == MNF_POISSON) lgam = warp_sum(lgam);
+          if (lane == 0) {
+            atomicAdd(&counters->n_live, live_cnt);
+            if (FAMILY == MNF_POISSON) atomicAdd(&counters->lgamma_sum, lgam);
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bMnFull + 8 * i);
+          if (k + kMnStages < my_tiles) fetch(k + kMnStages, yq[i], mq[i]);
         }
       }
     }
     if (bad_value) atomicOr(status, MNF_ST_BAD_VALUE);
+  } else if (warp == kMmaWarp) {
+    // ================= MMA issuer: warp-uniform loop, one elected lane issues ================
+    constexpr uint32_t idesc_eta = idesc_tf32(kNS, kTileM, 0, 0);   // M=64 N=128, B K-major
+    constexpr uint32_t idesc_g = idesc_tf32(kNS, kP, 0, 1);         // M=64 N=64,  B MN-major
+    // descriptor words that do not depend on the stage
+    const uint64_t dK = smem_desc(sK, 16, 1024, 2);                 // K-major SWIZZLE_128B
+    const uint64_t dMN = smem_desc(sMN, kAtomBytes, 512, 1);        // MN-major SWIZZLE_128B_BASE32B
+    const uint32_t dK_lo = (uint32_t)dK, dK_hi = (uint32_t)(dK >> 32);
+    const uint32_t dMN_lo = (uint32_t)dMN, dMN_hi = (uint32_t)(dMN >> 32);
+    TC_DECL();
+    for (int64_t k = 0; k <= my_tiles; ++k) {
+      TC_T0();
+      if (k < my_tiles) {
+        const int kst = (int)(k % kKStages), mst = (int)(k % kMnStages);
+        const uint32_t b = (uint32_t)(k & 1);
+        mbar_wait(bKFull + 8 * kst, (uint32_t)((k / kKStages) & 1));
+        // the MN-major stage carries the (y, live) pairs the epilogue of this tile will read
+        mbar_wait(bMnFull + 8 * mst, (uint32_t)((k / kMnStages) & 1));
+        TC_ACC(0);   // mma: wait operands
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t lo = dK_lo + (uint32_t)kst * (kXImageBytes >> 4);
+          const uint32_t d = tmem + kColEta + b * kTileM;
+#pragma unroll
+          for (int a = 0; a < kP / 32; ++a) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              tc_mma_ts(d, tmem + kColTheta + (a * 4 + ks) * 8,
+                        lo + ((a * kAtomBytes + ks * 32) >> 4), dK_hi, idesc_eta, (a | ks) != 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(bEtaFull + 8 * b);
+          tc_commit(bKEmpty + 8 * kst);
+        }
+        __syncwarp();
+        TC_ACC(1);   // mma: issue eta
+      }
+      if (k >= 1) {
+        const int64_t kk = k - 1;
+        const int mst = (int)(kk % kMnStages);
+        const uint32_t b = (uint32_t)(kk & 1);
+        const int64_t grp = kk / kFlush;
+        const uint32_t gb = (uint32_t)(grp & 1);
+        const bool first = (kk % kFlush) == 0;
+        const bool last = (kk % kFlush) == kFlush - 1 || kk == my_tiles - 1;
+        mbar_wait(bRReady + 8 * b, (uint32_t)((kk >> 1) & 1));
+        TC_ACC(2);   // mma: wait r_ready
+        if (first) mbar_wait(bGEmpty + 8 * gb, (uint32_t)(((grp >> 1) & 1) ^ 1));
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t lo = dMN_lo + (uint32_t)mst * (kXImageBytes >> 4);
+          const uint32_t d = tmem + kColG + gb * kP;
+          const uint32_t a0 = tmem + kColEta + b * kTileM;
+#pragma unroll
+          for (int ks = 0; ks < kTileM / 8; ++ks) {
+            tc_mma_ts(d, a0 + ks * 8, lo + ks * 64, dMN_hi, idesc_g, (!first || ks > 0) ? 1u : 0u);
+          }
+          tc_commit(bMnEmpty + 8 * mst);
+          if (last) tc_commit(bGFull + 8 * gb);
+        }
+        __syncwarp();
+        TC_ACC(3);   // mma: issue G
+      }
+    }
+    TC_FLUSH(4, 4, lane == 0);
+  } else {
+    // ================= epilogue warps: thread (warp, lane < 16) owns particle 16*warp + lane ===
+    const int s = warp * 16 + lane;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // Statistics: with the 16x256b access shape thread t works on particles 16*warp + t/4 (A) and
+    // + 8 (B), columns 8g + 2*(t%4) + {0,1} of every 8-column group.
+    double stA_total = 0.0, stB_total = 0.0;  // Normal: sum r^2 | others: sum log-density (w/o lgamma)
+    // drained gradient tiles live in shared memory, one padded row per particle (conflict-free)
+    float* grad_row = reinterpret_cast<float*>(gbase + kOffGrad) + (size_t)(lane < 16 ? s : 0) * (kP + 1);
+    if (lane < 16)
+      for (int j = 0; j < kP; ++j) grad_row[j] = 0.f;
+    int64_t n_drained = 0;
+
+    auto drain = [&]() {
+      const int64_t grp = n_drained;
+      const uint32_t gb = (uint32_t)(grp & 1);
+      mbar_wait(bGFull + 8 * gb, (uint32_t)((grp >> 1) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < kP / 32; ++ch) {
+        uint32_t v[32];
+        tc_ld32(tmem + lane_base + kColG + gb * kP + ch * 32, v);
+        tc_wait_ld();
+        if (lane < 16) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) grad_row[ch * 32 + c] += __uint_as_float(v[c]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bGEmpty + 8 * gb);
+      ++n_drained;
+    };
+
+    // one (row, particle) point: score for the gradient product and the running statistic
+    auto point = [&](uint32_t& cell, float y, float live, float& stat) {
+      const float eta = __uint_as_float(cell);
+      float score;
+      if (FAMILY == MNF_NORMAL) {
+        score = fmaf(-live, eta, y);             // live * (y - eta); 1/sigma^2 applied at the end
+        stat = fmaf(score, score, stat);
+      } else if (FAMILY == MNF_BERNOULLI_LOGITS) {
+        const float e = __expf(-fabsf(eta));
+        const float inv = __fdividef(1.0f, 1.0f + e);
+        const float sig = eta >= 0.f ? inv : e * inv;
+        score = live * (y - sig);
+        stat += live * (y * eta - (fmaxf(eta, 0.f) + log1pf(e)));
+      } else {
+        const float rate = expf(eta);
+        score = live * (y - rate);
+        stat += live * fmaf(y, eta, -rate);
+      }
+      cell = rn_tf32(score);
+    };
+    // 32 columns (tile rows): thread t touches rows 32ch + 8g + 2(t%4) + {0,1}; their (y, live)
+    // pairs are one 16-byte shared-memory word
+    auto process = [&](uint32_t (&v)[16], const float4* yl, int ch, float& sa, float& sb) {
+      float4 w[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) w[g] = yl[16 * ch + 4 * g + (lane & 3)];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        point(v[4 * g + 0], w[g].x, w[g].y, sa);
+        point(v[4 * g + 1], w[g].z, w[g].w, sa);
+        point(v[4 * g + 2], w[g].x, w[g].y, sb);
+        point(v[4 * g + 3], w[g].z, w[g].w, sb);
+      }
+    };
+
+    TC_DECL();
+    for (int64_t k = 0; k < my_tiles; ++k) {
+      TC_T0();
+      const uint32_t b = (uint32_t)(k & 1);
+      const float4* yl = reinterpret_cast<const float4*>(gbase + kOffY + (size_t)(k % kMnStages) * kYBytes);
+      // the gradient group that ended two tiles ago has been issued (its R tile was handed over
+      // two iterations back), so waiting for its commit cannot deadlock
+      if (k >= 2 && ((k - 2) % kFlush) == kFlush - 1) drain();
+      mbar_wait(bEtaFull + 8 * b, (uint32_t)((k >> 1) & 1));
+      TC_ACC(0);   // epi: wait eta_full (+ drain)
+      tc_fence_after();
+      const uint32_t t_eta = tmem + lane_base + kColEta + b * kTileM;
+      // software pipeline over four 32-column chunks: the next chunk's tcgen05.ld is in flight
+      // while the current one is processed; R^T replaces eta^T in place (A operand of the G product)
+      float sa = 0.f, sb = 0.f;
+      uint32_t va[16], vb[16];
+      tc_ld_16x256b_x4(t_eta, va);
+      tc_wait_ld();
+      tc_ld_16x256b_x4(t_eta + 32, vb);
+      process(va, yl, 0, sa, sb);
+      tc_st_16x256b_x4(t_eta, va);
+      tc_wait_ld();
+      tc_ld_16x256b_x4(t_eta + 64, va);
+      process(vb, yl, 1, sa, sb);
+      tc_st_16x256b_x4(t_eta + 32, vb);
+      tc_wait_ld();
+      tc_ld_16x256b_x4(t_eta + 96, vb);
+      process(va, yl, 2, sa, sb);
+      tc_st_16x256b_x4(t_eta + 64, va);
+      tc_wait_ld();
+      process(vb, yl, 3, sa, sb);
+      tc_st_16x256b_x4(t_eta + 96, vb);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(bRReady + 8 * b);
+      stA_total += (double)sa;
+      stB_total += (double)sb;
+      TC_ACC(1);   // epi: compute
+    }
+    TC_FLUSH(8, 2, tid == 0);
+    // drain the gradient groups still in tensor memory (at most the last two)
+    {
+      const int64_t n_grp = (my_tiles + kFlush - 1) / kFlush;
+      while (n_drained < n_grp) drain();
+    }
+    // the four threads t%4 = 0..3 of a quad hold partial sums of the same two particles
+    stA_total += __shfl_xor_sync(0xffffffffu, stA_total, 1);
+    stA_total += __shfl_xor_sync(0xffffffffu, stA_total, 2);
+    stB_total += __shfl_xor_sync(0xffffffffu, stB_total, 1);
+    stB_total += __shfl_xor_sync(0xffffffffu, stB_total, 2);
+    float* s_stat = reinterpret_cast<float*>(gbase + kOffStat);
+    if ((lane & 3) == 0) {
+      s_stat[warp * 16 + (lane >> 2)] = (float)stA_total;
+      s_stat[warp * 16 + (lane >> 2) + 8] = (float)stB_total;
+    }
+    __syncwarp();
+    const float st0 = lane < 16 ? s_stat[s] : 0.f;
+
+    // ---- per-particle results: this thread is the only owner of particle s --------------------
+    if (lane < 16 && s < S) {
+      const int ncol = 1 + kP + 2;
+      float* out = partial + ((size_t)blockIdx.x * S + s) * ncol;
+      const DenseParticle pp = sPar[s];
+      const float cnt = *reinterpret_cast<volatile float*>(&counters->n_live);
+      const double lgsum = *reinterpret_cast<volatile double*>(&counters->lgamma_sum);
+      float lp, gscale = 1.0f, dscale = 0.f;
+      if (FAMILY == MNF_NORMAL) {
+        const float inv = 1.0f / pp.scale, iv = inv * inv;
+        lp = -0.5f * iv * st0 - cnt * (logf(pp.scale) + kLogSqrt2Pi);
+        dscale = (st0 * iv * inv - cnt * inv) * pp.dscale;
+        gscale = iv;
+      } else if (FAMILY == MNF_BERNOULLI_LOGITS) {
+        lp = st0;
+      } else {
+        lp = st0 - (float)lgsum;
+      }
+      out[0] = lp;
+#pragma unroll
+      for (int j = 0; j < kP; ++j) out[1 + j] = grad_row[j] * gscale;
+      out[1 + kP] = 0.f;      // intercept gradient: intercepts are routed to the fp32 kernel
+      out[2 + kP] = dscale;
+    }
     tc_fence_before();
   }
 
