@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MNF_ABI_VERSION 3
+#define MNF_ABI_VERSION 4
 
 /* error codes */
 #define MNF_OK 0
@@ -63,8 +63,8 @@ extern "C" {
 
 /*
  * One distribution parameter as a scalar link:  value_i = T(A_i + B_i * x_i)  with
- *   A_i = a_lat < 0 ? a_const : z[s][a_lat + a_stride * i]
- *   B_i = b_lat < 0 ? b_const : z[s][b_lat + b_stride * i]
+ *   A_i = a_const + (a_lat < 0 ? 0 : z[s][a_lat + a_stride * i])
+ *   B_i = b_const + (b_lat < 0 ? 0 : z[s][b_lat + b_stride * i])
  *   x_i = x == NULL ? 1       : x[x_stride * i]
  * This closed form covers the user link code of SURVEY §8a row a10 short of matrix products:
  * constants, data tensors, a latent itself (prior sites), `c + d*x`, `exp(a + b*x)`.

@@ -241,8 +241,8 @@ struct LinkVal {
 };
 
 __device__ __forceinline__ LinkVal eval_link(const mnf_link_t& L, const float* zs, int64_t i) {
-  const float A = L.a_lat < 0 ? L.a_const : zs[L.a_lat + (int64_t)L.a_stride * i];
-  const float B = L.b_lat < 0 ? L.b_const : zs[L.b_lat + (int64_t)L.b_stride * i];
+  const float A = L.a_const + (L.a_lat < 0 ? 0.0f : zs[L.a_lat + (int64_t)L.a_stride * i]);
+  const float B = L.b_const + (L.b_lat < 0 ? 0.0f : zs[L.b_lat + (int64_t)L.b_stride * i]);
   const float x = L.x == nullptr ? 1.0f : __ldg(L.x + (int64_t)L.x_stride * i);
   const float u = fmaf(B, x, A);
   LinkVal o;

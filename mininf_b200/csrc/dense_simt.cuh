@@ -25,7 +25,7 @@ struct DenseParticle {
 __device__ __forceinline__ DenseParticle dense_particle(const mnf_dense_site_t& site,
                                                         const float* zs) {
   DenseParticle o;
-  o.icpt = site.icpt_lat >= 0 ? zs[site.icpt_lat] : site.icpt_const;
+  o.icpt = site.icpt_const + (site.icpt_lat >= 0 ? zs[site.icpt_lat] : 0.0f);
   o.scale = 1.0f;
   o.dscale = 0.0f;
   if (site.family == MNF_NORMAL) {

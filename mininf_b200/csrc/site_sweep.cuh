@@ -88,8 +88,8 @@ site_sweep_kernel(SweepArgs<NSITES> args, const float* __restrict__ z, int S, in
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         const mnf_link_t& L = args.site[i].param[p];
-        A[i][p][q] = L.a_lat >= 0 ? zs[L.a_lat] : L.a_const;
-        B[i][p][q] = L.b_lat >= 0 ? zs[L.b_lat] : L.b_const;
+        A[i][p][q] = L.a_const + (L.a_lat >= 0 ? zs[L.a_lat] : 0.0f);
+        B[i][p][q] = L.b_const + (L.b_lat >= 0 ? zs[L.b_lat] : 0.0f);
       }
   }
   double acc[NC][Q];

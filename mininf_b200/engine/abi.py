@@ -11,7 +11,7 @@ from pathlib import Path
 
 from . import build as _build
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # families (include/mininf_b200.h)
 NORMAL, GAMMA, BETA, BERNOULLI_PROBS, BERNOULLI_LOGITS, POISSON = range(6)

@@ -1,0 +1,353 @@
+"""Lower a traced site table to the C-ABI tables and run ELBO steps on the CUDA engine.
+
+A :class:`Plan` is built once per (model, conditioned tensors, approximation structure, particle
+count) and then only enqueues kernels: ``mnf_rsample`` -> sweeps over the observed data
+(``mnf_dense_sweep`` / ``mnf_site_sweep`` / ``mnf_small_sites``) -> optional all-reduce of the
+[S][1+D] accumulator across ranks -> global (latent-valued) sites -> ``mnf_finalize``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+from torch import distributions as td
+
+from . import abi
+from .trace import Affine, Dense, LatentRef, LinkTensor, SiteRecord
+from ..util import is_masked
+
+BIG_SITE = 2048          # observed sites at least this long go through the fused site sweep
+
+_LATENT_FAMILIES = {td.Normal: abi.NORMAL, td.Gamma: abi.GAMMA, td.Beta: abi.BETA}
+
+
+def latent_parameters(dist: td.Distribution) -> Tuple[int, torch.Tensor, torch.Tensor]:
+    """Family id and the two constrained parameter tensors of an approximation factor."""
+    family = _LATENT_FAMILIES.get(type(dist))
+    if family is None:
+        raise NotImplementedError(
+            f"the CUDA engine supports Normal, Gamma and Beta approximations, not {type(dist)}")
+    if family == abi.NORMAL:
+        return family, dist.loc, dist.scale
+    if family == abi.GAMMA:
+        return family, dist.concentration, dist.rate
+    return family, dist.concentration1, dist.concentration0
+
+
+@dataclasses.dataclass
+class LatentSpec:
+    name: str
+    family: int
+    shape: torch.Size
+    numel: int
+    offset: int
+
+
+def _bytes_to_device(struct_array: Any, device: torch.device) -> torch.Tensor:
+    return torch.frombuffer(bytearray(bytes(struct_array)), dtype=torch.uint8).to(device)
+
+
+def _f32(tensor: torch.Tensor, device: torch.device) -> torch.Tensor:
+    if isinstance(tensor, LinkTensor):
+        tensor = tensor.unwrap()
+    if tensor.device != device:
+        raise ValueError(f"all tensors of an ELBO evaluation must live on {device}; found one on "
+                         f"{tensor.device}")
+    return tensor.detach().to(torch.float32).contiguous()
+
+
+class Plan:
+    """Everything one ELBO step needs, resolved to device pointers."""
+
+    def __init__(self, sites: Sequence[SiteRecord], latents: Sequence[LatentSpec],
+                 n_particles: int, device: torch.device, dense_mode: str = "auto",
+                 dry_run: bool = False) -> None:
+        """``dry_run`` lowers the site table without touching the GPU (host-logic tests)."""
+        if device.type != "cuda" and not dry_run:
+            raise RuntimeError("the mininf_b200 ELBO engine runs on CUDA tensors only; move the "
+                               "approximation parameters and the conditioned data to the GPU")
+        self.lib = abi.load()
+        self.device = device
+        self.S = int(n_particles)
+        self.latents = list(latents)
+        self.by_name = {spec.name: spec for spec in self.latents}
+        self.D = sum(spec.numel for spec in self.latents)
+        if self.S < 1 or self.D < 1:
+            raise ValueError("need at least one particle and one latent element")
+        self.dense_mode = dense_mode
+        self.keepalive: List[torch.Tensor] = []
+        self.all_normal = all(spec.family == abi.NORMAL for spec in self.latents)
+
+        S, D = self.S, self.D
+        f32 = dict(device=device, dtype=torch.float32)
+        self.P0 = torch.zeros(D, **f32)
+        self.P1 = torch.ones(D, **f32)
+        self.z = torch.empty(S, D, **f32)
+        self.noise = torch.empty(S, D, **f32)
+        self.noise_in = torch.empty(S, D, **f32)
+        self.acc = torch.empty(S, D + 1, device=device, dtype=torch.float64)
+        self.status = torch.zeros(1, device=device, dtype=torch.int32)
+        self.out = torch.empty(1 + 2 * D, **f32)
+        if dry_run:
+            self.workspace_bytes = 0
+            self.workspace = torch.empty(0, device=device, dtype=torch.uint8)
+        else:
+            with torch.cuda.device(device):
+                self.workspace_bytes = max(self.lib.workspace_bytes(S, D), 1 << 20)
+            self.workspace = torch.empty(self.workspace_bytes, device=device, dtype=torch.uint8)
+
+        table = (abi.Latent * len(self.latents))()
+        for i, spec in enumerate(self.latents):
+            table[i] = abi.Latent(family=spec.family, numel=spec.numel, offset=spec.offset, reserved=0,
+                                  p0=self.P0.data_ptr() + 4 * spec.offset,
+                                  p1=self.P1.data_ptr() + 4 * spec.offset)
+        self.latent_table = _bytes_to_device(table, device)
+
+        self.dense_sites: List[Tuple[abi.DenseSite, int]] = []
+        self.sweep_groups: List[Any] = []
+        small_observed: List[abi.Site] = []
+        small_global: List[abi.Site] = []
+        big: Dict[int, List[abi.Site]] = {}
+        for record in sites:
+            self._lower(record, small_observed, small_global, big)
+        for numel, group in big.items():
+            for start in range(0, len(group), abi.MAX_FUSED_SITES):
+                chunk = group[start:start + abi.MAX_FUSED_SITES]
+                array = (abi.Site * len(chunk))(*chunk)
+                self.sweep_groups.append(array)
+        self.small_observed = self._site_table(small_observed)
+        self.small_global = self._site_table(small_global)
+
+    # ------------------------------------------------------------------------------------------
+    # lowering
+    # ------------------------------------------------------------------------------------------
+    def _site_table(self, sites: List[abi.Site]) -> Optional[Tuple[torch.Tensor, int, int]]:
+        if not sites:
+            return None
+        array = (abi.Site * len(sites))(*sites)
+        return _bytes_to_device(array, self.device), len(sites), max(s.numel for s in sites)
+
+    def _latent_column(self, ref: LatentRef, numel: int, what: str) -> Tuple[int, int]:
+        """(column, stride) of a latent reference inside a site of ``numel`` elements."""
+        spec = self.by_name.get(ref.name)
+        if spec is None:
+            raise NotImplementedError(f"{what} depends on '{ref.name}', which the approximation "
+                                      "does not provide")
+        if ref.is_scalar:
+            return spec.offset + ref.index, 0
+        if spec.numel == 1:
+            return spec.offset, 0
+        if spec.numel != numel:
+            raise NotImplementedError(f"{what}: latent '{ref.name}' with {spec.numel} elements is "
+                                      f"not aligned with a site of {numel} elements")
+        return spec.offset, 1
+
+    def _link(self, param: Any, shape: torch.Size, what: str) -> abi.Link:
+        """A distribution parameter (already broadcast by the distribution) as a scalar link."""
+        numel = shape.numel()
+        if isinstance(param, LinkTensor):
+            expr = param._expr
+            if not isinstance(expr, Affine):
+                raise NotImplementedError(
+                    f"{what} is not a supported link of the latent variables (supported: a latent "
+                    "itself, constants, data, `c + d*x`, `exp(a + b*x)`, `X @ theta`)")
+            link = abi.Link(a_const=expr.a_const, b_const=expr.b_const, a_lat=-1, b_lat=-1,
+                            a_stride=0, b_stride=0, x=None, x_stride=0,
+                            transform=abi.T_EXP if expr.transform == "exp" else abi.T_ID)
+            if expr.a_lat is not None:
+                link.a_lat, link.a_stride = self._latent_column(expr.a_lat, numel, what)
+            if expr.b_lat is not None:
+                link.b_lat, link.b_stride = self._latent_column(expr.b_lat, numel, what)
+            if expr.x is not None:
+                x = _f32(expr.x.expand(shape), self.device).reshape(-1)
+                self.keepalive.append(x)
+                link.x, link.x_stride = x.data_ptr(), 1
+            elif expr.has_x_term:
+                raise NotImplementedError(f"{what}: slope term without a covariate")
+            return link
+        tensor = torch.as_tensor(param)
+        if tensor.numel() == 1 or bool((tensor == tensor.reshape(-1)[0]).all()):
+            return abi.const_link(float(tensor.reshape(-1)[0]))
+        data = _f32(tensor.expand(shape), self.device).reshape(-1)
+        self.keepalive.append(data)
+        link = abi.const_link(0.0)
+        link.b_const, link.x, link.x_stride = 1.0, data.data_ptr(), 1
+        return link
+
+    def _lower(self, record: SiteRecord, small_observed: List[abi.Site],
+               small_global: List[abi.Site], big: Dict[int, List[abi.Site]]) -> None:
+        dist, value, name = record.distribution, record.value, record.name
+        what = f"site '{name}'"
+        # family and raw parameters
+        if isinstance(dist, td.Normal):
+            family, params = abi.NORMAL, (dist.loc, dist.scale)
+        elif isinstance(dist, td.Gamma):
+            family, params = abi.GAMMA, (dist.concentration, dist.rate)
+        elif isinstance(dist, td.Beta):
+            family, params = abi.BETA, (dist.concentration1, dist.concentration0)
+        elif isinstance(dist, td.Bernoulli):
+            if "logits" in dist.__dict__:
+                family, params = abi.BERNOULLI_LOGITS, (dist.logits,)
+            else:
+                family, params = abi.BERNOULLI_PROBS, (dist.probs,)
+        elif isinstance(dist, td.Poisson):
+            family, params = abi.POISSON, (dist.rate,)
+        else:
+            raise NotImplementedError(f"{what}: {type(dist).__name__} has no CUDA log-density "
+                                      "(supported: Normal, Gamma, Beta, Bernoulli, Poisson)")
+        if dist.event_shape:
+            raise NotImplementedError(f"{what}: event-shaped distributions are not supported")
+
+        # value: a latent itself (prior site) or observed data (possibly masked)
+        mask = None
+        value_lat = -1
+        if isinstance(value, LinkTensor):
+            expr = value._expr
+            if not (isinstance(expr, Affine) and expr.is_pure_latent):
+                raise NotImplementedError(f"{what}: its value is a function of latent variables")
+            shape, numel, data_ptr = value.shape, value.numel(), None
+            value_lat, stride = self._latent_column(expr.a_lat, numel, what)
+            if stride == 0 and numel != 1:
+                raise NotImplementedError(f"{what}: a scalar latent broadcast over the site")
+        else:
+            if is_masked(value):
+                mask = value.get_mask().contiguous()
+                if mask.device != self.device:
+                    raise ValueError(f"{what}: mask lives on {mask.device}, expected {self.device}")
+                self.keepalive.append(mask)
+                value = value.get_data()
+            data = _f32(value, self.device)
+            self.keepalive.append(data)
+            shape, numel, data_ptr = data.shape, data.numel(), data.data_ptr()
+        if numel == 0:
+            return
+
+        # dense linear predictor in the first parameter?
+        first = params[0]
+        if isinstance(first, LinkTensor) and isinstance(first._expr, Dense):
+            self._lower_dense(record, family, params, data_ptr, mask, numel, what)
+            return
+
+        site = abi.Site(family=family, value_lat=value_lat, value=data_ptr,
+                        mask=mask.data_ptr() if mask is not None else None, numel=numel,
+                        scale=float(record.scale))
+        site.param[0] = self._link(params[0], shape, what)
+        site.param[1] = self._link(params[1], shape, what) if len(params) > 1 else abi.const_link(1.0)
+        scalar_links = all(not ((link.a_lat >= 0 and link.a_stride) or (link.b_lat >= 0 and link.b_stride))
+                           for link in (site.param[0], site.param[1]))
+        if value_lat >= 0:
+            small_global.append(site)
+        elif numel >= BIG_SITE and scalar_links:
+            big.setdefault(numel, []).append(site)
+        else:
+            small_observed.append(site)
+
+    def _lower_dense(self, record: SiteRecord, family: int, params: Tuple[Any, ...],
+                     data_ptr: Optional[int], mask: Optional[torch.Tensor], numel: int,
+                     what: str) -> None:
+        expr: Dense = params[0]._expr
+        if data_ptr is None:
+            raise NotImplementedError(f"{what}: a dense-link site must be observed")
+        if family == abi.NORMAL and expr.transform == "id":
+            dense_family = abi.NORMAL
+        elif family == abi.BERNOULLI_LOGITS and expr.transform == "id":
+            dense_family = abi.BERNOULLI_LOGITS
+        elif family == abi.POISSON and expr.transform == "exp":
+            dense_family = abi.POISSON
+        else:
+            raise NotImplementedError(f"{what}: dense links are supported for Normal(loc=X@theta), "
+                                      "Bernoulli(logits=X@theta) and Poisson(rate=exp(X@theta))")
+        X = _f32(expr.X, self.device)
+        self.keepalive.append(X)
+        n, p = X.shape
+        if n != numel:
+            raise NotImplementedError(f"{what}: X has {n} rows but the site has {numel} elements")
+        theta = self.by_name.get(expr.theta)
+        if theta is None or theta.numel != p:
+            raise NotImplementedError(f"{what}: coefficient vector '{expr.theta}' does not match X")
+        icpt_lat = -1
+        if expr.icpt_lat is not None:
+            icpt_lat, _ = self._latent_column(expr.icpt_lat, 1, what)
+        scale_link = abi.const_link(1.0)
+        if dense_family == abi.NORMAL:
+            scale_link = self._link(params[1], torch.Size([numel]), what)
+            if scale_link.x:
+                raise NotImplementedError(f"{what}: per-observation scales are not supported for "
+                                          "dense-link sites")
+            if scale_link.b_lat >= 0 or scale_link.a_stride:
+                raise NotImplementedError(f"{what}: the scale must be a constant or a scalar latent")
+        site = abi.DenseSite(family=dense_family, p=p, n_rows=n, ldx=X.stride(0), X=X.data_ptr(),
+                             y=data_ptr, mask=mask.data_ptr() if mask is not None else None,
+                             theta_lat=theta.offset, icpt_lat=icpt_lat, icpt_const=expr.icpt_const,
+                             reserved=0, scale=scale_link, weight=float(record.scale))
+        has_icpt = icpt_lat >= 0 or expr.icpt_const != 0.0
+        tf32_ok = p == 64 and self.S <= 64 and not has_icpt and X.data_ptr() % 16 == 0 and \
+            X.stride(0) % 4 == 0 and n < 2 ** 31
+        if self.dense_mode == "tf32" and not tf32_ok:
+            raise NotImplementedError(f"{what}: the tcgen05 TF32 kernel needs p == 64, at most 64 "
+                                      "particles, no intercept and 16-byte aligned rows")
+        mode = abi.DENSE_TF32 if (self.dense_mode in ("auto", "tf32") and tf32_ok) else abi.DENSE_FP32
+        self.dense_sites.append((site, mode))
+
+    # ------------------------------------------------------------------------------------------
+    # execution
+    # ------------------------------------------------------------------------------------------
+    @property
+    def gpu_launches_per_step(self) -> int:
+        """Kernels of this library launched by one :meth:`step` (sweeps come with a reduction)."""
+        count = 2  # rsample + finalize
+        count += 2 * (len(self.dense_sites) + len(self.sweep_groups))
+        count += (self.small_observed is not None) + (self.small_global is not None)
+        return count
+
+    def step(self, noise: Optional[torch.Tensor], seed: int, offset: int, with_entropy: bool = True,
+             reduce_fn: Optional[Callable[[torch.Tensor], None]] = None) -> torch.Tensor:
+        """Enqueue one ELBO evaluation on the current stream; returns the [1 + 2D] output buffer
+        (loss, d loss / d p0, d loss / d p1). Parameters must already be in ``P0`` / ``P1``."""
+        lib, S, D = self.lib, self.S, self.D
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        status = self.status.data_ptr()
+        noise_ptr = None
+        if noise is not None:
+            self.noise_in.copy_(noise.reshape(S, D))
+            noise_ptr = self.noise_in.data_ptr()
+        elif not self.all_normal:
+            raise RuntimeError("Gamma / Beta approximations need host-provided noise")
+        lib.call("mnf_rsample", self.latent_table.data_ptr(), len(self.latents), S, D, noise_ptr,
+                 seed, offset, self.z.data_ptr(), self.noise.data_ptr(), self.acc.data_ptr(), status,
+                 stream)
+        for site, mode in self.dense_sites:
+            lib.call("mnf_dense_sweep", C.byref(site), mode, self.z.data_ptr(), S, D,
+                     self.acc.data_ptr(), self.workspace.data_ptr(), self.workspace_bytes, status,
+                     stream)
+        for group in self.sweep_groups:
+            lib.call("mnf_site_sweep", group, len(group), self.z.data_ptr(), S, D,
+                     self.acc.data_ptr(), self.workspace.data_ptr(), self.workspace_bytes, status,
+                     stream)
+        if self.small_observed is not None:
+            table, count, longest = self.small_observed
+            lib.call("mnf_small_sites", table.data_ptr(), count, longest, self.z.data_ptr(), S, D,
+                     self.acc.data_ptr(), status, stream)
+        if reduce_fn is not None:
+            reduce_fn(self.acc)   # observed sites are row shards: sum the partial accumulators
+        if self.small_global is not None:
+            table, count, longest = self.small_global
+            lib.call("mnf_small_sites", table.data_ptr(), count, longest, self.z.data_ptr(), S, D,
+                     self.acc.data_ptr(), status, stream)
+        lib.call("mnf_finalize", self.latent_table.data_ptr(), len(self.latents), S, D,
+                 self.z.data_ptr(), self.noise.data_ptr(), self.acc.data_ptr(), int(with_entropy),
+                 self.out.data_ptr(), status, stream)
+        return self.out
+
+
+def status_message(bits: int) -> str:
+    parts = []
+    if bits & abi.ST_BAD_PARAM:
+        parts.append("a distribution parameter left its constraint (e.g. a non-positive scale)")
+    if bits & abi.ST_BAD_VALUE:
+        parts.append("an observed value is not in the support of its distribution")
+    if bits & abi.ST_NONFINITE:
+        parts.append("the loss or a gradient is not finite")
+    return "; ".join(parts)

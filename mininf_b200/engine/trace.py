@@ -1,0 +1,364 @@
+"""Trace a model ONCE into a flat site table.
+
+The reference re-executes the Python model on every step and lets autograd differentiate whatever
+torch code links latent draws to distribution parameters (mininf/nn.py:223-225). Here the model
+is replayed a single time under :class:`SiteTableTracer` with the latent draws wrapped in
+:class:`LinkTensor` - a ``torch.Tensor`` subclass that carries real values (so every shape check
+and argument validation of ``torch.distributions`` runs as usual) plus a symbolic *link
+expression* describing how the value was built from latents and data. The closed set of link
+forms is what the CUDA kernels implement (include/mininf_b200.h):
+
+* ``Affine``:  ``T(a_const + a_lat + (b_const + b_lat) * x)`` - constants, data tensors, a latent
+  itself, ``c + d*x``, ``exp(a + b*x)``;
+* ``Dense``:   ``T(icpt + X @ theta)`` - ``X @ theta`` with an optional scalar intercept.
+
+Anything else makes the tensor *opaque*; an opaque tensor reaching a distribution parameter of a
+site that contributes to the log-density raises ``NotImplementedError`` (no fallback).
+"""
+from __future__ import annotations
+
+import dataclasses
+import numbers
+from typing import Any, Dict, List, Optional, Tuple
+
+import torch
+from torch.distributions import Distribution
+
+from ..core import State, TracerMixin, Value, batch, batch_scale, no_log_prob
+from ..util import OptionalSize, is_masked
+
+
+@dataclasses.dataclass(frozen=True)
+class LatentRef:
+    """A reference to latent site ``name``: the whole tensor (``index is None``, aligned
+    element-wise with the expression) or one flat element of it."""
+    name: str
+    index: Optional[int] = None
+
+    @property
+    def is_scalar(self) -> bool:
+        return self.index is not None
+
+
+@dataclasses.dataclass
+class Affine:
+    a_const: float = 0.0
+    a_lat: Optional[LatentRef] = None
+    b_const: float = 0.0
+    b_lat: Optional[LatentRef] = None
+    x: Optional[torch.Tensor] = None      # data covariate, shaped like the expression
+    transform: str = "id"
+
+    @property
+    def has_x_term(self) -> bool:
+        return self.b_const != 0.0 or self.b_lat is not None
+
+    @property
+    def is_pure_latent(self) -> bool:
+        return self.a_lat is not None and self.a_const == 0.0 and not self.has_x_term and \
+            self.transform == "id"
+
+    @property
+    def only_scalars(self) -> bool:
+        return all(ref is None or ref.is_scalar for ref in (self.a_lat, self.b_lat))
+
+
+@dataclasses.dataclass
+class Dense:
+    X: torch.Tensor                       # [n, p] data
+    theta: str                            # latent site holding the p coefficients
+    icpt_const: float = 0.0
+    icpt_lat: Optional[LatentRef] = None
+    transform: str = "id"
+
+
+Expr = Any  # Affine | Dense | None (opaque)
+
+
+def _as_const(value: Any) -> Optional[float]:
+    """A Python number or a one-element plain tensor as a float constant."""
+    if isinstance(value, numbers.Number):
+        return float(value)
+    if isinstance(value, torch.Tensor) and not isinstance(value, LinkTensor) and value.numel() == 1:
+        return float(value)
+    return None
+
+
+def _plain(value: Any) -> bool:
+    return isinstance(value, torch.Tensor) and not isinstance(value, LinkTensor)
+
+
+class LinkTensor(torch.Tensor):
+    """Real values + the symbolic link expression that produced them (``None`` = opaque)."""
+    _expr: Expr
+
+    @staticmethod
+    def wrap(data: torch.Tensor, expr: Expr) -> "LinkTensor":
+        out = torch.Tensor._make_subclass(LinkTensor, data.detach(), False)
+        out._expr = expr
+        return out
+
+    def unwrap(self) -> torch.Tensor:
+        with torch._C.DisableTorchFunctionSubclass():
+            return self.as_subclass(torch.Tensor)
+
+    def __repr__(self, *args: Any, **kwargs: Any) -> str:  # pragma: no cover - debugging aid
+        return f"LinkTensor(shape={tuple(self.shape)}, expr={getattr(self, '_expr', None)})"
+
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):  # type: ignore[override]
+        kwargs = kwargs or {}
+        with torch._C.DisableTorchFunctionSubclass():
+            raw = func(*args, **kwargs)
+        name = getattr(func, "__name__", "")
+        rule = _RULES.get(name)
+        if isinstance(raw, (tuple, list)):
+            if name == "broadcast_tensors":
+                return type(raw)(_rewrap(r, _shape_rule(a, r)) if isinstance(a, LinkTensor)
+                                 else _strip(r) for a, r in zip(_flatten_args(args), raw))
+            return type(raw)(_strip(r) for r in raw)
+        if not isinstance(raw, torch.Tensor) or not raw.is_floating_point():
+            return _strip(raw)
+        expr = rule(args, kwargs, raw) if rule is not None else None
+        return _rewrap(raw, expr)
+
+
+def _strip(value: Any) -> Any:
+    if isinstance(value, LinkTensor):
+        return value.unwrap()
+    return value
+
+
+def _rewrap(raw: torch.Tensor, expr: Expr) -> LinkTensor:
+    raw = _strip(raw)
+    return LinkTensor.wrap(raw, expr)
+
+
+def _flatten_args(args: Tuple[Any, ...]) -> List[Any]:
+    if len(args) == 1 and isinstance(args[0], (tuple, list)):
+        return list(args[0])
+    return list(args)
+
+
+def _expr_of(value: Any) -> Expr:
+    return getattr(value, "_expr", None) if isinstance(value, LinkTensor) else None
+
+
+# ---------------------------------------------------------------------------------------------
+# rules: (args, kwargs, raw result) -> expression of the result or None
+# ---------------------------------------------------------------------------------------------
+def _shape_rule(source: LinkTensor, raw: torch.Tensor, reshaper=None) -> Expr:
+    """Shape-only operations keep the expression if element alignment survives."""
+    expr = _expr_of(source)
+    if expr is None:
+        return None
+    same_numel = raw.numel() == source.numel()
+    if isinstance(expr, Dense):
+        return expr if same_numel and raw.ndim == 1 else None
+    whole = [ref for ref in (expr.a_lat, expr.b_lat) if ref is not None and not ref.is_scalar]
+    if whole and not same_numel:
+        return None                     # an element-wise latent cannot be broadcast periodically
+    x = expr.x
+    if x is not None:
+        with torch._C.DisableTorchFunctionSubclass():
+            x = x.expand(raw.shape) if reshaper is None else reshaper(x)
+        if x.shape != raw.shape:
+            return None
+    return dataclasses.replace(expr, x=x)
+
+
+def _rule_identity(args, kwargs, raw):
+    return _shape_rule(args[0], raw) if isinstance(args[0], LinkTensor) else None
+
+
+def _rule_reshape(args, kwargs, raw):
+    source = args[0]
+    if not isinstance(source, LinkTensor):
+        return None
+    return _shape_rule(source, raw, reshaper=lambda x: x.expand(source.shape).reshape(raw.shape))
+
+
+def _rule_to(args, kwargs, raw):
+    if raw.dtype != args[0].dtype:
+        return None
+    return _rule_identity(args, kwargs, raw)
+
+
+def _combine_add(left: Expr, right: Expr, shape: torch.Size) -> Expr:
+    """left + right for two expressions."""
+    if left is None or right is None:
+        return None
+    if isinstance(right, Dense):
+        left, right = right, left
+    if isinstance(left, Dense):
+        if not isinstance(right, Affine) or right.has_x_term or right.transform != "id" or \
+                left.transform != "id":
+            return None
+        if right.a_lat is not None and (left.icpt_lat is not None or not right.a_lat.is_scalar):
+            return None
+        return dataclasses.replace(left, icpt_const=left.icpt_const + right.a_const,
+                                   icpt_lat=left.icpt_lat or right.a_lat)
+    if left.transform != "id" or right.transform != "id":
+        return None
+    if left.has_x_term and right.has_x_term:
+        return None
+    if left.a_lat is not None and right.a_lat is not None:
+        return None
+    carrier = left if left.has_x_term else right
+    return Affine(a_const=left.a_const + right.a_const, a_lat=left.a_lat or right.a_lat,
+                  b_const=carrier.b_const, b_lat=carrier.b_lat, x=carrier.x)
+
+
+def _lift(value: Any, like: torch.Tensor) -> Expr:
+    """Constants and plain data tensors as expressions."""
+    const = _as_const(value)
+    if const is not None:
+        return Affine(a_const=const)
+    if _plain(value):
+        with torch._C.DisableTorchFunctionSubclass():
+            x = value.to(like.dtype).expand(like.shape) if value.shape != like.shape else value
+        return Affine(b_const=1.0, x=x)
+    return _expr_of(value)
+
+
+def _rule_add(args, kwargs, raw):
+    if kwargs.get("alpha", 1) != 1:
+        return None
+    return _combine_add(_lift(args[0], raw), _lift(args[1], raw), raw.shape)
+
+
+def _rule_sub(args, kwargs, raw):
+    if kwargs.get("alpha", 1) != 1:
+        return None
+    const = _as_const(args[1])
+    if const is None:
+        return None                       # subtracting data or latents needs a coefficient of -1
+    return _combine_add(_lift(args[0], raw), Affine(a_const=-const), raw.shape)
+
+
+def _rule_mul(args, kwargs, raw):
+    left, right = args[0], args[1]
+    if isinstance(right, LinkTensor) and not isinstance(left, LinkTensor):
+        left, right = right, left
+    expr = _expr_of(left)
+    if expr is None or isinstance(right, LinkTensor):
+        return None
+    const = _as_const(right)
+    if const is not None:
+        # `1 * x` is how ParameterizedDistribution hides raw parameters (mininf/nn.py:92-94)
+        return _shape_rule(left, raw) if const == 1.0 else None
+    if isinstance(expr, Affine) and expr.is_pure_latent and _plain(right):
+        if not expr.a_lat.is_scalar and left.numel() != raw.numel():
+            return None
+        with torch._C.DisableTorchFunctionSubclass():
+            x = right.to(raw.dtype).expand(raw.shape)
+        return Affine(b_lat=expr.a_lat, x=x)
+    return None
+
+
+def _rule_exp(args, kwargs, raw):
+    expr = _expr_of(args[0])
+    if expr is None or expr.transform != "id":
+        return None
+    return dataclasses.replace(expr, transform="exp")
+
+
+def _rule_matmul(args, kwargs, raw):
+    X, theta = args[0], args[1]
+    expr = _expr_of(theta)
+    if not _plain(X) or X.ndim != 2 or not isinstance(expr, Affine) or not expr.is_pure_latent:
+        return None
+    if expr.a_lat.is_scalar or theta.ndim != 1:
+        return None
+    return Dense(X=X, theta=expr.a_lat.name)
+
+
+def _rule_getitem(args, kwargs, raw):
+    source, index = args[0], args[1]
+    expr = _expr_of(source)
+    if not isinstance(expr, Affine) or not expr.is_pure_latent or expr.a_lat.is_scalar:
+        return None
+    if raw.numel() != 1:
+        return None
+    if isinstance(index, torch.Tensor):
+        if index.numel() != 1:
+            return None
+        index = int(index)
+    if isinstance(index, int):
+        index = (index,)
+    if not (isinstance(index, tuple) and len(index) == source.ndim and
+            all(isinstance(i, int) for i in index)):
+        return None
+    flat = 0
+    for i, size in zip(index, source.shape):
+        flat = flat * size + (i % size)
+    return Affine(a_lat=LatentRef(expr.a_lat.name, flat))
+
+
+def _rule_select(args, kwargs, raw):
+    source = args[0]
+    if source.ndim != 1:
+        return None
+    index = args[2] if len(args) > 2 else kwargs.get("index")
+    return _rule_getitem((source, int(index)), {}, raw)
+
+
+_RULES: Dict[str, Any] = {
+    "add": _rule_add, "__add__": _rule_add, "__radd__": _rule_add,
+    "sub": _rule_sub, "__sub__": _rule_sub, "subtract": _rule_sub,
+    "mul": _rule_mul, "__mul__": _rule_mul, "__rmul__": _rule_mul, "multiply": _rule_mul,
+    "exp": _rule_exp,
+    "matmul": _rule_matmul, "__matmul__": _rule_matmul, "mv": _rule_matmul,
+    "__getitem__": _rule_getitem, "select": _rule_select,
+    "expand": _rule_identity, "expand_as": _rule_identity, "broadcast_to": _rule_identity,
+    "contiguous": _rule_identity, "clone": _rule_identity, "detach": _rule_identity,
+    "reshape": _rule_reshape, "view": _rule_reshape, "squeeze": _rule_reshape,
+    "unsqueeze": _rule_reshape, "flatten": _rule_reshape,
+    "to": _rule_to, "float": _rule_to, "type_as": _rule_to,
+}
+
+
+# ---------------------------------------------------------------------------------------------
+# the tracer
+# ---------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class SiteRecord:
+    name: str
+    distribution: Distribution
+    value: torch.Tensor          # LinkTensor (latent), plain tensor or MaskedTensor (observed)
+    scale: float                 # declared-over-actual batch ratio (mininf/core.py:267-271)
+
+
+class SiteTableTracer(TracerMixin):
+    """Record every log-density site of one model execution (the plan-time counterpart of
+    ``LogProbTracer.sample``, mininf/core.py:211-245): same ``Value`` handling, duplicate /
+    missing-value errors, validation and ``no_log_prob`` skip - but nothing is evaluated."""
+
+    def __init__(self, *args: Any, **kwargs: Any) -> None:
+        super().__init__(*args, **kwargs)
+        self.sites: List[SiteRecord] = []
+        self._names: set = set()
+
+    def sample(self, state: State, name: str, distribution: Distribution,
+               sample_shape: OptionalSize = None) -> torch.Tensor:
+        if isinstance(distribution, Value):
+            current = state.get(name, distribution.value)
+            self._assert_valid_parameter(current, name, distribution, sample_shape)
+            return current
+        if name in self._names:
+            raise RuntimeError(f"Log probability has already been evaluated for '{name}'. Did you "
+                               "call `sample` twice with the same variable name?")
+        current = state.get(name)
+        if current is None:
+            raise ValueError(f"Cannot evaluate log probability; variable '{name}' is missing. Did "
+                             "you forget to condition on observed data?")
+        self._assert_valid_parameter(current, name, distribution, sample_shape)
+        if no_log_prob.get_instance():
+            return current
+        declared = batch.get_shape()
+        if is_masked(current) and declared:
+            raise ValueError("Batch dimensions are not supported for masked data.")
+        self._names.add(name)
+        self.sites.append(SiteRecord(name, distribution, current,
+                                     batch_scale(current.shape, declared)))
+        return current

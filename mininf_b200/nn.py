@@ -1,0 +1,342 @@
+"""Variational-inference layer behind the reference's ``mininf.nn`` interface.
+
+``ParameterizedDistribution`` / ``FactorizedDistribution`` / ``ParameterizedFactorizedDistribution``
+keep the reference's semantics (mininf/nn.py:29-187). ``EvidenceLowerBoundLoss`` keeps its call
+signature and return contract (a 0-dim tensor with ``grad_fn`` whose ``backward`` fills the
+unconstrained parameters, mininf/nn.py:190-228, tests/test_nn.py:50-66) but computes the Monte
+Carlo ELBO and its gradient with the CUDA engine:
+
+* the conditioned model is traced ONCE into a site table (``engine.trace``), cached per plan;
+* every step enqueues the fused forward+backward kernels (``engine.plan``) for ``n_particles``
+  reparameterised draws (the reference uses exactly one, mininf/nn.py:217; S particles are the
+  mean of S reference evaluations);
+* gradients come back for the CONSTRAINED parameters of the approximation, so stock autograd
+  still chains through ``ParameterizedDistribution``'s transforms (mininf/nn.py:88-96).
+
+There is no CPU or eager fallback: CPU tensors, unsupported distributions or link functions
+raise.
+"""
+from __future__ import annotations
+
+from typing import Any, Callable, Dict, List, Optional, Set, Tuple, Type
+
+import torch
+from torch import distributions, nn
+
+from .core import LogProbTracer, condition
+from .util import OptionalSize, TensorDict, _normalize_shape, maybe_as_tensor
+
+DistributionDict = Dict[str, torch.distributions.Distribution]
+
+
+def _is_identity_transform(transform: distributions.Transform) -> bool:
+    return isinstance(transform, distributions.ComposeTransform) and not transform.parts
+
+
+class ParameterizedDistribution(nn.Module):
+    """A distribution type with trainable parameters stored in unconstrained space
+    (``transform_to(constraint).inv``); calling the module rebuilds the distribution.
+
+    ``_const`` names parameters to keep fixed, ``_clone`` protects caller-owned tensors of
+    identity-constrained parameters from in-place optimiser updates.
+    """
+
+    def __init__(self, cls: Type[distributions.Distribution], *, _const: Set[str] | None = None,
+                 _clone: bool = True, **parameters: Any) -> None:
+        super().__init__()
+        self.distribution_cls = cls
+        fixed = _const or set()
+        constraints = cls.arg_constraints
+        self.distribution_constants: Dict[str, Any] = {}
+        trainable: Dict[str, nn.Parameter] = {}
+        for name, given in parameters.items():
+            if name in fixed or name not in constraints:
+                self.distribution_constants[name] = given
+                continue
+            given = maybe_as_tensor(given)
+            transform = distributions.transform_to(constraints[name])
+            if _is_identity_transform(transform) and _clone:
+                raw = 1 * given
+            else:
+                raw = transform.inv(given)
+            trainable[name] = nn.Parameter(raw)
+        self.distribution_parameters = nn.ParameterDict(trainable)
+
+    def forward(self) -> distributions.Distribution:
+        constraints = self.distribution_cls.arg_constraints
+        constrained = {}
+        for name, raw in self.distribution_parameters.items():
+            transform = distributions.transform_to(constraints[name])
+            # `1 * raw` keeps the nn.Parameter itself out of the distribution
+            constrained[name] = 1 * raw if _is_identity_transform(transform) else transform(raw)
+        return self.distribution_cls(**constrained, **self.distribution_constants)
+
+
+class FactorizedDistribution(DistributionDict):
+    """Independent named factors: entropy adds up, sampling maps over the factors in order."""
+
+    def entropy(self) -> torch.Tensor:
+        return sum(factor.entropy().sum() for factor in self.values())  # type: ignore
+
+    def rsample(self, sample_shape: OptionalSize = None) -> TensorDict:
+        shape = _normalize_shape(sample_shape)
+        return {name: factor.rsample(shape) for name, factor in self.items()}
+
+    def sample(self, sample_shape: OptionalSize = None) -> TensorDict:
+        shape = _normalize_shape(sample_shape)
+        return {name: factor.sample(shape) for name, factor in self.items()}
+
+
+class ParameterizedFactorizedDistribution(nn.ModuleDict):
+    """``nn.ModuleDict`` of :class:`ParameterizedDistribution`; calling it yields a
+    :class:`FactorizedDistribution`."""
+
+    def __init__(self, arg: Dict[str, ParameterizedDistribution] | None = None,
+                 **kwargs: ParameterizedDistribution) -> None:
+        modules = dict(arg or {})
+        modules.update(kwargs)
+        super().__init__(modules)
+
+    def forward(self) -> FactorizedDistribution:
+        return FactorizedDistribution({name: module() for name, module in self.items()})
+
+
+# -------------------------------------------------------------------------------------------------
+# the engine-backed loss
+# -------------------------------------------------------------------------------------------------
+def _unwrap_conditioning(model: Callable) -> Tuple[Callable, List[Tuple[str, Any]]]:
+    """Base callable and every conditioned (name, value) pair of a ``condition`` chain."""
+    pinned: List[Tuple[str, Any]] = []
+    while hasattr(model, "_mininf_values"):
+        pinned.extend(model._mininf_values.items())
+        model = model._mininf_model
+    return model, pinned
+
+
+def _tensor_key(value: Any) -> Tuple:
+    if isinstance(value, torch.masked.MaskedTensor):
+        return ("masked",) + _tensor_key(value.get_data()) + _tensor_key(value.get_mask())
+    if isinstance(value, torch.Tensor):
+        return (value.data_ptr(), tuple(value.shape), str(value.dtype), str(value.device),
+                value._version)
+    return (repr(value),)
+
+
+class _EngineFunction(torch.autograd.Function):
+    """One fused forward+backward evaluation; inputs are the constrained parameter tensors."""
+
+    @staticmethod
+    def forward(ctx, loss_module, plan, noise, seed, offset, reduce_fn, with_entropy, *params):
+        with torch.no_grad():
+            for spec, p0, p1 in zip(plan.latents, params[0::2], params[1::2]):
+                lo, hi = spec.offset, spec.offset + spec.numel
+                plan.P0[lo:hi].copy_(p0.reshape(-1))
+                plan.P1[lo:hi].copy_(p1.reshape(-1))
+            out = plan.step(noise, seed, offset, with_entropy=with_entropy, reduce_fn=reduce_fn)
+            saved = out.clone()
+        ctx.plan = plan
+        ctx.save_for_backward(saved)
+        loss_module._schedule_status_check(plan)
+        return saved[0].clone()
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        (saved,) = ctx.saved_tensors
+        plan = ctx.plan
+        grads: List[Optional[torch.Tensor]] = [None] * 7
+        for spec in plan.latents:
+            lo, hi = 1 + spec.offset, 1 + spec.offset + spec.numel
+            grads.append((saved[lo:hi] * grad_output).reshape(spec.shape))
+            grads.append((saved[plan.D + lo:plan.D + hi] * grad_output).reshape(spec.shape))
+        return tuple(grads)
+
+
+class EvidenceLowerBoundLoss(nn.Module):
+    """Negative Monte Carlo ELBO of ``model`` under ``approximation``.
+
+    Args (all optional, all beyond the reference's zero-argument constructor):
+        n_particles: reparameterised draws averaged per evaluation (default 1 = the reference).
+        dense_precision: ``"auto"`` (tcgen05 TF32 kernel where its shape constraints hold, fp32
+            SIMT otherwise), ``"tf32"`` (require it) or ``"fp32"``.
+        cache: reuse the traced plan while the model, conditioned tensors and approximation
+            structure are unchanged (the reference re-runs the model every step).
+        process_group: ``True`` / a ``torch.distributed`` group to treat every observed site as
+            this rank's row shard and all-reduce the partial sums (one collective per step).
+        check: ``"lazy"`` validates the device status word of the previous step at the next call
+            (no extra synchronisation), ``"sync"`` synchronises every call, ``"off"`` never.
+    """
+
+    def __init__(self, n_particles: int = 1, *, dense_precision: str = "auto", cache: bool = True,
+                 process_group: Any = None, check: str = "lazy") -> None:
+        super().__init__()
+        if dense_precision not in ("auto", "tf32", "fp32"):
+            raise ValueError("dense_precision must be 'auto', 'tf32' or 'fp32'")
+        if check not in ("lazy", "sync", "off"):
+            raise ValueError("check must be 'lazy', 'sync' or 'off'")
+        self.n_particles = int(n_particles)
+        self.dense_precision = dense_precision
+        self.cache = cache
+        self.process_group = process_group
+        self.check = check
+        self._plans: Dict[Tuple, Any] = {}
+        self._pending: List[Tuple[Any, torch.Tensor, torch.cuda.Event]] = []
+        self._calls = 0
+        self.last_plan = None
+
+    # -- status word ------------------------------------------------------------------------
+    def _schedule_status_check(self, plan: Any) -> None:
+        if self.check == "off":
+            return
+        if self.check == "sync":
+            self._raise_for_status(int(plan.status.item()))
+            return
+        host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+        host.copy_(plan.status, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record(torch.cuda.current_stream(plan.device))
+        self._pending.append((plan, host, event))
+
+    def _drain_status(self, block: bool = False) -> None:
+        remaining = []
+        for plan, host, event in self._pending:
+            if block:
+                event.synchronize()
+            if event.query():
+                self._raise_for_status(int(host.item()))
+            else:
+                remaining.append((plan, host, event))
+        self._pending = remaining
+
+    @staticmethod
+    def _raise_for_status(bits: int) -> None:
+        if bits:
+            from .engine.plan import status_message
+            raise ValueError("the ELBO engine flagged invalid values: " + status_message(bits))
+
+    def synchronize(self) -> None:
+        """Wait for outstanding evaluations and raise if any of them flagged invalid values."""
+        self._drain_status(block=True)
+
+    # -- tracing ----------------------------------------------------------------------------
+    def _build_plan(self, model: Callable, approximation: DistributionDict) -> Any:
+        from .engine import abi
+        from .engine.plan import LatentSpec, Plan, latent_parameters
+        from .engine.trace import Affine, LatentRef, LinkTensor, SiteTableTracer
+
+        specs: List[LatentSpec] = []
+        draws: Dict[str, torch.Tensor] = {}
+        offset = 0
+        device = None
+        for name, factor in approximation.items():
+            family, p0, _ = latent_parameters(factor)
+            if factor.event_shape:
+                raise NotImplementedError("event-shaped approximations are not supported")
+            shape = factor.batch_shape
+            numel = max(shape.numel(), 1)
+            specs.append(LatentSpec(name, family, shape, numel, offset))
+            offset += numel
+            device = device or p0.device
+            with torch.no_grad():
+                draw = factor.sample()
+            # one-element latents are referenced as scalars so they may broadcast over any site
+            ref = LatentRef(name, 0) if numel == 1 else LatentRef(name)
+            draws[name] = LinkTensor.wrap(draw, Affine(a_lat=ref))
+        if device is None:
+            raise ValueError("the approximation has no factors")
+        if device.type != "cuda":
+            raise RuntimeError("the mininf_b200 ELBO engine runs on CUDA tensors only (there is "
+                               "no CPU fallback); got approximation parameters on " + str(device))
+        with SiteTableTracer() as tracer:
+            condition(model, **draws)()
+        missing = {spec.name for spec in specs} - {site.name for site in tracer.sites}
+        # latent draws the model never scored still take part in the entropy term; that mirrors
+        # the reference, where `condition` silently accepts unused names
+        del missing
+        return Plan(tracer.sites, specs, self.n_particles, device,
+                    dense_mode=self.dense_precision)
+
+    def _plan_for(self, model: Callable, approximation: DistributionDict) -> Any:
+        if not self.cache:
+            return self._build_plan(model, approximation)
+        base, pinned = _unwrap_conditioning(model)
+        key = (id(base), tuple((name, _tensor_key(val)) for name, val in pinned),
+               tuple((name, type(factor).__name__, tuple(factor.batch_shape))
+                     for name, factor in approximation.items()),
+               self.n_particles, self.dense_precision)
+        plan = self._plans.get(key)
+        if plan is None:
+            if len(self._plans) >= 8:
+                self._plans.pop(next(iter(self._plans)))
+            plan = self._build_plan(model, approximation)
+            plan._pin = (base, [val for _, val in pinned])   # keep ids / data pointers valid
+            self._plans[key] = plan
+        return plan
+
+    # -- noise ------------------------------------------------------------------------------
+    def _noise(self, plan: Any, approximation: DistributionDict,
+               given: Optional[Dict[str, torch.Tensor]]) -> Optional[torch.Tensor]:
+        """Reparameterisation noise [S, D]: ``None`` lets the kernel draw Normal eps with Philox;
+        Gamma / Beta factors use torch's standard-gamma / Dirichlet samplers on the device."""
+        from .engine import abi
+        S = plan.S
+        if given is None and plan.all_normal:
+            return None
+        noise = torch.empty(S, plan.D, device=plan.device, dtype=torch.float32)
+        with torch.no_grad():
+            for spec in plan.latents:
+                block = noise[:, spec.offset:spec.offset + spec.numel]
+                if given is not None and spec.name in given:
+                    block.copy_(given[spec.name].to(plan.device, torch.float32).reshape(S, spec.numel))
+                elif spec.family == abi.NORMAL:
+                    block.normal_()
+                elif spec.family == abi.GAMMA:
+                    alpha = approximation[spec.name].concentration.detach().float()
+                    block.copy_(torch._standard_gamma(alpha.expand(spec.shape).reshape(1, -1)
+                                                      .expand(S, spec.numel).contiguous()))
+                else:
+                    beta = approximation[spec.name]
+                    conc = torch.stack([beta.concentration1.detach().float().expand(spec.shape),
+                                        beta.concentration0.detach().float().expand(spec.shape)], -1)
+                    conc = conc.reshape(1, spec.numel, 2).expand(S, spec.numel, 2).contiguous()
+                    block.copy_(torch._sample_dirichlet(conc)[..., 0])
+        return noise
+
+    # -- forward ----------------------------------------------------------------------------
+    def forward(self, model: Callable,
+                approximation: torch.distributions.Distribution | DistributionDict, *,
+                _noise: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+        if not isinstance(approximation, dict):
+            raise TypeError("Expected a distribution which samples dictionaries of tensors but got "
+                            f"a sample of type {type(approximation)}")
+        self._drain_status()
+        plan = self._plan_for(model, approximation)
+        self.last_plan = plan
+        from .engine.plan import latent_parameters
+        params: List[torch.Tensor] = []
+        for spec in plan.latents:
+            _, p0, p1 = latent_parameters(approximation[spec.name])
+            shape = spec.shape if len(spec.shape) else torch.Size([])
+            params.append(p0.to(torch.float32).expand(shape))
+            params.append(p1.to(torch.float32).expand(shape))
+        noise = self._noise(plan, approximation, _noise)
+        seed = torch.cuda.default_generators[plan.device.index or 0].initial_seed() \
+            if plan.device.index is not None else torch.cuda.initial_seed()
+        self._calls += 1
+        reduce_fn = None
+        if self.process_group is not None:
+            import torch.distributed as dist
+            group = None if self.process_group is True else self.process_group
+            reduce_fn = lambda acc: dist.all_reduce(acc, group=group)  # noqa: E731
+        return _EngineFunction.apply(self, plan, noise, int(seed) & (2 ** 63 - 1), self._calls,
+                                     reduce_fn, True, *params)
+
+
+class LogLikelihoodLoss(nn.Module):
+    """Negative joint log-density at fixed parameter values (mininf/nn.py:231-257). Evaluated
+    with ``torch.distributions`` through :class:`~mininf_b200.core.LogProbTracer`; porting it to
+    the engine is listed as next in SURVEY.md §8f."""
+
+    def forward(self, model: Callable, parameters: TensorDict) -> torch.Tensor:
+        with LogProbTracer() as log_prob:
+            condition(model, **parameters)()
+        return - log_prob.total

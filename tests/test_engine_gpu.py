@@ -1,0 +1,237 @@
+"""Parity of the CUDA engine (through the public API and the C-ABI underneath) with the oracle
+and with the golden fixtures generated from the reference. Needs a B200."""
+import numpy as np
+import pytest
+import torch
+
+import mininf_b200 as mininf
+from mininf_b200.engine import abi
+from oracle import configs, elbo
+
+from conftest import GOLDEN_CASES, golden_noise, load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def engine_eval(config, noise, n_particles, precision="fp32", approx=None, leaves=None):
+    if approx is None:
+        approx, leaves = config.approximation(device=DEV)
+    loss_module = mininf.nn.EvidenceLowerBoundLoss(n_particles, dense_precision=precision, check="sync")
+    conditioned = mininf.condition(lambda: config.model(mininf), **config.data)
+    loss = loss_module(conditioned, approx, _noise=noise)
+    loss.backward()
+    return loss, leaves, loss_module
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.mark.parametrize("case", list(GOLDEN_CASES))
+def test_matches_reference_golden(case):
+    """fp32 mode against values produced by the unmodified reference (tests/golden)."""
+    config, golden = load_golden(case, device=DEV)
+    S = int(golden["n_particles"])
+    loss, leaves, _ = engine_eval(config, golden_noise(config, golden, DEV), S)
+    assert loss.ndim == 0 and loss.dtype == torch.float32
+    assert abs(float(loss) - float(golden["loss"])) <= 1e-5 * abs(float(golden["loss"]))  # north-star tolerance
+    for key, leaf in leaves.items():
+        assert leaf.grad is not None, key
+        assert rel(leaf.grad.cpu().numpy(), golden[f"grad/{key}"]) < 1e-4, key
+
+
+@pytest.mark.parametrize("case", ["regression", "regression_sigma"])
+def test_tf32_tensor_core_path_matches_golden(case):
+    """tcgen05 kernel: TF32 operands (round to nearest), fp32 accumulate. Stated tolerances at
+    these few-hundred-row sizes: 1e-4 relative on the loss, 2e-3 relative L2 on gradients. The
+    rounding noise is unbiased and averages down as 1/sqrt(N): test_tf32_error_shrinks_with_rows
+    asserts the north-star 1e-5 on the loss at N = 2e5."""
+    config, golden = load_golden(case, device=DEV)
+    S = int(golden["n_particles"])
+    loss, leaves, module = engine_eval(config, golden_noise(config, golden, DEV), S, precision="tf32")
+    assert module.last_plan.dense_sites[0][1] == abi.DENSE_TF32
+    assert abs(float(loss) - float(golden["loss"])) <= 1e-4 * abs(float(golden["loss"]))
+    for key, leaf in leaves.items():
+        assert rel(leaf.grad.cpu().numpy(), golden[f"grad/{key}"]) < 2e-3, key
+
+
+@pytest.mark.parametrize("n,p,S,sigma", [(1, 64, 1, False), (127, 64, 3, True), (128, 64, 64, False),
+                                         (129, 64, 5, True), (5000, 64, 64, True), (1000, 7, 2, False),
+                                         (777, 130, 9, True)])
+@pytest.mark.parametrize("precision", ["fp32", "auto"])
+def test_regression_against_oracle(n, p, S, sigma, precision):
+    """Ragged row counts, one-row and one-particle edge cases, feature counts outside the tensor
+    core kernel's shape (those fall to the fp32 kernel under 'auto')."""
+    torch.manual_seed(n + p)
+    cpu = configs.regression(n, p, sigma_latent=sigma)
+    gpu = configs.regression(n, p, sigma_latent=sigma, device=DEV, gen_device="cpu")
+    approx_c, leaves_c = cpu.approximation()
+    noise = {name: elbo.draw_noise(dist, S) for name, dist in approx_c.items()}
+    expected = elbo.neg_elbo(cpu.model, cpu.data, approx_c, noise, S)
+    expected.backward()
+    loss, leaves, module = engine_eval(gpu, {k: v.to(DEV) for k, v in noise.items()}, S, precision)
+    tf32 = module.last_plan.dense_sites[0][1] == abi.DENSE_TF32
+    assert tf32 == (precision == "auto" and p == 64)
+    assert abs(float(loss) - float(expected)) <= (2e-4 if tf32 else 1e-5) * abs(float(expected))
+    for key, leaf in leaves.items():
+        assert rel(leaf.grad.cpu().numpy(), leaves_c[key].grad.numpy()) < (5e-3 if tf32 else 1e-4), key
+
+
+def test_tf32_error_shrinks_with_rows():
+    """Rounding errors of the TF32 path are unbiased: relative gradient error at N=2e5 is far
+    below the small-N tolerance (fp64 torch on the GPU is the yardstick here)."""
+    n, p, S = 200_000, 64, 64
+    gpu = configs.regression(n, p, device=DEV)
+    approx, leaves = gpu.approximation(device=DEV)
+    noise = {"theta": torch.randn(S, p, device=DEV)}
+    loss, leaves, _ = engine_eval(gpu, noise, S, "tf32", approx, leaves)
+    loc = leaves["theta.loc"].detach().double().requires_grad_()
+    scale = leaves["theta.scale"].detach().double().requires_grad_()
+    theta = loc + noise["theta"].double() * scale
+    eta = gpu.data["X"].double() @ theta.T
+    ll = torch.distributions.Normal(eta, 1.0).log_prob(gpu.data["y"].double()[:, None]).sum(0)
+    prior = torch.distributions.Normal(0.0, 1.0).log_prob(theta).sum(1)
+    ref = -((ll + prior).mean() + torch.distributions.Normal(loc, scale).entropy().sum())
+    ref.backward()
+    assert abs(float(loss) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert rel(leaves["theta.loc"].grad.cpu().numpy(), loc.grad.cpu().numpy()) < 2e-4
+    assert rel(leaves["theta.scale"].grad.cpu().numpy(), scale.grad.cpu().numpy()) < 2e-4
+
+
+@pytest.mark.parametrize("n,S", [(1, 1), (31, 2), (2048, 64), (50_000, 17)])
+def test_missing_observations_against_oracle(n, S):
+    """Masked Poisson + Normal sites sharing a covariate (small-site kernel below 2048 rows,
+    fused site sweep from there on)."""
+    torch.manual_seed(n)
+    cpu = configs.missing(n)
+    gpu = configs.missing(n, device=DEV, gen_device="cpu")
+    approx_c, leaves_c = cpu.approximation()
+    noise = {name: elbo.draw_noise(dist, S) for name, dist in approx_c.items()}
+    expected = elbo.neg_elbo(cpu.model, cpu.data, approx_c, noise, S)
+    expected.backward()
+    loss, leaves, module = engine_eval(gpu, {k: v.to(DEV) for k, v in noise.items()}, S)
+    assert (len(module.last_plan.sweep_groups) == 1) == (n >= 2048)
+    assert abs(float(loss) - float(expected)) <= 1e-5 * abs(float(expected))
+    for key, leaf in leaves.items():
+        np.testing.assert_allclose(leaf.grad.cpu().numpy(), leaves_c[key].grad.numpy(), rtol=2e-4, atol=1e-3)
+
+
+def test_integer_exact_mask_and_count_sums():
+    """Bit-exact integer work: number of observed entries and sum of observed counts."""
+    gpu = configs.missing(100_003, device=DEV, gen_device="cpu")
+    raw = gpu.extra["raw"]
+    lib = abi.load()
+    out = torch.zeros(2, dtype=torch.int64, device=DEV)
+    stream = torch.cuda.current_stream().cuda_stream
+    lib.call("mnf_masked_count", raw["counts"].data_ptr(), raw["m_counts"].data_ptr(), raw["counts"].numel(),
+             out.data_ptr(), stream)
+    assert out.tolist() == [int(raw["m_counts"].sum()), int(raw["counts"][raw["m_counts"]].double().sum())]
+    lib.call("mnf_masked_count", raw["counts"].data_ptr(), None, raw["counts"].numel(), out.data_ptr(), stream)
+    assert out.tolist() == [raw["counts"].numel(), int(raw["counts"].double().sum())]
+
+
+@pytest.mark.parametrize("batch_rows", [400, 1, 4097])
+def test_minibatch_scaling_against_oracle(batch_rows):
+    """`batch` rescaling (declared / actual rows) on a Bernoulli(logits = X @ theta) site."""
+    torch.manual_seed(batch_rows)
+    S = 4
+    cpu = configs.logistic(100_000, batch_rows, p=64)
+    gpu = configs.logistic(100_000, batch_rows, p=64, device=DEV, gen_device="cpu")
+    approx_c, leaves_c = cpu.approximation()
+    noise = {name: elbo.draw_noise(dist, S) for name, dist in approx_c.items()}
+    expected = elbo.neg_elbo(cpu.model, cpu.data, approx_c, noise, S)
+    expected.backward()
+    for precision in ("fp32", "tf32"):
+        loss, leaves, module = engine_eval(gpu, {k: v.to(DEV) for k, v in noise.items()}, S, precision)
+        assert module.last_plan.dense_sites[0][0].weight == 100_000 / batch_rows
+        tol = 1e-5 if precision == "fp32" else 1e-4
+        assert abs(float(loss) - float(expected)) <= tol * abs(float(expected))
+        for key, leaf in leaves.items():
+            assert rel(leaf.grad.cpu().numpy(), leaves_c[key].grad.numpy()) < (1e-4 if precision == "fp32" else 5e-3)
+
+
+def test_readme_training_loop_recovers_posterior():
+    """README.md:57-70: Beta approximation of the coin bias trained with Adam through the
+    unchanged API; exact posterior is Beta(11, 3)."""
+    torch.manual_seed(0)
+    config = configs.coin(device=DEV)
+    approximation = mininf.nn.ParameterizedDistribution(
+        torch.distributions.Beta, concentration0=torch.tensor(2.0, device=DEV),
+        concentration1=torch.tensor(2.0, device=DEV))
+    conditioned = mininf.condition(lambda: config.model(mininf), **config.data)
+    optimizer = torch.optim.Adam(approximation.parameters(), lr=0.02)
+    loss = mininf.nn.EvidenceLowerBoundLoss(n_particles=8)
+    for _ in range(600):
+        optimizer.zero_grad()
+        loss(conditioned, {"theta": approximation()}).backward()
+        optimizer.step()
+    fitted = approximation()
+    mean = float(fitted.mean)
+    assert abs(mean - 11 / 14) < 0.05
+    assert 6 < float(fitted.concentration1) < 18 and 1.5 < float(fitted.concentration0) < 6
+
+
+def test_loss_contract_and_parameter_gradients():
+    """tests/test_nn.py:50-66 of the reference, on the engine: 0-dim finite loss with grad_fn,
+    gradients appear on the unconstrained parameters only after backward."""
+    def model():
+        mininf.sample("x", torch.distributions.Normal(0, 1), 3)
+
+    approximation = mininf.nn.ParameterizedDistribution(
+        torch.distributions.Normal, loc=torch.tensor(0.0, device=DEV), scale=torch.ones(3, device=DEV))
+    loss = mininf.nn.EvidenceLowerBoundLoss()
+    value = loss(model, {"x": approximation()})
+    assert value.grad_fn is not None and value.ndim == 0 and np.isfinite(value.item())
+    assert all(p.grad is None for p in approximation.distribution_parameters.values())
+    value.backward()
+    assert all(p.grad is not None for p in approximation.distribution_parameters.values())
+    with pytest.raises(TypeError, match="dictionaries of tensors"):
+        loss(None, torch.distributions.Normal(0, 1))
+
+
+def test_philox_draws_are_standard_normal_and_seeded():
+    """Without external noise Normal factors draw eps in-kernel (Philox4x32-10)."""
+    config = configs.regression(256, 64, device=DEV)
+    conditioned = mininf.condition(lambda: config.model(mininf), **config.data)
+    approx, _ = config.approximation(device=DEV)
+    loss = mininf.nn.EvidenceLowerBoundLoss(64, check="sync")
+    torch.manual_seed(5)
+    first = float(loss(conditioned, approx))
+    eps = loss.last_plan.noise.clone()
+    assert abs(float(eps.mean())) < 0.06 and abs(float(eps.std()) - 1) < 0.05
+    second = float(loss(conditioned, approx))
+    assert first != second                      # the stream advances between calls
+    torch.manual_seed(5)
+    again = mininf.nn.EvidenceLowerBoundLoss(64, check="sync")
+    assert float(again(conditioned, approx)) == first
+
+
+def test_invalid_values_are_reported():
+    config = configs.regression(300, 64, device=DEV)
+    config.data["y"][17] = float("nan")
+    conditioned = mininf.condition(lambda: config.model(mininf), **config.data)
+    approx, _ = config.approximation(device=DEV)
+    with pytest.raises(ValueError, match="not in the support"):
+        mininf.nn.EvidenceLowerBoundLoss(2, check="sync")(conditioned, approx)   # caught at trace time
+
+
+def test_no_cpu_fallback():
+    config = configs.regression(64, 8)
+    conditioned = mininf.condition(lambda: config.model(mininf), **config.data)
+    approx, _ = config.approximation()
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        mininf.nn.EvidenceLowerBoundLoss()(conditioned, approx)
+
+
+def test_unsupported_link_raises():
+    x = torch.randn(50, device=DEV)
+
+    def model():
+        a = mininf.sample("a", torch.distributions.Normal(0, 1))
+        mininf.sample("y", torch.distributions.Normal(torch.sin(a * x), 1.0))
+
+    approx = {"a": torch.distributions.Normal(torch.tensor(0.0, device=DEV), torch.tensor(1.0, device=DEV))}
+    with pytest.raises(NotImplementedError, match="not a supported link"):
+        mininf.nn.EvidenceLowerBoundLoss()(mininf.condition(model, y=torch.randn(50, device=DEV)), approx)
