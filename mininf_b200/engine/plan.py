@@ -105,6 +105,10 @@ class Plan:
                                   p1=self.P1.data_ptr() + 4 * spec.offset)
         self.latent_table = _bytes_to_device(table, device)
 
+        # optional instrumentation: CUDA event pairs around every dense sweep (bench.py roofline)
+        self.record_sweep_events = False
+        self.sweep_events: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
+
         self.dense_sites: List[Tuple[abi.DenseSite, int]] = []
         self.sweep_groups: List[Any] = []
         small_observed: List[abi.Site] = []
@@ -319,9 +323,15 @@ class Plan:
                  seed, offset, self.z.data_ptr(), self.noise.data_ptr(), self.acc.data_ptr(), status,
                  stream)
         for site, mode in self.dense_sites:
+            if self.record_sweep_events:
+                begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                begin.record(torch.cuda.current_stream(self.device))
             lib.call("mnf_dense_sweep", C.byref(site), mode, self.z.data_ptr(), S, D,
                      self.acc.data_ptr(), self.workspace.data_ptr(), self.workspace_bytes, status,
                      stream)
+            if self.record_sweep_events:
+                end.record(torch.cuda.current_stream(self.device))
+                self.sweep_events.append((begin, end))
         for group in self.sweep_groups:
             lib.call("mnf_site_sweep", group, len(group), self.z.data_ptr(), S, D,
                      self.acc.data_ptr(), self.workspace.data_ptr(), self.workspace_bytes, status,
