@@ -278,7 +278,9 @@ def sample(state: State, name: str, distribution: Distribution,
            sample_shape: OptionalSize = None) -> torch.Tensor:
     """Declare random variable ``name`` with the given distribution and iid ``sample_shape``;
     returns its value of shape ``sample_shape + batch_shape + event_shape``."""
-    tracer = TracerMixin.get_instance() or SampleTracer()
+    tracer = TracerMixin.get_instance()
+    if tracer is None:      # not `or`: an empty LogProbTracer is a falsy dict
+        tracer = SampleTracer()
     return tracer.sample(state, name, distribution, sample_shape)
 
 

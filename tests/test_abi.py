@@ -1,0 +1,70 @@
+"""The C-ABI shared library loads on a machine without a GPU and exports every symbol that
+include/mininf_b200.h declares; the ctypes structures match the C layout."""
+import ctypes
+import pathlib
+import re
+import subprocess
+
+import pytest
+
+from mininf_b200.engine import abi, build
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+HEADER = ROOT / "include" / "mininf_b200.h"
+
+
+@pytest.fixture(scope="module")
+def library():
+    build.build()
+    return abi.load()
+
+
+def declared_functions():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(mnf_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported(library):
+    names = declared_functions()
+    assert len(names) >= 10
+    for name in names:
+        assert hasattr(library._dll, name), f"{name} is declared in the header but not exported"
+        assert name in abi.EXPORTS, f"{name} has no ctypes prototype"
+    assert library.raw("mnf_abi_version")() == abi.ABI_VERSION
+    match = re.search(r"#define MNF_ABI_VERSION (\d+)", HEADER.read_text())
+    assert int(match.group(1)) == abi.ABI_VERSION
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    source = tmp_path / "sizes.c"
+    source.write_text('''#include <stdio.h>
+#include <stddef.h>
+#include "mininf_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mnf_link_t), sizeof(mnf_latent_t), sizeof(mnf_site_t),
+         sizeof(mnf_dense_site_t), sizeof(mnf_device_info_t), offsetof(mnf_site_t, param),
+         offsetof(mnf_dense_site_t, scale), offsetof(mnf_dense_site_t, weight));
+  return 0;
+}''')
+    binary = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), str(source), "-o", str(binary)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(binary)], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(abi.Link), ctypes.sizeof(abi.Latent), ctypes.sizeof(abi.Site),
+                     ctypes.sizeof(abi.DenseSite), ctypes.sizeof(abi.DeviceInfo), abi.Site.param.offset,
+                     abi.DenseSite.scale.offset, abi.DenseSite.weight.offset]
+
+
+def test_argument_errors_do_not_need_a_gpu(library):
+    """Null pointers are rejected before any CUDA call; the message is retrievable."""
+    code = library.raw("mnf_finalize")(None, 0, 1, 1, None, None, None, 1, None, None, None)
+    assert code == abi.E_INVALID
+    assert b"mnf_finalize" in library.raw("mnf_last_error")()
+    with pytest.raises(abi.NativeError, match="mnf_site_sweep"):
+        library.call("mnf_site_sweep", None, 1, None, 1, 1, None, None, 0, None, None)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(abi, "_LIBRARY", None)
+    monkeypatch.setattr(build, "LIB_PATH", tmp_path / "nope.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        abi.load()

@@ -1,0 +1,142 @@
+"""Host logic of the engine without a GPU: tracing a model into a site table and lowering it to
+the C-ABI structures (``Plan(..., dry_run=True)`` touches no device)."""
+import pytest
+import torch
+from torch.distributions import Bernoulli, Beta, Gamma, Normal, Poisson
+
+import mininf_b200 as mininf
+from mininf_b200.engine import abi
+from mininf_b200.engine.plan import LatentSpec, Plan
+from mininf_b200.engine.trace import Affine, Dense, LatentRef, LinkTensor, SiteTableTracer
+from oracle import configs
+
+CPU = torch.device("cpu")
+
+
+def trace(model, latents, data):
+    draws, specs, offset = {}, [], 0
+    for name, (family, value) in latents.items():
+        numel = max(value.numel(), 1)
+        ref = LatentRef(name, 0) if numel == 1 else LatentRef(name)
+        draws[name] = LinkTensor.wrap(value, Affine(a_lat=ref))
+        specs.append(LatentSpec(name, family, value.shape, numel, offset))
+        offset += numel
+    with SiteTableTracer() as tracer:
+        mininf.condition(mininf.condition(model, **data), **draws)()
+    return tracer.sites, specs
+
+
+def test_regression_lowers_to_one_dense_site_and_two_priors():
+    config = configs.regression(3000, 64, sigma_latent=True)
+    sites, specs = trace(lambda: config.model(mininf),
+                         {"theta": (abi.NORMAL, torch.randn(64)), "sigma": (abi.GAMMA, torch.tensor(1.3))}, config.data)
+    assert [s.name for s in sites] == ["theta", "sigma", "y"]          # X is under no_log_prob
+    plan = Plan(sites, specs, 64, CPU, dense_mode="auto", dry_run=True)
+    assert plan.D == 65 and len(plan.dense_sites) == 1 and not plan.sweep_groups
+    site, mode = plan.dense_sites[0]
+    assert mode == abi.DENSE_TF32 and site.family == abi.NORMAL and (site.p, site.n_rows) == (64, 3000)
+    assert site.theta_lat == 0 and site.icpt_lat == -1 and site.scale.a_lat == 64 and site.weight == 1.0
+    assert plan.small_global[1] == 2 and plan.small_observed is None
+    assert plan.gpu_launches_per_step == 5
+
+
+def test_shapes_outside_the_tensor_core_kernel_use_fp32_or_raise():
+    config = configs.regression(100, 24)
+    sites, specs = trace(lambda: config.model(mininf), {"theta": (abi.NORMAL, torch.randn(24))}, config.data)
+    assert Plan(sites, specs, 8, CPU, dry_run=True).dense_sites[0][1] == abi.DENSE_FP32
+    with pytest.raises(NotImplementedError, match="p == 64"):
+        Plan(sites, specs, 8, CPU, dense_mode="tf32", dry_run=True)
+
+
+def test_minibatch_weight_and_logits_family():
+    config = configs.logistic(100_000, 500, p=64)
+    sites, specs = trace(lambda: config.model(mininf), {"theta": (abi.NORMAL, torch.randn(64))}, config.data)
+    site, _ = Plan(sites, specs, 16, CPU, dry_run=True).dense_sites[0]
+    assert site.family == abi.BERNOULLI_LOGITS and site.weight == 200.0
+
+
+def test_masked_sites_are_fused_into_one_sweep():
+    config = configs.missing(5000)
+    latents = {k: (abi.NORMAL, torch.randn(())) for k in "abcd"}
+    latents["sigma"] = (abi.GAMMA, torch.tensor(0.7))
+    sites, specs = trace(lambda: config.model(mininf), latents, config.data)
+    plan = Plan(sites, specs, 64, CPU, dry_run=True)
+    assert [len(group) for group in plan.sweep_groups] == [2] and plan.small_global[1] == 5
+    poisson, normal = plan.sweep_groups[0]
+    assert poisson.family == abi.POISSON and poisson.mask and poisson.numel == 5000
+    assert (poisson.param[0].a_lat, poisson.param[0].b_lat, poisson.param[0].transform) == (0, 1, abi.T_EXP)
+    assert (normal.param[0].a_lat, normal.param[0].b_lat, normal.param[0].transform) == (2, 3, abi.T_ID)
+    assert normal.param[1].a_lat == 4 and not normal.param[1].x
+    # the two sites share the covariate buffer's values
+    assert poisson.param[0].x and normal.param[0].x
+
+
+def test_short_sites_go_to_the_small_kernel():
+    config = configs.coin()
+    sites, specs = trace(lambda: config.model(mininf), {"theta": (abi.BETA, torch.tensor(0.6))}, config.data)
+    plan = Plan(sites, specs, 1, CPU, dry_run=True)
+    assert plan.small_observed[1] == 1 and plan.small_global[1] == 1 and not plan.dense_sites
+
+
+def test_link_algebra():
+    a = LinkTensor.wrap(torch.tensor(0.5), Affine(a_lat=LatentRef("a", 0)))
+    b = LinkTensor.wrap(torch.tensor(2.0), Affine(a_lat=LatentRef("b", 0)))
+    theta = LinkTensor.wrap(torch.randn(4), Affine(a_lat=LatentRef("theta")))
+    x = torch.randn(6)
+    X = torch.randn(6, 4)
+    expr = (0.25 + a + b * x)._expr
+    assert (expr.a_const, expr.a_lat.name, expr.b_lat.name, expr.transform) == (0.25, "a", "b", "id")
+    assert torch.equal(expr.x, x)
+    assert (a + b * x).exp()._expr.transform == "exp" and torch.exp(a + x * b)._expr.transform == "exp"
+    dense = (X @ theta + a)._expr
+    assert isinstance(dense, Dense) and dense.theta == "theta" and dense.icpt_lat.name == "a"
+    assert (theta[2] + 1.0)._expr.a_lat == LatentRef("theta", 2)
+    assert (1 * theta)._expr.is_pure_latent
+    # real values ride along, so torch.distributions validates as usual
+    torch.testing.assert_close((a + b * x).unwrap(), 0.5 + 2.0 * x)
+    # outside the closed set: opaque
+    for opaque in (torch.sin(a), a * b, x - a, theta @ X.T @ X[:, 0], 2.0 * theta):
+        assert opaque._expr is None
+
+
+def test_unsupported_models_raise_instead_of_falling_back():
+    x = torch.randn(50)
+    y = torch.randn(50)
+
+    def sine():
+        a = mininf.sample("a", Normal(0, 1))
+        mininf.sample("y", Normal(torch.sin(a * x), 1.0))
+
+    sites, specs = trace(sine, {"a": (abi.NORMAL, torch.tensor(0.1))}, {"y": y})
+    with pytest.raises(NotImplementedError, match="not a supported link"):
+        Plan(sites, specs, 2, CPU, dry_run=True)
+
+    def student():
+        a = mininf.sample("a", Normal(0, 1))
+        mininf.sample("y", torch.distributions.StudentT(3.0, a + 0 * x, 1.0))
+
+    sites, specs = trace(student, {"a": (abi.NORMAL, torch.tensor(0.1))}, {"y": y})
+    with pytest.raises(NotImplementedError, match="StudentT has no CUDA log-density"):
+        Plan(sites, specs, 2, CPU, dry_run=True)
+
+
+def test_tracer_keeps_reference_errors():
+    def model():
+        mininf.sample("a", Normal(0, 1))
+        mininf.sample("y", Normal(0, 1), 5)
+
+    a = LinkTensor.wrap(torch.tensor(0.1), Affine(a_lat=LatentRef("a", 0)))
+    with SiteTableTracer(), pytest.raises(ValueError, match="'y' is missing"):
+        mininf.condition(model, a=a)()
+    with SiteTableTracer(), pytest.raises(ValueError, match="Expected shape"):
+        mininf.condition(model, a=a, y=torch.randn(4))()
+    with SiteTableTracer(), pytest.raises(ValueError, match="is not in the support"):
+        mininf.condition(lambda: mininf.sample("c", Poisson(3.0), 3), c=torch.tensor([1.0, 2.5, 0.0]))()
+    masked = torch.masked.as_masked_tensor(torch.randn(5), torch.rand(5) > 0.5)
+
+    def batched():
+        with mininf.batch(10):
+            mininf.sample("y", Normal(0, 1), 10)
+
+    with SiteTableTracer(), pytest.raises(ValueError, match="not supported for masked data"):
+        mininf.condition(batched, y=masked)()
