@@ -231,11 +231,13 @@ def run_b200(args):
         sampler.start()
     begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
+    torch.cuda.nvtx.range_push("timed")       # lets `ncu --nvtx --nvtx-include timed/` see only these steps
     begin.record()
     for _ in range(args.steps):
         loss = step()
     end.record()
     fence()
+    torch.cuda.nvtx.range_pop()
     clocks = sampler.stop() if rank == 0 else None
     plan.record_sweep_events = False
     elapsed_ms = begin.elapsed_time(end)
