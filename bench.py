@@ -90,7 +90,9 @@ def model_factory(m, n_rows):
 # clocks: sample nvidia-smi during the timed region
 # ---------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+    """`nvidia-smi -lms` in the background from before the warm-up; only samples whose timestamp
+    falls inside the timed region [t0, t1] count (B200_PROFILING.md clocks line)."""
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
 
@@ -104,33 +106,39 @@ class ClockSampler:
             self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "20"], stdout=self.file, stderr=subprocess.DEVNULL)
+                 "-lms", "10"], stdout=self.file, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t0, t1):
+        import datetime
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         self.proc.wait()
         self.file.flush()
         rows = [line.strip().split(", ") for line in open(self.file.name) if line.strip()]
         os.unlink(self.file.name)
-        clocks, reasons, sm_max = [], set(), None
+        inside, everything, reasons, sm_max = [], [], set(), None
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for row in rows:
             try:
-                clocks.append(float(row[0]))
-                sm_max = float(row[1])
+                stamp = datetime.datetime.strptime(row[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clock = float(row[1])
+                sm_max = float(row[2])
             except (ValueError, IndexError):
                 continue
-            for name, flag in zip(names, row[2:6]):
-                if flag.strip().lower().startswith("active"):
-                    reasons.add(name)
-        clocks.sort()
-        median = clocks[len(clocks) // 2] if clocks else None
-        return {"sm_mhz": median, "sm_max_mhz": sm_max, "reasons": sorted(reasons), "samples": len(clocks)}
+            everything.append(clock)
+            if t0 - 0.005 <= stamp <= t1 + 0.005:
+                inside.append(clock)
+                for name, flag in zip(names, row[3:7]):
+                    if flag.strip().lower().startswith("active"):
+                        reasons.add(name)
+        chosen = sorted(inside) if inside else sorted(everything[-5:])
+        median = chosen[len(chosen) // 2] if chosen else None
+        return {"sm_mhz": median, "sm_max_mhz": sm_max, "reasons": sorted(reasons),
+                "samples_in_timed_region": len(inside), "samples_total": len(everything)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -220,17 +228,18 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     fence()
     plan = loss_module.last_plan
     plan.sweep_events.clear()
     plan.record_sweep_events = True
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
+    wall0 = time.time()
     torch.cuda.nvtx.range_push("timed")       # lets `ncu --nvtx --nvtx-include timed/` see only these steps
     begin.record()
     for _ in range(args.steps):
@@ -238,12 +247,13 @@ def run_b200(args):
     end.record()
     fence()
     torch.cuda.nvtx.range_pop()
-    clocks = sampler.stop() if rank == 0 else None
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     plan.record_sweep_events = False
     elapsed_ms = begin.elapsed_time(end)
     kernel_ms = sum(b.elapsed_time(e) for b, e in plan.sweep_events) / max(len(plan.sweep_events), 1)
     loss_module.synchronize()
-    final_loss = float(loss)
+    final_loss = float(loss.detach())
     if distributed:
         t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
