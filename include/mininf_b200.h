@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MNF_ABI_VERSION 4
+#define MNF_ABI_VERSION 5
 
 /* error codes */
 #define MNF_OK 0
@@ -122,6 +122,40 @@ typedef struct mnf_dense_site {
   double weight;        /* batch rescaling (core.py:267-271) */
 } mnf_dense_site_t;
 
+/*
+ * A per-observation ("row") latent matrix Z [n_rows][p] with a mean-field Normal approximation
+ * q(Z) = Normal(loc, scale) and the model sites that touch it
+ * (examples/regression-with-feature-uncertainty.md:28-38, widened to p features):
+ *   prior     Z_ij ~ Normal(prior_loc, prior_scale)            value is the latent itself
+ *   features  X_ij ~ Normal(Z_ij, feat_scale)                  observed, optional
+ *   response  y_i  ~ F(T(icpt + Z_i . beta))                   observed, optional; F = Poisson (T = exp),
+ *                                                              Normal (T = id) or Bernoulli logits
+ * Z is never materialised: particle s draws eps_ij from Philox4x32-10 (key = seed, counter =
+ * (offset, i*p + j, s/4)) unless `eps` supplies it ([S][n_rows][p], parity tests). The kernel
+ * writes d loss/d loc and d loss/d scale (entropy term included, mean over particles) and adds
+ * the sites' log-densities, the entropy of q(Z) and the gradients w.r.t. global latents to acc.
+ */
+typedef struct mnf_rowlatent {
+  int64_t n_rows;
+  int32_t p;               /* features per row, 1..32 in this build */
+  int32_t resp_family;     /* MNF_POISSON | MNF_NORMAL | MNF_BERNOULLI_LOGITS, or -1 for none */
+  const float* loc;        /* [n_rows][p] */
+  const float* scale;      /* [n_rows][p], positive */
+  float* grad_loc;         /* out [n_rows][p] */
+  float* grad_scale;       /* out [n_rows][p] */
+  const float* eps;        /* optional external noise [S][n_rows][p] */
+  mnf_link_t prior_loc;    /* scalar links (x == NULL): constant or scalar latent */
+  mnf_link_t prior_scale;
+  const float* feat;       /* observed features [n_rows][p] or NULL */
+  mnf_link_t feat_scale;
+  const float* resp;       /* observed response [n_rows] or NULL */
+  int32_t beta_lat;        /* column of beta[0] in z */
+  int32_t icpt_lat;        /* scalar latent intercept column or -1 */
+  float icpt_const;
+  int32_t resp_transform;  /* MNF_T_* applied to icpt + Z.beta */
+  mnf_link_t resp_scale;   /* Normal response only */
+} mnf_rowlatent_t;
+
 /* precision modes of the dense sweep */
 #define MNF_DENSE_FP32 0   /* SIMT fp32 FMA, any p / S                                          */
 #define MNF_DENSE_TF32 1   /* tcgen05 kind::tf32, operands rounded-to-nearest to TF32 in-kernel, */
@@ -196,6 +230,15 @@ int mnf_small_sites(const mnf_site_t* sites_dev, int n_sites, int64_t max_numel,
 int mnf_finalize(const mnf_latent_t* latents_dev, int n_latents, int n_particles,
                  int n_latent_total, const float* z, const float* noise, const double* acc,
                  int with_entropy, float* out, uint32_t* status, void* stream);
+
+/*
+ * Row-latent sweep (see mnf_rowlatent_t): one pass over loc / scale / features / response for all
+ * particles; `entropy_weight` (1 or 0) switches the entropy of q(Z) on.
+ */
+int mnf_rowlatent_sweep(const mnf_rowlatent_t* desc, const float* z, int n_particles,
+                        int n_latent_total, uint64_t seed, uint64_t offset, int with_entropy,
+                        double* acc, void* workspace, size_t workspace_bytes, uint32_t* status,
+                        void* stream);
 
 /* Counting scan used by the integer-exact parity checks: out[0]=sum(mask), out[1]=sum(mask*value)
  * as int64 (value must hold integers); mask may be NULL (all ones). */

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "dense_simt.cuh"
 #include "dense_tc.cuh"
+#include "rowlatent.cuh"
 #include "site_sweep.cuh"
 #include "small.cuh"
 
@@ -135,6 +136,22 @@ int launch_site_sweep(const mnf_site_t* sites, const float* z, int S, int D, flo
 }
 
 bool family_has_two_params(int family) { return family <= MNF_BETA; }
+
+bool host_link_has_latent(const mnf_link_t& L) { return L.a_lat >= 0 || L.b_lat >= 0; }
+
+template <int SP>
+int launch_rowlatent(const mnf_rowlatent_t& d, const float* z, int S, int D, int s_begin,
+                            int first_pass, uint64_t seed, uint64_t offset, int with_entropy,
+                            float* partial, uint32_t* status, int grid, cudaStream_t stream) {
+  auto kernel = rowlatent_kernel<SP>;
+  const size_t smem = rowlatent_smem_bytes<SP>();
+  MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kernel<<<grid, kRowThreads, smem, stream>>>(d, z, S, D, s_begin, first_pass, seed, offset,
+                                               with_entropy, partial, status);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
 
 }  // namespace
 
@@ -307,6 +324,62 @@ int mnf_site_sweep(const mnf_site_t* sites, int n_sites, const float* z, int n_p
     map.scalar_lat[4 * i + 2] = two ? sites[i].param[1].a_lat : -1;
     map.scalar_lat[4 * i + 3] = two ? sites[i].param[1].b_lat : -1;
   }
+  return launch_reduce(partial, grid, S, ncol, map, 1.0, D, acc, stream);
+}
+
+int mnf_rowlatent_sweep(const mnf_rowlatent_t* desc, const float* z, int n_particles,
+                        int n_latent_total, uint64_t seed, uint64_t offset, int with_entropy,
+                        double* acc, void* workspace, size_t workspace_bytes, uint32_t* status,
+                        void* stream_) {
+  if (!desc || !z || !acc || !workspace || !status)
+    return fail(MNF_E_INVALID, "mnf_rowlatent_sweep: null pointer%s%s");
+  const mnf_rowlatent_t d = *desc;
+  const int S = n_particles, D = n_latent_total;
+  if (!d.loc || !d.scale || !d.grad_loc || !d.grad_scale || d.n_rows < 0 || S <= 0)
+    return fail(MNF_E_INVALID, "mnf_rowlatent_sweep: bad descriptor%s%s");
+  if (d.p < 1 || d.p > 32)
+    return fail(MNF_E_UNSUPPORTED, "mnf_rowlatent_sweep: 1..32 features per row in this build%s%s");
+  if (host_link_has_latent(d.prior_loc) || d.prior_loc.x || d.prior_scale.x || d.prior_scale.b_lat >= 0 ||
+      (d.feat && (host_link_has_latent(d.feat_scale) || d.feat_scale.x)))
+    return fail(MNF_E_UNSUPPORTED,
+                "mnf_rowlatent_sweep: prior location and feature scale must be constants, the prior "
+                "scale a constant or scalar latent%s%s");
+  if (d.resp) {
+    if (d.resp_family != MNF_POISSON && d.resp_family != MNF_NORMAL && d.resp_family != MNF_BERNOULLI_LOGITS)
+      return fail(MNF_E_UNSUPPORTED, "mnf_rowlatent_sweep: response family%s%s");
+    if (d.beta_lat < 0 || d.beta_lat + d.p > D || d.icpt_lat >= D)
+      return fail(MNF_E_INVALID, "mnf_rowlatent_sweep: latent columns out of range%s%s");
+  }
+  if (d.n_rows == 0) return MNF_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DeviceCache* c;
+  if (int rc = device_cache(-1, &c)) return rc;
+  const int ncol = 1 + d.p + 5;
+  const int grid = (int)std::min<int64_t>((d.n_rows + kRowWarps - 1) / kRowWarps, 2 * c->sm_count);
+  if ((size_t)grid * S * ncol * sizeof(float) > workspace_bytes)
+    return fail(MNF_E_INVALID, "mnf_rowlatent_sweep: workspace too small%s%s");
+  float* partial = static_cast<float*>(workspace);
+  const int sp = S <= 4 ? 4 : (S <= 8 ? 8 : (S <= 16 ? 16 : 32));
+  for (int s_begin = 0, pass = 0; s_begin < S; s_begin += sp, ++pass) {
+    int rc;
+    if (sp == 4) rc = launch_rowlatent<4>(d, z, S, D, s_begin, pass == 0, seed, offset, with_entropy, partial, status, grid, stream);
+    else if (sp == 8) rc = launch_rowlatent<8>(d, z, S, D, s_begin, pass == 0, seed, offset, with_entropy, partial, status, grid, stream);
+    else if (sp == 16) rc = launch_rowlatent<16>(d, z, S, D, s_begin, pass == 0, seed, offset, with_entropy, partial, status, grid, stream);
+    else rc = launch_rowlatent<32>(d, z, S, D, s_begin, pass == 0, seed, offset, with_entropy, partial, status, grid, stream);
+    if (rc) return rc;
+  }
+  // physical partial layout: 0 log-density, 1..p beta gradient (zeros without a response), then
+  // intercept, prior location, prior scale, feature scale, response scale
+  ColMap map;
+  map.n_vec = d.p;
+  map.vec_lat = d.resp ? d.beta_lat : 0;
+  map.n_scalar = 5;
+  for (int i = 0; i < 16; ++i) map.scalar_lat[i] = -1;
+  map.scalar_lat[0] = d.resp ? d.icpt_lat : -1;
+  map.scalar_lat[1] = -1;                     // prior location: constant
+  map.scalar_lat[2] = d.prior_scale.a_lat;
+  map.scalar_lat[3] = -1;                     // feature scale: constant
+  map.scalar_lat[4] = (d.resp && d.resp_family == MNF_NORMAL) ? d.resp_scale.a_lat : -1;
   return launch_reduce(partial, grid, S, ncol, map, 1.0, D, acc, stream);
 }
 

@@ -11,7 +11,7 @@ from pathlib import Path
 
 from . import build as _build
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # families (include/mininf_b200.h)
 NORMAL, GAMMA, BETA, BERNOULLI_PROBS, BERNOULLI_LOGITS, POISSON = range(6)
@@ -59,6 +59,17 @@ class DenseSite(C.Structure):
     ]
 
 
+class RowLatent(C.Structure):
+    _fields_ = [
+        ("n_rows", C.c_int64), ("p", C.c_int32), ("resp_family", C.c_int32),
+        ("loc", C.c_void_p), ("scale", C.c_void_p), ("grad_loc", C.c_void_p), ("grad_scale", C.c_void_p),
+        ("eps", C.c_void_p), ("prior_loc", Link), ("prior_scale", Link),
+        ("feat", C.c_void_p), ("feat_scale", Link), ("resp", C.c_void_p),
+        ("beta_lat", C.c_int32), ("icpt_lat", C.c_int32), ("icpt_const", C.c_float),
+        ("resp_transform", C.c_int32), ("resp_scale", Link),
+    ]
+
+
 class DeviceInfo(C.Structure):
     _fields_ = [
         ("sm_count", C.c_int32), ("cc_major", C.c_int32), ("cc_minor", C.c_int32),
@@ -83,6 +94,9 @@ EXPORTS = {
                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "mnf_site_sweep": (C.c_int, [C.POINTER(Site), C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "mnf_rowlatent_sweep": (C.c_int, [C.POINTER(RowLatent), C.c_void_p, C.c_int, C.c_int, C.c_uint64,
+                                      C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                      C.c_void_p, C.c_void_p]),
     "mnf_small_sites": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "mnf_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -15,10 +15,11 @@ import torch
 from torch import distributions as td
 
 from . import abi
-from .trace import Affine, Dense, LatentRef, LinkTensor, SiteRecord
+from .trace import Affine, Dense, LatentRef, LinkTensor, RowDot, SiteRecord
 from ..util import is_masked
 
 BIG_SITE = 2048          # observed sites at least this long go through the fused site sweep
+ROW_LATENT = 8192        # Normal latent sites with more elements are per-observation ("row") latents
 
 _LATENT_FAMILIES = {td.Normal: abi.NORMAL, td.Gamma: abi.GAMMA, td.Beta: abi.BETA}
 
@@ -42,7 +43,22 @@ class LatentSpec:
     family: int
     shape: torch.Size
     numel: int
-    offset: int
+    offset: int          # first column in the packed z / noise; -1 for row latents
+    row_latent: bool = False
+
+
+def assign_offsets(entries: Sequence[Tuple[str, int, torch.Size]]) -> List[LatentSpec]:
+    """Latent specs for (name, family, shape) triples: small sites are packed into z[S][D] in
+    order; large Normal sites become row latents that are never materialised."""
+    specs, offset = [], 0
+    for name, family, shape in entries:
+        numel = max(shape.numel(), 1)
+        if numel > ROW_LATENT and family == abi.NORMAL and len(shape) in (1, 2):
+            specs.append(LatentSpec(name, family, shape, numel, -1, True))
+        else:
+            specs.append(LatentSpec(name, family, shape, numel, offset))
+            offset += numel
+    return specs
 
 
 def _bytes_to_device(struct_array: Any, device: torch.device) -> torch.Tensor:
@@ -71,8 +87,10 @@ class Plan:
         self.lib = abi.load()
         self.device = device
         self.S = int(n_particles)
-        self.latents = list(latents)
-        self.by_name = {spec.name: spec for spec in self.latents}
+        self.all_latents = list(latents)
+        self.latents = [spec for spec in latents if not spec.row_latent]     # packed into z[S][D]
+        self.row_latents = [spec for spec in latents if spec.row_latent]
+        self.by_name = {spec.name: spec for spec in self.all_latents}
         self.D = sum(spec.numel for spec in self.latents)
         if self.S < 1 or self.D < 1:
             raise ValueError("need at least one particle and one latent element")
@@ -95,7 +113,8 @@ class Plan:
             self.workspace = torch.empty(0, device=device, dtype=torch.uint8)
         else:
             with torch.cuda.device(device):
-                self.workspace_bytes = max(self.lib.workspace_bytes(S, D), 1 << 20)
+                widest = max([D] + [spec.numel // spec.shape[0] + 3 for spec in self.row_latents])
+                self.workspace_bytes = max(self.lib.workspace_bytes(S, widest), 1 << 20)
             self.workspace = torch.empty(self.workspace_bytes, device=device, dtype=torch.uint8)
 
         table = (abi.Latent * len(self.latents))()
@@ -108,6 +127,19 @@ class Plan:
         # optional instrumentation: CUDA event pairs around every dense sweep (bench.py roofline)
         self.record_sweep_events = False
         self.sweep_events: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
+
+        # one descriptor per row latent, filled in by the sites that touch it
+        self.row_groups: Dict[str, abi.RowLatent] = {}
+        for spec in self.row_latents:
+            n_rows = spec.shape[0]
+            desc = abi.RowLatent(n_rows=n_rows, p=spec.numel // n_rows, resp_family=-1, beta_lat=-1,
+                                 icpt_lat=-1, icpt_const=0.0, resp_transform=abi.T_ID)
+            desc.prior_loc = abi.const_link(0.0)
+            desc.prior_scale = abi.const_link(1.0)
+            desc.feat_scale = abi.const_link(1.0)
+            desc.resp_scale = abi.const_link(1.0)
+            desc._has_prior = False
+            self.row_groups[spec.name] = desc
 
         self.dense_sites: List[Tuple[abi.DenseSite, int]] = []
         self.sweep_groups: List[Any] = []
@@ -123,6 +155,9 @@ class Plan:
                 self.sweep_groups.append(array)
         self.small_observed = self._site_table(small_observed)
         self.small_global = self._site_table(small_global)
+        for name, desc in self.row_groups.items():
+            if not desc._has_prior:
+                raise NotImplementedError(f"row latent '{name}' has no prior site in the model")
 
     # ------------------------------------------------------------------------------------------
     # lowering
@@ -139,6 +174,10 @@ class Plan:
         if spec is None:
             raise NotImplementedError(f"{what} depends on '{ref.name}', which the approximation "
                                       "does not provide")
+        if spec.row_latent:
+            raise NotImplementedError(f"{what}: per-observation latent '{ref.name}' is only supported "
+                                      "as a site value, as the location of an observed Normal site or "
+                                      "in `Z @ beta`")
         if ref.is_scalar:
             return spec.offset + ref.index, 0
         if spec.numel == 1:
@@ -204,6 +243,9 @@ class Plan:
         if dist.event_shape:
             raise NotImplementedError(f"{what}: event-shaped distributions are not supported")
 
+        if self._lower_row_latent(record, family, params, what):
+            return
+
         # value: a latent itself (prior site) or observed data (possibly masked)
         mask = None
         value_lat = -1
@@ -247,6 +289,75 @@ class Plan:
             big.setdefault(numel, []).append(site)
         else:
             small_observed.append(site)
+
+    def _scalar_link(self, param: Any, what: str) -> abi.Link:
+        link = self._link(param, torch.Size([1]), what)
+        if link.x or link.b_lat >= 0 or link.a_stride:
+            raise NotImplementedError(f"{what}: expected a constant or a scalar latent")
+        return link
+
+    def _lower_row_latent(self, record: SiteRecord, family: int, params: Tuple[Any, ...], what: str) -> bool:
+        """Sites touching a per-observation latent go into that latent's row-latent descriptor."""
+        value = record.value
+
+        def row_spec(tensor: Any) -> Optional[LatentSpec]:
+            expr = getattr(tensor, "_expr", None) if isinstance(tensor, LinkTensor) else None
+            if isinstance(expr, Affine) and expr.is_pure_latent and not expr.a_lat.is_scalar:
+                spec = self.by_name.get(expr.a_lat.name)
+                if spec is not None and spec.row_latent:
+                    return spec
+            return None
+
+        spec = row_spec(value)
+        if spec is not None:                                   # prior: Z ~ Normal(const, const | latent)
+            if family != abi.NORMAL or record.scale != 1.0:
+                raise NotImplementedError(f"{what}: row latents need an unbatched Normal prior")
+            desc = self.row_groups[spec.name]
+            desc.prior_loc = self._scalar_link(params[0], what)
+            desc.prior_scale = self._scalar_link(params[1], what)
+            if desc.prior_loc.a_lat >= 0:
+                raise NotImplementedError(f"{what}: the prior location of a row latent must be constant")
+            desc._has_prior = True
+            return True
+        first = params[0]
+        spec = row_spec(first)
+        if spec is not None:                                   # features: X ~ Normal(Z, const)
+            if family != abi.NORMAL or isinstance(value, LinkTensor) or is_masked(value) or \
+                    record.scale != 1.0 or value.numel() != spec.numel:
+                raise NotImplementedError(f"{what}: only an unmasked Normal(loc=Z, scale=const) site can "
+                                          "observe a row latent element-wise")
+            desc = self.row_groups[spec.name]
+            data = _f32(value, self.device)
+            self.keepalive.append(data)
+            desc.feat = data.data_ptr()
+            desc.feat_scale = self._scalar_link(params[1], what)
+            if desc.feat_scale.a_lat >= 0:
+                raise NotImplementedError(f"{what}: the feature scale must be a constant")
+            return True
+        expr = getattr(first, "_expr", None) if isinstance(first, LinkTensor) else None
+        if isinstance(expr, RowDot):                           # response: y ~ F(T(icpt + Z @ beta))
+            spec = self.by_name[expr.Z]
+            beta = self.by_name.get(expr.beta)
+            if not spec.row_latent or beta is None or beta.row_latent or isinstance(value, LinkTensor) or \
+                    is_masked(value) or record.scale != 1.0:
+                raise NotImplementedError(f"{what}: unsupported `Z @ beta` site")
+            desc = self.row_groups[spec.name]
+            if beta.numel != desc.p or value.numel() != desc.n_rows:
+                raise NotImplementedError(f"{what}: shapes of Z, beta and the response do not match")
+            ok = (family == abi.POISSON) or (family in (abi.NORMAL, abi.BERNOULLI_LOGITS) and expr.transform == "id")
+            if not ok:
+                raise NotImplementedError(f"{what}: `Z @ beta` supports Poisson, Normal(loc) and Bernoulli(logits)")
+            data = _f32(value, self.device)
+            self.keepalive.append(data)
+            desc.resp, desc.resp_family = data.data_ptr(), family
+            desc.resp_transform = abi.T_EXP if expr.transform == "exp" else abi.T_ID
+            desc.beta_lat, desc.icpt_const = beta.offset, expr.icpt_const
+            if expr.icpt_lat is not None:
+                desc.icpt_lat, _ = self._latent_column(expr.icpt_lat, 1, what)
+            if family == abi.NORMAL:
+                desc.resp_scale = self._scalar_link(params[1], what)
+            return True
+        return False
 
     def _lower_dense(self, record: SiteRecord, family: int, params: Tuple[Any, ...],
                      data_ptr: Optional[int], mask: Optional[torch.Tensor], numel: int,
@@ -303,6 +414,7 @@ class Plan:
         """Kernels of this library launched by one :meth:`step` (sweeps come with a reduction)."""
         count = 2  # rsample + finalize
         count += 2 * (len(self.dense_sites) + len(self.sweep_groups))
+        count += sum(1 + -(-self.S // 32) for _ in self.row_groups)
         count += (self.small_observed is not None) + (self.small_global is not None)
         return count
 
@@ -340,6 +452,10 @@ class Plan:
             table, count, longest = self.small_observed
             lib.call("mnf_small_sites", table.data_ptr(), count, longest, self.z.data_ptr(), S, D,
                      self.acc.data_ptr(), status, stream)
+        for name, desc in self.row_groups.items():
+            lib.call("mnf_rowlatent_sweep", C.byref(desc), self.z.data_ptr(), S, D, seed, offset,
+                     int(with_entropy), self.acc.data_ptr(), self.workspace.data_ptr(),
+                     self.workspace_bytes, status, stream)
         if reduce_fn is not None:
             reduce_fn(self.acc)   # observed sites are row shards: sum the partial accumulators
         if self.small_global is not None:

@@ -10,7 +10,8 @@ forms is what the CUDA kernels implement (include/mininf_b200.h):
 
 * ``Affine``:  ``T(a_const + a_lat + (b_const + b_lat) * x)`` - constants, data tensors, a latent
   itself, ``c + d*x``, ``exp(a + b*x)``;
-* ``Dense``:   ``T(icpt + X @ theta)`` - ``X @ theta`` with an optional scalar intercept.
+* ``Dense``:   ``T(icpt + X @ theta)`` - ``X @ theta`` with an optional scalar intercept;
+* ``RowDot``:  ``T(icpt + Z @ beta)`` - a per-observation latent matrix times a latent vector.
 
 Anything else makes the tensor *opaque*; an opaque tensor reaching a distribution parameter of a
 site that contributes to the log-density raises ``NotImplementedError`` (no fallback).
@@ -72,7 +73,18 @@ class Dense:
     transform: str = "id"
 
 
-Expr = Any  # Affine | Dense | None (opaque)
+@dataclasses.dataclass
+class RowDot:
+    """``T(icpt + Z @ beta)`` with Z a per-observation latent matrix [n, p] and beta a latent
+    vector [p] (examples/regression-with-feature-uncertainty.md:38 widened to p features)."""
+    Z: str
+    beta: str
+    icpt_const: float = 0.0
+    icpt_lat: Optional[LatentRef] = None
+    transform: str = "id"
+
+
+Expr = Any  # Affine | Dense | RowDot | None (opaque)
 
 
 def _as_const(value: Any) -> Optional[float]:
@@ -153,7 +165,7 @@ def _shape_rule(source: LinkTensor, raw: torch.Tensor, reshaper=None) -> Expr:
     if expr is None:
         return None
     same_numel = raw.numel() == source.numel()
-    if isinstance(expr, Dense):
+    if isinstance(expr, (Dense, RowDot)):
         return expr if same_numel and raw.ndim == 1 else None
     whole = [ref for ref in (expr.a_lat, expr.b_lat) if ref is not None and not ref.is_scalar]
     if whole and not same_numel:
@@ -188,9 +200,9 @@ def _combine_add(left: Expr, right: Expr, shape: torch.Size) -> Expr:
     """left + right for two expressions."""
     if left is None or right is None:
         return None
-    if isinstance(right, Dense):
+    if isinstance(right, (Dense, RowDot)):
         left, right = right, left
-    if isinstance(left, Dense):
+    if isinstance(left, (Dense, RowDot)):
         if not isinstance(right, Affine) or right.has_x_term or right.transform != "id" or \
                 left.transform != "id":
             return None
@@ -243,10 +255,9 @@ def _rule_mul(args, kwargs, raw):
     expr = _expr_of(left)
     if expr is None or isinstance(right, LinkTensor):
         return None
-    const = _as_const(right)
-    if const is not None:
+    if isinstance(right, numbers.Number):
         # `1 * x` is how ParameterizedDistribution hides raw parameters (mininf/nn.py:92-94)
-        return _shape_rule(left, raw) if const == 1.0 else None
+        return _shape_rule(left, raw) if float(right) == 1.0 else None
     if isinstance(expr, Affine) and expr.is_pure_latent and _plain(right):
         if not expr.a_lat.is_scalar and left.numel() != raw.numel():
             return None
@@ -266,11 +277,17 @@ def _rule_exp(args, kwargs, raw):
 def _rule_matmul(args, kwargs, raw):
     X, theta = args[0], args[1]
     expr = _expr_of(theta)
-    if not _plain(X) or X.ndim != 2 or not isinstance(expr, Affine) or not expr.is_pure_latent:
+    if not isinstance(expr, Affine) or not expr.is_pure_latent or theta.ndim != 1:
         return None
-    if expr.a_lat.is_scalar or theta.ndim != 1:
-        return None
-    return Dense(X=X, theta=expr.a_lat.name)
+    if expr.a_lat.is_scalar and not (theta.numel() == 1 and expr.a_lat.index == 0):
+        return None                       # one-element latents are referenced as scalars
+    if _plain(X) and X.ndim == 2:
+        return Dense(X=X, theta=expr.a_lat.name)
+    left = _expr_of(X)
+    if isinstance(X, LinkTensor) and X.ndim == 2 and isinstance(left, Affine) and left.is_pure_latent \
+            and not left.a_lat.is_scalar:
+        return RowDot(Z=left.a_lat.name, beta=expr.a_lat.name)
+    return None
 
 
 def _rule_getitem(args, kwargs, raw):

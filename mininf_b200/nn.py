@@ -126,15 +126,28 @@ class _EngineFunction(torch.autograd.Function):
     """One fused forward+backward evaluation; inputs are the constrained parameter tensors."""
 
     @staticmethod
-    def forward(ctx, loss_module, plan, noise, seed, offset, reduce_fn, with_entropy, *params):
+    def forward(ctx, loss_module, plan, noise, row_noise, seed, offset, reduce_fn, with_entropy, *params):
         with torch.no_grad():
-            for spec, p0, p1 in zip(plan.latents, params[0::2], params[1::2]):
-                lo, hi = spec.offset, spec.offset + spec.numel
-                plan.P0[lo:hi].copy_(p0.reshape(-1))
-                plan.P1[lo:hi].copy_(p1.reshape(-1))
+            big_grads = []
+            for spec, p0, p1 in zip(plan.all_latents, params[0::2], params[1::2]):
+                if spec.row_latent:
+                    # row latents are read in place; their gradients are written by the kernel
+                    loc, scale = p0.contiguous(), p1.contiguous()
+                    g_loc, g_scale = torch.empty_like(loc), torch.empty_like(scale)
+                    desc = plan.row_groups[spec.name]
+                    desc.loc, desc.scale = loc.data_ptr(), scale.data_ptr()
+                    desc.grad_loc, desc.grad_scale = g_loc.data_ptr(), g_scale.data_ptr()
+                    given = row_noise.get(spec.name) if row_noise else None
+                    desc.eps = given.data_ptr() if given is not None else None
+                    big_grads += [loc, scale, g_loc, g_scale]
+                else:
+                    lo, hi = spec.offset, spec.offset + spec.numel
+                    plan.P0[lo:hi].copy_(p0.reshape(-1))
+                    plan.P1[lo:hi].copy_(p1.reshape(-1))
             out = plan.step(noise, seed, offset, with_entropy=with_entropy, reduce_fn=reduce_fn)
             saved = out.clone()
         ctx.plan = plan
+        ctx.big_grads = big_grads
         ctx.save_for_backward(saved)
         loss_module._schedule_status_check(plan)
         return saved[0].clone()
@@ -143,8 +156,14 @@ class _EngineFunction(torch.autograd.Function):
     def backward(ctx, grad_output):
         (saved,) = ctx.saved_tensors
         plan = ctx.plan
-        grads: List[Optional[torch.Tensor]] = [None] * 7
-        for spec in plan.latents:
+        grads: List[Optional[torch.Tensor]] = [None] * 8
+        big = iter(ctx.big_grads)
+        for spec in plan.all_latents:
+            if spec.row_latent:
+                _, _, g_loc, g_scale = next(big), next(big), next(big), next(big)
+                grads.append(g_loc.reshape(spec.shape) * grad_output)
+                grads.append(g_scale.reshape(spec.shape) * grad_output)
+                continue
             lo, hi = 1 + spec.offset, 1 + spec.offset + spec.numel
             grads.append((saved[lo:hi] * grad_output).reshape(spec.shape))
             grads.append((saved[plan.D + lo:plan.D + hi] * grad_output).reshape(spec.shape))
@@ -220,12 +239,11 @@ class EvidenceLowerBoundLoss(nn.Module):
     # -- tracing ----------------------------------------------------------------------------
     def _build_plan(self, model: Callable, approximation: DistributionDict) -> Any:
         from .engine import abi
-        from .engine.plan import LatentSpec, Plan, latent_parameters
+        from .engine.plan import Plan, assign_offsets, latent_parameters
         from .engine.trace import Affine, LatentRef, LinkTensor, SiteTableTracer
 
-        specs: List[LatentSpec] = []
+        entries = []
         draws: Dict[str, torch.Tensor] = {}
-        offset = 0
         device = None
         for name, factor in approximation.items():
             family, p0, _ = latent_parameters(factor)
@@ -233,8 +251,7 @@ class EvidenceLowerBoundLoss(nn.Module):
                 raise NotImplementedError("event-shaped approximations are not supported")
             shape = factor.batch_shape
             numel = max(shape.numel(), 1)
-            specs.append(LatentSpec(name, family, shape, numel, offset))
-            offset += numel
+            entries.append((name, family, shape))
             device = device or p0.device
             with torch.no_grad():
                 draw = factor.sample()
@@ -248,11 +265,9 @@ class EvidenceLowerBoundLoss(nn.Module):
                                "no CPU fallback); got approximation parameters on " + str(device))
         with SiteTableTracer() as tracer:
             condition(model, **draws)()
-        missing = {spec.name for spec in specs} - {site.name for site in tracer.sites}
-        # latent draws the model never scored still take part in the entropy term; that mirrors
+        # latent draws the model never scores still take part in the entropy term; that mirrors
         # the reference, where `condition` silently accepts unused names
-        del missing
-        return Plan(tracer.sites, specs, self.n_particles, device,
+        return Plan(tracer.sites, assign_offsets(entries), self.n_particles, device,
                     dense_mode=self.dense_precision)
 
     def _plan_for(self, model: Callable, approximation: DistributionDict) -> Any:
@@ -313,12 +328,15 @@ class EvidenceLowerBoundLoss(nn.Module):
         self.last_plan = plan
         from .engine.plan import latent_parameters
         params: List[torch.Tensor] = []
-        for spec in plan.latents:
+        for spec in plan.all_latents:
             _, p0, p1 = latent_parameters(approximation[spec.name])
             shape = spec.shape if len(spec.shape) else torch.Size([])
             params.append(p0.to(torch.float32).expand(shape))
             params.append(p1.to(torch.float32).expand(shape))
         noise = self._noise(plan, approximation, _noise)
+        # external noise of row latents [S, n, p] (parity tests); otherwise in-kernel Philox
+        row_noise = {spec.name: _noise[spec.name].to(plan.device, torch.float32).contiguous()
+                     for spec in plan.row_latents if _noise is not None and spec.name in _noise}
         seed = torch.cuda.default_generators[plan.device.index or 0].initial_seed() \
             if plan.device.index is not None else torch.cuda.initial_seed()
         self._calls += 1
@@ -327,7 +345,7 @@ class EvidenceLowerBoundLoss(nn.Module):
             import torch.distributed as dist
             group = None if self.process_group is True else self.process_group
             reduce_fn = lambda acc: dist.all_reduce(acc, group=group)  # noqa: E731
-        return _EngineFunction.apply(self, plan, noise, int(seed) & (2 ** 63 - 1), self._calls,
+        return _EngineFunction.apply(self, plan, noise, row_noise, int(seed) & (2 ** 63 - 1), self._calls,
                                      reduce_fn, True, *params)
 
 

@@ -10,6 +10,7 @@ Model sources in the reference:
   regression   tests/test_mininf.py:7-12 / examples/minibatch.md:24-33 (with ``no_log_prob`` X)
   logistic     examples/minibatch.md:24-33 with a Bernoulli(logits) likelihood under ``batch``
   missing      examples/missing-observations.md:131 (masked conditioning), Poisson + Normal sites
+  features     examples/regression-with-feature-uncertainty.md:28-38 widened to p features
 """
 from __future__ import annotations
 
@@ -196,3 +197,40 @@ def missing(n: int, device: Any = "cpu", seed0: int = 5000, missing_fraction: fl
                                 for k in "abcd"}
     families["sigma"] = (Gamma, {"concentration": torch.tensor(2.0), "rate": torch.tensor(2.0)})
     return Config("missing", model, data, families, {"raw": raw, "n": n})
+
+
+# ---------------------------------------------------------------------------------------------
+# C4: regression with feature uncertainty (per-observation latent features)
+# ---------------------------------------------------------------------------------------------
+def feature_uncertainty(n: int, p: int = 32, device: Any = "cpu", seed0: int = 4000,
+                        rows: Tuple[int, int] | None = None, gen_device: Any = None) -> Config:
+    target, device = device, gen_device or device
+    noise_scale = 0.5
+    g = torch.Generator(device=device)
+    g.manual_seed(seed0 - 1)
+    slope_true = torch.randn(p, generator=g, device=device) / p ** 0.5
+
+    def fill(count: int, generator: torch.Generator) -> Dict[str, torch.Tensor]:
+        z = torch.randn(count, p, generator=generator, device=device)
+        x = z + noise_scale * torch.randn(count, p, generator=generator, device=device)
+        y = torch.poisson(torch.exp(0.5 + z @ slope_true), generator=generator)
+        return {"x": x, "y": y}
+
+    data = {k: v.to(target) for k, v in _chunked(n, seed0, device, fill, rows).items()}
+    n_local = data["x"].shape[0]
+
+    def model(m: Any) -> None:
+        population_scale = m.sample("population_scale", Gamma(2, 2))
+        z = m.sample("z", Normal(0, population_scale), (n_local, p))
+        m.sample("x", Normal(z, noise_scale))
+        intercept = m.sample("intercept", Normal(0, 1))
+        slope = m.sample("slope", Normal(0, 1), p)
+        m.sample("y", Poisson((intercept + z @ slope).exp()))
+
+    families: Dict[str, Any] = {
+        "population_scale": (Gamma, {"concentration": torch.tensor(2.0), "rate": torch.tensor(2.0)}),
+        "z": (Normal, {"loc": data["x"].detach().cpu().clone(), "scale": torch.ones(n_local, p)}),
+        "intercept": (Normal, {"loc": torch.tensor(0.1), "scale": torch.tensor(0.2)}),
+        "slope": (Normal, {"loc": torch.zeros(p), "scale": 0.2 * torch.ones(p)}),
+    }
+    return Config("features", model, data, families, {"n": n, "p": p, "slope_true": slope_true.to(target)})

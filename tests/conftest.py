@@ -35,6 +35,7 @@ GOLDEN_CASES = {
     "regression_ragged": lambda cfgs, **kw: cfgs.regression(301, 24, sigma_latent=True, **kw),
     "logistic": lambda cfgs, **kw: cfgs.logistic(20000, 400, p=32, **kw),
     "missing": lambda cfgs, **kw: cfgs.missing(600, **kw),
+    "features": lambda cfgs, **kw: cfgs.feature_uncertainty(300, 32, **kw),
 }
 
 

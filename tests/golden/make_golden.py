@@ -72,6 +72,7 @@ CASES = {
     "regression_ragged": (lambda: configs.regression(301, 24, sigma_latent=True), 3),
     "logistic": (lambda: configs.logistic(20000, 400, p=32), 2),
     "missing": (lambda: configs.missing(600), 4),
+    "features": (lambda: configs.feature_uncertainty(300, 32), 2),
 }
 
 

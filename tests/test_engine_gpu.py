@@ -118,6 +118,49 @@ def test_missing_observations_against_oracle(n, S):
         np.testing.assert_allclose(leaf.grad.cpu().numpy(), leaves_c[key].grad.numpy(), rtol=2e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("n,p,S", [(300, 32, 1), (2000, 8, 5), (520, 17, 64), (9000, 1, 3)])
+def test_feature_uncertainty_against_oracle(n, p, S):
+    """Config C4: per-observation latent features (row-latent kernel), external noise for parity:
+    1-, 8- and 64-particle template instances (two passes at S = 64), p below the warp width."""
+    torch.manual_seed(n + p)
+    cpu = configs.feature_uncertainty(n, p)
+    gpu = configs.feature_uncertainty(n, p, device=DEV, gen_device="cpu")
+    approx_c, leaves_c = cpu.approximation()
+    noise = {name: elbo.draw_noise(dist, S) for name, dist in approx_c.items()}
+    expected = elbo.neg_elbo(cpu.model, cpu.data, approx_c, noise, S)
+    expected.backward()
+    loss, leaves, module = engine_eval(gpu, {k: v.to(DEV) for k, v in noise.items()}, S)
+    assert list(module.last_plan.row_groups) == ["z"] and module.last_plan.D == 2 + p
+    assert abs(float(loss) - float(expected)) <= 1e-5 * abs(float(expected))
+    for key, leaf in leaves.items():
+        assert rel(leaf.grad.cpu().numpy(), leaves_c[key].grad.numpy()) < 2e-4, key
+
+
+def test_feature_uncertainty_philox_draws():
+    """Without external noise the row latents draw in-kernel (Philox): the Monte Carlo estimate
+    must agree with a large-sample oracle estimate and be reproducible under the same seed."""
+    n, p, S = 4000, 16, 64
+    gpu = configs.feature_uncertainty(n, p, device=DEV, gen_device="cpu")
+    cpu = configs.feature_uncertainty(n, p)
+    for config in (gpu, cpu):       # a tight approximation keeps the Monte Carlo noise of exp(.) small
+        cls, params = config.families["z"]
+        config.families["z"] = (cls, {"loc": params["loc"], "scale": 0.05 * params["scale"]})
+        config.families["population_scale"] = (torch.distributions.Gamma, {
+            "concentration": torch.tensor(400.0), "rate": torch.tensor(400.0)})
+    approx, leaves = gpu.approximation(device=DEV)
+    conditioned = mininf.condition(lambda: gpu.model(mininf), **gpu.data)
+    loss_module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+    torch.manual_seed(3)
+    values = [float(loss_module(conditioned, approx)) for _ in range(4)]
+    torch.manual_seed(3)
+    again = float(mininf.nn.EvidenceLowerBoundLoss(S, check="sync")(conditioned, approx))
+    assert again == values[0] and len(set(values)) == 4
+    approx_c, _ = cpu.approximation(requires_grad=False)
+    torch.manual_seed(0)
+    reference = float(elbo.neg_elbo(cpu.model, cpu.data, approx_c, None, 48))
+    assert abs(np.median(values) - reference) < 3e-3 * abs(reference)
+
+
 def test_integer_exact_mask_and_count_sums():
     """Bit-exact integer work: number of observed entries and sum of observed counts."""
     gpu = configs.missing(100_003, device=DEV, gen_device="cpu")
