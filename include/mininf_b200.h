@@ -182,8 +182,9 @@ size_t mnf_workspace_bytes(int n_particles, int n_latent_total, int device);
  * Gamma.rsample gamma.py:79-87; Beta.rsample beta.py:84-85).
  *   noise_in != NULL : external noise [S][D] (parity mode: the host drew it with the torch
  *                      generator in the reference's order) and is copied to noise_out;
- *   noise_in == NULL : Normal sites draw eps from Philox4x32-10 (key = seed, counter =
- *                      (offset, particle*D + column)); Gamma/Beta sites require external noise.
+ *   noise_in == NULL : every site draws from Philox4x32-10 (key = seed, counter = (offset,
+ *                      particle*D + column [, rejection round])): Normal eps by Box-Muller, standard
+ *                      gammas by Marsaglia-Tsang, Beta as G1 / (G1 + G0).
  * Also zeroes `acc` [S][1+D] for the step and clears nothing else.
  */
 int mnf_rsample(const mnf_latent_t* latents_dev, int n_latents, int n_particles, int n_latent_total,

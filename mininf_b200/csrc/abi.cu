@@ -390,8 +390,9 @@ int mnf_small_sites(const mnf_site_t* sites_dev, int n_sites, int64_t max_numel,
   if (!sites_dev || !z || !acc || !status || n_sites < 0 || max_numel < 0)
     return fail(MNF_E_INVALID, "mnf_small_sites: null pointer or negative size%s%s");
   if (max_numel == 0) return MNF_OK;
-  const int bx = (int)std::min<int64_t>((max_numel + kSmallThreads - 1) / kSmallThreads, 1024);
-  dim3 grid(bx, n_sites);
+  const int bx = (int)std::min<int64_t>((max_numel + kSmallThreads - 1) / kSmallThreads, 256);
+  if (n_particles > 65535) return fail(MNF_E_UNSUPPORTED, "mnf_small_sites: too many particles%s%s");
+  dim3 grid(bx, n_sites, n_particles);
   small_sites_kernel<<<grid, kSmallThreads, 0, (cudaStream_t)stream>>>(sites_dev, z, n_particles,
                                                                        n_latent_total, acc, status);
   MNF_CUDA_CHECK(cudaGetLastError());

@@ -9,6 +9,36 @@
 
 namespace mnf {
 
+// Standard Gamma(alpha, 1) draw by Marsaglia & Tsang's squeeze method (ACM TOMS 26, 2000), the
+// algorithm behind ATen's sample_gamma (TORCH include/ATen/native/Distributions.h:85-113), on a
+// private Philox stream; alpha < 1 uses the boost Gamma(alpha + 1) * U^(1/alpha).
+__device__ inline float philox_standard_gamma(float alpha, uint64_t seed, uint64_t offset, uint64_t index) {
+  float scale = 1.0f;
+  uint32_t round = 0;
+  if (alpha < 1.0f) {
+    Philox rng(seed, offset, (index << 8) | 0xFFu);
+    const uint4 r = rng.next();
+    const float u = ((float)(r.x >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    scale = powf(u, 1.0f / alpha);
+    alpha += 1.0f;
+  }
+  const float d = alpha - 1.0f / 3.0f;
+  const float c = rsqrtf(9.0f * d);
+  for (; round < 64; ++round) {
+    Philox rng(seed, offset, (index << 8) | round);
+    const uint4 r = rng.next();
+    const float x = box_muller(r.x, r.y).x;
+    const float t = 1.0f + c * x;
+    if (t <= 0.0f) continue;
+    const float v = t * t * t;
+    const float u = ((float)(r.z >> 8) + 1.0f) * (1.0f / 16777216.0f);
+    const float xx = x * x;
+    if (u < 1.0f - 0.0331f * xx * xx || logf(u) < 0.5f * xx + d * (1.0f - v + logf(v)))
+      return fmaxf(scale * d * v, kFloatTiny);
+  }
+  return fmaxf(scale * d, kFloatTiny);   // unreachable in practice (acceptance > 95 % per round)
+}
+
 __device__ __forceinline__ int find_latent(const mnf_latent_t* lat, int n, int col) {
   int k = 0;
   for (int i = 1; i < n; ++i)
@@ -48,12 +78,19 @@ __global__ void rsample_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, 
       if (!(p1 > 0.0f) || p0 != p0) bad |= MNF_ST_BAD_PARAM;
     } else if (L.family == MNF_GAMMA) {
       // Gamma.rsample: standard_gamma(alpha) / rate, clamped at tiny   TORCH gamma.py:79-87
-      nz = noise_in != nullptr ? noise_in[i] : NAN;
+      nz = noise_in != nullptr ? noise_in[i] : philox_standard_gamma(p0, seed, offset, (uint64_t)i);
       val = fmaxf(nz / p1, kFloatTiny);
       if (!(p0 > 0.0f) || !(p1 > 0.0f)) bad |= MNF_ST_BAD_PARAM;
     } else {
-      // Beta.rsample: first component of a 2-simplex Dirichlet draw    TORCH beta.py:84-85
-      nz = noise_in != nullptr ? noise_in[i] : NAN;
+      // Beta.rsample: first component of a 2-simplex Dirichlet draw    TORCH beta.py:84-85,
+      // i.e. G1 / (G1 + G0) for independent standard gammas (dirichlet.py:85-88)
+      if (noise_in != nullptr) {
+        nz = noise_in[i];
+      } else {
+        const float g1 = philox_standard_gamma(p0, seed, offset, (uint64_t)(2 * i));
+        const float g0 = philox_standard_gamma(p1, seed, offset, (uint64_t)(2 * i + 1) | ((uint64_t)1 << 40));
+        nz = fminf(fmaxf(g1 / (g1 + g0), kFloatEps), 1.0f - kFloatEps);
+      }
       val = nz;
       if (!(p0 > 0.0f) || !(p1 > 0.0f)) bad |= MNF_ST_BAD_PARAM;
     }
@@ -65,7 +102,8 @@ __global__ void rsample_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, 
 
 // -------------------------------------------------------------------------------------------
 // small sites: LogProbTracer.sample + contribution (mininf/core.py:211-273) for short sites.
-// grid = (blocks over elements, n_sites); every thread owns elements, loops over particles.
+// grid = (blocks over elements, n_sites, particles): one block evaluates a chunk of one site for
+// one particle; sums are reduced in the block and leave it as one fp64 atomic per target.
 // -------------------------------------------------------------------------------------------
 constexpr int kSmallThreads = 128;
 
@@ -73,6 +111,7 @@ __global__ void __launch_bounds__(kSmallThreads)
 small_sites_kernel(const mnf_site_t* __restrict__ sites, const float* __restrict__ z, int S, int D,
                    double* __restrict__ acc, uint32_t* __restrict__ status) {
   const mnf_site_t site = sites[blockIdx.y];
+  const int s = blockIdx.z;
   const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   if ((int64_t)blockIdx.x * blockDim.x >= site.numel) return;
@@ -80,58 +119,60 @@ small_sites_kernel(const mnf_site_t* __restrict__ sites, const float* __restrict
   const bool g1 = link_has_latent(site.param[1]);
   const bool two = site.family <= MNF_BETA;  // families with a second parameter
   const float w = (float)site.scale;
-  __shared__ double s_lp[kSmallThreads / 32];
+  const float* zs = z + (int64_t)s * D;
+  double* as = acc + (int64_t)s * (D + 1);
   uint32_t bad = 0;
 
-  for (int s = 0; s < S; ++s) {
-    const float* zs = z + (int64_t)s * D;
-    double* as = acc + (int64_t)s * (D + 1);
-    double lp_sum = 0.0;
-    // scalar-latent gradient sums of this thread (stride-0 targets)
-    float gA0 = 0.f, gB0 = 0.f, gA1 = 0.f, gB1 = 0.f;
-    for (int64_t i = i0; i < site.numel; i += stride) {
-      if (site.mask != nullptr && site.mask[i] == 0) continue;
-      const float v = site.value_lat >= 0 ? zs[site.value_lat + i] : site.value[i];
-      const LinkVal l0 = eval_link(site.param[0], zs, i);
-      LinkVal l1; l1.value = 0.f; l1.du = 0.f; l1.x = 1.f;
-      if (two) l1 = eval_link(site.param[1], zs, i);
-      const Dens dn = density(site.family, v, l0.value, l1.value, g0 || g1);
-      if (dn.bad_param) bad |= MNF_ST_BAD_PARAM;
-      if (dn.bad_value) bad |= MNF_ST_BAD_VALUE;
-      lp_sum += (double)dn.lp;
-      if (site.value_lat >= 0) atomicAdd(as + 1 + site.value_lat + i, (double)(w * dn.dv));
-      if (g0) {
-        const float du = dn.d0 * l0.du;
-        const mnf_link_t& L = site.param[0];
-        if (L.a_lat >= 0) { if (L.a_stride) atomicAdd(as + 1 + L.a_lat + L.a_stride * i, (double)(w * du)); else gA0 += du; }
-        if (L.b_lat >= 0) { if (L.b_stride) atomicAdd(as + 1 + L.b_lat + L.b_stride * i, (double)(w * du * l0.x)); else gB0 += du * l0.x; }
-      }
-      if (two && g1) {
-        const float du = dn.d1 * l1.du;
-        const mnf_link_t& L = site.param[1];
-        if (L.a_lat >= 0) { if (L.a_stride) atomicAdd(as + 1 + L.a_lat + L.a_stride * i, (double)(w * du)); else gA1 += du; }
-        if (L.b_lat >= 0) { if (L.b_stride) atomicAdd(as + 1 + L.b_lat + L.b_stride * i, (double)(w * du * l1.x)); else gB1 += du * l1.x; }
-      }
+  double lp_sum = 0.0;
+  // gradient sums of this thread for scalar-latent (stride-0) targets
+  float gA0 = 0.f, gB0 = 0.f, gA1 = 0.f, gB1 = 0.f;
+  for (int64_t i = i0; i < site.numel; i += stride) {
+    if (site.mask != nullptr && site.mask[i] == 0) continue;
+    const float v = site.value_lat >= 0 ? zs[site.value_lat + i] : site.value[i];
+    const LinkVal l0 = eval_link(site.param[0], zs, i);
+    LinkVal l1; l1.value = 0.f; l1.du = 0.f; l1.x = 1.f;
+    if (two) l1 = eval_link(site.param[1], zs, i);
+    const Dens dn = density(site.family, v, l0.value, l1.value, g0 || g1);
+    if (dn.bad_param) bad |= MNF_ST_BAD_PARAM;
+    if (dn.bad_value) bad |= MNF_ST_BAD_VALUE;
+    lp_sum += (double)dn.lp;
+    // element-wise latent targets are distinct addresses within a site; other sites may touch
+    // the same column, hence atomics
+    if (site.value_lat >= 0) atomicAdd(as + 1 + site.value_lat + i, (double)(w * dn.dv));
+    if (g0) {
+      const float du = dn.d0 * l0.du;
+      const mnf_link_t& L = site.param[0];
+      if (L.a_lat >= 0) { if (L.a_stride) atomicAdd(as + 1 + L.a_lat + L.a_stride * i, (double)(w * du)); else gA0 += du; }
+      if (L.b_lat >= 0) { if (L.b_stride) atomicAdd(as + 1 + L.b_lat + L.b_stride * i, (double)(w * du * l0.x)); else gB0 += du * l0.x; }
     }
-    // block-reduce the log-density and the scalar-latent gradient sums, one atomic per block
-    lp_sum = warp_sum(lp_sum);
-    gA0 = warp_sum(gA0); gB0 = warp_sum(gB0); gA1 = warp_sum(gA1); gB1 = warp_sum(gB1);
-    if ((threadIdx.x & 31) == 0) {
-      s_lp[threadIdx.x >> 5] = lp_sum;
-      const mnf_link_t& L0 = site.param[0];
-      const mnf_link_t& L1 = site.param[1];
-      if (g0 && L0.a_lat >= 0 && L0.a_stride == 0 && gA0 != 0.f) atomicAdd(as + 1 + L0.a_lat, (double)(w * gA0));
-      if (g0 && L0.b_lat >= 0 && L0.b_stride == 0 && gB0 != 0.f) atomicAdd(as + 1 + L0.b_lat, (double)(w * gB0));
-      if (two && g1 && L1.a_lat >= 0 && L1.a_stride == 0 && gA1 != 0.f) atomicAdd(as + 1 + L1.a_lat, (double)(w * gA1));
-      if (two && g1 && L1.b_lat >= 0 && L1.b_stride == 0 && gB1 != 0.f) atomicAdd(as + 1 + L1.b_lat, (double)(w * gB1));
+    if (two && g1) {
+      const float du = dn.d1 * l1.du;
+      const mnf_link_t& L = site.param[1];
+      if (L.a_lat >= 0) { if (L.a_stride) atomicAdd(as + 1 + L.a_lat + L.a_stride * i, (double)(w * du)); else gA1 += du; }
+      if (L.b_lat >= 0) { if (L.b_stride) atomicAdd(as + 1 + L.b_lat + L.b_stride * i, (double)(w * du * l1.x)); else gB1 += du * l1.x; }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double t = 0.0;
-      for (int k = 0; k < kSmallThreads / 32; ++k) t += s_lp[k];
-      atomicAdd(as, (double)site.scale * t);
-    }
-    __syncthreads();
+  }
+  // block reduction: warp shuffles, then one warp finishes through shared memory
+  __shared__ double s_red[kSmallThreads / 32][5];
+  lp_sum = warp_sum(lp_sum);
+  gA0 = warp_sum(gA0); gB0 = warp_sum(gB0); gA1 = warp_sum(gA1); gB1 = warp_sum(gB1);
+  if ((threadIdx.x & 31) == 0) {
+    double* row = s_red[threadIdx.x >> 5];
+    row[0] = lp_sum; row[1] = gA0; row[2] = gB0; row[3] = gA1; row[4] = gB1;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double t = 0.0;
+    for (int k = 0; k < kSmallThreads / 32; ++k) t += s_red[k][threadIdx.x];
+    const mnf_link_t& L0 = site.param[0];
+    const mnf_link_t& L1 = site.param[1];
+    int target = -1;
+    if (threadIdx.x == 0) target = 0;
+    else if (threadIdx.x == 1 && g0 && L0.a_lat >= 0 && L0.a_stride == 0) target = 1 + L0.a_lat;
+    else if (threadIdx.x == 2 && g0 && L0.b_lat >= 0 && L0.b_stride == 0) target = 1 + L0.b_lat;
+    else if (threadIdx.x == 3 && two && g1 && L1.a_lat >= 0 && L1.a_stride == 0) target = 1 + L1.a_lat;
+    else if (threadIdx.x == 4 && two && g1 && L1.b_lat >= 0 && L1.b_stride == 0) target = 1 + L1.b_lat;
+    if (target >= 0 && t != 0.0) atomicAdd(as + target, site.scale * t);
   }
   if (bad) atomicOr(status, bad);
 }

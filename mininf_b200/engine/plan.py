@@ -429,8 +429,6 @@ class Plan:
         if noise is not None:
             self.noise_in.copy_(noise.reshape(S, D))
             noise_ptr = self.noise_in.data_ptr()
-        elif not self.all_normal:
-            raise RuntimeError("Gamma / Beta approximations need host-provided noise")
         lib.call("mnf_rsample", self.latent_table.data_ptr(), len(self.latents), S, D, noise_ptr,
                  seed, offset, self.z.data_ptr(), self.noise.data_ptr(), self.acc.data_ptr(), status,
                  stream)

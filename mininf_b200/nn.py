@@ -288,32 +288,21 @@ class EvidenceLowerBoundLoss(nn.Module):
         return plan
 
     # -- noise ------------------------------------------------------------------------------
-    def _noise(self, plan: Any, approximation: DistributionDict,
-               given: Optional[Dict[str, torch.Tensor]]) -> Optional[torch.Tensor]:
-        """Reparameterisation noise [S, D]: ``None`` lets the kernel draw Normal eps with Philox;
-        Gamma / Beta factors use torch's standard-gamma / Dirichlet samplers on the device."""
-        from .engine import abi
-        S = plan.S
-        if given is None and plan.all_normal:
+    def _noise(self, plan: Any, given: Optional[Dict[str, torch.Tensor]]) -> Optional[torch.Tensor]:
+        """External reparameterisation noise [S, D] for the packed latents, or ``None`` to let
+        the kernel draw everything with Philox. Convention per family: eps for Normal, the
+        standard-gamma draw for Gamma, the drawn value for Beta."""
+        if given is None:
             return None
+        missing = [spec.name for spec in plan.latents if spec.name not in given]
+        if missing:
+            raise ValueError(f"_noise must cover every packed latent site; missing {missing}")
+        S = plan.S
         noise = torch.empty(S, plan.D, device=plan.device, dtype=torch.float32)
         with torch.no_grad():
             for spec in plan.latents:
                 block = noise[:, spec.offset:spec.offset + spec.numel]
-                if given is not None and spec.name in given:
-                    block.copy_(given[spec.name].to(plan.device, torch.float32).reshape(S, spec.numel))
-                elif spec.family == abi.NORMAL:
-                    block.normal_()
-                elif spec.family == abi.GAMMA:
-                    alpha = approximation[spec.name].concentration.detach().float()
-                    block.copy_(torch._standard_gamma(alpha.expand(spec.shape).reshape(1, -1)
-                                                      .expand(S, spec.numel).contiguous()))
-                else:
-                    beta = approximation[spec.name]
-                    conc = torch.stack([beta.concentration1.detach().float().expand(spec.shape),
-                                        beta.concentration0.detach().float().expand(spec.shape)], -1)
-                    conc = conc.reshape(1, spec.numel, 2).expand(S, spec.numel, 2).contiguous()
-                    block.copy_(torch._sample_dirichlet(conc)[..., 0])
+                block.copy_(given[spec.name].to(plan.device, torch.float32).reshape(S, spec.numel))
         return noise
 
     # -- forward ----------------------------------------------------------------------------
@@ -333,7 +322,7 @@ class EvidenceLowerBoundLoss(nn.Module):
             shape = spec.shape if len(spec.shape) else torch.Size([])
             params.append(p0.to(torch.float32).expand(shape))
             params.append(p1.to(torch.float32).expand(shape))
-        noise = self._noise(plan, approximation, _noise)
+        noise = self._noise(plan, _noise)
         # external noise of row latents [S, n, p] (parity tests); otherwise in-kernel Philox
         row_noise = {spec.name: _noise[spec.name].to(plan.device, torch.float32).contiguous()
                      for spec in plan.row_latents if _noise is not None and spec.name in _noise}

@@ -251,6 +251,33 @@ def test_philox_draws_are_standard_normal_and_seeded():
     assert float(again(conditioned, approx)) == first
 
 
+def test_philox_gamma_and_beta_draws_have_the_right_moments():
+    """Gamma / Beta factors draw in-kernel too (Marsaglia-Tsang on Philox): check the first two
+    moments of the draws the kernel leaves in the plan's z buffer."""
+    def model():
+        mininf.sample("g", torch.distributions.Gamma(2.0, 2.0), 3)
+        mininf.sample("b", torch.distributions.Beta(2.0, 2.0), 3)
+
+    conc = torch.tensor([0.4, 2.5, 30.0], device=DEV)
+    rate = torch.tensor([1.5, 0.5, 10.0], device=DEV)
+    c1 = torch.tensor([0.5, 3.0, 20.0], device=DEV)
+    c0 = torch.tensor([0.7, 1.5, 40.0], device=DEV)
+    approx = {"g": torch.distributions.Gamma(conc, rate), "b": torch.distributions.Beta(c1, c0)}
+    module = mininf.nn.EvidenceLowerBoundLoss(64, check="sync")
+    draws = []
+    for _ in range(64):
+        assert np.isfinite(float(module(model, approx)))
+        draws.append(module.last_plan.z.clone())
+    z = torch.cat(draws).double()                     # [4096, 6]
+    g, b = z[:, :3], z[:, 3:]
+    mean_g, var_g = (conc / rate).double(), (conc / rate ** 2).double()
+    mean_b = (c1 / (c1 + c0)).double()
+    var_b = (c1 * c0 / ((c1 + c0) ** 2 * (c1 + c0 + 1))).double()
+    assert torch.allclose(g.mean(0), mean_g, rtol=0.08) and torch.allclose(g.var(0), var_g, rtol=0.25)
+    assert torch.allclose(b.mean(0), mean_b, rtol=0.05) and torch.allclose(b.var(0), var_b, rtol=0.25)
+    assert (g > 0).all() and ((b > 0) & (b < 1)).all()
+
+
 def test_invalid_values_are_reported():
     config = configs.regression(300, 64, device=DEV)
     config.data["y"][17] = float("nan")
