@@ -199,6 +199,7 @@ class EvidenceLowerBoundLoss(nn.Module):
         self.check = check
         self._plans: Dict[Tuple, Any] = {}
         self._pending: List[Tuple[Any, torch.Tensor, torch.cuda.Event]] = []
+        self._free_slots: List[torch.Tensor] = []
         self._calls = 0
         self.last_plan = None
 
@@ -209,22 +210,32 @@ class EvidenceLowerBoundLoss(nn.Module):
         if self.check == "sync":
             self._raise_for_status(int(plan.status.item()))
             return
-        host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+        if len(self._pending) >= 8:          # bounded backlog: settle the oldest check first
+            _, host, event = self._pending.pop(0)
+            event.synchronize()
+            self._raise_for_status(int(host.item()))
+        else:
+            # pinned slots are recycled: allocating pinned memory every step is slow and may
+            # synchronise the device
+            host = self._free_slots.pop() if self._free_slots else \
+                torch.empty(1, dtype=torch.int32, pin_memory=True)
+            event = torch.cuda.Event()
         host.copy_(plan.status, non_blocking=True)
-        event = torch.cuda.Event()
         event.record(torch.cuda.current_stream(plan.device))
         self._pending.append((plan, host, event))
 
     def _drain_status(self, block: bool = False) -> None:
-        remaining = []
+        remaining, flagged = [], 0
         for plan, host, event in self._pending:
             if block:
                 event.synchronize()
             if event.query():
-                self._raise_for_status(int(host.item()))
+                flagged |= int(host.item())
+                self._free_slots.append(host)
             else:
                 remaining.append((plan, host, event))
         self._pending = remaining
+        self._raise_for_status(flagged)
 
     @staticmethod
     def _raise_for_status(bits: int) -> None:
