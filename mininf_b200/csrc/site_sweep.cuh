@@ -57,6 +57,23 @@ __device__ __forceinline__ void sweep_point(int family, float v, float c, float 
   }
 }
 
+// Normal site whose scale is a per-particle constant: sigma, 1/sigma, log sigma and d sigma/du
+// are hoisted out of the element loop (the common case: `Normal(c + d*x, sigma)`).
+struct ScaleConst {
+  float inv;     // 1 / sigma
+  float logs;    // log sigma + log sqrt(2 pi)
+  float dsig;    // d sigma / d u (sigma for the exp link, 1 for identity)
+};
+
+__device__ __forceinline__ void normal_point_hoisted(float v, float u0, int t0, const ScaleConst& sc,
+                                                     float& lp, float& du0, float& du1) {
+  const float loc = t0 == MNF_T_EXP ? expf(u0) : u0;
+  const float r = (v - loc) * sc.inv;
+  lp = fmaf(-0.5f * r, r, -sc.logs);
+  du0 = r * sc.inv * (t0 == MNF_T_EXP ? loc : 1.0f);
+  du1 = fmaf(r, r, -1.0f) * sc.inv * sc.dsig;
+}
+
 __device__ __forceinline__ bool in_support(int family, float v) {
   switch (family) {
     case MNF_NORMAL: return v == v;
@@ -70,7 +87,7 @@ __device__ __forceinline__ bool in_support(int family, float v) {
 // partial layout per CTA: [S][ncol], ncol = 1 + 4*NSITES: col 0 scaled log-density, then per site
 // the scaled sums of (du0, du0*x0, du1, du1*x1)
 template <int NSITES, int Q>
-__global__ void __launch_bounds__(kSweepThreads)
+__global__ void __launch_bounds__(kSweepThreads, 3)
 site_sweep_kernel(SweepArgs<NSITES> args, const float* __restrict__ z, int S, int D,
                   float* __restrict__ partial, uint32_t* __restrict__ status) {
   constexpr int NC = 1 + 4 * NSITES;
@@ -92,16 +109,40 @@ site_sweep_kernel(SweepArgs<NSITES> args, const float* __restrict__ z, int S, in
         B[i][p][q] = L.b_const + (L.b_lat >= 0 ? zs[L.b_lat] : 0.0f);
       }
   }
-  double acc[NC][Q];
+  // fp64 running sums live in shared memory (touched once per 32-element chunk), laid out as the
+  // final cross-warp reduction reads them: [warp][particle slot][column]
+  extern __shared__ double s_acc[];
+  double* my_acc = s_acc + ((size_t)warp * Q * 32 + lane) * NC;     // + q * 32 * NC + c
 #pragma unroll
-  for (int c = 0; c < NC; ++c)
+  for (int q = 0; q < Q; ++q)
 #pragma unroll
-    for (int q = 0; q < Q; ++q) acc[c][q] = 0.0;
+    for (int c = 0; c < NC; ++c) my_acc[(size_t)q * 32 * NC + c] = 0.0;
 
   bool bad_param = false, bad_value = false;
+  // Normal sites with an element-independent scale: hoist its derived constants per particle
+  bool hoisted[NSITES];
+  ScaleConst sconst[NSITES][Q];
+#pragma unroll
+  for (int k = 0; k < NSITES; ++k) {
+    const mnf_link_t& L = args.site[k].param[1];
+    hoisted[k] = args.site[k].family == MNF_NORMAL && L.x == nullptr;
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const float u = A[k][1][q] + B[k][1][q];           // x == NULL means x == 1
+      const float sigma = L.transform == MNF_T_EXP ? expf(u) : u;
+      sconst[k][q].inv = 1.0f / sigma;
+      sconst[k][q].logs = logf(sigma) + kLogSqrt2Pi;
+      sconst[k][q].dsig = L.transform == MNF_T_EXP ? sigma : 1.0f;
+      if (hoisted[k] && !(sigma > 0.0f) && lane + 32 * q < S) bad_param = true;
+    }
+  }
   const int64_t n_chunks = (n + 31) / 32;
   const int64_t warp_global = (int64_t)blockIdx.x * kSweepWarps + warp;
   const int64_t warps_total = (int64_t)gridDim.x * kSweepWarps;
+
+  // per-warp staging of a chunk's element data: one float4 (value, data-only term, x0, x1) per
+  // site and element, read back as 16-byte broadcasts (one LDS.128 instead of four shuffles)
+  float4* stage = reinterpret_cast<float4*>(s_acc + (size_t)kSweepWarps * Q * 32 * NC) + (size_t)warp * NSITES * 32;
 
   for (int64_t chunk = warp_global; chunk < n_chunks; chunk += warps_total) {
     const int64_t i = chunk * 32 + lane;
@@ -121,7 +162,9 @@ site_sweep_kernel(SweepArgs<NSITES> args, const float* __restrict__ z, int S, in
         if (st.family == MNF_POISSON) ec[k] = lgammaf(ev[k] + 1.0f);
       }
       live_bits[k] = __ballot_sync(0xffffffffu, live);
+      stage[k * 32 + lane] = make_float4(ev[k], ec[k], ex0[k], ex1[k]);
     }
+    __syncwarp();
     float part[NC][Q];
 #pragma unroll
     for (int c = 0; c < NC; ++c)
@@ -134,18 +177,19 @@ site_sweep_kernel(SweepArgs<NSITES> args, const float* __restrict__ z, int S, in
       for (int k = 0; k < NSITES; ++k) {
         if (!((live_bits[k] >> e) & 1u)) continue;  // warp-uniform
         const mnf_site_t& st = args.site[k];
-        const float v = __shfl_sync(0xffffffffu, ev[k], e);
-        const float c = __shfl_sync(0xffffffffu, ec[k], e);
-        const float x0 = __shfl_sync(0xffffffffu, ex0[k], e);
-        const float x1 = __shfl_sync(0xffffffffu, ex1[k], e);
+        const float4 el = stage[k * 32 + e];
+        const float v = el.x, c = el.y, x0 = el.z, x1 = el.w;
         const float w = (float)st.scale;
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
           const float u0 = fmaf(B[k][0][q], x0, A[k][0][q]);
           const float u1 = fmaf(B[k][1][q], x1, A[k][1][q]);
           float lp, du0, du1;
-          sweep_point(st.family, v, c, u0, st.param[0].transform, u1, st.param[1].transform, lp,
-                      du0, du1, bad_param);
+          if (hoisted[k])
+            normal_point_hoisted(v, u0, st.param[0].transform, sconst[k][q], lp, du0, du1);
+          else
+            sweep_point(st.family, v, c, u0, st.param[0].transform, u1, st.param[1].transform, lp,
+                        du0, du1, bad_param);
           part[0][q] = fmaf(w, lp, part[0][q]);
           du0 *= w;
           du1 *= w;
@@ -157,17 +201,13 @@ site_sweep_kernel(SweepArgs<NSITES> args, const float* __restrict__ z, int S, in
       }
     }
 #pragma unroll
-    for (int c = 0; c < NC; ++c)
+    for (int q = 0; q < Q; ++q)
 #pragma unroll
-      for (int q = 0; q < Q; ++q) acc[c][q] += (double)part[c][q];
+      for (int c = 0; c < NC; ++c) my_acc[(size_t)q * 32 * NC + c] += (double)part[c][q];
+    __syncwarp();   // the staging slots are rewritten by the next chunk
   }
 
   // cross-warp reduction in fixed order, then one partial block per CTA
-  extern __shared__ double s_acc[];  // [kSweepWarps][Q*32][NC]
-#pragma unroll
-  for (int q = 0; q < Q; ++q)
-#pragma unroll
-    for (int c = 0; c < NC; ++c) s_acc[((size_t)warp * Q * 32 + q * 32 + lane) * NC + c] = acc[c][q];
   __syncthreads();
   float* out = partial + (size_t)blockIdx.x * S * NC;
   for (int idx = threadIdx.x; idx < S * NC; idx += kSweepThreads) {
@@ -184,7 +224,8 @@ site_sweep_kernel(SweepArgs<NSITES> args, const float* __restrict__ z, int S, in
 
 template <int NSITES, int Q>
 inline size_t site_sweep_smem_bytes() {
-  return sizeof(double) * kSweepWarps * Q * 32 * (1 + 4 * NSITES);
+  return sizeof(double) * kSweepWarps * Q * 32 * (1 + 4 * NSITES) +     // running sums
+         sizeof(float4) * kSweepWarps * NSITES * 32;                    // element staging
 }
 
 }  // namespace mnf
