@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "dense_simt.cuh"
 #include "dense_tc.cuh"
+#include "dense_tcr.cuh"
 #include "rowlatent.cuh"
 #include "site_sweep.cuh"
 #include "small.cuh"
@@ -108,6 +109,55 @@ int launch_dense_tc(const mnf_dense_site_t& site, const float* z, int S, int D, 
   kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_k, map_mn, site, z, S, D, partial, status);
   MNF_CUDA_CHECK(cudaGetLastError());
   return MNF_OK;
+}
+
+// rows-on-lanes tcgen05 kernel: p = 64 * C, S <= 32, optional intercept (dense_tcr.cuh)
+struct TcrShape {
+  int NS, C, k_stages, mn_stages;
+  size_t smem;
+};
+bool tcr_shape(int p, int S, int max_smem_optin, TcrShape* out) {
+  if (p <= 0 || p % tcr::kChunk != 0 || S > 32) return false;
+  TcrShape sh;
+  sh.NS = S <= 16 ? 16 : 32;
+  sh.C = p / tcr::kChunk;
+  if ((2 + 2 * sh.C) * sh.NS > (int)tcr::kTmemCols) return false;
+  // split what is left of shared memory between the two operand rings, K ring first
+  for (int stages = 2 * tcr::kMaxStages; stages >= 4; --stages) {
+    sh.k_stages = (stages + 1) / 2;
+    sh.mn_stages = stages / 2;
+    sh.smem = tcr::make_layout(sh.NS, sh.C, sh.k_stages, sh.mn_stages).total;
+    if (sh.smem <= (size_t)max_smem_optin) {
+      *out = sh;
+      return true;
+    }
+  }
+  return false;
+}
+
+template <int FAMILY, int NS, bool ICPT>
+int launch_dense_tcr_inst(const CUtensorMap& map_k, const CUtensorMap& map_mn, const mnf_dense_site_t& site,
+                          const float* z, int S, int D, const TcrShape& sh, float* partial, uint32_t* status,
+                          int grid, cudaStream_t stream) {
+  auto kernel = tcr::dense_tcr_kernel<FAMILY, NS, ICPT>;
+  MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
+  kernel<<<grid, tcr::kThreads, sh.smem, stream>>>(map_k, map_mn, site, z, S, D, sh.C, sh.k_stages, sh.mn_stages, partial, status);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+template <int FAMILY>
+int launch_dense_tcr(const mnf_dense_site_t& site, const float* z, int S, int D, const TcrShape& sh,
+                     bool has_icpt, float* partial, uint32_t* status, int grid, cudaStream_t stream) {
+  CUtensorMap map_k, map_mn;
+  if (int rc = make_x_map(site, CU_TENSOR_MAP_SWIZZLE_128B, &map_k)) return rc;
+  if (int rc = make_x_map(site, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, &map_mn)) return rc;
+  if (sh.NS == 16) {
+    return has_icpt ? launch_dense_tcr_inst<FAMILY, 16, true>(map_k, map_mn, site, z, S, D, sh, partial, status, grid, stream)
+                    : launch_dense_tcr_inst<FAMILY, 16, false>(map_k, map_mn, site, z, S, D, sh, partial, status, grid, stream);
+  }
+  return has_icpt ? launch_dense_tcr_inst<FAMILY, 32, true>(map_k, map_mn, site, z, S, D, sh, partial, status, grid, stream)
+                  : launch_dense_tcr_inst<FAMILY, 32, false>(map_k, map_mn, site, z, S, D, sh, partial, status, grid, stream);
 }
 
 template <int NSITES>
@@ -223,18 +273,28 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
     const bool aligned = (reinterpret_cast<uintptr_t>(s.X) % 16 == 0) && (s.ldx % 4 == 0) &&
                          s.n_rows < (int64_t)1 << 31;
     const bool has_icpt = s.icpt_lat >= 0 || s.icpt_const != 0.0f;
-    if (p != tc::kP || S > tc::kNS || !aligned || has_icpt || c->cc_major != 10)
+    const bool c2_shape = p == tc::kP && S <= tc::kNS && !has_icpt;   // dense_tc.cuh
+    TcrShape sh;
+    const bool wide_shape = !c2_shape && tcr_shape(p, S, c->max_smem_optin, &sh);   // dense_tcr.cuh
+    if (!aligned || c->cc_major != 10 || !(c2_shape || wide_shape))
       return fail(MNF_E_UNSUPPORTED,
-                  "mnf_dense_sweep: TF32 mode needs p == 64, S <= 64, no intercept, 16-byte aligned "
-                  "rows and an sm_100 device%s%s");
+                  "mnf_dense_sweep: TF32 mode needs p == 64 with S <= 64 and no intercept, or p a "
+                  "multiple of 64 with S <= 32 (and (2 + p/32) * S within 512 TMEM columns), 16-byte "
+                  "aligned rows and an sm_100 device%s%s");
     const int64_t n_tiles = (s.n_rows + tc::kTileM - 1) / tc::kTileM;
     grid = (int)std::min<int64_t>(n_tiles, c->sm_count);
     if ((size_t)grid * S * ncol * sizeof(float) > workspace_bytes)
       return fail(MNF_E_INVALID, "mnf_dense_sweep: workspace too small%s%s");
     int rc;
-    if (s.family == MNF_NORMAL) rc = launch_dense_tc<MNF_NORMAL>(s, z, S, D, partial, status, grid, stream);
-    else if (s.family == MNF_BERNOULLI_LOGITS) rc = launch_dense_tc<MNF_BERNOULLI_LOGITS>(s, z, S, D, partial, status, grid, stream);
-    else rc = launch_dense_tc<MNF_POISSON>(s, z, S, D, partial, status, grid, stream);
+    if (c2_shape) {
+      if (s.family == MNF_NORMAL) rc = launch_dense_tc<MNF_NORMAL>(s, z, S, D, partial, status, grid, stream);
+      else if (s.family == MNF_BERNOULLI_LOGITS) rc = launch_dense_tc<MNF_BERNOULLI_LOGITS>(s, z, S, D, partial, status, grid, stream);
+      else rc = launch_dense_tc<MNF_POISSON>(s, z, S, D, partial, status, grid, stream);
+    } else {
+      if (s.family == MNF_NORMAL) rc = launch_dense_tcr<MNF_NORMAL>(s, z, S, D, sh, has_icpt, partial, status, grid, stream);
+      else if (s.family == MNF_BERNOULLI_LOGITS) rc = launch_dense_tcr<MNF_BERNOULLI_LOGITS>(s, z, S, D, sh, has_icpt, partial, status, grid, stream);
+      else rc = launch_dense_tcr<MNF_POISSON>(s, z, S, D, sh, has_icpt, partial, status, grid, stream);
+    }
     if (rc) return rc;
   } else if (mode == MNF_DENSE_FP32) {
     const size_t smem = dense_simt_smem_bytes(S, p);

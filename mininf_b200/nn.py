@@ -319,7 +319,8 @@ class EvidenceLowerBoundLoss(nn.Module):
     # -- forward ----------------------------------------------------------------------------
     def forward(self, model: Callable,
                 approximation: torch.distributions.Distribution | DistributionDict, *,
-                _noise: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+                _noise: Optional[Dict[str, torch.Tensor]] = None,
+                _with_entropy: bool = True) -> torch.Tensor:
         if not isinstance(approximation, dict):
             raise TypeError("Expected a distribution which samples dictionaries of tensors but got "
                             f"a sample of type {type(approximation)}")
@@ -346,15 +347,31 @@ class EvidenceLowerBoundLoss(nn.Module):
             group = None if self.process_group is True else self.process_group
             reduce_fn = lambda acc: dist.all_reduce(acc, group=group)  # noqa: E731
         return _EngineFunction.apply(self, plan, noise, row_noise, int(seed) & (2 ** 63 - 1), self._calls,
-                                     reduce_fn, True, *params)
+                                     reduce_fn, bool(_with_entropy), *params)
 
 
 class LogLikelihoodLoss(nn.Module):
-    """Negative joint log-density at fixed parameter values (mininf/nn.py:231-257). Evaluated
-    with ``torch.distributions`` through :class:`~mininf_b200.core.LogProbTracer`; porting it to
-    the engine is listed as next in SURVEY.md §8f."""
+    """Negative joint log-density at fixed parameter values (mininf/nn.py:231-257).
+
+    CUDA tensors run on the engine: the same site table and sweeps as the ELBO with one
+    "particle" pinned to the given values (zero noise, no entropy term), so the gradient with
+    respect to ``parameters`` comes from the fused kernels. CPU tensors keep the reference's
+    behaviour through :class:`~mininf_b200.core.LogProbTracer` (this loss is not on the ELBO hot
+    path).
+    """
+
+    def __init__(self, *, dense_precision: str = "auto") -> None:
+        super().__init__()
+        self._engine = EvidenceLowerBoundLoss(1, dense_precision=dense_precision)
 
     def forward(self, model: Callable, parameters: TensorDict) -> torch.Tensor:
-        with LogProbTracer() as log_prob:
-            condition(model, **parameters)()
-        return - log_prob.total
+        values = {name: maybe_as_tensor(value) for name, value in parameters.items()}
+        if not values or not all(isinstance(v, torch.Tensor) and v.is_cuda for v in values.values()):
+            with LogProbTracer() as log_prob:
+                condition(model, **values)()
+            return - log_prob.total
+        # a unit-scale Normal around each value with zero noise draws exactly the value, and
+        # d loss / d loc is the gradient with respect to the value
+        point = {name: distributions.Normal(value, torch.ones_like(value)) for name, value in values.items()}
+        zeros = {name: torch.zeros((1,) + tuple(value.shape), device=value.device) for name, value in values.items()}
+        return self._engine(model, point, _noise=zeros, _with_entropy=False)

@@ -6,7 +6,7 @@ import torch
 
 import mininf_b200 as mininf
 from mininf_b200.engine import abi
-from oracle import configs, elbo
+from oracle import configs, elbo, handlers
 
 from conftest import GOLDEN_CASES, golden_noise, load_golden
 
@@ -232,6 +232,30 @@ def test_loss_contract_and_parameter_gradients():
     assert all(p.grad is not None for p in approximation.distribution_parameters.values())
     with pytest.raises(TypeError, match="dictionaries of tensors"):
         loss(None, torch.distributions.Normal(0, 1))
+
+
+def test_log_likelihood_loss_on_the_engine():
+    """mininf/nn.py:231-257 / tests/test_nn.py:114-129: joint log-density at point values, with
+    gradients, through the same kernels (compared with torch.distributions on the CPU)."""
+    cpu = configs.regression(700, 64, sigma_latent=True)
+    gpu = configs.regression(700, 64, sigma_latent=True, device=DEV, gen_device="cpu")
+    torch.manual_seed(4)
+    theta = 0.1 * torch.randn(64)
+    sigma = torch.tensor(0.8)
+    expected_params = {"theta": theta.clone().requires_grad_(), "sigma": sigma.clone().requires_grad_()}
+    log_probs = handlers.evaluate(lambda: cpu.model(handlers), {**cpu.data, **expected_params})
+    expected = -sum(value.sum() for value in log_probs.values())
+    expected.backward()
+    params = {"theta": theta.to(DEV).requires_grad_(), "sigma": sigma.to(DEV).requires_grad_()}
+    loss = mininf.nn.LogLikelihoodLoss()(mininf.condition(lambda: gpu.model(mininf), **gpu.data), params)
+    assert loss.grad_fn is not None and loss.ndim == 0
+    loss.backward()
+    assert abs(float(loss) - float(expected)) <= 2e-4 * abs(float(expected))     # TF32 dense path at N = 700
+    for name in params:
+        assert rel(params[name].grad.cpu().numpy(), expected_params[name].grad.numpy()) < 5e-3, name
+    exact = mininf.nn.LogLikelihoodLoss(dense_precision="fp32")(
+        mininf.condition(lambda: gpu.model(mininf), **gpu.data), {k: v.detach() for k, v in params.items()})
+    assert abs(float(exact) - float(expected)) <= 1e-5 * abs(float(expected))
 
 
 def test_philox_draws_are_standard_normal_and_seeded():

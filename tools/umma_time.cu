@@ -131,5 +131,17 @@ int main() {
     run("A TMEM      B MN/SW32B", {128, 64, 0, 2, 1, 1, 1, R, nacc, 16, 1024, 16384, 512});
     run("A TMEM      B MN/SW32B", {64, 128, 0, 2, 1, 1, 1, R, nacc, 16, 1024, 16384, 512});
   }
+  // small-N shapes of the rows-on-lanes kernel (dense_tcr.cuh): particles on N
+  for (int nacc = 1; nacc <= 4; nacc *= 4) {
+    printf("--- small N, %s\n", nacc == 1 ? "one accumulator" : "4 accumulators round-robin");
+    for (int N = 16; N <= 64; N *= 2) {
+      run("A K/SW128   B K/SW128", {128, N, 0, 2, 0, 2, 0, R, nacc, 16, 1024, 16, 1024});
+      run("A K/SW128   B K/SW128", {64, N, 0, 2, 0, 2, 0, R, nacc, 16, 1024, 16, 1024});
+      run("A MN/SW32B  B K/SW128", {64, N, 1, 1, 0, 2, 0, R, nacc, 16384, 512, 16, 1024});
+      run("A MN/SW32B  B K/SW128", {128, N, 1, 1, 0, 2, 0, R, nacc, 16384, 512, 16, 1024});
+      run("A TMEM      B K/SW128", {128, N, 0, 2, 0, 2, 1, R, nacc, 16, 1024, 16, 1024});
+      run("A TMEM      B K/SW128", {64, N, 0, 2, 0, 2, 1, R, nacc, 16, 1024, 16, 1024});
+    }
+  }
   return 0;
 }
