@@ -135,7 +135,8 @@ def regression(n: int, p: int = 64, sigma_latent: bool = False, device: Any = "c
 # C3: minibatch logistic regression
 # ---------------------------------------------------------------------------------------------
 def logistic(n_declared: int, batch_rows: int, p: int = 256, device: Any = "cpu",
-             seed0: int = 3000, batch_id: int = 0, gen_device: Any = None) -> Config:
+             seed0: int = 3000, batch_id: int = 0, gen_device: Any = None,
+             intercept: bool = False) -> Config:
     target, device = device, gen_device or device
     g = torch.Generator(device=device)
     g.manual_seed(seed0 - 1)
@@ -143,7 +144,7 @@ def logistic(n_declared: int, batch_rows: int, p: int = 256, device: Any = "cpu"
 
     def fill(count: int, generator: torch.Generator) -> Dict[str, torch.Tensor]:
         X = torch.randn(count, p, generator=generator, device=device)
-        y = torch.bernoulli(torch.sigmoid(X @ theta_true), generator=generator)
+        y = torch.bernoulli(torch.sigmoid(X @ theta_true + (0.4 if intercept else 0.0)), generator=generator)
         return {"X": X, "y": y}
 
     data = {k: v.to(target) for k, v in _chunked(batch_rows, seed0 + 1000 * batch_id, device, fill).items()}
@@ -156,7 +157,18 @@ def logistic(n_declared: int, batch_rows: int, p: int = 256, device: Any = "cpu"
                 X = m.sample("X", Normal(0, 1), (n_declared, p))
             m.sample("y", Bernoulli(logits=X @ theta))
 
+    def model_with_intercept(m: Any) -> None:
+        alpha = m.sample("alpha", Normal(0, 2))
+        theta = m.sample("theta", Normal(0, 1), p)
+        with m.batch(n_declared):
+            with m.no_log_prob():
+                X = m.sample("X", Normal(0, 1), (n_declared, p))
+            m.sample("y", Bernoulli(logits=alpha + X @ theta))
+
     families = {"theta": (Normal, {"loc": torch.zeros(p), "scale": 0.1 * torch.ones(p)})}
+    if intercept:
+        families["alpha"] = (Normal, {"loc": torch.tensor(0.1), "scale": torch.tensor(0.2)})
+        model = model_with_intercept
     return Config("logistic", model, {"X": data["X"], "y": data["y"]}, families,
                   {"theta_true": theta_true, "n_declared": n_declared, "p": p})
 

@@ -34,6 +34,7 @@ GOLDEN_CASES = {
     "regression_sigma": lambda cfgs, **kw: cfgs.regression(384, 64, sigma_latent=True, **kw),
     "regression_ragged": lambda cfgs, **kw: cfgs.regression(301, 24, sigma_latent=True, **kw),
     "logistic": lambda cfgs, **kw: cfgs.logistic(20000, 400, p=32, **kw),
+    "logistic_wide": lambda cfgs, **kw: cfgs.logistic(50000, 333, p=128, intercept=True, **kw),
     "missing": lambda cfgs, **kw: cfgs.missing(600, **kw),
     "features": lambda cfgs, **kw: cfgs.feature_uncertainty(300, 32, **kw),
 }

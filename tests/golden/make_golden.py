@@ -71,6 +71,7 @@ CASES = {
     "regression_sigma": (lambda: configs.regression(384, 64, sigma_latent=True), 4),
     "regression_ragged": (lambda: configs.regression(301, 24, sigma_latent=True), 3),
     "logistic": (lambda: configs.logistic(20000, 400, p=32), 2),
+    "logistic_wide": (lambda: configs.logistic(50000, 333, p=128, intercept=True), 3),
     "missing": (lambda: configs.missing(600), 4),
     "features": (lambda: configs.feature_uncertainty(300, 32), 2),
 }

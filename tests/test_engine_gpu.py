@@ -175,6 +175,81 @@ def test_integer_exact_mask_and_count_sums():
     assert out.tolist() == [raw["counts"].numel(), int(raw["counts"].double().sum())]
 
 
+def test_wide_tensor_core_kernel_matches_golden():
+    """dense_tcr.cuh (p = 128, three particles, latent intercept) against the reference's values.
+    Stated TF32 tolerances at 333 rows: 1e-4 relative on the loss, 3e-3 relative L2 on gradients."""
+    config, golden = load_golden("logistic_wide", device=DEV)
+    S = int(golden["n_particles"])
+    loss, leaves, module = engine_eval(config, golden_noise(config, golden, DEV), S, precision="tf32")
+    site, mode = module.last_plan.dense_sites[0]
+    assert mode == abi.DENSE_TF32 and site.p == 128 and site.icpt_lat >= 0
+    assert abs(float(loss) - float(golden["loss"])) <= 1e-4 * abs(float(golden["loss"]))
+    for key, leaf in leaves.items():
+        assert rel(leaf.grad.cpu().numpy(), golden[f"grad/{key}"]) < 3e-3, key
+
+
+@pytest.mark.parametrize("n,p,S,intercept", [(1, 64, 1, True), (129, 128, 16, False), (1000, 256, 16, True),
+                                             (5000, 192, 17, True), (4097, 448, 32, False),
+                                             (70_000, 256, 32, True)])
+def test_wide_tensor_core_kernel_against_oracle(n, p, S, intercept):
+    """Shapes around the tile (128 rows), chunk (64 features), particle-slot (16 / 32) and
+    drain-group (8 tiles) boundaries of dense_tcr.cuh, minibatch weight included; the fp32 kernel
+    and the oracle agree to 1e-5, the TF32 kernel within the stated TF32 tolerance."""
+    torch.manual_seed(n + p)
+    cpu = configs.logistic(10 * n, n, p=p, intercept=intercept)
+    gpu = configs.logistic(10 * n, n, p=p, intercept=intercept, device=DEV, gen_device="cpu")
+    approx_c, leaves_c = cpu.approximation()
+    noise = {name: elbo.draw_noise(dist, S) for name, dist in approx_c.items()}
+    expected = elbo.neg_elbo(cpu.model, cpu.data, approx_c, noise, S)
+    expected.backward()
+    for precision in ("fp32", "tf32"):
+        loss, leaves, module = engine_eval(gpu, {k: v.to(DEV) for k, v in noise.items()}, S, precision)
+        assert module.last_plan.dense_sites[0][1] == (abi.DENSE_TF32 if precision == "tf32" else abi.DENSE_FP32)
+        tol = 1e-5 if precision == "fp32" else 2e-4
+        assert abs(float(loss) - float(expected)) <= tol * abs(float(expected)), precision
+        for key, leaf in leaves.items():
+            assert rel(leaf.grad.cpu().numpy(), leaves_c[key].grad.numpy()) < (1e-4 if precision == "fp32" else 5e-3), \
+                (precision, key)
+
+
+def test_wide_tensor_core_kernel_normal_and_poisson_families():
+    """The Normal (latent sigma, exp link) and Poisson (exp link, intercept) epilogues of the wide
+    kernel against the exact fp32 kernel on the same inputs (raw C-ABI, 20000 rows, p = 128)."""
+    import ctypes
+    lib = abi.load()
+    torch.manual_seed(9)
+    n, p, S = 20_000, 128, 24
+    D = p + 2
+    X = torch.randn(n, p, device=DEV)
+    z = (0.05 * torch.randn(S, D, device=DEV)).contiguous()
+    stream = torch.cuda.current_stream().cuda_stream
+    ws_bytes = lib.workspace_bytes(S, D)
+    ws = torch.empty(ws_bytes, device=DEV, dtype=torch.uint8)
+    status = torch.zeros(1, device=DEV, dtype=torch.int32)
+    mask = (torch.rand(n, device=DEV) < 0.7).to(torch.uint8)
+    for family in (abi.NORMAL, abi.POISSON):
+        y = torch.randn(n, device=DEV) if family == abi.NORMAL else torch.poisson(torch.full((n,), 1.3, device=DEV))
+        scale = abi.Link(x=None, a_const=0.0, a_lat=p + 1, a_stride=0, b_const=0.0, b_lat=-1, b_stride=0,
+                         transform=abi.T_EXP) if family == abi.NORMAL else abi.const_link(1.0)
+        site = abi.DenseSite(family=family, p=p, n_rows=n, ldx=p, X=X.data_ptr(), y=y.data_ptr(),
+                             mask=mask.data_ptr(), theta_lat=0, icpt_lat=p, icpt_const=0.25, reserved=0,
+                             scale=scale, weight=3.0)
+        results = []
+        for mode in (abi.DENSE_FP32, abi.DENSE_TF32):
+            acc = torch.zeros(S, D + 1, device=DEV, dtype=torch.float64)
+            lib.call("mnf_dense_sweep", ctypes.byref(site), mode, z.data_ptr(), S, D, acc.data_ptr(), ws.data_ptr(),
+                     ws_bytes, status.data_ptr(), stream)
+            torch.cuda.synchronize()
+            results.append(acc.cpu().numpy())
+        exact, fast = results
+        assert int(status.item()) == 0
+        assert np.max(np.abs(fast[:, 0] - exact[:, 0]) / np.abs(exact[:, 0])) < 2e-4, family
+        assert rel(fast[:, 1:1 + p], exact[:, 1:1 + p]) < 5e-3, family          # theta
+        assert rel(fast[:, 1 + p], exact[:, 1 + p]) < 5e-3, family              # intercept
+        if family == abi.NORMAL:
+            assert rel(fast[:, 2 + p], exact[:, 2 + p]) < 1e-3                    # log-sigma
+
+
 @pytest.mark.parametrize("batch_rows", [400, 1, 4097])
 def test_minibatch_scaling_against_oracle(batch_rows):
     """`batch` rescaling (declared / actual rows) on a Bernoulli(logits = X @ theta) site."""
