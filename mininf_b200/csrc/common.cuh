@@ -152,6 +152,17 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
 // ---------------------------------------------------------------------------------------------
 // log-density and partial derivatives, one (value, parameters) pair at a time
 // ---------------------------------------------------------------------------------------------
+// support of an observed value (torch.distributions' validate_args / mininf/core.py:183)
+__device__ __forceinline__ bool in_support(int family, float v) {
+  switch (family) {
+    case MNF_NORMAL: return v == v;
+    case MNF_GAMMA: return v >= 0.0f;
+    case MNF_BETA: return v >= 0.0f && v <= 1.0f;
+    case MNF_POISSON: return v >= 0.0f && floorf(v) == v;
+    default: return v == 0.0f || v == 1.0f;
+  }
+}
+
 struct Dens {
   float lp;  // log p(v | p0, p1)
   float dv;  // d lp / d v

@@ -109,7 +109,7 @@ dense_simt_kernel(mnf_dense_site_t site, const float* __restrict__ z, int S, int
         for (int j = 0; j < p; ++j) eta = fmaf(xr[j], th[j], eta);
         const float y = __ldg(site.y + row);
         dense_point(site.family, y, eta, sPar[s].scale, lp, deta, dsig);
-        if (y != y) bad |= MNF_ST_BAD_VALUE;
+        if (!in_support(site.family, y)) bad |= MNF_ST_BAD_VALUE;
       }
       sR[s * (kSimtRows + 1) + r] = deta;
       lp = warp_sum(lp);

@@ -446,7 +446,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
             lv[q] = live ? 1.f : 0.f;
             if (live) {
               live_cnt += 1.f;
-              if (yr[q] != yr[q]) bad_value = true;
+              if (!in_support(FAMILY, yr[q])) bad_value = true;
               if (FAMILY == MNF_POISSON) lgam += (double)lgammaf(yr[q] + 1.0f);
             }
           }

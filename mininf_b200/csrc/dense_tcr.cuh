@@ -433,7 +433,7 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
       fetch(k + 1, y_next, l_next);
       if (live != 0.f) {
         live_rows += 1.0;
-        if (y != y) bad_value = true;
+        if (!in_support(FAMILY, y)) bad_value = true;
         if (FAMILY == MNF_POISSON) lgam += (double)lgammaf(y + 1.0f);
       }
       // the gradient group that ended two tiles ago has been issued (its R tile was handed over

@@ -74,16 +74,6 @@ __device__ __forceinline__ void normal_point_hoisted(float v, float u0, int t0, 
   du1 = fmaf(r, r, -1.0f) * sc.inv * sc.dsig;
 }
 
-__device__ __forceinline__ bool in_support(int family, float v) {
-  switch (family) {
-    case MNF_NORMAL: return v == v;
-    case MNF_GAMMA: return v >= 0.0f;
-    case MNF_BETA: return v >= 0.0f && v <= 1.0f;
-    case MNF_POISSON: return v >= 0.0f && floorf(v) == v;
-    default: return v == 0.0f || v == 1.0f;
-  }
-}
-
 // partial layout per CTA: [S][ncol], ncol = 1 + 4*NSITES: col 0 scaled log-density, then per site
 // the scaled sums of (du0, du0*x0, du1, du1*x1)
 template <int NSITES, int Q>

@@ -158,6 +158,10 @@ class Plan:
 
         self.dense_sites: List[Tuple[abi.DenseSite, int]] = []
         self.sweep_groups: List[Any] = []
+        self._host_tables: List[Tuple[Any, torch.Tensor]] = []   # (host struct array, its device copy)
+        self._folded_constant = False     # a tensor parameter was folded into a constant link
+        self._sources: List[Tuple[int, int]] = []
+        self.rebindable = False
         small_observed: List[abi.Site] = []
         small_global: List[abi.Site] = []
         big: Dict[int, List[abi.Site]] = {}
@@ -181,7 +185,9 @@ class Plan:
         if not sites:
             return None
         array = (abi.Site * len(sites))(*sites)
-        return _bytes_to_device(array, self.device), len(sites), max(s.numel for s in sites)
+        table = _bytes_to_device(array, self.device)
+        self._host_tables.append((array, table))
+        return table, len(sites), max(s.numel for s in sites)
 
     def _latent_column(self, ref: LatentRef, numel: int, what: str) -> Tuple[int, int]:
         """(column, stride) of a latent reference inside a site of ``numel`` elements."""
@@ -227,6 +233,7 @@ class Plan:
             return link
         tensor = torch.as_tensor(param)
         if tensor.numel() == 1 or bool((tensor == tensor.reshape(-1)[0]).all()):
+            self._folded_constant = self._folded_constant or tensor.numel() > 1
             return abi.const_link(float(tensor.reshape(-1)[0]))
         data = _f32(tensor.expand(shape), self.device).reshape(-1)
         self.keepalive.append(data)
@@ -421,6 +428,93 @@ class Plan:
                                       "32 particles, and 16-byte aligned rows")
         mode = abi.DENSE_TF32 if (self.dense_mode in ("auto", "tf32") and tf32_ok) else abi.DENSE_FP32
         self.dense_sites.append((site, mode))
+
+    # ------------------------------------------------------------------------------------------
+    # rebinding to new conditioned tensors of the same layout (minibatch streams)
+    # ------------------------------------------------------------------------------------------
+    _PER_STEP_FIELDS = ("loc", "scale", "grad_loc", "grad_scale", "eps")   # RowLatent, set by every step
+
+    def _host_structs(self) -> List[Any]:
+        structs: List[Any] = [site for site, _ in self.dense_sites]
+        for group in self.sweep_groups:
+            structs.extend(group[i] for i in range(len(group)))
+        for array, _ in self._host_tables:
+            structs.extend(array[i] for i in range(len(array)))
+        structs.extend(self.row_groups.values())
+        return structs
+
+    def _walk_pointers(self, struct: Any, visit: Callable[[Any, str, int], None]) -> None:
+        per_step = self._PER_STEP_FIELDS if isinstance(struct, abi.RowLatent) else ()
+        for name, ctype in struct._fields_:
+            if ctype is C.c_void_p:
+                value = getattr(struct, name)
+                if value and name not in per_step:
+                    visit(struct, name, value)
+            elif isinstance(ctype, type) and issubclass(ctype, C.Structure):
+                self._walk_pointers(getattr(struct, name), visit)
+            elif isinstance(ctype, type) and issubclass(ctype, C.Array):
+                array = getattr(struct, name)
+                for i in range(len(array)):
+                    if isinstance(array[i], C.Structure):
+                        self._walk_pointers(array[i], visit)
+
+    @staticmethod
+    def _ranges(leaves: Sequence[torch.Tensor]) -> List[Tuple[int, int]]:
+        return [(t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()) for t in leaves]
+
+    def bind_sources(self, leaves: Sequence[torch.Tensor]) -> None:
+        """Declare the conditioned tensors this plan was lowered from. The plan becomes
+        *rebindable* when every data pointer it stores lies inside one of them (no converted or
+        re-laid-out copies, no tensor folded into a constant, no overlapping sources): then a new
+        batch of the same shapes, dtypes and strides only needs its pointers patched."""
+        ranges = self._ranges(leaves)
+        self._sources = ranges
+        contiguous = all(t.is_contiguous() for t in leaves)
+        ordered = sorted(r for r in ranges if r[1] > r[0])
+        disjoint = all(a[1] <= b[0] for a, b in zip(ordered, ordered[1:]))
+        resolved = [True]
+
+        def visit(struct: Any, name: str, value: int) -> None:
+            if not any(lo <= value < hi for lo, hi in ranges):
+                resolved[0] = False
+
+        for struct in self._host_structs():
+            self._walk_pointers(struct, visit)
+        self.rebindable = contiguous and disjoint and resolved[0] and not self._folded_constant
+
+    def rebind(self, leaves: Sequence[torch.Tensor]) -> bool:
+        """Point the plan at new conditioned tensors (same order and layout as the ones given to
+        :meth:`bind_sources`). Returns ``False`` if the new tensors cannot be used as they are
+        (the caller then lowers a fresh plan). The support checks the reference repeats on every
+        call (mininf/core.py:142-189) are left to the kernels' status word for the new data."""
+        new = self._ranges(leaves)
+        old = self._sources
+        if not self.rebindable or len(new) != len(old) or \
+                any(a[1] - a[0] != b[1] - b[0] for a, b in zip(old, new)) or \
+                not all(t.is_contiguous() and t.device == self.device for t in leaves):
+            return False
+        if new == old:
+            return True
+        ordered = sorted(r for r in new if r[1] > r[0])
+        if not all(a[1] <= b[0] for a, b in zip(ordered, ordered[1:])):
+            return False
+
+        def translate(value: int) -> int:
+            for (lo, hi), (new_lo, _) in zip(old, new):
+                if lo <= value < hi:
+                    return new_lo + (value - lo)
+            raise AssertionError("unresolved data pointer in a rebindable plan")
+
+        # the tcgen05 kernels need 16-byte aligned rows; check before anything is modified
+        for site, mode in self.dense_sites:
+            if mode == abi.DENSE_TF32 and translate(site.X) % 16:
+                return False
+        for struct in self._host_structs():
+            self._walk_pointers(struct, lambda st, name, value: setattr(st, name, translate(value)))
+        for array, table in self._host_tables:
+            table.copy_(torch.frombuffer(bytearray(bytes(array)), dtype=torch.uint8))
+        self._sources = new
+        return True
 
     # ------------------------------------------------------------------------------------------
     # execution

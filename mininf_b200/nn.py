@@ -113,13 +113,24 @@ def _unwrap_conditioning(model: Callable) -> Tuple[Callable, List[Tuple[str, Any
     return model, pinned
 
 
-def _tensor_key(value: Any) -> Tuple:
+def _layout_key(value: Any) -> Tuple:
+    """What a plan depends on structurally: the layout of a conditioned value, not its address."""
     if isinstance(value, torch.masked.MaskedTensor):
-        return ("masked",) + _tensor_key(value.get_data()) + _tensor_key(value.get_mask())
+        return ("masked",) + _layout_key(value.get_data()) + _layout_key(value.get_mask())
     if isinstance(value, torch.Tensor):
-        return (value.data_ptr(), tuple(value.shape), str(value.dtype), str(value.device),
-                value._version)
+        return (tuple(value.shape), tuple(value.stride()), str(value.dtype), str(value.device))
     return (repr(value),)
+
+
+def _leaves(values: List[Any]) -> List[torch.Tensor]:
+    """Tensors behind the conditioned values, in a fixed order (data then mask for masked ones)."""
+    out: List[torch.Tensor] = []
+    for value in values:
+        if isinstance(value, torch.masked.MaskedTensor):
+            out.extend([value.get_data(), value.get_mask()])
+        elif isinstance(value, torch.Tensor):
+            out.append(value)
+    return out
 
 
 class _EngineFunction(torch.autograd.Function):
@@ -282,20 +293,34 @@ class EvidenceLowerBoundLoss(nn.Module):
                     dense_mode=self.dense_precision)
 
     def _plan_for(self, model: Callable, approximation: DistributionDict) -> Any:
+        """Cached plan for this model, data layout and approximation structure. The same tensors
+        (address and version counter) reuse the plan as it is; new tensors of the same layout -
+        the next minibatch - only have their pointers patched (:meth:`Plan.rebind`) when the plan
+        reads them in place; anything else is traced and lowered again."""
         if not self.cache:
             return self._build_plan(model, approximation)
         base, pinned = _unwrap_conditioning(model)
-        key = (id(base), tuple((name, _tensor_key(val)) for name, val in pinned),
+        values = [val for _, val in pinned]
+        leaves = _leaves(values)
+        key = (id(base), tuple((name, _layout_key(val)) for name, val in pinned),
                tuple((name, type(factor).__name__, tuple(factor.batch_shape))
                      for name, factor in approximation.items()),
                self.n_particles, self.dense_precision)
+        bound = tuple((leaf.data_ptr(), leaf._version) for leaf in leaves)
         plan = self._plans.get(key)
-        if plan is None:
-            if len(self._plans) >= 8:
-                self._plans.pop(next(iter(self._plans)))
-            plan = self._build_plan(model, approximation)
-            plan._pin = (base, [val for _, val in pinned])   # keep ids / data pointers valid
-            self._plans[key] = plan
+        if plan is not None:
+            if plan._bound == bound:
+                return plan
+            if plan.rebind(leaves):
+                plan._bound, plan._pin = bound, (base, values)
+                return plan
+            del self._plans[key]
+        if len(self._plans) >= 8:
+            self._plans.pop(next(iter(self._plans)))
+        plan = self._build_plan(model, approximation)
+        plan.bind_sources(leaves)
+        plan._bound, plan._pin = bound, (base, values)   # keep ids / data pointers valid
+        self._plans[key] = plan
         return plan
 
     # -- noise ------------------------------------------------------------------------------

@@ -270,6 +270,42 @@ def test_minibatch_scaling_against_oracle(batch_rows):
             assert rel(leaf.grad.cpu().numpy(), leaves_c[key].grad.numpy()) < (1e-4 if precision == "fp32" else 5e-3)
 
 
+def test_minibatch_stream_rebinds_the_plan_instead_of_retracing():
+    """examples/minibatch.md:44-60 conditions the model on a fresh batch every step. Batches of the
+    same layout reuse one plan with patched pointers; values equal those of a fresh evaluation;
+    data written in place is picked up; out-of-support data in a later batch is still reported."""
+    S, p, rows = 8, 128, 3000
+    batches = [configs.logistic(90_000, rows, p=p, batch_id=i, device=DEV, gen_device="cpu", intercept=True)
+               for i in range(3)]
+    torch.manual_seed(3)
+    approx, leaves = batches[0].approximation(device=DEV)
+    noise = {name: elbo.draw_noise(dist, S).to(DEV) for name, dist in approx.items()}
+    model = lambda: batches[0].model(mininf)   # noqa: E731  one model, many conditionings
+    stream = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+    values, plans = [], []
+    for config in batches + batches[:1]:
+        values.append(float(stream(mininf.condition(model, **config.data), approx, _noise=noise)))
+        plans.append(stream.last_plan)
+    assert all(plan is plans[0] for plan in plans) and plans[0].rebindable
+    assert values[3] == values[0]
+    for config, value in zip(batches, values):
+        fresh = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+        assert float(fresh(mininf.condition(model, **config.data), approx, _noise=noise)) == value
+    assert len({round(v, 3) for v in values[:3]}) == 3
+    # in-place refill of the same buffers (a pinned-memory loader writing into a staging batch)
+    staging = {k: v.clone() for k, v in batches[0].data.items()}
+    first = float(stream(mininf.condition(model, **staging), approx, _noise=noise))
+    assert first == values[0]
+    for key in staging:
+        staging[key].copy_(batches[1].data[key])
+    assert float(stream(mininf.condition(model, **staging), approx, _noise=noise)) == values[1]
+    assert stream.last_plan is plans[0]
+    # the support check of the reference (mininf/core.py:183) survives rebinding via the status word
+    staging["y"][17] = 2.0
+    with pytest.raises(ValueError, match="not in the support"):
+        stream(mininf.condition(model, **staging), approx, _noise=noise)
+
+
 def test_readme_training_loop_recovers_posterior():
     """README.md:57-70: Beta approximation of the coin bias trained with Adam through the
     unchanged API; exact posterior is Beta(11, 3)."""

@@ -140,3 +140,77 @@ def test_tracer_keeps_reference_errors():
 
     with SiteTableTracer(), pytest.raises(ValueError, match="not supported for masked data"):
         mininf.condition(batched, y=masked)()
+
+
+# -------------------------------------------------------------------------------------------------
+# rebinding a plan to the next minibatch (Plan.bind_sources / Plan.rebind)
+# -------------------------------------------------------------------------------------------------
+def _leaves(data):
+    from mininf_b200.nn import _leaves as leaves
+    return leaves(list(data.values()))
+
+
+def test_plan_rebinds_dense_site_to_a_new_batch():
+    first = configs.logistic(100_000, 512, p=64)
+    second = configs.logistic(100_000, 512, p=64, batch_id=1)
+    sites, specs = trace(lambda: first.model(mininf), {"theta": (abi.NORMAL, torch.randn(64))}, first.data)
+    plan = Plan(sites, specs, 16, CPU, dry_run=True)
+    plan.bind_sources(_leaves(first.data))
+    assert plan.rebindable
+    site, mode = plan.dense_sites[0]
+    assert mode == abi.DENSE_TF32 and site.X == first.data["X"].data_ptr() and site.y == first.data["y"].data_ptr()
+    assert plan.rebind(_leaves(second.data))
+    assert site.X == second.data["X"].data_ptr() and site.y == second.data["y"].data_ptr()
+    # a batch whose rows are not 16-byte aligned cannot feed the TMA path: the caller re-lowers
+    shifted = {"X": torch.randn(512 * 64 + 1)[1:].view(512, 64), "y": second.data["y"]}
+    assert shifted["X"].data_ptr() % 16 != 0
+    assert not plan.rebind(_leaves(shifted))
+    assert site.X == second.data["X"].data_ptr()            # untouched by the refused rebind
+    # different sizes never rebind
+    assert not plan.rebind(_leaves(configs.logistic(100_000, 256, p=64).data))
+
+
+def test_plan_rebinds_masked_sweep_groups_and_covariates():
+    n = 5000
+
+    def model():
+        a = mininf.sample("a", Normal(0, 1))
+        b = mininf.sample("b", Normal(0, 1))
+        with mininf.no_log_prob():
+            x = mininf.sample("x", Normal(0, 1), n)
+        mininf.sample("counts", Poisson((a + b * x).exp()))
+
+    def batch(seed):
+        raw = configs.missing(n, seed0=seed).extra["raw"]
+        return {"x": raw["x"], "counts": torch.masked.as_masked_tensor(raw["counts"], raw["m_counts"])}
+
+    first, second = batch(5000), batch(7000)
+    latents = {k: (abi.NORMAL, torch.randn(())) for k in "ab"}
+    sites, specs = trace(model, latents, first)
+    plan = Plan(sites, specs, 8, CPU, dry_run=True)
+    plan.bind_sources(_leaves(first))
+    assert plan.rebindable and len(plan.sweep_groups) == 1
+    site = plan.sweep_groups[0][0]
+    assert (site.value, site.mask, site.param[0].x) == (first["counts"].get_data().data_ptr(),
+                                                       first["counts"].get_mask().data_ptr(), first["x"].data_ptr())
+    assert plan.rebind(_leaves(second))
+    assert (site.value, site.mask, site.param[0].x) == (second["counts"].get_data().data_ptr(),
+                                                       second["counts"].get_mask().data_ptr(), second["x"].data_ptr())
+    # a covariate captured by the model's closure is not a conditioned tensor: such plans re-lower
+    config = configs.missing(n)
+    latents = {k: (abi.NORMAL, torch.randn(())) for k in "abcd"}
+    latents["sigma"] = (abi.GAMMA, torch.tensor(0.7))
+    sites, specs = trace(lambda: config.model(mininf), latents, config.data)
+    plan = Plan(sites, specs, 8, CPU, dry_run=True)
+    plan.bind_sources(_leaves(config.data))
+    assert not plan.rebindable
+
+
+def test_plans_with_converted_copies_are_not_rebindable():
+    config = configs.logistic(100_000, 300, p=64)
+    data = {"X": config.data["X"], "y": config.data["y"].double()}       # float64 -> the plan owns a float32 copy
+    sites, specs = trace(lambda: config.model(mininf), {"theta": (abi.NORMAL, torch.randn(64))}, data)
+    plan = Plan(sites, specs, 4, CPU, dry_run=True)
+    plan.bind_sources(_leaves(data))
+    assert not plan.rebindable and not plan.rebind(_leaves(data | {"y": data["y"].clone()}))
+    assert plan.rebind(_leaves(data)) is False
