@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MNF_ABI_VERSION 5
+#define MNF_ABI_VERSION 6
 
 /* error codes */
 #define MNF_OK 0
@@ -158,8 +158,8 @@ typedef struct mnf_rowlatent {
 
 /* precision modes of the dense sweep */
 #define MNF_DENSE_FP32 0   /* SIMT fp32 FMA, any p / S                                          */
-#define MNF_DENSE_TF32 1   /* tcgen05 kind::tf32, operands rounded-to-nearest to TF32 in-kernel, */
-                           /* fp32 accumulate in TMEM; needs p in {32,64,96,128}, S in {16..64} %16==0 */
+#define MNF_DENSE_TF32 1   /* tcgen05 kind::tf32: operands rounded to nearest to TF32, fp32        */
+                           /* accumulate in TMEM; shapes as reported by mnf_dense_tf32_kernel       */
 
 typedef struct mnf_device_info {
   int32_t sm_count;
@@ -200,6 +200,15 @@ int mnf_rsample(const mnf_latent_t* latents_dev, int n_latents, int n_particles,
  * X and y are read exactly once per call for all particles and both directions
  * (replaces aten::mv + MvBackward + the elementwise log_prob chain).
  */
+/*
+ * Which tcgen05 kernel MNF_DENSE_TF32 runs for a dense site of `family` with p features and S
+ * particles (host-only query, no device needed): 0 = shape not covered (use MNF_DENSE_FP32),
+ * 1 = csrc/dense_tc.cuh (p == 64, S <= 64), 2 = csrc/dense_tcr.cuh (p = 64 C, S <= 32, within
+ * 512 TMEM columns and 227 KB of shared memory). Intercepts are supported by both. X must also be
+ * 16-byte aligned with ldx % 4 == 0 and fewer than 2^31 rows.
+ */
+int mnf_dense_tf32_kernel(int family, int p, int n_particles);
+
 int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int n_particles,
                     int n_latent_total, double* acc, void* workspace, size_t workspace_bytes,
                     uint32_t* status, void* stream);

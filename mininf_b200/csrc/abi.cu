@@ -4,6 +4,9 @@
 #include <algorithm>
 #include <mutex>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "dense_simt.cuh"
 #include "dense_tc.cuh"
@@ -97,13 +100,13 @@ int make_x_map(const mnf_dense_site_t& site, CUtensorMapSwizzle swizzle, CUtenso
   return MNF_OK;
 }
 
-template <int FAMILY>
+template <int FAMILY, bool ICPT>
 int launch_dense_tc(const mnf_dense_site_t& site, const float* z, int S, int D, float* partial,
                     uint32_t* status, int grid, cudaStream_t stream) {
   CUtensorMap map_k, map_mn;
   if (int rc = make_x_map(site, CU_TENSOR_MAP_SWIZZLE_128B, &map_k)) return rc;
   if (int rc = make_x_map(site, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, &map_mn)) return rc;
-  auto kernel = tc::dense_tc_kernel<FAMILY>;
+  auto kernel = tc::dense_tc_kernel<FAMILY, ICPT>;
   MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)tc::kSmemBytes));
   kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_k, map_mn, site, z, S, D, partial, status);
@@ -133,6 +136,24 @@ bool tcr_shape(int p, int S, int max_smem_optin, TcrShape* out) {
     }
   }
   return false;
+}
+
+// 0 = no tcgen05 kernel for this shape, 1 = dense_tc.cuh, 2 = dense_tcr.cuh
+int dense_tf32_kernel(int family, int p, int S, int max_smem_optin, TcrShape* sh) {
+  if (family != MNF_NORMAL && family != MNF_BERNOULLI_LOGITS && family != MNF_POISSON) return 0;
+  if (S <= 0) return 0;
+  bool c2_shape = p == tc::kP && S <= tc::kNS;
+  bool wide_shape = tcr_shape(p, S, max_smem_optin, sh);
+  if (c2_shape && wide_shape) {
+    // both cover p = 64 with S <= 32. Measured on B200: dense_tc.cuh wins for
+    // the Normal and Poisson epilogues; the Bernoulli epilogue (exp, reciprocal, log per point) costs
+    // per particle SLOT, and dense_tcr.cuh has 16 or 32 of them where dense_tc.cuh always has 64.
+    const char* force = std::getenv("MNF_DENSE_TC_KERNEL");   // developer override: "tc" | "tcr"
+    const bool prefer_wide = force ? std::strcmp(force, "tcr") == 0 : family == MNF_BERNOULLI_LOGITS;
+    c2_shape = !prefer_wide;
+    wide_shape = prefer_wide;
+  }
+  return c2_shape ? 1 : (wide_shape ? 2 : 0);
 }
 
 template <int FAMILY, int NS, bool ICPT>
@@ -245,6 +266,11 @@ int mnf_rsample(const mnf_latent_t* latents_dev, int n_latents, int n_particles,
   return MNF_OK;
 }
 
+int mnf_dense_tf32_kernel(int family, int p, int n_particles) {
+  TcrShape sh;
+  return dense_tf32_kernel(family, p, n_particles, 232448 /* sm_100 opt-in shared memory */, &sh);
+}
+
 int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int n_particles,
                     int n_latent_total, double* acc, void* workspace, size_t workspace_bytes,
                     uint32_t* status, void* stream_) {
@@ -273,12 +299,12 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
     const bool aligned = (reinterpret_cast<uintptr_t>(s.X) % 16 == 0) && (s.ldx % 4 == 0) &&
                          s.n_rows < (int64_t)1 << 31;
     const bool has_icpt = s.icpt_lat >= 0 || s.icpt_const != 0.0f;
-    const bool c2_shape = p == tc::kP && S <= tc::kNS && !has_icpt;   // dense_tc.cuh
     TcrShape sh;
-    const bool wide_shape = !c2_shape && tcr_shape(p, S, c->max_smem_optin, &sh);   // dense_tcr.cuh
+    const int which = dense_tf32_kernel(s.family, p, S, c->max_smem_optin, &sh);
+    const bool c2_shape = which == 1, wide_shape = which == 2;
     if (!aligned || c->cc_major != 10 || !(c2_shape || wide_shape))
       return fail(MNF_E_UNSUPPORTED,
-                  "mnf_dense_sweep: TF32 mode needs p == 64 with S <= 64 and no intercept, or p a "
+                  "mnf_dense_sweep: TF32 mode needs p == 64 with S <= 64, or p a "
                   "multiple of 64 with S <= 32 (and (2 + p/32) * S within 512 TMEM columns), 16-byte "
                   "aligned rows and an sm_100 device%s%s");
     const int64_t n_tiles = (s.n_rows + tc::kTileM - 1) / tc::kTileM;
@@ -287,9 +313,15 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
       return fail(MNF_E_INVALID, "mnf_dense_sweep: workspace too small%s%s");
     int rc;
     if (c2_shape) {
-      if (s.family == MNF_NORMAL) rc = launch_dense_tc<MNF_NORMAL>(s, z, S, D, partial, status, grid, stream);
-      else if (s.family == MNF_BERNOULLI_LOGITS) rc = launch_dense_tc<MNF_BERNOULLI_LOGITS>(s, z, S, D, partial, status, grid, stream);
-      else rc = launch_dense_tc<MNF_POISSON>(s, z, S, D, partial, status, grid, stream);
+      if (s.family == MNF_NORMAL)
+        rc = has_icpt ? launch_dense_tc<MNF_NORMAL, true>(s, z, S, D, partial, status, grid, stream)
+                      : launch_dense_tc<MNF_NORMAL, false>(s, z, S, D, partial, status, grid, stream);
+      else if (s.family == MNF_BERNOULLI_LOGITS)
+        rc = has_icpt ? launch_dense_tc<MNF_BERNOULLI_LOGITS, true>(s, z, S, D, partial, status, grid, stream)
+                      : launch_dense_tc<MNF_BERNOULLI_LOGITS, false>(s, z, S, D, partial, status, grid, stream);
+      else
+        rc = has_icpt ? launch_dense_tc<MNF_POISSON, true>(s, z, S, D, partial, status, grid, stream)
+                      : launch_dense_tc<MNF_POISSON, false>(s, z, S, D, partial, status, grid, stream);
     } else {
       if (s.family == MNF_NORMAL) rc = launch_dense_tcr<MNF_NORMAL>(s, z, S, D, sh, has_icpt, partial, status, grid, stream);
       else if (s.family == MNF_BERNOULLI_LOGITS) rc = launch_dense_tcr<MNF_BERNOULLI_LOGITS>(s, z, S, D, sh, has_icpt, partial, status, grid, stream);

@@ -84,8 +84,8 @@ constexpr uint32_t kOffBar = kOffY + kMnStages * kYBytes;
 constexpr uint32_t kNumBars = 2 * kKStages + 2 * kMnStages + 8;  // + eta_full, r_ready, g_full, g_empty (x2 each)
 constexpr uint32_t kOffMisc = kOffBar + 8 * kNumBars;         // tmem slot, counters, per-particle params
 constexpr uint32_t kOffGrad = kOffMisc + 64 + kNS * 16;         // drained gradient [kNS][kP + 1] fp32
-constexpr uint32_t kOffStat = kOffGrad + kNS * (kP + 1) * 4;    // per-particle statistic exchange [kNS]
-constexpr uint32_t kSmemBytes = kOffStat + kNS * 4 + 1024 /* alignment slack */;
+constexpr uint32_t kOffStat = kOffGrad + kNS * (kP + 1) * 4;    // per-particle statistic exchange [2][kNS]
+constexpr uint32_t kSmemBytes = kOffStat + 2 * kNS * 4 + 1024 /* alignment slack */;
 static_assert(kOffMisc % 16 == 0, "misc block alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -279,7 +279,7 @@ struct TileCounters {   // particle-independent sums over the live rows this CTA
 };
 
 // partial layout per CTA: [S][ncol], ncol = 1 + kP + 2 (same as the SIMT variant)
-template <int FAMILY>
+template <int FAMILY, bool ICPT>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_mn,
                 mnf_dense_site_t site, const float* __restrict__ z, int S, int D,
@@ -429,6 +429,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
       if (i < my_tiles) fetch(i, yq[i], mq[i]);
     }
     bool bad_value = false;
+    int live_total = 0;          // per-lane sums, combined once after the last tile: fp64 adds and
+    double lgam_total = 0.0;     // shuffles are slow enough to matter inside the per-tile loop
     for (int64_t k0 = 0; k0 < my_tiles; k0 += kMnStages) {
 #pragma unroll
       for (int i = 0; i < kMnStages; ++i) {
@@ -437,29 +439,22 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
           mbar_wait(bMnEmpty + 8 * i, (uint32_t)(((k / kMnStages) & 1) ^ 1));
           const float yr[4] = {yq[i].x, yq[i].y, yq[i].z, yq[i].w};
           float yv[4], lv[4];
-          float live_cnt = 0.f;
-          double lgam = 0.0;
+          float lgam = 0.f;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const bool live = ((mq[i] >> (8 * q)) & 0xFFu) != 0;
             yv[q] = live ? yr[q] : 0.f;
             lv[q] = live ? 1.f : 0.f;
             if (live) {
-              live_cnt += 1.f;
+              ++live_total;
               if (!in_support(FAMILY, yr[q])) bad_value = true;
-              if (FAMILY == MNF_POISSON) lgam += (double)lgammaf(yr[q] + 1.0f);
+              if (FAMILY == MNF_POISSON) lgam += log_factorial(yr[q]);
             }
           }
+          if (FAMILY == MNF_POISSON) lgam_total += (double)lgam;
           const uint32_t dst = sY + (uint32_t)i * kYBytes + lane * 32;
           sts128(dst, __float_as_uint(yv[0]), __float_as_uint(lv[0]), __float_as_uint(yv[1]), __float_as_uint(lv[1]));
           sts128(dst + 16, __float_as_uint(yv[2]), __float_as_uint(lv[2]), __float_as_uint(yv[3]), __float_as_uint(lv[3]));
-          // particle-independent tile sums; ordered before the consumers by the mn_full barrier chain
-          live_cnt = warp_sum(live_cnt);
-          if (FAMILY == MNF_POISSON) lgam = warp_sum(lgam);
-          if (lane == 0) {
-            atomicAdd(&counters->n_live, live_cnt);
-            if (FAMILY == MNF_POISSON) atomicAdd(&counters->lgamma_sum, lgam);
-          }
           __syncwarp();
           if (lane == 0) mbar_arrive(bMnFull + 8 * i);
           if (k + kMnStages < my_tiles) fetch(k + kMnStages, yq[i], mq[i]);
@@ -467,6 +462,14 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
       }
     }
     if (bad_value) atomicOr(status, MNF_ST_BAD_VALUE);
+    // particle-independent sums of this CTA; the epilogue warps read them behind the same barrier
+    const float live_sum = warp_sum((float)live_total);
+    if (FAMILY == MNF_POISSON) lgam_total = warp_sum(lgam_total);
+    if (lane == 0) {
+      counters->n_live = live_sum;
+      counters->lgamma_sum = lgam_total;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"((kEpiWarps + 1) * 32) : "memory");
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer: warp-uniform loop, one elected lane issues ================
     constexpr uint32_t idesc_eta = idesc_tf32(kNS, kTileM, 0, 0);   // M=64 N=128, B K-major
@@ -539,6 +542,9 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
     // Statistics: with the 16x256b access shape thread t works on particles 16*warp + t/4 (A) and
     // + 8 (B), columns 8g + 2*(t%4) + {0,1} of every 8-column group.
     double stA_total = 0.0, stB_total = 0.0;  // Normal: sum r^2 | others: sum log-density (w/o lgamma)
+    double scA_total = 0.0, scB_total = 0.0;  // sum of scores: the intercept gradient (ICPT only)
+    const float icptA = ICPT ? sPar[warp * 16 + (lane >> 2)].icpt : 0.f;
+    const float icptB = ICPT ? sPar[warp * 16 + (lane >> 2) + 8].icpt : 0.f;
     // drained gradient tiles live in shared memory, one padded row per particle (conflict-free)
     float* grad_row = reinterpret_cast<float*>(gbase + kOffGrad) + (size_t)(lane < 16 ? s : 0) * (kP + 1);
     if (lane < 16)
@@ -566,8 +572,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
     };
 
     // one (row, particle) point: score for the gradient product and the running statistic
-    auto point = [&](uint32_t& cell, float y, float live, float& stat) {
-      const float eta = __uint_as_float(cell);
+    auto point = [&](uint32_t& cell, float y, float live, float icpt, float& stat, float& ssum) {
+      const float eta = ICPT ? __uint_as_float(cell) + icpt : __uint_as_float(cell);
       float score;
       if (FAMILY == MNF_NORMAL) {
         score = fmaf(-live, eta, y);             // live * (y - eta); 1/sigma^2 applied at the end
@@ -577,26 +583,27 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
         const float inv = __fdividef(1.0f, 1.0f + e);
         const float sig = eta >= 0.f ? inv : e * inv;
         score = live * (y - sig);
-        stat += live * (y * eta - (fmaxf(eta, 0.f) + log1pf(e)));
+        stat += live * (y * eta - (fmaxf(eta, 0.f) + __logf(1.0f + e)));   // softplus, abs. error ~1e-7
       } else {
-        const float rate = expf(eta);
+        const float rate = __expf(eta);
         score = live * (y - rate);
         stat += live * fmaf(y, eta, -rate);
       }
+      if (ICPT) ssum += score;
       cell = rn_tf32(score);
     };
     // 32 columns (tile rows): thread t touches rows 32ch + 8g + 2(t%4) + {0,1}; their (y, live)
     // pairs are one 16-byte shared-memory word
-    auto process = [&](uint32_t (&v)[16], const float4* yl, int ch, float& sa, float& sb) {
+    auto process = [&](uint32_t (&v)[16], const float4* yl, int ch, float& sa, float& sb, float& ra, float& rb) {
       float4 w[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) w[g] = yl[16 * ch + 4 * g + (lane & 3)];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        point(v[4 * g + 0], w[g].x, w[g].y, sa);
-        point(v[4 * g + 1], w[g].z, w[g].w, sa);
-        point(v[4 * g + 2], w[g].x, w[g].y, sb);
-        point(v[4 * g + 3], w[g].z, w[g].w, sb);
+        point(v[4 * g + 0], w[g].x, w[g].y, icptA, sa, ra);
+        point(v[4 * g + 1], w[g].z, w[g].w, icptA, sa, ra);
+        point(v[4 * g + 2], w[g].x, w[g].y, icptB, sb, rb);
+        point(v[4 * g + 3], w[g].z, w[g].w, icptB, sb, rb);
       }
     };
 
@@ -614,29 +621,33 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
       const uint32_t t_eta = tmem + lane_base + kColEta + b * kTileM;
       // software pipeline over four 32-column chunks: the next chunk's tcgen05.ld is in flight
       // while the current one is processed; R^T replaces eta^T in place (A operand of the G product)
-      float sa = 0.f, sb = 0.f;
+      float sa = 0.f, sb = 0.f, ra = 0.f, rb = 0.f;
       uint32_t va[16], vb[16];
       tc_ld_16x256b_x4(t_eta, va);
       tc_wait_ld();
       tc_ld_16x256b_x4(t_eta + 32, vb);
-      process(va, yl, 0, sa, sb);
+      process(va, yl, 0, sa, sb, ra, rb);
       tc_st_16x256b_x4(t_eta, va);
       tc_wait_ld();
       tc_ld_16x256b_x4(t_eta + 64, va);
-      process(vb, yl, 1, sa, sb);
+      process(vb, yl, 1, sa, sb, ra, rb);
       tc_st_16x256b_x4(t_eta + 32, vb);
       tc_wait_ld();
       tc_ld_16x256b_x4(t_eta + 96, vb);
-      process(va, yl, 2, sa, sb);
+      process(va, yl, 2, sa, sb, ra, rb);
       tc_st_16x256b_x4(t_eta + 64, va);
       tc_wait_ld();
-      process(vb, yl, 3, sa, sb);
+      process(vb, yl, 3, sa, sb, ra, rb);
       tc_st_16x256b_x4(t_eta + 96, vb);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(bRReady + 8 * b);
       stA_total += (double)sa;
       stB_total += (double)sb;
+      if (ICPT) {
+        scA_total += (double)ra;
+        scB_total += (double)rb;
+      }
       TC_ACC(1);   // epi: compute
     }
     TC_FLUSH(8, 2, tid == 0);
@@ -645,18 +656,30 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
       const int64_t n_grp = (my_tiles + kFlush - 1) / kFlush;
       while (n_drained < n_grp) drain();
     }
+    asm volatile("bar.sync 1, %0;" ::"n"((kEpiWarps + 1) * 32) : "memory");   // y warp's counters are final
     // the four threads t%4 = 0..3 of a quad hold partial sums of the same two particles
     stA_total += __shfl_xor_sync(0xffffffffu, stA_total, 1);
     stA_total += __shfl_xor_sync(0xffffffffu, stA_total, 2);
     stB_total += __shfl_xor_sync(0xffffffffu, stB_total, 1);
     stB_total += __shfl_xor_sync(0xffffffffu, stB_total, 2);
+    if (ICPT) {
+      scA_total += __shfl_xor_sync(0xffffffffu, scA_total, 1);
+      scA_total += __shfl_xor_sync(0xffffffffu, scA_total, 2);
+      scB_total += __shfl_xor_sync(0xffffffffu, scB_total, 1);
+      scB_total += __shfl_xor_sync(0xffffffffu, scB_total, 2);
+    }
     float* s_stat = reinterpret_cast<float*>(gbase + kOffStat);
     if ((lane & 3) == 0) {
       s_stat[warp * 16 + (lane >> 2)] = (float)stA_total;
       s_stat[warp * 16 + (lane >> 2) + 8] = (float)stB_total;
+      if (ICPT) {
+        s_stat[kNS + warp * 16 + (lane >> 2)] = (float)scA_total;
+        s_stat[kNS + warp * 16 + (lane >> 2) + 8] = (float)scB_total;
+      }
     }
     __syncwarp();
     const float st0 = lane < 16 ? s_stat[s] : 0.f;
+    const float sc0 = (ICPT && lane < 16) ? s_stat[kNS + s] : 0.f;
 
     // ---- per-particle results: this thread is the only owner of particle s --------------------
     if (lane < 16 && s < S) {
@@ -679,7 +702,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
       out[0] = lp;
 #pragma unroll
       for (int j = 0; j < kP; ++j) out[1 + j] = grad_row[j] * gscale;
-      out[1 + kP] = 0.f;      // intercept gradient: intercepts are routed to the fp32 kernel
+      out[1 + kP] = sc0 * gscale;   // intercept gradient
       out[2 + kP] = dscale;
     }
     tc_fence_before();

@@ -28,7 +28,8 @@
 // t - kSkew: both rings drain at a steady rate and need only cover the L2 latency.
 //
 // Warps (256 threads): 0-3 epilogue (thread = tile row = TMEM lane), 4 MN-ring TMA, 5 K-ring TMA
-// and L2 prefetch, 6 idle, 7 TMEM allocation and every MMA.
+// and L2 prefetch, 6 stages y (and the mask) of each tile in shared memory, 7 TMEM allocation and
+// every MMA.
 //
 // Precision mode: the same as dense_tc.cuh (TF32 operands rounded to nearest, fp32 accumulate in
 // TMEM, the gradient accumulators ping-ponged and drained every kFlush tiles, fp32/fp64 SIMT for
@@ -79,17 +80,18 @@ constexpr int kStatFlush = 256;        // tiles between fp32 -> fp64 hand-overs 
 #endif
 constexpr int kPrefetchChunks = MNF_TCR_PREFETCH;   // L2 prefetch distance ahead of the K-ring loads
 constexpr int kEpiWarps = 4;
-constexpr int kWarpMnTma = 4, kWarpKTma = 5, kMmaWarp = 7;
+constexpr int kWarpMnTma = 4, kWarpKTma = 5, kWarpY = 6, kMmaWarp = 7;
 constexpr int kThreads = 8 * 32;
 constexpr uint32_t kTmemCols = 512;
 
 constexpr uint32_t kAtomBytes = kTileM * 128;          // 128 rows x 32 fp32
 constexpr uint32_t kChunkBytes = 2 * kAtomBytes;       // 32 KB per image of a chunk
-constexpr uint32_t kBarBytes = 8 * (4 * kMaxStages + 8);
+constexpr uint32_t kBarBytes = 8 * (4 * kMaxStages + 8 + 2);   // + y_full, y_empty
+constexpr uint32_t kYBytes = kTileM * 4;               // one tile of responses (masked-out rows are NaN)
 
 // dynamic shared memory map (bytes from the 1024-aligned base)
 struct Layout {
-  uint32_t off_k, off_mn, off_theta, off_r, off_bar, off_misc, off_par, off_stat, total;
+  uint32_t off_k, off_mn, off_theta, off_r, off_bar, off_misc, off_par, off_stat, off_y, total;
 };
 __host__ __device__ inline Layout make_layout(int NS, int C, int k_stages, int mn_stages) {
   Layout l;
@@ -101,7 +103,8 @@ __host__ __device__ inline Layout make_layout(int NS, int C, int k_stages, int m
   l.off_misc = l.off_bar + kBarBytes;                                 // tmem slot + two fp64 counters
   l.off_par = l.off_misc + 32;                                        // DenseParticle[NS], 16 B apart
   l.off_stat = l.off_par + (uint32_t)NS * 16u;                        // double [NS][2]
-  l.total = l.off_stat + (uint32_t)NS * 16u + 1024u /* alignment slack */;
+  l.off_y = l.off_stat + (uint32_t)NS * 16u;
+  l.total = l.off_y + kYBytes + 1024u /* alignment slack */;
   return l;
 }
 
@@ -152,6 +155,7 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
   const uint32_t bMnFull = bKEmpty + 8 * kMaxStages, bMnEmpty = bMnFull + 8 * kMaxStages;
   const uint32_t bEtaFull = bMnEmpty + 8 * kMaxStages, bRReady = bEtaFull + 16;
   const uint32_t bGFull = bRReady + 16, bGEmpty = bGFull + 16;
+  const uint32_t bYFull = bGEmpty + 16, bYEmpty = bYFull + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + L.off_misc);
   double* counters = reinterpret_cast<double*>(gbase + L.off_misc + 16);   // [0] live rows, [1] sum lgamma(y+1)
   auto par_at = [&](int n) { return reinterpret_cast<DenseParticle*>(gbase + L.off_par + 16 * n); };
@@ -179,6 +183,8 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
       mbar_init(bGFull + 8 * i, 1);
       mbar_init(bGEmpty + 8 * i, kEpiWarps * 32);
     }
+    mbar_init(bYFull, 1);
+    mbar_init(bYEmpty, kEpiWarps * 32);
     counters[0] = 0.0;
     counters[1] = 0.0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -265,6 +271,66 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
       }
     }
     __syncwarp();
+  } else if (warp == kWarpY) {
+    // ================= y warp: responses of each tile -> shared memory =========================
+    // The epilogue threads must not have global loads of their own in flight: their
+    // fence.proxy.async (R tile -> tensor core) waits for them, which would put a memory latency
+    // on the per-tile critical path. This warp loads y and the mask four rows per lane, two
+    // tiles ahead in registers, folds the mask into the value (NaN = masked out or past the end),
+    // and keeps the particle-independent sums (live rows, sum log y!).
+    float* sY = reinterpret_cast<float*>(gbase + L.off_y);
+    constexpr int kYDepth = 4;     // tiles in flight: one tile time is shorter than a memory latency
+    float yq[kYDepth][4];
+    auto fetch = [&](int64_t k, float (&out)[4]) {
+      const int64_t row = (blockIdx.x + k * gridDim.x) * kTileM + lane * 4;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        out[q] = __int_as_float(0x7fc00000);
+        if (k < my_tiles && row + q < site.n_rows && (site.mask == nullptr || __ldg(site.mask + row + q) != 0)) {
+          const float y = __ldg(site.y + row + q);
+          out[q] = y;
+          if (y != y) out[q] = __int_as_float(0x7fc00001);   // a live NaN: reported below
+        }
+      }
+    };
+#pragma unroll
+    for (int i = 0; i < kYDepth; ++i) fetch(i, yq[i]);
+    int live_total = 0;            // per-lane sums, combined once after the last tile
+    double lgam_total = 0.0;
+    bool bad_value = false;
+    for (int64_t k0 = 0; k0 < my_tiles; k0 += kYDepth) {
+#pragma unroll
+      for (int i = 0; i < kYDepth; ++i) {
+        const int64_t k = k0 + i;
+        if (k < my_tiles) {
+          mbar_wait(bYEmpty, (uint32_t)((k & 1) ^ 1));
+          *reinterpret_cast<float4*>(sY + lane * 4) = make_float4(yq[i][0], yq[i][1], yq[i][2], yq[i][3]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bYFull);
+          float lgam = 0.f;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float y = yq[i][q];
+            if (__float_as_int(y) == 0x7fc00001) bad_value = true;
+            if (y == y) {
+              ++live_total;
+              if (!in_support(FAMILY, y)) bad_value = true;
+              if (FAMILY == MNF_POISSON) lgam += log_factorial(y);
+            }
+          }
+          if (FAMILY == MNF_POISSON) lgam_total += (double)lgam;
+          fetch(k + kYDepth, yq[i]);
+        }
+      }
+    }
+    const double live_rows = warp_sum((double)live_total);
+    if (FAMILY == MNF_POISSON) lgam_total = warp_sum(lgam_total);
+    if (lane == 0) {
+      counters[0] = live_rows;
+      counters[1] = lgam_total;
+    }
+    if (bad_value) atomicOr(status, MNF_ST_BAD_VALUE);
+    asm volatile("bar.sync 1, %0;" ::"n"((kEpiWarps + 1) * 32) : "memory");
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer: warp-uniform loops, one elected lane issues ================
     constexpr uint32_t idesc_eta = idesc_tf32(kTileM, NS, 0, 0);   // M=128 N=NS, A and B K-major
@@ -413,29 +479,16 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
       }
     };
 
-    double live_rows = 0.0, lgam = 0.0;
-    bool bad_value = false;
-    auto fetch = [&](int64_t k, float& yv, float& lv) {
-      const int64_t row = (blockIdx.x + k * gridDim.x) * kTileM + trow;
-      yv = 0.f; lv = 0.f;
-      if (k < my_tiles && row < site.n_rows) {
-        const bool live = site.mask == nullptr || __ldg(site.mask + row) != 0;
-        const float y = __ldg(site.y + row);
-        if (live) { yv = y; lv = 1.f; }
-      }
-    };
-    float y_next, l_next;
-    fetch(0, y_next, l_next);
+    const float* sY = reinterpret_cast<const float*>(gbase + L.off_y);
 
     for (int64_t k = 0; k < my_tiles; ++k) {
       const uint32_t b = (uint32_t)(k & 1);
-      const float y = y_next, live = l_next;
-      fetch(k + 1, y_next, l_next);
-      if (live != 0.f) {
-        live_rows += 1.0;
-        if (!in_support(FAMILY, y)) bad_value = true;
-        if (FAMILY == MNF_POISSON) lgam += (double)lgammaf(y + 1.0f);
-      }
+      // this row's response, staged by the y warp (NaN = masked out or past the end)
+      mbar_wait(bYFull, (uint32_t)(k & 1));
+      const float y_raw = sY[trow];
+      mbar_arrive(bYEmpty);
+      const float live = y_raw == y_raw ? 1.f : 0.f;
+      const float y = y_raw == y_raw ? y_raw : 0.f;
       // the gradient group that ended two tiles ago has been issued (its R tile was handed over
       // two iterations back), so waiting for its commit cannot deadlock
       if (k >= 2 && ((k - 2) % kFlush) == kFlush - 1) drain();
@@ -463,9 +516,9 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
           const float inv = __fdividef(1.0f, 1.0f + e);
           const float sig = eta >= 0.f ? inv : e * inv;
           score = live * (y - sig);
-          st[n] += live * (y * eta - (fmaxf(eta, 0.f) + log1pf(e)));
+          st[n] += live * (y * eta - (fmaxf(eta, 0.f) + __logf(1.0f + e)));   // softplus, abs. error ~1e-7
         } else {
-          const float rate = expf(eta);
+          const float rate = __expf(eta);
           score = live * (y - rate);
           st[n] += live * fmaf(y, eta, -rate);
         }
@@ -481,14 +534,8 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
       while (n_drained < n_grp) drain();
     }
     hand_over();
-    live_rows = warp_sum(live_rows);
-    if (FAMILY == MNF_POISSON) lgam = warp_sum(lgam);
-    if (lane == 0) {
-      atomicAdd(&counters[0], live_rows);
-      if (FAMILY == MNF_POISSON) atomicAdd(&counters[1], lgam);
-    }
-    if (bad_value) atomicOr(status, MNF_ST_BAD_VALUE);
-    asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+    // the y warp's counters are complete once it has passed the same barrier
+    asm volatile("bar.sync 1, %0;" ::"n"((kEpiWarps + 1) * 32) : "memory");
 
     // ---- per-particle results -----------------------------------------------------------------
     if (FAMILY == MNF_NORMAL && g_owner) {

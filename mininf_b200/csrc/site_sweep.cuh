@@ -149,7 +149,7 @@ site_sweep_kernel(SweepArgs<NSITES> args, const float* __restrict__ z, int S, in
       ec[k] = 0.0f;
       if (live) {
         if (!in_support(st.family, ev[k])) bad_value = true;
-        if (st.family == MNF_POISSON) ec[k] = lgammaf(ev[k] + 1.0f);
+        if (st.family == MNF_POISSON) ec[k] = log_factorial(ev[k]);
       }
       live_bits[k] = __ballot_sync(0xffffffffu, live);
       stage[k * 32 + lane] = make_float4(ev[k], ec[k], ex0[k], ex1[k]);

@@ -11,7 +11,7 @@ from pathlib import Path
 
 from . import build as _build
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # families (include/mininf_b200.h)
 NORMAL, GAMMA, BETA, BERNOULLI_PROBS, BERNOULLI_LOGITS, POISSON = range(6)
@@ -90,6 +90,7 @@ EXPORTS = {
     "mnf_rsample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
                               C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p]),
+    "mnf_dense_tf32_kernel": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "mnf_dense_sweep": (C.c_int, [C.POINTER(DenseSite), C.c_int, C.c_void_p, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "mnf_site_sweep": (C.c_int, [C.POINTER(Site), C.c_int, C.c_void_p, C.c_int, C.c_int,

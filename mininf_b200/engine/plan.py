@@ -74,21 +74,6 @@ def _f32(tensor: torch.Tensor, device: torch.device) -> torch.Tensor:
     return tensor.detach().to(torch.float32).contiguous()
 
 
-def tf32_shape_supported(p: int, n_particles: int, has_intercept: bool) -> bool:
-    """Shapes the two tcgen05 kernels cover (mirrors ``mnf_dense_sweep`` in csrc/abi.cu):
-    dense_tc.cuh for p = 64, S <= 64 without intercept; dense_tcr.cuh for p = 64 C, S <= 32 within
-    the 512 TMEM columns and 227 KB of shared memory of an SM."""
-    if p == 64 and n_particles <= 64 and not has_intercept:
-        return True
-    if p <= 0 or p % 64 or n_particles > 32:
-        return False
-    slots, chunks = (16 if n_particles <= 16 else 32), p // 64
-    if (2 + 2 * chunks) * slots > 512:
-        return False
-    smem = 4 * 32768 + 2 * chunks * slots * 128 + 8 * slots * 128 + 160 + 32 + 32 * slots + 1024
-    return smem <= 232448
-
-
 class Plan:
     """Everything one ELBO step needs, resolved to device pointers."""
 
@@ -420,12 +405,12 @@ class Plan:
                              theta_lat=theta.offset, icpt_lat=icpt_lat, icpt_const=expr.icpt_const,
                              reserved=0, scale=scale_link, weight=float(record.scale))
         has_icpt = icpt_lat >= 0 or expr.icpt_const != 0.0
-        tf32_ok = tf32_shape_supported(p, self.S, has_icpt) and X.data_ptr() % 16 == 0 and \
+        tf32_ok = self.lib.raw("mnf_dense_tf32_kernel")(dense_family, p, self.S) != 0 and X.data_ptr() % 16 == 0 and \
             X.stride(0) % 4 == 0 and n < 2 ** 31
         if self.dense_mode == "tf32" and not tf32_ok:
             raise NotImplementedError(f"{what}: the tcgen05 TF32 kernels need p == 64 with at most 64 "
-                                      "particles and no intercept, or p a multiple of 64 with at most "
-                                      "32 particles, and 16-byte aligned rows")
+                                      "particles, or p a multiple of 64 with at most 32 particles, "
+                                      "and 16-byte aligned rows")
         mode = abi.DENSE_TF32 if (self.dense_mode in ("auto", "tf32") and tf32_ok) else abi.DENSE_FP32
         self.dense_sites.append((site, mode))
 
@@ -509,10 +494,12 @@ class Plan:
         for site, mode in self.dense_sites:
             if mode == abi.DENSE_TF32 and translate(site.X) % 16:
                 return False
+        before = [bytes(array) for array, _ in self._host_tables]
         for struct in self._host_structs():
             self._walk_pointers(struct, lambda st, name, value: setattr(st, name, translate(value)))
-        for array, table in self._host_tables:
-            table.copy_(torch.frombuffer(bytearray(bytes(array)), dtype=torch.uint8))
+        for (array, table), old_bytes in zip(self._host_tables, before):
+            if bytes(array) != old_bytes:       # tables of latent-valued sites hold no data pointers
+                table.copy_(torch.frombuffer(bytearray(bytes(array)), dtype=torch.uint8))
         self._sources = new
         return True
 

@@ -190,11 +190,12 @@ def test_wide_tensor_core_kernel_matches_golden():
 
 @pytest.mark.parametrize("n,p,S,intercept", [(1, 64, 1, True), (129, 128, 16, False), (1000, 256, 16, True),
                                              (5000, 192, 17, True), (4097, 448, 32, False),
-                                             (70_000, 256, 32, True)])
+                                             (70_000, 256, 32, True), (3000, 64, 64, True), (40_000, 64, 33, True)])
 def test_wide_tensor_core_kernel_against_oracle(n, p, S, intercept):
     """Shapes around the tile (128 rows), chunk (64 features), particle-slot (16 / 32) and
-    drain-group (8 tiles) boundaries of dense_tcr.cuh, minibatch weight included; the fp32 kernel
-    and the oracle agree to 1e-5, the TF32 kernel within the stated TF32 tolerance."""
+    drain-group (8 tiles) boundaries of dense_tcr.cuh, and p = 64 with an intercept (dense_tc.cuh),
+    minibatch weight included; the fp32 kernel and the oracle agree to 1e-5, the TF32 kernels
+    within the stated TF32 tolerance."""
     torch.manual_seed(n + p)
     cpu = configs.logistic(10 * n, n, p=p, intercept=intercept)
     gpu = configs.logistic(10 * n, n, p=p, intercept=intercept, device=DEV, gen_device="cpu")
@@ -212,13 +213,15 @@ def test_wide_tensor_core_kernel_against_oracle(n, p, S, intercept):
                 (precision, key)
 
 
-def test_wide_tensor_core_kernel_normal_and_poisson_families():
-    """The Normal (latent sigma, exp link) and Poisson (exp link, intercept) epilogues of the wide
-    kernel against the exact fp32 kernel on the same inputs (raw C-ABI, 20000 rows, p = 128)."""
+@pytest.mark.parametrize("p,S", [(128, 24), (64, 64)])
+def test_tensor_core_kernels_normal_and_poisson_families_with_intercept(p, S):
+    """The Normal (latent sigma, exp link) and Poisson (exp link) epilogues with a latent plus
+    constant intercept and a row mask, dense_tcr.cuh (p = 128) and dense_tc.cuh (p = 64), against
+    the exact fp32 kernel on the same inputs (raw C-ABI, 20000 rows)."""
     import ctypes
     lib = abi.load()
     torch.manual_seed(9)
-    n, p, S = 20_000, 128, 24
+    n = 20_000
     D = p + 2
     X = torch.randn(n, p, device=DEV)
     z = (0.05 * torch.randn(S, D, device=DEV)).contiguous()
