@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rows", type=float, default=float(os.environ.get("MNF_BENCH_ROWS", N_FULL)),
                     help="observations per GPU (default 1e8, the BASELINE configuration)")
+    ap.add_argument("--eager", action="store_true", help="do not replay the step from a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -211,12 +212,12 @@ def run_b200(args):
     X, y = make_data(n_rows, device, SEED0 + rank * 256)
     approximation = mininf.nn.ParameterizedDistribution(
         Normal, loc=torch.zeros(P, device=device), scale=0.1 * torch.ones(P, device=device))
-    optimizer = torch.optim.Adam(approximation.parameters(), lr=0.01)
+    optimizer = torch.optim.Adam(approximation.parameters(), lr=0.01, capturable=not args.eager)
     loss_module = mininf.nn.EvidenceLowerBoundLoss(S, dense_precision="tf32",
                                                    process_group=True if distributed else None)
     conditioned = mininf.condition(model_factory(mininf, n_rows), X=X, y=y)
 
-    def step():
+    def eager_step():
         optimizer.zero_grad(set_to_none=True)
         loss = loss_module(conditioned, {"theta": approximation()})
         loss.backward()
@@ -232,11 +233,32 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
-        step()
+        eager_step()
     fence()
     plan = loss_module.last_plan
+    # Roofline numerator: per-launch duration of the dense sweep from CUDA events recorded around
+    # the launch on its stream, averaged over eager steps on the same resident data (events inside
+    # a graph replay cannot be timed; the kernel and its arguments are identical).
     plan.sweep_events.clear()
     plan.record_sweep_events = True
+    eager_begin, eager_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eager_begin.record()
+    for _ in range(args.steps):
+        eager_step()
+    eager_end.record()
+    fence()
+    plan.record_sweep_events = False
+    kernel_ms = sum(b.elapsed_time(e) for b, e in plan.sweep_events) / max(len(plan.sweep_events), 1)
+    eager_ms_per_step = eager_begin.elapsed_time(eager_end) / args.steps
+
+    # The SVI step is recorded once into a CUDA graph (mininf_b200.nn.GraphedStep) and replayed:
+    # the same kernels in the same order, one launch per step. Sharded runs keep the eager loop:
+    # capturing the NCCL all-reduce of this torch/NCCL build into the graph hung on 2 GPUs.
+    graphed = not args.eager and not distributed
+    step = mininf.nn.GraphedStep(loss_module, conditioned, lambda: {"theta": approximation()},
+                                 optimizer) if graphed else eager_step
+    for _ in range(max(args.warmup, 3)):
+        step()
     begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
     wall0 = time.time()
@@ -249,9 +271,7 @@ def run_b200(args):
     torch.cuda.nvtx.range_pop()
     wall1 = time.time()
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    plan.record_sweep_events = False
     elapsed_ms = begin.elapsed_time(end)
-    kernel_ms = sum(b.elapsed_time(e) for b, e in plan.sweep_events) / max(len(plan.sweep_events), 1)
     loss_module.synchronize()
     final_loss = float(loss.detach())
     if distributed:
@@ -293,14 +313,19 @@ def run_b200(args):
             "config": {"workload": "bayesian_linear_regression_p64_N1e8_S64", "rows_per_gpu": n_rows,
                        "features": P, "particles": S, "parallelism": f"row shards x{world}, one all-reduce/step",
                        "l2": "inputs (26 GB per GPU) far exceed the 126 MB L2; no flush needed",
-                       "step": "zero_grad + ELBO/grad kernels + backward + Adam", "final_loss": final_loss},
+                       "step": "zero_grad + ELBO/grad kernels + backward + Adam" +
+                               (", replayed from one CUDA graph (GraphedStep)" if graphed else ", eager launches"),
+                       "final_loss": final_loss},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": plan.gpu_launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_source,
                          "kernel": "mnf::tc::dense_tc_kernel<Normal> (+ its 5 us partial-sum reduction)",
-                         "kernel_ms": kernel_ms, "algorithmic_bytes": algorithmic_bytes},
+                         "kernel_ms": kernel_ms, "algorithmic_bytes": algorithmic_bytes,
+                         "kernel_timing": f"CUDA events around each launch, {args.steps} eager steps run "
+                                          "right before the timed region on the same data"},
+            "eager_ms_per_step": eager_ms_per_step,
             "cpu_baseline": cpu_baseline,
             "steps_per_sec": 1e3 / ms_per_step,
         }

@@ -186,9 +186,12 @@ size_t mnf_workspace_bytes(int n_particles, int n_latent_total, int device);
  *                      particle*D + column [, rejection round])): Normal eps by Box-Muller, standard
  *                      gammas by Marsaglia-Tsang, Beta as G1 / (G1 + G0).
  * Also zeroes `acc` [S][1+D] for the step and clears nothing else.
+ * `offset_dev` (may be NULL): a device-resident counter added to `offset` inside the kernel. A
+ * step captured in a CUDA graph passes it together with `mnf_finalize(step_counter=...)`, which
+ * increments it, so every replay draws with a new call index although its arguments are frozen.
  */
 int mnf_rsample(const mnf_latent_t* latents_dev, int n_latents, int n_particles, int n_latent_total,
-                const float* noise_in, uint64_t seed, uint64_t offset,
+                const float* noise_in, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
                 float* z, float* noise_out, double* acc, uint32_t* status, void* stream);
 
 /*
@@ -239,16 +242,16 @@ int mnf_small_sites(const mnf_site_t* sites_dev, int n_sites, int64_t max_numel,
  */
 int mnf_finalize(const mnf_latent_t* latents_dev, int n_latents, int n_particles,
                  int n_latent_total, const float* z, const float* noise, const double* acc,
-                 int with_entropy, float* out, uint32_t* status, void* stream);
+                 int with_entropy, float* out, uint64_t* step_counter, uint32_t* status, void* stream);
 
 /*
  * Row-latent sweep (see mnf_rowlatent_t): one pass over loc / scale / features / response for all
  * particles; `entropy_weight` (1 or 0) switches the entropy of q(Z) on.
  */
 int mnf_rowlatent_sweep(const mnf_rowlatent_t* desc, const float* z, int n_particles,
-                        int n_latent_total, uint64_t seed, uint64_t offset, int with_entropy,
-                        double* acc, void* workspace, size_t workspace_bytes, uint32_t* status,
-                        void* stream);
+                        int n_latent_total, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                        int with_entropy, double* acc, void* workspace, size_t workspace_bytes,
+                        uint32_t* status, void* stream);
 
 /* Counting scan used by the integer-exact parity checks: out[0]=sum(mask), out[1]=sum(mask*value)
  * as int64 (value must hold integers); mask may be NULL (all ones). */

@@ -212,12 +212,12 @@ bool host_link_has_latent(const mnf_link_t& L) { return L.a_lat >= 0 || L.b_lat 
 
 template <int SP>
 int launch_rowlatent(const mnf_rowlatent_t& d, const float* z, int S, int D, int s_begin,
-                            int first_pass, uint64_t seed, uint64_t offset, int with_entropy,
-                            float* partial, uint32_t* status, int grid, cudaStream_t stream) {
+                            int first_pass, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                            int with_entropy, float* partial, uint32_t* status, int grid, cudaStream_t stream) {
   auto kernel = rowlatent_kernel<SP>;
   const size_t smem = rowlatent_smem_bytes<SP>();
   MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kernel<<<grid, kRowThreads, smem, stream>>>(d, z, S, D, s_begin, first_pass, seed, offset,
+  kernel<<<grid, kRowThreads, smem, stream>>>(d, z, S, D, s_begin, first_pass, seed, offset, offset_dev,
                                                with_entropy, partial, status);
   MNF_CUDA_CHECK(cudaGetLastError());
   return MNF_OK;
@@ -252,16 +252,16 @@ size_t mnf_workspace_bytes(int n_particles, int n_latent_total, int device) {
 }
 
 int mnf_rsample(const mnf_latent_t* latents_dev, int n_latents, int n_particles, int n_latent_total,
-                const float* noise_in, uint64_t seed, uint64_t offset, float* z, float* noise_out,
-                double* acc, uint32_t* status, void* stream) {
+                const float* noise_in, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                float* z, float* noise_out, double* acc, uint32_t* status, void* stream) {
   if (!latents_dev || !z || !noise_out || !acc || !status || n_latents <= 0 || n_particles <= 0 ||
       n_latent_total <= 0)
     return fail(MNF_E_INVALID, "mnf_rsample: null pointer or empty latent table%s%s");
   const int64_t total = (int64_t)n_particles * (n_latent_total + 1);
   const int grid = (int)std::min<int64_t>((total + 255) / 256, 1024);
   rsample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(latents_dev, n_latents, n_particles,
-                                                         n_latent_total, noise_in, seed, offset, z,
-                                                         noise_out, acc, status);
+                                                         n_latent_total, noise_in, seed, offset,
+                                                         offset_dev, z, noise_out, acc, status);
   MNF_CUDA_CHECK(cudaGetLastError());
   return MNF_OK;
 }
@@ -420,9 +420,9 @@ int mnf_site_sweep(const mnf_site_t* sites, int n_sites, const float* z, int n_p
 }
 
 int mnf_rowlatent_sweep(const mnf_rowlatent_t* desc, const float* z, int n_particles,
-                        int n_latent_total, uint64_t seed, uint64_t offset, int with_entropy,
-                        double* acc, void* workspace, size_t workspace_bytes, uint32_t* status,
-                        void* stream_) {
+                        int n_latent_total, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                        int with_entropy, double* acc, void* workspace, size_t workspace_bytes,
+                        uint32_t* status, void* stream_) {
   if (!desc || !z || !acc || !workspace || !status)
     return fail(MNF_E_INVALID, "mnf_rowlatent_sweep: null pointer%s%s");
   const mnf_rowlatent_t d = *desc;
@@ -454,10 +454,10 @@ int mnf_rowlatent_sweep(const mnf_rowlatent_t* desc, const float* z, int n_parti
   const int sp = S <= 4 ? 4 : (S <= 8 ? 8 : (S <= 16 ? 16 : 32));
   for (int s_begin = 0, pass = 0; s_begin < S; s_begin += sp, ++pass) {
     int rc;
-    if (sp == 4) rc = launch_rowlatent<4>(d, z, S, D, s_begin, pass == 0, seed, offset, with_entropy, partial, status, grid, stream);
-    else if (sp == 8) rc = launch_rowlatent<8>(d, z, S, D, s_begin, pass == 0, seed, offset, with_entropy, partial, status, grid, stream);
-    else if (sp == 16) rc = launch_rowlatent<16>(d, z, S, D, s_begin, pass == 0, seed, offset, with_entropy, partial, status, grid, stream);
-    else rc = launch_rowlatent<32>(d, z, S, D, s_begin, pass == 0, seed, offset, with_entropy, partial, status, grid, stream);
+    if (sp == 4) rc = launch_rowlatent<4>(d, z, S, D, s_begin, pass == 0, seed, offset, offset_dev, with_entropy, partial, status, grid, stream);
+    else if (sp == 8) rc = launch_rowlatent<8>(d, z, S, D, s_begin, pass == 0, seed, offset, offset_dev, with_entropy, partial, status, grid, stream);
+    else if (sp == 16) rc = launch_rowlatent<16>(d, z, S, D, s_begin, pass == 0, seed, offset, offset_dev, with_entropy, partial, status, grid, stream);
+    else rc = launch_rowlatent<32>(d, z, S, D, s_begin, pass == 0, seed, offset, offset_dev, with_entropy, partial, status, grid, stream);
     if (rc) return rc;
   }
   // physical partial layout: 0 log-density, 1..p beta gradient (zeros without a response), then
@@ -493,12 +493,12 @@ int mnf_small_sites(const mnf_site_t* sites_dev, int n_sites, int64_t max_numel,
 
 int mnf_finalize(const mnf_latent_t* latents_dev, int n_latents, int n_particles, int n_latent_total,
                  const float* z, const float* noise, const double* acc, int with_entropy, float* out,
-                 uint32_t* status, void* stream) {
+                 uint64_t* step_counter, uint32_t* status, void* stream) {
   if (!latents_dev || !z || !noise || !acc || !out || !status || n_latents <= 0)
     return fail(MNF_E_INVALID, "mnf_finalize: null pointer or empty latent table%s%s");
   finalize_kernel<<<1, kFinalThreads, 0, (cudaStream_t)stream>>>(latents_dev, n_latents, n_particles,
                                                                  n_latent_total, z, noise, acc,
-                                                                 with_entropy, out, status);
+                                                                 with_entropy, out, step_counter, status);
   MNF_CUDA_CHECK(cudaGetLastError());
   return MNF_OK;
 }

@@ -35,9 +35,10 @@ struct RowParticle {   // per-particle scalars of the row-latent sites, staged i
 template <int SP>
 __global__ void __launch_bounds__(kRowThreads)
 rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, int s_begin,
-                 int first_pass, uint64_t seed, uint64_t offset, int with_entropy,
-                 float* __restrict__ partial, uint32_t* __restrict__ status) {
+                 int first_pass, uint64_t seed, uint64_t offset, const uint64_t* __restrict__ offset_dev,
+                 int with_entropy, float* __restrict__ partial, uint32_t* __restrict__ status) {
   extern __shared__ float smem[];
+  if (offset_dev != nullptr) offset += *offset_dev;   // device-side call index (CUDA-graph replays)
   const int p = d.p;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* sBeta = smem;                                             // [SP][32]

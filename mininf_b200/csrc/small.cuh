@@ -51,8 +51,10 @@ __device__ __forceinline__ int find_latent(const mnf_latent_t* lat, int n, int c
 // -------------------------------------------------------------------------------------------
 __global__ void rsample_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
                                const float* __restrict__ noise_in, uint64_t seed, uint64_t offset,
+                               const uint64_t* __restrict__ offset_dev,
                                float* __restrict__ z, float* __restrict__ noise_out,
                                double* __restrict__ acc, uint32_t* __restrict__ status) {
+  if (offset_dev != nullptr) offset += *offset_dev;   // device-side call index (CUDA-graph replays)
   const int64_t n_z = (int64_t)S * D;
   const int64_t n_acc = (int64_t)S * (D + 1);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -221,8 +223,10 @@ __global__ void __launch_bounds__(kFinalThreads)
 finalize_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
                 const float* __restrict__ z, const float* __restrict__ noise,
                 const double* __restrict__ acc, int with_entropy, float* __restrict__ out,
-                uint32_t* __restrict__ status) {
+                uint64_t* __restrict__ step_counter, uint32_t* __restrict__ status) {
   __shared__ double red[kFinalThreads];
+  // last kernel of a step: the next replay of a captured step draws with the next call index
+  if (step_counter != nullptr && threadIdx.x == 0) *step_counter += 1;
   const double invS = 1.0 / (double)S;
   double ent = 0.0;
   bool nonfinite = false;

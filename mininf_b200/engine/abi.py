@@ -88,7 +88,7 @@ EXPORTS = {
     "mnf_device_info": (C.c_int, [C.c_int, C.POINTER(DeviceInfo)]),
     "mnf_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "mnf_rsample": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64,
-                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                              C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                               C.c_void_p]),
     "mnf_dense_tf32_kernel": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "mnf_dense_sweep": (C.c_int, [C.POINTER(DenseSite), C.c_int, C.c_void_p, C.c_int, C.c_int,
@@ -96,12 +96,12 @@ EXPORTS = {
     "mnf_site_sweep": (C.c_int, [C.POINTER(Site), C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "mnf_rowlatent_sweep": (C.c_int, [C.POINTER(RowLatent), C.c_void_p, C.c_int, C.c_int, C.c_uint64,
-                                      C.c_uint64, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                      C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_void_p, C.c_void_p]),
     "mnf_small_sites": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "mnf_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                               C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+                               C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mnf_masked_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
 }
 

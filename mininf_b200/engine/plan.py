@@ -107,6 +107,7 @@ class Plan:
         self.noise_in = torch.empty(S, D, **f32)
         self.acc = torch.empty(S, D + 1, device=device, dtype=torch.float64)
         self.status = torch.zeros(1, device=device, dtype=torch.int32)
+        self.step_counter = torch.zeros(1, device=device, dtype=torch.int64)   # graph replays (see step)
         self.out = torch.empty(1 + 2 * D, **f32)
         if dry_run:
             self.workspace_bytes = 0
@@ -516,10 +517,15 @@ class Plan:
         return count
 
     def step(self, noise: Optional[torch.Tensor], seed: int, offset: int, with_entropy: bool = True,
-             reduce_fn: Optional[Callable[[torch.Tensor], None]] = None) -> torch.Tensor:
+             reduce_fn: Optional[Callable[[torch.Tensor], None]] = None,
+             device_counter: bool = False) -> torch.Tensor:
         """Enqueue one ELBO evaluation on the current stream; returns the [1 + 2D] output buffer
-        (loss, d loss / d p0, d loss / d p1). Parameters must already be in ``P0`` / ``P1``."""
+        (loss, d loss / d p0, d loss / d p1). Parameters must already be in ``P0`` / ``P1``.
+        ``device_counter``: the Philox call index is ``offset`` plus a device-resident counter that
+        the last kernel of the step increments - for steps recorded into a CUDA graph, whose
+        arguments are frozen at capture time."""
         lib, S, D = self.lib, self.S, self.D
+        counter = self.step_counter.data_ptr() if device_counter else None
         stream = torch.cuda.current_stream(self.device).cuda_stream
         status = self.status.data_ptr()
         noise_ptr = None
@@ -527,8 +533,8 @@ class Plan:
             self.noise_in.copy_(noise.reshape(S, D))
             noise_ptr = self.noise_in.data_ptr()
         lib.call("mnf_rsample", self.latent_table.data_ptr(), len(self.latents), S, D, noise_ptr,
-                 seed, offset, self.z.data_ptr(), self.noise.data_ptr(), self.acc.data_ptr(), status,
-                 stream)
+                 seed, offset, counter, self.z.data_ptr(), self.noise.data_ptr(), self.acc.data_ptr(),
+                 status, stream)
         for site, mode in self.dense_sites:
             if self.record_sweep_events:
                 begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -548,7 +554,7 @@ class Plan:
             lib.call("mnf_small_sites", table.data_ptr(), count, longest, self.z.data_ptr(), S, D,
                      self.acc.data_ptr(), status, stream)
         for name, desc in self.row_groups.items():
-            lib.call("mnf_rowlatent_sweep", C.byref(desc), self.z.data_ptr(), S, D, seed, offset,
+            lib.call("mnf_rowlatent_sweep", C.byref(desc), self.z.data_ptr(), S, D, seed, offset, counter,
                      int(with_entropy), self.acc.data_ptr(), self.workspace.data_ptr(),
                      self.workspace_bytes, status, stream)
         if reduce_fn is not None:
@@ -559,7 +565,7 @@ class Plan:
                      self.acc.data_ptr(), status, stream)
         lib.call("mnf_finalize", self.latent_table.data_ptr(), len(self.latents), S, D,
                  self.z.data_ptr(), self.noise.data_ptr(), self.acc.data_ptr(), int(with_entropy),
-                 self.out.data_ptr(), status, stream)
+                 self.out.data_ptr(), counter, status, stream)
         return self.out
 
 

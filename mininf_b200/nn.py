@@ -137,7 +137,8 @@ class _EngineFunction(torch.autograd.Function):
     """One fused forward+backward evaluation; inputs are the constrained parameter tensors."""
 
     @staticmethod
-    def forward(ctx, loss_module, plan, noise, row_noise, seed, offset, reduce_fn, with_entropy, *params):
+    def forward(ctx, loss_module, plan, noise, row_noise, seed, offset, reduce_fn, with_entropy, capturing,
+                *params):
         with torch.no_grad():
             big_grads = []
             for spec, p0, p1 in zip(plan.all_latents, params[0::2], params[1::2]):
@@ -155,19 +156,23 @@ class _EngineFunction(torch.autograd.Function):
                     lo, hi = spec.offset, spec.offset + spec.numel
                     plan.P0[lo:hi].copy_(p0.reshape(-1))
                     plan.P1[lo:hi].copy_(p1.reshape(-1))
-            out = plan.step(noise, seed, offset, with_entropy=with_entropy, reduce_fn=reduce_fn)
+            out = plan.step(noise, seed, offset, with_entropy=with_entropy, reduce_fn=reduce_fn,
+                            device_counter=capturing)
             saved = out.clone()
         ctx.plan = plan
         ctx.big_grads = big_grads
         ctx.save_for_backward(saved)
-        loss_module._schedule_status_check(plan)
+        if capturing:
+            loss_module._graphed_plans[id(plan)] = plan     # status is read by synchronize()
+        else:
+            loss_module._schedule_status_check(plan)
         return saved[0].clone()
 
     @staticmethod
     def backward(ctx, grad_output):
         (saved,) = ctx.saved_tensors
         plan = ctx.plan
-        grads: List[Optional[torch.Tensor]] = [None] * 8
+        grads: List[Optional[torch.Tensor]] = [None] * 9
         big = iter(ctx.big_grads)
         for spec in plan.all_latents:
             if spec.row_latent:
@@ -211,6 +216,7 @@ class EvidenceLowerBoundLoss(nn.Module):
         self._plans: Dict[Tuple, Any] = {}
         self._pending: List[Tuple[Any, torch.Tensor, torch.cuda.Event]] = []
         self._free_slots: List[torch.Tensor] = []
+        self._graphed_plans: Dict[int, Any] = {}
         self._calls = 0
         self.last_plan = None
 
@@ -219,7 +225,10 @@ class EvidenceLowerBoundLoss(nn.Module):
         if self.check == "off":
             return
         if self.check == "sync":
-            self._raise_for_status(int(plan.status.item()))
+            bits = int(plan.status.item())
+            if bits:
+                plan.status.zero_()          # report once; the plan stays usable for the next batch
+            self._raise_for_status(bits)
             return
         if len(self._pending) >= 8:          # bounded backlog: settle the oldest check first
             _, host, event = self._pending.pop(0)
@@ -241,7 +250,10 @@ class EvidenceLowerBoundLoss(nn.Module):
             if block:
                 event.synchronize()
             if event.query():
-                flagged |= int(host.item())
+                bits = int(host.item())
+                if bits:
+                    plan.status.zero_()      # report once
+                flagged |= bits
                 self._free_slots.append(host)
             else:
                 remaining.append((plan, host, event))
@@ -255,8 +267,16 @@ class EvidenceLowerBoundLoss(nn.Module):
             raise ValueError("the ELBO engine flagged invalid values: " + status_message(bits))
 
     def synchronize(self) -> None:
-        """Wait for outstanding evaluations and raise if any of them flagged invalid values."""
+        """Wait for outstanding evaluations and raise if any of them flagged invalid values
+        (including steps replayed from a CUDA graph, whose status word is only read here)."""
         self._drain_status(block=True)
+        flagged = 0
+        for plan in self._graphed_plans.values():
+            bits = int(plan.status.item())
+            if bits:
+                plan.status.zero_()
+            flagged |= bits
+        self._raise_for_status(flagged)
 
     # -- tracing ----------------------------------------------------------------------------
     def _build_plan(self, model: Callable, approximation: DistributionDict) -> Any:
@@ -349,7 +369,11 @@ class EvidenceLowerBoundLoss(nn.Module):
         if not isinstance(approximation, dict):
             raise TypeError("Expected a distribution which samples dictionaries of tensors but got "
                             f"a sample of type {type(approximation)}")
-        self._drain_status()
+        # inside torch.cuda.graph(...) nothing may query events or touch pinned memory: the step is
+        # recorded with a device-side Philox call index and its status word is read by synchronize()
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self._drain_status()
         plan = self._plan_for(model, approximation)
         self.last_plan = plan
         from .engine.plan import latent_parameters
@@ -371,8 +395,62 @@ class EvidenceLowerBoundLoss(nn.Module):
             import torch.distributed as dist
             group = None if self.process_group is True else self.process_group
             reduce_fn = lambda acc: dist.all_reduce(acc, group=group)  # noqa: E731
-        return _EngineFunction.apply(self, plan, noise, row_noise, int(seed) & (2 ** 63 - 1), self._calls,
-                                     reduce_fn, bool(_with_entropy), *params)
+        offset = self._calls + (1 << 40 if capturing else 0)    # replays count on from here on the device
+        return _EngineFunction.apply(self, plan, noise, row_noise, int(seed) & (2 ** 63 - 1), offset,
+                                     reduce_fn, bool(_with_entropy), capturing, *params)
+
+
+class GraphedStep:
+    """One SVI step - ``zero_grad``, loss, ``backward``, ``optimizer.step`` - recorded once into a
+    CUDA graph and replayed with a single launch (``torch.cuda.graph``; the reference's loop of
+    README.md:66-69 issues ~20 small kernels around the sweeps, which costs 5-15 % of a step).
+
+    ``approximation`` is a callable returning the approximation dictionary, e.g.
+    ``lambda: {"theta": q()}``; the optimizer must be capturable (``Adam(..., capturable=True)``).
+    Conditioned tensors are read in place on every replay: refill them with ``copy_`` to feed the
+    next minibatch. Every replay draws fresh Philox noise (the call index lives on the device).
+    ``loss`` holds the value of the most recent replay; ``loss_module.synchronize()`` reports
+    invalid values flagged by the kernels.
+    """
+
+    def __init__(self, loss_module: "EvidenceLowerBoundLoss", model: Callable, approximation: Callable[[], Any],
+                 optimizer: torch.optim.Optimizer, warmup: int = 3) -> None:
+        self.loss_module, self.model, self.approximation, self.optimizer = loss_module, model, approximation, optimizer
+        for group in optimizer.param_groups:
+            if "capturable" in group and not group["capturable"]:
+                raise ValueError("GraphedStep needs a capturable optimizer, e.g. torch.optim.Adam(..., capturable=True)")
+        # eager warm-up on a side stream (builds the plan, optimizer state and kernel attributes)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(int(warmup), 1)):
+                self._step()
+        torch.cuda.current_stream().wait_stream(side)
+        loss_module.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        # torch.distributions validates constructor arguments with a host round trip
+        # (`if not valid.all()`), which a capture cannot contain; the warm-up steps above ran
+        # with validation on, and the kernels keep checking scales and supports on the device
+        validate = torch.distributions.Distribution._validate_args
+        torch.distributions.Distribution.set_default_validate_args(False)
+        try:
+            with torch.cuda.graph(self.graph):
+                self.loss = self._step(zero_grad=False).detach()
+        finally:
+            torch.distributions.Distribution.set_default_validate_args(validate)
+
+    def _step(self, zero_grad: bool = True) -> torch.Tensor:
+        if zero_grad:
+            self.optimizer.zero_grad(set_to_none=True)
+        loss = self.loss_module(self.model, self.approximation())
+        loss.backward()
+        self.optimizer.step()
+        return loss
+
+    def __call__(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.loss
 
 
 class LogLikelihoodLoss(nn.Module):

@@ -56,7 +56,7 @@ int main(void) {
 
 def test_argument_errors_do_not_need_a_gpu(library):
     """Null pointers are rejected before any CUDA call; the message is retrievable."""
-    code = library.raw("mnf_finalize")(None, 0, 1, 1, None, None, None, 1, None, None, None)
+    code = library.raw("mnf_finalize")(None, 0, 1, 1, None, None, None, 1, None, None, None, None)
     assert code == abi.E_INVALID
     assert b"mnf_finalize" in library.raw("mnf_last_error")()
     with pytest.raises(abi.NativeError, match="mnf_site_sweep"):

@@ -49,14 +49,14 @@ dense = abi.DenseSite(family=abi.NORMAL, p=p, n_rows=N, ldx=p, X=X.data_ptr(), y
 
 
 def step(mode):
-    lib.call("mnf_rsample", lat_dev.data_ptr(), 1, S, D, eps.data_ptr(), 0, 0, z.data_ptr(),
+    lib.call("mnf_rsample", lat_dev.data_ptr(), 1, S, D, eps.data_ptr(), 0, 0, None, z.data_ptr(),
              noise.data_ptr(), acc.data_ptr(), status.data_ptr(), stream)
     lib.call("mnf_dense_sweep", C.byref(dense), mode, z.data_ptr(), S, D, acc.data_ptr(),
              ws.data_ptr(), ws_bytes, status.data_ptr(), stream)
     lib.call("mnf_small_sites", sites_dev.data_ptr(), 1, p, z.data_ptr(), S, D, acc.data_ptr(),
              status.data_ptr(), stream)
     lib.call("mnf_finalize", lat_dev.data_ptr(), 1, S, D, z.data_ptr(), noise.data_ptr(),
-             acc.data_ptr(), 1, out.data_ptr(), status.data_ptr(), stream)
+             acc.data_ptr(), 1, out.data_ptr(), None, status.data_ptr(), stream)
 
 
 # fp64 torch reference on the same device
