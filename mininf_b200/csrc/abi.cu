@@ -206,6 +206,37 @@ int launch_site_sweep(const mnf_site_t* sites, const float* z, int S, int D, flo
   return MNF_OK;
 }
 
+
+template <int KIND>
+int launch_site_fast(const mnf_site_t& site, const float* z, int S, int D, float* partial,
+                     uint32_t* status, int grid, cudaStream_t stream) {
+  if (S <= 32) {
+    auto kernel = site_fast_kernel<KIND, 1>;
+    const size_t smem = site_fast_smem_bytes<KIND, 1>();
+    kernel<<<grid, kSweepThreads, smem, stream>>>(site, z, S, D, partial, status);
+  } else if (S <= 64) {
+    auto kernel = site_fast_kernel<KIND, 2>;
+    const size_t smem = site_fast_smem_bytes<KIND, 2>();
+    kernel<<<grid, kSweepThreads, smem, stream>>>(site, z, S, D, partial, status);
+  } else {
+    auto kernel = site_fast_kernel<KIND, 4>;
+    const size_t smem = site_fast_smem_bytes<KIND, 4>();
+    MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, kSweepThreads, smem, stream>>>(site, z, S, D, partial, status);
+  }
+  MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+// scalar-latent columns of one site's four gradient sums (du0, du0*x0, du1, du1*x1)
+void site_columns(const mnf_site_t& site, int32_t* cols) {
+  const bool two = site.family <= MNF_BETA;
+  cols[0] = site.param[0].a_lat;
+  cols[1] = site.param[0].b_lat;
+  cols[2] = two ? site.param[1].a_lat : -1;
+  cols[3] = two ? site.param[1].b_lat : -1;
+}
+
 bool family_has_two_params(int family) { return family <= MNF_BETA; }
 
 bool host_link_has_latent(const mnf_link_t& L) { return L.a_lat >= 0 || L.b_lat >= 0; }
@@ -383,11 +414,39 @@ int mnf_site_sweep(const mnf_site_t* sites, int n_sites, const float* z, int n_p
   if (int rc = device_cache(-1, &c)) return rc;
   const int64_t n_chunks = (sites[0].numel + 31) / 32;
   const int grid = (int)std::min<int64_t>((n_chunks + kSweepWarps - 1) / kSweepWarps, 2 * c->sm_count);
+  float* partial = static_cast<float*>(workspace);
+
+  // Sites with a specialised kernel (site_sweep.cuh: Poisson with an exp link, Normal with a
+  // per-particle scale) run on their own, one kernel + reduction each; the rest stay fused.
+  mnf_site_t generic[MNF_MAX_FUSED_SITES];
+  int n_generic = 0;
+  for (int i = 0; i < n_sites; ++i) {
+    const int kind = site_fast_kind(sites[i]);
+    if (kind == kFastNone) {
+      generic[n_generic++] = sites[i];
+      continue;
+    }
+    if ((size_t)grid * S * 5 * sizeof(float) > workspace_bytes)
+      return fail(MNF_E_INVALID, "mnf_site_sweep: workspace too small%s%s");
+    const int rc = kind == kFastPoissonExp
+                       ? launch_site_fast<kFastPoissonExp>(sites[i], z, S, D, partial, status, grid, stream)
+                       : launch_site_fast<kFastNormalId>(sites[i], z, S, D, partial, status, grid, stream);
+    if (rc) return rc;
+    ColMap fast_map;
+    fast_map.n_vec = 0;
+    fast_map.vec_lat = 0;
+    fast_map.n_scalar = 4;
+    for (int k = 0; k < 16; ++k) fast_map.scalar_lat[k] = -1;
+    site_columns(sites[i], fast_map.scalar_lat);
+    if (int rr = launch_reduce(partial, grid, S, 5, fast_map, 1.0, D, acc, stream)) return rr;
+  }
+  if (n_generic == 0) return MNF_OK;
+  sites = generic;
+  n_sites = n_generic;
   const int n_templ = n_sites == 1 ? 1 : (n_sites == 2 ? 2 : 4);
   const int ncol = 1 + 4 * n_templ;
   if ((size_t)grid * S * ncol * sizeof(float) > workspace_bytes)
     return fail(MNF_E_INVALID, "mnf_site_sweep: workspace too small%s%s");
-  float* partial = static_cast<float*>(workspace);
 
   // pad the site list to the template width with inert duplicates of zero weight
   mnf_site_t padded[MNF_MAX_FUSED_SITES];

@@ -74,6 +74,12 @@ def _f32(tensor: torch.Tensor, device: torch.device) -> torch.Tensor:
     return tensor.detach().to(torch.float32).contiguous()
 
 
+def _has_fast_sweep(site: abi.Site) -> bool:
+    first, second = site.param[0], site.param[1]
+    return (site.family == abi.POISSON and first.transform == abi.T_EXP) or \
+        (site.family == abi.NORMAL and first.transform == abi.T_ID and not second.x)
+
+
 class Plan:
     """Everything one ELBO step needs, resolved to device pointers."""
 
@@ -511,7 +517,11 @@ class Plan:
     def gpu_launches_per_step(self) -> int:
         """Kernels of this library launched by one :meth:`step` (sweeps come with a reduction)."""
         count = 2  # rsample + finalize
-        count += 2 * (len(self.dense_sites) + len(self.sweep_groups))
+        count += 2 * len(self.dense_sites)
+        for group in self.sweep_groups:
+            # sites with a specialised kernel run on their own (csrc/site_sweep.cuh::site_fast_kind)
+            fast = sum(1 for i in range(len(group)) if _has_fast_sweep(group[i]))
+            count += 2 * fast + (2 if fast < len(group) else 0)
         count += sum(1 + -(-self.S // 32) for _ in self.row_groups)
         count += (self.small_observed is not None) + (self.small_global is not None)
         return count
