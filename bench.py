@@ -1,9 +1,12 @@
 """Benchmark of the ELBO + gradient hot path (BASELINE.json metric) on synthetic data.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3]
 
-Workload (config[1] of BASELINE.json): Bayesian linear regression, mean-field Normal
+Default workload c2 (config[1] of BASELINE.json): Bayesian linear regression, mean-field Normal
 approximation, p = 64 features, N = 1e8 observations PER GPU (weak scaling), S = 64 particles.
+`--workload c3` (config[2]): minibatch logistic regression, p = 256, batches of 1e7 rows per GPU
+of a declared N = 1e9 stream, S = 16; every step conditions the model on the next batch (two
+resident batches alternate; the plan is rebound, not retraced).
 A step is one full SVI step through the public API: zero_grad, EvidenceLowerBoundLoss forward
 (fused ELBO + gradient kernels), backward through the parameter transforms, Adam. The metric is
 particle-observation log-density evaluations per second: rows * S / time, whole job.
@@ -29,9 +32,25 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "elbo_grad_particle_obs_evals_per_sec"
 UNIT = "evals/s"
-P, S = 64, 64
-N_FULL = 100_000_000
 SEED0 = 2000
+N_CHUNKS = 256     # synthetic rows are generated in 256 chunks, chunk c seeded seed0 + c
+
+
+class Workload:
+    def __init__(self, key, name, p, particles, rows, family, declared_rows, n_batches, kernel, traffic_file):
+        self.key, self.name, self.p, self.particles, self.rows = key, name, p, particles, rows
+        self.family, self.declared_rows, self.n_batches = family, declared_rows, n_batches
+        self.kernel, self.traffic_file = kernel, traffic_file
+
+
+WORKLOADS = {
+    "c2": Workload("c2", "bayesian_linear_regression_p64_N1e8_S64", 64, 64, 100_000_000, "normal", None, 1,
+                   "mnf::tc::dense_tc_kernel<Normal> (+ its 5 us partial-sum reduction)", "dense_tc_traffic.json"),
+    "c3": Workload("c3", "minibatch_logistic_regression_p256_batch1e7_of_N1e9_S16", 256, 16, 10_000_000,
+                   "bernoulli", 1_000_000_000, 2,
+                   "mnf::tcr::dense_tcr_kernel<BernoulliLogits, 16> (+ its partial-sum reduction)",
+                   "dense_tcr_traffic.json"),
+}
 
 
 def parse_args():
@@ -40,8 +59,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=float, default=float(os.environ.get("MNF_BENCH_ROWS", N_FULL)),
-                    help="observations per GPU (default 1e8, the BASELINE configuration)")
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--rows", type=float, default=float(os.environ.get("MNF_BENCH_ROWS", 0)),
+                    help="observations (c3: batch rows) per GPU; default: the BASELINE configuration")
     ap.add_argument("--eager", action="store_true", help="do not replay the step from a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -58,33 +78,49 @@ def measured_peak_gbs():
 # ---------------------------------------------------------------------------------------------
 # synthetic data: 256 row chunks, chunk c seeded seed0 + c
 # ---------------------------------------------------------------------------------------------
-def make_data(n, device, seed0):
-    from oracle.configs import N_CHUNKS, chunk_bounds
+def chunk_bounds(n, chunk):
+    per = -(-n // N_CHUNKS)
+    return min(chunk * per, n), min((chunk + 1) * per, n)
+
+
+def make_data(w, n, device, seed0):
     g = torch.Generator(device=device)
     g.manual_seed(SEED0 - 1)
-    theta_true = torch.randn(P, generator=g, device=device) / P ** 0.5
-    X = torch.empty(n, P, device=device)
+    theta_true = torch.randn(w.p, generator=g, device=device) / w.p ** 0.5
+    X = torch.empty(n, w.p, device=device)
     y = torch.empty(n, device=device)
     for chunk in range(N_CHUNKS):
         lo, hi = chunk_bounds(n, chunk)
         if hi <= lo:
             continue
         g.manual_seed(seed0 + chunk)
-        torch.randn(hi - lo, P, generator=g, device=device, out=X[lo:hi])
-        torch.randn(hi - lo, generator=g, device=device, out=y[lo:hi])
-        y[lo:hi].addmv_(X[lo:hi], theta_true)
+        torch.randn(hi - lo, w.p, generator=g, device=device, out=X[lo:hi])
+        if w.family == "normal":
+            torch.randn(hi - lo, generator=g, device=device, out=y[lo:hi])
+            y[lo:hi].addmv_(X[lo:hi], theta_true)
+        else:
+            y[lo:hi] = torch.bernoulli(torch.sigmoid(X[lo:hi] @ theta_true), generator=g)
     return X, y
 
 
-def model_factory(m, n_rows):
-    from torch.distributions import Normal
+def model_factory(m, w, n_rows):
+    from torch.distributions import Bernoulli, Normal
+    declared = w.declared_rows or n_rows
 
-    def model():
-        theta = m.sample("theta", Normal(0, 1), P)
+    def regression():
+        theta = m.sample("theta", Normal(0, 1), w.p)
         with m.no_log_prob():
-            X = m.sample("X", Normal(0, 1), (n_rows, P))
+            X = m.sample("X", Normal(0, 1), (n_rows, w.p))
         m.sample("y", Normal(X @ theta, 1.0))
-    return model
+
+    def minibatch_logistic():          # examples/minibatch.md:26-35 with a Bernoulli response
+        theta = m.sample("theta", Normal(0, 1), w.p)
+        with m.batch(declared):
+            with m.no_log_prob():
+                X = m.sample("X", Normal(0, 1), (declared, w.p))
+            m.sample("y", Bernoulli(logits=X @ theta))
+
+    return regression if w.family == "normal" else minibatch_logistic
 
 
 # ---------------------------------------------------------------------------------------------
@@ -145,12 +181,13 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle port on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_sample(rows, particles, steps, warmup):
+def cpu_sample(w, rows, particles, steps, warmup):
     """Time the CPU restatement of the reference path (validation on, as shipped) on a bounded
     sample: `rows` observations, `particles` sequential evaluations per step."""
     from oracle import configs, elbo
     torch.manual_seed(0)
-    config = configs.regression(rows, P, seed0=SEED0)
+    config = configs.regression(rows, w.p, seed0=SEED0) if w.family == "normal" else \
+        configs.logistic(w.declared_rows, rows, p=w.p, seed0=SEED0)
     approx, leaves = config.approximation()
     optimizer = torch.optim.Adam(list(leaves.values()), lr=0.01)
 
@@ -173,17 +210,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    rows, particles = 2_000_000, 2
-    value, seconds = cpu_sample(rows, particles, args.steps, args.warmup)
+    w = WORKLOADS[args.workload]
+    rows, particles = (2_000_000, 2) if w.key == "c2" else (500_000, 2)
+    value, seconds = cpu_sample(w, rows, particles, args.steps, args.warmup)
     cores = torch.get_num_threads()
-    sample = (f"{rows} rows x {particles} particles per step of the N=1e8, S=64 workload "
+    sample = (f"{rows} rows x {particles} particles per step of the {w.name} workload "
               f"(oracle port of mininf's torch.distributions path, validation on, {cores} threads)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "bayesian_linear_regression_p64_N1e8_S64", "rows_per_gpu": N_FULL,
-                   "features": P, "particles": S, "cpu_sample": sample},
+        "config": {"workload": w.name, "rows_per_gpu": w.rows,
+                   "features": w.p, "particles": w.particles, "cpu_sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -208,18 +246,32 @@ def run_b200(args):
     if distributed:
         dist.init_process_group("nccl", device_id=device)
 
-    n_rows = int(args.rows)
-    X, y = make_data(n_rows, device, SEED0 + rank * 256)
+    w = WORKLOADS[args.workload]
+    P, S = w.p, w.particles
+    n_rows = int(args.rows) or w.rows
+    # one resident data set (c2) or the resident batches of the stream (c3), 256 seeds apart
+    batches = [make_data(w, n_rows, device, SEED0 + (rank * w.n_batches + b) * 256) for b in range(w.n_batches)]
+    X, y = batches[0]
+    # validate_args=False is passed through to torch.distributions.Normal (as in the reference):
+    # its constructor check is a host round trip per step; the kernels check scales on the device
     approximation = mininf.nn.ParameterizedDistribution(
-        Normal, loc=torch.zeros(P, device=device), scale=0.1 * torch.ones(P, device=device))
-    optimizer = torch.optim.Adam(approximation.parameters(), lr=0.01, capturable=not args.eager)
+        Normal, loc=torch.zeros(P, device=device), scale=0.1 * torch.ones(P, device=device), validate_args=False)
+    streaming = w.n_batches > 1
+    optimizer = torch.optim.Adam(approximation.parameters(), lr=0.01, capturable=not (args.eager or streaming))
     loss_module = mininf.nn.EvidenceLowerBoundLoss(S, dense_precision="tf32",
                                                    process_group=True if distributed else None)
-    conditioned = mininf.condition(model_factory(mininf, n_rows), X=X, y=y)
+    model = model_factory(mininf, w, n_rows)
+    conditioned = mininf.condition(model, X=X, y=y)
+    calls = [0]
 
     def eager_step():
         optimizer.zero_grad(set_to_none=True)
-        loss = loss_module(conditioned, {"theta": approximation()})
+        if streaming:       # condition on the next batch, as the reference's data-loader loop does
+            Xb, yb = batches[calls[0] % w.n_batches]
+            calls[0] += 1
+            loss = loss_module(mininf.condition(model, X=Xb, y=yb), {"theta": approximation()})
+        else:
+            loss = loss_module(conditioned, {"theta": approximation()})
         loss.backward()
         optimizer.step()
         return loss
@@ -254,7 +306,7 @@ def run_b200(args):
     # The SVI step is recorded once into a CUDA graph (mininf_b200.nn.GraphedStep) and replayed:
     # the same kernels in the same order, one launch per step. Sharded runs keep the eager loop:
     # capturing the NCCL all-reduce of this torch/NCCL build into the graph hung on 2 GPUs.
-    graphed = not args.eager and not distributed
+    graphed = not args.eager and not distributed and not streaming
     step = mininf.nn.GraphedStep(loss_module, conditioned, lambda: {"theta": approximation()},
                                  optimizer) if graphed else eager_step
     for _ in range(max(args.warmup, 3)):
@@ -284,14 +336,14 @@ def run_b200(args):
     # ---- end to end: host buffers, H2D of the step's inputs and D2H of its result every step ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, step, X, y, n_rows, world, device, fence, distributed)
+        e2e = run_e2e(args, w, step, batches, n_rows, world, device, fence, distributed)
 
     if rank == 0:
         peak, peak_source = measured_peak_gbs()
         algorithmic_bytes = n_rows * (4 * P + 4)
         achieved = algorithmic_bytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
-        traffic_file = ROOT / "profiles" / "dense_tc_traffic.json"
+        traffic_file = ROOT / "profiles" / w.traffic_file
         if traffic_file.exists():
             try:
                 per_row = json.loads(traffic_file.read_text())["dram_bytes_per_row"]
@@ -300,19 +352,22 @@ def run_b200(args):
                 traffic = None
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            rows_cpu, parts_cpu = 2_000_000, 2
-            cpu_value, _ = cpu_sample(rows_cpu, parts_cpu, steps=3, warmup=1)
+            rows_cpu, parts_cpu = (2_000_000, 2) if w.key == "c2" else (500_000, 2)
+            cpu_value, _ = cpu_sample(w, rows_cpu, parts_cpu, steps=3, warmup=1)
             cpu_baseline = {"value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                             "sample": f"{rows_cpu} rows x {parts_cpu} particles per step, 3 timed steps, of the "
-                                      "N=1e8 S=64 workload; oracle port of the reference's torch.distributions "
+                                      f"{w.name} workload; oracle port of the reference's torch.distributions "
                                       "path with validation on"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "tf32 operands / f32 accumulate", "data": "synthetic",
-            "config": {"workload": "bayesian_linear_regression_p64_N1e8_S64", "rows_per_gpu": n_rows,
+            "config": {"workload": w.name, "rows_per_gpu": n_rows,
                        "features": P, "particles": S, "parallelism": f"row shards x{world}, one all-reduce/step",
-                       "l2": "inputs (26 GB per GPU) far exceed the 126 MB L2; no flush needed",
+                       "l2": f"inputs ({n_rows * (4 * P + 4) / 1e9:.1f} GB per step and GPU) far exceed the "
+                             "126 MB L2; no flush needed",
+                       "stream": (f"{w.n_batches} resident batches alternate; the cached plan is rebound to "
+                                  "each batch (no retrace)") if streaming else "one resident data set",
                        "step": "zero_grad + ELBO/grad kernels + backward + Adam" +
                                (", replayed from one CUDA graph (GraphedStep)" if graphed else ", eager launches"),
                        "final_loss": final_loss},
@@ -321,7 +376,7 @@ def run_b200(args):
             "gpu_launches": plan.gpu_launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_source,
-                         "kernel": "mnf::tc::dense_tc_kernel<Normal> (+ its 5 us partial-sum reduction)",
+                         "kernel": w.kernel,
                          "kernel_ms": kernel_ms, "algorithmic_bytes": algorithmic_bytes,
                          "kernel_timing": f"CUDA events around each launch, {args.steps} eager steps run "
                                           "right before the timed region on the same data"},
@@ -334,10 +389,12 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, step, X, y, n_rows, world, device, fence, distributed):
+def run_e2e(args, w, step, batches, n_rows, world, device, fence, distributed):
     """Same step, but the inputs live in pinned host memory and are copied to the device inside
     the timed region every step; the loss is read back to the host every step."""
     import psutil
+    P, S = w.p, w.particles
+    X, y = batches[0]
     need = X.numel() * 4 + y.numel() * 4
     available = psutil.virtual_memory().available
     rows = n_rows
@@ -355,13 +412,15 @@ def run_e2e(args, step, X, y, n_rows, world, device, fence, distributed):
     fence()
     begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     begin.record()
-    for _ in range(steps):
-        # every input byte of the step crosses PCIe; if the pinned buffer is smaller than the
-        # data set it is sent repeatedly until all n_rows rows have been overwritten
+    for i in range(steps):
+        # every input byte of the step crosses PCIe into the buffers the step reads; if the
+        # pinned buffer is smaller than the data set it is sent repeatedly until all n_rows rows
+        # have been overwritten
+        Xd, yd = batches[i % len(batches)]
         for lo in range(0, n_rows, rows):
             m = min(rows, n_rows - lo)
-            X[lo:lo + m].copy_(X_host[:m], non_blocking=True)
-            y[lo:lo + m].copy_(y_host[:m], non_blocking=True)
+            Xd[lo:lo + m].copy_(X_host[:m], non_blocking=True)
+            yd[lo:lo + m].copy_(y_host[:m], non_blocking=True)
         loss = step()
         loss_host = loss.item()        # device -> host read of the step's result
     end.record()

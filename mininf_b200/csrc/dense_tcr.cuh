@@ -25,7 +25,7 @@
 // rings; HBM latency is hidden by L2 prefetches (cp.async.bulk.prefetch.tensor) issued
 // kPrefetchChunks ahead of the K-ring loads, so both rings hit L2 and X leaves HBM once. The MMA
 // warp interleaves, chunk by chunk, the eta product of tile t with the gradient product of tile
-// t - kSkew: both rings drain at a steady rate and need only cover the L2 latency.
+// t - 1: both rings drain at a steady rate and need only cover the L2 latency.
 //
 // Warps (256 threads): 0-3 epilogue (thread = tile row = TMEM lane), 4 MN-ring TMA, 5 K-ring TMA
 // and L2 prefetch, 6 stages y (and the mask) of each tile in shared memory, 7 TMEM allocation and
@@ -68,11 +68,9 @@ using tc::tma_load_2d;
 constexpr int kTileM = 128;            // rows per tile: MMA M of the eta product, K of the gradient product
 constexpr int kChunk = 64;             // features per operand chunk
 constexpr int kMaxStages = 4;          // ring depths (chunks) are chosen by the host, 2..4 each
-#ifndef MNF_TCR_SKEW
-#define MNF_TCR_SKEW 1
-#endif
-constexpr int kSkew = MNF_TCR_SKEW;    // the gradient product of a tile is issued kSkew tiles after its eta product
-static_assert(kSkew == 1 || kSkew == 2, "skew");
+// The gradient product of a tile is issued one tile after its eta product. (Two tiles would take
+// the epilogue off the critical path entirely but measured 25 % slower at p = 256: the MN-major
+// re-read of a tile then arrives too long after its first touch and misses L2.)
 constexpr int kFlush = 8;              // tiles accumulated in TMEM before the gradient tiles are drained
 constexpr int kStatFlush = 256;        // tiles between fp32 -> fp64 hand-overs of the row statistics
 #ifndef MNF_TCR_PREFETCH
@@ -347,25 +345,21 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     int kst = 0, mst = 0;
     uint32_t kph = 0, mph = 0;
     // Step t interleaves, chunk by chunk, the eta product of tile t with the gradient product of
-    // tile t - kSkew, so both rings drain at a steady rate and the epilogue of a tile overlaps
+    // tile t - 1, so both rings drain at a steady rate and the epilogue of a tile overlaps
     // tensor-core work of its neighbours.
-    for (int64_t t = 0; t < my_tiles + kSkew; ++t) {
+    for (int64_t t = 0; t <= my_tiles; ++t) {
       const bool has_eta = t < my_tiles;
-      const int64_t kk = t - kSkew;
+      const int64_t kk = t - 1;
       const bool has_g = kk >= 0;
       const uint32_t be = (uint32_t)(t & 1), bg = (uint32_t)(kk & 1);
       const int64_t grp = has_g ? kk / kFlush : 0;
       const uint32_t gb = (uint32_t)(grp & 1);
       const bool first = has_g && (kk % kFlush) == 0;
       const bool last = has_g && ((kk % kFlush) == kFlush - 1 || kk == my_tiles - 1);
-      // eta buffer `be` was read by the epilogue of tile t-2: with kSkew == 1 its r_ready was
-      // awaited in the previous step; with kSkew == 2 it is the tile whose gradient product runs now
-      if (kSkew == 2 && has_g) {
-        mbar_wait(bRReady + 8 * bg, (uint32_t)((kk >> 1) & 1));
-        if (first) mbar_wait(bGEmpty + 8 * gb, (uint32_t)(((grp >> 1) & 1) ^ 1));
-      }
       for (int c = 0; c < C; ++c) {
         if (has_eta) {
+          // eta buffer `be` was read by the epilogue of tile t-2, whose r_ready was awaited in the
+          // previous step
           mbar_wait(bKFull + 8 * kst, kph);
           tc_fence_after();
           if (elect_one()) {
@@ -381,15 +375,15 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
               }
             }
             tc_commit(bKEmpty + 8 * kst);
-            // kSkew == 1: the epilogue may start now (it writes the R buffer the gradient product
-            // of this step does not read). kSkew == 2: see the end of the step.
-            if (kSkew == 1 && c == C - 1) tc_commit(bEtaFull + 8 * be);
+            // the epilogue may start now: it writes the R buffer that the gradient product of
+            // this step does not read
+            if (c == C - 1) tc_commit(bEtaFull + 8 * be);
           }
           __syncwarp();
           if (++kst == k_stages) { kst = 0; kph ^= 1u; }
         }
         if (has_g) {
-          if (kSkew == 1 && c == 0) {
+          if (c == 0) {
             mbar_wait(bRReady + 8 * bg, (uint32_t)((kk >> 1) & 1));
             if (first) mbar_wait(bGEmpty + 8 * gb, (uint32_t)(((grp >> 1) & 1) ^ 1));
           }
@@ -410,12 +404,6 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
           __syncwarp();
           if (++mst == mn_stages) { mst = 0; mph ^= 1u; }
         }
-      }
-      // kSkew == 2: the epilogue of tile t writes the R buffer the gradient product of this step
-      // has been reading, so it is released only behind those MMAs
-      if (kSkew == 2 && has_eta) {
-        if (elect_one()) tc_commit(bEtaFull + 8 * be);
-        __syncwarp();
       }
     }
   } else if (warp < kEpiWarps) {
