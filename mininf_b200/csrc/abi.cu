@@ -117,12 +117,15 @@ int launch_dense_tc(const mnf_dense_site_t& site, const float* z, int S, int D, 
 // rows-on-lanes tcgen05 kernel: p = 64 * C, S <= 32, optional intercept (dense_tcr.cuh)
 struct TcrShape {
   int NS, C, k_stages, mn_stages;
+  int passes, s_pass;     // more than 32 particles run as `passes` sweeps of at most s_pass particles
   size_t smem;
 };
 bool tcr_shape(int p, int S, int max_smem_optin, TcrShape* out) {
-  if (p <= 0 || p % tcr::kChunk != 0 || S > 32) return false;
+  if (p <= 0 || p % tcr::kChunk != 0 || S > 128) return false;
   TcrShape sh;
-  sh.NS = S <= 16 ? 16 : 32;
+  sh.passes = (S + 31) / 32;
+  sh.s_pass = (S + sh.passes - 1) / sh.passes;
+  sh.NS = sh.s_pass <= 16 ? 16 : 32;
   sh.C = p / tcr::kChunk;
   if ((2 + 2 * sh.C) * sh.NS > (int)tcr::kTmemCols) return false;
   // split what is left of shared memory between the two operand rings, K ring first
@@ -325,6 +328,14 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
   const int ncol = 1 + p + 2;
   float* partial = static_cast<float*>(workspace);
   int grid = 0;
+  ColMap map;
+  map.n_vec = p;
+  map.vec_lat = s.theta_lat;
+  map.n_scalar = 2;
+  for (int i = 0; i < 16; ++i) map.scalar_lat[i] = -1;
+  map.scalar_lat[0] = s.icpt_lat;
+  // gradient w.r.t. the scale link's pre-transform value u goes to its latent scalar
+  map.scalar_lat[1] = s.family == MNF_NORMAL ? s.scale.a_lat : -1;
 
   if (mode == MNF_DENSE_TF32) {
     const bool aligned = (reinterpret_cast<uintptr_t>(s.X) % 16 == 0) && (s.ldx % 4 == 0) &&
@@ -335,8 +346,8 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
     const bool c2_shape = which == 1, wide_shape = which == 2;
     if (!aligned || c->cc_major != 10 || !(c2_shape || wide_shape))
       return fail(MNF_E_UNSUPPORTED,
-                  "mnf_dense_sweep: TF32 mode needs p == 64 with S <= 64, or p a "
-                  "multiple of 64 with S <= 32 (and (2 + p/32) * S within 512 TMEM columns), 16-byte "
+                  "mnf_dense_sweep: TF32 mode needs p == 64 with S <= 64, or p a multiple of 64 with "
+                  "S <= 128 (passes of <= 32 particles, (2 + p/32) * 32 within 512 TMEM columns), 16-byte "
                   "aligned rows and an sm_100 device%s%s");
     const int64_t n_tiles = (s.n_rows + tc::kTileM - 1) / tc::kTileM;
     grid = (int)std::min<int64_t>(n_tiles, c->sm_count);
@@ -354,9 +365,19 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
         rc = has_icpt ? launch_dense_tc<MNF_POISSON, true>(s, z, S, D, partial, status, grid, stream)
                       : launch_dense_tc<MNF_POISSON, false>(s, z, S, D, partial, status, grid, stream);
     } else {
-      if (s.family == MNF_NORMAL) rc = launch_dense_tcr<MNF_NORMAL>(s, z, S, D, sh, has_icpt, partial, status, grid, stream);
-      else if (s.family == MNF_BERNOULLI_LOGITS) rc = launch_dense_tcr<MNF_BERNOULLI_LOGITS>(s, z, S, D, sh, has_icpt, partial, status, grid, stream);
-      else rc = launch_dense_tcr<MNF_POISSON>(s, z, S, D, sh, has_icpt, partial, status, grid, stream);
+      // at most 32 particles per sweep: larger S runs in passes (X is re-read by every pass)
+      for (int pass = 0; pass < sh.passes; ++pass) {
+        const int s0 = pass * sh.s_pass, sn = std::min(sh.s_pass, S - s0);
+        const float* zp = z + (size_t)s0 * D;
+        float* pp = partial + (size_t)grid * s0 * ncol;
+        if (s.family == MNF_NORMAL) rc = launch_dense_tcr<MNF_NORMAL>(s, zp, sn, D, sh, has_icpt, pp, status, grid, stream);
+        else if (s.family == MNF_BERNOULLI_LOGITS) rc = launch_dense_tcr<MNF_BERNOULLI_LOGITS>(s, zp, sn, D, sh, has_icpt, pp, status, grid, stream);
+        else rc = launch_dense_tcr<MNF_POISSON>(s, zp, sn, D, sh, has_icpt, pp, status, grid, stream);
+        if (rc) return rc;
+        rc = launch_reduce(pp, grid, sn, ncol, map, s.weight, D, acc + (size_t)s0 * (D + 1), stream);
+        if (rc) return rc;
+      }
+      return MNF_OK;
     }
     if (rc) return rc;
   } else if (mode == MNF_DENSE_FP32) {
@@ -374,14 +395,6 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
     return fail(MNF_E_INVALID, "mnf_dense_sweep: unknown mode%s%s");
   }
 
-  ColMap map;
-  map.n_vec = p;
-  map.vec_lat = s.theta_lat;
-  map.n_scalar = 2;
-  for (int i = 0; i < 16; ++i) map.scalar_lat[i] = -1;
-  map.scalar_lat[0] = s.icpt_lat;
-  // gradient w.r.t. the scale link's pre-transform value u goes to its latent scalar
-  map.scalar_lat[1] = s.family == MNF_NORMAL ? s.scale.a_lat : -1;
   return launch_reduce(partial, grid, S, ncol, map, s.weight, D, acc, stream);
 }
 

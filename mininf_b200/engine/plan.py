@@ -517,7 +517,10 @@ class Plan:
     def gpu_launches_per_step(self) -> int:
         """Kernels of this library launched by one :meth:`step` (sweeps come with a reduction)."""
         count = 2  # rsample + finalize
-        count += 2 * len(self.dense_sites)
+        for site, mode in self.dense_sites:
+            # the wide tcgen05 kernel takes at most 32 particles per sweep (csrc/abi.cu::tcr_shape)
+            wide = mode == abi.DENSE_TF32 and self.lib.raw("mnf_dense_tf32_kernel")(site.family, site.p, self.S) == 2
+            count += 2 * (-(-self.S // 32) if wide else 1)
         for group in self.sweep_groups:
             # sites with a specialised kernel run on their own (csrc/site_sweep.cuh::site_fast_kind)
             fast = sum(1 for i in range(len(group)) if _has_fast_sweep(group[i]))
