@@ -206,7 +206,7 @@ int mnf_rsample(const mnf_latent_t* latents_dev, int n_latents, int n_particles,
 /*
  * Which tcgen05 kernel MNF_DENSE_TF32 runs for a dense site of `family` with p features and S
  * particles (host-only query, no device needed): 0 = shape not covered (use MNF_DENSE_FP32),
- * 1 = csrc/dense_tc.cuh (p == 64, S <= 64), 2 = csrc/dense_tcr.cuh (p = 64 C within 512 TMEM
+ * 1 = csrc/dense_tc.cuh (p == 64, S <= 64), 2 = csrc/dense_tcr.cuh (p % 4 == 0, ceil(p/64) chunks within 512 TMEM
  * columns and 227 KB of shared memory; up to 32 particles per sweep, 33..128 particles run as 2-4
  * sweeps over X). Intercepts are supported by both. X must also be 16-byte aligned with
  * ldx % 4 == 0 and fewer than 2^31 rows.

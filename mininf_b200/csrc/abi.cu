@@ -121,12 +121,12 @@ struct TcrShape {
   size_t smem;
 };
 bool tcr_shape(int p, int S, int max_smem_optin, TcrShape* out) {
-  if (p <= 0 || p % tcr::kChunk != 0 || S > 128) return false;
+  if (p <= 0 || p % 4 != 0 || S > 128) return false;     // rows must be 16-byte multiples for TMA
   TcrShape sh;
   sh.passes = (S + 31) / 32;
   sh.s_pass = (S + sh.passes - 1) / sh.passes;
   sh.NS = sh.s_pass <= 16 ? 16 : 32;
-  sh.C = p / tcr::kChunk;
+  sh.C = (p + tcr::kChunk - 1) / tcr::kChunk;            // the last chunk is zero-padded by TMA
   if ((2 + 2 * sh.C) * sh.NS > (int)tcr::kTmemCols) return false;
   // split what is left of shared memory between the two operand rings, K ring first
   for (int stages = 2 * tcr::kMaxStages; stages >= 4; --stages) {
@@ -346,9 +346,9 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
     const bool c2_shape = which == 1, wide_shape = which == 2;
     if (!aligned || c->cc_major != 10 || !(c2_shape || wide_shape))
       return fail(MNF_E_UNSUPPORTED,
-                  "mnf_dense_sweep: TF32 mode needs p == 64 with S <= 64, or p a multiple of 64 with "
-                  "S <= 128 (passes of <= 32 particles, (2 + p/32) * 32 within 512 TMEM columns), 16-byte "
-                  "aligned rows and an sm_100 device%s%s");
+                  "mnf_dense_sweep: TF32 mode needs p == 64 with S <= 64, or p a multiple of 4 with "
+                  "S <= 128 (passes of <= 32 particles, (2 + ceil(p/64) * 2) * 32 within 512 TMEM columns), "
+                  "16-byte aligned rows and an sm_100 device%s%s");
     const int64_t n_tiles = (s.n_rows + tc::kTileM - 1) / tc::kTileM;
     grid = (int)std::min<int64_t>(n_tiles, c->sm_count);
     if ((size_t)grid * S * ncol * sizeof(float) > workspace_bytes)

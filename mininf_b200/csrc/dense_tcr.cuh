@@ -1,6 +1,7 @@
 // Dense-link sweep, tcgen05 variant with observations on the TMEM lanes ("rows-on-lanes"):
-// the tensor-core kernel for wide design matrices (p = 64 * C features, any C that fits), at most
-// 32 particles, with or without an intercept. Config C3 (minibatch logistic regression, p = 256,
+// the tensor-core kernel for wide design matrices (p <= 64 * C features, p % 4 == 0, any C that
+// fits; the TMA unit zero-fills the padding columns of the last chunk), at most 32 particles per
+// sweep, with or without an intercept. Config C3 (minibatch logistic regression, p = 256,
 // S = 16) runs here; dense_tc.cuh keeps the p = 64 / S <= 64 shape of config C2.
 //
 // One persistent CTA per SM walks 128-row tiles; a tile is streamed as C chunks of 64 features
@@ -161,7 +162,8 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int p = C * kChunk;
+  const int p = site.p;                 // features; C * kChunk >= p, the padding columns are zero
+  const int p_pad = C * kChunk;
   const int ncol = 1 + p + 2;
 
   const int64_t n_tiles = (site.n_rows + kTileM - 1) / kTileM;
@@ -209,9 +211,9 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
   }
   // Theta as the B operand of the eta product: particle n is row n, feature j is k; spare particle
   // rows are zero. Consecutive threads take consecutive features of one particle.
-  for (int i = tid; i < NS * p; i += kThreads) {
-    const int n = i / p, j = i - n * p;
-    const uint32_t v = n < S ? rn_tf32(z[(int64_t)n * D + site.theta_lat + j]) : 0u;
+  for (int i = tid; i < NS * p_pad; i += kThreads) {
+    const int n = i / p_pad, j = i - n * p_pad;
+    const uint32_t v = (n < S && j < p) ? rn_tf32(z[(int64_t)n * D + site.theta_lat + j]) : 0u;
     sts32(sTheta + kmajor_offset(NS, n, j), v);
   }
   fence_proxy_async();
@@ -411,10 +413,12 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     const int trow = warp * 32 + lane;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
     // gradient drain: lanes 0-15 of quadrant `warp` carry features 16*warp + lane of every chunk
-    const bool g_owner = lane < 16;
+    // (features past p exist only as zero padding of the last chunk)
+    const int f_lane = 16 * warp + lane;
+    auto owns = [&](int c) { return lane < 16 && kChunk * c + f_lane < p; };
     float* g_out = partial + (size_t)blockIdx.x * S * ncol + 1 + 16 * warp + lane;   // + n * ncol + 64 * c
-    if (g_owner)
-      for (int c = 0; c < C; ++c)
+    for (int c = 0; c < C; ++c)
+      if (owns(c))
         for (int n = 0; n < S; ++n) g_out[(size_t)n * ncol + kChunk * c] = 0.f;
     int64_t n_drained = 0;
     auto drain = [&]() {
@@ -426,6 +430,7 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
         uint32_t v[NS];
         float old[NS];
         // all loads of the read-modify-write first: one L2 round trip per chunk instead of NS
+        const bool g_owner = owns(c);
         if (g_owner) {
 #pragma unroll
           for (int n = 0; n < NS; ++n) old[n] = n < S ? __ldcg(g_out + (size_t)n * ncol + kChunk * c) : 0.f;
@@ -526,11 +531,12 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     asm volatile("bar.sync 1, %0;" ::"n"((kEpiWarps + 1) * 32) : "memory");
 
     // ---- per-particle results -----------------------------------------------------------------
-    if (FAMILY == MNF_NORMAL && g_owner) {
+    if (FAMILY == MNF_NORMAL) {
       for (int n = 0; n < S; ++n) {
         const float sc = par_at(n)->scale;
         const float iv = 1.0f / (sc * sc);
-        for (int c = 0; c < C; ++c) g_out[(size_t)n * ncol + kChunk * c] *= iv;
+        for (int c = 0; c < C; ++c)
+          if (owns(c)) g_out[(size_t)n * ncol + kChunk * c] *= iv;
       }
     }
     if (trow < S) {

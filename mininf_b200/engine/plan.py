@@ -416,7 +416,7 @@ class Plan:
             X.stride(0) % 4 == 0 and n < 2 ** 31
         if self.dense_mode == "tf32" and not tf32_ok:
             raise NotImplementedError(f"{what}: the tcgen05 TF32 kernels need p == 64 with at most 64 "
-                                      "particles, or p a multiple of 64 with at most 32 particles, "
+                                      "particles, or p a multiple of 4 with at most 128 particles, "
                                       "and 16-byte aligned rows")
         mode = abi.DENSE_TF32 if (self.dense_mode in ("auto", "tf32") and tf32_ok) else abi.DENSE_FP32
         self.dense_sites.append((site, mode))

@@ -191,11 +191,13 @@ def test_wide_tensor_core_kernel_matches_golden():
 @pytest.mark.parametrize("n,p,S,intercept", [(1, 64, 1, True), (129, 128, 16, False), (1000, 256, 16, True),
                                              (5000, 192, 17, True), (4097, 448, 32, False),
                                              (70_000, 256, 32, True), (3000, 64, 64, True), (40_000, 64, 33, True),
-                                             (3000, 128, 64, True), (2000, 192, 40, False), (900, 128, 100, True)])
+                                             (3000, 128, 64, True), (2000, 192, 40, False), (900, 128, 100, True),
+                                             (301, 24, 3, False), (5000, 100, 20, True), (700, 8, 8, True)])
 def test_wide_tensor_core_kernel_against_oracle(n, p, S, intercept):
     """Shapes around the tile (128 rows), chunk (64 features), particle-slot (16 / 32) and
     drain-group (8 tiles) boundaries of dense_tcr.cuh, more than 32 particles (two to four passes
-    of the wide kernel), and p = 64 with an intercept (dense_tc.cuh),
+    of the wide kernel), feature counts that are not multiples of 64 (zero-filled last chunk),
+    and p = 64 with an intercept (dense_tc.cuh),
     minibatch weight included; the fp32 kernel and the oracle agree to 1e-5, the TF32 kernels
     within the stated TF32 tolerance."""
     torch.manual_seed(n + p)

@@ -41,11 +41,21 @@ def test_regression_lowers_to_one_dense_site_and_two_priors():
 
 
 def test_shapes_outside_the_tensor_core_kernel_use_fp32_or_raise():
-    config = configs.regression(100, 24)
-    sites, specs = trace(lambda: config.model(mininf), {"theta": (abi.NORMAL, torch.randn(24))}, config.data)
+    # rows of 22 floats are not 16-byte multiples: no TMA, hence no tcgen05 kernel
+    config = configs.regression(100, 22)
+    sites, specs = trace(lambda: config.model(mininf), {"theta": (abi.NORMAL, torch.randn(22))}, config.data)
     assert Plan(sites, specs, 8, CPU, dry_run=True).dense_sites[0][1] == abi.DENSE_FP32
     with pytest.raises(NotImplementedError, match="p == 64"):
         Plan(sites, specs, 8, CPU, dense_mode="tf32", dry_run=True)
+    # more than 128 particles
+    config = configs.regression(100, 128)
+    sites, specs = trace(lambda: config.model(mininf), {"theta": (abi.NORMAL, torch.randn(128))}, config.data)
+    assert Plan(sites, specs, 129, CPU, dry_run=True).dense_sites[0][1] == abi.DENSE_FP32
+    # any multiple of four features runs on the wide kernel (TMA zero-fills the last chunk)
+    config = configs.regression(100, 24)
+    sites, specs = trace(lambda: config.model(mininf), {"theta": (abi.NORMAL, torch.randn(24))}, config.data)
+    plan = Plan(sites, specs, 40, CPU, dry_run=True)
+    assert plan.dense_sites[0][1] == abi.DENSE_TF32 and plan.gpu_launches_per_step == 2 + 2 * 2 + 1
 
 
 def test_minibatch_weight_and_logits_family():
