@@ -307,8 +307,13 @@ def run_b200(args):
     # the same kernels in the same order, one launch per step. Sharded runs keep the eager loop:
     # capturing the NCCL all-reduce of this torch/NCCL build into the graph hung on 2 GPUs.
     graphed = not args.eager and not distributed and not streaming
-    step = mininf.nn.GraphedStep(loss_module, conditioned, lambda: {"theta": approximation()},
-                                 optimizer) if graphed else eager_step
+    step, graph_note = eager_step, None
+    if graphed:
+        try:
+            step = mininf.nn.GraphedStep(loss_module, conditioned, lambda: {"theta": approximation()}, optimizer)
+        except Exception as error:  # noqa: BLE001  keep measuring: the eager loop runs the same kernels
+            graphed, graph_note = False, f"CUDA graph capture failed ({type(error).__name__}); eager launches"
+            torch.cuda.synchronize()
     for _ in range(max(args.warmup, 3)):
         step()
     begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -369,7 +374,8 @@ def run_b200(args):
                        "stream": (f"{w.n_batches} resident batches alternate; the cached plan is rebound to "
                                   "each batch (no retrace)") if streaming else "one resident data set",
                        "step": "zero_grad + ELBO/grad kernels + backward + Adam" +
-                               (", replayed from one CUDA graph (GraphedStep)" if graphed else ", eager launches"),
+                               (", replayed from one CUDA graph (GraphedStep)" if graphed
+                                else ", " + (graph_note or "eager launches")),
                        "final_loss": final_loss},
             "clocks": clocks,
             "e2e": e2e,
