@@ -210,23 +210,42 @@ int launch_site_sweep(const mnf_site_t* sites, const float* z, int S, int D, flo
 }
 
 
-template <int KIND>
-int launch_site_fast(const mnf_site_t& site, const float* z, int S, int D, float* partial,
-                     uint32_t* status, int grid, cudaStream_t stream) {
-  if (S <= 32) {
-    auto kernel = site_fast_kernel<KIND, 1>;
-    const size_t smem = site_fast_smem_bytes<KIND, 1>();
-    kernel<<<grid, kSweepThreads, smem, stream>>>(site, z, S, D, partial, status);
-  } else if (S <= 64) {
-    auto kernel = site_fast_kernel<KIND, 2>;
-    const size_t smem = site_fast_smem_bytes<KIND, 2>();
-    kernel<<<grid, kSweepThreads, smem, stream>>>(site, z, S, D, partial, status);
-  } else {
-    auto kernel = site_fast_kernel<KIND, 4>;
-    const size_t smem = site_fast_smem_bytes<KIND, 4>();
-    MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kernel<<<grid, kSweepThreads, smem, stream>>>(site, z, S, D, partial, status);
-  }
+template <int Q>
+int launch_poisson_exp_q(const mnf_site_t& site, const float* z, int S, int D, float* partial,
+                         uint32_t* status, int grid, cudaStream_t stream) {
+  auto kernel = poisson_exp_kernel<Q>;
+  const size_t smem = poisson_exp_smem_bytes<Q>();
+  MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kernel<<<grid, kSweepThreads, smem, stream>>>(site, z, S, D, partial, status);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+int launch_poisson_exp(const mnf_site_t& site, const float* z, int S, int D, float* partial,
+                       uint32_t* status, int grid, cudaStream_t stream) {
+  if (S <= 32) return launch_poisson_exp_q<1>(site, z, S, D, partial, status, grid, stream);
+  if (S <= 64) return launch_poisson_exp_q<2>(site, z, S, D, partial, status, grid, stream);
+  return launch_poisson_exp_q<4>(site, z, S, D, partial, status, grid, stream);
+}
+
+// Normal site with an identity location link and an element-independent scale: one data-only pass
+// for six sufficient statistics, then the per-particle closed forms straight into acc.
+int launch_normal_stats(const mnf_site_t& site, const float* z, int S, int D, double* acc, void* workspace,
+                        size_t workspace_bytes, uint32_t* status, int sm_count, cudaStream_t stream) {
+  const mnf_link_t& L0 = site.param[0];
+  const bool vec = reinterpret_cast<uintptr_t>(site.value) % 16 == 0 &&
+                   (L0.x == nullptr || (L0.x_stride == 1 && reinterpret_cast<uintptr_t>(L0.x) % 16 == 0)) &&
+                   (site.mask == nullptr || reinterpret_cast<uintptr_t>(site.mask) % 4 == 0);
+  const int64_t per_thread = vec ? 4 : 1;
+  const int64_t want = (site.numel + kStatThreads * per_thread - 1) / (kStatThreads * per_thread);
+  const int64_t fits = (int64_t)(workspace_bytes / (kStatCols * sizeof(double)));   // one row of statistics per CTA
+  if (fits < 1) return fail(MNF_E_INVALID, "mnf_site_sweep: workspace too small%s%s");
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, fits), 8 * (int64_t)sm_count));
+  double* cta_stats = static_cast<double*>(workspace);
+  if (vec) normal_stats_kernel<true><<<grid, kStatThreads, 0, stream>>>(site, cta_stats, status);
+  else normal_stats_kernel<false><<<grid, kStatThreads, 0, stream>>>(site, cta_stats, status);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  normal_stats_finish_kernel<<<1, 32 * kStatCols, 0, stream>>>(site, cta_stats, grid, z, S, D, acc, status);
   MNF_CUDA_CHECK(cudaGetLastError());
   return MNF_OK;
 }
@@ -244,17 +263,29 @@ bool family_has_two_params(int family) { return family <= MNF_BETA; }
 
 bool host_link_has_latent(const mnf_link_t& L) { return L.a_lat >= 0 || L.b_lat >= 0; }
 
-template <int SP>
-int launch_rowlatent(const mnf_rowlatent_t& d, const float* z, int S, int D, int s_begin,
-                            int first_pass, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
-                            int with_entropy, float* partial, uint32_t* status, int grid, cudaStream_t stream) {
-  auto kernel = rowlatent_kernel<SP>;
+template <int SP, bool FULL>
+int launch_rowlatent_inst(const mnf_rowlatent_t& d, const float* z, int S, int D, int s_begin,
+                          int first_pass, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                          int with_entropy, float* partial, uint32_t* status, int grid, cudaStream_t stream) {
+  auto kernel = rowlatent_kernel<SP, FULL>;
   const size_t smem = rowlatent_smem_bytes<SP>();
   MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel<<<grid, kRowThreads, smem, stream>>>(d, z, S, D, s_begin, first_pass, seed, offset, offset_dev,
                                                with_entropy, partial, status);
   MNF_CUDA_CHECK(cudaGetLastError());
   return MNF_OK;
+}
+
+// FULL: all SP particle slots of the launch are in use (no masking code in the kernel)
+template <int SP>
+int launch_rowlatent(const mnf_rowlatent_t& d, const float* z, int S, int D, int s_begin,
+                     int first_pass, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                     int with_entropy, float* partial, uint32_t* status, int grid, cudaStream_t stream) {
+  if (S - s_begin >= SP)
+    return launch_rowlatent_inst<SP, true>(d, z, S, D, s_begin, first_pass, seed, offset, offset_dev,
+                                           with_entropy, partial, status, grid, stream);
+  return launch_rowlatent_inst<SP, false>(d, z, S, D, s_begin, first_pass, seed, offset, offset_dev,
+                                          with_entropy, partial, status, grid, stream);
 }
 
 
@@ -429,8 +460,8 @@ int mnf_site_sweep(const mnf_site_t* sites, int n_sites, const float* z, int n_p
   const int grid = (int)std::min<int64_t>((n_chunks + kSweepWarps - 1) / kSweepWarps, 2 * c->sm_count);
   float* partial = static_cast<float*>(workspace);
 
-  // Sites with a specialised kernel (site_sweep.cuh: Poisson with an exp link, Normal with a
-  // per-particle scale) run on their own, one kernel + reduction each; the rest stay fused.
+  // Sites with a specialised kernel (site_sweep.cuh: Poisson with an exp link, Normal with an
+  // identity location link and a per-particle scale) run on their own; the rest stay fused.
   mnf_site_t generic[MNF_MAX_FUSED_SITES];
   int n_generic = 0;
   for (int i = 0; i < n_sites; ++i) {
@@ -439,19 +470,23 @@ int mnf_site_sweep(const mnf_site_t* sites, int n_sites, const float* z, int n_p
       generic[n_generic++] = sites[i];
       continue;
     }
-    if ((size_t)grid * S * 5 * sizeof(float) > workspace_bytes)
+    if (kind == kFastNormalId) {
+      if (int rc = launch_normal_stats(sites[i], z, S, D, acc, workspace, workspace_bytes, status, c->sm_count, stream))
+        return rc;
+      continue;
+    }
+    const int pgrid = (int)std::min<int64_t>((n_chunks + kSweepWarps - 1) / kSweepWarps,
+                                             (int64_t)pois_min_blocks(S <= 32 ? 1 : (S <= 64 ? 2 : 4)) * c->sm_count);
+    if ((size_t)pgrid * S * 5 * sizeof(float) > workspace_bytes)
       return fail(MNF_E_INVALID, "mnf_site_sweep: workspace too small%s%s");
-    const int rc = kind == kFastPoissonExp
-                       ? launch_site_fast<kFastPoissonExp>(sites[i], z, S, D, partial, status, grid, stream)
-                       : launch_site_fast<kFastNormalId>(sites[i], z, S, D, partial, status, grid, stream);
-    if (rc) return rc;
+    if (int rc = launch_poisson_exp(sites[i], z, S, D, partial, status, pgrid, stream)) return rc;
     ColMap fast_map;
     fast_map.n_vec = 0;
     fast_map.vec_lat = 0;
     fast_map.n_scalar = 4;
     for (int k = 0; k < 16; ++k) fast_map.scalar_lat[k] = -1;
     site_columns(sites[i], fast_map.scalar_lat);
-    if (int rr = launch_reduce(partial, grid, S, 5, fast_map, 1.0, D, acc, stream)) return rr;
+    if (int rr = launch_reduce(partial, pgrid, S, 5, fast_map, 1.0, D, acc, stream)) return rr;
   }
   if (n_generic == 0) return MNF_OK;
   sites = generic;
@@ -519,11 +554,15 @@ int mnf_rowlatent_sweep(const mnf_rowlatent_t* desc, const float* z, int n_parti
   DeviceCache* c;
   if (int rc = device_cache(-1, &c)) return rc;
   const int ncol = 1 + d.p + 5;
-  const int grid = (int)std::min<int64_t>((d.n_rows + kRowWarps - 1) / kRowWarps, 2 * c->sm_count);
+  const int grid = (int)std::min<int64_t>((d.n_rows + kRowWarps - 1) / kRowWarps, max_ctas(*c));
   if ((size_t)grid * S * ncol * sizeof(float) > workspace_bytes)
     return fail(MNF_E_INVALID, "mnf_rowlatent_sweep: workspace too small%s%s");
   float* partial = static_cast<float*>(workspace);
-  const int sp = S <= 4 ? 4 : (S <= 8 ? 8 : (S <= 16 ? 16 : 32));
+  int sp = S <= 4 ? 4 : (S <= 8 ? 8 : (S <= 16 ? 16 : 32));
+  if (const char* force = std::getenv("MNF_ROWLATENT_SP")) {   // developer override: particles per pass
+    const int v = std::atoi(force);
+    if (v == 4 || v == 8 || v == 16 || v == 32) sp = v;
+  }
   for (int s_begin = 0, pass = 0; s_begin < S; s_begin += sp, ++pass) {
     int rc;
     if (sp == 4) rc = launch_rowlatent<4>(d, z, S, D, s_begin, pass == 0, seed, offset, offset_dev, with_entropy, partial, status, grid, stream);

@@ -6,68 +6,109 @@
 // element-wise log_prob chains of three sites (mininf/core.py:241), `z @ slope` and its backward,
 // the entropy of q(Z) (TORCH normal.py:114-115) and autograd's n*p-sized gradient passes.
 //
-// Mapping: a warp owns a row, lane j owns feature j. Per row a lane keeps loc, scale, feature and
-// its two gradient accumulators in registers and loops over the particles in groups of four (one
-// Philox4x32-10 call -> two Box-Muller pairs). The per-particle dot products Z_i . beta_s are
-// reduced AND transposed in one 31-shuffle butterfly so that lane s ends up with particle s's
-// linear predictor: each lane then evaluates one exp per row instead of 32 redundant ones.
+// Mapping: a warp owns a row, lane j owns feature j. Per row a lane keeps loc, scale and feature
+// in registers and loops over the particles in groups of four (one Philox4x32-10 call -> two
+// Box-Muller pairs). The kernel is instruction-bound, so the per-(element, particle)
+// work is cut to what cannot be shared:
+//   * with z = loc + scale eps the feature site needs only E1 = sum_s eps, E2 = sum_s eps^2 per
+//     element (its scale is a constant): sum_s (x - z_s), sum_s (x - z_s) eps_s and
+//     sum_s (x - z_s)^2 are polynomials in them;
+//   * the prior site (scale sigma_s is a per-particle latent) needs W1 = sum_s eps_s / sigma_s^2,
+//     W2 = sum_s eps_s^2 / sigma_s^2 per element and sum_ij (z - m)^2 per particle;
+//   * the dot products Z_i . beta_s are reduced AND transposed in one 31-shuffle butterfly so that
+//     lane s ends up with particle s's linear predictor: one exp per lane and row;
+//   * d eta is handed back through a shared-memory slot read as 128-bit broadcasts; beta lives in
+//     shared memory as [lane][particle] (padded) so four particles come with one LDS.128.
 // Per-(particle, lane) statistics live in registers (SP is a template parameter), so the hot loop
-// has no shared-memory or atomic traffic. Algorithmic bytes per row: p * (loc 4 + scale 4 +
-// feature 4 + two gradients 8) + response 4.
+// has no atomics. Algorithmic bytes per row: p * (loc 4 + scale 4 + feature 4 + two gradients 8)
+// + response 4.
 #pragma once
 
 #include "common.cuh"
 
 namespace mnf {
 
-constexpr int kRowThreads = 256;
+constexpr int kRowThreads = 128;
 constexpr int kRowWarps = kRowThreads / 32;
 
 struct RowParticle {   // per-particle scalars of the row-latent sites, staged in shared memory
-  float prior_loc, prior_inv_var, prior_scale, prior_dscale;  // Normal prior of Z
-  float feat_inv_var, feat_scale, feat_dscale;                // Normal features
+  float prior_inv_var, prior_scale, prior_dscale;  // Normal prior of Z
   float icpt, resp_scale, resp_dscale;
+};
+
+// Two standard normals from two 32-bit words: Box-Muller on the MUFU pipe (lg2, sqrt, sin, cos
+// approximations; absolute error of the draws ~1e-6). The uniforms are built by bit insertion
+// (23 bits each, no integer->float conversion): u1 in (0, 1], the angle in [-pi, pi).
+__device__ __forceinline__ float2 box_muller_fast(uint32_t a, uint32_t b) {
+  const float f1 = __uint_as_float(0x3f800000u | (a >> 9));    // [1, 2)
+  const float f2 = __uint_as_float(0x3f800000u | (b >> 9));
+  const float u1 = 2.0f - f1;                                   // (0, 1]
+  const float theta = fmaf(f2, 6.2831853071795865f, -9.4247779607693797f);
+  const float r = __fsqrt_rn(-1.3862943611198906f * __log2f(u1));   // sqrt(-2 ln u1)
+  return make_float2(r * __cosf(theta), r * __sinf(theta));
+}
+
+// exp(u) as ex2(u * log2 e) with the product carried in two terms (relative error ~2 ulp)
+__device__ __forceinline__ float exp_fast(float u) {
+  const float t = fmaf(u, 1.925963033500011e-8f, u * 1.4426950216293335f);
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
+  return r;
+}
+
+template <int SP>
+struct RowSmem {
+  static constexpr int kBetaStride = SP + 4;             // floats; 16-byte rows, LDS.128 conflict-free
+  float beta[32 * kBetaStride];                          // [lane][particle]
+  float ipv[SP];                                         // prior 1/sigma_s^2 (0 for dead particles)
+  float deta[kRowWarps][SP];                             // d log p(y) / d eta of the row in flight
+  RowParticle par[SP];
+  float out[kRowWarps][SP][40];                          // final reduction scratch
 };
 
 // partial layout per CTA: [S][ncol], ncol = 1 + p + 5:
 //   0 log-density (+ entropy share), 1..p beta gradient, p+1 intercept, p+2 prior loc (du),
 //   p+3 prior scale (du), p+4 feature scale (du), p+5 response scale (du)
-template <int SP>
+// FULL: every particle slot of this launch is in use (s_count == SP): no masking code.
+template <int SP, bool FULL>
 __global__ void __launch_bounds__(kRowThreads)
 rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, int s_begin,
                  int first_pass, uint64_t seed, uint64_t offset, const uint64_t* __restrict__ offset_dev,
                  int with_entropy, float* __restrict__ partial, uint32_t* __restrict__ status) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RowSmem<SP>& sm = *reinterpret_cast<RowSmem<SP>*>(smem_raw);
+  constexpr int BS = RowSmem<SP>::kBetaStride;
   if (offset_dev != nullptr) offset += *offset_dev;   // device-side call index (CUDA-graph replays)
   const int p = d.p;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* sBeta = smem;                                             // [SP][32]
-  RowParticle* sPar = reinterpret_cast<RowParticle*>(sBeta + SP * 32);   // [SP]
-  float* sOut = reinterpret_cast<float*>(sPar + SP);               // [kRowWarps][SP][32 + 8] reduction scratch
+  const bool has_feat = d.feat != nullptr, has_resp = d.resp != nullptr;
 
-  const int s_count = min(SP, S - s_begin);   // particles handled by this launch
+  const int s_count = FULL ? SP : min(SP, S - s_begin);   // particles handled by this launch
   for (int i = threadIdx.x; i < SP * 32; i += kRowThreads) {
     const int s = i >> 5, j = i & 31;
-    sBeta[i] = (s < s_count && j < p && d.resp != nullptr) ? z[(int64_t)(s_begin + s) * D + d.beta_lat + j] : 0.0f;
+    sm.beta[j * BS + s] = (s < s_count && j < p && has_resp) ? z[(int64_t)(s_begin + s) * D + d.beta_lat + j] : 0.0f;
   }
   uint32_t bad = 0;
+  // prior location and feature scale are constants in this build (checked on the host)
+  const float prior_loc = d.prior_loc.a_const + d.prior_loc.b_const;
+  float feat_scale = 1.0f, feat_inv_var = 0.0f;
+  if (has_feat) {
+    const float u = d.feat_scale.a_const + d.feat_scale.b_const;
+    feat_scale = d.feat_scale.transform == MNF_T_EXP ? expf(u) : u;
+    feat_inv_var = 1.0f / (feat_scale * feat_scale);
+    if (!(feat_scale > 0.0f)) bad |= MNF_ST_BAD_PARAM;
+  }
   for (int s = threadIdx.x; s < SP; s += kRowThreads) {
     RowParticle rp;
-    rp.prior_loc = 0.f; rp.prior_inv_var = 0.f; rp.prior_scale = 1.f; rp.prior_dscale = 0.f;
-    rp.feat_inv_var = 0.f; rp.feat_scale = 1.f; rp.feat_dscale = 0.f;
+    rp.prior_inv_var = 0.f; rp.prior_scale = 1.f; rp.prior_dscale = 0.f;
     rp.icpt = 0.f; rp.resp_scale = 1.f; rp.resp_dscale = 0.f;
     if (s < s_count) {
       const float* zs = z + (int64_t)(s_begin + s) * D;
-      const LinkVal pl = eval_link(d.prior_loc, zs, 0), ps = eval_link(d.prior_scale, zs, 0);
-      rp.prior_loc = pl.value; rp.prior_scale = ps.value; rp.prior_dscale = ps.du;
+      const LinkVal ps = eval_link(d.prior_scale, zs, 0);
+      rp.prior_scale = ps.value; rp.prior_dscale = ps.du;
       rp.prior_inv_var = 1.0f / (ps.value * ps.value);
       if (!(ps.value > 0.0f)) bad |= MNF_ST_BAD_PARAM;
-      if (d.feat != nullptr) {
-        const LinkVal fs = eval_link(d.feat_scale, zs, 0);
-        rp.feat_scale = fs.value; rp.feat_dscale = fs.du; rp.feat_inv_var = 1.0f / (fs.value * fs.value);
-        if (!(fs.value > 0.0f)) bad |= MNF_ST_BAD_PARAM;
-      }
-      if (d.resp != nullptr) {
+      if (has_resp) {
         rp.icpt = d.icpt_const + (d.icpt_lat >= 0 ? zs[d.icpt_lat] : 0.0f);
         if (d.resp_family == MNF_NORMAL) {
           const LinkVal rs = eval_link(d.resp_scale, zs, 0);
@@ -76,9 +117,12 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
         }
       }
     }
-    sPar[s] = rp;
+    sm.par[s] = rp;
+    sm.ipv[s] = rp.prior_inv_var;
   }
   __syncthreads();
+  float ipv_sum = 0.f;     // sum over the live particles of 1/sigma_s^2
+  for (int s = 0; s < SP; ++s) ipv_sum += sm.ipv[s];
 
   // per-(particle, lane) statistics, registers
   float z2[SP], gb[SP];      // sum (z - prior_loc)^2 ; sum dlp/deta * z
@@ -86,28 +130,36 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
   for (int s = 0; s < SP; ++s) { z2[s] = 0.f; gb[s] = 0.f; }
   // per-particle statistics owned by lane s (after the butterfly lane s holds particle s)
   float ga = 0.f, lpy = 0.f, gresp_scale = 0.f;
-  // The feature scale and the prior location are constants in this build (checked on the host),
-  // so their residual sums need no per-particle breakdown: only the mean over particles is used.
   float f2 = 0.f;            // sum over particles and rows of (x - z)^2
   double ent = 0.0;          // entropy of q(Z)
   float n_rows_lane = 0.f;
   bool bad_value = false;
   const float invS = 1.0f / (float)S;
+  const float n_live = (float)s_count;
   const bool active = lane < p;
+  const float4* beta4 = reinterpret_cast<const float4*>(sm.beta + lane * BS);
+  const float4* ipv4 = reinterpret_cast<const float4*>(sm.ipv);
+  float* my_deta = sm.deta[warp];
+  const int sl = lane & (SP - 1);
+  const RowParticle rp_l = sm.par[sl];      // the particle this lane owns after the butterfly
+  const bool lane_live = sl < s_count;
 
   const int64_t warp_global = (int64_t)blockIdx.x * kRowWarps + warp;
   const int64_t warps_total = (int64_t)gridDim.x * kRowWarps;
   for (int64_t row = warp_global; row < d.n_rows; row += warps_total) {
     const int64_t e = row * p + lane;
-    const float loc = active ? __ldg(d.loc + e) : 0.f;
-    const float scale = active ? __ldg(d.scale + e) : 1.f;
-    const float x = (active && d.feat != nullptr) ? __ldg(d.feat + e) : 0.f;
-    const float y = d.resp != nullptr ? __ldg(d.resp + row) : 0.f;
-    if (active && !(scale > 0.0f)) bad |= MNF_ST_BAD_PARAM;
+    // inactive lanes (feature index >= p) are inert: z == prior_loc == x, scale 0, beta 0
+    const float loc = active ? __ldg(d.loc + e) : prior_loc;
+    const float scale_raw = active ? __ldg(d.scale + e) : 1.f;
+    const float scale = active ? scale_raw : 0.f;
+    const float x = (active && has_feat) ? __ldg(d.feat + e) : loc;
+    const float y = has_resp ? __ldg(d.resp + row) : 0.f;
+    if (!(scale_raw > 0.0f)) bad |= MNF_ST_BAD_PARAM;
     if (y != y || x != x) bad_value = true;
-    float gl = 0.f, gs = 0.f;
-    float zs[SP], v[SP];
+    float eps_r[SP], v[SP];
+    float E1 = 0.f, E2 = 0.f, W1 = 0.f, W2 = 0.f;
     n_rows_lane += 1.f;
+    const float dloc = loc - prior_loc;
     // ---- draws and the element-wise sites -------------------------------------------------
 #pragma unroll
     for (int q = 0; q < SP / 4; ++q) {
@@ -121,35 +173,48 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
       } else {
         Philox rng(seed, offset, ((uint64_t)e << 8) | (uint64_t)((s_begin >> 2) + q));
         const uint4 r = rng.next();
-        const float2 n0 = box_muller(r.x, r.y), n1 = box_muller(r.z, r.w);
+        const float2 n0 = box_muller_fast(r.x, r.y), n1 = box_muller_fast(r.z, r.w);
         eps4[0] = n0.x; eps4[1] = n0.y; eps4[2] = n1.x; eps4[3] = n1.y;
+        if (!FULL) {
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (4 * q + t >= s_count) eps4[t] = 0.f;
+        }
       }
+      const float4 b4 = beta4[q], i4 = ipv4[q];
+      const float bq[4] = {b4.x, b4.y, b4.z, b4.w}, iq[4] = {i4.x, i4.y, i4.z, i4.w};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int s = 4 * q + t;
-        const RowParticle& rp = sPar[s];
         const float eps = eps4[t];
-        const float zz = active ? fmaf(eps, scale, loc) : 0.f;
-        zs[s] = zz;
-        const float live = (active && s < s_count) ? 1.f : 0.f;
-        // prior: d/dz = -(z - m)/ps^2
-        const float dzp = zz - rp.prior_loc;
-        z2[s] = fmaf(live * dzp, dzp, z2[s]);
-        float dz = -dzp * rp.prior_inv_var;
-        // features: d/dz = (x - z)/ns^2
-        if (d.feat != nullptr) {
-          const float r = x - zz;
-          f2 = fmaf(live * r, r, f2);
-          dz = fmaf(r, rp.feat_inv_var, dz);
-        }
-        dz *= live;
-        gl += dz;
-        gs = fmaf(dz, eps, gs);
-        v[s] = zz * sBeta[s * 32 + lane];
+        eps_r[s] = eps;
+        const float dzp = fmaf(eps, scale, dloc);          // z - prior_loc
+        z2[s] = fmaf(dzp, dzp, z2[s]);
+        const float tw = iq[t] * eps;
+        W1 += tw;
+        W2 = fmaf(tw, eps, W2);
+        E1 += eps;
+        E2 = fmaf(eps, eps, E2);
+        v[s] = fmaf(eps, scale, loc) * bq[t];
       }
     }
+    // prior: d/dz = -(z - m)/sigma_s^2 ; features: d/dz = (x - z)/ns^2, summed over particles
+    //   sum_s (z_s - m)/sigma_s^2       = dloc * ipv_sum + scale * W1
+    //   sum_s (z_s - m) eps_s/sigma_s^2 = dloc * W1 + scale * W2
+    //   sum_s (x - z_s)                 = n dx - scale E1          dx = x - loc
+    //   sum_s (x - z_s) eps_s           = dx E1 - scale E2
+    //   sum_s (x - z_s)^2               = n dx^2 - 2 dx scale E1 + scale^2 E2
+    float gl = -fmaf(dloc, ipv_sum, scale * W1);
+    float gs = -fmaf(dloc, W1, scale * W2);
+    if (has_feat) {
+      const float dx = x - loc;
+      gl = fmaf(feat_inv_var, fmaf(n_live, dx, -scale * E1), gl);
+      gs = fmaf(feat_inv_var, fmaf(dx, E1, -scale * E2), gs);
+      const float se = scale * E1;
+      f2 += fmaf(scale * scale, E2, fmaf(n_live * dx, dx, -2.0f * dx * se));
+    }
     // ---- response: transpose-reduce the dot products so lane s owns particle s -----------------
-    if (d.resp != nullptr) {
+    if (has_resp) {
 #pragma unroll
       for (int w = SP / 2; w >= 1; w >>= 1) {
         // SP < 32 leaves the upper lanes as idle copies; the butterfly still lands particle s on lane s
@@ -164,59 +229,65 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
       // lanes beyond SP hold partial sums of other lane groups: fold them in
 #pragma unroll
       for (int w = SP; w < 32; w <<= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], w);
-      const int sl = lane & (SP - 1);
-      const RowParticle& rp = sPar[sl];
-      const float eta = rp.icpt + v[0];
+      const float eta = rp_l.icpt + v[0];
       float deta = 0.f, lp = 0.f, dsc = 0.f;
-      if (sl < s_count) {
+      if (lane_live) {
         if (d.resp_family == MNF_POISSON) {
           if (d.resp_transform == MNF_T_EXP) {
-            const float rate = expf(eta);
-            lp = fmaf(y, eta, -rate) - lgammaf(y + 1.0f);
+            const float rate = exp_fast(eta);
+            lp = fmaf(y, eta, -rate) - log_factorial(y);
             deta = y - rate;
           } else {
-            lp = xlogy(y, eta) - eta - lgammaf(y + 1.0f);
+            lp = xlogy(y, eta) - eta - log_factorial(y);
             deta = y == 0.f ? -1.f : y / eta - 1.0f;
           }
         } else if (d.resp_family == MNF_NORMAL) {
-          const float inv = 1.0f / rp.resp_scale;
+          const float inv = 1.0f / rp_l.resp_scale;
           const float r = (y - eta) * inv;
-          lp = -0.5f * r * r - logf(rp.resp_scale) - kLogSqrt2Pi;
+          lp = -0.5f * r * r - logf(rp_l.resp_scale) - kLogSqrt2Pi;
           deta = r * inv;
-          dsc = (r * r - 1.0f) * inv * rp.resp_dscale;
+          dsc = (r * r - 1.0f) * inv * rp_l.resp_dscale;
         } else {
           lp = y * eta - softplus_f(eta);
           deta = y - sigmoid_f(eta);
         }
       }
-      if (lane < SP) { lpy += lp; ga += deta; gresp_scale += dsc; }
+      if (lane < SP) { lpy += lp; ga += deta; gresp_scale += dsc; my_deta[lane] = deta; }
+      __syncwarp();
       // back to features: dz_ij += deta_s * beta_sj ; gbeta_sj += deta_s * z_ij
+      const float4* de4 = reinterpret_cast<const float4*>(my_deta);
 #pragma unroll
-      for (int s = 0; s < SP; ++s) {
-        const float de = __shfl_sync(0xffffffffu, deta, s);
-        const float dzr = de * sBeta[s * 32 + lane];
-        gl += dzr;
-        gs = fmaf(dzr, (zs[s] - loc) / scale, gs);
-        gb[s] = fmaf(de, zs[s], gb[s]);
+      for (int q = 0; q < SP / 4; ++q) {
+        const float4 d4 = de4[q], b4 = beta4[q];
+        const float dq[4] = {d4.x, d4.y, d4.z, d4.w}, bq[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int s = 4 * q + t;
+          const float dzr = dq[t] * bq[t];
+          gl += dzr;
+          gs = fmaf(dzr, eps_r[s], gs);
+          gb[s] = fmaf(dq[t], fmaf(eps_r[s], scale, loc), gb[s]);
+        }
       }
+      __syncwarp();   // the slot is rewritten by the next row
     }
     if (active) {
       // d loss = -(mean_s dLJ + dH); H = sum log scale + const, dH/dscale = 1/scale
       const float e_w = with_entropy ? 1.0f : 0.0f;
       const float out_l = -gl * invS;
-      const float out_s = -(gs * invS + (first_pass ? e_w / scale : 0.0f));
+      const float out_s = -(gs * invS + (first_pass ? __fdividef(e_w, scale) : 0.0f));
       if (first_pass) { d.grad_loc[e] = out_l; d.grad_scale[e] = out_s; }
       else { d.grad_loc[e] += out_l; d.grad_scale[e] += out_s; }
       // added to every particle's log-density column (only the mean over particles is used), so
       // every pass over a particle range accumulates it
-      if (with_entropy) ent += (double)(0.5f + kLogSqrt2Pi + logf(scale));
+      if (with_entropy) ent += (double)(0.5f + kLogSqrt2Pi + __logf(scale));
     }
   }
 
   // ---- CTA reduction -> one partial block per CTA -------------------------------------------
   // stage per-warp values [warp][s][40]: 0..31 gbeta per lane, 32 z2 (summed over lanes),
   // 34 (slot of s = 0) the feature residual sum, 35-37 per-particle response sums, 38 rows, 39 entropy
-  float* mine = sOut + (size_t)warp * SP * 40;
+  float* mine = &sm.out[warp][0][0];
 #pragma unroll
   for (int s = 0; s < SP; ++s) {
     mine[s * 40 + lane] = gb[s];
@@ -237,22 +308,22 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
   float* out = partial + (size_t)blockIdx.x * S * ncol;
   float rows_cta = 0.f, ent_cta = 0.f, f2_cta = 0.f;
   for (int w = 0; w < kRowWarps; ++w) {
-    rows_cta += sOut[(size_t)w * SP * 40 + 38];
-    ent_cta += sOut[(size_t)w * SP * 40 + 39];
-    f2_cta += sOut[(size_t)w * SP * 40 + 34];
+    rows_cta += sm.out[w][0][38];
+    ent_cta += sm.out[w][0][39];
+    f2_cta += sm.out[w][0][34];
   }
   for (int idx = threadIdx.x; idx < s_count * ncol; idx += kRowThreads) {
     const int s = idx / ncol, c = idx % ncol;
-    const RowParticle& rp = sPar[s];
-    auto total = [&](int col) { float a = 0.f; for (int w = 0; w < kRowWarps; ++w) a += sOut[((size_t)w * SP + s) * 40 + col]; return a; };
+    const RowParticle& rp = sm.par[s];
+    auto total = [&](int col) { float a = 0.f; for (int w = 0; w < kRowWarps; ++w) a += sm.out[w][s][col]; return a; };
     float val = 0.f;
     const float n_elem = rows_cta * (float)p;
     if (c == 0) {
       const float Z2 = total(32), LY = total(35);
       val = -0.5f * rp.prior_inv_var * Z2 - n_elem * (logf(rp.prior_scale) + kLogSqrt2Pi) + LY;
       // constant feature scale: every particle of this launch gets an equal share of the residual sum
-      if (d.feat != nullptr)
-        val += -0.5f * rp.feat_inv_var * (f2_cta / (float)s_count) - n_elem * (logf(rp.feat_scale) + kLogSqrt2Pi);
+      if (has_feat)
+        val += -0.5f * feat_inv_var * (f2_cta / (float)s_count) - n_elem * (logf(feat_scale) + kLogSqrt2Pi);
       val += ent_cta;      // entropy of q(Z), the same for every particle (only the mean over s is used)
     } else if (c <= p) {
       val = total(c - 1);
@@ -275,7 +346,7 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
 
 template <int SP>
 inline size_t rowlatent_smem_bytes() {
-  return sizeof(float) * SP * 32 + sizeof(RowParticle) * SP + sizeof(float) * kRowWarps * SP * 40;
+  return sizeof(RowSmem<SP>);
 }
 
 }  // namespace mnf

@@ -219,19 +219,25 @@ inline size_t site_sweep_smem_bytes() {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Specialised single-site sweeps for the two hot site kinds of the missing-observations config.
-// The generic kernel above spends ~40 instructions per (element, particle); here everything that
-// does not depend on the particle is summed once per element, and the per-particle work shrinks to
-// the irreducible running sums:
-//   Poisson(exp(A_s + B_s x)):   R_s = sum rate, Rx_s = sum rate*x          (5 instructions)
-//       log p = A_s V + B_s Vx - R_s - C,  d/dA = V - R_s,  d/dB = Vx - Rx_s
-//       with V = sum v, Vx = sum v*x, C = sum log v! over the live elements
-//   Normal(A_s + B_s x, sigma_s): T1 = sum r, Tx = sum r*x, T2 = sum r^2, r = v - A_s - B_s x (5)
+// Specialised single-site sweeps for the two hot site kinds of the missing-observations config
+// (counts ~ Poisson(exp(a + b x)), w ~ Normal(c + d x, sigma), both masked). The generic kernel
+// above spends ~40 instructions per (element, particle); here everything that does not depend on
+// the particle is summed once per element.
+//
+//   Poisson(exp(A_s + B_s x)):  log p = A_s V + B_s Vx - R_s - C,  d/dA = V - R_s,  d/dB = Vx - Rx_s
+//       with the data-only sums V = sum v, Vx = sum v x, C = sum log v! over the live elements and
+//       the irreducible per-particle sums R_s = sum rate, Rx_s = sum rate x  (one ex2 + four FMA-pipe
+//       instructions per (element, particle): the kernel is bound by the MUFU pipe).
+//   Normal(A_s + B_s x, sigma_s): the residual sums are polynomials in (A_s, B_s) of SIX data-only
+//       sufficient statistics n, Sx, Sxx, Sv, Svx, Svv:
+//           T1 = sum r   = Sv  - A n  - B Sx          r = v - A - B x
+//           Tx = sum r x = Svx - A Sx - B Sxx
+//           T2 = sum r^2 = Svv - A Sv - B Svx - A T1 - B Tx
 //       log p = -T2 / (2 sigma^2) - n log(sigma sqrt(2 pi)), d/dA = T1/sigma^2, d/dB = Tx/sigma^2,
-//       d/dsigma = (T2/sigma^2 - n)/sigma
-// Same mapping as the generic kernel (particles on lanes, elements broadcast from a per-warp
-// staging slot, masked elements skipped warp-uniformly) and the same partial layout as its
-// one-site instance: [S][5] = weight * (log p, du0, du0*x0, du1, du1*x1).
+//       d/dsigma = (T2/sigma^2 - n)/sigma.
+//       So the sweep does NO per-particle work: one HBM-bound pass (value 4 + covariate 4 + mask 1
+//       bytes per element) whatever S is. Products and sums are carried in fp64 (fp32 x fp32 is
+//       exact in fp64), so the cancellation in T2 costs log10(Svv / T2) of 16 digits.
 // ---------------------------------------------------------------------------------------------
 constexpr int kFastNone = -1, kFastPoissonExp = 0, kFastNormalId = 1;
 
@@ -242,44 +248,61 @@ inline int site_fast_kind(const mnf_site_t& st) {
   return kFastNone;
 }
 
-// exp(u) as ex2(u * log2(e)) with the product carried in two terms (relative error ~2 ulp)
-__device__ __forceinline__ float fast_exp(float u) {
-  const float t = fmaf(u, 1.925963033500011e-8f, u * 1.4426950216293335f);
+__device__ __forceinline__ float ex2_approx(float t) {
   float r;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t));
   return r;
 }
 
-template <int KIND, int Q>
-__global__ void __launch_bounds__(kSweepThreads, 3)
-site_fast_kernel(mnf_site_t st, const float* __restrict__ z, int S, int D, float* __restrict__ partial,
-                 uint32_t* __restrict__ status) {
-  constexpr int NA = KIND == kFastPoissonExp ? 2 : 3;
+// ---- Poisson(exp(A_s + B_s x)) -------------------------------------------------------------------
+// Particles on lanes (lane l owns particles l, l+32, ...). A warp walks chunks of 32 elements (one
+// per lane, coalesced), adds the data-only terms, and appends the covariates of the LIVE elements
+// to a 64-entry ring in shared memory (ballot + popc compaction). Whenever 32 are queued they are
+// consumed by a branch-free, fully unrolled loop (LDS.128 broadcasts, two FMAs + ex2 + add + FMA
+// per particle), so masked-out elements cost nothing in the hot loop and it has no control flow.
+// exp(u) = 2^(u log2 e): log2 e is folded into the per-particle constants in fp64 and split as
+// hi + lo, the lo part of A is applied once at the end as a factor on R_s and Rx_s.
+constexpr int pois_min_blocks(int q) { return q <= 2 ? 4 : 2; }   // 64 / 128 registers per thread
+
+template <int Q>
+__global__ void __launch_bounds__(kSweepThreads, pois_min_blocks(Q))
+poisson_exp_kernel(mnf_site_t st, const float* __restrict__ z, int S, int D, float* __restrict__ partial,
+                   uint32_t* __restrict__ status) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n = st.numel;
-  const mnf_link_t L0 = st.param[0], L1 = st.param[1];
+  const mnf_link_t L0 = st.param[0];
 
-  float A[Q], B[Q];
+  extern __shared__ double s_pois[];
+  double* s_sums = s_pois;                                          // [warp][Q*32][2]
+  double* s_elem = s_pois + (size_t)kSweepWarps * Q * 32 * 2;       // [warp][4]: V, Vx, C, n
+  float* s_ring = reinterpret_cast<float*>(s_elem + kSweepWarps * 4);   // [warp][64], 16-byte aligned
+  float* s_logfact = s_ring + kSweepWarps * 64;                     // [64] copy of the constant table
+  float* ring = s_ring + warp * 64;
+  if (threadIdx.x < 64) s_logfact[threadIdx.x] = kLogFactorial[threadIdx.x];
+  __syncthreads();
+
+  float A2[Q], Bh[Q], Bl[Q];
+  double corr[Q];
 #pragma unroll
   for (int q = 0; q < Q; ++q) {
     const int s = lane + 32 * q;
     const float* zs = z + (int64_t)(s < S ? s : 0) * D;
-    A[q] = L0.a_const + (L0.a_lat >= 0 ? zs[L0.a_lat] : 0.0f);
-    B[q] = L0.b_const + (L0.b_lat >= 0 ? zs[L0.b_lat] : 0.0f);
+    const float A = L0.a_const + (L0.a_lat >= 0 ? zs[L0.a_lat] : 0.0f);
+    const float B = L0.b_const + (L0.b_lat >= 0 ? zs[L0.b_lat] : 0.0f);
+    const double a2 = (double)A * 1.4426950408889634074, b2 = (double)B * 1.4426950408889634074;
+    A2[q] = (float)a2;
+    corr[q] = exp2(a2 - (double)A2[q]);
+    Bh[q] = (float)b2;
+    Bl[q] = (float)(b2 - (double)Bh[q]);
   }
-  extern __shared__ double s_fast[];
-  double* s_sums = s_fast;                                          // [warp][Q*32][NA]
-  double* s_elem = s_fast + (size_t)kSweepWarps * Q * 32 * NA;      // [warp][4]: V, Vx, C, n
-  float2* stage = reinterpret_cast<float2*>(s_elem + kSweepWarps * 4) + warp * 32;
 
-  double run[Q][NA];
+  double run[Q][2];
 #pragma unroll
-  for (int q = 0; q < Q; ++q)
-#pragma unroll
-    for (int a = 0; a < NA; ++a) run[q][a] = 0.0;
+  for (int q = 0; q < Q; ++q) { run[q][0] = 0.0; run[q][1] = 0.0; }
   double e_v = 0.0, e_vx = 0.0, e_c = 0.0;     // this lane's share of the per-element sums
   int e_n = 0;
   bool bad_value = false;
+  int head = 0, fill = 0;                      // ring state, warp-uniform
 
   const int64_t n_chunks = (n + 31) / 32;
   const int64_t warp_global = (int64_t)blockIdx.x * kSweepWarps + warp;
@@ -287,55 +310,72 @@ site_fast_kernel(mnf_site_t st, const float* __restrict__ z, int S, int D, float
   for (int64_t chunk = warp_global; chunk < n_chunks; chunk += warps_total) {
     const int64_t i = chunk * 32 + lane;
     const bool inb = i < n;
-    const bool live = inb && (st.mask == nullptr || st.mask[i] != 0);
-    const float v = live ? __ldg(st.value + i) : 0.0f;
+    const bool live = inb && (st.mask == nullptr || __ldg(st.mask + i) != 0);
+    const float v = inb ? __ldg(st.value + i) : 0.0f;
     const float x = (inb && L0.x != nullptr) ? __ldg(L0.x + (int64_t)L0.x_stride * i) : 1.0f;
     if (live) {
-      if (!in_support(st.family, v)) bad_value = true;
       ++e_n;
-      if (KIND == kFastPoissonExp) {
-        e_v += (double)v;
-        e_vx += (double)(v * x);
+      e_v += (double)v;
+      e_vx += (double)v * (double)x;
+      if (v >= 0.0f && v < 64.0f && v == floorf(v)) {
+        e_c += (double)s_logfact[(int)v];
+      } else {
+        if (!in_support(MNF_POISSON, v)) bad_value = true;
         e_c += (double)log_factorial(v);
       }
     }
-    const uint32_t live_bits = __ballot_sync(0xffffffffu, live);
-    stage[lane] = make_float2(v, x);
+    const uint32_t bits = __ballot_sync(0xffffffffu, live);
+    if (live) ring[(head + fill + __popc(bits & ((1u << lane) - 1u))) & 63] = x;
+    fill += __popc(bits);
     __syncwarp();
-    float part[NA][Q];
+    if (fill >= 32) {
+      float r0[Q], r1[Q];
 #pragma unroll
-    for (int a = 0; a < NA; ++a)
+      for (int q = 0; q < Q; ++q) { r0[q] = 0.0f; r1[q] = 0.0f; }
+      const float4* b4 = reinterpret_cast<const float4*>(ring + head);
 #pragma unroll
-      for (int q = 0; q < Q; ++q) part[a][q] = 0.0f;
-#pragma unroll 4
-    for (int e = 0; e < 32; ++e) {
-      if (!((live_bits >> e) & 1u)) continue;   // warp-uniform
-      const float2 el = stage[e];
+      for (int j = 0; j < 8; ++j) {
+        const float4 xs = b4[j];
+        const float xe[4] = {xs.x, xs.y, xs.z, xs.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            const float rate = ex2_approx(fmaf(Bh[q], xe[t], fmaf(Bl[q], xe[t], A2[q])));
+            r0[q] += rate;
+            r1[q] = fmaf(rate, xe[t], r1[q]);
+          }
+      }
+#pragma unroll
+      for (int q = 0; q < Q; ++q) { run[q][0] += (double)r0[q]; run[q][1] += (double)r1[q]; }
+      head ^= 32;
+      fill -= 32;
+      __syncwarp();   // consumed slots are rewritten by the next append
+    }
+  }
+  // what is left in the ring (< 32 covariates)
+  {
+    float r0[Q], r1[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) { r0[q] = 0.0f; r1[q] = 0.0f; }
+    for (int e = 0; e < fill; ++e) {
+      const float xe = ring[(head + e) & 63];
 #pragma unroll
       for (int q = 0; q < Q; ++q) {
-        if (KIND == kFastPoissonExp) {
-          const float rate = fast_exp(fmaf(B[q], el.y, A[q]));
-          part[0][q] += rate;
-          part[1][q] = fmaf(rate, el.y, part[1][q]);
-        } else {
-          const float r = fmaf(-B[q], el.y, el.x - A[q]);
-          part[0][q] += r;
-          part[1][q] = fmaf(r, el.y, part[1][q]);
-          part[2][q] = fmaf(r, r, part[2][q]);
-        }
+        const float rate = ex2_approx(fmaf(Bh[q], xe, fmaf(Bl[q], xe, A2[q])));
+        r0[q] += rate;
+        r1[q] = fmaf(rate, xe, r1[q]);
       }
     }
 #pragma unroll
-    for (int q = 0; q < Q; ++q)
-#pragma unroll
-      for (int a = 0; a < NA; ++a) run[q][a] += (double)part[a][q];
-    __syncwarp();   // the staging slot is rewritten by the next chunk
+    for (int q = 0; q < Q; ++q) { run[q][0] += (double)r0[q]; run[q][1] += (double)r1[q]; }
   }
 
 #pragma unroll
-  for (int q = 0; q < Q; ++q)
-#pragma unroll
-    for (int a = 0; a < NA; ++a) s_sums[((size_t)warp * Q * 32 + q * 32 + lane) * NA + a] = run[q][a];
+  for (int q = 0; q < Q; ++q) {
+    s_sums[((size_t)warp * Q * 32 + q * 32 + lane) * 2 + 0] = run[q][0] * corr[q];
+    s_sums[((size_t)warp * Q * 32 + q * 32 + lane) * 2 + 1] = run[q][1] * corr[q];
+  }
   e_v = warp_sum(e_v);
   e_vx = warp_sum(e_vx);
   e_c = warp_sum(e_c);
@@ -348,54 +388,143 @@ site_fast_kernel(mnf_site_t st, const float* __restrict__ z, int S, int D, float
   }
   __syncthreads();
 
-  // one particle per thread: combine the warps in fixed order and finish the closed forms
-  bool bad_param = false;
+  // one particle per thread: combine the warps in fixed order and finish the closed form
   for (int s = threadIdx.x; s < S; s += kSweepThreads) {
-    double t[NA], el[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int a = 0; a < NA; ++a) t[a] = 0.0;
+    double t[2] = {0.0, 0.0}, el[4] = {0.0, 0.0, 0.0, 0.0};
     for (int w = 0; w < kSweepWarps; ++w) {
-#pragma unroll
-      for (int a = 0; a < NA; ++a) t[a] += s_sums[((size_t)w * Q * 32 + s) * NA + a];
+      t[0] += s_sums[((size_t)w * Q * 32 + s) * 2 + 0];
+      t[1] += s_sums[((size_t)w * Q * 32 + s) * 2 + 1];
 #pragma unroll
       for (int a = 0; a < 4; ++a) el[a] += s_elem[w * 4 + a];
     }
     const float* zs = z + (int64_t)s * D;
     const double a_s = (double)(L0.a_const + (L0.a_lat >= 0 ? zs[L0.a_lat] : 0.0f));
     const double b_s = (double)(L0.b_const + (L0.b_lat >= 0 ? zs[L0.b_lat] : 0.0f));
-    double lp, d0, d0x, d1 = 0.0;
-    if (KIND == kFastPoissonExp) {
-      lp = a_s * el[0] + b_s * el[1] - t[0] - el[2];
-      d0 = el[0] - t[0];
-      d0x = el[1] - t[1];
-    } else {
-      const float u = (L1.a_const + (L1.a_lat >= 0 ? zs[L1.a_lat] : 0.0f)) +
-                      (L1.b_const + (L1.b_lat >= 0 ? zs[L1.b_lat] : 0.0f));    // x == NULL means x == 1
-      const float sigma_f = L1.transform == MNF_T_EXP ? expf(u) : u;
-      if (!(sigma_f > 0.0f)) bad_param = true;
-      const double sigma = (double)sigma_f, inv = 1.0 / sigma, iv = inv * inv;
-      lp = -0.5 * iv * t[2] - el[3] * ((double)logf(sigma_f) + (double)kLogSqrt2Pi);
-      d0 = iv * t[0];
-      d0x = iv * t[1];
-      d1 = (iv * t[2] - el[3]) * inv * (L1.transform == MNF_T_EXP ? sigma : 1.0);
-    }
     float* out = partial + ((size_t)blockIdx.x * S + s) * 5;
     const double w = st.scale;
-    out[0] = (float)(w * lp);
-    out[1] = (float)(w * d0);
-    out[2] = (float)(w * d0x);
-    out[3] = (float)(w * d1);
-    out[4] = (float)(w * d1);
+    out[0] = (float)(w * (a_s * el[0] + b_s * el[1] - t[0] - el[2]));
+    out[1] = (float)(w * (el[0] - t[0]));
+    out[2] = (float)(w * (el[1] - t[1]));
+    out[3] = 0.0f;
+    out[4] = 0.0f;
   }
   if (bad_value) atomicOr(status, MNF_ST_BAD_VALUE);
-  if (bad_param) atomicOr(status, MNF_ST_BAD_PARAM);
 }
 
-template <int KIND, int Q>
-inline size_t site_fast_smem_bytes() {
-  constexpr int NA = KIND == kFastPoissonExp ? 2 : 3;
-  return sizeof(double) * kSweepWarps * Q * 32 * NA + sizeof(double) * kSweepWarps * 4 +
-         sizeof(float2) * kSweepWarps * 32;
+template <int Q>
+inline size_t poisson_exp_smem_bytes() {
+  return sizeof(double) * kSweepWarps * Q * 32 * 2 + sizeof(double) * kSweepWarps * 4 +
+         sizeof(float) * kSweepWarps * 64 + sizeof(float) * 64;
+}
+
+// ---- Normal(A_s + B_s x, sigma_s): data-only sufficient statistics -------------------------------
+constexpr int kStatThreads = 256;
+constexpr int kStatCols = 6;   // n, Sx, Sxx, Sv, Svx, Svv
+
+struct NormalStats {
+  double sx = 0.0, sxx = 0.0, sv = 0.0, svx = 0.0, svv = 0.0;
+  unsigned int n = 0;
+  bool bad = false;
+  __device__ __forceinline__ void add(float v, float x, bool live) {
+    if (live) {
+      const double dv = (double)v, dx = (double)x;
+      ++n;
+      sx += dx;
+      sxx = fma(dx, dx, sxx);
+      sv += dv;
+      svx = fma(dv, dx, svx);
+      svv = fma(dv, dv, svv);
+      bad |= v != v;
+    }
+  }
+};
+
+// VEC: value (and x, mask) are 16-byte (4-byte for the mask) aligned with unit stride: 128-bit loads
+template <bool VEC>
+__global__ void __launch_bounds__(kStatThreads)
+normal_stats_kernel(mnf_site_t st, double* __restrict__ cta_stats, uint32_t* __restrict__ status) {
+  const int64_t n = st.numel;
+  const float* __restrict__ value = st.value;
+  const float* __restrict__ xp = st.param[0].x;
+  const int64_t xs = st.param[0].x_stride;
+  const uint8_t* __restrict__ mask = st.mask;
+  const int64_t tid = (int64_t)blockIdx.x * kStatThreads + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * kStatThreads;
+  NormalStats acc;
+  if (VEC) {
+    const int64_t n4 = n >> 2;
+    for (int64_t g = tid; g < n4; g += nth) {
+      const float4 v4 = __ldg(reinterpret_cast<const float4*>(value) + g);
+      const float4 x4 = xp != nullptr ? __ldg(reinterpret_cast<const float4*>(xp) + g) : make_float4(1.f, 1.f, 1.f, 1.f);
+      const uint32_t m4 = mask != nullptr ? __ldg(reinterpret_cast<const uint32_t*>(mask) + g) : 0x01010101u;
+      acc.add(v4.x, x4.x, (m4 & 0x000000ffu) != 0);
+      acc.add(v4.y, x4.y, (m4 & 0x0000ff00u) != 0);
+      acc.add(v4.z, x4.z, (m4 & 0x00ff0000u) != 0);
+      acc.add(v4.w, x4.w, (m4 & 0xff000000u) != 0);
+    }
+    const int64_t i = (n4 << 2) + tid;     // ragged tail: at most three elements
+    if (i < n) acc.add(__ldg(value + i), xp != nullptr ? __ldg(xp + i) : 1.0f, mask == nullptr || __ldg(mask + i) != 0);
+  } else {
+    for (int64_t i = tid; i < n; i += nth)
+      acc.add(__ldg(value + i), xp != nullptr ? __ldg(xp + xs * i) : 1.0f, mask == nullptr || __ldg(mask + i) != 0);
+  }
+  __shared__ double s_red[kStatThreads / 32][kStatCols];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double c[kStatCols] = {(double)acc.n, acc.sx, acc.sxx, acc.sv, acc.svx, acc.svv};
+#pragma unroll
+  for (int k = 0; k < kStatCols; ++k) c[k] = warp_sum(c[k]);
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < kStatCols; ++k) s_red[warp][k] = c[k];
+  __syncthreads();
+  if (threadIdx.x < kStatCols) {
+    double t = 0.0;
+    for (int w = 0; w < kStatThreads / 32; ++w) t += s_red[w][threadIdx.x];
+    cta_stats[(size_t)blockIdx.x * kStatCols + threadIdx.x] = t;
+  }
+  if (acc.bad) atomicOr(status, MNF_ST_BAD_VALUE);
+}
+
+// One block of kStatCols warps: warp k sums statistic k over the CTAs in fixed order; then one
+// thread per particle evaluates the closed forms and adds them to the step accumulator.
+__global__ void __launch_bounds__(32 * kStatCols)
+normal_stats_finish_kernel(mnf_site_t st, const double* __restrict__ cta_stats, int n_cta,
+                           const float* __restrict__ z, int S, int D, double* __restrict__ acc,
+                           uint32_t* __restrict__ status) {
+  __shared__ double s_tot[kStatCols];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double t = 0.0;
+  for (int b = lane; b < n_cta; b += 32) t += cta_stats[(size_t)b * kStatCols + warp];
+  t = warp_sum(t);
+  if (lane == 0) s_tot[warp] = t;
+  __syncthreads();
+  const double cnt = s_tot[0], Sx = s_tot[1], Sxx = s_tot[2], Sv = s_tot[3], Svx = s_tot[4], Svv = s_tot[5];
+  const mnf_link_t L0 = st.param[0], L1 = st.param[1];
+  bool bad_param = false;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const float* zs = z + (int64_t)s * D;
+    const double A = (double)(L0.a_const + (L0.a_lat >= 0 ? zs[L0.a_lat] : 0.0f));
+    const double B = (double)(L0.b_const + (L0.b_lat >= 0 ? zs[L0.b_lat] : 0.0f));
+    const float u = (L1.a_const + (L1.a_lat >= 0 ? zs[L1.a_lat] : 0.0f)) +
+                    (L1.b_const + (L1.b_lat >= 0 ? zs[L1.b_lat] : 0.0f));    // x == NULL means x == 1
+    const float sigma_f = L1.transform == MNF_T_EXP ? expf(u) : u;
+    if (!(sigma_f > 0.0f)) bad_param = true;
+    const double T1 = Sv - A * cnt - B * Sx;
+    const double Tx = Svx - A * Sx - B * Sxx;
+    const double T2 = Svv - A * Sv - B * Svx - A * T1 - B * Tx;
+    const double sigma = (double)sigma_f, inv = 1.0 / sigma, iv = inv * inv;
+    const double w = st.scale;
+    const double lp = -0.5 * iv * T2 - cnt * (log(sigma) + 0.91893853320467274178);
+    const double d1 = (iv * T2 - cnt) * inv * (L1.transform == MNF_T_EXP ? sigma : 1.0);
+    double* as = acc + (int64_t)s * (D + 1);
+    // several links may name the same latent column, hence atomics (launches are stream-ordered)
+    atomicAdd(as, w * lp);
+    if (L0.a_lat >= 0) atomicAdd(as + 1 + L0.a_lat, w * iv * T1);
+    if (L0.b_lat >= 0) atomicAdd(as + 1 + L0.b_lat, w * iv * Tx);
+    if (L1.a_lat >= 0) atomicAdd(as + 1 + L1.a_lat, w * d1);
+    if (L1.b_lat >= 0) atomicAdd(as + 1 + L1.b_lat, w * d1);
+  }
+  if (bad_param) atomicOr(status, MNF_ST_BAD_PARAM);
 }
 
 }  // namespace mnf

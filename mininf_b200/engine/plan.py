@@ -134,6 +134,7 @@ class Plan:
         # optional instrumentation: CUDA event pairs around every dense sweep (bench.py roofline)
         self.record_sweep_events = False
         self.sweep_events: List[Tuple[torch.cuda.Event, torch.cuda.Event]] = []
+        self.sweep_event_kinds: List[str] = []
 
         # one descriptor per row latent, filled in by the sites that touch it
         self.row_groups: Dict[str, abi.RowLatent] = {}
@@ -548,28 +549,35 @@ class Plan:
         lib.call("mnf_rsample", self.latent_table.data_ptr(), len(self.latents), S, D, noise_ptr,
                  seed, offset, counter, self.z.data_ptr(), self.noise.data_ptr(), self.acc.data_ptr(),
                  status, stream)
+        def timed(kind: str, call: Callable[[], None]) -> None:
+            """CUDA events around one sweep call on its stream (bench.py's roofline numerator)."""
+            if not self.record_sweep_events:
+                call()
+                return
+            begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            begin.record(torch.cuda.current_stream(self.device))
+            call()
+            end.record(torch.cuda.current_stream(self.device))
+            self.sweep_events.append((begin, end))
+            self.sweep_event_kinds.append(kind)
+
         for site, mode in self.dense_sites:
-            if self.record_sweep_events:
-                begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                begin.record(torch.cuda.current_stream(self.device))
-            lib.call("mnf_dense_sweep", C.byref(site), mode, self.z.data_ptr(), S, D,
-                     self.acc.data_ptr(), self.workspace.data_ptr(), self.workspace_bytes, status,
-                     stream)
-            if self.record_sweep_events:
-                end.record(torch.cuda.current_stream(self.device))
-                self.sweep_events.append((begin, end))
+            timed("dense", lambda: lib.call(
+                "mnf_dense_sweep", C.byref(site), mode, self.z.data_ptr(), S, D, self.acc.data_ptr(),
+                self.workspace.data_ptr(), self.workspace_bytes, status, stream))
         for group in self.sweep_groups:
-            lib.call("mnf_site_sweep", group, len(group), self.z.data_ptr(), S, D,
-                     self.acc.data_ptr(), self.workspace.data_ptr(), self.workspace_bytes, status,
-                     stream)
+            timed("site", lambda: lib.call(
+                "mnf_site_sweep", group, len(group), self.z.data_ptr(), S, D, self.acc.data_ptr(),
+                self.workspace.data_ptr(), self.workspace_bytes, status, stream))
         if self.small_observed is not None:
             table, count, longest = self.small_observed
             lib.call("mnf_small_sites", table.data_ptr(), count, longest, self.z.data_ptr(), S, D,
                      self.acc.data_ptr(), status, stream)
         for name, desc in self.row_groups.items():
-            lib.call("mnf_rowlatent_sweep", C.byref(desc), self.z.data_ptr(), S, D, seed, offset, counter,
-                     int(with_entropy), self.acc.data_ptr(), self.workspace.data_ptr(),
-                     self.workspace_bytes, status, stream)
+            timed("rowlatent", lambda: lib.call(
+                "mnf_rowlatent_sweep", C.byref(desc), self.z.data_ptr(), S, D, seed, offset, counter,
+                int(with_entropy), self.acc.data_ptr(), self.workspace.data_ptr(), self.workspace_bytes,
+                status, stream))
         if reduce_fn is not None:
             reduce_fn(self.acc)   # observed sites are row shards: sum the partial accumulators
         if self.small_global is not None:

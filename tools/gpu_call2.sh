@@ -1,0 +1,9 @@
+#!/bin/bash
+# parity tests + C5 timing and launch list (only this library's kernels)
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+timeout 300 python tools/c5_check.py 1e8 > gpurun_out/c5.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:mnf -c 60 --csv --log-file gpurun_out/c5_launches.csv python tools/c5_check.py 1e8 > gpurun_out/c5_ncu.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:mnf -c 40 --csv --log-file gpurun_out/c4_launches.csv python tools/c4_check.py 1e7 > gpurun_out/c4_ncu.log 2>&1
+exit 0
