@@ -1,12 +1,16 @@
 """Benchmark of the ELBO + gradient hot path (BASELINE.json metric) on synthetic data.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|c4|c5]
 
 Default workload c2 (config[1] of BASELINE.json): Bayesian linear regression, mean-field Normal
 approximation, p = 64 features, N = 1e8 observations PER GPU (weak scaling), S = 64 particles.
 `--workload c3` (config[2]): minibatch logistic regression, p = 256, batches of 1e7 rows per GPU
 of a declared N = 1e9 stream, S = 16; every step conditions the model on the next batch (two
 resident batches alternate; the plan is rebound, not retraced).
+`--workload c4` (config[3]): regression with feature uncertainty, N = 1e7 rows per GPU with a
+per-observation latent feature vector (p = 32), S = 32 (the row-latent kernel; instruction-bound).
+`--workload c5` (config[4]): masked Poisson + Normal sites over N = 1e8 elements per GPU, 30 %
+missing, S = 64 (the site sweeps; the Poisson site is bound by the MUFU pipe).
 A step is one full SVI step through the public API: zero_grad, EvidenceLowerBoundLoss forward
 (fused ELBO + gradient kernels), backward through the parameter transforms, Adam. The metric is
 particle-observation log-density evaluations per second: rows * S / time, whole job.
@@ -37,10 +41,15 @@ N_CHUNKS = 256     # synthetic rows are generated in 256 chunks, chunk c seeded 
 
 
 class Workload:
-    def __init__(self, key, name, p, particles, rows, family, declared_rows, n_batches, kernel, traffic_file):
+    def __init__(self, key, name, p, particles, rows, family, declared_rows, n_batches, kernel, traffic_file,
+                 event_kind="dense", cpu_sample=(2_000_000, 2), bytes_per_row=None, bound_note=None):
         self.key, self.name, self.p, self.particles, self.rows = key, name, p, particles, rows
         self.family, self.declared_rows, self.n_batches = family, declared_rows, n_batches
         self.kernel, self.traffic_file = kernel, traffic_file
+        self.event_kind, self.cpu_rows, self.cpu_particles = event_kind, cpu_sample[0], cpu_sample[1]
+        # algorithmic bytes one sweep call moves per row
+        self.bytes_per_row = bytes_per_row if bytes_per_row is not None else 4 * p + 4
+        self.bound_note = bound_note
 
 
 WORKLOADS = {
@@ -49,7 +58,17 @@ WORKLOADS = {
     "c3": Workload("c3", "minibatch_logistic_regression_p256_batch1e7_of_N1e9_S16", 256, 16, 10_000_000,
                    "bernoulli", 1_000_000_000, 2,
                    "mnf::tcr::dense_tcr_kernel<BernoulliLogits, 16> (+ its partial-sum reduction)",
-                   "dense_tcr_traffic.json"),
+                   "dense_tcr_traffic.json", cpu_sample=(500_000, 2)),
+    "c4": Workload("c4", "feature_uncertainty_rowlatent_p32_N1e7_S32", 32, 32, 10_000_000, "rowlatent", None, 1,
+                   "mnf::rowlatent_kernel<32> (+ its partial-sum reduction)", "rowlatent_traffic.json",
+                   event_kind="rowlatent", cpu_sample=(200_000, 2), bytes_per_row=32 * 20 + 4,
+                   bound_note="instruction-issue bound (N*p*S = 1.0e10 Philox normal draws per step), not HBM; "
+                              "see profiles/ for the pipe utilisation"),
+    "c5": Workload("c5", "missing_observations_poisson_normal_N1e8_S64_30pct_masked", 1, 64, 100_000_000, "missing",
+                   None, 1, "mnf::poisson_exp_kernel<2> + mnf::normal_stats_kernel (one mnf_site_sweep call)",
+                   "site_sweep_traffic.json", event_kind="site", cpu_sample=(2_000_000, 2), bytes_per_row=14,
+                   bound_note="the Poisson site is bound by the MUFU pipe (one ex2 per live element and particle), "
+                              "the Normal site by HBM (sufficient statistics, 9 B per element)"),
 }
 
 
@@ -84,8 +103,30 @@ def chunk_bounds(n, chunk):
 
 
 def make_data(w, n, device, seed0):
+    """One resident data set (dict of device tensors) in the chunk-seeded recipe."""
     g = torch.Generator(device=device)
     g.manual_seed(SEED0 - 1)
+    if w.family == "missing":
+        x = torch.empty(n, device=device)
+        counts = torch.empty(n, device=device)
+        wv = torch.empty(n, device=device)
+        m_counts = torch.empty(n, device=device, dtype=torch.bool)
+        m_w = torch.empty(n, device=device, dtype=torch.bool)
+        for chunk in range(N_CHUNKS):
+            lo, hi = chunk_bounds(n, chunk)
+            if hi <= lo:
+                continue
+            g.manual_seed(seed0 + chunk)
+            k = hi - lo
+            torch.randn(k, generator=g, device=device, out=x[lo:hi])
+            counts[lo:hi] = torch.poisson(torch.exp(0.3 + 0.5 * x[lo:hi]), generator=g)
+            wv[lo:hi] = -0.2 + 0.8 * x[lo:hi] + 0.7 * torch.randn(k, generator=g, device=device)
+            m_counts[lo:hi] = torch.rand(k, generator=g, device=device) > 0.3
+            m_w[lo:hi] = torch.rand(k, generator=g, device=device) > 0.3
+        # finite fill in the holes, as in examples/missing-observations.md
+        counts.mul_(m_counts)
+        wv.mul_(m_w)
+        return {"x": x, "counts": counts, "w": wv, "m_counts": m_counts, "m_w": m_w}
     theta_true = torch.randn(w.p, generator=g, device=device) / w.p ** 0.5
     X = torch.empty(n, w.p, device=device)
     y = torch.empty(n, device=device)
@@ -98,13 +139,16 @@ def make_data(w, n, device, seed0):
         if w.family == "normal":
             torch.randn(hi - lo, generator=g, device=device, out=y[lo:hi])
             y[lo:hi].addmv_(X[lo:hi], theta_true)
-        else:
+        elif w.family == "bernoulli":
             y[lo:hi] = torch.bernoulli(torch.sigmoid(X[lo:hi] @ theta_true), generator=g)
-    return X, y
+        else:   # rowlatent: X holds the noisy features x = z + 0.5 eps, y ~ Poisson(exp(0.5 + z . slope))
+            y[lo:hi] = torch.poisson(torch.exp(0.5 + X[lo:hi] @ theta_true), generator=g)
+            X[lo:hi].add_(torch.randn(hi - lo, w.p, generator=g, device=device), alpha=0.5)
+    return {"X": X, "y": y}
 
 
-def model_factory(m, w, n_rows):
-    from torch.distributions import Bernoulli, Normal
+def model_factory(m, w, n_rows, data):
+    from torch.distributions import Bernoulli, Gamma, Normal, Poisson
     declared = w.declared_rows or n_rows
 
     def regression():
@@ -120,7 +164,59 @@ def model_factory(m, w, n_rows):
                 X = m.sample("X", Normal(0, 1), (declared, w.p))
             m.sample("y", Bernoulli(logits=X @ theta))
 
-    return regression if w.family == "normal" else minibatch_logistic
+    def feature_uncertainty():         # examples/regression-with-feature-uncertainty.md:28-38, p features
+        population_scale = m.sample("population_scale", Gamma(2, 2))
+        z = m.sample("z", Normal(0, population_scale), (n_rows, w.p))
+        m.sample("X", Normal(z, 0.5))
+        intercept = m.sample("intercept", Normal(0, 1))
+        slope = m.sample("slope", Normal(0, 1), w.p)
+        m.sample("y", Poisson((intercept + z @ slope).exp()))
+
+    def missing_observations():        # examples/missing-observations.md:131 (masked conditioning)
+        x = data["x"]
+        a = m.sample("a", Normal(0, 1))
+        b = m.sample("b", Normal(0, 1))
+        c = m.sample("c", Normal(0, 1))
+        d = m.sample("d", Normal(0, 1))
+        sigma = m.sample("sigma", Gamma(2, 2))
+        m.sample("counts", Poisson((a + b * x).exp()))
+        m.sample("w", Normal(c + d * x, sigma))
+
+    return {"normal": regression, "bernoulli": minibatch_logistic, "rowlatent": feature_uncertainty,
+            "missing": missing_observations}[w.family]
+
+
+def condition_on(m, model, w, data):
+    """`mininf.condition` of the workload's model on one resident data set."""
+    if w.family == "missing":
+        return m.condition(model, counts=torch.masked.as_masked_tensor(data["counts"], data["m_counts"]),
+                           w=torch.masked.as_masked_tensor(data["w"], data["m_w"]))
+    return m.condition(model, X=data["X"], y=data["y"])
+
+
+def make_approximation(m, w, n_rows, data, device):
+    """name -> ParameterizedDistribution (validate_args=False is passed through to
+    torch.distributions exactly as in the reference: its constructor check is a host round trip
+    per step; the kernels check scales on the device)."""
+    from torch.distributions import Gamma, Normal
+    PD = m.nn.ParameterizedDistribution
+
+    def scalar(value):
+        return torch.tensor(value, device=device)
+
+    if w.family in ("normal", "bernoulli"):
+        return {"theta": PD(Normal, loc=torch.zeros(w.p, device=device), scale=0.1 * torch.ones(w.p, device=device),
+                            validate_args=False)}
+    if w.family == "rowlatent":
+        return {"population_scale": PD(Gamma, concentration=scalar(2.0), rate=scalar(2.0), validate_args=False),
+                "z": PD(Normal, loc=data["X"].clone(), scale=torch.ones(n_rows, w.p, device=device),
+                        validate_args=False),
+                "intercept": PD(Normal, loc=scalar(0.1), scale=scalar(0.2), validate_args=False),
+                "slope": PD(Normal, loc=torch.zeros(w.p, device=device), scale=0.2 * torch.ones(w.p, device=device),
+                            validate_args=False)}
+    approximation = {k: PD(Normal, loc=scalar(0.1), scale=scalar(0.2), validate_args=False) for k in "abcd"}
+    approximation["sigma"] = PD(Gamma, concentration=scalar(2.0), rate=scalar(2.0), validate_args=False)
+    return approximation
 
 
 # ---------------------------------------------------------------------------------------------
@@ -186,8 +282,14 @@ def cpu_sample(w, rows, particles, steps, warmup):
     sample: `rows` observations, `particles` sequential evaluations per step."""
     from oracle import configs, elbo
     torch.manual_seed(0)
-    config = configs.regression(rows, w.p, seed0=SEED0) if w.family == "normal" else \
-        configs.logistic(w.declared_rows, rows, p=w.p, seed0=SEED0)
+    if w.family == "normal":
+        config = configs.regression(rows, w.p, seed0=SEED0)
+    elif w.family == "bernoulli":
+        config = configs.logistic(w.declared_rows, rows, p=w.p, seed0=SEED0)
+    elif w.family == "rowlatent":
+        config = configs.feature_uncertainty(rows, w.p, seed0=SEED0)
+    else:
+        config = configs.missing(rows, seed0=SEED0)
     approx, leaves = config.approximation()
     optimizer = torch.optim.Adam(list(leaves.values()), lr=0.01)
 
@@ -211,7 +313,7 @@ def run_reference(args):
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
-    rows, particles = (2_000_000, 2) if w.key == "c2" else (500_000, 2)
+    rows, particles = w.cpu_rows, w.cpu_particles
     value, seconds = cpu_sample(w, rows, particles, args.steps, args.warmup)
     cores = torch.get_num_threads()
     sample = (f"{rows} rows x {particles} particles per step of the {w.name} workload "
@@ -249,29 +351,29 @@ def run_b200(args):
     w = WORKLOADS[args.workload]
     P, S = w.p, w.particles
     n_rows = int(args.rows) or w.rows
-    # one resident data set (c2) or the resident batches of the stream (c3), 256 seeds apart
+    # one resident data set or the resident batches of the stream (c3), 256 seeds apart
     batches = [make_data(w, n_rows, device, SEED0 + (rank * w.n_batches + b) * 256) for b in range(w.n_batches)]
-    X, y = batches[0]
-    # validate_args=False is passed through to torch.distributions.Normal (as in the reference):
-    # its constructor check is a host round trip per step; the kernels check scales on the device
-    approximation = mininf.nn.ParameterizedDistribution(
-        Normal, loc=torch.zeros(P, device=device), scale=0.1 * torch.ones(P, device=device), validate_args=False)
+    modules = make_approximation(mininf, w, n_rows, batches[0], device)
+    parameters = [p for module in modules.values() for p in module.parameters()]
     streaming = w.n_batches > 1
-    optimizer = torch.optim.Adam(approximation.parameters(), lr=0.01, capturable=not (args.eager or streaming))
+    optimizer = torch.optim.Adam(parameters, lr=0.01, capturable=not (args.eager or streaming))
     loss_module = mininf.nn.EvidenceLowerBoundLoss(S, dense_precision="tf32",
                                                    process_group=True if distributed else None)
-    model = model_factory(mininf, w, n_rows)
-    conditioned = mininf.condition(model, X=X, y=y)
+    model = model_factory(mininf, w, n_rows, batches[0])
+    conditioned = condition_on(mininf, model, w, batches[0])
     calls = [0]
+
+    def approximation():
+        return {name: module() for name, module in modules.items()}
 
     def eager_step():
         optimizer.zero_grad(set_to_none=True)
         if streaming:       # condition on the next batch, as the reference's data-loader loop does
-            Xb, yb = batches[calls[0] % w.n_batches]
+            batch = batches[calls[0] % w.n_batches]
             calls[0] += 1
-            loss = loss_module(mininf.condition(model, X=Xb, y=yb), {"theta": approximation()})
+            loss = loss_module(condition_on(mininf, model, w, batch), approximation())
         else:
-            loss = loss_module(conditioned, {"theta": approximation()})
+            loss = loss_module(conditioned, approximation())
         loss.backward()
         optimizer.step()
         return loss
@@ -292,6 +394,7 @@ def run_b200(args):
     # the launch on its stream, averaged over eager steps on the same resident data (events inside
     # a graph replay cannot be timed; the kernel and its arguments are identical).
     plan.sweep_events.clear()
+    plan.sweep_event_kinds.clear()
     plan.record_sweep_events = True
     eager_begin, eager_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     eager_begin.record()
@@ -300,7 +403,9 @@ def run_b200(args):
     eager_end.record()
     fence()
     plan.record_sweep_events = False
-    kernel_ms = sum(b.elapsed_time(e) for b, e in plan.sweep_events) / max(len(plan.sweep_events), 1)
+    timed = [b.elapsed_time(e) for (b, e), kind in zip(plan.sweep_events, plan.sweep_event_kinds)
+             if kind == w.event_kind]
+    kernel_ms = sum(timed) / max(len(timed), 1)
     eager_ms_per_step = eager_begin.elapsed_time(eager_end) / args.steps
 
     # The SVI step is recorded once into a CUDA graph (mininf_b200.nn.GraphedStep) and replayed:
@@ -310,7 +415,7 @@ def run_b200(args):
     step, graph_note = eager_step, None
     if graphed:
         try:
-            step = mininf.nn.GraphedStep(loss_module, conditioned, lambda: {"theta": approximation()}, optimizer)
+            step = mininf.nn.GraphedStep(loss_module, conditioned, approximation, optimizer)
         except Exception as error:  # noqa: BLE001  keep measuring: the eager loop runs the same kernels
             graphed, graph_note = False, f"CUDA graph capture failed ({type(error).__name__}); eager launches"
             torch.cuda.synchronize()
@@ -345,7 +450,7 @@ def run_b200(args):
 
     if rank == 0:
         peak, peak_source = measured_peak_gbs()
-        algorithmic_bytes = n_rows * (4 * P + 4)
+        algorithmic_bytes = n_rows * w.bytes_per_row
         achieved = algorithmic_bytes / (kernel_ms * 1e-3) / 1e9
         traffic = None
         traffic_file = ROOT / "profiles" / w.traffic_file
@@ -357,7 +462,7 @@ def run_b200(args):
                 traffic = None
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            rows_cpu, parts_cpu = (2_000_000, 2) if w.key == "c2" else (500_000, 2)
+            rows_cpu, parts_cpu = w.cpu_rows, w.cpu_particles
             cpu_value, _ = cpu_sample(w, rows_cpu, parts_cpu, steps=3, warmup=1)
             cpu_baseline = {"value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                             "sample": f"{rows_cpu} rows x {parts_cpu} particles per step, 3 timed steps, of the "
@@ -366,10 +471,12 @@ def run_b200(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "tf32 operands / f32 accumulate", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32 operands / f32 accumulate" if w.event_kind == "dense" else "f32 (f64 sums)",
+            "data": "synthetic",
             "config": {"workload": w.name, "rows_per_gpu": n_rows,
                        "features": P, "particles": S, "parallelism": f"row shards x{world}, one all-reduce/step",
-                       "l2": f"inputs ({n_rows * (4 * P + 4) / 1e9:.1f} GB per step and GPU) far exceed the "
+                       "l2": f"inputs ({n_rows * w.bytes_per_row / 1e9:.1f} GB per step and GPU) far exceed the "
                              "126 MB L2; no flush needed",
                        "stream": (f"{w.n_batches} resident batches alternate; the cached plan is rebound to "
                                   "each batch (no retrace)") if streaming else "one resident data set",
@@ -385,7 +492,8 @@ def run_b200(args):
                          "kernel": w.kernel,
                          "kernel_ms": kernel_ms, "algorithmic_bytes": algorithmic_bytes,
                          "kernel_timing": f"CUDA events around each launch, {args.steps} eager steps run "
-                                          "right before the timed region on the same data"},
+                                          "right before the timed region on the same data",
+                         **({"note": w.bound_note} if w.bound_note else {})},
             "eager_ms_per_step": eager_ms_per_step,
             "cpu_baseline": cpu_baseline,
             "steps_per_sec": 1e3 / ms_per_step,
@@ -399,21 +507,22 @@ def run_e2e(args, w, step, batches, n_rows, world, device, fence, distributed):
     """Same step, but the inputs live in pinned host memory and are copied to the device inside
     the timed region every step; the loss is read back to the host every step."""
     import psutil
-    P, S = w.p, w.particles
-    X, y = batches[0]
-    need = X.numel() * 4 + y.numel() * 4
+    S = w.particles
+    names = sorted(batches[0])
+    row_bytes = sum(batches[0][k][0].numel() * batches[0][k].element_size() for k in names)
+    need = n_rows * row_bytes
     available = psutil.virtual_memory().available
     rows = n_rows
     if need * world > 0.6 * available:
-        rows = int(0.6 * available / world / (4 * P + 4))
+        rows = int(0.6 * available / world / row_bytes)
     try:
-        X_host = torch.empty(rows, P, pin_memory=True)
-        y_host = torch.empty(rows, pin_memory=True)
+        host = {k: torch.empty((rows,) + tuple(batches[0][k].shape[1:]), dtype=batches[0][k].dtype, pin_memory=True)
+                for k in names}
     except RuntimeError:
         return {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                 "note": "could not pin host memory for the inputs"}
-    X_host.copy_(X[:rows])
-    y_host.copy_(y[:rows])
+    for k in names:
+        host[k].copy_(batches[0][k][:rows])
     steps = max(2, min(args.steps, 5))
     fence()
     begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -422,11 +531,11 @@ def run_e2e(args, w, step, batches, n_rows, world, device, fence, distributed):
         # every input byte of the step crosses PCIe into the buffers the step reads; if the
         # pinned buffer is smaller than the data set it is sent repeatedly until all n_rows rows
         # have been overwritten
-        Xd, yd = batches[i % len(batches)]
+        target = batches[i % len(batches)]
         for lo in range(0, n_rows, rows):
             m = min(rows, n_rows - lo)
-            Xd[lo:lo + m].copy_(X_host[:m], non_blocking=True)
-            yd[lo:lo + m].copy_(y_host[:m], non_blocking=True)
+            for k in names:
+                target[k][lo:lo + m].copy_(host[k][:m], non_blocking=True)
         loss = step()
         loss_host = loss.item()        # device -> host read of the step's result
     end.record()
@@ -439,7 +548,7 @@ def run_e2e(args, w, step, batches, n_rows, world, device, fence, distributed):
         ms = float(t)
     del loss_host
     return {"value": n_rows * world * S / (ms * 1e-3), "unit": UNIT,
-            "h2d_bytes_per_step": n_rows * (4 * P + 4), "d2h_bytes_per_step": 4, "ms_per_step": ms, "steps": steps,
+            "h2d_bytes_per_step": n_rows * row_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms, "steps": steps,
             "note": ("inputs copied from pinned host memory every step; PCIe-bound"
                      + ("" if rows == n_rows else f"; pinned staging buffer of {rows} rows sent repeatedly"))}
 

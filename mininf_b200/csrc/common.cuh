@@ -155,7 +155,7 @@ __device__ __forceinline__ float2 box_muller(uint32_t a, uint32_t b) {
 // log(y!) = lgamma(y + 1) of a Poisson count: integers below 64 from a constant-memory table,
 // y >= 8 from the Stirling series (truncation < 3e-8 absolute), anything else (invalid data,
 // flagged separately) from lgammaf. As accurate as lgammaf at a fraction of its instruction count.
-__constant__ float kLogFactorial[64] = {
+static __constant__ float kLogFactorial[64] = {
     0.0f, 0.0f, 0.693147181f, 1.79175947f,
     3.17805383f, 4.78749174f, 6.57925121f, 8.52516136f,
     10.6046029f, 12.8018275f, 15.1044126f, 17.5023078f,

@@ -146,14 +146,31 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
 
   const int64_t warp_global = (int64_t)blockIdx.x * kRowWarps + warp;
   const int64_t warps_total = (int64_t)gridDim.x * kRowWarps;
+  // the next row's operands are fetched while the current row is being worked on
+  float n_loc = prior_loc, n_scale = 1.f, n_x = 0.f, n_y = 0.f;
+  if (warp_global < d.n_rows) {
+    const int64_t e0 = warp_global * p + lane;
+    if (active) { n_loc = __ldg(d.loc + e0); n_scale = __ldg(d.scale + e0); }
+    if (active && has_feat) n_x = __ldg(d.feat + e0);
+    if (has_resp) n_y = __ldg(d.resp + warp_global);
+  }
   for (int64_t row = warp_global; row < d.n_rows; row += warps_total) {
     const int64_t e = row * p + lane;
     // inactive lanes (feature index >= p) are inert: z == prior_loc == x, scale 0, beta 0
-    const float loc = active ? __ldg(d.loc + e) : prior_loc;
-    const float scale_raw = active ? __ldg(d.scale + e) : 1.f;
+    const float loc = active ? n_loc : prior_loc;
+    const float scale_raw = active ? n_scale : 1.f;
     const float scale = active ? scale_raw : 0.f;
-    const float x = (active && has_feat) ? __ldg(d.feat + e) : loc;
-    const float y = has_resp ? __ldg(d.resp + row) : 0.f;
+    const float x = (active && has_feat) ? n_x : loc;
+    const float y = n_y;
+    {
+      const int64_t row_n = row + warps_total;
+      if (row_n < d.n_rows) {
+        const int64_t en = row_n * p + lane;
+        if (active) { n_loc = __ldg(d.loc + en); n_scale = __ldg(d.scale + en); }
+        if (active && has_feat) n_x = __ldg(d.feat + en);
+        if (has_resp) n_y = __ldg(d.resp + row_n);
+      }
+    }
     if (!(scale_raw > 0.0f)) bad |= MNF_ST_BAD_PARAM;
     if (y != y || x != x) bad_value = true;
     float eps_r[SP], v[SP];

@@ -1,0 +1,188 @@
+// Element-wise site sweeps (csrc/site_sweep.cuh) and the mnf_site_sweep entry point of
+// include/mininf_b200.h.
+#include "host.h"
+#include "site_sweep.cuh"
+
+using namespace mnf;
+
+namespace {
+
+template <int NSITES>
+int launch_site_sweep(const mnf_site_t* sites, const float* z, int S, int D, float* partial,
+                      uint32_t* status, int grid, cudaStream_t stream) {
+  SweepArgs<NSITES> args;
+  for (int i = 0; i < NSITES; ++i) args.site[i] = sites[i];
+  if (S <= 32) {
+    auto kernel = site_sweep_kernel<NSITES, 1>;
+    const size_t smem = site_sweep_smem_bytes<NSITES, 1>();
+    MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, kSweepThreads, smem, stream>>>(args, z, S, D, partial, status);
+  } else if (S <= 64) {
+    auto kernel = site_sweep_kernel<NSITES, 2>;
+    const size_t smem = site_sweep_smem_bytes<NSITES, 2>();
+    MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, kSweepThreads, smem, stream>>>(args, z, S, D, partial, status);
+  } else {
+    auto kernel = site_sweep_kernel<NSITES, 4>;
+    const size_t smem = site_sweep_smem_bytes<NSITES, 4>();
+    MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kernel<<<grid, kSweepThreads, smem, stream>>>(args, z, S, D, partial, status);
+  }
+  MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+
+template <int Q>
+int launch_poisson_exp_q(const mnf_site_t& site, const float* z, int S, int D, float* partial,
+                         uint32_t* status, int grid, cudaStream_t stream) {
+  auto kernel = poisson_exp_kernel<Q>;
+  const size_t smem = poisson_exp_smem_bytes<Q>();
+  MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kernel<<<grid, kSweepThreads, smem, stream>>>(site, z, S, D, partial, status);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+int launch_poisson_exp(const mnf_site_t& site, const float* z, int S, int D, float* partial,
+                       uint32_t* status, int grid, cudaStream_t stream) {
+  if (S <= 32) return launch_poisson_exp_q<1>(site, z, S, D, partial, status, grid, stream);
+  if (S <= 64) return launch_poisson_exp_q<2>(site, z, S, D, partial, status, grid, stream);
+  return launch_poisson_exp_q<4>(site, z, S, D, partial, status, grid, stream);
+}
+
+// Normal site with an identity location link and an element-independent scale: one data-only pass
+// for six sufficient statistics, then the per-particle closed forms straight into acc.
+int launch_normal_stats(const mnf_site_t& site, const float* z, int S, int D, double* acc, void* workspace,
+                        size_t workspace_bytes, uint32_t* status, int sm_count, cudaStream_t stream) {
+  const mnf_link_t& L0 = site.param[0];
+  const bool vec = reinterpret_cast<uintptr_t>(site.value) % 16 == 0 &&
+                   (L0.x == nullptr || (L0.x_stride == 1 && reinterpret_cast<uintptr_t>(L0.x) % 16 == 0)) &&
+                   (site.mask == nullptr || reinterpret_cast<uintptr_t>(site.mask) % 4 == 0);
+  const int64_t per_thread = vec ? 4 : 1;
+  const int64_t want = (site.numel + kStatThreads * per_thread - 1) / (kStatThreads * per_thread);
+  const int64_t fits = (int64_t)(workspace_bytes / (kStatCols * sizeof(double)));   // one row of statistics per CTA
+  if (fits < 1) return fail(MNF_E_INVALID, "mnf_site_sweep: workspace too small%s%s");
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, fits), 8 * (int64_t)sm_count));
+  double* cta_stats = static_cast<double*>(workspace);
+  if (vec) normal_stats_kernel<true><<<grid, kStatThreads, 0, stream>>>(site, cta_stats, status);
+  else normal_stats_kernel<false><<<grid, kStatThreads, 0, stream>>>(site, cta_stats, status);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  normal_stats_finish_kernel<<<1, 32 * kStatCols, 0, stream>>>(site, cta_stats, grid, z, S, D, acc, status);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+// scalar-latent columns of one site's four gradient sums (du0, du0*x0, du1, du1*x1)
+void site_columns(const mnf_site_t& site, int32_t* cols) {
+  const bool two = site.family <= MNF_BETA;
+  cols[0] = site.param[0].a_lat;
+  cols[1] = site.param[0].b_lat;
+  cols[2] = two ? site.param[1].a_lat : -1;
+  cols[3] = two ? site.param[1].b_lat : -1;
+}
+
+bool family_has_two_params(int family) { return family <= MNF_BETA; }
+
+}  // namespace
+
+extern "C" {
+
+int mnf_site_sweep(const mnf_site_t* sites, int n_sites, const float* z, int n_particles,
+                   int n_latent_total, double* acc, void* workspace, size_t workspace_bytes,
+                   uint32_t* status, void* stream_) {
+  if (!sites || !z || !acc || !workspace || !status)
+    return fail(MNF_E_INVALID, "mnf_site_sweep: null pointer%s%s");
+  if (n_sites < 1 || n_sites > MNF_MAX_FUSED_SITES)
+    return fail(MNF_E_INVALID, "mnf_site_sweep: 1..MNF_MAX_FUSED_SITES sites per call%s%s");
+  const int S = n_particles, D = n_latent_total;
+  if (S <= 0 || S > 128) return fail(MNF_E_UNSUPPORTED, "mnf_site_sweep: 1..128 particles%s%s");
+  for (int i = 0; i < n_sites; ++i) {
+    const mnf_site_t& st = sites[i];
+    if (st.numel != sites[0].numel || st.value == nullptr || st.value_lat >= 0)
+      return fail(MNF_E_INVALID, "mnf_site_sweep: fused sites need observed values of equal length%s%s");
+    if (st.family < 0 || st.family >= MNF_NUM_FAMILIES)
+      return fail(MNF_E_INVALID, "mnf_site_sweep: unknown family%s%s");
+    for (int p = 0; p < 2; ++p) {
+      const mnf_link_t& L = st.param[p];
+      if ((L.a_lat >= 0 && L.a_stride != 0) || (L.b_lat >= 0 && L.b_stride != 0))
+        return fail(MNF_E_UNSUPPORTED, "mnf_site_sweep: links must reference scalar latents%s%s");
+      if (L.a_lat >= D || L.b_lat >= D)
+        return fail(MNF_E_INVALID, "mnf_site_sweep: latent column out of range%s%s");
+    }
+  }
+  if (sites[0].numel == 0) return MNF_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DeviceCache* c;
+  if (int rc = device_cache(-1, &c)) return rc;
+  const int64_t n_chunks = (sites[0].numel + 31) / 32;
+  const int grid = (int)std::min<int64_t>((n_chunks + kSweepWarps - 1) / kSweepWarps, 2 * c->sm_count);
+  float* partial = static_cast<float*>(workspace);
+
+  // Sites with a specialised kernel (site_sweep.cuh: Poisson with an exp link, Normal with an
+  // identity location link and a per-particle scale) run on their own; the rest stay fused.
+  mnf_site_t generic[MNF_MAX_FUSED_SITES];
+  int n_generic = 0;
+  for (int i = 0; i < n_sites; ++i) {
+    const int kind = site_fast_kind(sites[i]);
+    if (kind == kFastNone) {
+      generic[n_generic++] = sites[i];
+      continue;
+    }
+    if (kind == kFastNormalId) {
+      if (int rc = launch_normal_stats(sites[i], z, S, D, acc, workspace, workspace_bytes, status, c->sm_count, stream))
+        return rc;
+      continue;
+    }
+    const int pgrid = (int)std::min<int64_t>((n_chunks + kSweepWarps - 1) / kSweepWarps,
+                                             (int64_t)pois_min_blocks(S <= 32 ? 1 : (S <= 64 ? 2 : 4)) * c->sm_count);
+    if ((size_t)pgrid * S * 5 * sizeof(float) > workspace_bytes)
+      return fail(MNF_E_INVALID, "mnf_site_sweep: workspace too small%s%s");
+    if (int rc = launch_poisson_exp(sites[i], z, S, D, partial, status, pgrid, stream)) return rc;
+    ColMap fast_map;
+    fast_map.n_vec = 0;
+    fast_map.vec_lat = 0;
+    fast_map.n_scalar = 4;
+    for (int k = 0; k < 16; ++k) fast_map.scalar_lat[k] = -1;
+    site_columns(sites[i], fast_map.scalar_lat);
+    if (int rr = launch_reduce(partial, pgrid, S, 5, fast_map, 1.0, D, acc, stream)) return rr;
+  }
+  if (n_generic == 0) return MNF_OK;
+  sites = generic;
+  n_sites = n_generic;
+  const int n_templ = n_sites == 1 ? 1 : (n_sites == 2 ? 2 : 4);
+  const int ncol = 1 + 4 * n_templ;
+  if ((size_t)grid * S * ncol * sizeof(float) > workspace_bytes)
+    return fail(MNF_E_INVALID, "mnf_site_sweep: workspace too small%s%s");
+
+  // pad the site list to the template width with inert duplicates of zero weight
+  mnf_site_t padded[MNF_MAX_FUSED_SITES];
+  for (int i = 0; i < n_templ; ++i) {
+    padded[i] = sites[i < n_sites ? i : 0];
+    if (i >= n_sites) {
+      padded[i].scale = 0.0;
+      for (int p = 0; p < 2; ++p) { padded[i].param[p].a_lat = -1; padded[i].param[p].b_lat = -1; }
+    }
+  }
+  int rc;
+  if (n_templ == 1) rc = launch_site_sweep<1>(padded, z, S, D, partial, status, grid, stream);
+  else if (n_templ == 2) rc = launch_site_sweep<2>(padded, z, S, D, partial, status, grid, stream);
+  else rc = launch_site_sweep<4>(padded, z, S, D, partial, status, grid, stream);
+  if (rc) return rc;
+
+  ColMap map;
+  map.n_vec = 0;
+  map.vec_lat = 0;
+  map.n_scalar = 4 * n_templ;
+  for (int i = 0; i < 16; ++i) map.scalar_lat[i] = -1;
+  for (int i = 0; i < n_sites; ++i) {
+    const bool two = family_has_two_params(sites[i].family);
+    map.scalar_lat[4 * i + 0] = sites[i].param[0].a_lat;
+    map.scalar_lat[4 * i + 1] = sites[i].param[0].b_lat;
+    map.scalar_lat[4 * i + 2] = two ? sites[i].param[1].a_lat : -1;
+    map.scalar_lat[4 * i + 3] = two ? sites[i].param[1].b_lat : -1;
+  }
+  return launch_reduce(partial, grid, S, ncol, map, 1.0, D, acc, stream);
+}
+
+}  // extern "C"

@@ -299,39 +299,56 @@ poisson_exp_kernel(mnf_site_t st, const float* __restrict__ z, int S, int D, flo
   double run[Q][2];
 #pragma unroll
   for (int q = 0; q < Q; ++q) { run[q][0] = 0.0; run[q][1] = 0.0; }
+  float r0[Q], r1[Q];                          // fp32 running sums, flushed to `run` every kFlush groups
+#pragma unroll
+  for (int q = 0; q < Q; ++q) { r0[q] = 0.0f; r1[q] = 0.0f; }
   double e_v = 0.0, e_vx = 0.0, e_c = 0.0;     // this lane's share of the per-element sums
+  float f_v = 0.0f, f_vx = 0.0f, f_c = 0.0f;   // fp32 staging of the same, flushed every kFlush chunks
   int e_n = 0;
   bool bad_value = false;
   int head = 0, fill = 0;                      // ring state, warp-uniform
+  int groups = 0, chunks = 0;
+  constexpr int kFlush = 8;                    // 256 rates / 8 elements per fp32 sum: error ~1e-7 * sqrt(256)
 
   const int64_t n_chunks = (n + 31) / 32;
   const int64_t warp_global = (int64_t)blockIdx.x * kSweepWarps + warp;
   const int64_t warps_total = (int64_t)gridDim.x * kSweepWarps;
-  for (int64_t chunk = warp_global; chunk < n_chunks; chunk += warps_total) {
+  // software pipeline: the next chunk's loads are in flight while the ring is consumed
+  float n_v = 0.0f, n_x = 1.0f;
+  bool n_live = false;
+  auto fetch = [&](int64_t chunk) {
     const int64_t i = chunk * 32 + lane;
     const bool inb = i < n;
-    const bool live = inb && (st.mask == nullptr || __ldg(st.mask + i) != 0);
-    const float v = inb ? __ldg(st.value + i) : 0.0f;
-    const float x = (inb && L0.x != nullptr) ? __ldg(L0.x + (int64_t)L0.x_stride * i) : 1.0f;
+    n_live = inb && (st.mask == nullptr || __ldg(st.mask + i) != 0);
+    n_v = inb ? __ldg(st.value + i) : 0.0f;
+    n_x = (inb && L0.x != nullptr) ? __ldg(L0.x + (int64_t)L0.x_stride * i) : 1.0f;
+  };
+  if (warp_global < n_chunks) fetch(warp_global);
+  for (int64_t chunk = warp_global; chunk < n_chunks; chunk += warps_total) {
+    const float v = n_v, x = n_x;
+    const bool live = n_live;
+    if (chunk + warps_total < n_chunks) fetch(chunk + warps_total);
     if (live) {
       ++e_n;
-      e_v += (double)v;
-      e_vx += (double)v * (double)x;
+      f_v += v;
+      f_vx = fmaf(v, x, f_vx);
       if (v >= 0.0f && v < 64.0f && v == floorf(v)) {
-        e_c += (double)s_logfact[(int)v];
+        f_c += s_logfact[(int)v];
       } else {
         if (!in_support(MNF_POISSON, v)) bad_value = true;
-        e_c += (double)log_factorial(v);
+        f_c += log_factorial(v);
       }
+    }
+    if (++chunks == kFlush) {
+      e_v += (double)f_v; e_vx += (double)f_vx; e_c += (double)f_c;
+      f_v = 0.0f; f_vx = 0.0f; f_c = 0.0f;
+      chunks = 0;
     }
     const uint32_t bits = __ballot_sync(0xffffffffu, live);
     if (live) ring[(head + fill + __popc(bits & ((1u << lane) - 1u))) & 63] = x;
     fill += __popc(bits);
     __syncwarp();
     if (fill >= 32) {
-      float r0[Q], r1[Q];
-#pragma unroll
-      for (int q = 0; q < Q; ++q) { r0[q] = 0.0f; r1[q] = 0.0f; }
       const float4* b4 = reinterpret_cast<const float4*>(ring + head);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -346,30 +363,32 @@ poisson_exp_kernel(mnf_site_t st, const float* __restrict__ z, int S, int D, flo
             r1[q] = fmaf(rate, xe[t], r1[q]);
           }
       }
+      if (++groups == kFlush) {
 #pragma unroll
-      for (int q = 0; q < Q; ++q) { run[q][0] += (double)r0[q]; run[q][1] += (double)r1[q]; }
+        for (int q = 0; q < Q; ++q) {
+          run[q][0] += (double)r0[q]; run[q][1] += (double)r1[q];
+          r0[q] = 0.0f; r1[q] = 0.0f;
+        }
+        groups = 0;
+      }
       head ^= 32;
       fill -= 32;
       __syncwarp();   // consumed slots are rewritten by the next append
     }
   }
+  e_v += (double)f_v; e_vx += (double)f_vx; e_c += (double)f_c;
   // what is left in the ring (< 32 covariates)
-  {
-    float r0[Q], r1[Q];
+  for (int e = 0; e < fill; ++e) {
+    const float xe = ring[(head + e) & 63];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) { r0[q] = 0.0f; r1[q] = 0.0f; }
-    for (int e = 0; e < fill; ++e) {
-      const float xe = ring[(head + e) & 63];
-#pragma unroll
-      for (int q = 0; q < Q; ++q) {
-        const float rate = ex2_approx(fmaf(Bh[q], xe, fmaf(Bl[q], xe, A2[q])));
-        r0[q] += rate;
-        r1[q] = fmaf(rate, xe, r1[q]);
-      }
+    for (int q = 0; q < Q; ++q) {
+      const float rate = ex2_approx(fmaf(Bh[q], xe, fmaf(Bl[q], xe, A2[q])));
+      r0[q] += rate;
+      r1[q] = fmaf(rate, xe, r1[q]);
     }
-#pragma unroll
-    for (int q = 0; q < Q; ++q) { run[q][0] += (double)r0[q]; run[q][1] += (double)r1[q]; }
   }
+#pragma unroll
+  for (int q = 0; q < Q; ++q) { run[q][0] += (double)r0[q]; run[q][1] += (double)r1[q]; }
 
 #pragma unroll
   for (int q = 0; q < Q; ++q) {

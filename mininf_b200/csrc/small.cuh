@@ -4,7 +4,7 @@
 // pathwise gradients. None of these touches the big observed arrays.
 #pragma once
 
-#include "common.cuh"
+#include "host.h"
 #include "implicit_grad.cuh"
 
 namespace mnf {
@@ -183,19 +183,15 @@ small_sites_kernel(const mnf_site_t* __restrict__ sites, const float* __restrict
 // Fixed-order reduction of per-CTA sweep partials [n_cta][S][ncol] (fp32) into acc (fp64).
 // Column c of a partial goes to acc column colmap(c): 0 -> log-density, 1+k -> latent column.
 // -------------------------------------------------------------------------------------------
-struct ColMap {
-  // partial column 0 is the log-density; then `n_vec` consecutive latent columns starting at
-  // vec_lat (theta of a dense site), then up to 16 individually mapped scalar latent columns.
-  int32_t n_vec;
-  int32_t vec_lat;
-  int32_t n_scalar;
-  int32_t scalar_lat[16];
-};
+constexpr int kReduceThreads = 256;
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_cta, int S, int ncol,
-                                       ColMap map, double weight, int D,
-                                       double* __restrict__ acc) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per (particle, column) output: lane l sums CTAs l, l+32, ... in order, then a fixed
+// butterfly combines the lanes - the same order on every run, and no serial walk over the CTAs.
+__global__ void __launch_bounds__(kReduceThreads)
+reduce_partials_kernel(const float* __restrict__ partial, int n_cta, int S, int ncol,
+                       ColMap map, double weight, int D, double* __restrict__ acc) {
+  const int idx = blockIdx.x * (kReduceThreads / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (idx >= S * ncol) return;
   const int s = idx / ncol, c = idx % ncol;
   int target;
@@ -207,94 +203,112 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int n_
     target = 1 + map.scalar_lat[k];
   }
   double t = 0.0;
-  for (int b = 0; b < n_cta; ++b) t += (double)partial[((int64_t)b * S + s) * ncol + c];
+  for (int b = lane; b < n_cta; b += 32) t += (double)partial[((int64_t)b * S + s) * ncol + c];
+  t = warp_sum(t);
   // several partial columns may map to one latent column (e.g. the same scalar latent used by
   // two fused sites), hence the atomic; launches are stream-ordered.
-  atomicAdd(acc + (int64_t)s * (D + 1) + target, weight * t);
+  if (lane == 0) atomicAdd(acc + (int64_t)s * (D + 1) + target, weight * t);
 }
 
 // -------------------------------------------------------------------------------------------
 // finalize: loss = -(mean_s acc[s][0] + H[q]) (mininf/nn.py:226-228) and gradients w.r.t. the
 // constrained parameters via the pathwise derivative of each family's rsample.
 // -------------------------------------------------------------------------------------------
-constexpr int kFinalThreads = 256;
+constexpr int kFinalThreads = 512;
 
+// One warp per latent column: the lanes walk the particles (the implicit Gamma / Beta gradients
+// are ~100 fp64 operations per particle), a fixed butterfly combines them, lane 0 adds the
+// entropy terms. Sums run in the same order on every launch.
 __global__ void __launch_bounds__(kFinalThreads)
 finalize_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
                 const float* __restrict__ z, const float* __restrict__ noise,
                 const double* __restrict__ acc, int with_entropy, float* __restrict__ out,
                 uint64_t* __restrict__ step_counter, uint32_t* __restrict__ status) {
-  __shared__ double red[kFinalThreads];
+  constexpr int kWarps = kFinalThreads / 32;
+  __shared__ double red[kWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // last kernel of a step: the next replay of a captured step draws with the next call index
   if (step_counter != nullptr && threadIdx.x == 0) *step_counter += 1;
   const double invS = 1.0 / (double)S;
-  double ent = 0.0;
+  double ent = 0.0;        // lane 0 of each warp: entropy of its columns
   bool nonfinite = false;
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+  for (int d = warp; d < D; d += kWarps) {
     const mnf_latent_t L = lat[find_latent(lat, n_lat, d)];
     const int e = d - L.offset;
     const double p0 = (double)L.p0[e], p1 = (double)L.p1[e];
-    double g0 = 0.0, g1 = 0.0, h = 0.0, dh0 = 0.0, dh1 = 0.0;
+    double g0 = 0.0, g1 = 0.0;
     if (L.family == MNF_NORMAL) {
-      // z = loc + eps*scale; H = 0.5 + 0.5 log(2 pi) + log(scale)   TORCH normal.py:114-115
-      for (int s = 0; s < S; ++s) {
+      // z = loc + eps*scale
+      for (int s = lane; s < S; s += 32) {
         const double g = acc[(int64_t)s * (D + 1) + 1 + d];
         g0 += g;
         g1 += g * (double)noise[(int64_t)s * D + d];
       }
-      h = 0.5 + 0.91893853320467274178 + log(p1);
-      dh1 = 1.0 / p1;
     } else if (L.family == MNF_GAMMA) {
       // z = g/rate: dz/dalpha = standard_gamma_grad(alpha, g)/rate, dz/drate = -g/rate^2
-      // H = alpha - log(rate) + lgamma(alpha) + (1-alpha) digamma(alpha)   TORCH gamma.py:100-106
-      for (int s = 0; s < S; ++s) {
+      // (the clamp_ at tiny is outside autograd: gradients as if unclamped)
+      for (int s = lane; s < S; s += 32) {
         const double g = acc[(int64_t)s * (D + 1) + 1 + d];
         const double gam = (double)noise[(int64_t)s * D + d];
-        const bool clamped = gam / p1 < (double)kFloatTiny;  // clamp_ is outside autograd: grads as if unclamped
-        (void)clamped;
         g0 += g * standard_gamma_grad(p0, gam) / p1;
         g1 += g * (-gam / (p1 * p1));
       }
-      h = p0 - log(p1) + lgamma(p0) + (1.0 - p0) * digamma_d(p0);
-      dh0 = 1.0 + (1.0 - p0) * trigamma_d(p0);
-      dh1 = -1.0 / p1;
     } else {
       // Beta(c1 = p0, c0 = p1) as a 2-simplex Dirichlet; _Dirichlet backward dirichlet.py:16-35:
       // grad_k = dirichlet_grad(x_k, c_k, total) * (go_k - sum_j x_j go_j) with go = (g, 0).
       const double tot = p0 + p1;
-      for (int s = 0; s < S; ++s) {
+      for (int s = lane; s < S; s += 32) {
         const double g = acc[(int64_t)s * (D + 1) + 1 + d];
         const double x = (double)noise[(int64_t)s * D + d];
         g0 += dirichlet_grad(x, p0, tot) * g * (1.0 - x);
         g1 += dirichlet_grad(1.0 - x, p1, tot) * (-x * g);
       }
-      // Dirichlet entropy with k = 2                                TORCH dirichlet.py:122-130
-      const double dt = digamma_d(tot);
-      h = lgamma(p0) + lgamma(p1) - lgamma(tot) - (p0 - 1.0) * digamma_d(p0) -
-          (p1 - 1.0) * digamma_d(p1) + (tot - 2.0) * dt;
-      const double tt = trigamma_d(tot);
-      dh0 = -(p0 - 1.0) * trigamma_d(p0) + (tot - 2.0) * tt;
-      dh1 = -(p1 - 1.0) * trigamma_d(p1) + (tot - 2.0) * tt;
     }
-    if (!with_entropy) { h = 0.0; dh0 = 0.0; dh1 = 0.0; }
-    ent += h;
-    const double o0 = -(g0 * invS + dh0);
-    const double o1 = -(g1 * invS + dh1);
-    if (!isfinite(o0) || !isfinite(o1)) nonfinite = true;
-    out[1 + d] = (float)o0;
-    out[1 + D + d] = (float)o1;
+    g0 = warp_sum(g0);
+    g1 = warp_sum(g1);
+    if (lane == 0) {
+      double h = 0.0, dh0 = 0.0, dh1 = 0.0;
+      if (L.family == MNF_NORMAL) {
+        // H = 0.5 + 0.5 log(2 pi) + log(scale)                      TORCH normal.py:114-115
+        h = 0.5 + 0.91893853320467274178 + log(p1);
+        dh1 = 1.0 / p1;
+      } else if (L.family == MNF_GAMMA) {
+        // H = alpha - log(rate) + lgamma(alpha) + (1-alpha) digamma(alpha)   TORCH gamma.py:100-106
+        h = p0 - log(p1) + lgamma(p0) + (1.0 - p0) * digamma_d(p0);
+        dh0 = 1.0 + (1.0 - p0) * trigamma_d(p0);
+        dh1 = -1.0 / p1;
+      } else {
+        // Dirichlet entropy with k = 2                                TORCH dirichlet.py:122-130
+        const double tot = p0 + p1;
+        const double dt = digamma_d(tot);
+        h = lgamma(p0) + lgamma(p1) - lgamma(tot) - (p0 - 1.0) * digamma_d(p0) -
+            (p1 - 1.0) * digamma_d(p1) + (tot - 2.0) * dt;
+        const double tt = trigamma_d(tot);
+        dh0 = -(p0 - 1.0) * trigamma_d(p0) + (tot - 2.0) * tt;
+        dh1 = -(p1 - 1.0) * trigamma_d(p1) + (tot - 2.0) * tt;
+      }
+      if (!with_entropy) { h = 0.0; dh0 = 0.0; dh1 = 0.0; }
+      ent += h;
+      const double o0 = -(g0 * invS + dh0);
+      const double o1 = -(g1 * invS + dh1);
+      if (!isfinite(o0) || !isfinite(o1)) nonfinite = true;
+      out[1 + d] = (float)o0;
+      out[1 + D + d] = (float)o1;
+    }
   }
-  // total log joint over particles
-  double lj = 0.0;
-  for (int s = threadIdx.x; s < S; s += blockDim.x) lj += acc[(int64_t)s * (D + 1)];
-  red[threadIdx.x] = ent + lj * invS;
+  // total log joint over particles: warp 0's lanes, added to its entropy share
+  if (warp == 0) {
+    double lj = 0.0;
+    for (int s = lane; s < S; s += 32) lj += acc[(int64_t)s * (D + 1)];
+    lj = warp_sum(lj);
+    ent += lj * invS;
+  }
+  if (lane == 0) red[warp] = ent;
   __syncthreads();
-  for (int o = kFinalThreads / 2; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
-  }
   if (threadIdx.x == 0) {
-    const double loss = -red[0];
+    double total = 0.0;
+    for (int w = 0; w < kWarps; ++w) total += red[w];
+    const double loss = -total;
     out[0] = (float)loss;
     if (!isfinite(loss)) nonfinite = true;
   }

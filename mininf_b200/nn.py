@@ -458,9 +458,8 @@ class LogLikelihoodLoss(nn.Module):
 
     CUDA tensors run on the engine: the same site table and sweeps as the ELBO with one
     "particle" pinned to the given values (zero noise, no entropy term), so the gradient with
-    respect to ``parameters`` comes from the fused kernels. CPU tensors keep the reference's
-    behaviour through :class:`~mininf_b200.core.LogProbTracer` (this loss is not on the ELBO hot
-    path).
+    respect to ``parameters`` comes from the fused kernels. CPU tensors raise, exactly like
+    :class:`EvidenceLowerBoundLoss`: there is no CPU fallback.
     """
 
     def __init__(self, *, dense_precision: str = "auto") -> None:
@@ -470,9 +469,8 @@ class LogLikelihoodLoss(nn.Module):
     def forward(self, model: Callable, parameters: TensorDict) -> torch.Tensor:
         values = {name: maybe_as_tensor(value) for name, value in parameters.items()}
         if not values or not all(isinstance(v, torch.Tensor) and v.is_cuda for v in values.values()):
-            with LogProbTracer() as log_prob:
-                condition(model, **values)()
-            return - log_prob.total
+            raise RuntimeError("the mininf_b200 engine runs on CUDA tensors only (there is no CPU fallback); "
+                               "LogLikelihoodLoss got parameter values that are not CUDA tensors")
         # a unit-scale Normal around each value with zero noise draws exactly the value, and
         # d loss / d loc is the gradient with respect to the value
         point = {name: distributions.Normal(value, torch.ones_like(value)) for name, value in values.items()}

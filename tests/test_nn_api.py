@@ -75,12 +75,11 @@ def test_elbo_rejects_non_dictionaries_and_cpu_tensors():
         EvidenceLowerBoundLoss(dense_precision="bf16")
 
 
-def test_log_likelihood_loss_with_grad():
+def test_log_likelihood_loss_has_no_cpu_fallback():
+    """mininf/nn.py:231-257 on the engine: CUDA tensors only (GPU parity: test_engine_gpu.py)."""
     def model():
         mininf.sample("x", distributions.Normal(0, 1), 3)
 
     estimate = torch.nn.Parameter(torch.ones(3))
-    value = LogLikelihoodLoss()(model, {"x": estimate})
-    assert value.grad_fn is not None and value.ndim == 0 and np.isfinite(value.item())
-    value.backward()
-    assert estimate.grad is not None
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        LogLikelihoodLoss()(model, {"x": estimate})
