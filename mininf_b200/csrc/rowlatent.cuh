@@ -44,7 +44,9 @@ __device__ __forceinline__ float2 box_muller_fast(uint32_t a, uint32_t b) {
   const float f2 = __uint_as_float(0x3f800000u | (b >> 9));
   const float u1 = 2.0f - f1;                                   // (0, 1]
   const float theta = fmaf(f2, 6.2831853071795865f, -9.4247779607693797f);
-  const float r = __fsqrt_rn(-1.3862943611198906f * __log2f(u1));   // sqrt(-2 ln u1)
+  float lg, r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));          // u1 >= 2^-23: never denormal
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg));   // sqrt(-2 ln u1)
   return make_float2(r * __cosf(theta), r * __sinf(theta));
 }
 
@@ -177,34 +179,37 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
     float E1 = 0.f, E2 = 0.f, W1 = 0.f, W2 = 0.f;
     n_rows_lane += 1.f;
     const float dloc = loc - prior_loc;
-    // ---- draws and the element-wise sites -------------------------------------------------
+    // ---- draws: one uniform branch per row, so the independent Philox chains of the row share a
+    // basic block and the scheduler can interleave them ---------------------------------------
+    if (d.eps != nullptr) {
 #pragma unroll
-    for (int q = 0; q < SP / 4; ++q) {
-      float eps4[4];
-      if (d.eps != nullptr) {
+      for (int s = 0; s < SP; ++s) {
+        const int sg = s_begin + s;
+        eps_r[s] = (active && sg < S) ? __ldg(d.eps + ((int64_t)sg * d.n_rows + row) * p + lane) : 0.f;
+      }
+    } else {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int s = s_begin + 4 * q + t;
-          eps4[t] = (active && s < S) ? __ldg(d.eps + ((int64_t)s * d.n_rows + row) * p + lane) : 0.f;
-        }
-      } else {
+      for (int q = 0; q < SP / 4; ++q) {
         Philox rng(seed, offset, ((uint64_t)e << 8) | (uint64_t)((s_begin >> 2) + q));
         const uint4 r = rng.next();
         const float2 n0 = box_muller_fast(r.x, r.y), n1 = box_muller_fast(r.z, r.w);
-        eps4[0] = n0.x; eps4[1] = n0.y; eps4[2] = n1.x; eps4[3] = n1.y;
-        if (!FULL) {
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-            if (4 * q + t >= s_count) eps4[t] = 0.f;
-        }
+        eps_r[4 * q + 0] = n0.x; eps_r[4 * q + 1] = n0.y; eps_r[4 * q + 2] = n1.x; eps_r[4 * q + 3] = n1.y;
       }
+      if (!FULL) {
+#pragma unroll
+        for (int s = 0; s < SP; ++s)
+          if (s >= s_count) eps_r[s] = 0.f;
+      }
+    }
+    // ---- the element-wise sites ----------------------------------------------------------------
+#pragma unroll
+    for (int q = 0; q < SP / 4; ++q) {
       const float4 b4 = beta4[q], i4 = ipv4[q];
       const float bq[4] = {b4.x, b4.y, b4.z, b4.w}, iq[4] = {i4.x, i4.y, i4.z, i4.w};
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         const int s = 4 * q + t;
-        const float eps = eps4[t];
-        eps_r[s] = eps;
+        const float eps = eps_r[s];
         const float dzp = fmaf(eps, scale, dloc);          // z - prior_loc
         z2[s] = fmaf(dzp, dzp, z2[s]);
         const float tw = iq[t] * eps;

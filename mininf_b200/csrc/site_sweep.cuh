@@ -262,7 +262,7 @@ __device__ __forceinline__ float ex2_approx(float t) {
 // per particle), so masked-out elements cost nothing in the hot loop and it has no control flow.
 // exp(u) = 2^(u log2 e): log2 e is folded into the per-particle constants in fp64 and split as
 // hi + lo, the lo part of A is applied once at the end as a factor on R_s and Rx_s.
-constexpr int pois_min_blocks(int q) { return q <= 2 ? 4 : 2; }   // 64 / 128 registers per thread
+constexpr int pois_min_blocks(int q) { return q <= 2 ? 3 : 2; }   // 80 / 128 registers per thread
 
 template <int Q>
 __global__ void __launch_bounds__(kSweepThreads, pois_min_blocks(Q))
@@ -313,21 +313,27 @@ poisson_exp_kernel(mnf_site_t st, const float* __restrict__ z, int S, int D, flo
   const int64_t n_chunks = (n + 31) / 32;
   const int64_t warp_global = (int64_t)blockIdx.x * kSweepWarps + warp;
   const int64_t warps_total = (int64_t)gridDim.x * kSweepWarps;
-  // software pipeline: the next chunk's loads are in flight while the ring is consumed
-  float n_v = 0.0f, n_x = 1.0f;
-  bool n_live = false;
-  auto fetch = [&](int64_t chunk) {
+  // software pipeline: the loads of the next kAhead chunks are in flight while the ring is
+  // consumed (an iteration that finds fewer than 32 queued covariates is much shorter than the
+  // HBM latency, so one chunk of lookahead is not enough)
+  constexpr int kAhead = 3;
+  float p_v[kAhead], p_x[kAhead];
+  uint32_t p_m[kAhead];       // raw mask byte: it is only LOOKED at when the chunk is consumed
+  auto fetch = [&](int64_t chunk, float& fv, float& fx, uint32_t& fm) {
     const int64_t i = chunk * 32 + lane;
-    const bool inb = i < n;
-    n_live = inb && (st.mask == nullptr || __ldg(st.mask + i) != 0);
-    n_v = inb ? __ldg(st.value + i) : 0.0f;
-    n_x = (inb && L0.x != nullptr) ? __ldg(L0.x + (int64_t)L0.x_stride * i) : 1.0f;
+    const bool inb = chunk < n_chunks && i < n;
+    fm = inb ? (st.mask == nullptr ? 1u : (uint32_t)__ldg(st.mask + i)) : 0u;
+    fv = inb ? __ldg(st.value + i) : 0.0f;
+    fx = (inb && L0.x != nullptr) ? __ldg(L0.x + (int64_t)L0.x_stride * i) : 1.0f;
   };
-  if (warp_global < n_chunks) fetch(warp_global);
+#pragma unroll
+  for (int k = 0; k < kAhead; ++k) fetch(warp_global + k * warps_total, p_v[k], p_x[k], p_m[k]);
   for (int64_t chunk = warp_global; chunk < n_chunks; chunk += warps_total) {
-    const float v = n_v, x = n_x;
-    const bool live = n_live;
-    if (chunk + warps_total < n_chunks) fetch(chunk + warps_total);
+    const float v = p_v[0], x = p_x[0];
+    const bool live = p_m[0] != 0u;
+#pragma unroll
+    for (int k = 0; k + 1 < kAhead; ++k) { p_v[k] = p_v[k + 1]; p_x[k] = p_x[k + 1]; p_m[k] = p_m[k + 1]; }
+    fetch(chunk + kAhead * warps_total, p_v[kAhead - 1], p_x[kAhead - 1], p_m[kAhead - 1]);
     if (live) {
       ++e_n;
       f_v += v;

@@ -556,3 +556,74 @@ def test_row_permutation_invariance_and_determinism():
     shuffled = _evaluate(model, X[perm].contiguous(), y[perm].contiguous(), noise, "tf32")
     assert abs(shuffled[0] - first[0]) <= 2e-6 * abs(first[0])
     assert float((shuffled[1] - first[1]).norm() / first[1].norm()) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------
+# Normal sites through the sufficient-statistics sweep (csrc/site_sweep.cuh::normal_stats_kernel)
+# ---------------------------------------------------------------------------------------------
+def _normal_site_case(n, offset=0.0, masked=True, covariate=True, misalign=0, seed=0):
+    """w ~ Normal(c + d x, sigma) (or Normal(c, sigma) without a covariate) on n elements; the
+    float64 copy feeds the oracle, the float32 copy - optionally a misaligned view - the engine."""
+    from torch.distributions import Gamma, Normal
+    g = torch.Generator().manual_seed(seed)
+    x64 = torch.randn(n + misalign, generator=g, dtype=torch.float64)
+    w64 = offset - 0.2 + 0.8 * x64 + 0.7 * torch.randn(n + misalign, generator=g, dtype=torch.float64)
+    mask = torch.rand(n + misalign, generator=g) > 0.3
+    # the engine sees float32 data: the oracle must score exactly those values
+    x32, w32 = x64.float(), w64.float()
+    x64, w64 = x32.double(), w32.double()
+
+    def make(xv, wv, mv, device):
+        xv, wv, mv = xv.to(device)[misalign:], wv.to(device)[misalign:], mv.to(device)[misalign:]
+
+        def model(m):
+            c = m.sample("c", Normal(0, 1))
+            sigma = m.sample("sigma", Gamma(2, 2))
+            if covariate:
+                d = m.sample("d", Normal(0, 1))
+                m.sample("w", Normal(c + d * xv, sigma))
+            else:
+                m.sample("w", Normal(c, sigma))
+
+        data = {"w": torch.masked.as_masked_tensor(wv, mv) if masked else wv}
+        return model, data
+
+    families = {"c": (Normal, {"loc": torch.tensor(offset + 0.1), "scale": torch.tensor(0.2)}),
+                "d": (Normal, {"loc": torch.tensor(0.5), "scale": torch.tensor(0.2)}),
+                "sigma": (Gamma, {"concentration": torch.tensor(3.0), "rate": torch.tensor(3.0)})}
+    if not covariate:
+        del families["d"]
+    return make, (x64, w64, mask), (x32, w32, mask), families
+
+
+@pytest.mark.parametrize("n,offset,masked,covariate,misalign", [
+    (4096, 0.0, True, True, 0),          # vector path, whole float4 groups
+    (4099, 0.0, True, True, 0),          # ragged tail of three elements
+    (5000, 0.0, False, True, 0),         # no mask
+    (5001, 0.0, True, True, 1),          # misaligned views: scalar path
+    (70_001, 50.0, True, True, 0),       # large common offset: cancellation in sum r^2 (fp64 statistics)
+    (3000, 0.0, True, False, 0),         # no covariate: Normal(c, sigma)
+])
+def test_normal_site_sufficient_statistics(n, offset, masked, covariate, misalign):
+    """The Normal site sweep keeps six data-only sums and evaluates every particle from them; it
+    must agree with a float64 evaluation of the reference algorithm on the same float32 data."""
+    S = 16
+    make, data64, data32, families = _normal_site_case(n, offset, masked, covariate, misalign, seed=n)
+    torch.manual_seed(n)
+    cpu = configs.Config("normal_site", None, {}, families)
+    approx64, leaves64 = cpu.approximation(dtype=torch.float64)
+    noise = {name: elbo.draw_noise(dist, S) for name, dist in approx64.items()}
+    model64, cond64 = make(*data64, "cpu")
+    expected = elbo.neg_elbo(lambda m: model64(m), cond64, approx64, noise, S)
+    expected.backward()
+
+    model32, cond32 = make(*data32, DEV)
+    approx, leaves = cpu.approximation(device=DEV)
+    loss_module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+    loss = loss_module(mininf.condition(lambda: model32(mininf), **cond32), approx,
+                       _noise={k: v.float().to(DEV) for k, v in noise.items()})
+    loss.backward()
+    assert len(loss_module.last_plan.sweep_groups) == 1          # the site sweep ran, not the small-site kernel
+    assert abs(float(loss) - float(expected)) <= 1e-5 * abs(float(expected))
+    for key, leaf in leaves.items():
+        np.testing.assert_allclose(leaf.grad.cpu().numpy(), leaves64[key].grad.numpy(), rtol=3e-4, atol=2e-3)
