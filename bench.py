@@ -42,7 +42,7 @@ N_CHUNKS = 256     # synthetic rows are generated in 256 chunks, chunk c seeded 
 
 class Workload:
     def __init__(self, key, name, p, particles, rows, family, declared_rows, n_batches, kernel, traffic_file,
-                 event_kind="dense", cpu_sample=(2_000_000, 2), bytes_per_row=None, bound_note=None):
+                 event_kind="dense", cpu_sample=(4_000_000, 4), bytes_per_row=None, bound_note=None):
         self.key, self.name, self.p, self.particles, self.rows = key, name, p, particles, rows
         self.family, self.declared_rows, self.n_batches = family, declared_rows, n_batches
         self.kernel, self.traffic_file = kernel, traffic_file
@@ -58,15 +58,15 @@ WORKLOADS = {
     "c3": Workload("c3", "minibatch_logistic_regression_p256_batch1e7_of_N1e9_S16", 256, 16, 10_000_000,
                    "bernoulli", 1_000_000_000, 2,
                    "mnf::tcr::dense_tcr_kernel<BernoulliLogits, 16> (+ its partial-sum reduction)",
-                   "dense_tcr_traffic.json", cpu_sample=(500_000, 2)),
+                   "dense_tcr_traffic.json", cpu_sample=(1_000_000, 4)),
     "c4": Workload("c4", "feature_uncertainty_rowlatent_p32_N1e7_S32", 32, 32, 10_000_000, "rowlatent", None, 1,
                    "mnf::rowlatent_kernel<32> (+ its partial-sum reduction)", "rowlatent_traffic.json",
-                   event_kind="rowlatent", cpu_sample=(200_000, 2), bytes_per_row=32 * 20 + 4,
+                   event_kind="rowlatent", cpu_sample=(500_000, 4), bytes_per_row=32 * 20 + 4,
                    bound_note="instruction-issue bound (N*p*S = 1.0e10 Philox normal draws per step), not HBM; "
                               "see profiles/ for the pipe utilisation"),
     "c5": Workload("c5", "missing_observations_poisson_normal_N1e8_S64_30pct_masked", 1, 64, 100_000_000, "missing",
                    None, 1, "mnf::poisson_exp_kernel<2> + mnf::normal_stats_kernel (one mnf_site_sweep call)",
-                   "site_sweep_traffic.json", event_kind="site", cpu_sample=(2_000_000, 2), bytes_per_row=14,
+                   "site_sweep_traffic.json", event_kind="site", cpu_sample=(10_000_000, 4), bytes_per_row=14,
                    bound_note="the Poisson site is bound by the MUFU pipe (one ex2 per live element and particle), "
                               "the Normal site by HBM (sufficient statistics, 9 B per element)"),
 }
@@ -465,9 +465,9 @@ def run_b200(args):
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             rows_cpu, parts_cpu = w.cpu_rows, w.cpu_particles
-            cpu_value, _ = cpu_sample(w, rows_cpu, parts_cpu, steps=3, warmup=1)
+            cpu_value, _ = cpu_sample(w, rows_cpu, parts_cpu, steps=8, warmup=1)
             cpu_baseline = {"value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                            "sample": f"{rows_cpu} rows x {parts_cpu} particles per step, 3 timed steps, of the "
+                            "sample": f"{rows_cpu} rows x {parts_cpu} particles per step, 8 timed steps, of the "
                                       f"{w.name} workload; oracle port of the reference's torch.distributions "
                                       "path with validation on"}
         line = {
@@ -556,6 +556,9 @@ def run_e2e(args, w, step, batches, n_rows, world, device, fence, distributed):
 
 
 def main():
+    import warnings
+    warnings.filterwarnings("ignore", message=".*MaskedTensors is in prototype.*")
+    warnings.filterwarnings("ignore", message=".*Converting a tensor with requires_grad=True to a scalar.*")
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
