@@ -44,26 +44,8 @@ int launch_poisson_exp_q(const mnf_site_t& site, const float* z, int S, int D, f
   return MNF_OK;
 }
 
-template <int Q>
-int launch_poisson_exp_ws_q(const mnf_site_t& site, const float* z, int S, int D, float* partial,
-                            uint32_t* status, int grid, cudaStream_t stream) {
-  auto kernel = poisson_exp_ws_kernel<Q>;
-  const size_t smem = poisson_exp_ws_smem_bytes<Q>();
-  MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kernel<<<grid, kSweepThreads, smem, stream>>>(site, z, S, D, partial, status);
-  MNF_CUDA_CHECK(cudaGetLastError());
-  return MNF_OK;
-}
-
 int launch_poisson_exp(const mnf_site_t& site, const float* z, int S, int D, float* partial,
                        uint32_t* status, int grid, cudaStream_t stream) {
-  if (const char* mode = std::getenv("MNF_POISSON_KERNEL")) {      // developer override: "ws" = warp-specialised
-    if (std::strcmp(mode, "ws") == 0) {
-      if (S <= 32) return launch_poisson_exp_ws_q<1>(site, z, S, D, partial, status, grid, stream);
-      if (S <= 64) return launch_poisson_exp_ws_q<2>(site, z, S, D, partial, status, grid, stream);
-      return launch_poisson_exp_ws_q<4>(site, z, S, D, partial, status, grid, stream);
-    }
-  }
   if (S <= 32) return launch_poisson_exp_q<1>(site, z, S, D, partial, status, grid, stream);
   if (S <= 64) return launch_poisson_exp_q<2>(site, z, S, D, partial, status, grid, stream);
   return launch_poisson_exp_q<4>(site, z, S, D, partial, status, grid, stream);

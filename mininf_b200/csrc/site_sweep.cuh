@@ -262,7 +262,7 @@ __device__ __forceinline__ float ex2_approx(float t) {
 // per particle), so masked-out elements cost nothing in the hot loop and it has no control flow.
 // exp(u) = 2^(u log2 e): log2 e is folded into the per-particle constants in fp64 and split as
 // hi + lo, the lo part of A is applied once at the end as a factor on R_s and Rx_s.
-constexpr int pois_min_blocks(int q) { return q <= 2 ? 4 : 2; }   // 64 / 128 registers per thread
+constexpr int pois_min_blocks(int q) { return q <= 2 ? 3 : 2; }   // 80 / 128 registers per thread
 
 template <int Q>
 __global__ void __launch_bounds__(kSweepThreads, pois_min_blocks(Q))
@@ -440,229 +440,6 @@ template <int Q>
 inline size_t poisson_exp_smem_bytes() {
   return sizeof(double) * kSweepWarps * Q * 32 * 2 + sizeof(double) * kSweepWarps * 4 +
          sizeof(float) * kSweepWarps * 64 + sizeof(float) * 64;
-}
-
-// ---- warp-specialised variant -----------------------------------------------------------------
-// In the kernel above every warp alternates between a chunk phase (loads, data-only sums,
-// compaction: no MUFU work) and a group phase (64 ex2 per 32 queued covariates); ncu shows the XU
-// pipe ~75 % busy because too few warps are in the group phase at any time. Here the roles are
-// split: kPoisProducers warps per CTA only walk chunks and hand groups of 32 live covariates to
-// the consumer warps through shared-memory slots (full/empty counters, two slots per consumer,
-// strict round robin so the hand-off order is fixed), and the consumers run nothing but the
-// branch-free group block. Same arithmetic, same partial layout; the per-particle sums of a
-// particle are combined over the consumer warps in fixed order.
-constexpr int kPoisProducers = 2;
-constexpr int kPoisConsumers = kSweepWarps - kPoisProducers;            // 6
-constexpr int kPoisFeed = kPoisConsumers / kPoisProducers;              // consumers fed by one producer
-constexpr int kPoisSlots = 2 * kPoisConsumers;                          // two slots per consumer
-static_assert(kPoisConsumers % kPoisProducers == 0, "consumers must split evenly over the producers");
-
-template <int Q>
-__global__ void __launch_bounds__(kSweepThreads, Q <= 2 ? 4 : 2)
-poisson_exp_ws_kernel(mnf_site_t st, const float* __restrict__ z, int S, int D, float* __restrict__ partial,
-                      uint32_t* __restrict__ status) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t n = st.numel;
-  const mnf_link_t L0 = st.param[0];
-
-  extern __shared__ double s_pois[];
-  double* s_sums = s_pois;                                              // [consumer][Q*32][2]
-  double* s_elem = s_pois + (size_t)kPoisConsumers * Q * 32 * 2;        // [producer][4]: V, Vx, C, n
-  float* s_slot = reinterpret_cast<float*>(s_elem + kPoisProducers * 4);    // [slot][32], 16-byte aligned
-  float* s_ring = s_slot + kPoisSlots * 32;                             // [producer][64]
-  float* s_logfact = s_ring + kPoisProducers * 64;                      // [64]
-  volatile int* s_count = reinterpret_cast<volatile int*>(s_logfact + 64);  // [slot]: 0 empty, k > 0 covariates, -1 end
-  if (threadIdx.x < 64) s_logfact[threadIdx.x] = kLogFactorial[threadIdx.x];
-  if (threadIdx.x < kPoisSlots) s_count[threadIdx.x] = 0;
-  __syncthreads();
-
-  if (warp < kPoisProducers) {
-    // ------------------------------- producer -------------------------------------------------
-    float* ring = s_ring + warp * 64;
-    double e_v = 0.0, e_vx = 0.0, e_c = 0.0;
-    float f_v = 0.0f, f_vx = 0.0f, f_c = 0.0f;
-    int e_n = 0, chunks = 0;
-    bool bad_value = false;
-    int head = 0, fill = 0, turn = 0;            // turn: position in this producer's round robin
-    constexpr int kFlush = 8;
-    // slot of round-robin position t: consumer (t % kPoisFeed) of this producer, its slot (t / kPoisFeed) & 1
-    auto slot_of = [&](int t) { return 2 * (warp * kPoisFeed + t % kPoisFeed) + ((t / kPoisFeed) & 1); };
-    auto hand_over = [&](int count) {            // count > 0: ring[head .. head+count) ; count < 0: end marker
-      const int slot = slot_of(turn);
-      while (s_count[slot] != 0) __nanosleep(32);
-      if (count > 0 && lane < count) s_slot[slot * 32 + lane] = ring[(head + lane) & 63];
-      __threadfence_block();
-      __syncwarp();
-      if (lane == 0) s_count[slot] = count;
-      turn = (turn + 1) % (2 * kPoisFeed);
-    };
-    const int64_t n_chunks = (n + 31) / 32;
-    const int64_t prod_global = (int64_t)blockIdx.x * kPoisProducers + warp;
-    const int64_t prod_total = (int64_t)gridDim.x * kPoisProducers;
-    constexpr int kAhead = 3;
-    float p_v[kAhead], p_x[kAhead];
-    uint32_t p_m[kAhead];
-    auto fetch = [&](int64_t chunk, float& fv, float& fx, uint32_t& fm) {
-      const int64_t i = chunk * 32 + lane;
-      const bool inb = chunk < n_chunks && i < n;
-      fm = inb ? (st.mask == nullptr ? 1u : (uint32_t)__ldg(st.mask + i)) : 0u;
-      fv = inb ? __ldg(st.value + i) : 0.0f;
-      fx = (inb && L0.x != nullptr) ? __ldg(L0.x + (int64_t)L0.x_stride * i) : 1.0f;
-    };
-#pragma unroll
-    for (int k = 0; k < kAhead; ++k) fetch(prod_global + k * prod_total, p_v[k], p_x[k], p_m[k]);
-    for (int64_t chunk = prod_global; chunk < n_chunks; chunk += prod_total) {
-      const float v = p_v[0], x = p_x[0];
-      const bool live = p_m[0] != 0u;
-#pragma unroll
-      for (int k = 0; k + 1 < kAhead; ++k) { p_v[k] = p_v[k + 1]; p_x[k] = p_x[k + 1]; p_m[k] = p_m[k + 1]; }
-      fetch(chunk + kAhead * prod_total, p_v[kAhead - 1], p_x[kAhead - 1], p_m[kAhead - 1]);
-      if (live) {
-        ++e_n;
-        f_v += v;
-        f_vx = fmaf(v, x, f_vx);
-        if (v >= 0.0f && v < 64.0f && v == floorf(v)) {
-          f_c += s_logfact[(int)v];
-        } else {
-          if (!in_support(MNF_POISSON, v)) bad_value = true;
-          f_c += log_factorial(v);
-        }
-      }
-      if (++chunks == kFlush) {
-        e_v += (double)f_v; e_vx += (double)f_vx; e_c += (double)f_c;
-        f_v = 0.0f; f_vx = 0.0f; f_c = 0.0f;
-        chunks = 0;
-      }
-      const uint32_t bits = __ballot_sync(0xffffffffu, live);
-      if (live) ring[(head + fill + __popc(bits & ((1u << lane) - 1u))) & 63] = x;
-      fill += __popc(bits);
-      __syncwarp();
-      if (fill >= 32) {
-        hand_over(32);
-        head = (head + 32) & 63;
-        fill -= 32;
-        __syncwarp();
-      }
-    }
-    if (fill > 0) hand_over(fill);
-    for (int k = 0; k < kPoisFeed; ++k) hand_over(-1);     // one end marker per consumer, in turn order
-    e_v += (double)f_v; e_vx += (double)f_vx; e_c += (double)f_c;
-    e_v = warp_sum(e_v);
-    e_vx = warp_sum(e_vx);
-    e_c = warp_sum(e_c);
-    const double e_cnt = warp_sum((double)e_n);
-    if (lane == 0) {
-      s_elem[warp * 4 + 0] = e_v;
-      s_elem[warp * 4 + 1] = e_vx;
-      s_elem[warp * 4 + 2] = e_c;
-      s_elem[warp * 4 + 3] = e_cnt;
-    }
-    if (bad_value) atomicOr(status, MNF_ST_BAD_VALUE);
-  } else {
-    // ------------------------------- consumer -------------------------------------------------
-    const int cons = warp - kPoisProducers;
-    float A2[Q], Bh[Q], Bl[Q];
-    double corr[Q];
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const int s = lane + 32 * q;
-      const float* zs = z + (int64_t)(s < S ? s : 0) * D;
-      const float A = L0.a_const + (L0.a_lat >= 0 ? zs[L0.a_lat] : 0.0f);
-      const float B = L0.b_const + (L0.b_lat >= 0 ? zs[L0.b_lat] : 0.0f);
-      const double a2 = (double)A * 1.4426950408889634074, b2 = (double)B * 1.4426950408889634074;
-      A2[q] = (float)a2;
-      corr[q] = exp2(a2 - (double)A2[q]);
-      Bh[q] = (float)b2;
-      Bl[q] = (float)(b2 - (double)Bh[q]);
-    }
-    double run[Q][2];
-    float r0[Q], r1[Q];
-#pragma unroll
-    for (int q = 0; q < Q; ++q) { run[q][0] = 0.0; run[q][1] = 0.0; r0[q] = 0.0f; r1[q] = 0.0f; }
-    int groups = 0, which = 0;
-    constexpr int kFlush = 8;
-    for (;;) {
-      const int slot = 2 * cons + which;
-      int count;
-      while ((count = s_count[slot]) == 0) __nanosleep(32);
-      __threadfence_block();
-      __syncwarp();
-      if (count < 0) break;
-      if (count == 32) {
-        const float4* b4 = reinterpret_cast<const float4*>(s_slot + slot * 32);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 xs = b4[j];
-          const float xe[4] = {xs.x, xs.y, xs.z, xs.w};
-#pragma unroll
-          for (int t = 0; t < 4; ++t)
-#pragma unroll
-            for (int q = 0; q < Q; ++q) {
-              const float rate = ex2_approx(fmaf(Bh[q], xe[t], fmaf(Bl[q], xe[t], A2[q])));
-              r0[q] += rate;
-              r1[q] = fmaf(rate, xe[t], r1[q]);
-            }
-        }
-      } else {
-        for (int e = 0; e < count; ++e) {
-          const float xe = s_slot[slot * 32 + e];
-#pragma unroll
-          for (int q = 0; q < Q; ++q) {
-            const float rate = ex2_approx(fmaf(Bh[q], xe, fmaf(Bl[q], xe, A2[q])));
-            r0[q] += rate;
-            r1[q] = fmaf(rate, xe, r1[q]);
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) s_count[slot] = 0;        // release the slot
-      which ^= 1;
-      if (++groups == kFlush) {
-#pragma unroll
-        for (int q = 0; q < Q; ++q) {
-          run[q][0] += (double)r0[q]; run[q][1] += (double)r1[q];
-          r0[q] = 0.0f; r1[q] = 0.0f;
-        }
-        groups = 0;
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      run[q][0] += (double)r0[q]; run[q][1] += (double)r1[q];
-      s_sums[((size_t)cons * Q * 32 + q * 32 + lane) * 2 + 0] = run[q][0] * corr[q];
-      s_sums[((size_t)cons * Q * 32 + q * 32 + lane) * 2 + 1] = run[q][1] * corr[q];
-    }
-  }
-  __syncthreads();
-
-  // one particle per thread: combine the warps in fixed order and finish the closed form
-  for (int s = threadIdx.x; s < S; s += kSweepThreads) {
-    double t[2] = {0.0, 0.0}, el[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int w = 0; w < kPoisConsumers; ++w) {
-      t[0] += s_sums[((size_t)w * Q * 32 + s) * 2 + 0];
-      t[1] += s_sums[((size_t)w * Q * 32 + s) * 2 + 1];
-    }
-    for (int w = 0; w < kPoisProducers; ++w)
-#pragma unroll
-      for (int a = 0; a < 4; ++a) el[a] += s_elem[w * 4 + a];
-    const float* zs = z + (int64_t)s * D;
-    const double a_s = (double)(L0.a_const + (L0.a_lat >= 0 ? zs[L0.a_lat] : 0.0f));
-    const double b_s = (double)(L0.b_const + (L0.b_lat >= 0 ? zs[L0.b_lat] : 0.0f));
-    float* out = partial + ((size_t)blockIdx.x * S + s) * 5;
-    const double w = st.scale;
-    out[0] = (float)(w * (a_s * el[0] + b_s * el[1] - t[0] - el[2]));
-    out[1] = (float)(w * (el[0] - t[0]));
-    out[2] = (float)(w * (el[1] - t[1]));
-    out[3] = 0.0f;
-    out[4] = 0.0f;
-  }
-}
-
-template <int Q>
-inline size_t poisson_exp_ws_smem_bytes() {
-  return sizeof(double) * kPoisConsumers * Q * 32 * 2 + sizeof(double) * kPoisProducers * 4 +
-         sizeof(float) * kPoisSlots * 32 + sizeof(float) * kPoisProducers * 64 + sizeof(float) * 64 +
-         sizeof(int) * kPoisSlots;
 }
 
 // ---- Normal(A_s + B_s x, sigma_s): data-only sufficient statistics -------------------------------

@@ -23,7 +23,7 @@ from typing import Any, Callable, Dict, List, Optional, Set, Tuple, Type
 import torch
 from torch import distributions, nn
 
-from .core import LogProbTracer, condition
+from .core import condition
 from .util import OptionalSize, TensorDict, _normalize_shape, maybe_as_tensor
 
 DistributionDict = Dict[str, torch.distributions.Distribution]
@@ -280,7 +280,6 @@ class EvidenceLowerBoundLoss(nn.Module):
 
     # -- tracing ----------------------------------------------------------------------------
     def _build_plan(self, model: Callable, approximation: DistributionDict) -> Any:
-        from .engine import abi
         from .engine.plan import Plan, assign_offsets, latent_parameters
         from .engine.trace import Affine, LatentRef, LinkTensor, SiteTableTracer
 

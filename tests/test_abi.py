@@ -68,3 +68,18 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(build, "LIB_PATH", tmp_path / "nope.so")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         abi.load()
+
+
+def test_build_units_track_their_own_headers():
+    """Every translation unit is rebuilt when (and only when) a header it includes changes."""
+    assert set(build.UNITS) == {path.stem for path in build.CSRC_DIR.glob("*.cu")}
+    closures = {}
+    for unit in build.UNITS:
+        seen = {}
+        build._closure(build.CSRC_DIR / f"{unit}.cu", seen)
+        closures[unit] = {path.name for path in seen}
+        assert {"common.cuh", "host.h", "mininf_b200.h", f"{unit}.cu"} <= closures[unit]
+    assert "site_sweep.cuh" in closures["site"] and "site_sweep.cuh" not in closures["dense"]
+    assert {"dense_tc.cuh", "dense_tcr.cuh", "dense_simt.cuh"} <= closures["dense"]
+    assert "rowlatent.cuh" in closures["rowlatent"] and "small.cuh" in closures["abi"]
+    assert len({build.unit_digest(unit) for unit in build.UNITS}) == len(build.UNITS)

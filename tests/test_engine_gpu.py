@@ -583,7 +583,7 @@ def _normal_site_case(n, offset=0.0, masked=True, covariate=True, misalign=0, se
                 d = m.sample("d", Normal(0, 1))
                 m.sample("w", Normal(c + d * xv, sigma))
             else:
-                m.sample("w", Normal(c, sigma))
+                m.sample("w", Normal(c, sigma), wv.shape)
 
         data = {"w": torch.masked.as_masked_tensor(wv, mv) if masked else wv}
         return model, data
@@ -627,3 +627,105 @@ def test_normal_site_sufficient_statistics(n, offset, masked, covariate, misalig
     assert abs(float(loss) - float(expected)) <= 1e-5 * abs(float(expected))
     for key, leaf in leaves.items():
         np.testing.assert_allclose(leaf.grad.cpu().numpy(), leaves64[key].grad.numpy(), rtol=3e-4, atol=2e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size properties of the site sweeps (config C5) and the row-latent sweep (config C4)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_site_sweeps_permutation_invariance_determinism_and_counts():
+    """N = 1e8 elements, S = 64, 30 % missing (BASELINE.json config[4]): the joint is a sum over
+    elements, so permuting (x, counts, w, masks) jointly changes nothing beyond reassociation;
+    repeating a call is bit-identical; the observed-entry and count sums are integer-exact."""
+    from torch.distributions import Gamma, Normal, Poisson
+    n, S = 100_000_000, 64
+    g = torch.Generator(device=DEV).manual_seed(77)
+    x = torch.randn(n, generator=g, device=DEV)
+    counts = torch.poisson(torch.exp(0.3 + 0.5 * x), generator=g)
+    w = -0.2 + 0.8 * x + 0.7 * torch.randn(n, generator=g, device=DEV)
+    m_counts = torch.rand(n, generator=g, device=DEV) > 0.3
+    m_w = torch.rand(n, generator=g, device=DEV) > 0.3
+
+    def evaluate(x, counts, w, m_counts, m_w):
+        def model():
+            a = mininf.sample("a", Normal(0, 1))
+            b = mininf.sample("b", Normal(0, 1))
+            c = mininf.sample("c", Normal(0, 1))
+            d = mininf.sample("d", Normal(0, 1))
+            sigma = mininf.sample("sigma", Gamma(2, 2))
+            mininf.sample("counts", Poisson((a + b * x).exp()))
+            mininf.sample("w", Normal(c + d * x, sigma))
+
+        leaves = {k: (torch.tensor(0.1, device=DEV).requires_grad_(), torch.tensor(0.2, device=DEV).requires_grad_())
+                  for k in "abcd"}
+        approx = {k: Normal(*v) for k, v in leaves.items()}
+        conc, rate = torch.tensor(2.0, device=DEV).requires_grad_(), torch.tensor(2.0, device=DEV).requires_grad_()
+        approx["sigma"] = Gamma(conc, rate)
+        gen = torch.Generator().manual_seed(9)
+        noise = {k: torch.randn(S, generator=gen).to(DEV) for k in "abcd"}
+        noise["sigma"] = torch._standard_gamma(torch.full((S,), 2.0), generator=gen).to(DEV)
+        module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+        loss = module(mininf.condition(model, counts=torch.masked.as_masked_tensor(counts, m_counts),
+                                       w=torch.masked.as_masked_tensor(w, m_w)), approx, _noise=noise)
+        loss.backward()
+        grads = torch.stack([t.grad for pair in leaves.values() for t in pair] + [conc.grad, rate.grad])
+        return float(loss), grads
+
+    first = evaluate(x, counts, w, m_counts, m_w)
+    again = evaluate(x, counts, w, m_counts, m_w)
+    assert first[0] == again[0] and torch.equal(first[1], again[1])
+    perm = torch.randperm(n, device=DEV)
+    shuffled = evaluate(x[perm], counts[perm], w[perm], m_counts[perm], m_w[perm])
+    assert abs(shuffled[0] - first[0]) <= 2e-6 * abs(first[0])
+    assert float((shuffled[1] - first[1]).norm() / first[1].norm()) < 2e-5
+    out = torch.zeros(2, dtype=torch.int64, device=DEV)
+    abi.load().call("mnf_masked_count", counts.data_ptr(), m_counts.data_ptr(), n, out.data_ptr(),
+                    torch.cuda.current_stream().cuda_stream)
+    assert out.tolist() == [int(m_counts.sum()), int(counts[m_counts].double().sum())]
+
+
+def test_full_size_row_latent_sweep_is_seeded_and_its_gradients_are_consistent():
+    """N = 1e7 rows, p = 32, S = 32 (BASELINE.json config[3]) with in-kernel Philox draws: the
+    same seed reproduces the loss and every gradient bit for bit, and because the draws are a fixed
+    function of (seed, call index) the loss is a smooth function of the parameters whose central
+    difference along the intercept location must match the analytic gradient."""
+    from torch.distributions import Gamma, Normal, Poisson
+    n, p, S = 10_000_000, 32, 32
+    g = torch.Generator(device=DEV).manual_seed(41)
+    slope_true = torch.randn(p, generator=g, device=DEV) / p ** 0.5
+    zt = torch.randn(n, p, generator=g, device=DEV)
+    y = torch.poisson(torch.exp(0.5 + zt @ slope_true), generator=g)
+    x = zt + 0.5 * torch.randn(n, p, generator=g, device=DEV)
+    del zt
+
+    def model():
+        population_scale = mininf.sample("population_scale", Gamma(2, 2))
+        z = mininf.sample("z", Normal(0, population_scale), (n, p))
+        mininf.sample("x", Normal(z, 0.5))
+        intercept = mininf.sample("intercept", Normal(0, 1))
+        slope = mininf.sample("slope", Normal(0, 1), p)
+        mininf.sample("y", Poisson((intercept + z @ slope).exp()))
+
+    conditioned = mininf.condition(model, x=x, y=y)
+    z_loc, z_scale = x.clone().requires_grad_(), torch.full((n, p), 0.3, device=DEV).requires_grad_()
+
+    def evaluate(intercept_loc, backward=True):
+        icpt = torch.tensor(intercept_loc, device=DEV).requires_grad_()
+        approx = {"population_scale": Gamma(torch.tensor(40.0, device=DEV), torch.tensor(40.0, device=DEV)),
+                  "z": Normal(z_loc, z_scale), "intercept": Normal(icpt, torch.tensor(0.05, device=DEV)),
+                  "slope": Normal(0.1 * slope_true, torch.full((p,), 0.02, device=DEV))}
+        torch.manual_seed(123)                       # the engine derives its Philox key from torch's generator
+        loss = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")(conditioned, approx)
+        if backward:
+            z_loc.grad = z_scale.grad = None
+            loss.backward()
+            return float(loss), icpt.grad.item(), z_loc.grad.clone(), z_scale.grad.clone()
+        return float(loss)
+
+    first = evaluate(0.4)
+    again = evaluate(0.4)
+    assert first[0] == again[0] and first[1] == again[1]
+    assert torch.equal(first[2], again[2]) and torch.equal(first[3], again[3])
+    assert bool(torch.isfinite(first[2]).all()) and bool(torch.isfinite(first[3]).all())
+    h = 0.03     # fp32 loss resolution (~2e2 of 2e9) and the cubic term both stay near 1e-3 of the slope
+    numeric = (evaluate(0.4 + h, backward=False) - evaluate(0.4 - h, backward=False)) / (2 * h)
+    assert abs(numeric - first[1]) <= 5e-3 * abs(first[1]), (numeric, first[1])
