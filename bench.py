@@ -64,10 +64,14 @@ WORKLOADS = {
                    bound_note="instruction-issue bound (N*p*S = 1.0e10 Philox normal draws per step), not HBM; "
                               "see profiles/ for the pipe utilisation"),
     "c5": Workload("c5", "missing_observations_poisson_normal_N1e8_S64_30pct_masked", 1, 64, 100_000_000, "missing",
-                   None, 1, "mnf::poisson_exp_kernel<2> + mnf::normal_stats_kernel (one mnf_site_sweep call)",
+                   None, 1, "mnf::poisson_range_kernel + mnf::poisson_moment_kernel + mnf::normal_stats_kernel "
+                            "(one mnf_site_sweep call)",
                    "site_sweep_traffic.json", event_kind="site", cpu_sample=(10_000_000, 4), bytes_per_row=14,
-                   bound_note="the Poisson site is bound by the MUFU pipe (one ex2 per live element and particle), "
-                              "the Normal site by HBM (sufficient statistics, 9 B per element)"),
+                   bound_note="both sites are reduced to data-only sufficient statistics (33 Chebyshev moments of "
+                              "the covariate for the Poisson site, six sums for the Normal site): three streaming "
+                              "passes that move 23 B per element for 14 algorithmic bytes (the covariate is read by "
+                              "each pass); the moment pass is bound by fp32 issue (64 FFMA/FADD per element), the "
+                              "other two by HBM"),
 }
 
 
@@ -313,6 +317,9 @@ def run_reference(args):
         return
     w = WORKLOADS[args.workload]
     rows, particles = w.cpu_rows, w.cpu_particles
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; rank 0 runs alone here, so give the CPU arm
+    # every host thread this process may use
+    torch.set_num_threads(max(len(os.sched_getaffinity(0)), 1))
     value, seconds = cpu_sample(w, rows, particles, args.steps, args.warmup)
     cores = torch.get_num_threads()
     sample = (f"{rows} rows x {particles} particles per step of the {w.name} workload "

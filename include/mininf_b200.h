@@ -221,6 +221,12 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
  * Element-wise sweep over up to MNF_MAX_FUSED_SITES sites of equal numel whose values are
  * observed data and whose links reference only scalar latents (stride 0): one pass over the
  * data for all particles (LogProbTracer.sample + contribution, core.py:211-273).
+ * Normal(A + B x, sigma) and Poisson(exp(A + B x)) sites are reduced to data-only sufficient
+ * statistics (six sums / up to 33 Chebyshev moments of x) and cost the same for any number of
+ * particles; the Poisson expansion is checked on the device per call and a per-particle kernel
+ * takes over when the check fails. `workspace` must hold mnf_workspace_bytes(); with less the
+ * call still works but without the moment path / the overlap of the two statistics passes.
+ * Uses one internal side stream per device (forked from and joined to `stream` inside the call).
  */
 #define MNF_MAX_FUSED_SITES 4
 int mnf_site_sweep(const mnf_site_t* sites, int n_sites, const float* z, int n_particles,

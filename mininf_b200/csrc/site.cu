@@ -1,5 +1,8 @@
 // Element-wise site sweeps (csrc/site_sweep.cuh) and the mnf_site_sweep entry point of
 // include/mininf_b200.h.
+#include <cstdlib>
+#include <mutex>
+
 #include "host.h"
 #include "site_sweep.cuh"
 
@@ -35,41 +38,116 @@ int launch_site_sweep(const mnf_site_t* sites, const float* z, int S, int D, flo
 
 template <int Q>
 int launch_poisson_exp_q(const mnf_site_t& site, const float* z, int S, int D, float* partial,
-                         uint32_t* status, int grid, cudaStream_t stream) {
+                         uint32_t* status, const uint32_t* need_exact, int grid, cudaStream_t stream) {
   auto kernel = poisson_exp_kernel<Q>;
   const size_t smem = poisson_exp_smem_bytes<Q>();
   MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kernel<<<grid, kSweepThreads, smem, stream>>>(site, z, S, D, partial, status);
+  kernel<<<grid, kSweepThreads, smem, stream>>>(site, z, S, D, partial, status, need_exact);
   MNF_CUDA_CHECK(cudaGetLastError());
   return MNF_OK;
 }
 
 int launch_poisson_exp(const mnf_site_t& site, const float* z, int S, int D, float* partial,
-                       uint32_t* status, int grid, cudaStream_t stream) {
-  if (S <= 32) return launch_poisson_exp_q<1>(site, z, S, D, partial, status, grid, stream);
-  if (S <= 64) return launch_poisson_exp_q<2>(site, z, S, D, partial, status, grid, stream);
-  return launch_poisson_exp_q<4>(site, z, S, D, partial, status, grid, stream);
+                       uint32_t* status, const uint32_t* need_exact, int grid, cudaStream_t stream) {
+  if (S <= 32) return launch_poisson_exp_q<1>(site, z, S, D, partial, status, need_exact, grid, stream);
+  if (S <= 64) return launch_poisson_exp_q<2>(site, z, S, D, partial, status, need_exact, grid, stream);
+  return launch_poisson_exp_q<4>(site, z, S, D, partial, status, need_exact, grid, stream);
+}
+
+// Developer A/B switch: MNF_POISSON_EXACT=1 keeps the per-particle MUFU kernel for every call.
+bool poisson_moments_disabled() {
+  const char* v = std::getenv("MNF_POISSON_EXACT");     // read per call so a test can flip it
+  return v != nullptr && v[0] != '\0' && v[0] != '0';
+}
+
+// Poisson(exp(A_s + B_s x)) through the data-only Chebyshev moments of site_sweep.cuh. `scratch`
+// (after the exact kernel's partial rows) holds the range partials, the per-CTA moment rows and
+// the need_exact word the finish kernel sets; returns that word's address, or NULL when this
+// site's layout does not qualify (no covariate, strided or misaligned data, scratch too small).
+int launch_poisson_moments(const mnf_site_t& site, const float* z, int S, int D, double* acc, char* scratch,
+                           size_t scratch_bytes, uint32_t* status, int sm_count, cudaStream_t stream,
+                           uint32_t** need_exact_out) {
+  *need_exact_out = nullptr;
+  const mnf_link_t& L0 = site.param[0];
+  const bool vec = L0.x != nullptr && L0.x_stride == 1 && reinterpret_cast<uintptr_t>(L0.x) % 16 == 0 &&
+                   reinterpret_cast<uintptr_t>(site.value) % 16 == 0 &&
+                   (site.mask == nullptr || reinterpret_cast<uintptr_t>(site.mask) % 4 == 0);
+  if (!vec || poisson_moments_disabled()) return MNF_OK;
+  const int64_t groups = (site.numel + 4 * kChebThreads - 1) / (4 * kChebThreads);
+  const int range_grid = (int)std::max<int64_t>(1, std::min<int64_t>(groups, 8 * (int64_t)sm_count));
+  const int moment_grid = (int)std::max<int64_t>(1, std::min<int64_t>(groups, 3 * (int64_t)sm_count));
+  const size_t rows_bytes = sizeof(double) * kChebCols * (size_t)moment_grid;
+  const size_t range_bytes = (sizeof(float) * 2 * (size_t)range_grid + 15) / 16 * 16;
+  if (rows_bytes + range_bytes + 16 > scratch_bytes) return MNF_OK;
+  double* rows = reinterpret_cast<double*>(scratch);
+  float* range_partial = reinterpret_cast<float*>(scratch + rows_bytes);
+  uint32_t* need_exact = reinterpret_cast<uint32_t*>(scratch + rows_bytes + range_bytes);
+  const size_t smem = poisson_moment_smem_bytes();
+  auto moment_kernel = poisson_moment_kernel;
+  MNF_CUDA_CHECK(cudaFuncSetAttribute(moment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  poisson_range_kernel<<<range_grid, kChebThreads, 0, stream>>>(site, range_partial);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  moment_kernel<<<moment_grid, kChebThreads, smem, stream>>>(site, range_partial, range_grid, z, S, D, rows, status);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  poisson_moment_finish_kernel<<<1, kChebThreads, 0, stream>>>(site, rows, moment_grid, range_partial, range_grid,
+                                                              z, S, D, acc, need_exact);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  *need_exact_out = need_exact;
+  return MNF_OK;
 }
 
 // Normal site with an identity location link and an element-independent scale: one data-only pass
-// for six sufficient statistics, then the per-particle closed forms straight into acc.
-int launch_normal_stats(const mnf_site_t& site, const float* z, int S, int D, double* acc, void* workspace,
-                        size_t workspace_bytes, uint32_t* status, int sm_count, cudaStream_t stream) {
+// for six sufficient statistics (on `stream`, which may be the side stream of overlap_streams),
+// then - launch_normal_finish, always on the caller's stream - the per-particle closed forms
+// straight into acc.
+int normal_stats_grid(const mnf_site_t& site, bool* vec_out, int sm_count) {
   const mnf_link_t& L0 = site.param[0];
   const bool vec = reinterpret_cast<uintptr_t>(site.value) % 16 == 0 &&
                    (L0.x == nullptr || (L0.x_stride == 1 && reinterpret_cast<uintptr_t>(L0.x) % 16 == 0)) &&
                    (site.mask == nullptr || reinterpret_cast<uintptr_t>(site.mask) % 4 == 0);
   const int64_t per_thread = vec ? 4 : 1;
   const int64_t want = (site.numel + kStatThreads * per_thread - 1) / (kStatThreads * per_thread);
-  const int64_t fits = (int64_t)(workspace_bytes / (kStatCols * sizeof(double)));   // one row of statistics per CTA
-  if (fits < 1) return fail(MNF_E_INVALID, "mnf_site_sweep: workspace too small%s%s");
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(want, fits), 8 * (int64_t)sm_count));
-  double* cta_stats = static_cast<double*>(workspace);
+  *vec_out = vec;
+  return (int)std::max<int64_t>(1, std::min<int64_t>(want, 8 * (int64_t)sm_count));
+}
+
+int launch_normal_stats(const mnf_site_t& site, bool vec, int grid, double* cta_stats, uint32_t* status,
+                        cudaStream_t stream) {
   if (vec) normal_stats_kernel<true><<<grid, kStatThreads, 0, stream>>>(site, cta_stats, status);
   else normal_stats_kernel<false><<<grid, kStatThreads, 0, stream>>>(site, cta_stats, status);
   MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+int launch_normal_finish(const mnf_site_t& site, const double* cta_stats, int grid, const float* z, int S, int D,
+                         double* acc, uint32_t* status, cudaStream_t stream) {
   normal_stats_finish_kernel<<<1, 32 * kStatCols, 0, stream>>>(site, cta_stats, grid, z, S, D, acc, status);
   MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+// A second stream per device (plus fork / join events) so that the HBM-bound statistics pass of a
+// Normal site runs beside the issue-bound moment pass of a Poisson site. The fork / join pattern
+// is legal inside a stream capture, so a graphed step keeps the overlap.
+struct OverlapStreams {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+
+int overlap_streams(OverlapStreams** out) {
+  static std::mutex mutex;
+  static OverlapStreams table[64];
+  int device = 0;
+  MNF_CUDA_CHECK(cudaGetDevice(&device));
+  if (device < 0 || device >= 64) return fail(MNF_E_INVALID, "device index out of range%s%s");
+  std::lock_guard<std::mutex> lock(mutex);
+  OverlapStreams& o = table[device];
+  if (o.side == nullptr) {
+    MNF_CUDA_CHECK(cudaStreamCreateWithFlags(&o.side, cudaStreamNonBlocking));
+    MNF_CUDA_CHECK(cudaEventCreateWithFlags(&o.fork, cudaEventDisableTiming));
+    MNF_CUDA_CHECK(cudaEventCreateWithFlags(&o.join, cudaEventDisableTiming));
+  }
+  *out = &o;
   return MNF_OK;
 }
 
@@ -122,30 +200,75 @@ int mnf_site_sweep(const mnf_site_t* sites, int n_sites, const float* z, int n_p
   // Sites with a specialised kernel (site_sweep.cuh: Poisson with an exp link, Normal with an
   // identity location link and a per-particle scale) run on their own; the rest stay fused.
   mnf_site_t generic[MNF_MAX_FUSED_SITES];
-  int n_generic = 0;
+  int n_generic = 0, n_normal = 0, n_poisson = 0;
+  int normal_idx[MNF_MAX_FUSED_SITES], poisson_idx[MNF_MAX_FUSED_SITES];
   for (int i = 0; i < n_sites; ++i) {
     const int kind = site_fast_kind(sites[i]);
-    if (kind == kFastNone) {
-      generic[n_generic++] = sites[i];
-      continue;
+    if (kind == kFastNone) generic[n_generic++] = sites[i];
+    else if (kind == kFastNormalId) normal_idx[n_normal++] = i;
+    else poisson_idx[n_poisson++] = i;
+  }
+
+  // Workspace plan: the Poisson kernels use the front (per-CTA partial rows of the per-particle
+  // kernel, then the scratch of the moment path); the Normal statistics rows are carved from the
+  // back so that both families can be in flight at once.
+  const int pgrid = (int)std::min<int64_t>((n_chunks + kSweepWarps - 1) / kSweepWarps,
+                                           (int64_t)pois_min_blocks(S <= 32 ? 1 : (S <= 64 ? 2 : 4)) * c->sm_count);
+  const size_t exact_bytes = n_poisson ? ((size_t)pgrid * S * 5 * sizeof(float) + 255) / 256 * 256 : 0;
+  if (exact_bytes > workspace_bytes) return fail(MNF_E_INVALID, "mnf_site_sweep: workspace too small%s%s");
+  size_t back = workspace_bytes / 256 * 256;
+  double* normal_rows[MNF_MAX_FUSED_SITES];
+  int normal_grid[MNF_MAX_FUSED_SITES];
+  bool normal_vec[MNF_MAX_FUSED_SITES];
+  bool disjoint = true;                      // every Normal site got rows of its own behind the Poisson scratch
+  for (int k = 0; k < n_normal; ++k) {
+    normal_grid[k] = normal_stats_grid(sites[normal_idx[k]], &normal_vec[k], c->sm_count);
+    const size_t bytes = ((size_t)normal_grid[k] * kStatCols * sizeof(double) + 255) / 256 * 256;
+    if (back >= bytes && back - bytes >= exact_bytes + ((size_t)1 << 18)) {
+      back -= bytes;
+      normal_rows[k] = reinterpret_cast<double*>(static_cast<char*>(workspace) + back);
+    } else {                                 // small workspace: one shared row block at the front, no overlap
+      disjoint = false;
+      const int64_t fits = (int64_t)(workspace_bytes / (kStatCols * sizeof(double)));
+      if (fits < 1) return fail(MNF_E_INVALID, "mnf_site_sweep: workspace too small%s%s");
+      normal_grid[k] = (int)std::min<int64_t>(normal_grid[k], fits);
+      normal_rows[k] = static_cast<double*>(workspace);
     }
-    if (kind == kFastNormalId) {
-      if (int rc = launch_normal_stats(sites[i], z, S, D, acc, workspace, workspace_bytes, status, c->sm_count, stream))
+  }
+  const bool overlap = disjoint && n_normal > 0 && n_poisson > 0;
+  OverlapStreams* os = nullptr;
+  if (overlap) {
+    if (int rc = overlap_streams(&os)) return rc;
+    MNF_CUDA_CHECK(cudaEventRecord(os->fork, stream));
+    MNF_CUDA_CHECK(cudaStreamWaitEvent(os->side, os->fork, 0));
+    for (int k = 0; k < n_normal; ++k)
+      if (int rc = launch_normal_stats(sites[normal_idx[k]], normal_vec[k], normal_grid[k], normal_rows[k], status, os->side))
         return rc;
-      continue;
-    }
-    const int pgrid = (int)std::min<int64_t>((n_chunks + kSweepWarps - 1) / kSweepWarps,
-                                             (int64_t)pois_min_blocks(S <= 32 ? 1 : (S <= 64 ? 2 : 4)) * c->sm_count);
-    if ((size_t)pgrid * S * 5 * sizeof(float) > workspace_bytes)
-      return fail(MNF_E_INVALID, "mnf_site_sweep: workspace too small%s%s");
-    if (int rc = launch_poisson_exp(sites[i], z, S, D, partial, status, pgrid, stream)) return rc;
+    MNF_CUDA_CHECK(cudaEventRecord(os->join, os->side));
+  }
+  for (int k = 0; k < n_poisson; ++k) {
+    const mnf_site_t& site = sites[poisson_idx[k]];
+    // data-only moment path first; the per-particle kernel runs only if its check fails (device flag)
+    uint32_t* need_exact = nullptr;
+    const size_t scratch_bytes = back - exact_bytes;
+    if (int rc = launch_poisson_moments(site, z, S, D, acc, static_cast<char*>(workspace) + exact_bytes,
+                                        scratch_bytes, status, c->sm_count, stream, &need_exact))
+      return rc;
+    if (int rc = launch_poisson_exp(site, z, S, D, partial, status, need_exact, pgrid, stream)) return rc;
     ColMap fast_map;
     fast_map.n_vec = 0;
     fast_map.vec_lat = 0;
     fast_map.n_scalar = 4;
-    for (int k = 0; k < 16; ++k) fast_map.scalar_lat[k] = -1;
-    site_columns(sites[i], fast_map.scalar_lat);
+    for (int q = 0; q < 16; ++q) fast_map.scalar_lat[q] = -1;
+    site_columns(site, fast_map.scalar_lat);
     if (int rr = launch_reduce(partial, pgrid, S, 5, fast_map, 1.0, D, acc, stream)) return rr;
+  }
+  if (overlap) MNF_CUDA_CHECK(cudaStreamWaitEvent(stream, os->join, 0));
+  for (int k = 0; k < n_normal; ++k) {
+    const mnf_site_t& site = sites[normal_idx[k]];
+    if (!overlap)
+      if (int rc = launch_normal_stats(site, normal_vec[k], normal_grid[k], normal_rows[k], status, stream)) return rc;
+    if (int rc = launch_normal_finish(site, normal_rows[k], normal_grid[k], z, S, D, acc, status, stream)) return rc;
   }
   if (n_generic == 0) return MNF_OK;
   sites = generic;

@@ -11,6 +11,8 @@
 // Up to kMaxSites sites of equal length are fused so shared covariates are read once.
 #pragma once
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mnf {
@@ -267,10 +269,15 @@ constexpr int pois_min_blocks(int q) { return q <= 2 ? 3 : 2; }   // 80 / 128 re
 template <int Q>
 __global__ void __launch_bounds__(kSweepThreads, pois_min_blocks(Q))
 poisson_exp_kernel(mnf_site_t st, const float* __restrict__ z, int S, int D, float* __restrict__ partial,
-                   uint32_t* __restrict__ status) {
+                   uint32_t* __restrict__ status, const uint32_t* __restrict__ need_exact) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t n = st.numel;
   const mnf_link_t L0 = st.param[0];
+  // The moment path below already added this site to the accumulator: hand the reduction zeros.
+  if (need_exact != nullptr && *need_exact == 0u) {
+    for (int idx = threadIdx.x; idx < S * 5; idx += kSweepThreads) partial[(size_t)blockIdx.x * S * 5 + idx] = 0.0f;
+    return;
+  }
 
   extern __shared__ double s_pois[];
   double* s_sums = s_pois;                                          // [warp][Q*32][2]
@@ -440,6 +447,377 @@ template <int Q>
 inline size_t poisson_exp_smem_bytes() {
   return sizeof(double) * kSweepWarps * Q * 32 * 2 + sizeof(double) * kSweepWarps * 4 +
          sizeof(float) * kSweepWarps * 64 + sizeof(float) * 64;
+}
+
+// ---- Poisson(exp(A_s + B_s x)) through data-only Chebyshev moments ------------------------------
+// The irreducible per-particle sums of the kernel above, R_s = sum_i exp(A_s + B_s x_i) and
+// Rx_s = sum_i x_i exp(A_s + B_s x_i), are the moment generating function of the covariate and its
+// derivative. With t = (x - mid) / half in [-1, 1] over the live elements,
+//       exp(B half t) = I_0(B half) + 2 sum_{j>=1} I_j(B half) T_j(t)          (Jacobi-Anger)
+// so   R_s  = exp(A_s + B_s mid) * sum_j w_j(B_s half) mu_j,    mu_j = sum_i T_j(t_i)   (data only)
+//      Rx_s = mid R_s + half exp(A_s + B_s mid) * sum_j w_j'(B_s half) mu_j,  I_j' = (I_{j-1} + I_{j+1}) / 2.
+// The series converges like (B half / 2)^j / j!: kChebMoments = 33 terms leave a truncation below
+// 1e-13 for |B| half <= 8. The sweep therefore does NO per-particle work: a range pass (5 bytes
+// per element) and a moment pass (value 4 + covariate 4 + mask 1 bytes, one FFMA + one FADD per
+// moment and element) whatever S is - the MUFU bound of the kernel above disappears. The finish
+// kernel evaluates the modified Bessel functions per particle in fp64 and CHECKS the expansion
+// (truncation bound and the cancellation sum_j |w_j mu_j| / |sum_j w_j mu_j|) from the data; if any
+// particle fails the check it raises `need_exact` and the kernel above runs instead (launched
+// unconditionally, it returns at once when the flag is clear), so the result never depends on
+// the expansion being applicable.
+constexpr int kChebMoments = 33;                   // T_0 .. T_32
+constexpr int kChebCols = kChebMoments + 4;        // + V, Vx, C, n
+constexpr int kChebThreads = 256;
+constexpr double kChebMaxArg = 12.0;               // |B| half beyond which the exact kernel runs
+constexpr double kChebMaxCancel = 1024.0;          // moments carry ~1e-9 relative error
+constexpr double kChebMaxTrunc = 1e-9;
+
+struct ChebRange {
+  float mid, inv;     // t = (x - mid) * inv
+};
+
+// every CTA reduces the range partials the same way => identical (mid, inv) everywhere
+__device__ __forceinline__ ChebRange cheb_range(const float* __restrict__ range_partial, int n_range, float* s_tmp) {
+  float lo = INFINITY, hi = -INFINITY;
+  for (int b = threadIdx.x; b < n_range; b += blockDim.x) {
+    lo = fminf(lo, range_partial[2 * b]);
+    hi = fmaxf(hi, range_partial[2 * b + 1]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) { s_tmp[2 * warp] = lo; s_tmp[2 * warp + 1] = hi; }
+  __syncthreads();
+  lo = INFINITY; hi = -INFINITY;
+  for (int w = 0; w < nw; ++w) { lo = fminf(lo, s_tmp[2 * w]); hi = fmaxf(hi, s_tmp[2 * w + 1]); }
+  __syncthreads();
+  ChebRange r;
+  if (!(lo <= hi)) { r.mid = 0.0f; r.inv = 0.0f; return r; }      // no live element
+  r.mid = 0.5f * lo + 0.5f * hi;
+  const float half = fmaxf(hi - r.mid, r.mid - lo);
+  r.inv = half > 0.0f ? 1.0f / half : 0.0f;
+  return r;
+}
+
+// min / max of the covariate over the live elements; 128-bit loads (the launcher checks alignment)
+__global__ void __launch_bounds__(kChebThreads)
+poisson_range_kernel(mnf_site_t st, float* __restrict__ range_partial) {
+  const int64_t n = st.numel;
+  const float* __restrict__ xp = st.param[0].x;
+  const uint8_t* __restrict__ mask = st.mask;
+  const int64_t tid = (int64_t)blockIdx.x * kChebThreads + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * kChebThreads;
+  float lo = INFINITY, hi = -INFINITY;
+  auto take = [&](float x, bool live) {
+    if (live) { lo = fminf(lo, x); hi = fmaxf(hi, x); }
+  };
+  const int64_t n4 = n >> 2;
+  for (int64_t g = tid; g < n4; g += nth) {
+    const float4 x4 = __ldg(reinterpret_cast<const float4*>(xp) + g);
+    const uint32_t m4 = mask != nullptr ? __ldg(reinterpret_cast<const uint32_t*>(mask) + g) : 0x01010101u;
+    take(x4.x, (m4 & 0x000000ffu) != 0);
+    take(x4.y, (m4 & 0x0000ff00u) != 0);
+    take(x4.z, (m4 & 0x00ff0000u) != 0);
+    take(x4.w, (m4 & 0xff000000u) != 0);
+  }
+  const int64_t i = (n4 << 2) + tid;
+  if (i < n) take(__ldg(xp + i), mask == nullptr || __ldg(mask + i) != 0);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  __shared__ float s_r[2 * kChebThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_r[2 * warp] = lo; s_r[2 * warp + 1] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kChebThreads / 32; ++w) { lo = fminf(lo, s_r[2 * w]); hi = fmaxf(hi, s_r[2 * w + 1]); }
+    range_partial[2 * blockIdx.x] = lo;
+    range_partial[2 * blockIdx.x + 1] = hi;
+  }
+}
+
+// Number of moments the expansion needs for the largest |B_s| half of this call: the smallest of
+// 13 / 17 / 21 / 25 / 33 with 4 I_{J+1}(arg) exp(arg) <= 1e-10 (truncation relative to the smallest
+// possible rate sum), evaluated the same way by the moment and the finish kernel.
+__device__ __forceinline__ int cheb_moments_needed(const mnf_link_t& L0, const float* __restrict__ z, int S, int D,
+                                                   float inv, float* s_tmp) {
+  float bmax = 0.0f;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const float b = L0.b_const + (L0.b_lat >= 0 ? z[(int64_t)s * D + L0.b_lat] : 0.0f);
+    bmax = b == b ? fmaxf(bmax, fabsf(b)) : INFINITY;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) bmax = fmaxf(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (lane == 0) s_tmp[warp] = bmax;
+  __syncthreads();
+  bmax = 0.0f;
+  for (int w = 0; w < nw; ++w) bmax = fmaxf(bmax, s_tmp[w]);
+  __syncthreads();
+  const float arg = inv > 0.0f ? bmax / inv : 0.0f;
+  if (arg <= 1.5f) return 13;
+  if (arg <= 2.8f) return 17;
+  if (arg <= 4.3f) return 21;
+  if (arg <= 5.9f) return 25;
+  return kChebMoments;
+}
+
+// log v! outside the shared-memory table (v >= 64, or data outside the support): kept out of line
+__device__ __noinline__ float poisson_log_factorial_slow(float v) { return log_factorial(v); }
+
+// per-CTA output row: mu_0 .. mu_32, V = sum v, Vx = sum v x, C = sum log v!, n  (live elements)
+//
+// Four elements per thread and iteration (one 128-bit load each of x and v, four mask bytes) give
+// four independent recurrence chains; the next iteration's loads are issued before the current
+// one is consumed, and the loop is instantiated for each moment count of cheb_moments_needed.
+// Packed FFMA2 / FADD2 were tried and rejected: `tools/f32x2_probe.cu` measures the same 128
+// fp32 lanes per clock and SM for packed and scalar code, and the packed kernel's register pairs
+// cost a third of the occupancy (445 us against 394 us at N = 1e8).
+__global__ void __launch_bounds__(kChebThreads, 3)
+poisson_moment_kernel(mnf_site_t st, const float* __restrict__ range_partial, int n_range,
+                      const float* __restrict__ z, int S, int D,
+                      double* __restrict__ cta_out, uint32_t* __restrict__ status) {
+  extern __shared__ double s_mom[];                     // [kChebMoments + 3][kChebThreads] fp64 running sums
+  __shared__ float s_tmp[2 * kChebThreads / 32];
+  __shared__ float s_logfact[64];
+  __shared__ double s_red[kChebThreads / 32];
+  const int64_t n = st.numel;
+  const float* __restrict__ value = st.value;
+  const float* __restrict__ xp = st.param[0].x;
+  const uint8_t* __restrict__ mask = st.mask;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 64) s_logfact[threadIdx.x] = kLogFactorial[threadIdx.x];
+  const ChebRange range = cheb_range(range_partial, n_range, s_tmp);   // has the block barriers
+  const float mid = range.mid, inv = range.inv;
+  const int n_moments = cheb_moments_needed(st.param[0], z, S, D, inv, s_tmp);
+#pragma unroll
+  for (int j = 0; j < kChebMoments + 3; ++j) s_mom[j * kChebThreads + threadIdx.x] = 0.0;
+
+  float mu[kChebMoments];
+#pragma unroll
+  for (int j = 0; j < kChebMoments; ++j) mu[j] = 0.0f;
+  float f_v = 0.0f, f_vx = 0.0f, f_c = 0.0f;
+  unsigned int cnt = 0;
+  bool bad_value = false;
+  constexpr int kFlushEvery = 32;                       // 128 elements per fp32 running sum
+  const int64_t tid = (int64_t)blockIdx.x * kChebThreads + threadIdx.x;
+  const int64_t nth = (int64_t)gridDim.x * kChebThreads;
+  const int64_t n4 = n >> 2;
+
+  auto run = [&](auto nm_tag) {
+    constexpr int NM = decltype(nm_tag)::value;
+    auto flush = [&]() {
+#pragma unroll
+      for (int j = 0; j < NM; ++j) {
+        s_mom[j * kChebThreads + threadIdx.x] += (double)mu[j];
+        mu[j] = 0.0f;
+      }
+      s_mom[(kChebMoments + 0) * kChebThreads + threadIdx.x] += (double)f_v;
+      s_mom[(kChebMoments + 1) * kChebThreads + threadIdx.x] += (double)f_vx;
+      s_mom[(kChebMoments + 2) * kChebThreads + threadIdx.x] += (double)f_c;
+      f_v = 0.0f; f_vx = 0.0f; f_c = 0.0f;
+    };
+    // dead elements enter with weight 0: the recurrence is linear in (T_0, T_1), so every T_j is 0
+    auto take4 = [&](const float4& x4, const float4& v4, uint32_t m4) {
+      const float x[4] = {x4.x, x4.y, x4.z, x4.w}, v[4] = {v4.x, v4.y, v4.z, v4.w};
+      float w0[4], w1[4], tp[4], cv[4];
+      bool all_small = true;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool live = ((m4 >> (8 * e)) & 0xffu) != 0u;
+        const float xs = live ? x[e] : 0.0f;
+        cv[e] = live ? v[e] : 0.0f;
+        const float t = live ? (x[e] - mid) * inv : 0.0f;
+        w0[e] = live ? 1.0f : 0.0f;
+        w1[e] = t;
+        tp[e] = t + t;
+        cnt += live ? 1u : 0u;
+        f_v += cv[e];
+        f_vx = fmaf(cv[e], xs, f_vx);
+        // integer in [0, 64): 2^23 + cv is exact and carries cv in its low mantissa bits
+        const float big = cv[e] + 8388608.0f;
+        const bool small = cv[e] >= 0.0f && cv[e] < 64.0f && (big - 8388608.0f) == cv[e];
+        f_c += small ? s_logfact[__float_as_uint(big) & 63u] : 0.0f;
+        all_small = all_small && small;
+      }
+      if (!all_small) {                                 // rare: large counts, or data outside the support
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float big = cv[e] + 8388608.0f;
+          if (!(cv[e] >= 0.0f && cv[e] < 64.0f && (big - 8388608.0f) == cv[e])) {
+            if (!in_support(MNF_POISSON, cv[e])) bad_value = true;
+            f_c += poisson_log_factorial_slow(cv[e]);
+          }
+        }
+      }
+      mu[0] += (w0[0] + w0[1]) + (w0[2] + w0[3]);
+      mu[1] += (w1[0] + w1[1]) + (w1[2] + w1[3]);
+#pragma unroll
+      for (int j = 2; j < NM; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float wn = fmaf(tp[e], w1[e], -w0[e]);
+          w0[e] = w1[e];
+          w1[e] = wn;
+        }
+        mu[j] += (w1[0] + w1[1]) + (w1[2] + w1[3]);
+      }
+    };
+    auto fetch = [&](int64_t g, float4& x4, float4& v4, uint32_t& m4) {
+      if (g < n4) {
+        x4 = __ldg(reinterpret_cast<const float4*>(xp) + g);
+        v4 = __ldg(reinterpret_cast<const float4*>(value) + g);
+        m4 = mask != nullptr ? __ldg(reinterpret_cast<const uint32_t*>(mask) + g) : 0x01010101u;
+      } else {
+        m4 = 0u;
+      }
+    };
+    float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f), v4 = x4, nx4 = x4, nv4 = x4;
+    uint32_t m4 = 0u, nm4 = 0u;
+    int pending = 0;
+    fetch(tid, x4, v4, m4);
+    for (int64_t g = tid; g < n4; g += nth) {
+      fetch(g + nth, nx4, nv4, nm4);             // in flight while this group is consumed
+      take4(x4, v4, m4);
+      if (++pending == kFlushEvery) { flush(); pending = 0; }
+      x4 = nx4; v4 = nv4; m4 = nm4;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) {   // ragged tail: at most three elements, one warp
+      const int64_t i = (n4 << 2) + threadIdx.x;
+      const bool inb = i < n;
+      const float4 tx = make_float4(inb ? __ldg(xp + i) : 0.0f, 0.0f, 0.0f, 0.0f);
+      const float4 tv = make_float4(inb ? __ldg(value + i) : 0.0f, 0.0f, 0.0f, 0.0f);
+      take4(tx, tv, (inb && (mask == nullptr || __ldg(mask + i) != 0)) ? 1u : 0u);
+    }
+    flush();
+  };
+  switch (n_moments) {
+    case 13: run(std::integral_constant<int, 13>{}); break;
+    case 17: run(std::integral_constant<int, 17>{}); break;
+    case 21: run(std::integral_constant<int, 21>{}); break;
+    case 25: run(std::integral_constant<int, 25>{}); break;
+    default: run(std::integral_constant<int, kChebMoments>{}); break;
+  }
+  __syncthreads();
+  // column j: warp (j mod 8) adds the 256 thread slots in fixed order
+  double* out = cta_out + (size_t)blockIdx.x * kChebCols;
+  for (int j = warp; j < kChebMoments + 3; j += kChebThreads / 32) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < kChebThreads / 32; ++k) t += s_mom[j * kChebThreads + k * 32 + lane];
+    t = warp_sum(t);
+    if (lane == 0) out[j] = t;
+  }
+  const double c = warp_sum((double)cnt);
+  if (lane == 0) s_red[warp] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kChebThreads / 32; ++w) t += s_red[w];
+    out[kChebMoments + 3] = t;
+  }
+  if (bad_value) atomicOr(status, MNF_ST_BAD_VALUE);
+}
+
+inline size_t poisson_moment_smem_bytes() { return sizeof(double) * (kChebMoments + 3) * kChebThreads; }
+
+// modified Bessel functions I_0(b) .. I_{jmax}(b), 0 <= b <= kChebMaxArg: Miller's downward
+// recurrence p_{j-1} = p_{j+1} + (2j / b) p_j from j = jmax + 24, normalised with
+// exp(b) = I_0 + 2 sum_{j>=1} I_j; below b = 1e-2 the leading terms of the power series.
+__device__ inline void bessel_i(double b, int jmax, double* out) {
+  if (b < 1e-2) {
+    const double h = 0.5 * b, q = h * h;
+    double pref = 1.0;
+    for (int j = 0; j <= jmax; ++j) {
+      if (j > 0) pref *= h / (double)j;
+      out[j] = pref * (1.0 + q / (double)(j + 1) * (1.0 + q / (2.0 * (double)(j + 2))));
+    }
+    return;
+  }
+  const double two_over_b = 2.0 / b;
+  double p_hi = 0.0, p = 1e-250, sum = 0.0;     // (2j/b)^(jmax+24) <= 1e4^57: no overflow
+  for (int j = jmax + 24; j >= 1; --j) {
+    const double p_lo = p_hi + (double)j * two_over_b * p;
+    sum += p;                                   // p = p_j
+    if (j <= jmax) out[j] = p;
+    p_hi = p;
+    p = p_lo;
+  }
+  out[0] = p;
+  const double norm = exp(b) / (p + 2.0 * sum);
+  for (int j = 0; j <= jmax; ++j) out[j] *= norm;
+}
+
+// One block: sum the CTA rows in fixed order, evaluate the expansion per particle, check it, and
+// either add the site to the step accumulator (need_exact = 0) or leave it to the exact kernel.
+__global__ void __launch_bounds__(kChebThreads)
+poisson_moment_finish_kernel(mnf_site_t st, const double* __restrict__ cta_rows, int n_cta,
+                             const float* __restrict__ range_partial, int n_range,
+                             const float* __restrict__ z, int S, int D, double* __restrict__ acc,
+                             uint32_t* __restrict__ need_exact) {
+  __shared__ double s_tot[kChebCols];
+  __shared__ float s_tmp[2 * kChebThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const ChebRange range = cheb_range(range_partial, n_range, s_tmp);
+  const int nm = cheb_moments_needed(st.param[0], z, S, D, range.inv, s_tmp);     // moments the sweep kept
+  for (int c = warp; c < kChebCols; c += kChebThreads / 32) {
+    double t = 0.0;
+    for (int b = lane; b < n_cta; b += 32) t += cta_rows[(size_t)b * kChebCols + c];
+    t = warp_sum(t);
+    if (lane == 0) s_tot[c] = t;
+  }
+  __syncthreads();
+  const double V = s_tot[kChebMoments], Vx = s_tot[kChebMoments + 1], C = s_tot[kChebMoments + 2];
+  const double cnt = s_tot[kChebMoments + 3];
+  const double mid = (double)range.mid, half = range.inv > 0.0f ? 1.0 / (double)range.inv : 0.0;
+  const mnf_link_t L0 = st.param[0];
+
+  bool ok = true;
+  double lp = 0.0, dA = 0.0, dB = 0.0;
+  const int s = threadIdx.x;
+  if (s < S) {
+    const float* zs = z + (int64_t)s * D;
+    const double a_s = (double)(L0.a_const + (L0.a_lat >= 0 ? zs[L0.a_lat] : 0.0f));
+    const double b_s = (double)(L0.b_const + (L0.b_lat >= 0 ? zs[L0.b_lat] : 0.0f));
+    const double arg = b_s * half;
+    ok = fabs(arg) <= kChebMaxArg && isfinite(a_s);          // false for NaN / inf too
+    if (ok) {
+      double f[kChebMoments + 1];                            // f_j = sign^j I_j(|arg|), j = 0 .. J + 1
+      bessel_i(fabs(arg), kChebMoments, f);
+      if (arg < 0.0)
+        for (int j = 1; j <= kChebMoments; j += 2) f[j] = -f[j];
+      double s0 = f[0] * s_tot[0], mag = fabs(s0);
+      double s1 = f[1] * s_tot[0];
+      for (int j = 1; j < nm; ++j) {
+        const double term = 2.0 * f[j] * s_tot[j];
+        s0 += term;
+        mag += fabs(term);
+        s1 += (f[j - 1] + f[j + 1]) * s_tot[j];
+      }
+      // |T_j| <= 1: the dropped tail is at most 2 n sum_{j > J} I_j, dominated by its first term
+      const double tail = 4.0 * fabs(f[nm]) * cnt;
+      ok = cnt == 0.0 || (s0 > 0.0 && mag <= kChebMaxCancel * s0 && tail <= kChebMaxTrunc * s0);
+      const double base = exp(a_s + b_s * mid);
+      const double R = base * s0, Rx = mid * R + half * base * s1;
+      ok = ok && isfinite(R) && isfinite(Rx);
+      lp = a_s * V + b_s * Vx - R - C;
+      dA = V - R;
+      dB = Vx - Rx;
+    }
+  }
+  const int any_bad = __syncthreads_or(ok ? 0 : 1);
+  if (threadIdx.x == 0) *need_exact = any_bad ? 1u : 0u;
+  if (any_bad || s >= S) return;
+  const double w = st.scale;
+  double* as = acc + (int64_t)s * (D + 1);
+  atomicAdd(as, w * lp);
+  if (L0.a_lat >= 0) atomicAdd(as + 1 + L0.a_lat, w * dA);
+  if (L0.b_lat >= 0) atomicAdd(as + 1 + L0.b_lat, w * dB);
 }
 
 // ---- Normal(A_s + B_s x, sigma_s): data-only sufficient statistics -------------------------------

@@ -313,6 +313,41 @@ def test_minibatch_stream_rebinds_the_plan_instead_of_retracing():
         stream(mininf.condition(model, **staging), approx, _noise=noise)
 
 
+def test_host_batch_stream_feeds_the_rebound_plan():
+    """Out-of-core feed (examples/minibatch.md:68-88 with the data in host memory): batches staged
+    through the double-buffered ring give exactly the losses of conditioning on device slices, the
+    ragged last batch included, in natural and in shuffled order, without retracing."""
+    from mininf_b200.stream import HostBatchStream
+    S, p, rows, total = 4, 64, 4096, 3 * 4096 + 1000
+    full = configs.logistic(total, total, p=p, device="cpu", intercept=True)
+    host = {k: v for k, v in full.data.items()}
+    torch.manual_seed(5)
+    approx, _ = full.approximation(device=DEV)
+    noise = {name: elbo.draw_noise(dist, S).to(DEV) for name, dist in approx.items()}
+
+    def model():
+        return full.model(mininf)
+
+    def direct(lo, hi):
+        module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+        data = {k: v[lo:hi].to(DEV) for k, v in host.items()}
+        return float(module(mininf.condition(model, **data), approx, _noise=noise))
+
+    expected = [direct(lo, min(lo + rows, total)) for lo in range(0, total, rows)]
+    for order in (None, torch.tensor([2, 0, 3, 1])):
+        feed = HostBatchStream(host, rows, device=DEV, depth=2, order=order)
+        assert len(feed) == 4 and feed.bytes_per_batch == rows * (p * 4 + 4)
+        module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+        got, plans = [], []
+        for batch in feed:
+            got.append(float(module(mininf.condition(model, **batch), approx, _noise=noise)))
+            plans.append(module.last_plan)
+        want = expected if order is None else [expected[i] for i in order.tolist()]
+        assert got == want
+        full_plans = [plan for plan, index in zip(plans, range(4) if order is None else order.tolist()) if index != 3]
+        assert all(plan is full_plans[0] for plan in full_plans)      # full batches share one rebound plan
+
+
 def test_graphed_step_trains_like_the_eager_loop():
     """`GraphedStep` replays the whole SVI step from one CUDA graph: every replay draws new Philox
     noise (device-side call index), parameters move, and the fit matches the eager README loop."""
@@ -627,6 +662,131 @@ def test_normal_site_sufficient_statistics(n, offset, masked, covariate, misalig
     assert abs(float(loss) - float(expected)) <= 1e-5 * abs(float(expected))
     for key, leaf in leaves.items():
         np.testing.assert_allclose(leaf.grad.cpu().numpy(), leaves64[key].grad.numpy(), rtol=3e-4, atol=2e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# Poisson(exp(a + b x)) sites through the Chebyshev-moment sweep (csrc/site_sweep.cuh::
+# poisson_moment_kernel) with its device-side fallback to the per-particle kernel
+# ---------------------------------------------------------------------------------------------
+def _poisson_site_case(n, x_scale=1.0, x_shift=0.0, b_loc=0.5, masked=True, misalign=0, seed=0, constant_x=False):
+    from torch.distributions import Normal, Poisson
+    g = torch.Generator().manual_seed(seed)
+    x64 = x_shift + x_scale * torch.randn(n + misalign, generator=g, dtype=torch.float64)
+    if constant_x:
+        x64 = torch.full_like(x64, 0.75)
+    x32 = x64.float()
+    x64 = x32.double()
+    counts = torch.poisson(torch.exp((0.3 + b_loc * x64).clamp(max=8.0)), generator=g)
+    mask = torch.rand(n + misalign, generator=g) > 0.3
+
+    def make(xv, device, dtype):
+        xv, cv, mv = xv.to(device)[misalign:], counts.to(device=device, dtype=dtype)[misalign:], mask.to(device)[misalign:]
+
+        def model(m):
+            a = m.sample("a", Normal(0, 1))
+            b = m.sample("b", Normal(0, 1))
+            m.sample("counts", Poisson((a + b * xv).exp()))
+
+        return model, {"counts": torch.masked.as_masked_tensor(cv, mv) if masked else cv}
+
+    families = {"a": (Normal, {"loc": torch.tensor(0.25), "scale": torch.tensor(0.1)}),
+                "b": (Normal, {"loc": torch.tensor(b_loc), "scale": torch.tensor(0.1)})}
+    return make, x64, x32, families
+
+
+def _poisson_site_eval(make, x64, x32, families, S, seed):
+    torch.manual_seed(seed)
+    cpu = configs.Config("poisson_site", None, {}, families)
+    approx64, leaves64 = cpu.approximation(dtype=torch.float64)
+    noise = {name: elbo.draw_noise(dist, S) for name, dist in approx64.items()}
+    model64, cond64 = make(x64, "cpu", torch.float64)
+    expected = elbo.neg_elbo(lambda m: model64(m), cond64, approx64, noise, S)
+    expected.backward()
+    model32, cond32 = make(x32, DEV, torch.float32)
+    approx, leaves = cpu.approximation(device=DEV)
+    loss_module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+    loss = loss_module(mininf.condition(lambda: model32(mininf), **cond32), approx,
+                       _noise={k: v.float().to(DEV) for k, v in noise.items()})
+    loss.backward()
+    assert len(loss_module.last_plan.sweep_groups) == 1
+    return float(loss), {k: v.grad.cpu().numpy() for k, v in leaves.items()}, float(expected), \
+        {k: v.grad.numpy() for k, v in leaves64.items()}
+
+
+@pytest.mark.parametrize("n,kwargs", [
+    (4096, {}),                                   # moment path, whole float4 groups
+    (4099, {}),                                   # ragged tail of three elements
+    (5000, {"masked": False}),                    # no mask
+    (5001, {"misalign": 1}),                      # misaligned views: per-particle kernel
+    (60_001, {"b_loc": -0.8}),                    # negative slope: alternating Bessel weights
+    (30_000, {"x_scale": 0.01, "x_shift": 40.0, "b_loc": 0.05}),   # narrow range far from the origin
+    (3000, {"constant_x": True}),                 # zero-width range
+    (20_000, {"x_scale": 12.0, "b_loc": 0.4}),    # |b| * half-range > 12: the device check falls back
+])
+def test_poisson_site_moment_sweep_against_float64_oracle(n, kwargs):
+    """R_s = sum exp(a_s + b_s x_i) and its x-weighted twin come from 33 data-only Chebyshev
+    moments (or, when the in-kernel check rejects the expansion, from the per-particle kernel);
+    either way they must agree with a float64 evaluation of the reference algorithm."""
+    make, x64, x32, families = _poisson_site_case(n, seed=n, **kwargs)
+    loss, grads, expected, grads64 = _poisson_site_eval(make, x64, x32, families, S=16, seed=n)
+    assert abs(loss - expected) <= 1e-5 * abs(expected)
+    for key in grads:
+        np.testing.assert_allclose(grads[key], grads64[key], rtol=3e-4, atol=2e-3 + 1e-6 * abs(expected))
+
+
+def test_poisson_site_moment_sweep_agrees_with_per_particle_kernel(monkeypatch):
+    """A/B on identical inputs: the moment path against the MUFU kernel (MNF_POISSON_EXACT=1),
+    N = 3e6, S = 64, both within 2e-6 of each other on the loss and 2e-5 on the gradients."""
+    make, x64, x32, families = _poisson_site_case(3_000_000, seed=5)
+
+    def run():
+        torch.manual_seed(11)
+        cfg = configs.Config("poisson_site", None, {}, families)
+        approx, leaves = cfg.approximation(device=DEV)
+        gen = torch.Generator().manual_seed(3)
+        noise = {k: torch.randn(64, generator=gen).to(DEV) for k in families}
+        model32, cond32 = make(x32, DEV, torch.float32)
+        loss = mininf.nn.EvidenceLowerBoundLoss(64, check="sync")(
+            mininf.condition(lambda: model32(mininf), **cond32), approx, _noise=noise)
+        loss.backward()
+        return float(loss), torch.stack([v.grad for v in leaves.values()]).double().cpu()
+
+    monkeypatch.delenv("MNF_POISSON_EXACT", raising=False)
+    fast = run()
+    again = run()
+    assert fast[0] == again[0] and torch.equal(fast[1], again[1])          # fixed-order reductions
+    monkeypatch.setenv("MNF_POISSON_EXACT", "1")
+    exact = run()
+    assert abs(fast[0] - exact[0]) <= 2e-6 * abs(exact[0])
+    assert float((fast[1] - exact[1]).norm() / exact[1].norm()) < 2e-5
+
+
+def test_poisson_site_moment_sweep_flags_invalid_counts_and_propagates_nan_covariates():
+    """The per-step device checks of the moment path: a count outside the Poisson support raises
+    like the reference's validation; a NaN covariate makes the expansion check fail on the device,
+    the per-particle kernel takes over and the non-finite loss is reported."""
+    from torch.distributions import Normal, Poisson
+    n = 8192
+    x = torch.randn(n, device=DEV)
+    counts = torch.poisson(torch.exp(0.2 + 0.3 * x))
+    approx = {"a": Normal(torch.tensor(0.1, device=DEV), torch.tensor(0.1, device=DEV)),
+              "b": Normal(torch.tensor(0.3, device=DEV), torch.tensor(0.1, device=DEV))}
+
+    def model():
+        a = mininf.sample("a", Normal(0, 1))
+        b = mininf.sample("b", Normal(0, 1))
+        mininf.sample("counts", Poisson((a + b * x).exp()))
+
+    module = mininf.nn.EvidenceLowerBoundLoss(8, check="sync")
+    assert torch.isfinite(module(mininf.condition(model, counts=counts), approx))
+    counts[17] = 2.5                  # same tensors (cached plan), now with a non-integer count
+    with pytest.raises(ValueError, match="support"):
+        module(mininf.condition(model, counts=counts), approx)
+    counts[17] = 2.0
+    assert torch.isfinite(module(mininf.condition(model, counts=counts), approx))
+    x[5] = float("nan")
+    with pytest.raises(ValueError, match="not finite"):
+        module(mininf.condition(model, counts=counts), approx)
 
 
 # ---------------------------------------------------------------------------------------------
