@@ -352,6 +352,8 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if distributed:
+        # keep stdout to the one JSON line: NCCL's version / debug banner goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     w = WORKLOADS[args.workload]
