@@ -352,9 +352,20 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if distributed:
-        # keep stdout to the one JSON line: NCCL's version / debug banner goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=device)
+        # Keep stdout to the one JSON line: with NCCL_DEBUG set, NCCL printf()s its version banner
+        # to stdout while the communicator comes up, so fd 1 points at stderr until it has.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            warm = torch.zeros(1, device=device)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     w = WORKLOADS[args.workload]
     P, S = w.p, w.particles
@@ -400,23 +411,28 @@ def run_b200(args):
         eager_step()
     fence()
     plan = loss_module.last_plan
-    # Roofline numerator: per-launch duration of the dense sweep from CUDA events recorded around
-    # the launch on its stream, averaged over eager steps on the same resident data (events inside
-    # a graph replay cannot be timed; the kernel and its arguments are identical).
-    plan.sweep_events.clear()
-    plan.sweep_event_kinds.clear()
-    plan.record_sweep_events = True
-    eager_begin, eager_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eager_begin.record()
-    for _ in range(args.steps):
-        eager_step()
-    eager_end.record()
-    fence()
-    plan.record_sweep_events = False
-    timed = [b.elapsed_time(e) for (b, e), kind in zip(plan.sweep_events, plan.sweep_event_kinds)
-             if kind == w.event_kind]
-    kernel_ms = sum(timed) / max(len(timed), 1)
-    eager_ms_per_step = eager_begin.elapsed_time(eager_end) / args.steps
+
+    # Roofline numerator: per-launch duration of the workload's sweep call from CUDA events recorded
+    # around the launch on its stream, averaged over eager steps on the same resident data (events
+    # inside a graph replay cannot be timed; the kernel and its arguments are identical). Under the
+    # power cap the SM clock drifts over a run, so the measurement is taken right before AND right
+    # after the timed region and both halves are averaged.
+    def measure_sweep(steps):
+        plan.sweep_events.clear()
+        plan.sweep_event_kinds.clear()
+        plan.record_sweep_events = True
+        begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        begin.record()
+        for _ in range(steps):
+            eager_step()
+        end.record()
+        fence()
+        plan.record_sweep_events = False
+        timed = [b.elapsed_time(e) for (b, e), kind in zip(plan.sweep_events, plan.sweep_event_kinds)
+                 if kind == w.event_kind]
+        return sum(timed) / max(len(timed), 1), begin.elapsed_time(end) / steps
+
+    kernel_ms_before, eager_ms_per_step = measure_sweep(args.steps)
 
     # The SVI step is recorded once into a CUDA graph (mininf_b200.nn.GraphedStep) and replayed:
     # the same kernels in the same order, one launch per step. Sharded runs keep the eager loop:
@@ -452,6 +468,8 @@ def run_b200(args):
         elapsed_ms = float(t)
     ms_per_step = elapsed_ms / args.steps
     value = n_rows * world * S / (ms_per_step * 1e-3)
+    kernel_ms_after, _ = measure_sweep(args.steps)
+    kernel_ms = 0.5 * (kernel_ms_before + kernel_ms_after)
 
     # ---- end to end: host buffers, H2D of the step's inputs and D2H of its result every step ----
     e2e = None
@@ -501,8 +519,10 @@ def run_b200(args):
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_source,
                          "kernel": w.kernel,
                          "kernel_ms": kernel_ms, "algorithmic_bytes": algorithmic_bytes,
-                         "kernel_timing": f"CUDA events around each launch, {args.steps} eager steps run "
-                                          "right before the timed region on the same data",
+                         "kernel_ms_before_after": [kernel_ms_before, kernel_ms_after],
+                         "kernel_timing": f"CUDA events around each launch, {args.steps} eager steps right "
+                                          f"before and {args.steps} right after the timed region on the "
+                                          "same data, averaged",
                          **({"note": w.bound_note} if w.bound_note else {})},
             "eager_ms_per_step": eager_ms_per_step,
             "cpu_baseline": cpu_baseline,

@@ -80,6 +80,15 @@ def _has_fast_sweep(site: abi.Site) -> bool:
         (site.family == abi.NORMAL and first.transform == abi.T_ID and not second.x)
 
 
+def _has_moment_path(site: abi.Site) -> bool:
+    """Poisson(exp) site whose layout qualifies for the Chebyshev-moment kernels
+    (csrc/site.cu::launch_poisson_moments): unit-stride covariate, 16-byte aligned data."""
+    first = site.param[0]
+    if not (site.family == abi.POISSON and first.transform == abi.T_EXP and first.x and first.x_stride == 1):
+        return False
+    return first.x % 16 == 0 and (site.value or 0) % 16 == 0 and (site.mask or 0) % 4 == 0
+
+
 class Plan:
     """Everything one ELBO step needs, resolved to device pointers."""
 
@@ -526,6 +535,8 @@ class Plan:
             # sites with a specialised kernel run on their own (csrc/site_sweep.cuh::site_fast_kind)
             fast = sum(1 for i in range(len(group)) if _has_fast_sweep(group[i]))
             count += 2 * fast + (2 if fast < len(group) else 0)
+            # range + moment + finish kernels in front of the (skipped) per-particle kernel
+            count += 3 * sum(1 for i in range(len(group)) if _has_moment_path(group[i]))
         count += sum(1 + -(-self.S // 32) for _ in self.row_groups)
         count += (self.small_observed is not None) + (self.small_global is not None)
         return count
