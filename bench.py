@@ -377,7 +377,7 @@ def run_b200(args):
     streaming = w.n_batches > 1
     # fused=True: torch's single-kernel Adam (the foreach default issues six passes over every
     # parameter, which shows at C4's 6.4e8 variational parameters)
-    optimizer = torch.optim.Adam(parameters, lr=0.01, capturable=not (args.eager or streaming), fused=True)
+    optimizer = torch.optim.Adam(parameters, lr=0.01, capturable=not args.eager, fused=True)
     loss_module = mininf.nn.EvidenceLowerBoundLoss(S, dense_precision="tf32",
                                                    process_group=True if distributed else None)
     model = model_factory(mininf, w, n_rows, batches[0])
@@ -435,15 +435,31 @@ def run_b200(args):
     kernel_ms_before, eager_ms_per_step = measure_sweep(args.steps)
 
     # The SVI step is recorded once into a CUDA graph (mininf_b200.nn.GraphedStep) and replayed:
-    # the same kernels in the same order, one launch per step. Sharded runs keep the eager loop:
-    # capturing the NCCL all-reduce of this torch/NCCL build into the graph hung on 2 GPUs.
-    graphed = not args.eager and not distributed and not streaming
+    # the same kernels in the same order, one launch per step. The minibatch stream (c3) records
+    # one graph per resident batch - the pattern for a ring of staging buffers: conditioned tensors
+    # are baked into a graph by address - and replays them in turn; all graphs share the
+    # parameters and the optimizer. Sharded runs keep the eager loop: capturing the NCCL
+    # all-reduce of this torch/NCCL build into the graph hung on 2 GPUs.
+    graphed = not args.eager and not distributed
     step, graph_note = eager_step, None
     if graphed:
         try:
-            step = mininf.nn.GraphedStep(loss_module, conditioned, approximation, optimizer)
+            if streaming:
+                replays = []
+                for batch in batches:
+                    module_b = mininf.nn.EvidenceLowerBoundLoss(S, dense_precision="tf32")
+                    replays.append(mininf.nn.GraphedStep(module_b, condition_on(mininf, model, w, batch),
+                                                         approximation, optimizer))
+
+                def step():
+                    replay = replays[calls[0] % len(replays)]
+                    calls[0] += 1
+                    return replay()
+            else:
+                step = mininf.nn.GraphedStep(loss_module, conditioned, approximation, optimizer)
         except Exception as error:  # noqa: BLE001  keep measuring: the eager loop runs the same kernels
             graphed, graph_note = False, f"CUDA graph capture failed ({type(error).__name__}); eager launches"
+            step = eager_step
             torch.cuda.synchronize()
     for _ in range(max(args.warmup, 3)):
         step()
@@ -474,7 +490,7 @@ def run_b200(args):
     # ---- end to end: host buffers, H2D of the step's inputs and D2H of its result every step ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, w, step, batches, n_rows, world, device, fence, distributed)
+        e2e = run_e2e(args, w, step, batches, calls, n_rows, world, device, fence, distributed)
 
     if rank == 0:
         peak, peak_source = measured_peak_gbs()
@@ -506,10 +522,12 @@ def run_b200(args):
                        "features": P, "particles": S, "parallelism": f"row shards x{world}, one all-reduce/step",
                        "l2": f"inputs ({n_rows * w.bytes_per_row / 1e9:.1f} GB per step and GPU) far exceed the "
                              "126 MB L2; no flush needed",
-                       "stream": (f"{w.n_batches} resident batches alternate; the cached plan is rebound to "
-                                  "each batch (no retrace)") if streaming else "one resident data set",
+                       "stream": (f"{w.n_batches} resident batches alternate" +
+                                  ("; one recorded step per batch buffer, replayed in turn" if graphed else
+                                   "; the cached plan is rebound to each batch (no retrace)"))
+                       if streaming else "one resident data set",
                        "step": "zero_grad + ELBO/grad kernels + backward + Adam" +
-                               (", replayed from one CUDA graph (GraphedStep)" if graphed
+                               (", replayed from a CUDA graph (GraphedStep)" if graphed
                                 else ", " + (graph_note or "eager launches")),
                        "final_loss": final_loss},
             "clocks": clocks,
@@ -533,7 +551,7 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, w, step, batches, n_rows, world, device, fence, distributed):
+def run_e2e(args, w, step, batches, calls, n_rows, world, device, fence, distributed):
     """Same step, but the inputs live in pinned host memory and are copied to the device inside
     the timed region every step; the loss is read back to the host every step."""
     import psutil
@@ -561,7 +579,7 @@ def run_e2e(args, w, step, batches, n_rows, world, device, fence, distributed):
         # every input byte of the step crosses PCIe into the buffers the step reads; if the
         # pinned buffer is smaller than the data set it is sent repeatedly until all n_rows rows
         # have been overwritten
-        target = batches[i % len(batches)]
+        target = batches[calls[0] % len(batches)]      # the batch buffer the next step reads
         for lo in range(0, n_rows, rows):
             m = min(rows, n_rows - lo)
             for k in names:
