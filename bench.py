@@ -53,7 +53,8 @@ class Workload:
 
 WORKLOADS = {
     "c2": Workload("c2", "bayesian_linear_regression_p64_N1e8_S64", 64, 64, 100_000_000, "normal", None, 1,
-                   "mnf::tc::dense_tc_kernel<Normal> (+ its 5 us partial-sum reduction)", "dense_tc_traffic.json"),
+                   "mnf::gram::dense_gram_kernel (+ gram_reduce / gram_finish / reduce_partials, ~15 us together)",
+                   "dense_gram_traffic.json"),
     "c3": Workload("c3", "minibatch_logistic_regression_p256_batch1e7_of_N1e9_S16", 256, 16, 10_000_000,
                    "bernoulli", 1_000_000_000, 2,
                    "mnf::tcr::dense_tcr_kernel<BernoulliLogits, 16> (+ its partial-sum reduction)",

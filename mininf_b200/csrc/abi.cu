@@ -70,7 +70,8 @@ size_t mnf_workspace_bytes(int n_particles, int n_latent_total, int device) {
   const size_t ncol = (size_t)std::max(n_latent_total + 3, 1 + 4 * MNF_MAX_FUSED_SITES);
   // + the moment path's scratch (range partials, moment rows, flag word: < 256 KB) and one block of
   // statistics rows per Normal site (< 64 KB each), so both can be in flight at once (csrc/site.cu)
-  return (size_t)max_ctas(*c) * (size_t)n_particles * ncol * sizeof(float) + ((size_t)1 << 20);
+  return (size_t)max_ctas(*c) * (size_t)n_particles * ncol * sizeof(float) + ((size_t)1 << 20) +
+         (size_t)c->sm_count * 4400 * sizeof(float);   // + per-CTA Gram statistics (csrc/dense_gram.cuh)
 }
 
 int mnf_rsample(const mnf_latent_t* latents_dev, int n_latents, int n_particles, int n_latent_total,

@@ -4,6 +4,7 @@
 #include "dense_simt.cuh"
 #include "dense_tc.cuh"
 #include "dense_tcr.cuh"
+#include "dense_gram.cuh"
 
 using namespace mnf;
 
@@ -59,6 +60,42 @@ int launch_dense_tc(const mnf_dense_site_t& site, const float* z, int S, int D, 
                                       (int)tc::kSmemBytes));
   kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_k, map_mn, site, z, S, D, partial, status);
   MNF_CUDA_CHECK(cudaGetLastError());
+  return MNF_OK;
+}
+
+// Normal family, p = 64, no mask: data-only Gram statistics (dense_gram.cuh). Workspace: per-CTA
+// statistics, their fp64 totals, then one row block [S][1 + p + 2] for the common reduction.
+// MNF_DENSE_NO_GRAM=1 keeps the per-particle kernel (developer A/B switch).
+bool gram_disabled() {
+  const char* v = std::getenv("MNF_DENSE_NO_GRAM");
+  return v != nullptr && v[0] != '\0' && v[0] != '0';
+}
+
+size_t gram_workspace_bytes(int grid, int S) {
+  return ((size_t)grid * gram::kCtaFloats * sizeof(float) + 255) / 256 * 256 +
+         ((size_t)gram::kCtaFloats * sizeof(double) + 255) / 256 * 256 + (size_t)S * (1 + tc::kP + 2) * sizeof(float);
+}
+
+int launch_dense_gram(const mnf_dense_site_t& site, const float* z, int S, int D, void* workspace, float** rows_out,
+                      uint32_t* status, int grid, cudaStream_t stream) {
+  CUtensorMap map_mn;
+  if (int rc = make_x_map(site, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, &map_mn)) return rc;
+  char* ws = static_cast<char*>(workspace);
+  float* cta_out = reinterpret_cast<float*>(ws);
+  const size_t off_total = ((size_t)grid * gram::kCtaFloats * sizeof(float) + 255) / 256 * 256;
+  double* total = reinterpret_cast<double*>(ws + off_total);
+  float* rows = reinterpret_cast<float*>(ws + off_total + ((size_t)gram::kCtaFloats * sizeof(double) + 255) / 256 * 256);
+  MNF_CUDA_CHECK(cudaFuncSetAttribute(gram::dense_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)gram::kSmemBytes));
+  const char* dev = std::getenv("MNF_GRAM_DEV_SKIP");   // timing experiments only (dense_gram.cuh)
+  const uint32_t dev_skip = dev != nullptr ? (uint32_t)std::atoi(dev) : 0u;
+  gram::dense_gram_kernel<<<grid, gram::kThreads, gram::kSmemBytes, stream>>>(map_mn, site, cta_out, status, dev_skip);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  gram::gram_reduce_kernel<<<(gram::kCtaFloats + 255) / 256, 256, 0, stream>>>(cta_out, grid, total);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  gram::gram_finish_kernel<<<S, tc::kP, 0, stream>>>(site, total, z, S, D, rows, status);
+  MNF_CUDA_CHECK(cudaGetLastError());
+  *rows_out = rows;
   return MNF_OK;
 }
 
@@ -190,6 +227,12 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
     if ((size_t)grid * S * ncol * sizeof(float) > workspace_bytes)
       return fail(MNF_E_INVALID, "mnf_dense_sweep: workspace too small%s%s");
     int rc;
+    if (c2_shape && s.family == MNF_NORMAL && s.mask == nullptr && !gram_disabled() &&
+        gram_workspace_bytes(grid, S) <= workspace_bytes) {
+      float* rows = nullptr;
+      if (int rg = launch_dense_gram(s, z, S, D, workspace, &rows, status, grid, stream)) return rg;
+      return launch_reduce(rows, 1, S, ncol, map, s.weight, D, acc, stream);
+    }
     if (c2_shape) {
       if (s.family == MNF_NORMAL)
         rc = has_icpt ? launch_dense_tc<MNF_NORMAL, true>(s, z, S, D, partial, status, grid, stream)

@@ -1,0 +1,361 @@
+// Normal likelihood with a dense linear predictor and a row-independent scale, p = 64, no mask:
+// the sweep reduced to DATA-ONLY Gram statistics (the move site_sweep.cuh makes for scalar links).
+//
+//   sum_i (y_i - a - x_i.theta)^2 = Syy - 2 a Sy + n a^2 - 2 theta.(b - a sx) + theta' A theta
+//   A = X'X [64 x 64],  b = X'y,  sx = X'1,  Sy = sum y,  Syy = sum y^2,  n = rows
+//
+// so log p, d/dtheta = (b - a sx - A theta) / sigma^2, d/da and d/dsigma of EVERY particle follow
+// from one pass over X that does no per-particle work (gram_finish_kernel evaluates the closed
+// forms in fp64). Replaces, like dense_tc.cuh: aten::mv + MvBackward + Normal.log_prob and its
+// autograd twins (mininf/core.py:241, TORCH normal.py:87-103) for all S particles.
+//
+// Tensor work per 128-row tile: 16 tcgen05.mma kind::tf32 of M = N = 64, K = 8 whose A AND B
+// operand are the SAME MN-major shared-memory image (A = X' needs the feature index contiguous,
+// B = X too) - 2 N p^2 flop per step instead of 4 N p S, one TMA image per tile instead of two,
+// no TMEM epilogue. X is rounded to TF32 (nearest even) by the TMA unit, products are exact,
+// accumulation is fp32 in TMEM for kFlush tiles, then fp32 in shared memory, then fp64 across
+// CTAs. b and sx are summed by the four SIMT warps from the same shared-memory image (the
+// SWIZZLE_128B_ATOM_32B address map is applied by hand), y-dependent scalars by the y warp.
+//
+// Warps: 0-3 X'y / X'1, 4 TMA producer, 6 y staging, 7 TMEM allocation + MMA issue, 8-11 drain the
+// Gram accumulators (one TMEM lane quadrant each); 5 idles. Four accumulators rotate, so the MMA
+// issuer, the SIMT warps and the drains are coupled only through the ring and never wait for
+// each other in steady state.
+#pragma once
+
+#include "dense_tc.cuh"
+#include "dense_tcr.cuh"
+
+namespace mnf {
+namespace gram {
+
+using tc::elect_one;
+using tc::idesc_tf32;
+using tc::kAtomBytes;
+using tc::kP;
+using tc::kTileM;
+using tc::kXImageBytes;
+using tc::mbar_arrive;
+using tc::mbar_arrive_expect_tx;
+using tc::mbar_init;
+using tc::mbar_wait;
+using tc::smem_desc;
+using tc::smem_u32;
+using tc::tc_commit;
+using tc::tc_fence_after;
+using tc::tc_fence_before;
+using tc::tc_ld32;
+using tc::tc_wait_ld;
+using tc::tma_load_2d;
+using tcr::tc_mma_ss;
+
+constexpr int kStages = 6;       // MN-major image ring (32 KB each)
+constexpr int kFlush = 2;        // tiles accumulated in TMEM before the Gram tile is drained (truncating adds)
+constexpr int kFlush64 = 64;     // tiles per fp32 run of the X'y / X'1 sums before they move to fp64
+constexpr int kSimtWarps = 4;
+constexpr int kWarpTma = 4, kWarpY = 6, kWarpMma = 7;
+constexpr int kWarpDrain0 = 8;   // warps 8..11: TMEM lane quadrants 0..3
+constexpr int kAcc = 4;          // Gram accumulators in tensor memory
+constexpr int kThreads = 12 * 32;
+constexpr uint32_t kYBytes = kTileM * 4;
+constexpr uint32_t kTmemCols = 256;              // four 64-column accumulators
+
+constexpr uint32_t kOffX = 0;
+constexpr uint32_t kOffY = kOffX + kStages * kXImageBytes;
+constexpr uint32_t kOffBar = kOffY + kStages * kYBytes;
+constexpr uint32_t kNumBars = 2 * kStages + 2 * kAcc;         // full, empty per stage; g_full, g_empty per accumulator
+constexpr uint32_t kOffMisc = kOffBar + 8 * kNumBars;         // tmem slot
+constexpr uint32_t kOffG = kOffMisc + 64;                     // drained Gram rows [64][65] fp32
+constexpr uint32_t kOffVec = kOffG + kP * (kP + 1) * 4;       // [4 warps][2][64] doubles: X'y, X'1
+constexpr uint32_t kOffScal = kOffVec + kSimtWarps * 2 * kP * 8;   // Sy, Syy, n (doubles)
+constexpr uint32_t kSmemBytes = kOffScal + 32 + 1024 /* alignment slack */;
+static_assert(kSmemBytes <= 227 * 1024, "shared-memory budget");
+
+// per-CTA output: A [64][64], b [64], sx [64], Sy, Syy, n
+constexpr int kCtaFloats = kP * kP + 2 * kP + 3;
+
+__global__ void __launch_bounds__(kThreads, 1)
+dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t site,
+                  float* __restrict__ cta_out, uint32_t* __restrict__ status, uint32_t dev_skip) {
+  // dev_skip (MNF_GRAM_DEV_SKIP, timing experiments only, results are wrong): 1 = no MMAs, 2 = no X'y / X'1
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzled images: 1024-byte alignment
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t sX = base + kOffX, sY = base + kOffY;
+  const uint32_t bars = base + kOffBar;
+  const uint32_t bFull = bars, bEmpty = bFull + 8 * kStages;
+  const uint32_t bGFull = bEmpty + 8 * kStages, bGEmpty = bGFull + 8 * kAcc;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + kOffMisc);
+  float* sG = reinterpret_cast<float*>(gbase + kOffG);
+  double* sVec = reinterpret_cast<double*>(gbase + kOffVec);
+  double* sScal = reinterpret_cast<double*>(gbase + kOffScal);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (site.n_rows + kTileM - 1) / kTileM;
+  const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(bFull + 8 * i, 2);                   // arrive.expect_tx of the producer + the y warp
+      mbar_init(bEmpty + 8 * i, 1 + kSimtWarps);     // tcgen05.commit of the Gram product + the SIMT warps
+    }
+    for (int i = 0; i < kAcc; ++i) {
+      mbar_init(bGFull + 8 * i, 1);
+      mbar_init(bGEmpty + 8 * i, 4 * 32);            // the four drain warps
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kWarpMma) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (warp == kWarpTma && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_mn) : "memory");
+  for (int i = tid; i < kP * (kP + 1); i += kThreads) sG[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == kWarpTma) {
+    // ================= TMA producer (one elected lane) ========================================
+    if (elect_one()) {
+      for (int64_t k = 0; k < my_tiles; ++k) {
+        const int st = (int)(k % kStages);
+        const int row0 = (int)((blockIdx.x + k * gridDim.x) * kTileM);
+        mbar_wait(bEmpty + 8 * st, (uint32_t)(((k / kStages) & 1) ^ 1));
+        mbar_arrive_expect_tx(bFull + 8 * st, kXImageBytes);
+#pragma unroll
+        for (int a = 0; a < kP / 32; ++a)
+          tma_load_2d(sX + (uint32_t)st * kXImageBytes + a * kAtomBytes, &map_mn, a * 32, row0, bFull + 8 * st);
+      }
+    }
+    __syncwarp();
+  } else if (warp == kWarpY) {
+    // ================= y warp: the tile's responses (0 past the end), Sy, Syy, n ==============
+    const bool y_vec = reinterpret_cast<uintptr_t>(site.y) % 16 == 0;
+    double sy = 0.0, syy = 0.0;
+    int64_t cnt = 0;
+    bool bad_value = false;
+    auto fetch = [&](int64_t k) {
+      const int64_t row = (blockIdx.x + k * gridDim.x) * kTileM + lane * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (y_vec && row + 4 <= site.n_rows) {
+        v = __ldg(reinterpret_cast<const float4*>(site.y + row));
+      } else {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (row + q < site.n_rows) t[q] = __ldg(site.y + row + q);
+        v = make_float4(t[0], t[1], t[2], t[3]);
+      }
+      return v;
+    };
+    // Responses of the next kStages tiles stay in registers: one outstanding load per tile would tie
+    // the tile rate to the loaded HBM latency (~1 us), which is above the 0.75 us a tile may take.
+    float4 yq[kStages];
+#pragma unroll
+    for (int i = 0; i < kStages; ++i) yq[i] = i < my_tiles ? fetch(i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t k0 = 0; k0 < my_tiles; k0 += kStages) {
+#pragma unroll
+      for (int i = 0; i < kStages; ++i) {
+        const int64_t k = k0 + i;                      // k % kStages == i
+        if (k < my_tiles) {
+          const float4 v = yq[i];
+          const int64_t row = (blockIdx.x + k * gridDim.x) * kTileM + lane * 4;
+          const int64_t live = min((int64_t)4, max((int64_t)0, site.n_rows - row));
+          cnt += live;
+          const float t = (v.x + v.y) + (v.z + v.w);
+          const float t2 = fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
+          if (t != t) bad_value = true;                // NaN responses (rows past the end are zeros)
+          sy += (double)t;
+          syy += (double)t2;
+          mbar_wait(bEmpty + 8 * i, (uint32_t)(((k / kStages) & 1) ^ 1));
+          tc::sts128(sY + (uint32_t)i * kYBytes + lane * 16, __float_as_uint(v.x), __float_as_uint(v.y),
+                     __float_as_uint(v.z), __float_as_uint(v.w));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bFull + 8 * i);
+          if (k + kStages < my_tiles) yq[i] = fetch(k + kStages);
+        }
+      }
+    }
+    if (bad_value) atomicOr(status, MNF_ST_BAD_VALUE);
+    sy = warp_sum(sy);
+    syy = warp_sum(syy);
+    const double n_live = warp_sum((double)cnt);
+    if (lane == 0) { sScal[0] = sy; sScal[1] = syy; sScal[2] = n_live; }
+  } else if (warp == kWarpMma) {
+    // ================= MMA issuer: A and B are the same MN-major image =========================
+    constexpr uint32_t idesc = idesc_tf32(kP, kP, 1, 1);            // M = N = 64, both MN-major
+    const uint64_t dMN = smem_desc(sX, kAtomBytes, 512, 1);         // SWIZZLE_128B_BASE32B
+    const uint32_t d_lo = (uint32_t)dMN, d_hi = (uint32_t)(dMN >> 32);
+    for (int64_t k = 0; k < my_tiles; ++k) {
+      const int st = (int)(k % kStages);
+      const int64_t grp = k / kFlush;
+      const uint32_t gb = (uint32_t)(grp % kAcc);
+      const bool first = (k % kFlush) == 0;
+      const bool last = (k % kFlush) == kFlush - 1 || k == my_tiles - 1;
+      mbar_wait(bFull + 8 * st, (uint32_t)((k / kStages) & 1));
+      if (first) mbar_wait(bGEmpty + 8 * gb, (uint32_t)(((grp / kAcc) & 1) ^ 1));
+      tc_fence_after();
+      if (dev_skip & 1u) {
+        if (lane == 0) {
+          mbar_arrive(bEmpty + 8 * st);
+          if (last) mbar_arrive(bGFull + 8 * gb);
+        }
+      } else if (elect_one()) {
+        const uint32_t lo = d_lo + (uint32_t)st * (kXImageBytes >> 4);
+        const uint32_t d = tmem + gb * kP;
+#pragma unroll
+        for (int ks = 0; ks < kTileM / 8; ++ks)
+          tc_mma_ss(d, lo + ks * 64, d_hi, lo + ks * 64, d_hi, idesc, (!first || ks > 0) ? 1u : 0u);
+        tc_commit(bEmpty + 8 * st);
+        if (last) tc_commit(bGFull + 8 * gb);
+      }
+      __syncwarp();
+    }
+  } else if (warp < kSimtWarps) {
+    // ================= SIMT warps: b = X'y, sx = X'1 from the image; drains of the Gram tile ====
+    // Half-warp h = lane / 16 takes row 32 warp + 2 r + h of the tile, lane l' = lane % 16 its
+    // features 4 l' .. 4 l' + 3: atom l' / 8, 16-byte chunk l' % 8 of the 128-byte row, moved by the
+    // swizzle to 32-byte chunk ((l' % 8) / 2) ^ (row % 4).
+    const int lq = lane & 15, half = lane >> 4;
+    const uint32_t atom_off = (uint32_t)(lq >> 3) * kAtomBytes;
+    const uint32_t c16 = (uint32_t)(lq & 7);
+    float by[4] = {0.f, 0.f, 0.f, 0.f}, bx[4] = {0.f, 0.f, 0.f, 0.f};
+    double dby[4] = {0.0, 0.0, 0.0, 0.0}, dbx[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t k = 0; k < my_tiles; ++k) {
+      const int st = (int)(k % kStages);
+      mbar_wait(bFull + 8 * st, (uint32_t)((k / kStages) & 1));
+      const uint32_t img = sX + (uint32_t)st * kXImageBytes + atom_off;
+      const float* ys = reinterpret_cast<const float*>(gbase + kOffY + (size_t)st * kYBytes);
+#pragma unroll 4
+      for (int r = 0; r < ((dev_skip & 2u) ? 0 : 16); ++r) {
+        const int row = warp * 32 + 2 * r + half;
+        const uint32_t addr = img + (uint32_t)row * 128u + ((((c16 >> 1) ^ ((uint32_t)row & 3u)) << 5) | ((c16 & 1u) << 4));
+        const float4 x = tc::lds128(addr);
+        const float y = ys[row];
+        by[0] = fmaf(x.x, y, by[0]); by[1] = fmaf(x.y, y, by[1]);
+        by[2] = fmaf(x.z, y, by[2]); by[3] = fmaf(x.w, y, by[3]);
+        bx[0] += x.x; bx[1] += x.y; bx[2] += x.z; bx[3] += x.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bEmpty + 8 * st);
+      if ((k % kFlush64) == kFlush64 - 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          dby[c] += (double)by[c]; dbx[c] += (double)bx[c];
+          by[c] = 0.f; bx[c] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      dby[c] += (double)by[c]; dbx[c] += (double)bx[c];
+      dby[c] += __shfl_xor_sync(0xffffffffu, dby[c], 16);
+      dbx[c] += __shfl_xor_sync(0xffffffffu, dbx[c], 16);
+    }
+    if (half == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        sVec[(warp * 2 + 0) * kP + 4 * lq + c] = dby[c];
+        sVec[(warp * 2 + 1) * kP + 4 * lq + c] = dbx[c];
+      }
+    }
+  } else if (warp >= kWarpDrain0) {
+    // ================= drain warps: accumulator row m lives on TMEM lane (m % 16) + 32 (m / 16) ==
+    const int q = warp - kWarpDrain0;                     // == warp % 4: this warp's lane quadrant
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float* g_row = sG + (size_t)(lane < 16 ? q * 16 + lane : 0) * (kP + 1);
+    const int64_t n_grp = (my_tiles + kFlush - 1) / kFlush;
+    for (int64_t grp = 0; grp < n_grp; ++grp) {
+      const uint32_t gb = (uint32_t)(grp % kAcc);
+      mbar_wait(bGFull + 8 * gb, (uint32_t)((grp / kAcc) & 1));
+      tc_fence_after();
+#pragma unroll
+      for (int ch = 0; ch < kP / 32; ++ch) {
+        uint32_t v[32];
+        tc_ld32(tmem + lane_base + gb * kP + ch * 32, v);
+        tc_wait_ld();
+        if (lane < 16) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) g_row[ch * 32 + c] += __uint_as_float(v[c]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(bGEmpty + 8 * gb);
+    }
+    tc_fence_before();
+  }
+
+  __syncthreads();
+  // ---- this CTA's statistics, fp32 (values up to ~1e6, summed in fp64 across CTAs) --------------
+  float* out = cta_out + (size_t)blockIdx.x * kCtaFloats;
+  for (int i = tid; i < kP * kP; i += kThreads) out[i] = sG[(i / kP) * (kP + 1) + (i % kP)];
+  for (int i = tid; i < 2 * kP; i += kThreads) {
+    const int which = i / kP, j = i % kP;
+    double t = 0.0;
+    for (int w = 0; w < kSimtWarps; ++w) t += sVec[(w * 2 + which) * kP + j];
+    out[kP * kP + i] = (float)t;
+  }
+  if (tid < 3) out[kP * kP + 2 * kP + tid] = (float)(my_tiles > 0 ? sScal[tid] : 0.0);
+  if (warp == kWarpMma) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
+  }
+}
+
+// totals over the CTAs in fixed order, fp64: [kCtaFloats]
+__global__ void __launch_bounds__(256)
+gram_reduce_kernel(const float* __restrict__ cta_out, int n_cta, double* __restrict__ total) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= kCtaFloats) return;
+  double t = 0.0;
+  for (int b = 0; b < n_cta; ++b) t += (double)cta_out[(size_t)b * kCtaFloats + i];
+  total[i] = t;
+}
+
+// One block per particle, thread j = feature j: the closed forms, written as one row block
+// [S][1 + p + 2] in the layout of the other dense kernels (log-density, d/dtheta, d/dintercept,
+// d/d(scale link)) so the common reduction maps it into the step accumulator.
+__global__ void __launch_bounds__(kP)
+gram_finish_kernel(mnf_dense_site_t site, const double* __restrict__ total, const float* __restrict__ z, int S, int D,
+                   float* __restrict__ rows, uint32_t* __restrict__ status) {
+  __shared__ double s_theta[kP];
+  const int s = blockIdx.x, j = threadIdx.x;
+  const float* zs = z + (int64_t)s * D;
+  const DenseParticle pp = dense_particle(site, zs);
+  s_theta[j] = (double)zs[site.theta_lat + j];
+  __syncthreads();
+  const double* A = total;
+  const double* b = total + kP * kP;
+  const double* sx = b + kP;
+  const double Sy = total[kP * kP + 2 * kP], Syy = total[kP * kP + 2 * kP + 1], n = total[kP * kP + 2 * kP + 2];
+  double at = 0.0;                                   // (A theta)_j, A symmetric: column reads coalesce
+  for (int k = 0; k < kP; ++k) at = fma(A[k * kP + j], s_theta[k], at);
+  const double a = (double)pp.icpt;
+  const double bj = b[j] - a * sx[j];                // sum_i x_ij (y_i - a)
+  const double rj = bj - at;                         // sum_i x_ij (y_i - a - x_i.theta)
+  double q1 = s_theta[j] * bj, q2 = s_theta[j] * rj, q3 = s_theta[j] * sx[j];
+  q1 = warp_sum(q1); q2 = warp_sum(q2); q3 = warp_sum(q3);
+  __shared__ double s_q[3][kP / 32];
+  if ((j & 31) == 0) { s_q[0][j >> 5] = q1; s_q[1][j >> 5] = q2; s_q[2][j >> 5] = q3; }
+  __syncthreads();
+  const double t1 = s_q[0][0] + s_q[0][1], t2 = s_q[1][0] + s_q[1][1], t3 = s_q[2][0] + s_q[2][1];
+  const double sigma = (double)pp.scale, inv = 1.0 / sigma, iv = inv * inv;
+  const int ncol = 1 + kP + 2;
+  float* out = rows + (size_t)s * ncol;
+  out[1 + j] = (float)(rj * iv);
+  if (j == 0) {
+    const double Q = Syy - 2.0 * a * Sy + n * a * a - t1 - t2;          // sum of squared residuals
+    const double r1 = Sy - n * a - t3;                                  // sum of residuals
+    out[0] = (float)(-0.5 * iv * Q - n * (log(sigma) + 0.91893853320467274178));
+    out[1 + kP] = (float)(r1 * iv);
+    out[2 + kP] = (float)((Q * iv * inv - n * inv) * (double)pp.dscale);
+    if (!(pp.scale > 0.0f)) atomicOr(status, MNF_ST_BAD_PARAM);
+  }
+}
+
+}  // namespace gram
+}  // namespace mnf

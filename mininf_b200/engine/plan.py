@@ -8,6 +8,7 @@ count) and then only enqueues kernels: ``mnf_rsample`` -> sweeps over the observ
 from __future__ import annotations
 
 import ctypes as C
+import os
 import dataclasses
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -529,8 +530,12 @@ class Plan:
         count = 2  # rsample + finalize
         for site, mode in self.dense_sites:
             # the wide tcgen05 kernel takes at most 32 particles per sweep (csrc/abi.cu::tcr_shape)
-            wide = mode == abi.DENSE_TF32 and self.lib.raw("mnf_dense_tf32_kernel")(site.family, site.p, self.S) == 2
-            count += 2 * (-(-self.S // 32) if wide else 1)
+            kernel = self.lib.raw("mnf_dense_tf32_kernel")(site.family, site.p, self.S) if mode == abi.DENSE_TF32 else 0
+            if kernel == 1 and site.family == abi.NORMAL and not site.mask and \
+                    os.environ.get("MNF_DENSE_NO_GRAM", "0") in ("", "0"):
+                count += 4      # Gram statistics, their fp64 totals, closed forms per particle, reduction
+            else:
+                count += 2 * (-(-self.S // 32) if kernel == 2 else 1)
         for group in self.sweep_groups:
             # sites with a specialised kernel run on their own (csrc/site_sweep.cuh::site_fast_kind)
             fast = sum(1 for i in range(len(group)) if _has_fast_sweep(group[i]))

@@ -594,6 +594,89 @@ def test_row_permutation_invariance_and_determinism():
 
 
 # ---------------------------------------------------------------------------------------------
+# Normal likelihood, p = 64, no mask: data-only Gram statistics (csrc/dense_gram.cuh)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 127, 20_001, 1_000_003])
+def test_gram_statistics_kernel_against_exact_and_per_particle_kernels(n, monkeypatch):
+    """Raw C-ABI, Normal(a + X theta, exp(s)) with a latent + constant intercept, a latent scale,
+    features with non-zero means (the sums of squares do not cancel in the Gram form) and no row
+    mask: the Gram path (TF32 X, exact products, fp32/fp64 sums) and the per-particle tcgen05
+    kernel (MNF_DENSE_NO_GRAM=1) against the exact fp32 SIMT kernel. Ragged and one-row tiles."""
+    import ctypes
+    lib = abi.load()
+    torch.manual_seed(n)
+    p, S = 64, 37
+    D = p + 2
+    X = (torch.randn(n, p, device=DEV) + 0.5 * torch.rand(p, device=DEV)).contiguous()
+    y = torch.randn(n, device=DEV) + 0.3
+    z = (0.05 * torch.randn(S, D, device=DEV)).contiguous()
+    stream = torch.cuda.current_stream().cuda_stream
+    ws_bytes = lib.workspace_bytes(S, D)
+    ws = torch.empty(ws_bytes, device=DEV, dtype=torch.uint8)
+    status = torch.zeros(1, device=DEV, dtype=torch.int32)
+    scale = abi.Link(x=None, a_const=0.0, a_lat=p + 1, a_stride=0, b_const=0.0, b_lat=-1, b_stride=0,
+                     transform=abi.T_EXP)
+    site = abi.DenseSite(family=abi.NORMAL, p=p, n_rows=n, ldx=p, X=X.data_ptr(), y=y.data_ptr(), mask=None,
+                         theta_lat=0, icpt_lat=p, icpt_const=0.25, reserved=0, scale=scale, weight=3.0)
+
+    def sweep(mode):
+        acc = torch.zeros(S, D + 1, device=DEV, dtype=torch.float64)
+        lib.call("mnf_dense_sweep", ctypes.byref(site), mode, z.data_ptr(), S, D, acc.data_ptr(), ws.data_ptr(),
+                 ws_bytes, status.data_ptr(), stream)
+        torch.cuda.synchronize()
+        assert int(status.item()) == 0
+        return acc.cpu().numpy()
+
+    exact = sweep(abi.DENSE_FP32)
+    monkeypatch.delenv("MNF_DENSE_NO_GRAM", raising=False)
+    gram = sweep(abi.DENSE_TF32)
+    assert np.array_equal(gram, sweep(abi.DENSE_TF32))                  # fixed-order reductions
+    monkeypatch.setenv("MNF_DENSE_NO_GRAM", "1")
+    per_particle = sweep(abi.DENSE_TF32)
+    assert not np.array_equal(gram, per_particle)                        # the switch selects another kernel
+    for name, fast in (("gram", gram), ("per-particle", per_particle)):
+        # TF32 rounding of X is unbiased: few rows state the loose tolerance, 1e6 rows the tight one
+        tol = 5e-4 if n < 100_000 else 2e-5
+        assert np.max(np.abs(fast[:, 0] - exact[:, 0]) / np.abs(exact[:, 0])) < tol, name
+        gtol = 5e-3 if n < 100_000 else 5e-4
+        assert rel(fast[:, 1:1 + p], exact[:, 1:1 + p]) < gtol, name      # theta
+        assert rel(fast[:, 1 + p], exact[:, 1 + p]) < gtol, name          # intercept
+        assert rel(fast[:, 2 + p], exact[:, 2 + p]) < gtol, name          # log-sigma
+
+
+def test_gram_statistics_kernel_flags_nan_responses_and_bad_scales():
+    """Per-step device checks of the Gram path (raw C-ABI): a NaN response is outside the Normal
+    support (mininf/core.py:186-188) -> MNF_ST_BAD_VALUE; a non-positive scale is an invalid
+    parameter (TORCH normal.py:57 arg_constraints) -> MNF_ST_BAD_PARAM."""
+    import ctypes
+    lib = abi.load()
+    n, p, S = 1000, 64, 4
+    D = p
+    X = torch.randn(n, p, device=DEV)
+    z = (0.05 * torch.randn(S, D, device=DEV)).contiguous()
+    stream = torch.cuda.current_stream().cuda_stream
+    ws_bytes = lib.workspace_bytes(S, D)
+    ws = torch.empty(ws_bytes, device=DEV, dtype=torch.uint8)
+
+    def flags(y, sigma):
+        status = torch.zeros(1, device=DEV, dtype=torch.int32)
+        site = abi.DenseSite(family=abi.NORMAL, p=p, n_rows=n, ldx=p, X=X.data_ptr(), y=y.data_ptr(), mask=None,
+                             theta_lat=0, icpt_lat=-1, icpt_const=0.0, reserved=0, scale=abi.const_link(sigma),
+                             weight=1.0)
+        acc = torch.zeros(S, D + 1, device=DEV, dtype=torch.float64)
+        lib.call("mnf_dense_sweep", ctypes.byref(site), abi.DENSE_TF32, z.data_ptr(), S, D, acc.data_ptr(),
+                 ws.data_ptr(), ws_bytes, status.data_ptr(), stream)
+        torch.cuda.synchronize()
+        return int(status.item())
+
+    y = torch.randn(n, device=DEV)
+    assert flags(y, 1.0) == 0
+    assert flags(y, -1.0) == abi.ST_BAD_PARAM
+    y[777] = float("nan")
+    assert flags(y, 1.0) == abi.ST_BAD_VALUE
+
+
+# ---------------------------------------------------------------------------------------------
 # Normal sites through the sufficient-statistics sweep (csrc/site_sweep.cuh::normal_stats_kernel)
 # ---------------------------------------------------------------------------------------------
 def _normal_site_case(n, offset=0.0, masked=True, covariate=True, misalign=0, seed=0):
