@@ -45,6 +45,10 @@ def timed(label, reps=15):
     print(f"{label:28s} {ms:7.3f} ms  {n * (4 * p + 4) / ms / 1e6:7.0f} GB/s", flush=True)
 
 
+if len(sys.argv) > 2 and sys.argv[2] == "once":      # a few launches for an ncu capture
+    timed("gram", reps=2)
+    sys.exit(0)
+
 if len(sys.argv) > 2 and sys.argv[2] == "series":
     # sustained behaviour: 40 back-to-back blocks of 10 launches with the SM clock and power beside them
     import subprocess
