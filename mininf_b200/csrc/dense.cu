@@ -227,7 +227,8 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
     if ((size_t)grid * S * ncol * sizeof(float) > workspace_bytes)
       return fail(MNF_E_INVALID, "mnf_dense_sweep: workspace too small%s%s");
     int rc;
-    if (c2_shape && s.family == MNF_NORMAL && s.mask == nullptr && !gram_disabled() &&
+    // the Gram statistics do not depend on the particles: any S that a tcgen05 kernel would take
+    if (p == tc::kP && s.family == MNF_NORMAL && s.mask == nullptr && !gram_disabled() &&
         gram_workspace_bytes(grid, S) <= workspace_bytes) {
       float* rows = nullptr;
       if (int rg = launch_dense_gram(s, z, S, D, workspace, &rows, status, grid, stream)) return rg;

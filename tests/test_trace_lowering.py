@@ -37,7 +37,8 @@ def test_regression_lowers_to_one_dense_site_and_two_priors():
     assert mode == abi.DENSE_TF32 and site.family == abi.NORMAL and (site.p, site.n_rows) == (64, 3000)
     assert site.theta_lat == 0 and site.icpt_lat == -1 and site.scale.a_lat == 64 and site.weight == 1.0
     assert plan.small_global[1] == 2 and plan.small_observed is None
-    assert plan.gpu_launches_per_step == 5
+    # rsample, Gram statistics + totals + closed forms + row reduction (csrc/dense_gram.cuh), priors, finalize
+    assert plan.gpu_launches_per_step == 7
 
 
 def test_shapes_outside_the_tensor_core_kernel_use_fp32_or_raise():
