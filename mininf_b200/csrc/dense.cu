@@ -89,7 +89,8 @@ int launch_dense_gram(const mnf_dense_site_t& site, const float* z, int S, int D
                                       (int)gram::kSmemBytes));
   const char* dev = std::getenv("MNF_GRAM_DEV_SKIP");   // timing experiments only (dense_gram.cuh)
   const uint32_t dev_skip = dev != nullptr ? (uint32_t)std::atoi(dev) : 0u;
-  gram::dense_gram_kernel<<<grid, gram::kThreads, gram::kSmemBytes, stream>>>(map_mn, site, cta_out, status, dev_skip);
+  gram::dense_gram_kernel<<<grid, gram::kThreads, gram::kSmemBytes, stream>>>(map_mn, site, z, S, D, cta_out, status,
+                                                                              dev_skip);
   MNF_CUDA_CHECK(cudaGetLastError());
   gram::gram_reduce_kernel<<<(gram::kCtaFloats + 255) / 256, 256, 0, stream>>>(cta_out, grid, total);
   MNF_CUDA_CHECK(cudaGetLastError());

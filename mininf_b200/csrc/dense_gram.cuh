@@ -1,26 +1,30 @@
 // Normal likelihood with a dense linear predictor and a row-independent scale, p = 64, no mask:
-// the sweep reduced to DATA-ONLY Gram statistics (the move site_sweep.cuh makes for scalar links).
+// the sweep reduced to DATA-ONLY Gram statistics (the move site_sweep.cuh makes for scalar links),
+// expanded around the particle MEAN (a0, theta0) so that no large sums cancel:
 //
-//   sum_i (y_i - a - x_i.theta)^2 = Syy - 2 a Sy + n a^2 - 2 theta.(b - a sx) + theta' A theta
-//   A = X'X [64 x 64],  b = X'y,  sx = X'1,  Sy = sum y,  Syy = sum y^2,  n = rows
+//   r0_i = y_i - a0 - x_i.theta0,   alpha_s = a_s - a0,   delta_s = theta_s - theta0
+//   sum_i (y_i - a_s - x_i.theta_s)^2 = R2 - 2 alpha R1 + n alpha^2 - 2 delta.(c - alpha sx) + delta' A delta
+//   A = X'X [64 x 64],  c = X'r0,  sx = X'1,  R1 = sum r0,  R2 = sum r0^2,  n = rows
 //
-// so log p, d/dtheta = (b - a sx - A theta) / sigma^2, d/da and d/dsigma of EVERY particle follow
+// so log p, d/dtheta = (c - alpha sx - A delta) / sigma^2, d/da and d/dsigma of EVERY particle follow
 // from one pass over X that does no per-particle work (gram_finish_kernel evaluates the closed
-// forms in fp64). Replaces, like dense_tc.cuh: aten::mv + MvBackward + Normal.log_prob and its
-// autograd twins (mininf/core.py:241, TORCH normal.py:87-103) for all S particles.
+// forms in fp64). The dominant term R2 is summed directly from the residuals; the Gram matrix only
+// enters through the particles' spread delta' A delta. Replaces, like dense_tc.cuh: aten::mv +
+// MvBackward + Normal.log_prob and its autograd twins (mininf/core.py:241, TORCH normal.py:87-103)
+// for all S particles.
 //
 // Tensor work per 128-row tile: 16 tcgen05.mma kind::tf32 of M = N = 64, K = 8 whose A AND B
 // operand are the SAME MN-major shared-memory image (A = X' needs the feature index contiguous,
 // B = X too) - 2 N p^2 flop per step instead of 4 N p S, one TMA image per tile instead of two,
 // no TMEM epilogue. X is rounded to TF32 (nearest even) by the TMA unit, products are exact,
-// accumulation is fp32 in TMEM for kFlush tiles, then fp32 in shared memory, then fp64 across
-// CTAs. b and sx are summed by the four SIMT warps from the same shared-memory image (the
-// SWIZZLE_128B_ATOM_32B address map is applied by hand), y-dependent scalars by the y warp.
+// accumulation is fp32 in TMEM for kFlush tiles, then fp32 in registers per CTA, then fp64 across
+// CTAs. r0, c, sx, R1, R2 are computed by the four SIMT warps from the same shared-memory image (the
+// SWIZZLE_128B_ATOM_32B address map is applied by hand) in fp32 FMAs, summed in fp64.
 //
-// Warps: 0-3 X'y / X'1, 4 TMA producer, 6 y staging, 7 TMEM allocation + MMA issue, 8-11 drain the
-// Gram accumulators (one TMEM lane quadrant each); 5 idles. Four accumulators rotate, so the MMA
-// issuer, the SIMT warps and the drains are coupled only through the ring and never wait for
-// each other in steady state.
+// Warps: 0-3 residuals and X'r0 / X'1, 4 TMA producer, 6 y staging, 7 TMEM allocation + MMA issue,
+// 8-11 drain the Gram accumulators (one TMEM lane quadrant each); 5 idles. Four accumulators rotate,
+// so the MMA issuer, the SIMT warps and the drains are coupled only through the ring and never wait
+// for each other in steady state.
 #pragma once
 
 #include "dense_tc.cuh"
@@ -65,18 +69,35 @@ constexpr uint32_t kOffY = kOffX + kStages * kXImageBytes;
 constexpr uint32_t kOffBar = kOffY + kStages * kYBytes;
 constexpr uint32_t kNumBars = 2 * kStages + 2 * kAcc;         // full, empty per stage; g_full, g_empty per accumulator
 constexpr uint32_t kOffMisc = kOffBar + 8 * kNumBars;         // tmem slot
-constexpr uint32_t kOffG = kOffMisc + 64;                     // drained Gram rows [64][65] fp32
+constexpr uint32_t kOffG = kOffMisc + 64;                     // this CTA's Gram rows [64][65] fp32 (written once)
 constexpr uint32_t kOffVec = kOffG + kP * (kP + 1) * 4;       // [4 warps][2][64] doubles: X'y, X'1
-constexpr uint32_t kOffScal = kOffVec + kSimtWarps * 2 * kP * 8;   // Sy, Syy, n (doubles)
-constexpr uint32_t kSmemBytes = kOffScal + 32 + 1024 /* alignment slack */;
+constexpr uint32_t kOffScal = kOffVec + kSimtWarps * 2 * kP * 8;   // [4 warps][2 halves][R1, R2] doubles, then n
+constexpr uint32_t kOffCenter = kOffScal + (kSimtWarps * 4 + 1) * 8 + 8;   // theta0 [64] floats, a0
+constexpr uint32_t kSmemBytes = kOffCenter + (kP + 4) * 4 + 1024 /* alignment slack */;
 static_assert(kSmemBytes <= 227 * 1024, "shared-memory budget");
 
-// per-CTA output: A [64][64], b [64], sx [64], Sy, Syy, n
+// per-CTA output: A [64][64], c [64], sx [64], R1, R2, n
 constexpr int kCtaFloats = kP * kP + 2 * kP + 3;
 
+// The expansion point: the particle mean of theta_j and of the intercept, summed in a fixed order in
+// fp32 so that every CTA of the sweep and the finish kernel use bit-identical values.
+__device__ __forceinline__ float center_theta(const mnf_dense_site_t& site, const float* __restrict__ z, int S, int D,
+                                              int j) {
+  float t = 0.f;
+#pragma unroll 8
+  for (int s = 0; s < S; ++s) t += z[(int64_t)s * D + site.theta_lat + j];
+  return t / (float)S;
+}
+__device__ __forceinline__ float center_icpt(const mnf_dense_site_t& site, const float* __restrict__ z, int S, int D) {
+  float t = 0.f;
+  if (site.icpt_lat >= 0)
+    for (int s = 0; s < S; ++s) t += z[(int64_t)s * D + site.icpt_lat];
+  return site.icpt_const + t / (float)S;
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
-dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t site,
-                  float* __restrict__ cta_out, uint32_t* __restrict__ status, uint32_t dev_skip) {
+dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t site, const float* __restrict__ z,
+                  int S, int D, float* __restrict__ cta_out, uint32_t* __restrict__ status, uint32_t dev_skip) {
   // dev_skip (MNF_GRAM_DEV_SKIP, timing experiments only, results are wrong): 1 = no MMAs, 2 = no X'y / X'1
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzled images: 1024-byte alignment
@@ -89,9 +110,11 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
   float* sG = reinterpret_cast<float*>(gbase + kOffG);
   double* sVec = reinterpret_cast<double*>(gbase + kOffVec);
   double* sScal = reinterpret_cast<double*>(gbase + kOffScal);
+  float* sCenter = reinterpret_cast<float*>(gbase + kOffCenter);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
+  const int flush = (dev_skip >> 8) != 0 ? (int)(dev_skip >> 8) : kFlush;   // developer override of kFlush
   const int64_t n_tiles = (site.n_rows + kTileM - 1) / kTileM;
   const int64_t my_tiles = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
@@ -113,6 +136,8 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
   }
   if (warp == kWarpTma && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_mn) : "memory");
   for (int i = tid; i < kP * (kP + 1); i += kThreads) sG[i] = 0.f;
+  if (tid < kP) sCenter[tid] = center_theta(site, z, S, D, tid);
+  if (tid == kP) sCenter[kP] = center_icpt(site, z, S, D);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -133,9 +158,8 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
     }
     __syncwarp();
   } else if (warp == kWarpY) {
-    // ================= y warp: the tile's responses (0 past the end), Sy, Syy, n ==============
+    // ================= y warp: the tile's responses (0 past the end), NaN check, n ==============
     const bool y_vec = reinterpret_cast<uintptr_t>(site.y) % 16 == 0;
-    double sy = 0.0, syy = 0.0;
     int64_t cnt = 0;
     bool bad_value = false;
     auto fetch = [&](int64_t k) {
@@ -167,10 +191,7 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
           const int64_t live = min((int64_t)4, max((int64_t)0, site.n_rows - row));
           cnt += live;
           const float t = (v.x + v.y) + (v.z + v.w);
-          const float t2 = fmaf(v.x, v.x, v.y * v.y) + fmaf(v.z, v.z, v.w * v.w);
           if (t != t) bad_value = true;                // NaN responses (rows past the end are zeros)
-          sy += (double)t;
-          syy += (double)t2;
           mbar_wait(bEmpty + 8 * i, (uint32_t)(((k / kStages) & 1) ^ 1));
           tc::sts128(sY + (uint32_t)i * kYBytes + lane * 16, __float_as_uint(v.x), __float_as_uint(v.y),
                      __float_as_uint(v.z), __float_as_uint(v.w));
@@ -181,10 +202,8 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
       }
     }
     if (bad_value) atomicOr(status, MNF_ST_BAD_VALUE);
-    sy = warp_sum(sy);
-    syy = warp_sum(syy);
     const double n_live = warp_sum((double)cnt);
-    if (lane == 0) { sScal[0] = sy; sScal[1] = syy; sScal[2] = n_live; }
+    if (lane == 0) sScal[kSimtWarps * 4] = n_live;
   } else if (warp == kWarpMma) {
     // ================= MMA issuer: A and B are the same MN-major image =========================
     constexpr uint32_t idesc = idesc_tf32(kP, kP, 1, 1);            // M = N = 64, both MN-major
@@ -192,10 +211,10 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
     const uint32_t d_lo = (uint32_t)dMN, d_hi = (uint32_t)(dMN >> 32);
     for (int64_t k = 0; k < my_tiles; ++k) {
       const int st = (int)(k % kStages);
-      const int64_t grp = k / kFlush;
+      const int64_t grp = k / flush;
       const uint32_t gb = (uint32_t)(grp % kAcc);
-      const bool first = (k % kFlush) == 0;
-      const bool last = (k % kFlush) == kFlush - 1 || k == my_tiles - 1;
+      const bool first = (k % flush) == 0;
+      const bool last = (k % flush) == flush - 1 || k == my_tiles - 1;
       mbar_wait(bFull + 8 * st, (uint32_t)((k / kStages) & 1));
       if (first) mbar_wait(bGEmpty + 8 * gb, (uint32_t)(((grp / kAcc) & 1) ^ 1));
       tc_fence_after();
@@ -216,32 +235,69 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
       __syncwarp();
     }
   } else if (warp < kSimtWarps) {
-    // ================= SIMT warps: b = X'y, sx = X'1 from the image; drains of the Gram tile ====
+    // ================= SIMT warps: r0 = y - a0 - x.theta0, c = X'r0, sx = X'1, R1, R2 =============
     // Half-warp h = lane / 16 takes row 32 warp + 2 r + h of the tile, lane l' = lane % 16 its
     // features 4 l' .. 4 l' + 3: atom l' / 8, 16-byte chunk l' % 8 of the 128-byte row, moved by the
     // swizzle to 32-byte chunk ((l' % 8) / 2) ^ (row % 4).
     const int lq = lane & 15, half = lane >> 4;
     const uint32_t atom_off = (uint32_t)(lq >> 3) * kAtomBytes;
     const uint32_t c16 = (uint32_t)(lq & 7);
+    const float4 t0 = *reinterpret_cast<const float4*>(sCenter + 4 * lq);
+    const float a0 = sCenter[kP];
+    const bool need_sx = site.icpt_lat >= 0;           // without a latent intercept every alpha_s is zero
     float by[4] = {0.f, 0.f, 0.f, 0.f}, bx[4] = {0.f, 0.f, 0.f, 0.f};
     double dby[4] = {0.0, 0.0, 0.0, 0.0}, dbx[4] = {0.0, 0.0, 0.0, 0.0};
+    double dr1 = 0.0, dr2 = 0.0;
     for (int64_t k = 0; k < my_tiles; ++k) {
       const int st = (int)(k % kStages);
       mbar_wait(bFull + 8 * st, (uint32_t)((k / kStages) & 1));
       const uint32_t img = sX + (uint32_t)st * kXImageBytes + atom_off;
       const float* ys = reinterpret_cast<const float*>(gbase + kOffY + (size_t)st * kYBytes);
-#pragma unroll 4
-      for (int r = 0; r < ((dev_skip & 2u) ? 0 : 16); ++r) {
-        const int row = warp * 32 + 2 * r + half;
-        const uint32_t addr = img + (uint32_t)row * 128u + ((((c16 >> 1) ^ ((uint32_t)row & 3u)) << 5) | ((c16 & 1u) << 4));
-        const float4 x = tc::lds128(addr);
-        const float y = ys[row];
-        by[0] = fmaf(x.x, y, by[0]); by[1] = fmaf(x.y, y, by[1]);
-        by[2] = fmaf(x.z, y, by[2]); by[3] = fmaf(x.w, y, by[3]);
-        bx[0] += x.x; bx[1] += x.y; bx[2] += x.z; bx[3] += x.w;
+      const int64_t rows_left = site.n_rows - (blockIdx.x + k * gridDim.x) * kTileM;   // > 0
+      float r1 = 0.f, r2 = 0.f;
+      if (!(dev_skip & 2u)) {
+        // pass A: this lane's four features of its half-warp's 16 rows, partial dot products with theta0
+        float4 x[16];
+        float v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const int row = warp * 32 + 2 * r + half;
+          const uint32_t addr = img + (uint32_t)row * 128u + ((((c16 >> 1) ^ ((uint32_t)row & 3u)) << 5) | ((c16 & 1u) << 4));
+          x[r] = tc::lds128(addr);
+          v[r] = fmaf(x[r].x, t0.x, fmaf(x[r].y, t0.y, fmaf(x[r].z, t0.z, x[r].w * t0.w)));
+        }
+        // reduce-scatter butterfly over the 16 lanes of the half-warp: 15 shuffles instead of 64 (shuffles
+        // and shared-memory loads share the pipe this kernel is short of); lane l' ends up with row 2 l' + h
+#pragma unroll
+        for (int w = 8; w >= 1; w >>= 1) {
+          const bool up = (lq & w) != 0;
+#pragma unroll
+          for (int i = 0; i < w; ++i) {
+            const float send = up ? v[i] : v[i + w];
+            const float keep = up ? v[i + w] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+          }
+        }
+        const int own = warp * 32 + 2 * lq + half;
+        const float res_own = own < rows_left ? (ys[own] - a0) - v[0] : 0.f;   // rows past the end: X and y are zeros
+        r1 = res_own;
+        r2 = res_own * res_own;
+        // pass B: c += x r0, sx += x with the row's residual fetched from its owner
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const float res = __shfl_sync(0xffffffffu, res_own, (lane & 16) | r);
+          by[0] = fmaf(x[r].x, res, by[0]); by[1] = fmaf(x[r].y, res, by[1]);
+          by[2] = fmaf(x[r].z, res, by[2]); by[3] = fmaf(x[r].w, res, by[3]);
+        }
+        if (need_sx) {                                 // X'1 only multiplies alpha_s = a_s - a0
+#pragma unroll
+          for (int r = 0; r < 16; ++r) { bx[0] += x[r].x; bx[1] += x[r].y; bx[2] += x[r].z; bx[3] += x[r].w; }
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bEmpty + 8 * st);
+      dr1 += (double)r1;                               // one row per lane and tile: R2 is the dominant term
+      dr2 += (double)r2;
       if ((k % kFlush64) == kFlush64 - 1) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -263,12 +319,24 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
         sVec[(warp * 2 + 1) * kP + 4 * lq + c] = dbx[c];
       }
     }
+    dr1 += __shfl_xor_sync(0xffffffffu, dr1, 8); dr2 += __shfl_xor_sync(0xffffffffu, dr2, 8);
+    dr1 += __shfl_xor_sync(0xffffffffu, dr1, 4); dr2 += __shfl_xor_sync(0xffffffffu, dr2, 4);
+    dr1 += __shfl_xor_sync(0xffffffffu, dr1, 2); dr2 += __shfl_xor_sync(0xffffffffu, dr2, 2);
+    dr1 += __shfl_xor_sync(0xffffffffu, dr1, 1); dr2 += __shfl_xor_sync(0xffffffffu, dr2, 1);
+    if (lq == 0) {                                     // one row per lane and tile: the half-warp's sums
+      sScal[(warp * 2 + half) * 2 + 0] = dr1;
+      sScal[(warp * 2 + half) * 2 + 1] = dr2;
+    }
   } else if (warp >= kWarpDrain0) {
     // ================= drain warps: accumulator row m lives on TMEM lane (m % 16) + 32 (m / 16) ==
+    // The running Gram row stays in REGISTERS (64 per lane): shared-memory bandwidth is what this
+    // kernel runs out of first (TMA writes, MMA operand reads, the SIMT warps' loads and shuffles).
     const int q = warp - kWarpDrain0;                     // == warp % 4: this warp's lane quadrant
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    float* g_row = sG + (size_t)(lane < 16 ? q * 16 + lane : 0) * (kP + 1);
-    const int64_t n_grp = (my_tiles + kFlush - 1) / kFlush;
+    float g_acc[kP];
+#pragma unroll
+    for (int c = 0; c < kP; ++c) g_acc[c] = 0.f;
+    const int64_t n_grp = (my_tiles + flush - 1) / flush;
     for (int64_t grp = 0; grp < n_grp; ++grp) {
       const uint32_t gb = (uint32_t)(grp % kAcc);
       mbar_wait(bGFull + 8 * gb, (uint32_t)((grp / kAcc) & 1));
@@ -278,15 +346,18 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
         uint32_t v[32];
         tc_ld32(tmem + lane_base + gb * kP + ch * 32, v);
         tc_wait_ld();
-        if (lane < 16) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) g_row[ch * 32 + c] += __uint_as_float(v[c]);
-        }
+        for (int c = 0; c < 32; ++c) g_acc[ch * 32 + c] += __uint_as_float(v[c]);   // lanes >= 16 hold nothing
       }
       tc_fence_before();
       mbar_arrive(bGEmpty + 8 * gb);
     }
     tc_fence_before();
+    if (lane < 16) {
+      float* g_row = sG + (size_t)(q * 16 + lane) * (kP + 1);
+#pragma unroll
+      for (int c = 0; c < kP; ++c) g_row[c] = g_acc[c];
+    }
   }
 
   __syncthreads();
@@ -299,7 +370,12 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
     for (int w = 0; w < kSimtWarps; ++w) t += sVec[(w * 2 + which) * kP + j];
     out[kP * kP + i] = (float)t;
   }
-  if (tid < 3) out[kP * kP + 2 * kP + tid] = (float)(my_tiles > 0 ? sScal[tid] : 0.0);
+  if (tid < 2) {                                       // R1, R2: the eight half-warp sums in fixed order
+    double t = 0.0;
+    for (int w = 0; w < kSimtWarps * 2; ++w) t += sScal[w * 2 + tid];
+    out[kP * kP + 2 * kP + tid] = (float)(my_tiles > 0 ? t : 0.0);
+  }
+  if (tid == 2) out[kP * kP + 2 * kP + 2] = (float)(my_tiles > 0 ? sScal[kSimtWarps * 4] : 0.0);
   if (warp == kWarpMma) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols));
@@ -316,28 +392,28 @@ gram_reduce_kernel(const float* __restrict__ cta_out, int n_cta, double* __restr
   total[i] = t;
 }
 
-// One block per particle, thread j = feature j: the closed forms, written as one row block
-// [S][1 + p + 2] in the layout of the other dense kernels (log-density, d/dtheta, d/dintercept,
-// d/d(scale link)) so the common reduction maps it into the step accumulator.
+// One block per particle, thread j = feature j: the closed forms around the particle mean, written
+// as one row block [S][1 + p + 2] in the layout of the other dense kernels (log-density, d/dtheta,
+// d/dintercept, d/d(scale link)) so the common reduction maps it into the step accumulator.
 __global__ void __launch_bounds__(kP)
 gram_finish_kernel(mnf_dense_site_t site, const double* __restrict__ total, const float* __restrict__ z, int S, int D,
                    float* __restrict__ rows, uint32_t* __restrict__ status) {
-  __shared__ double s_theta[kP];
+  __shared__ double s_delta[kP];
   const int s = blockIdx.x, j = threadIdx.x;
   const float* zs = z + (int64_t)s * D;
   const DenseParticle pp = dense_particle(site, zs);
-  s_theta[j] = (double)zs[site.theta_lat + j];
+  s_delta[j] = (double)zs[site.theta_lat + j] - (double)center_theta(site, z, S, D, j);
   __syncthreads();
   const double* A = total;
-  const double* b = total + kP * kP;
-  const double* sx = b + kP;
-  const double Sy = total[kP * kP + 2 * kP], Syy = total[kP * kP + 2 * kP + 1], n = total[kP * kP + 2 * kP + 2];
-  double at = 0.0;                                   // (A theta)_j, A symmetric: column reads coalesce
-  for (int k = 0; k < kP; ++k) at = fma(A[k * kP + j], s_theta[k], at);
-  const double a = (double)pp.icpt;
-  const double bj = b[j] - a * sx[j];                // sum_i x_ij (y_i - a)
-  const double rj = bj - at;                         // sum_i x_ij (y_i - a - x_i.theta)
-  double q1 = s_theta[j] * bj, q2 = s_theta[j] * rj, q3 = s_theta[j] * sx[j];
+  const double* c = total + kP * kP;
+  const double* sx = c + kP;
+  const double R1 = total[kP * kP + 2 * kP], R2 = total[kP * kP + 2 * kP + 1], n = total[kP * kP + 2 * kP + 2];
+  double ad = 0.0;                                   // (A delta)_j, A symmetric: column reads coalesce
+  for (int k = 0; k < kP; ++k) ad = fma(A[k * kP + j], s_delta[k], ad);
+  const double alpha = (double)pp.icpt - (double)center_icpt(site, z, S, D);
+  const double cj = c[j] - alpha * sx[j];            // sum_i x_ij (r0_i - alpha)
+  const double rj = cj - ad;                         // sum_i x_ij (r0_i - alpha - x_i.delta)
+  double q1 = s_delta[j] * cj, q2 = s_delta[j] * rj, q3 = s_delta[j] * sx[j];
   q1 = warp_sum(q1); q2 = warp_sum(q2); q3 = warp_sum(q3);
   __shared__ double s_q[3][kP / 32];
   if ((j & 31) == 0) { s_q[0][j >> 5] = q1; s_q[1][j >> 5] = q2; s_q[2][j >> 5] = q3; }
@@ -348,8 +424,8 @@ gram_finish_kernel(mnf_dense_site_t site, const double* __restrict__ total, cons
   float* out = rows + (size_t)s * ncol;
   out[1 + j] = (float)(rj * iv);
   if (j == 0) {
-    const double Q = Syy - 2.0 * a * Sy + n * a * a - t1 - t2;          // sum of squared residuals
-    const double r1 = Sy - n * a - t3;                                  // sum of residuals
+    const double Q = R2 - 2.0 * alpha * R1 + n * alpha * alpha - t1 - t2;   // sum of squared residuals
+    const double r1 = R1 - n * alpha - t3;                                  // sum of residuals
     out[0] = (float)(-0.5 * iv * Q - n * (log(sigma) + 0.91893853320467274178));
     out[1 + kP] = (float)(r1 * iv);
     out[2 + kP] = (float)((Q * iv * inv - n * inv) * (double)pp.dscale);
