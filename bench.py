@@ -479,10 +479,13 @@ def run_b200(args):
     elapsed_ms = begin.elapsed_time(end)
     loss_module.synchronize()
     final_loss = float(loss.detach())
+    by_rank = None
     if distributed:
         t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t)
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        by_rank = [float(g) / args.steps for g in gathered]      # every rank's own clock: the step is the slowest one's
+        elapsed_ms = max(float(g) for g in gathered)
     ms_per_step = elapsed_ms / args.steps
     value = n_rows * world * S / (ms_per_step * 1e-3)
     kernel_ms_after, _ = measure_sweep(args.steps)
@@ -544,6 +547,7 @@ def run_b200(args):
                                           "same data, averaged",
                          **({"note": w.bound_note} if w.bound_note else {})},
             "eager_ms_per_step": eager_ms_per_step,
+            "ms_per_step_by_rank": by_rank,
             "cpu_baseline": cpu_baseline,
             "steps_per_sec": 1e3 / ms_per_step,
         }
