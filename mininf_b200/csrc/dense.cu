@@ -63,7 +63,7 @@ int launch_dense_tc(const mnf_dense_site_t& site, const float* z, int S, int D, 
   return MNF_OK;
 }
 
-// Normal family, p = 64, no mask: data-only Gram statistics (dense_gram.cuh). Workspace: per-CTA
+// Normal family, p <= 64, no mask: data-only Gram statistics (dense_gram.cuh). Workspace: per-CTA
 // statistics, their fp64 totals, then one row block [S][1 + p + 2] for the common reduction.
 // MNF_DENSE_NO_GRAM=1 keeps the per-particle kernel (developer A/B switch).
 bool gram_disabled() {
@@ -229,7 +229,7 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
       return fail(MNF_E_INVALID, "mnf_dense_sweep: workspace too small%s%s");
     int rc;
     // the Gram statistics do not depend on the particles: any S that a tcgen05 kernel would take
-    if (p == tc::kP && s.family == MNF_NORMAL && s.mask == nullptr && !gram_disabled() &&
+    if (p <= tc::kP && s.family == MNF_NORMAL && s.mask == nullptr && !gram_disabled() &&
         gram_workspace_bytes(grid, S) <= workspace_bytes) {
       float* rows = nullptr;
       if (int rg = launch_dense_gram(s, z, S, D, workspace, &rows, status, grid, stream)) return rg;

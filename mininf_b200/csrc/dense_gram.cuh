@@ -1,4 +1,5 @@
-// Normal likelihood with a dense linear predictor and a row-independent scale, p = 64, no mask:
+// Normal likelihood with a dense linear predictor and a row-independent scale, p <= 64 (a multiple
+// of 4; columns past p are zero-filled by the TMA unit and cost tensor time, not HBM traffic), no mask:
 // the sweep reduced to DATA-ONLY Gram statistics (the move site_sweep.cuh makes for scalar links),
 // expanded around the particle MEAN (a0, theta0) so that no large sums cancel:
 //
@@ -83,6 +84,7 @@ constexpr int kCtaFloats = kP * kP + 2 * kP + 3;
 // fp32 so that every CTA of the sweep and the finish kernel use bit-identical values.
 __device__ __forceinline__ float center_theta(const mnf_dense_site_t& site, const float* __restrict__ z, int S, int D,
                                               int j) {
+  if (j >= site.p) return 0.f;                         // p < 64: the TMA unit zero-fills those columns
   float t = 0.f;
 #pragma unroll 8
   for (int s = 0; s < S; ++s) t += z[(int64_t)s * D + site.theta_lat + j];
@@ -402,7 +404,8 @@ gram_finish_kernel(mnf_dense_site_t site, const double* __restrict__ total, cons
   const int s = blockIdx.x, j = threadIdx.x;
   const float* zs = z + (int64_t)s * D;
   const DenseParticle pp = dense_particle(site, zs);
-  s_delta[j] = (double)zs[site.theta_lat + j] - (double)center_theta(site, z, S, D, j);
+  const int p = site.p;                              // <= 64; columns past p hold zeros everywhere
+  s_delta[j] = j < p ? (double)zs[site.theta_lat + j] - (double)center_theta(site, z, S, D, j) : 0.0;
   __syncthreads();
   const double* A = total;
   const double* c = total + kP * kP;
@@ -420,15 +423,15 @@ gram_finish_kernel(mnf_dense_site_t site, const double* __restrict__ total, cons
   __syncthreads();
   const double t1 = s_q[0][0] + s_q[0][1], t2 = s_q[1][0] + s_q[1][1], t3 = s_q[2][0] + s_q[2][1];
   const double sigma = (double)pp.scale, inv = 1.0 / sigma, iv = inv * inv;
-  const int ncol = 1 + kP + 2;
+  const int ncol = 1 + p + 2;
   float* out = rows + (size_t)s * ncol;
-  out[1 + j] = (float)(rj * iv);
+  if (j < p) out[1 + j] = (float)(rj * iv);
   if (j == 0) {
     const double Q = R2 - 2.0 * alpha * R1 + n * alpha * alpha - t1 - t2;   // sum of squared residuals
     const double r1 = R1 - n * alpha - t3;                                  // sum of residuals
     out[0] = (float)(-0.5 * iv * Q - n * (log(sigma) + 0.91893853320467274178));
-    out[1 + kP] = (float)(r1 * iv);
-    out[2 + kP] = (float)((Q * iv * inv - n * inv) * (double)pp.dscale);
+    out[1 + p] = (float)(r1 * iv);
+    out[2 + p] = (float)((Q * iv * inv - n * inv) * (double)pp.dscale);
     if (!(pp.scale > 0.0f)) atomicOr(status, MNF_ST_BAD_PARAM);
   }
 }

@@ -594,19 +594,20 @@ def test_row_permutation_invariance_and_determinism():
 
 
 # ---------------------------------------------------------------------------------------------
-# Normal likelihood, p = 64, no mask: data-only Gram statistics (csrc/dense_gram.cuh)
+# Normal likelihood, p <= 64, no mask: data-only Gram statistics (csrc/dense_gram.cuh)
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n,S", [(1, 37), (127, 37), (20_001, 37), (1_000_003, 37), (5_000, 100)])
-def test_gram_statistics_kernel_against_exact_and_per_particle_kernels(n, S, monkeypatch):
+@pytest.mark.parametrize("n,S,p", [(1, 37, 64), (127, 37, 64), (20_001, 37, 64), (1_000_003, 37, 64), (5_000, 100, 64),
+                                   (20_001, 37, 32), (3_000, 5, 4), (200_003, 64, 48)])
+def test_gram_statistics_kernel_against_exact_and_per_particle_kernels(n, S, p, monkeypatch):
     """Raw C-ABI, Normal(a + X theta, exp(s)) with a latent + constant intercept, a latent scale,
     features with non-zero means (the sums of squares do not cancel in the Gram form) and no row
     mask: the Gram path (TF32 X, exact products, fp32/fp64 sums) and the per-particle tcgen05
     kernel (MNF_DENSE_NO_GRAM=1; three passes of the wide kernel at S = 100, where the Gram path still
-    reads X once) against the exact fp32 SIMT kernel. Ragged and one-row tiles."""
+    reads X once) against the exact fp32 SIMT kernel. Ragged and one-row tiles; feature counts below
+    64 (columns past p are zero-filled by the TMA unit)."""
     import ctypes
     lib = abi.load()
     torch.manual_seed(n)
-    p = 64
     D = p + 2
     X = (torch.randn(n, p, device=DEV) + 0.5 * torch.rand(p, device=DEV)).contiguous()
     y = torch.randn(n, device=DEV) + 0.3
