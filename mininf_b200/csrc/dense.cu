@@ -63,7 +63,7 @@ int launch_dense_tc(const mnf_dense_site_t& site, const float* z, int S, int D, 
   return MNF_OK;
 }
 
-// Normal family, p <= 64, no mask: data-only Gram statistics (dense_gram.cuh). Workspace: per-CTA
+// Normal family, p <= 64: data-only Gram statistics (dense_gram.cuh). Workspace: per-CTA
 // statistics, their fp64 totals, then one row block [S][1 + p + 2] for the common reduction.
 // MNF_DENSE_NO_GRAM=1 keeps the per-particle kernel (developer A/B switch).
 bool gram_disabled() {
@@ -85,12 +85,11 @@ int launch_dense_gram(const mnf_dense_site_t& site, const float* z, int S, int D
   const size_t off_total = ((size_t)grid * gram::kCtaFloats * sizeof(float) + 255) / 256 * 256;
   double* total = reinterpret_cast<double*>(ws + off_total);
   float* rows = reinterpret_cast<float*>(ws + off_total + ((size_t)gram::kCtaFloats * sizeof(double) + 255) / 256 * 256);
-  MNF_CUDA_CHECK(cudaFuncSetAttribute(gram::dense_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)gram::kSmemBytes));
   const char* dev = std::getenv("MNF_GRAM_DEV_SKIP");   // timing experiments only (dense_gram.cuh)
   const uint32_t dev_skip = dev != nullptr ? (uint32_t)std::atoi(dev) : 0u;
-  gram::dense_gram_kernel<<<grid, gram::kThreads, gram::kSmemBytes, stream>>>(map_mn, site, z, S, D, cta_out, status,
-                                                                              dev_skip);
+  auto kernel = site.mask != nullptr ? gram::dense_gram_kernel<true> : gram::dense_gram_kernel<false>;
+  MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram::kSmemBytes));
+  kernel<<<grid, gram::kThreads, gram::kSmemBytes, stream>>>(map_mn, site, z, S, D, cta_out, status, dev_skip);
   MNF_CUDA_CHECK(cudaGetLastError());
   gram::gram_reduce_kernel<<<(gram::kCtaFloats + 255) / 256, 256, 0, stream>>>(cta_out, grid, total);
   MNF_CUDA_CHECK(cudaGetLastError());
@@ -229,7 +228,7 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
       return fail(MNF_E_INVALID, "mnf_dense_sweep: workspace too small%s%s");
     int rc;
     // the Gram statistics do not depend on the particles: any S that a tcgen05 kernel would take
-    if (p <= tc::kP && s.family == MNF_NORMAL && s.mask == nullptr && !gram_disabled() &&
+    if (p <= tc::kP && s.family == MNF_NORMAL && !gram_disabled() &&
         gram_workspace_bytes(grid, S) <= workspace_bytes) {
       float* rows = nullptr;
       if (int rg = launch_dense_gram(s, z, S, D, workspace, &rows, status, grid, stream)) return rg;

@@ -1,5 +1,6 @@
 // Normal likelihood with a dense linear predictor and a row-independent scale, p <= 64 (a multiple
-// of 4; columns past p are zero-filled by the TMA unit and cost tensor time, not HBM traffic), no mask:
+// of 4; columns past p are zero-filled by the TMA unit and cost tensor time, not HBM traffic), with
+// or without a row mask:
 // the sweep reduced to DATA-ONLY Gram statistics (the move site_sweep.cuh makes for scalar links),
 // expanded around the particle MEAN (a0, theta0) so that no large sums cancel:
 //
@@ -68,7 +69,7 @@ constexpr uint32_t kTmemCols = 256;              // four 64-column accumulators
 constexpr uint32_t kOffX = 0;
 constexpr uint32_t kOffY = kOffX + kStages * kXImageBytes;
 constexpr uint32_t kOffBar = kOffY + kStages * kYBytes;
-constexpr uint32_t kNumBars = 2 * kStages + 2 * kAcc;         // full, empty per stage; g_full, g_empty per accumulator
+constexpr uint32_t kNumBars = 3 * kStages + 2 * kAcc;         // full, empty, ready per stage; g_full, g_empty per accumulator
 constexpr uint32_t kOffMisc = kOffBar + 8 * kNumBars;         // tmem slot
 constexpr uint32_t kOffG = kOffMisc + 64;                     // this CTA's Gram rows [64][65] fp32 (written once)
 constexpr uint32_t kOffVec = kOffG + kP * (kP + 1) * 4;       // [4 warps][2][64] doubles: X'y, X'1
@@ -97,6 +98,11 @@ __device__ __forceinline__ float center_icpt(const mnf_dense_site_t& site, const
   return site.icpt_const + t / (float)S;
 }
 
+// MASKED: rows whose mask byte is zero contribute nothing. The y warp stages their response as NaN;
+// the SIMT warps take that as the row's liveness, zero the row in the shared-memory image (and in
+// their registers) and only then release the stage to the MMA issuer through a third barrier, so
+// the Gram product sees X with the masked rows removed.
+template <bool MASKED>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t site, const float* __restrict__ z,
                   int S, int D, float* __restrict__ cta_out, uint32_t* __restrict__ status, uint32_t dev_skip) {
@@ -108,6 +114,7 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
   const uint32_t bars = base + kOffBar;
   const uint32_t bFull = bars, bEmpty = bFull + 8 * kStages;
   const uint32_t bGFull = bEmpty + 8 * kStages, bGEmpty = bGFull + 8 * kAcc;
+  const uint32_t bReady = bGEmpty + 8 * kAcc;         // MASKED only: image cleaned by the SIMT warps
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gbase + kOffMisc);
   float* sG = reinterpret_cast<float*>(gbase + kOffG);
   double* sVec = reinterpret_cast<double*>(gbase + kOffVec);
@@ -124,6 +131,7 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
     for (int i = 0; i < kStages; ++i) {
       mbar_init(bFull + 8 * i, 2);                   // arrive.expect_tx of the producer + the y warp
       mbar_init(bEmpty + 8 * i, 1 + kSimtWarps);     // tcgen05.commit of the Gram product + the SIMT warps
+      mbar_init(bReady + 8 * i, kSimtWarps);
     }
     for (int i = 0; i < kAcc; ++i) {
       mbar_init(bGFull + 8 * i, 1);
@@ -160,46 +168,60 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
     }
     __syncwarp();
   } else if (warp == kWarpY) {
-    // ================= y warp: the tile's responses (0 past the end), NaN check, n ==============
-    const bool y_vec = reinterpret_cast<uintptr_t>(site.y) % 16 == 0;
+    // ================= y warp: the tile's responses (0 past the end; NaN where masked), checks, n ===
+    const bool y_vec = reinterpret_cast<uintptr_t>(site.y) % 16 == 0 &&
+                       (!MASKED || reinterpret_cast<uintptr_t>(site.mask) % 4 == 0);
     int64_t cnt = 0;
     bool bad_value = false;
-    auto fetch = [&](int64_t k) {
+    auto fetch = [&](int64_t k, float4& v, uint32_t& m) {
       const int64_t row = (blockIdx.x + k * gridDim.x) * kTileM + lane * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (y_vec && row + 4 <= site.n_rows) {
         v = __ldg(reinterpret_cast<const float4*>(site.y + row));
+        m = MASKED ? __ldg(reinterpret_cast<const uint32_t*>(site.mask + row)) : 0x01010101u;
       } else {
         float t[4] = {0.f, 0.f, 0.f, 0.f};
+        m = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          if (row + q < site.n_rows) t[q] = __ldg(site.y + row + q);
+          if (row + q < site.n_rows) {
+            t[q] = __ldg(site.y + row + q);
+            m |= ((MASKED ? (uint32_t)__ldg(site.mask + row + q) : 1u) != 0 ? 1u : 0u) << (8 * q);
+          }
         v = make_float4(t[0], t[1], t[2], t[3]);
       }
-      return v;
     };
     // Responses of the next kStages tiles stay in registers: one outstanding load per tile would tie
     // the tile rate to the loaded HBM latency (~1 us), which is above the 0.75 us a tile may take.
     float4 yq[kStages];
+    uint32_t mq[kStages];
 #pragma unroll
-    for (int i = 0; i < kStages; ++i) yq[i] = i < my_tiles ? fetch(i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < kStages; ++i) {
+      yq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      mq[i] = 0;
+      if (i < my_tiles) fetch(i, yq[i], mq[i]);
+    }
     for (int64_t k0 = 0; k0 < my_tiles; k0 += kStages) {
 #pragma unroll
       for (int i = 0; i < kStages; ++i) {
         const int64_t k = k0 + i;                      // k % kStages == i
         if (k < my_tiles) {
-          const float4 v = yq[i];
-          const int64_t row = (blockIdx.x + k * gridDim.x) * kTileM + lane * 4;
-          const int64_t live = min((int64_t)4, max((int64_t)0, site.n_rows - row));
-          cnt += live;
-          const float t = (v.x + v.y) + (v.z + v.w);
-          if (t != t) bad_value = true;                // NaN responses (rows past the end are zeros)
+          float yv[4] = {yq[i].x, yq[i].y, yq[i].z, yq[i].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const bool live = ((mq[i] >> (8 * q)) & 0xFFu) != 0;     // false past the end
+            if (live) {
+              ++cnt;
+              if (yv[q] != yv[q]) bad_value = true;    // a live NaN response is outside the support
+            } else if (MASKED) {
+              yv[q] = __int_as_float(0x7fc00000);      // masked or past the end: not a row
+            }
+          }
           mbar_wait(bEmpty + 8 * i, (uint32_t)(((k / kStages) & 1) ^ 1));
-          tc::sts128(sY + (uint32_t)i * kYBytes + lane * 16, __float_as_uint(v.x), __float_as_uint(v.y),
-                     __float_as_uint(v.z), __float_as_uint(v.w));
+          tc::sts128(sY + (uint32_t)i * kYBytes + lane * 16, __float_as_uint(yv[0]), __float_as_uint(yv[1]),
+                     __float_as_uint(yv[2]), __float_as_uint(yv[3]));
           __syncwarp();
           if (lane == 0) mbar_arrive(bFull + 8 * i);
-          if (k + kStages < my_tiles) yq[i] = fetch(k + kStages);
+          if (k + kStages < my_tiles) fetch(k + kStages, yq[i], mq[i]);
         }
       }
     }
@@ -217,7 +239,7 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
       const uint32_t gb = (uint32_t)(grp % kAcc);
       const bool first = (k % flush) == 0;
       const bool last = (k % flush) == flush - 1 || k == my_tiles - 1;
-      mbar_wait(bFull + 8 * st, (uint32_t)((k / kStages) & 1));
+      mbar_wait((MASKED ? bReady : bFull) + 8 * st, (uint32_t)((k / kStages) & 1));
       if (first) mbar_wait(bGEmpty + 8 * gb, (uint32_t)(((grp / kAcc) & 1) ^ 1));
       tc_fence_after();
       if (dev_skip & 1u) {
@@ -281,9 +303,27 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
           }
         }
         const int own = warp * 32 + 2 * lq + half;
-        const float res_own = own < rows_left ? (ys[own] - a0) - v[0] : 0.f;   // rows past the end: X and y are zeros
+        const float y_own = ys[own];
+        const bool live_own = own < rows_left && (!MASKED || y_own == y_own);   // rows past the end: X and y are zeros
+        const float res_own = live_own ? (y_own - a0) - v[0] : 0.f;
         r1 = res_own;
         r2 = res_own * res_own;
+        if (MASKED) {
+          // masked rows leave the image (and the registers) before the tensor core reads the stage
+          const uint32_t live_bits = __ballot_sync(0xffffffffu, live_own);     // bit 16 h + r: row 2 r + h
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            if (!((live_bits >> ((lane & 16) | r)) & 1u)) {
+              const int row = warp * 32 + 2 * r + half;
+              const uint32_t addr = img + (uint32_t)row * 128u + ((((c16 >> 1) ^ ((uint32_t)row & 3u)) << 5) | ((c16 & 1u) << 4));
+              tc::sts128(addr, 0u, 0u, 0u, 0u);
+              x[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores before the MMA's reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bReady + 8 * st);
+        }
         // pass B: c += x r0, sx += x with the row's residual fetched from its owner
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
@@ -296,6 +336,7 @@ dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t s
           for (int r = 0; r < 16; ++r) { bx[0] += x[r].x; bx[1] += x[r].y; bx[2] += x[r].z; bx[3] += x[r].w; }
         }
       }
+      if (MASKED && (dev_skip & 2u) && lane == 0) mbar_arrive(bReady + 8 * st);
       __syncwarp();
       if (lane == 0) mbar_arrive(bEmpty + 8 * st);
       dr1 += (double)r1;                               // one row per lane and tile: R2 is the dominant term

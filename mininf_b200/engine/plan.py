@@ -531,7 +531,7 @@ class Plan:
         for site, mode in self.dense_sites:
             # the wide tcgen05 kernel takes at most 32 particles per sweep (csrc/abi.cu::tcr_shape)
             kernel = self.lib.raw("mnf_dense_tf32_kernel")(site.family, site.p, self.S) if mode == abi.DENSE_TF32 else 0
-            if kernel != 0 and site.p <= 64 and site.family == abi.NORMAL and not site.mask and \
+            if kernel != 0 and site.p <= 64 and site.family == abi.NORMAL and \
                     os.environ.get("MNF_DENSE_NO_GRAM", "0") in ("", "0"):
                 count += 4      # Gram statistics, their fp64 totals, closed forms per particle, reduction
             else:

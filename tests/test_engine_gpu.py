@@ -596,15 +596,17 @@ def test_row_permutation_invariance_and_determinism():
 # ---------------------------------------------------------------------------------------------
 # Normal likelihood, p <= 64, no mask: data-only Gram statistics (csrc/dense_gram.cuh)
 # ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("masked", [False, True])
 @pytest.mark.parametrize("n,S,p", [(1, 37, 64), (127, 37, 64), (20_001, 37, 64), (1_000_003, 37, 64), (5_000, 100, 64),
                                    (20_001, 37, 32), (3_000, 5, 4), (200_003, 64, 48)])
-def test_gram_statistics_kernel_against_exact_and_per_particle_kernels(n, S, p, monkeypatch):
+def test_gram_statistics_kernel_against_exact_and_per_particle_kernels(n, S, p, masked, monkeypatch):
     """Raw C-ABI, Normal(a + X theta, exp(s)) with a latent + constant intercept, a latent scale,
     features with non-zero means (the sums of squares do not cancel in the Gram form) and no row
     mask: the Gram path (TF32 X, exact products, fp32/fp64 sums) and the per-particle tcgen05
     kernel (MNF_DENSE_NO_GRAM=1; three passes of the wide kernel at S = 100, where the Gram path still
     reads X once) against the exact fp32 SIMT kernel. Ragged and one-row tiles; feature counts below
-    64 (columns past p are zero-filled by the TMA unit)."""
+    64 (columns past p are zero-filled by the TMA unit); with a row mask (30 % of the rows missing, their
+    responses NaN, at an address that is not 4-byte aligned) the masked rows must leave every sum."""
     import ctypes
     lib = abi.load()
     torch.manual_seed(n)
@@ -618,7 +620,16 @@ def test_gram_statistics_kernel_against_exact_and_per_particle_kernels(n, S, p, 
     status = torch.zeros(1, device=DEV, dtype=torch.int32)
     scale = abi.Link(x=None, a_const=0.0, a_lat=p + 1, a_stride=0, b_const=0.0, b_lat=-1, b_stride=0,
                      transform=abi.T_EXP)
-    site = abi.DenseSite(family=abi.NORMAL, p=p, n_rows=n, ldx=p, X=X.data_ptr(), y=y.data_ptr(), mask=None,
+    mask_ptr = None
+    if masked:
+        mask_store = torch.zeros(n + 1, device=DEV, dtype=torch.uint8)
+        mask = mask_store[1:] if (n > 127 and p == 64) else mask_store[:n]   # odd address: per-element loads
+        mask.copy_(torch.rand(n, device=DEV) < 0.7)
+        if n == 1:
+            mask.fill_(1)
+        y = torch.where(mask.bool(), y, torch.full_like(y, float("nan")))
+        mask_ptr = mask.data_ptr()
+    site = abi.DenseSite(family=abi.NORMAL, p=p, n_rows=n, ldx=p, X=X.data_ptr(), y=y.data_ptr(), mask=mask_ptr,
                          theta_lat=0, icpt_lat=p, icpt_const=0.25, reserved=0, scale=scale, weight=3.0)
 
     def sweep(mode):
@@ -660,9 +671,10 @@ def test_gram_statistics_kernel_flags_nan_responses_and_bad_scales():
     ws_bytes = lib.workspace_bytes(S, D)
     ws = torch.empty(ws_bytes, device=DEV, dtype=torch.uint8)
 
-    def flags(y, sigma):
+    def flags(y, sigma, mask=None):
         status = torch.zeros(1, device=DEV, dtype=torch.int32)
-        site = abi.DenseSite(family=abi.NORMAL, p=p, n_rows=n, ldx=p, X=X.data_ptr(), y=y.data_ptr(), mask=None,
+        site = abi.DenseSite(family=abi.NORMAL, p=p, n_rows=n, ldx=p, X=X.data_ptr(), y=y.data_ptr(),
+                             mask=None if mask is None else mask.data_ptr(),
                              theta_lat=0, icpt_lat=-1, icpt_const=0.0, reserved=0, scale=abi.const_link(sigma),
                              weight=1.0)
         acc = torch.zeros(S, D + 1, device=DEV, dtype=torch.float64)
@@ -676,6 +688,11 @@ def test_gram_statistics_kernel_flags_nan_responses_and_bad_scales():
     assert flags(y, -1.0) == abi.ST_BAD_PARAM
     y[777] = float("nan")
     assert flags(y, 1.0) == abi.ST_BAD_VALUE
+    mask = torch.ones(n, device=DEV, dtype=torch.uint8)
+    mask[777] = 0
+    assert flags(y, 1.0, mask) == 0                    # a masked NaN is not an observation
+    mask[777], mask[5] = 1, 0
+    assert flags(y, 1.0, mask) == abi.ST_BAD_VALUE
 
 
 # ---------------------------------------------------------------------------------------------
