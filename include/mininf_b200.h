@@ -210,7 +210,8 @@ int mnf_rsample(const mnf_latent_t* latents_dev, int n_latents, int n_particles,
  * columns and 227 KB of shared memory; up to 32 particles per sweep, 33..128 particles run as 2-4
  * sweeps over X). Intercepts are supported by both. X must also be 16-byte aligned with
  * ldx % 4 == 0 and fewer than 2^31 rows.
- * Whenever the answer is non-zero, a Normal site with p <= 64 (with or without a mask) is swept by
+ * 3 = only the Gram path below applies (Normal, p <= 64, p % 4 == 0, more than 128 particles).
+ * A Normal site with p <= 64 and p % 4 == 0 (with or without a mask, any particle count) is swept by
  * csrc/dense_gram.cuh instead: X'X, X'y, X'1, sum y, sum y^2 in one pass over X (tcgen05, TF32 X,
  * exact products), then the closed forms of every particle's log-density and gradients in fp64 -
  * same inputs, outputs and bytes read, no per-particle work.

@@ -71,6 +71,11 @@ bool gram_disabled() {
   return v != nullptr && v[0] != '\0' && v[0] != '0';
 }
 
+// The Gram statistics do not depend on the particles: any S, with or without a row mask.
+bool gram_shape(int family, int p) {
+  return family == MNF_NORMAL && p > 0 && p <= tc::kP && p % 4 == 0 && !gram_disabled();
+}
+
 size_t gram_workspace_bytes(int grid, int S) {
   return ((size_t)grid * gram::kCtaFloats * sizeof(float) + 255) / 256 * 256 +
          ((size_t)gram::kCtaFloats * sizeof(double) + 255) / 256 * 256 + (size_t)S * (1 + tc::kP + 2) * sizeof(float);
@@ -175,7 +180,8 @@ extern "C" {
 
 int mnf_dense_tf32_kernel(int family, int p, int n_particles) {
   TcrShape sh;
-  return dense_tf32_kernel(family, p, n_particles, 232448 /* sm_100 opt-in shared memory */, &sh);
+  const int which = dense_tf32_kernel(family, p, n_particles, 232448 /* sm_100 opt-in shared memory */, &sh);
+  return which != 0 ? which : (n_particles > 0 && gram_shape(family, p) ? 3 : 0);
 }
 
 int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int n_particles,
@@ -217,7 +223,7 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
     TcrShape sh;
     const int which = dense_tf32_kernel(s.family, p, S, c->max_smem_optin, &sh);
     const bool c2_shape = which == 1, wide_shape = which == 2;
-    if (!aligned || c->cc_major != 10 || !(c2_shape || wide_shape))
+    if (!aligned || c->cc_major != 10 || !(c2_shape || wide_shape || gram_shape(s.family, p)))
       return fail(MNF_E_UNSUPPORTED,
                   "mnf_dense_sweep: TF32 mode needs p == 64 with S <= 64, or p a multiple of 4 with "
                   "S <= 128 (passes of <= 32 particles, (2 + ceil(p/64) * 2) * 32 within 512 TMEM columns), "
@@ -227,13 +233,12 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
     if ((size_t)grid * S * ncol * sizeof(float) > workspace_bytes)
       return fail(MNF_E_INVALID, "mnf_dense_sweep: workspace too small%s%s");
     int rc;
-    // the Gram statistics do not depend on the particles: any S that a tcgen05 kernel would take
-    if (p <= tc::kP && s.family == MNF_NORMAL && !gram_disabled() &&
-        gram_workspace_bytes(grid, S) <= workspace_bytes) {
+    if (gram_shape(s.family, p) && gram_workspace_bytes(grid, S) <= workspace_bytes) {
       float* rows = nullptr;
       if (int rg = launch_dense_gram(s, z, S, D, workspace, &rows, status, grid, stream)) return rg;
       return launch_reduce(rows, 1, S, ncol, map, s.weight, D, acc, stream);
     }
+    if (!(c2_shape || wide_shape)) return fail(MNF_E_INVALID, "mnf_dense_sweep: workspace too small%s%s");
     if (c2_shape) {
       if (s.family == MNF_NORMAL)
         rc = has_icpt ? launch_dense_tc<MNF_NORMAL, true>(s, z, S, D, partial, status, grid, stream)

@@ -598,7 +598,7 @@ def test_row_permutation_invariance_and_determinism():
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("masked", [False, True])
 @pytest.mark.parametrize("n,S,p", [(1, 37, 64), (127, 37, 64), (20_001, 37, 64), (1_000_003, 37, 64), (5_000, 100, 64),
-                                   (20_001, 37, 32), (3_000, 5, 4), (200_003, 64, 48)])
+                                   (20_001, 37, 32), (3_000, 5, 4), (200_003, 64, 48), (5_000, 200, 64)])
 def test_gram_statistics_kernel_against_exact_and_per_particle_kernels(n, S, p, masked, monkeypatch):
     """Raw C-ABI, Normal(a + X theta, exp(s)) with a latent + constant intercept, a latent scale,
     features with non-zero means (the sums of squares do not cancel in the Gram form) and no row
@@ -645,8 +645,14 @@ def test_gram_statistics_kernel_against_exact_and_per_particle_kernels(n, S, p, 
     gram = sweep(abi.DENSE_TF32)
     assert np.array_equal(gram, sweep(abi.DENSE_TF32))                  # fixed-order reductions
     monkeypatch.setenv("MNF_DENSE_NO_GRAM", "1")
-    per_particle = sweep(abi.DENSE_TF32)
-    assert not np.array_equal(gram, per_particle)                        # the switch selects another kernel
+    if S > 128:                                        # beyond the per-particle kernels: only the Gram path
+        assert lib.raw("mnf_dense_tf32_kernel")(abi.NORMAL, p, S) == 0
+        monkeypatch.delenv("MNF_DENSE_NO_GRAM")
+        assert lib.raw("mnf_dense_tf32_kernel")(abi.NORMAL, p, S) == 3
+        per_particle = exact
+    else:
+        per_particle = sweep(abi.DENSE_TF32)
+    assert not np.array_equal(gram, per_particle)                        # the switch selects another kernel (or: not the exact one)
     for name, fast in (("gram", gram), ("per-particle", per_particle)):
         # TF32 rounding of X is unbiased: few rows state the loose tolerance, 1e6 rows the tight one
         tol = 5e-4 if n < 100_000 else 2e-5
