@@ -57,7 +57,7 @@ using tcr::tc_mma_ss;
 
 constexpr int kStages = 6;       // MN-major image ring (32 KB each)
 constexpr int kFlush = 2;        // tiles accumulated in TMEM before the Gram tile is drained (truncating adds)
-constexpr int kFlush64 = 64;     // tiles per fp32 run of the X'y / X'1 sums before they move to fp64
+constexpr int kFlush64 = 64;     // tiles per fp32 run of the X'r0 / X'1 sums before they move to fp64
 constexpr int kSimtWarps = 4;
 constexpr int kWarpTma = 4, kWarpY = 6, kWarpMma = 7;
 constexpr int kWarpDrain0 = 8;   // warps 8..11: TMEM lane quadrants 0..3
@@ -72,7 +72,7 @@ constexpr uint32_t kOffBar = kOffY + kStages * kYBytes;
 constexpr uint32_t kNumBars = 3 * kStages + 2 * kAcc;         // full, empty, ready per stage; g_full, g_empty per accumulator
 constexpr uint32_t kOffMisc = kOffBar + 8 * kNumBars;         // tmem slot
 constexpr uint32_t kOffG = kOffMisc + 64;                     // this CTA's Gram rows [64][65] fp32 (written once)
-constexpr uint32_t kOffVec = kOffG + kP * (kP + 1) * 4;       // [4 warps][2][64] doubles: X'y, X'1
+constexpr uint32_t kOffVec = kOffG + kP * (kP + 1) * 4;       // [4 warps][2][64] doubles: X'r0, X'1
 constexpr uint32_t kOffScal = kOffVec + kSimtWarps * 2 * kP * 8;   // [4 warps][2 halves][R1, R2] doubles, then n
 constexpr uint32_t kOffCenter = kOffScal + (kSimtWarps * 4 + 1) * 8 + 8;   // theta0 [64] floats, a0
 constexpr uint32_t kSmemBytes = kOffCenter + (kP + 4) * 4 + 1024 /* alignment slack */;
@@ -106,7 +106,8 @@ template <bool MASKED>
 __global__ void __launch_bounds__(kThreads, 1)
 dense_gram_kernel(const __grid_constant__ CUtensorMap map_mn, mnf_dense_site_t site, const float* __restrict__ z,
                   int S, int D, float* __restrict__ cta_out, uint32_t* __restrict__ status, uint32_t dev_skip) {
-  // dev_skip (MNF_GRAM_DEV_SKIP, timing experiments only, results are wrong): 1 = no MMAs, 2 = no X'y / X'1
+  // dev_skip (MNF_GRAM_DEV_SKIP, timing experiments only, results are wrong): 1 = no MMAs, 2 = no SIMT sums,
+  // bits 8.. = tiles per TMEM accumulation run instead of kFlush
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzled images: 1024-byte alignment
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
