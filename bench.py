@@ -424,10 +424,17 @@ def run_b200(args):
         plan.record_sweep_events = True
         begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         begin.record()
+        dbg, t_host0 = [], time.perf_counter()
         for _ in range(steps):
             eager_step()
+            if os.environ.get("MNF_BENCH_STEP_TIMES"):
+                dbg.append((torch.cuda.Event(enable_timing=True), time.perf_counter() - t_host0))
+                dbg[-1][0].record()
         end.record()
         fence()
+        if dbg:
+            print(f"rank {rank} eager loop: gpu step ends (ms) " + " ".join(f"{begin.elapsed_time(e):.2f}" for e, _ in dbg)
+                  + " | host returns (ms) " + " ".join(f"{1e3 * h:.2f}" for _, h in dbg), file=sys.stderr)
         plan.record_sweep_events = False
         timed = [b.elapsed_time(e) for (b, e), kind in zip(plan.sweep_events, plan.sweep_event_kinds)
                  if kind == w.event_kind]
@@ -469,10 +476,17 @@ def run_b200(args):
     wall0 = time.time()
     torch.cuda.nvtx.range_push("timed")       # lets `ncu --nvtx --nvtx-include timed/` see only these steps
     begin.record()
+    marks, t_host0 = [], time.perf_counter()   # MNF_BENCH_STEP_TIMES=1: per-step times on stderr (diagnostic)
     for _ in range(args.steps):
         loss = step()
+        if os.environ.get("MNF_BENCH_STEP_TIMES"):
+            marks.append((torch.cuda.Event(enable_timing=True), time.perf_counter() - t_host0))
+            marks[-1][0].record()
     end.record()
     fence()
+    if marks:
+        print(f"rank {rank} timed loop: gpu step ends (ms) " + " ".join(f"{begin.elapsed_time(m):.2f}" for m, _ in marks)
+              + " | host returns (ms) " + " ".join(f"{1e3 * h:.2f}" for _, h in marks), file=sys.stderr)
     torch.cuda.nvtx.range_pop()
     wall1 = time.time()
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
