@@ -63,6 +63,24 @@ def test_argument_errors_do_not_need_a_gpu(library):
         library.call("mnf_site_sweep", None, 1, None, 1, 1, None, None, 0, None, None)
 
 
+def test_dense_kernel_query_is_host_only(library, monkeypatch):
+    """mnf_dense_tf32_kernel: which tensor-core kernel a (family, p, S) shape gets - 1 dense_tc.cuh,
+    2 dense_tcr.cuh, 3 only the Gram-statistics path (Normal, p <= 64, beyond 128 particles), 0 none."""
+    query = library.raw("mnf_dense_tf32_kernel")
+    monkeypatch.delenv("MNF_DENSE_NO_GRAM", raising=False)
+    monkeypatch.delenv("MNF_DENSE_TC_KERNEL", raising=False)
+    assert query(abi.NORMAL, 64, 64) == 1
+    assert query(abi.BERNOULLI_LOGITS, 256, 16) == 2
+    assert query(abi.BERNOULLI_LOGITS, 64, 16) == 2          # the Bernoulli epilogue prefers 16/32 particle slots
+    assert query(abi.POISSON, 64, 32) == 1
+    assert query(abi.NORMAL, 128, 100) == 2                  # passes of <= 32 particles
+    assert query(abi.NORMAL, 64, 200) == 3 and query(abi.NORMAL, 8, 1000) == 3
+    assert query(abi.NORMAL, 66, 200) == 0 and query(abi.NORMAL, 128, 200) == 0
+    assert query(abi.POISSON, 64, 200) == 0 and query(abi.NORMAL, 7, 4) == 0
+    monkeypatch.setenv("MNF_DENSE_NO_GRAM", "1")
+    assert query(abi.NORMAL, 64, 200) == 0 and query(abi.NORMAL, 64, 64) == 1
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(abi, "_LIBRARY", None)
     monkeypatch.setattr(build, "LIB_PATH", tmp_path / "nope.so")
