@@ -1,23 +1,30 @@
 """Benchmark of the ELBO + gradient hot path (BASELINE.json metric) on synthetic data.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|c4|c5]
+                    [--closed-form] [--weak] [--eager]
 
 Default workload c2 (config[1] of BASELINE.json): Bayesian linear regression, mean-field Normal
-approximation, p = 64 features, N = 1e8 observations PER GPU (weak scaling), S = 64 particles.
-`--workload c3` (config[2]): minibatch logistic regression, p = 256, batches of 1e7 rows per GPU
-of a declared N = 1e9 stream, S = 16; every step conditions the model on the next batch (two
-resident batches alternate; the plan is rebound, not retraced).
-`--workload c4` (config[3]): regression with feature uncertainty, N = 1e7 rows per GPU with a
+approximation, p = 64 features, N = 1e8 observations IN TOTAL, S = 64 particles, evaluated by the
+BLACK-BOX sweep: one log-density + score evaluation per (particle, observation) on the tcgen05
+kernel of csrc/dense_tc.cuh. `--closed-form` lets Normal sites use their data-only sufficient
+statistics instead (Gram matrix / six sums / Chebyshev moments; no per-particle work) - reported
+as a clearly named secondary object in the default run.
+Under torchrun (N ranks) the default is STRONG scaling: the global data set is the same at every
+world size (256 row chunks, chunk c seeded seed0 + c) and rank r owns chunks
+[r*256/N, (r+1)*256/N); `--weak` gives every rank the full configuration instead.
+`--workload c3` (config[2]): minibatch logistic regression, p = 256, batches of 1e7 rows of a
+declared N = 1e9 stream, S = 16; two resident batches alternate (one recorded step each).
+`--workload c4` (config[3]): regression with feature uncertainty, N = 1e7 rows with a
 per-observation latent feature vector (p = 32), S = 32 (the row-latent kernel; instruction-bound).
-`--workload c5` (config[4]): masked Poisson + Normal sites over N = 1e8 elements per GPU, 30 %
-missing, S = 64 (the site sweeps; the Poisson site is bound by the MUFU pipe).
-A step is one full SVI step through the public API: zero_grad, EvidenceLowerBoundLoss forward
-(fused ELBO + gradient kernels), backward through the parameter transforms, Adam. The metric is
+`--workload c5` (config[4]): masked Poisson + Normal sites over N = 1e8 elements, 30 % missing,
+S = 64 (site sweeps; closed-form statistics by default for this workload, black-box beside it).
+A step is one full SVI step: parameter transforms, reparameterised draws, ELBO + gradient kernels,
+chain rule, Adam - `mininf_b200.nn.FusedSVIStep` (one native call, replayed from a CUDA graph);
+models with per-observation latents (c4) use `GraphedStep` with torch's fused Adam. The metric is
 particle-observation log-density evaluations per second: rows * S / time, whole job.
 
-`--impl reference` times the reference algorithm's CPU implementation (the oracle port: the
-reference is pure Python over torch.distributions and cannot travel to the GPU box) on the host
-cores, on a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference (baseline/_ref, installed from /root/reference)
+on the host cores, on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -41,7 +48,8 @@ N_CHUNKS = 256     # synthetic rows are generated in 256 chunks, chunk c seeded 
 
 class Workload:
     def __init__(self, key, name, p, particles, rows, family, declared_rows, n_batches, kernel, traffic_file,
-                 event_kind="dense", cpu_sample=(4_000_000, 4), bytes_per_row=None, bound_note=None):
+                 event_kind="dense", cpu_sample=(4_000_000, 4), bytes_per_row=None, bound_note=None,
+                 closed_form_kernel=None, closed_form_default=False, black_box_kernel=None):
         self.key, self.name, self.p, self.particles, self.rows = key, name, p, particles, rows
         self.family, self.declared_rows, self.n_batches = family, declared_rows, n_batches
         self.kernel, self.traffic_file = kernel, traffic_file
@@ -49,12 +57,16 @@ class Workload:
         # algorithmic bytes one sweep call moves per row
         self.bytes_per_row = bytes_per_row if bytes_per_row is not None else 4 * p + 4
         self.bound_note = bound_note
+        # Normal / Poisson sites have closed forms in data-only statistics; which path is the headline
+        self.closed_form_kernel, self.closed_form_default = closed_form_kernel, closed_form_default
+        self.black_box_kernel = black_box_kernel
 
 
 WORKLOADS = {
     "c2": Workload("c2", "bayesian_linear_regression_p64_N1e8_S64", 64, 64, 100_000_000, "normal", None, 1,
-                   "mnf::gram::dense_gram_kernel (+ gram_reduce / gram_finish / reduce_partials, ~15 us together)",
-                   "dense_gram_traffic.json"),
+                   "mnf::tc::dense_tc_kernel<Normal> (+ its partial-sum reduction, ~8 us)",
+                   "dense_tc_traffic.json",
+                   closed_form_kernel="mnf::gram::dense_gram_kernel (+ gram_reduce / gram_finish / reduce_partials)"),
     "c3": Workload("c3", "minibatch_logistic_regression_p256_batch1e7_of_N1e9_S16", 256, 16, 10_000_000,
                    "bernoulli", 1_000_000_000, 2,
                    "mnf::tcr::dense_tcr_kernel<BernoulliLogits, 16> (+ its partial-sum reduction)",
@@ -68,6 +80,9 @@ WORKLOADS = {
                    None, 1, "mnf::poisson_range_kernel + mnf::poisson_moment_kernel + mnf::normal_stats_kernel "
                             "(one mnf_site_sweep call)",
                    "site_sweep_traffic.json", event_kind="site", cpu_sample=(10_000_000, 4), bytes_per_row=14,
+                   closed_form_default=True,
+                   black_box_kernel="mnf::poisson_exp_kernel (one ex2 per live element and particle) + "
+                                    "mnf::site_sweep_kernel (Normal site, per particle)",
                    bound_note="both sites are reduced to data-only sufficient statistics (33 Chebyshev moments of "
                               "the covariate for the Poisson site, six sums for the Normal site): three streaming "
                               "passes that move 23 B per element for 14 algorithmic bytes (the covariate is read by "
@@ -84,8 +99,15 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", type=float, default=float(os.environ.get("MNF_BENCH_ROWS", 0)),
-                    help="observations (c3: batch rows) per GPU; default: the BASELINE configuration")
+                    help="observations (c3: batch rows) in total; default: the BASELINE configuration")
     ap.add_argument("--eager", action="store_true", help="do not replay the step from a CUDA graph")
+    ap.add_argument("--closed-form", action="store_true",
+                    help="let sites with closed-form sufficient statistics skip the per-particle sweep")
+    ap.add_argument("--black-box", action="store_true", help="force the per-particle sweep (c5 defaults to closed form)")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: the full configuration on every rank")
+    ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"], help="how sharded ranks combine partial sums")
+    ap.add_argument("--sustain", type=float, default=1.0, help="seconds of back-to-back steps for the sustained figure")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary objects (closed form, reference on CUDA)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -106,20 +128,31 @@ def chunk_bounds(n, chunk):
     return min(chunk * per, n), min((chunk + 1) * per, n)
 
 
-def make_data(w, n, device, seed0):
-    """One resident data set (dict of device tensors) in the chunk-seeded recipe."""
+def rank_rows(n, rank, world):
+    """Rows owned by `rank`: chunks [rank*256/W, (rank+1)*256/W) of the global data set."""
+    lo, _ = chunk_bounds(n, rank * N_CHUNKS // world)
+    _, hi = chunk_bounds(n, (rank + 1) * N_CHUNKS // world - 1)
+    return lo, hi
+
+
+def make_data(w, n, device, seed0, rows=None):
+    """Rows [rows[0], rows[1]) (default: all) of the global data set of `n` rows in the chunk-seeded
+    recipe: chunk c is drawn from seed0 + c, so the data are identical at every world size."""
     g = torch.Generator(device=device)
     g.manual_seed(SEED0 - 1)
+    first, last = rows if rows is not None else (0, n)
+    k_local = last - first
+    chunks = [(chunk, *chunk_bounds(n, chunk)) for chunk in range(N_CHUNKS)]
+    chunks = [(chunk, lo, hi) for chunk, lo, hi in chunks if hi > lo and lo >= first and hi <= last]
+    assert sum(hi - lo for _, lo, hi in chunks) == k_local, "rank rows must be whole chunks"
     if w.family == "missing":
-        x = torch.empty(n, device=device)
-        counts = torch.empty(n, device=device)
-        wv = torch.empty(n, device=device)
-        m_counts = torch.empty(n, device=device, dtype=torch.bool)
-        m_w = torch.empty(n, device=device, dtype=torch.bool)
-        for chunk in range(N_CHUNKS):
-            lo, hi = chunk_bounds(n, chunk)
-            if hi <= lo:
-                continue
+        x = torch.empty(k_local, device=device)
+        counts = torch.empty(k_local, device=device)
+        wv = torch.empty(k_local, device=device)
+        m_counts = torch.empty(k_local, device=device, dtype=torch.bool)
+        m_w = torch.empty(k_local, device=device, dtype=torch.bool)
+        for chunk, lo, hi in chunks:
+            lo, hi = lo - first, hi - first
             g.manual_seed(seed0 + chunk)
             k = hi - lo
             torch.randn(k, generator=g, device=device, out=x[lo:hi])
@@ -132,12 +165,10 @@ def make_data(w, n, device, seed0):
         wv.mul_(m_w)
         return {"x": x, "counts": counts, "w": wv, "m_counts": m_counts, "m_w": m_w}
     theta_true = torch.randn(w.p, generator=g, device=device) / w.p ** 0.5
-    X = torch.empty(n, w.p, device=device)
-    y = torch.empty(n, device=device)
-    for chunk in range(N_CHUNKS):
-        lo, hi = chunk_bounds(n, chunk)
-        if hi <= lo:
-            continue
+    X = torch.empty(k_local, w.p, device=device)
+    y = torch.empty(k_local, device=device)
+    for chunk, lo, hi in chunks:
+        lo, hi = lo - first, hi - first
         g.manual_seed(seed0 + chunk)
         torch.randn(hi - lo, w.p, generator=g, device=device, out=X[lo:hi])
         if w.family == "normal":
@@ -151,9 +182,11 @@ def make_data(w, n, device, seed0):
     return {"X": X, "y": y}
 
 
-def model_factory(m, w, n_rows, data):
+def model_factory(m, w, n_rows, data, declared=None):
+    """The workload's model over `n_rows` local rows; `declared` is the population size behind a
+    minibatch (c3; a rank of a sharded run declares its share of it)."""
     from torch.distributions import Bernoulli, Gamma, Normal, Poisson
-    declared = w.declared_rows or n_rows
+    declared = declared or w.declared_rows or n_rows
 
     def regression():
         theta = m.sample("theta", Normal(0, 1), w.p)
@@ -198,28 +231,29 @@ def condition_on(m, model, w, data):
     return m.condition(model, X=data["X"], y=data["y"])
 
 
-def make_approximation(m, w, n_rows, data, device):
-    """name -> ParameterizedDistribution (validate_args=False is passed through to
-    torch.distributions exactly as in the reference: its constructor check is a host round trip
-    per step; the kernels check scales on the device)."""
+def make_approximation(m, w, n_rows, data, device, validate=False):
+    """name -> ParameterizedDistribution. With `validate=False`, `validate_args=False` is passed
+    through to torch.distributions exactly as in the reference (its constructor check is a host
+    round trip per step; the kernels check scales on the device); the reference arm keeps the
+    shipped default (validation on)."""
     from torch.distributions import Gamma, Normal
-    PD = m.nn.ParameterizedDistribution
+    extra = {} if validate else {"validate_args": False}
+
+    def PD(cls, **parameters):
+        return m.nn.ParameterizedDistribution(cls, **parameters, **extra)
 
     def scalar(value):
         return torch.tensor(value, device=device)
 
     if w.family in ("normal", "bernoulli"):
-        return {"theta": PD(Normal, loc=torch.zeros(w.p, device=device), scale=0.1 * torch.ones(w.p, device=device),
-                            validate_args=False)}
+        return {"theta": PD(Normal, loc=torch.zeros(w.p, device=device), scale=0.1 * torch.ones(w.p, device=device))}
     if w.family == "rowlatent":
-        return {"population_scale": PD(Gamma, concentration=scalar(2.0), rate=scalar(2.0), validate_args=False),
-                "z": PD(Normal, loc=data["X"].clone(), scale=torch.ones(n_rows, w.p, device=device),
-                        validate_args=False),
-                "intercept": PD(Normal, loc=scalar(0.1), scale=scalar(0.2), validate_args=False),
-                "slope": PD(Normal, loc=torch.zeros(w.p, device=device), scale=0.2 * torch.ones(w.p, device=device),
-                            validate_args=False)}
-    approximation = {k: PD(Normal, loc=scalar(0.1), scale=scalar(0.2), validate_args=False) for k in "abcd"}
-    approximation["sigma"] = PD(Gamma, concentration=scalar(2.0), rate=scalar(2.0), validate_args=False)
+        return {"population_scale": PD(Gamma, concentration=scalar(2.0), rate=scalar(2.0)),
+                "z": PD(Normal, loc=data["X"].clone(), scale=torch.ones(n_rows, w.p, device=device)),
+                "intercept": PD(Normal, loc=scalar(0.1), scale=scalar(0.2)),
+                "slope": PD(Normal, loc=torch.zeros(w.p, device=device), scale=0.2 * torch.ones(w.p, device=device))}
+    approximation = {k: PD(Normal, loc=scalar(0.1), scale=scalar(0.2)) for k in "abcd"}
+    approximation["sigma"] = PD(Gamma, concentration=scalar(2.0), rate=scalar(2.0))
     return approximation
 
 
@@ -279,11 +313,64 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port on the host cores
+# CPU baseline / reference arm: the UNMODIFIED reference (baseline/_ref) on the host cores
 # ---------------------------------------------------------------------------------------------
-def cpu_sample(w, rows, particles, steps, warmup):
-    """Time the CPU restatement of the reference path (validation on, as shipped) on a bounded
-    sample: `rows` observations, `particles` sequential evaluations per step."""
+REF_DIR = ROOT / "baseline" / "_ref"
+
+
+def load_reference():
+    """The unmodified tillahoffmann/mininf package installed under baseline/_ref (git-ignored; it
+    travels to the GPU box with the snapshot). Returns None when it is not there."""
+    if not (REF_DIR / "mininf" / "__init__.py").exists():
+        return None
+    if str(REF_DIR) not in sys.path:
+        sys.path.insert(0, str(REF_DIR))
+    import importlib
+    return importlib.import_module("mininf")
+
+
+def reference_sample(w, rows, particles, steps, warmup, device="cpu", validate=True):
+    """Time the reference's own SVI step (README.md:66-69) on a bounded sample: `rows` observations,
+    `particles` sequential `mininf.nn.EvidenceLowerBoundLoss` calls per step (the reference draws
+    one particle per call, mininf/nn.py:217), validation on as shipped. Falls back to the oracle
+    port when baseline/_ref is missing. Returns (evals/s, seconds per step, kind)."""
+    ref = load_reference()
+    if ref is None:
+        value, seconds = port_sample(w, rows, particles, steps, warmup)
+        return value, seconds, "port"
+    torch.manual_seed(0)
+    device = torch.device(device)
+    data = make_data(w, rows, device, SEED0)
+    modules = make_approximation(ref, w, rows, data, device, validate=validate)
+    parameters = [p for module in modules.values() for p in module.parameters()]
+    optimizer = torch.optim.Adam(parameters, lr=0.01)
+    loss_module = ref.nn.EvidenceLowerBoundLoss()
+    conditioned = condition_on(ref, model_factory(ref, w, rows, data), w, data)
+
+    def step():
+        optimizer.zero_grad()
+        for _ in range(particles):
+            loss = loss_module(conditioned, {name: module() for name, module in modules.items()})
+            (loss / particles).backward()
+        optimizer.step()
+
+    def sync():
+        if device.type == "cuda":
+            torch.cuda.synchronize(device)
+
+    for _ in range(warmup):
+        step()
+    sync()
+    begin = time.perf_counter()
+    for _ in range(steps):
+        step()
+    sync()
+    seconds = (time.perf_counter() - begin) / steps
+    return rows * particles / seconds, seconds, "reference"
+
+
+def port_sample(w, rows, particles, steps, warmup):
+    """The oracle port of the same step (only used when baseline/_ref is absent)."""
     from oracle import configs, elbo
     torch.manual_seed(0)
     if w.family == "normal":
@@ -312,6 +399,13 @@ def cpu_sample(w, rows, particles, steps, warmup):
     return rows * particles / seconds, seconds
 
 
+def cpu_sample_text(w, rows, particles, cores, kind):
+    what = ("the unmodified reference (baseline/_ref: mininf.nn.EvidenceLowerBoundLoss, one call per particle, "
+            "validation on as shipped)" if kind == "reference" else
+            "oracle port of mininf's torch.distributions path, validation on")
+    return f"{rows} rows x {particles} particles per step of the {w.name} workload; {what}, {cores} threads"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -321,17 +415,16 @@ def run_reference(args):
     # torchrun exports OMP_NUM_THREADS=1 to every rank; rank 0 runs alone here, so give the CPU arm
     # every host thread this process may use
     torch.set_num_threads(max(len(os.sched_getaffinity(0)), 1))
-    value, seconds = cpu_sample(w, rows, particles, args.steps, args.warmup)
+    value, seconds, kind = reference_sample(w, rows, particles, args.steps, args.warmup)
     cores = torch.get_num_threads()
-    sample = (f"{rows} rows x {particles} particles per step of the {w.name} workload "
-              f"(oracle port of mininf's torch.distributions path, validation on, {cores} threads)")
+    sample = cpu_sample_text(w, rows, particles, cores, kind)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w.name, "rows_per_gpu": w.rows,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w.name, "rows_total": w.rows,
                    "features": w.p, "particles": w.particles, "cpu_sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -344,7 +437,6 @@ def run_reference(args):
 def run_b200(args):
     import torch.distributed as dist
     import mininf_b200 as mininf
-    from torch.distributions import Normal
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -370,35 +462,28 @@ def run_b200(args):
 
     w = WORKLOADS[args.workload]
     P, S = w.p, w.particles
-    n_rows = int(args.rows) or w.rows
-    # one resident data set or the resident batches of the stream (c3), 256 seeds apart
-    batches = [make_data(w, n_rows, device, SEED0 + (rank * w.n_batches + b) * 256) for b in range(w.n_batches)]
+    n_total = int(args.rows) or w.rows                 # observations (c3: batch rows) of the whole job ...
+    strong = distributed and not args.weak
+    if args.weak:
+        n_total *= world                               # ... unless every rank gets the full configuration
+    lo, hi = rank_rows(n_total, rank, world)
+    n_rows = hi - lo                                   # this rank's rows: whole chunks of the global data set
+    closed_form = (args.closed_form or w.closed_form_default) and not args.black_box
+    declared = (w.declared_rows * (world if args.weak else 1)) // world if w.declared_rows else None
+    # one resident data set, or the resident batches of the stream (c3), 256 seeds apart
+    batches = [make_data(w, n_total, device, SEED0 + b * 256, rows=(lo, hi)) for b in range(w.n_batches)]
     modules = make_approximation(mininf, w, n_rows, batches[0], device)
-    parameters = [p for module in modules.values() for p in module.parameters()]
     streaming = w.n_batches > 1
-    # fused=True: torch's single-kernel Adam (the foreach default issues six passes over every
-    # parameter, which shows at C4's 6.4e8 variational parameters)
-    optimizer = torch.optim.Adam(parameters, lr=0.01, capturable=not args.eager, fused=True)
-    loss_module = mininf.nn.EvidenceLowerBoundLoss(S, dense_precision="tf32",
-                                                   process_group=True if distributed else None)
-    model = model_factory(mininf, w, n_rows, batches[0])
-    conditioned = condition_on(mininf, model, w, batches[0])
-    calls = [0]
+    fused = w.family != "rowlatent"                    # per-observation latents: GraphedStep + torch Adam
+    graphed = not args.eager
+    model = model_factory(mininf, w, n_rows, batches[0], declared)
+
+    def make_loss(closed):
+        return mininf.nn.EvidenceLowerBoundLoss(S, dense_precision="tf32", closed_form=closed, reduce=args.reduce,
+                                                process_group=True if distributed else None)
 
     def approximation():
         return {name: module() for name, module in modules.items()}
-
-    def eager_step():
-        optimizer.zero_grad(set_to_none=True)
-        if streaming:       # condition on the next batch, as the reference's data-loader loop does
-            batch = batches[calls[0] % w.n_batches]
-            calls[0] += 1
-            loss = loss_module(condition_on(mininf, model, w, batch), approximation())
-        else:
-            loss = loss_module(conditioned, approximation())
-        loss.backward()
-        optimizer.step()
-        return loss
 
     def fence():
         if distributed:
@@ -408,107 +493,136 @@ def run_b200(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        eager_step()
-    fence()
-    plan = loss_module.last_plan
+
+    # ---- the step -------------------------------------------------------------------------------
+    calls = [0]
+    loss_modules = [make_loss(closed_form) for _ in batches]
+    if fused:
+        steps_by_batch = []
+        for loss_module, batch in zip(loss_modules, batches):
+            steps_by_batch.append(mininf.nn.FusedSVIStep(
+                loss_module, condition_on(mininf, model, w, batch), modules, lr=0.01, graph=graphed,
+                share_with=steps_by_batch[0] if steps_by_batch else None))
+        optimizer = None
+    else:
+        parameters = [p for module in modules.values() for p in module.parameters()]
+        # fused=True: torch's single-kernel Adam (the foreach default issues six passes over every
+        # parameter, which shows at C4's 6.4e8 variational parameters)
+        optimizer = torch.optim.Adam(parameters, lr=0.01, capturable=graphed, fused=True)
+        if graphed:
+            steps_by_batch = [mininf.nn.GraphedStep(loss_module, condition_on(mininf, model, w, batch), approximation,
+                                                    optimizer) for loss_module, batch in zip(loss_modules, batches)]
+        else:
+            def eager(loss_module, batch):
+                def run():
+                    optimizer.zero_grad(set_to_none=True)
+                    loss = loss_module(condition_on(mininf, model, w, batch), approximation())
+                    loss.backward()
+                    optimizer.step()
+                    return loss
+                return run
+            steps_by_batch = [eager(loss_module, batch) for loss_module, batch in zip(loss_modules, batches)]
+
+    def step():
+        run = steps_by_batch[calls[0] % len(steps_by_batch)]
+        calls[0] += 1
+        return run()
+
+    plan = loss_modules[0].last_plan
 
     # Roofline numerator: per-launch duration of the workload's sweep call from CUDA events recorded
-    # around the launch on its stream, averaged over eager steps on the same resident data (events
-    # inside a graph replay cannot be timed; the kernel and its arguments are identical). Under the
-    # power cap the SM clock drifts over a run, so the measurement is taken right before AND right
-    # after the timed region and both halves are averaged.
-    def measure_sweep(steps):
+    # around the launch on its stream (Plan.step with `record_sweep_events`: the same kernels with the
+    # same arguments as the recorded step, through the phase-level C-ABI; events inside a graph replay
+    # cannot be timed). Under the power cap the SM clock drifts over a run, so the measurement is taken
+    # right before AND right after the timed region and both halves are averaged.
+    def measure_sweep(repeats):
         plan.sweep_events.clear()
         plan.sweep_event_kinds.clear()
         plan.record_sweep_events = True
-        begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        begin.record()
-        dbg, t_host0 = [], time.perf_counter()
-        for _ in range(steps):
-            eager_step()
-            if os.environ.get("MNF_BENCH_STEP_TIMES"):
-                dbg.append((torch.cuda.Event(enable_timing=True), time.perf_counter() - t_host0))
-                dbg[-1][0].record()
-        end.record()
+        for i in range(repeats):
+            if fused:
+                plan.step(None, 1234, 1 << 50 | i)
+            else:      # row latents: the loss call binds this step's parameter / gradient buffers
+                with torch.no_grad():
+                    loss_modules[0](condition_on(mininf, model, w, batches[0]), approximation())
         fence()
-        if dbg:
-            print(f"rank {rank} eager loop: gpu step ends (ms) " + " ".join(f"{begin.elapsed_time(e):.2f}" for e, _ in dbg)
-                  + " | host returns (ms) " + " ".join(f"{1e3 * h:.2f}" for _, h in dbg), file=sys.stderr)
         plan.record_sweep_events = False
         timed = [b.elapsed_time(e) for (b, e), kind in zip(plan.sweep_events, plan.sweep_event_kinds)
                  if kind == w.event_kind]
-        return sum(timed) / max(len(timed), 1), begin.elapsed_time(end) / steps
+        return sum(timed) / max(len(timed), 1)
 
-    kernel_ms_before, eager_ms_per_step = measure_sweep(args.steps)
-
-    # The SVI step is recorded once into a CUDA graph (mininf_b200.nn.GraphedStep) and replayed:
-    # the same kernels in the same order, one launch per step. The minibatch stream (c3) records
-    # one graph per resident batch - the pattern for a ring of staging buffers: conditioned tensors
-    # are baked into a graph by address - and replays them in turn; all graphs share the
-    # parameters and the optimizer. Sharded runs keep the eager loop: capturing the NCCL
-    # all-reduce of this torch/NCCL build into the graph hung on 2 GPUs.
-    graphed = not args.eager and not distributed
-    step, graph_note = eager_step, None
-    if graphed:
-        try:
-            if streaming:
-                replays = []
-                for batch in batches:
-                    module_b = mininf.nn.EvidenceLowerBoundLoss(S, dense_precision="tf32")
-                    replays.append(mininf.nn.GraphedStep(module_b, condition_on(mininf, model, w, batch),
-                                                         approximation, optimizer))
-
-                def step():
-                    replay = replays[calls[0] % len(replays)]
-                    calls[0] += 1
-                    return replay()
-            else:
-                step = mininf.nn.GraphedStep(loss_module, conditioned, approximation, optimizer)
-        except Exception as error:  # noqa: BLE001  keep measuring: the eager loop runs the same kernels
-            graphed, graph_note = False, f"CUDA graph capture failed ({type(error).__name__}); eager launches"
-            step = eager_step
-            torch.cuda.synchronize()
     for _ in range(max(args.warmup, 3)):
         step()
-    begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fence()
-    wall0 = time.time()
+    kernel_ms_before = measure_sweep(args.steps)
+
+    def timed_loop(n_steps, marks=None):
+        begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fence()
+        t0 = time.time()
+        begin.record()
+        loss = None
+        for _ in range(n_steps):
+            loss = step()
+        end.record()
+        fence()
+        t1 = time.time()
+        elapsed = begin.elapsed_time(end)
+        by_rank = None
+        if distributed:
+            t = torch.tensor([elapsed], device=device, dtype=torch.float64)
+            gathered = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(gathered, t)
+            by_rank = [float(g) / n_steps for g in gathered]   # every rank's own clock: the step is the slowest one's
+            elapsed = max(float(g) for g in gathered)
+        return elapsed / n_steps, by_rank, loss, (t0, t1)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
     torch.cuda.nvtx.range_push("timed")       # lets `ncu --nvtx --nvtx-include timed/` see only these steps
-    begin.record()
-    marks, t_host0 = [], time.perf_counter()   # MNF_BENCH_STEP_TIMES=1: per-step times on stderr (diagnostic)
-    for _ in range(args.steps):
-        loss = step()
-        if os.environ.get("MNF_BENCH_STEP_TIMES"):
-            marks.append((torch.cuda.Event(enable_timing=True), time.perf_counter() - t_host0))
-            marks[-1][0].record()
-    end.record()
-    fence()
-    if marks:
-        print(f"rank {rank} timed loop: gpu step ends (ms) " + " ".join(f"{begin.elapsed_time(m):.2f}" for m, _ in marks)
-              + " | host returns (ms) " + " ".join(f"{1e3 * h:.2f}" for _, h in marks), file=sys.stderr)
+    ms_per_step, by_rank, loss, (wall0, wall1) = timed_loop(args.steps)
     torch.cuda.nvtx.range_pop()
-    wall1 = time.time()
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
-    elapsed_ms = begin.elapsed_time(end)
-    loss_module.synchronize()
+    for loss_module in loss_modules:
+        loss_module.synchronize()
     final_loss = float(loss.detach())
-    by_rank = None
-    if distributed:
-        t = torch.tensor([elapsed_ms], device=device, dtype=torch.float64)
-        gathered = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(gathered, t)
-        by_rank = [float(g) / args.steps for g in gathered]      # every rank's own clock: the step is the slowest one's
-        elapsed_ms = max(float(g) for g in gathered)
-    ms_per_step = elapsed_ms / args.steps
-    value = n_rows * world * S / (ms_per_step * 1e-3)
-    kernel_ms_after, _ = measure_sweep(args.steps)
+    value = n_total * S / (ms_per_step * 1e-3)
+    kernel_ms_after = measure_sweep(args.steps)
     kernel_ms = 0.5 * (kernel_ms_before + kernel_ms_after)
+
+    # ---- sustained: at least `--sustain` seconds of back-to-back steps (the power cap engages) ---
+    sustained = None
+    if args.sustain > 0:
+        n_sustain = max(args.steps, int(args.sustain * 1e3 / ms_per_step) + 1)
+        s_ms, _, _, _ = timed_loop(n_sustain)
+        sustained = {"steps": n_sustain, "ms_per_step": s_ms, "value": n_total * S / (s_ms * 1e-3), "unit": UNIT,
+                     "seconds": s_ms * n_sustain * 1e-3}
 
     # ---- end to end: host buffers, H2D of the step's inputs and D2H of its result every step ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, w, step, batches, calls, n_rows, world, device, fence, distributed)
+        e2e = run_e2e(args, w, step, batches, calls, n_rows, n_total, world, device, fence, distributed)
+
+    # ---- secondary objects (rank 0 prints; every rank takes part in sharded evaluations) ----------
+    secondary = {}
+    if not args.no_secondary and fused and (w.closed_form_kernel or w.black_box_kernel):
+        other = not closed_form
+        other_loss = make_loss(other)
+        other_step = mininf.nn.FusedSVIStep(other_loss, condition_on(mininf, model, w, batches[0]), modules, lr=0.01,
+                                            graph=graphed, share_with=steps_by_batch[0])
+        saved = steps_by_batch
+        steps_by_batch = [other_step]
+        for _ in range(3):
+            step()
+        o_ms, _, _, _ = timed_loop(args.steps)
+        steps_by_batch = saved
+        other_loss.synchronize()
+        secondary["closed_form" if other else "black_box"] = {
+            "what": ("the same step with Normal / Poisson sites reduced to data-only sufficient statistics "
+                     "(no per-particle work; value = rows * S / time is then free in S)" if other else
+                     "the same step with one evaluation per (particle, element) for every site"),
+            "kernel": w.closed_form_kernel if other else w.black_box_kernel,
+            "ms_per_step": o_ms, "value": n_total * S / (o_ms * 1e-3), "unit": UNIT, "steps": args.steps}
 
     if rank == 0:
         peak, peak_source = measured_peak_gbs()
@@ -525,52 +639,72 @@ def run_b200(args):
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
             rows_cpu, parts_cpu = w.cpu_rows, w.cpu_particles
-            cpu_value, _ = cpu_sample(w, rows_cpu, parts_cpu, steps=8, warmup=1)
-            cpu_baseline = {"value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                            "sample": f"{rows_cpu} rows x {parts_cpu} particles per step, 8 timed steps, of the "
-                                      f"{w.name} workload; oracle port of the reference's torch.distributions "
-                                      "path with validation on"}
+            torch.set_num_threads(max(len(os.sched_getaffinity(0)), 1))
+            cpu_value, _, kind = reference_sample(w, rows_cpu, parts_cpu, steps=4, warmup=1)
+            cpu_baseline = {"value": cpu_value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                            "sample": cpu_sample_text(w, rows_cpu, parts_cpu, torch.get_num_threads(), kind) +
+                                      ", 4 timed steps"}
+            if not args.no_secondary and load_reference() is not None:
+                # SURVEY 8d's secondary comparator: the same unmodified reference with CUDA tensors
+                # (stock torch eager kernels + cuBLAS), the only pre-existing Blackwell path
+                try:
+                    torch.cuda.empty_cache()
+                    rows_gpu = min(n_rows, 10 * rows_cpu)
+                    gpu_value, gpu_seconds, _ = reference_sample(w, rows_gpu, 2, steps=3, warmup=1, device=device)
+                    secondary["reference_cuda"] = {
+                        "what": "the unmodified reference (baseline/_ref) with CUDA tensors on this B200: stock torch "
+                                "eager kernels + cuBLAS, one EvidenceLowerBoundLoss call per particle, validation on",
+                        "value": gpu_value, "unit": UNIT, "ms_per_step": gpu_seconds * 1e3,
+                        "sample": f"{rows_gpu} rows x 2 particles per step, 3 timed steps"}
+                except Exception as error:  # noqa: BLE001  a secondary line must not fail the run
+                    secondary["reference_cuda"] = {"unavailable": f"{type(error).__name__}: {error}"[:200]}
+        step_kind = ("FusedSVIStep (mnf_svi_step: transforms + ELBO/grad kernels + chain rule + Adam in one native call)"
+                     if fused else "GraphedStep (zero_grad + ELBO/grad kernels + backward + torch fused Adam)")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
             "dtype": "tf32 operands / f32 accumulate" if w.event_kind == "dense" else "f32 (f64 sums)",
             "data": "synthetic",
-            "config": {"workload": w.name, "rows_per_gpu": n_rows,
-                       "features": P, "particles": S, "parallelism": f"row shards x{world}, one all-reduce/step",
-                       "l2": f"inputs ({n_rows * w.bytes_per_row / 1e9:.1f} GB per step and GPU) far exceed the "
+            "config": {"workload": w.name, "rows_total": n_total, "rows_per_gpu": n_rows,
+                       "features": P, "particles": S,
+                       "estimator": ("closed-form sufficient statistics where a site has them" if closed_form else
+                                     "black-box: one log-density + score evaluation per (particle, observation)"),
+                       "parallelism": (f"row shards x{world} (chunk ownership of one global data set), partial sums "
+                                       f"combined by {'the engine over peer memory (NVLink)' if args.reduce == 'peer' else 'one NCCL all-reduce'}"
+                                       if distributed else "single GPU"),
+                       "l2": f"inputs ({n_rows * w.bytes_per_row / 1e9:.2f} GB per step and GPU) exceed the "
                              "126 MB L2; no flush needed",
-                       "stream": (f"{w.n_batches} resident batches alternate" +
-                                  ("; one recorded step per batch buffer, replayed in turn" if graphed else
-                                   "; the cached plan is rebound to each batch (no retrace)"))
-                       if streaming else "one resident data set",
-                       "step": "zero_grad + ELBO/grad kernels + backward + Adam" +
-                               (", replayed from a CUDA graph (GraphedStep)" if graphed
-                                else ", " + (graph_note or "eager launches")),
+                       "stream": (f"{w.n_batches} resident batches alternate; one recorded step per batch buffer, "
+                                  "replayed in turn") if streaming else "one resident data set",
+                       "step": step_kind + (", replayed from a CUDA graph" if graphed else ", eager launches"),
                        "final_loss": final_loss},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": plan.gpu_launches_per_step * args.steps,
+            "kernels_per_step": plan.gpu_launches_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_source,
-                         "kernel": w.kernel,
+                         "kernel": (w.closed_form_kernel if closed_form and w.closed_form_kernel else w.kernel),
                          "kernel_ms": kernel_ms, "algorithmic_bytes": algorithmic_bytes,
                          "kernel_ms_before_after": [kernel_ms_before, kernel_ms_after],
-                         "kernel_timing": f"CUDA events around each launch, {args.steps} eager steps right "
+                         "kernel_timing": f"CUDA events around each launch, {args.steps} eager launches right "
                                           f"before and {args.steps} right after the timed region on the "
                                           "same data, averaged",
                          **({"note": w.bound_note} if w.bound_note else {})},
-            "eager_ms_per_step": eager_ms_per_step,
+            "sustained": sustained,
             "ms_per_step_by_rank": by_rank,
             "cpu_baseline": cpu_baseline,
             "steps_per_sec": 1e3 / ms_per_step,
+            **secondary,
         }
         print(json.dumps(line))
     if distributed:
+        dist.barrier()
         dist.destroy_process_group()
 
 
-def run_e2e(args, w, step, batches, calls, n_rows, world, device, fence, distributed):
+def run_e2e(args, w, step, batches, calls, n_rows, n_total, world, device, fence, distributed):
     """Same step, but the inputs live in pinned host memory and are copied to the device inside
     the timed region every step; the loss is read back to the host every step."""
     import psutil
@@ -580,8 +714,9 @@ def run_e2e(args, w, step, batches, calls, n_rows, world, device, fence, distrib
     need = n_rows * row_bytes
     available = psutil.virtual_memory().available
     rows = n_rows
-    if need * world > 0.6 * available:
-        rows = int(0.6 * available / world / row_bytes)
+    per_rank = world if distributed else 1
+    if need * per_rank > 0.6 * available:
+        rows = int(0.6 * available / per_rank / row_bytes)
     try:
         host = {k: torch.empty((rows,) + tuple(batches[0][k].shape[1:]), dtype=batches[0][k].dtype, pin_memory=True)
                 for k in names}
@@ -614,9 +749,10 @@ def run_e2e(args, w, step, batches, calls, n_rows, world, device, fence, distrib
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
     del loss_host
-    return {"value": n_rows * world * S / (ms * 1e-3), "unit": UNIT,
-            "h2d_bytes_per_step": n_rows * row_bytes, "d2h_bytes_per_step": 4, "ms_per_step": ms, "steps": steps,
-            "note": ("inputs copied from pinned host memory every step; PCIe-bound"
+    return {"value": n_total * S / (ms * 1e-3), "unit": UNIT,
+            "h2d_bytes_per_step": n_rows * row_bytes * (world if distributed else 1), "d2h_bytes_per_step": 4 * (world if distributed else 1),
+            "ms_per_step": ms, "steps": steps,
+            "note": ("inputs copied from pinned host memory every step (every rank its own shard); PCIe-bound"
                      + ("" if rows == n_rows else f"; pinned staging buffer of {rows} rows sent repeatedly"))}
 
 

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define MNF_ABI_VERSION 6
+#define MNF_ABI_VERSION 7
 
 /* error codes */
 #define MNF_OK 0
@@ -55,11 +55,14 @@ extern "C" {
 /* inverse links applied to a linear predictor */
 #define MNF_T_ID 0
 #define MNF_T_EXP 1
+#define MNF_T_MASK 0x0F         /* transform codes of mnf_adam_t: low bits = MNF_T_*              */
+#define MNF_T_FROZEN 0x80       /*   | this flag = the parameter is a constant, never updated     */
 
 /* device status bits, OR-ed into `status[0]` by kernels (checked by the host at its sync point) */
 #define MNF_ST_BAD_PARAM 1u     /* a distribution parameter left its arg constraint (e.g. scale<=0, NaN) */
 #define MNF_ST_BAD_VALUE 2u     /* an unmasked value left the support of its distribution      */
 #define MNF_ST_NONFINITE 4u     /* the loss or a gradient is NaN/Inf                           */
+#define MNF_ST_XRANK_TIMEOUT 8u /* a peer rank did not deliver its accumulator within ~2 s      */
 
 /*
  * One distribution parameter as a scalar link:  value_i = T(A_i + B_i * x_i)  with
@@ -158,8 +161,16 @@ typedef struct mnf_rowlatent {
 
 /* precision modes of the dense sweep */
 #define MNF_DENSE_FP32 0   /* SIMT fp32 FMA, any p / S                                          */
-#define MNF_DENSE_TF32 1   /* tcgen05 kind::tf32: operands rounded to nearest to TF32, fp32        */
-                           /* accumulate in TMEM; shapes as reported by mnf_dense_tf32_kernel       */
+#define MNF_DENSE_TF32 1   /* tcgen05 kind::tf32, one evaluation per (particle, observation): the */
+                           /* black-box sweep. X rounded to TF32 by the TMA unit, theta as hi + lo */
+                           /* TF32 pairs, fp32 accumulate in TMEM; shapes: mnf_dense_tf32_kernel   */
+#define MNF_DENSE_TF32_CLOSED_FORM 2 /* as 1, but a Normal site with p <= 64 may be reduced to its  */
+                           /* Gram statistics (no per-particle work; csrc/dense_gram.cuh)          */
+
+/* flags of mnf_site_sweep / mnf_plan_desc_t */
+#define MNF_SWEEP_CLOSED_FORM 1u /* allow the data-only sufficient-statistics paths (six sums for   */
+                           /* Normal(A + B x, sigma), Chebyshev moments for Poisson(exp(A + B x)))  */
+                           /* instead of one evaluation per (particle, element)                     */
 
 typedef struct mnf_device_info {
   int32_t sm_count;
@@ -211,10 +222,11 @@ int mnf_rsample(const mnf_latent_t* latents_dev, int n_latents, int n_particles,
  * sweeps over X). Intercepts are supported by both. X must also be 16-byte aligned with
  * ldx % 4 == 0 and fewer than 2^31 rows.
  * 3 = only the Gram path below applies (Normal, p <= 64, p % 4 == 0, more than 128 particles).
- * A Normal site with p <= 64 and p % 4 == 0 (with or without a mask, any particle count) is swept by
- * csrc/dense_gram.cuh instead: X'X, X'y, X'1, sum y, sum y^2 in one pass over X (tcgen05, TF32 X,
- * exact products), then the closed forms of every particle's log-density and gradients in fp64 -
- * same inputs, outputs and bytes read, no per-particle work.
+ * With MNF_DENSE_TF32_CLOSED_FORM a Normal site with p <= 64 and p % 4 == 0 (with or without a mask,
+ * any particle count) is swept by csrc/dense_gram.cuh instead: X'X, X'r0, X'1, sum r0, sum r0^2
+ * around the particle mean in one pass over X (tcgen05, TF32 X, exact products), then the closed
+ * forms of every particle's log-density and gradients in fp64 - same inputs, outputs and bytes
+ * read, no per-particle work. MNF_DENSE_TF32 never takes that path.
  */
 int mnf_dense_tf32_kernel(int family, int p, int n_particles);
 
@@ -236,7 +248,7 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
 #define MNF_MAX_FUSED_SITES 4
 int mnf_site_sweep(const mnf_site_t* sites, int n_sites, const float* z, int n_particles,
                    int n_latent_total, double* acc, void* workspace, size_t workspace_bytes,
-                   uint32_t* status, void* stream);
+                   uint32_t flags, uint32_t* status, void* stream);
 
 /*
  * Small sites (priors of global latents, short observed vectors): any link stride, any value
@@ -264,6 +276,111 @@ int mnf_rowlatent_sweep(const mnf_rowlatent_t* desc, const float* z, int n_parti
                         int n_latent_total, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
                         int with_entropy, double* acc, void* workspace, size_t workspace_bytes,
                         uint32_t* status, void* stream);
+
+/*
+ * ------------------------------------------------------------------------------------------------
+ * One call per step: the host traces the model ONCE, hands the flat tables to
+ * mnf_plan_create, and every evaluation of EvidenceLowerBoundLoss.forward (mininf/nn.py:212-228)
+ * is one mnf_elbo_fwd_bwd call that enqueues every kernel of the step. A C consumer needs nothing
+ * else (tests/c/plan_step.c runs a regression step from host tables without Python).
+ * ------------------------------------------------------------------------------------------------
+ */
+typedef struct mnf_plan mnf_plan_t;   /* opaque; owns only its own host / device copies of the tables */
+typedef struct mnf_xrank mnf_xrank_t; /* opaque; peer-memory exchange of the step accumulator        */
+
+typedef struct mnf_plan_desc {
+  int32_t n_particles;
+  int32_t n_latent_total;              /* D */
+  int32_t n_latents;
+  int32_t n_dense;
+  int32_t n_groups;                    /* fused element-wise sweeps (mnf_site_sweep calls) */
+  int32_t n_small_observed;
+  int32_t n_small_global;
+  int32_t n_rowlatent;
+  const mnf_latent_t* latents;         /* HOST arrays below; p0 / p1 / data pointers are device pointers */
+  const mnf_dense_site_t* dense;
+  const int32_t* dense_mode;           /* MNF_DENSE_* per dense site */
+  const mnf_site_t* group_sites;       /* the sites of all groups, concatenated */
+  const int32_t* group_sizes;          /* 1..MNF_MAX_FUSED_SITES each */
+  const mnf_site_t* small_observed;    /* short observed sites (any link stride) */
+  const mnf_site_t* small_global;      /* latent-valued (prior) sites: counted once, after the exchange */
+  const mnf_rowlatent_t* rowlatent;    /* loc / scale / grad_* / eps are taken from mnf_buffers_t per step */
+  uint32_t flags;                      /* MNF_SWEEP_CLOSED_FORM */
+  int32_t device;                      /* -1: the current device */
+} mnf_plan_desc_t;
+
+/* per-step pointers of one row latent (read in place; the gradients are written by the kernel) */
+typedef struct mnf_row_buffers {
+  const float* loc;
+  const float* scale;
+  float* grad_loc;
+  float* grad_scale;
+  const float* eps;                    /* optional external noise [S][n_rows][p] */
+} mnf_row_buffers_t;
+
+/* Caller-owned device buffers of a step; every pointer is borrowed for the enqueued work. */
+typedef struct mnf_buffers {
+  float* z;                            /* [S][D] */
+  float* noise;                        /* [S][D] */
+  double* acc;                         /* [S][1+D] */
+  float* out;                          /* [1+2D]: loss, d loss/d p0, d loss/d p1 */
+  void* workspace;
+  size_t workspace_bytes;              /* >= mnf_plan_workspace_bytes */
+  uint32_t* status;
+  const float* noise_in;               /* optional external noise [S][D] (parity mode) */
+  uint64_t* step_counter;              /* optional device counter added to `offset` (CUDA-graph replays) */
+  const mnf_row_buffers_t* rows;       /* HOST array, n_rowlatent entries */
+  mnf_xrank_t* xrank;                  /* optional: every observed site is this rank's row shard */
+} mnf_buffers_t;
+
+/* torch.optim.Adam (no weight decay, no amsgrad) over the UNCONSTRAINED parameters of the packed
+ * latent sites, fused into the last kernel of the step: raw[d] is the storage behind p0 of latent
+ * column d, raw[D+d] behind p1; `constrained` [2D] receives transform(raw) at the start of the
+ * step and must be where the plan's latent table points (p0 = constrained + offset,
+ * p1 = constrained + D + offset). README.md:63-69's zero_grad / backward / optimizer.step(). */
+typedef struct mnf_adam {
+  float lr, beta1, beta2, eps;
+  float* raw;
+  const uint8_t* transform;            /* device [2D]: MNF_T_ID / MNF_T_EXP, | MNF_T_FROZEN */
+  float* m;
+  float* v;
+  float* constrained;
+  int64_t* step;                       /* device: updates applied so far */
+} mnf_adam_t;
+
+#define MNF_STEP_ENTROPY 1u            /* add the entropy of the approximation (mininf/nn.py:226) */
+#define MNF_STEP_PRE 2u                /* rsample + every sweep over observed sites              */
+#define MNF_STEP_POST 4u               /* [exchange] + latent-valued sites + finalize [+ Adam]   */
+#define MNF_STEP_ALL (MNF_STEP_PRE | MNF_STEP_POST)
+
+int mnf_plan_create(const mnf_plan_desc_t* desc, mnf_plan_t** out);
+/* Same table shapes, new data pointers (the next minibatch); device tables are refreshed on `stream`. */
+int mnf_plan_update(mnf_plan_t* plan, const mnf_plan_desc_t* desc, void* stream);
+int mnf_plan_workspace_bytes(const mnf_plan_t* plan, size_t* bytes);
+/* Kernels of this library the most recent step call on this plan enqueued (0 before the first). */
+int mnf_plan_launches(const mnf_plan_t* plan, int* kernels);
+int mnf_plan_destroy(mnf_plan_t* plan);
+
+/* Enqueue one ELBO + gradient evaluation. Without MNF_STEP_PRE / MNF_STEP_POST both halves run
+ * (a caller that reduces `acc` itself, e.g. with ncclAllReduce, calls PRE, reduces, calls POST). */
+int mnf_elbo_fwd_bwd(mnf_plan_t* plan, const mnf_buffers_t* buffers, uint64_t seed, uint64_t offset,
+                     uint32_t flags, void* stream);
+/* The whole SVI step: parameter transforms + mnf_elbo_fwd_bwd + Adam, 4-6 kernels, no host work. */
+int mnf_svi_step(mnf_plan_t* plan, const mnf_buffers_t* buffers, const mnf_adam_t* adam, uint64_t seed,
+                 uint64_t offset, uint32_t flags, void* stream);
+
+/*
+ * Cross-rank exchange (replaces the ncclAllReduce of SURVEY §8e; csrc/small.cuh): every rank pushes
+ * its [S][1+D] accumulator into an inbox on each peer over NVLink and raises a flag; each rank adds
+ * the inboxes in rank order inside its tail kernel - bit-identical totals on every rank, no host
+ * call, capturable. The inbox is one cudaMalloc allocation shared through CUDA IPC: create it,
+ * exchange the MNF_XRANK_HANDLE_BYTES handles of all ranks by any means (torch.distributed
+ * all_gather in INTEGRATION.md), connect.
+ */
+#define MNF_XRANK_HANDLE_BYTES 64
+int mnf_xrank_create(int world, int rank, int64_t n_doubles, mnf_xrank_t** out, void* handle_out);
+int mnf_xrank_connect(mnf_xrank_t* xr, const void* handles /* world x MNF_XRANK_HANDLE_BYTES */);
+int mnf_xrank_destroy(mnf_xrank_t* xr);
 
 /* Counting scan used by the integer-exact parity checks: out[0]=sum(mask), out[1]=sum(mask*value)
  * as int64 (value must hold integers); mask may be NULL (all ones). */

@@ -40,7 +40,7 @@ int launch_reduce(const float* partial, int n_cta, int S, int ncol, const ColMap
   const int total = S * ncol, per_block = kReduceThreads / 32;   // one warp per output
   reduce_partials_kernel<<<(total + per_block - 1) / per_block, kReduceThreads, 0, stream>>>(
       partial, n_cta, S, ncol, map, weight, D, acc);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   return MNF_OK;
 }
 
@@ -84,8 +84,9 @@ int mnf_rsample(const mnf_latent_t* latents_dev, int n_latents, int n_particles,
   const int grid = (int)std::min<int64_t>((total + 255) / 256, 1024);
   rsample_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(latents_dev, n_latents, n_particles,
                                                          n_latent_total, noise_in, seed, offset,
-                                                         offset_dev, z, noise_out, acc, status);
-  MNF_CUDA_CHECK(cudaGetLastError());
+                                                         offset_dev, z, noise_out, acc, status,
+                                                         nullptr, nullptr, nullptr);
+  MNF_LAUNCH_CHECK();
   return MNF_OK;
 }
 
@@ -101,7 +102,7 @@ int mnf_small_sites(const mnf_site_t* sites_dev, int n_sites, int64_t max_numel,
   dim3 grid(bx, n_sites, n_particles);
   small_sites_kernel<<<grid, kSmallThreads, 0, (cudaStream_t)stream>>>(sites_dev, z, n_particles,
                                                                        n_latent_total, acc, status);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   return MNF_OK;
 }
 
@@ -113,7 +114,7 @@ int mnf_finalize(const mnf_latent_t* latents_dev, int n_latents, int n_particles
   finalize_kernel<<<1, kFinalThreads, 0, (cudaStream_t)stream>>>(latents_dev, n_latents, n_particles,
                                                                  n_latent_total, z, noise, acc,
                                                                  with_entropy, out, step_counter, status);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   return MNF_OK;
 }
 
@@ -125,8 +126,10 @@ int mnf_masked_count(const float* value, const uint8_t* mask, int64_t numel, int
   const int grid = (int)std::min<int64_t>((numel + 255) / 256, 2048);
   masked_count_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       value, mask, numel, reinterpret_cast<unsigned long long*>(out));
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   return MNF_OK;
 }
 
 }  // extern "C"
+
+#include "plan.cuh"

@@ -29,6 +29,16 @@ inline int fail(int code, const char* fmt, const char* a = "", const char* b = "
   return code;
 }
 
+// kernels enqueued by this thread so far (mnf_plan_launches reports the count of one step)
+inline thread_local int g_launches = 0;
+
+// after every kernel launch: count it and surface a launch error
+#define MNF_LAUNCH_CHECK()                                                                    \
+  do {                                                                                        \
+    ++::mnf::g_launches;                                                                      \
+    MNF_CUDA_CHECK(cudaGetLastError());                                                       \
+  } while (0)
+
 #define MNF_CUDA_CHECK(expr)                                                                  \
   do {                                                                                        \
     cudaError_t err__ = (expr);                                                               \
@@ -107,6 +117,15 @@ __device__ __forceinline__ float sigmoid_f(float x) {
 // Philox4x32-10 (Salmon et al. 2011), the counter-based generator torch's CUDA generator also
 // uses (TORCH include/ATen/core/PhiloxRNGEngine.h). key = seed, counter = (offset, index).
 // ---------------------------------------------------------------------------------------------
+// Stream tags: the top byte of the 64-bit index keeps the consumers of one (seed, call index)
+// apart, so no two draws of a step can share a counter (packed Normal draws use index = s*D + d,
+// Gamma draws (index << 8) | round, row latents (element << 8) | particle group: without a tag
+// those ranges overlap once S*D >= 256).
+constexpr uint64_t kPhiloxNormal = (uint64_t)1 << 56;
+constexpr uint64_t kPhiloxGamma = (uint64_t)2 << 56;
+constexpr uint64_t kPhiloxBeta0 = (uint64_t)3 << 56;
+constexpr uint64_t kPhiloxRowLatent = (uint64_t)4 << 56;
+
 struct Philox {
   uint32_t c[4];
   uint32_t k[2];

@@ -59,13 +59,14 @@ int launch_dense_tc(const mnf_dense_site_t& site, const float* z, int S, int D, 
   MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)tc::kSmemBytes));
   kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_k, map_mn, site, z, S, D, partial, status);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   return MNF_OK;
 }
 
-// Normal family, p <= 64: data-only Gram statistics (dense_gram.cuh). Workspace: per-CTA
-// statistics, their fp64 totals, then one row block [S][1 + p + 2] for the common reduction.
-// MNF_DENSE_NO_GRAM=1 keeps the per-particle kernel (developer A/B switch).
+// Normal family, p <= 64: data-only Gram statistics (dense_gram.cuh), taken only in mode
+// MNF_DENSE_TF32_CLOSED_FORM. Workspace: per-CTA statistics, their fp64 totals, then one row block
+// [S][1 + p + 2] for the common reduction. MNF_DENSE_NO_GRAM=1 switches it off for every mode
+// (developer A/B switch).
 bool gram_disabled() {
   const char* v = std::getenv("MNF_DENSE_NO_GRAM");
   return v != nullptr && v[0] != '\0' && v[0] != '0';
@@ -95,11 +96,11 @@ int launch_dense_gram(const mnf_dense_site_t& site, const float* z, int S, int D
   auto kernel = site.mask != nullptr ? gram::dense_gram_kernel<true> : gram::dense_gram_kernel<false>;
   MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram::kSmemBytes));
   kernel<<<grid, gram::kThreads, gram::kSmemBytes, stream>>>(map_mn, site, z, S, D, cta_out, status, dev_skip);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   gram::gram_reduce_kernel<<<(gram::kCtaFloats + 255) / 256, 256, 0, stream>>>(cta_out, grid, total);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   gram::gram_finish_kernel<<<S, tc::kP, 0, stream>>>(site, total, z, S, D, rows, status);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   *rows_out = rows;
   return MNF_OK;
 }
@@ -113,12 +114,28 @@ struct TcrShape {
 bool tcr_shape(int p, int S, int max_smem_optin, TcrShape* out) {
   if (p <= 0 || p % 4 != 0 || S > 128) return false;     // rows must be 16-byte multiples for TMA
   TcrShape sh;
-  sh.passes = (S + 31) / 32;
+  sh.C = (p + tcr::kChunk - 1) / tcr::kChunk;            // the last chunk is zero-padded by TMA
+  // tensor memory: two eta buffers of 2NS (hi, lo) columns + 2C gradient tiles of NS columns. Very
+  // wide matrices (C = 7) only fit 16 particle slots: they run in passes of 16 particles.
+  int per_pass = 32;
+  if ((4 + 2 * sh.C) * 32 > (int)tcr::kTmemCols) per_pass = 16;
+  sh.passes = (S + per_pass - 1) / per_pass;
   sh.s_pass = (S + sh.passes - 1) / sh.passes;
   sh.NS = sh.s_pass <= 16 ? 16 : 32;
-  sh.C = (p + tcr::kChunk - 1) / tcr::kChunk;            // the last chunk is zero-padded by TMA
-  if ((2 + 2 * sh.C) * sh.NS > (int)tcr::kTmemCols) return false;
+  if ((4 + 2 * sh.C) * sh.NS > (int)tcr::kTmemCols) return false;
   // split what is left of shared memory between the two operand rings, K ring first
+  if (const char* force = std::getenv("MNF_TCR_STAGES")) {   // developer override "k,mn" (timing experiments)
+    int k = 0, mn = 0;
+    if (std::sscanf(force, "%d,%d", &k, &mn) == 2 && k >= 2 && mn >= 2 && k <= tcr::kMaxStages && mn <= tcr::kMaxStages) {
+      sh.k_stages = k;
+      sh.mn_stages = mn;
+      sh.smem = tcr::make_layout(sh.NS, sh.C, k, mn).total;
+      if (sh.smem <= (size_t)max_smem_optin) {
+        *out = sh;
+        return true;
+      }
+    }
+  }
   for (int stages = 2 * tcr::kMaxStages; stages >= 4; --stages) {
     sh.k_stages = (stages + 1) / 2;
     sh.mn_stages = stages / 2;
@@ -156,7 +173,7 @@ int launch_dense_tcr_inst(const CUtensorMap& map_k, const CUtensorMap& map_mn, c
   auto kernel = tcr::dense_tcr_kernel<FAMILY, NS, ICPT>;
   MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
   kernel<<<grid, tcr::kThreads, sh.smem, stream>>>(map_k, map_mn, site, z, S, D, sh.C, sh.k_stages, sh.mn_stages, partial, status);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   return MNF_OK;
 }
 
@@ -216,24 +233,25 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
   // gradient w.r.t. the scale link's pre-transform value u goes to its latent scalar
   map.scalar_lat[1] = s.family == MNF_NORMAL ? s.scale.a_lat : -1;
 
-  if (mode == MNF_DENSE_TF32) {
+  if (mode == MNF_DENSE_TF32 || mode == MNF_DENSE_TF32_CLOSED_FORM) {
+    const bool closed_form = mode == MNF_DENSE_TF32_CLOSED_FORM && gram_shape(s.family, p);
     const bool aligned = (reinterpret_cast<uintptr_t>(s.X) % 16 == 0) && (s.ldx % 4 == 0) &&
                          s.n_rows < (int64_t)1 << 31;
     const bool has_icpt = s.icpt_lat >= 0 || s.icpt_const != 0.0f;
     TcrShape sh;
     const int which = dense_tf32_kernel(s.family, p, S, c->max_smem_optin, &sh);
     const bool c2_shape = which == 1, wide_shape = which == 2;
-    if (!aligned || c->cc_major != 10 || !(c2_shape || wide_shape || gram_shape(s.family, p)))
+    if (!aligned || c->cc_major != 10 || !(c2_shape || wide_shape || closed_form))
       return fail(MNF_E_UNSUPPORTED,
                   "mnf_dense_sweep: TF32 mode needs p == 64 with S <= 64, or p a multiple of 4 with "
-                  "S <= 128 (passes of <= 32 particles, (2 + ceil(p/64) * 2) * 32 within 512 TMEM columns), "
+                  "S <= 128 (passes of <= 32 particles, (4 + ceil(p/64) * 2) * 32 within 512 TMEM columns), "
                   "16-byte aligned rows and an sm_100 device%s%s");
     const int64_t n_tiles = (s.n_rows + tc::kTileM - 1) / tc::kTileM;
     grid = (int)std::min<int64_t>(n_tiles, c->sm_count);
     if ((size_t)grid * S * ncol * sizeof(float) > workspace_bytes)
       return fail(MNF_E_INVALID, "mnf_dense_sweep: workspace too small%s%s");
     int rc;
-    if (gram_shape(s.family, p) && gram_workspace_bytes(grid, S) <= workspace_bytes) {
+    if (closed_form && gram_workspace_bytes(grid, S) <= workspace_bytes) {
       float* rows = nullptr;
       if (int rg = launch_dense_gram(s, z, S, D, workspace, &rows, status, grid, stream)) return rg;
       return launch_reduce(rows, 1, S, ncol, map, s.weight, D, acc, stream);
@@ -275,7 +293,7 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
       return fail(MNF_E_INVALID, "mnf_dense_sweep: workspace too small%s%s");
     MNF_CUDA_CHECK(cudaFuncSetAttribute(dense_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dense_simt_kernel<<<grid, kSimtThreads, smem, stream>>>(s, z, S, D, partial, status);
-    MNF_CUDA_CHECK(cudaGetLastError());
+    MNF_LAUNCH_CHECK();
   } else {
     return fail(MNF_E_INVALID, "mnf_dense_sweep: unknown mode%s%s");
   }

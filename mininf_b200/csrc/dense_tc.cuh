@@ -4,21 +4,32 @@
 // products of the ELBO step on the 5th-generation tensor cores, in the transposed orientation
 // that keeps every intermediate in tensor memory:
 //
-//   eta^T[S x 128] = Theta[S x p] . Xtile^T[p x 128]      tcgen05.mma kind::tf32, M=64 N=128 K=p
+//   eta^T[2S x 128] = Theta[2S x p] . Xtile^T[p x 128]    tcgen05.mma kind::tf32, M=128 N=128 K=p
 //                    A = Theta resident in TMEM (TS mode), B = X tile, K-major SWIZZLE_128B
-//   R^T  [S x 128] = score(y, eta)                        epilogue warps, IN PLACE in TMEM:
+//   R^T  [2S x 128] = score(y, eta)                       epilogue warps, IN PLACE in TMEM:
 //                    tcgen05.ld -> registers -> log-density / score -> tcgen05.st
-//   G^T  [S x p]  += R^T[S x 128] . Xtile[128 x p]        tcgen05.mma kind::tf32, M=64 N=p K=128
+//   G^T  [2S x p]  += R^T[2S x 128] . Xtile[128 x p]      tcgen05.mma kind::tf32, M=128 N=p K=128
 //                    A = the eta accumulator columns themselves (TS mode), B = X tile, MN-major
 //
 // so the residual matrix never touches shared memory, and an epilogue thread owns one particle:
 // its per-particle statistics are single registers.
 //
+// TWO MMA ROWS PER PARTICLE (hi / lo). An M = 128 MMA costs exactly what an M = 64 one does
+// (tools/umma_time.cu: 74.4 cycles at N = 128, 42.4 at N = 64, A in TMEM), so the 64 rows an
+// S <= 64 problem leaves idle carry the low-order halves of the per-particle operands:
+// theta_s = hi + lo with hi = tf32(theta_s), lo = tf32(theta_s - hi), and likewise for the score.
+// Row 32q + i (i < 16) of the MMA is the hi half of particle 16q + i, row 32q + 16 + i its lo
+// half, so both halves live in the TMEM lane quadrant of epilogue warp q and come back with the
+// same register mapping from two tcgen05.ld.16x256b (lane offsets 0 and 16,
+// tools/tmem_shape_probe.cu). eta = hi row + lo row carries theta to 22 bits: the systematic
+// per-particle error of a TF32-rounded Theta (it does not average out over rows) is gone, at no
+// tensor-pipe cost.
+//
 // Facts measured on B200 that shape this kernel (tools/umma_probe.cu, umma_time.cu,
 // umma_ts_probe.cu; numbers in DESIGN.md):
 //  * kind::tf32 accepts MN-major operands ONLY in the SWIZZLE_128B_BASE32B layout and K-major
 //    operands only in the 16-byte-atom layouts, so the X tile is kept in shared memory as two
-//    images written from the same registers (HBM is still read once).
+//    images, each written by its own TMA load (the second one hits L2: HBM is read once).
 //  * one tf32 MMA costs about N/2 + 11 cycles, plus M/4 when A is fetched from shared memory;
 //    A-in-TMEM removes that term, and MN-major costs the same as K-major.
 //  * MMAs must be issued by an `elect.sync`-elected lane under warp-uniform control flow; a
@@ -27,11 +38,11 @@
 //    bias the sum by ~3e-4 relative. The gradient accumulator is therefore ping-ponged between two
 //    TMEM tiles and drained into fp32 registers every kFlush tiles.
 //
-// Precision mode (stated): X, Theta and R are rounded to nearest to TF32 (10-bit
-// mantissa) before they reach the tensor core - X by the TMA unit on its way from HBM to shared
-// memory (ties to even), Theta and R by the epilogue warps (ties away) - products are exact,
-// accumulation is fp32 in TMEM; log-densities, residual statistics and reductions are fp32 / fp64
-// SIMT.
+// Precision mode (stated): X is rounded to nearest-even to TF32 (10-bit mantissa)
+// by the TMA unit on its way from HBM to shared memory - an unbiased per-element error that
+// averages out over rows; Theta and the scores R enter as hi + lo TF32 pairs (21 mantissa bits,
+// see above); products are exact, accumulation is fp32 in TMEM; log-densities, residual
+// statistics and reductions are fp32 / fp64 SIMT.
 //
 //  * register-staged loads cannot stream X fast enough: a warp sustains only ~4-5 outstanding
 //    LDG.128, so HBM rate is set by the NUMBER OF WARPS issuing loads (tools/ldg_probe.cu: 8
@@ -45,10 +56,12 @@
 // needed until its eta product has retired, so that ring is kKStages deep and its loads hit L2
 // (the same rows were fetched moments earlier for the MN-major image). X is read from HBM once.
 //
-// Warp roles (256 threads): warps 0-3 epilogue (TMEM lane quadrant == warp id; lanes 0-15 of each
-// quadrant carry the 64 particle rows of an M=64 accumulator), warp 4 MN-ring TMA producer,
-// warp 5 K-ring TMA producer, warp 6 stages (y, live) pairs of each tile, warp 7 allocates TMEM
-// and issues every MMA.
+// Warp roles (384 threads): warps 0-3 and 8-11 epilogue (TMEM lane quadrant == warp id % 4; lanes
+// 0-15 of each quadrant carry the hi rows of 16 particles, lanes 16-31 their lo rows; warps 0-3
+// take tile rows 0-63, warps 8-11 rows 64-127 - the epilogue is the longest per-tile chain, and
+// two warps per scheduler also hide the tcgen05.ld latency), warp 4 MN-ring TMA producer, warp 5
+// K-ring TMA producer, warp 6 stages (y, live) pairs of each tile, warp 7 allocates TMEM and issues
+// every MMA.
 //
 // Replaces: aten::mv / addmv_ and MvBackward of `X @ theta` (tests/test_mininf.py:11,
 // examples/minibatch.md:33) plus the element-wise Normal / Bernoulli / Poisson log_prob chains
@@ -64,14 +77,27 @@ namespace mnf {
 namespace tc {
 
 constexpr int kP = 64;          // features handled by this instantiation
-constexpr int kNS = 64;         // particle slots (MMA M); S <= kNS, spare slots carry theta = 0
+constexpr int kNS = 64;         // particle slots; S <= kNS, spare slots carry theta = 0
+constexpr int kMmaM = 2 * kNS;  // MMA M: a hi and a lo row per particle slot
 constexpr int kTileM = 128;     // rows per tile (MMA N of the eta product, K of the gradient product)
 constexpr int kKStages = 2;     // K-major image ring (live until the eta product retires)
 constexpr int kMnStages = 4;    // MN-major image ring (live until the gradient product retires)
 constexpr int kFlush = 8;       // tiles accumulated in TMEM before the gradient tile is drained
-constexpr int kEpiWarps = 4;
+// Developer A/B switches (tools/r2_variants.sh): epilogue warps per TMEM lane quadrant, and whether
+// the scores go back as hi / lo pairs (M = 128 gradient product) or as one TF32-rounded row
+// (M = 64 gradient product: half the tcgen05.st traffic, half the gradient accumulator traffic).
+#ifndef MNF_TC_EPI_WARPS
+#define MNF_TC_EPI_WARPS 8
+#endif
+#ifndef MNF_TC_R_LO
+#define MNF_TC_R_LO 0
+#endif
+constexpr int kEpiWarps = MNF_TC_EPI_WARPS;   // 4: warps 0-3 | 8: warps 0-3 (tile rows 0-63) and 8-11 (rows 64-127)
+constexpr int kHalves = kEpiWarps / 4;
+constexpr bool kRLo = MNF_TC_R_LO != 0;
+static_assert(kEpiWarps == 4 || kEpiWarps == 8, "one or two epilogue warps per TMEM lane quadrant");
 constexpr int kWarpMnTma = 4, kWarpKTma = 5, kWarpY = 6, kMmaWarp = 7;
-constexpr int kThreads = 8 * 32;
+constexpr int kThreads = (kEpiWarps == 4 ? 8 : 12) * 32;
 
 constexpr uint32_t kAtomBytes = kTileM * 128;                 // 128 rows x 128 B (32 fp32)
 constexpr uint32_t kXImageBytes = (kP / 32) * kAtomBytes;     // 32 KB per image
@@ -84,8 +110,8 @@ constexpr uint32_t kOffBar = kOffY + kMnStages * kYBytes;
 constexpr uint32_t kNumBars = 2 * kKStages + 2 * kMnStages + 8;  // + eta_full, r_ready, g_full, g_empty (x2 each)
 constexpr uint32_t kOffMisc = kOffBar + 8 * kNumBars;         // tmem slot, counters, per-particle params
 constexpr uint32_t kOffGrad = kOffMisc + 64 + kNS * 16;         // drained gradient [kNS][kP + 1] fp32
-constexpr uint32_t kOffStat = kOffGrad + kNS * (kP + 1) * 4;    // per-particle statistic exchange [2][kNS]
-constexpr uint32_t kSmemBytes = kOffStat + 2 * kNS * 4 + 1024 /* alignment slack */;
+constexpr uint32_t kOffStat = kOffGrad + kNS * (kP + 1) * 4;    // per-particle statistic exchange [2 halves][2][kNS]
+constexpr uint32_t kSmemBytes = kOffStat + 4 * kNS * 4 + 1024 /* alignment slack */;
 static_assert(kOffMisc % 16 == 0, "misc block alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -237,7 +263,9 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_
 
 // round-to-nearest (ties away) to TF32: the tensor core then only drops zero bits
 __device__ __forceinline__ uint32_t rn_tf32(float x) {
-  return (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
 }
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 r;
@@ -348,18 +376,23 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < kEpiWarps) {
-    // Theta -> TMEM as the A operand of the eta product: particle s on lane (s%16)+32*(s/16),
-    // feature j in column kColTheta + j, rounded to TF32. Spare particle slots are zero.
-    const int s = warp * 16 + lane;
-    const bool owner = lane < 16 && s < S;
+  if (warp < 4) {
+    // Theta -> TMEM as the A operand of the eta product (M = 128: MMA row m lives on lane m).
+    // Lane 32*warp + i (i < 16) holds hi = tf32(theta) of particle 16*warp + i, lane 32*warp + 16 + i
+    // its lo = tf32(theta - hi); feature j in column kColTheta + j. Spare particle slots are zero.
+    const int s = warp * 16 + (lane & 15);
+    const bool owner = s < S;
+    const bool lo_row = lane >= 16;
     const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
 #pragma unroll
     for (int ch = 0; ch < kP / 16; ++ch) {
       uint32_t v[16];
 #pragma unroll
-      for (int c = 0; c < 16; ++c)
-        v[c] = owner ? rn_tf32(z[(int64_t)s * D + site.theta_lat + ch * 16 + c]) : 0u;
+      for (int c = 0; c < 16; ++c) {
+        const float th = owner ? z[(int64_t)s * D + site.theta_lat + ch * 16 + c] : 0.f;
+        const uint32_t hi = rn_tf32(th);
+        v[c] = lo_row ? rn_tf32(th - __uint_as_float(hi)) : hi;
+      }
       tc_st16(tmem + lane_base + kColTheta + ch * 16, v);
     }
     tc_wait_st();
@@ -472,8 +505,10 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
     asm volatile("bar.sync 1, %0;" ::"n"((kEpiWarps + 1) * 32) : "memory");
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer: warp-uniform loop, one elected lane issues ================
-    constexpr uint32_t idesc_eta = idesc_tf32(kNS, kTileM, 0, 0);   // M=64 N=128, B K-major
-    constexpr uint32_t idesc_g = idesc_tf32(kNS, kP, 0, 1);         // M=64 N=64,  B MN-major
+    constexpr uint32_t idesc_eta = idesc_tf32(kMmaM, kTileM, 0, 0);   // M=128 N=128, B K-major
+    // gradient product: M = 128 over hi and lo score rows, or M = 64 over the hi rows alone (the
+    // M = 64 A operand and accumulator live on lanes 0-15 of every quadrant: exactly the hi rows)
+    constexpr uint32_t idesc_g = idesc_tf32(kRLo ? kMmaM : kNS, kP, 0, 1);   // N=64, B MN-major
     // descriptor words that do not depend on the stage
     const uint64_t dK = smem_desc(sK, 16, 1024, 2);                 // K-major SWIZZLE_128B
     const uint64_t dMN = smem_desc(sMN, kAtomBytes, 512, 1);        // MN-major SWIZZLE_128B_BASE32B
@@ -536,19 +571,23 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
     }
     TC_FLUSH(4, 4, lane == 0);
   } else {
-    // ================= epilogue warps: thread (warp, lane < 16) owns particle 16*warp + lane ===
-    const int s = warp * 16 + lane;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    // Statistics: with the 16x256b access shape thread t works on particles 16*warp + t/4 (A) and
+    // ================= epilogue warps: quadrant q = warp % 4, column half = warp / 8 ============
+    // thread (q, lane < 16) is the owner of particle 16*q + lane for its half of the tile rows
+    const int q = warp & 3, half = warp >> 3;
+    const int s = q * 16 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    // Statistics: with the 16x256b access shape thread t works on particles 16*q + t/4 (A) and
     // + 8 (B), columns 8g + 2*(t%4) + {0,1} of every 8-column group.
     double stA_total = 0.0, stB_total = 0.0;  // Normal: sum r^2 | others: sum log-density (w/o lgamma)
     double scA_total = 0.0, scB_total = 0.0;  // sum of scores: the intercept gradient (ICPT only)
-    const float icptA = ICPT ? sPar[warp * 16 + (lane >> 2)].icpt : 0.f;
-    const float icptB = ICPT ? sPar[warp * 16 + (lane >> 2) + 8].icpt : 0.f;
-    // drained gradient tiles live in shared memory, one padded row per particle (conflict-free)
-    float* grad_row = reinterpret_cast<float*>(gbase + kOffGrad) + (size_t)(lane < 16 ? s : 0) * (kP + 1);
+    const float icptA = ICPT ? sPar[q * 16 + (lane >> 2)].icpt : 0.f;
+    const float icptB = ICPT ? sPar[q * 16 + (lane >> 2) + 8].icpt : 0.f;
+    // drained gradient tiles live in shared memory, one padded row per particle (conflict-free);
+    // this warp owns features [32*half, 32*half + 32) of its 16 particles
+    constexpr int kDrainCols = kP / kHalves;    // features drained by this warp
+    float* grad_row = reinterpret_cast<float*>(gbase + kOffGrad) + (size_t)(lane < 16 ? s : 0) * (kP + 1) + kDrainCols * half;
     if (lane < 16)
-      for (int j = 0; j < kP; ++j) grad_row[j] = 0.f;
+      for (int j = 0; j < kDrainCols; ++j) grad_row[j] = 0.f;
     int64_t n_drained = 0;
 
     auto drain = [&]() {
@@ -557,13 +596,17 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
       mbar_wait(bGFull + 8 * gb, (uint32_t)((grp >> 1) & 1));
       tc_fence_after();
 #pragma unroll
-      for (int ch = 0; ch < kP / 32; ++ch) {
+      for (int ch = 0; ch < kDrainCols / 32; ++ch) {
+        // 32x32b: thread == TMEM lane; lanes 0-15 hold the rows fed by the hi scores of particle
+        // 16*q + lane, lanes 16-31 (kRLo only) the rows fed by its lo scores
         uint32_t v[32];
-        tc_ld32(tmem + lane_base + kColG + gb * kP + ch * 32, v);
+        tc_ld32(tmem + lane_base + kColG + gb * kP + half * kDrainCols + ch * 32, v);
         tc_wait_ld();
-        if (lane < 16) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) grad_row[ch * 32 + c] += __uint_as_float(v[c]);
+        for (int c = 0; c < 32; ++c) {
+          float g = __uint_as_float(v[c]);
+          if (kRLo) g += __shfl_down_sync(0xffffffffu, g, 16);
+          if (lane < 16) grad_row[ch * 32 + c] += g;
         }
       }
       tc_fence_before();
@@ -571,9 +614,11 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
       ++n_drained;
     };
 
-    // one (row, particle) point: score for the gradient product and the running statistic
-    auto point = [&](uint32_t& cell, float y, float live, float icpt, float& stat, float& ssum) {
-      const float eta = ICPT ? __uint_as_float(cell) + icpt : __uint_as_float(cell);
+    // one (row, particle) point: eta = hi row + lo row; the score goes back as a hi / lo pair for
+    // the gradient product, and into the running statistic
+    auto point = [&](uint32_t& cell, uint32_t& cell_lo, float y, float live, float icpt, float& stat, float& ssum) {
+      float eta = __uint_as_float(cell) + __uint_as_float(cell_lo);
+      if (ICPT) eta += icpt;
       float score;
       if (FAMILY == MNF_NORMAL) {
         score = fmaf(-live, eta, y);             // live * (y - eta); 1/sigma^2 applied at the end
@@ -590,23 +635,27 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
         stat += live * fmaf(y, eta, -rate);
       }
       if (ICPT) ssum += score;
-      cell = rn_tf32(score);
+      const uint32_t hi = rn_tf32(score);
+      cell = hi;
+      if (kRLo) cell_lo = rn_tf32(score - __uint_as_float(hi));
     };
     // 32 columns (tile rows): thread t touches rows 32ch + 8g + 2(t%4) + {0,1}; their (y, live)
     // pairs are one 16-byte shared-memory word
-    auto process = [&](uint32_t (&v)[16], const float4* yl, int ch, float& sa, float& sb, float& ra, float& rb) {
+    auto process = [&](uint32_t (&v)[16], uint32_t (&l)[16], const float4* yl, int ch, float& sa, float& sb,
+                       float& ra, float& rb) {
       float4 w[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) w[g] = yl[16 * ch + 4 * g + (lane & 3)];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        point(v[4 * g + 0], w[g].x, w[g].y, icptA, sa, ra);
-        point(v[4 * g + 1], w[g].z, w[g].w, icptA, sa, ra);
-        point(v[4 * g + 2], w[g].x, w[g].y, icptB, sb, rb);
-        point(v[4 * g + 3], w[g].z, w[g].w, icptB, sb, rb);
+        point(v[4 * g + 0], l[4 * g + 0], w[g].x, w[g].y, icptA, sa, ra);
+        point(v[4 * g + 1], l[4 * g + 1], w[g].z, w[g].w, icptA, sa, ra);
+        point(v[4 * g + 2], l[4 * g + 2], w[g].x, w[g].y, icptB, sb, rb);
+        point(v[4 * g + 3], l[4 * g + 3], w[g].z, w[g].w, icptB, sb, rb);
       }
     };
 
+    constexpr uint32_t kLoRows = 16u << 16;   // TMEM lane offset of the lo rows inside a quadrant
     TC_DECL();
     for (int64_t k = 0; k < my_tiles; ++k) {
       TC_T0();
@@ -618,27 +667,25 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
       mbar_wait(bEtaFull + 8 * b, (uint32_t)((k >> 1) & 1));
       TC_ACC(0);   // epi: wait eta_full (+ drain)
       tc_fence_after();
-      const uint32_t t_eta = tmem + lane_base + kColEta + b * kTileM;
-      // software pipeline over four 32-column chunks: the next chunk's tcgen05.ld is in flight
-      // while the current one is processed; R^T replaces eta^T in place (A operand of the G product)
+      constexpr int kChunks = 4 / kHalves;      // 32-column chunks of the tile handled by this warp
+      const uint32_t t_eta = tmem + lane_base + kColEta + b * kTileM + 32 * kChunks * half;
+      // software pipeline over the chunks: the next chunk's tcgen05.ld pair (hi rows, lo rows) is in
+      // flight while the current one is processed; R^T replaces eta^T in place (A operand of the G product)
       float sa = 0.f, sb = 0.f, ra = 0.f, rb = 0.f;
-      uint32_t va[16], vb[16];
-      tc_ld_16x256b_x4(t_eta, va);
-      tc_wait_ld();
-      tc_ld_16x256b_x4(t_eta + 32, vb);
-      process(va, yl, 0, sa, sb, ra, rb);
-      tc_st_16x256b_x4(t_eta, va);
-      tc_wait_ld();
-      tc_ld_16x256b_x4(t_eta + 64, va);
-      process(vb, yl, 1, sa, sb, ra, rb);
-      tc_st_16x256b_x4(t_eta + 32, vb);
-      tc_wait_ld();
-      tc_ld_16x256b_x4(t_eta + 96, vb);
-      process(va, yl, 2, sa, sb, ra, rb);
-      tc_st_16x256b_x4(t_eta + 64, va);
-      tc_wait_ld();
-      process(vb, yl, 3, sa, sb, ra, rb);
-      tc_st_16x256b_x4(t_eta + 96, vb);
+      uint32_t v[2][16], l[2][16];
+      tc_ld_16x256b_x4(t_eta, v[0]);
+      tc_ld_16x256b_x4(t_eta + kLoRows, l[0]);
+#pragma unroll
+      for (int ch = 0; ch < kChunks; ++ch) {
+        tc_wait_ld();
+        if (ch + 1 < kChunks) {
+          tc_ld_16x256b_x4(t_eta + 32 * (ch + 1), v[(ch + 1) & 1]);
+          tc_ld_16x256b_x4(t_eta + kLoRows + 32 * (ch + 1), l[(ch + 1) & 1]);
+        }
+        process(v[ch & 1], l[ch & 1], yl, kChunks * half + ch, sa, sb, ra, rb);
+        tc_st_16x256b_x4(t_eta + 32 * ch, v[ch & 1]);
+        if (kRLo) tc_st_16x256b_x4(t_eta + kLoRows + 32 * ch, l[ch & 1]);
+      }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(bRReady + 8 * b);
@@ -656,7 +703,6 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
       const int64_t n_grp = (my_tiles + kFlush - 1) / kFlush;
       while (n_drained < n_grp) drain();
     }
-    asm volatile("bar.sync 1, %0;" ::"n"((kEpiWarps + 1) * 32) : "memory");   // y warp's counters are final
     // the four threads t%4 = 0..3 of a quad hold partial sums of the same two particles
     stA_total += __shfl_xor_sync(0xffffffffu, stA_total, 1);
     stA_total += __shfl_xor_sync(0xffffffffu, stA_total, 2);
@@ -668,21 +714,31 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constant
       scB_total += __shfl_xor_sync(0xffffffffu, scB_total, 1);
       scB_total += __shfl_xor_sync(0xffffffffu, scB_total, 2);
     }
-    float* s_stat = reinterpret_cast<float*>(gbase + kOffStat);
+    float* s_stat = reinterpret_cast<float*>(gbase + kOffStat) + half * 2 * kNS;   // [half][2][kNS]
     if ((lane & 3) == 0) {
-      s_stat[warp * 16 + (lane >> 2)] = (float)stA_total;
-      s_stat[warp * 16 + (lane >> 2) + 8] = (float)stB_total;
+      s_stat[q * 16 + (lane >> 2)] = (float)stA_total;
+      s_stat[q * 16 + (lane >> 2) + 8] = (float)stB_total;
       if (ICPT) {
-        s_stat[kNS + warp * 16 + (lane >> 2)] = (float)scA_total;
-        s_stat[kNS + warp * 16 + (lane >> 2) + 8] = (float)scB_total;
+        s_stat[kNS + q * 16 + (lane >> 2)] = (float)scA_total;
+        s_stat[kNS + q * 16 + (lane >> 2) + 8] = (float)scB_total;
       }
     }
-    __syncwarp();
-    const float st0 = lane < 16 ? s_stat[s] : 0.f;
-    const float sc0 = (ICPT && lane < 16) ? s_stat[kNS + s] : 0.f;
+    // every epilogue warp's statistics and gradient columns, and the y warp's counters, are final
+    asm volatile("bar.sync 1, %0;" ::"n"((kEpiWarps + 1) * 32) : "memory");
+    const float* s_all = reinterpret_cast<const float*>(gbase + kOffStat);
+    const bool owner_thread = half == 0 && lane < 16;
+    float st0 = 0.f, sc0 = 0.f;
+    if (owner_thread) {
+#pragma unroll
+      for (int h = 0; h < kHalves; ++h) {
+        st0 += s_all[2 * kNS * h + s];
+        if (ICPT) sc0 += s_all[2 * kNS * h + kNS + s];
+      }
+    }
+    grad_row -= kDrainCols * half;
 
     // ---- per-particle results: this thread is the only owner of particle s --------------------
-    if (lane < 16 && s < S) {
+    if (owner_thread && s < S) {
       const int ncol = 1 + kP + 2;
       float* out = partial + ((size_t)blockIdx.x * S + s) * ncol;
       const DenseParticle pp = sPar[s];

@@ -7,17 +7,20 @@
 // One persistent CTA per SM walks 128-row tiles; a tile is streamed as C chunks of 64 features
 // (32 KB per operand image):
 //
-//   eta[128 x NS]   = sum_c Xc[128 x 64] . Theta_c^T[64 x NS]   tcgen05.mma kind::tf32 M=128 N=NS
-//                     A = X chunk, K-major SWIZZLE_128B image; B = Theta, K-major, staged once
+//   eta[128 x 2NS]  = sum_c Xc[128 x 64] . Theta_c^T[64 x 2NS]  tcgen05.mma kind::tf32 M=128 N=2NS
+//                     A = X chunk, K-major SWIZZLE_128B image; B = Theta, K-major, staged once as
+//                     NS hi rows tf32(theta) and NS lo rows tf32(theta - hi): eta = hi column + lo
+//                     column carries theta to 22 bits (a TF32-rounded Theta is a systematic
+//                     per-particle error that does not average out over rows); + 8 cycles per MMA
 //   R  [128 x NS]   = score(y, eta + intercept)                 epilogue: thread == row; written to
 //                     shared memory as the K-major B operand of the gradient product
 //   Gc [64 x NS]   += Xc^T[64 x 128] . R[128 x NS]              tcgen05.mma kind::tf32 M=64 N=NS
 //                     A = X chunk, MN-major SWIZZLE_128B_BASE32B image; B = R
 //
 // Why this orientation: with particles on the MMA N dimension one MMA costs about
-// NS/2 + 11 + M/4 cycles (tools/umma_time.cu), i.e. 8*51 + 16*35 = 968 cycles per chunk at
+// N/2 + 11 + M/4 cycles (tools/umma_time.cu), i.e. 8*59 + 16*35 = 1032 cycles per chunk at
 // NS = 16 against ~1100 cycles of HBM time per 32 KB chunk and SM, and tensor memory holds only
-// (2 + 2C) * NS columns. The transposed orientation of dense_tc.cuh would need 256 columns for
+// (4 + 2C) * NS columns. The transposed orientation of dense_tc.cuh would need 256 columns for
 // Theta alone at p = 256 and 75 + 43 cycles per MMA pair.
 //
 // Data movement: as in dense_tc.cuh both operand images of a chunk come from TMA with the
@@ -32,9 +35,9 @@
 // and L2 prefetch, 6 stages y (and the mask) of each tile in shared memory, 7 TMEM allocation and
 // every MMA.
 //
-// Precision mode: the same as dense_tc.cuh (TF32 operands rounded to nearest, fp32 accumulate in
-// TMEM, the gradient accumulators ping-ponged and drained every kFlush tiles, fp32/fp64 SIMT for
-// log-densities and sums).
+// Precision mode: the same as dense_tc.cuh (X rounded to TF32 by the TMA unit, Theta as hi + lo
+// TF32 pairs, scores rounded to TF32, fp32 accumulate in TMEM, the gradient accumulators
+// ping-ponged and drained every kFlush tiles, fp32/fp64 SIMT for log-densities and sums).
 //
 // Replaces: aten::mv / addmv_ and MvBackward of `X @ theta (+ intercept)`
 // (examples/minibatch.md:33, tests/test_mininf.py:11) and the Normal / Bernoulli / Poisson
@@ -97,7 +100,7 @@ __host__ __device__ inline Layout make_layout(int NS, int C, int k_stages, int m
   l.off_k = 0;
   l.off_mn = l.off_k + (uint32_t)k_stages * kChunkBytes;
   l.off_theta = l.off_mn + (uint32_t)mn_stages * kChunkBytes;
-  l.off_r = l.off_theta + (uint32_t)(2 * C) * (uint32_t)NS * 128u;   // Theta: 2C atoms of NS rows x 128 B
+  l.off_r = l.off_theta + (uint32_t)(2 * C) * (uint32_t)(2 * NS) * 128u;   // Theta: 2C atoms of 2NS (hi, lo) rows x 128 B
   l.off_bar = l.off_r + 2u * 4u * (uint32_t)NS * 128u;                // R: two buffers of four atoms
   l.off_misc = l.off_bar + kBarBytes;                                 // tmem slot + two fp64 counters
   l.off_par = l.off_misc + 32;                                        // DenseParticle[NS], 16 B apart
@@ -209,20 +212,23 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     sStat[2 * n] = 0.0;
     sStat[2 * n + 1] = 0.0;
   }
-  // Theta as the B operand of the eta product: particle n is row n, feature j is k; spare particle
-  // rows are zero. Consecutive threads take consecutive features of one particle.
+  // Theta as the B operand of the eta product: particle n is row n (hi half) and row NS + n (lo
+  // half), feature j is k; spare particle rows are zero. Consecutive threads take consecutive
+  // features of one particle.
   for (int i = tid; i < NS * p_pad; i += kThreads) {
     const int n = i / p_pad, j = i - n * p_pad;
-    const uint32_t v = (n < S && j < p) ? rn_tf32(z[(int64_t)n * D + site.theta_lat + j]) : 0u;
-    sts32(sTheta + kmajor_offset(NS, n, j), v);
+    const float th = (n < S && j < p) ? z[(int64_t)n * D + site.theta_lat + j] : 0.f;
+    const uint32_t hi = rn_tf32(th);
+    sts32(sTheta + kmajor_offset(2 * NS, n, j), hi);
+    sts32(sTheta + kmajor_offset(2 * NS, NS + n, j), rn_tf32(th - __uint_as_float(hi)));
   }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t col_eta = 0;                   // + b * NS
-  const uint32_t col_g = 2 * NS;                // + (gb * C + c) * NS
+  const uint32_t col_eta = 0;                   // + b * 2NS (hi columns, then lo columns)
+  const uint32_t col_g = 4 * NS;                // + (gb * C + c) * NS
 
   if (warp == kWarpMnTma) {
     // ================= MN-major ring: TMA producer (one elected lane) =========================
@@ -333,7 +339,7 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     asm volatile("bar.sync 1, %0;" ::"n"((kEpiWarps + 1) * 32) : "memory");
   } else if (warp == kMmaWarp) {
     // ================= MMA issuer: warp-uniform loops, one elected lane issues ================
-    constexpr uint32_t idesc_eta = idesc_tf32(kTileM, NS, 0, 0);   // M=128 N=NS, A and B K-major
+    constexpr uint32_t idesc_eta = idesc_tf32(kTileM, 2 * NS, 0, 0);   // M=128 N=2NS, A and B K-major
     constexpr uint32_t idesc_g = idesc_tf32(kChunk, NS, 1, 0);     // M=64  N=NS, A MN-major, B K-major
     const uint64_t dK = smem_desc(sK, 16, 1024, 2);                // K-major SWIZZLE_128B
     const uint64_t dMN = smem_desc(sMN, kAtomBytes, 512, 1);       // MN-major SWIZZLE_128B_BASE32B
@@ -343,7 +349,8 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
     const uint32_t dMN_lo = (uint32_t)dMN, dMN_hi = (uint32_t)(dMN >> 32);
     const uint32_t dT_lo = (uint32_t)dT, dT_hi = (uint32_t)(dT >> 32);
     const uint32_t dR_lo = (uint32_t)dR, dR_hi = (uint32_t)(dR >> 32);
-    constexpr uint32_t kBAtom16 = (uint32_t)(NS * 128) >> 4;        // B-operand atom stride, 16-byte units
+    constexpr uint32_t kBAtom16 = (uint32_t)(NS * 128) >> 4;        // R atom stride (NS rows), 16-byte units
+    constexpr uint32_t kTAtom16 = (uint32_t)(2 * NS * 128) >> 4;    // Theta atom stride (2NS rows)
     int kst = 0, mst = 0;
     uint32_t kph = 0, mph = 0;
     // Step t interleaves, chunk by chunk, the eta product of tile t with the gradient product of
@@ -365,14 +372,14 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
           mbar_wait(bKFull + 8 * kst, kph);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t d = tmem + col_eta + be * NS;
+            const uint32_t d = tmem + col_eta + be * (2 * NS);
             const uint32_t a_lo = dK_lo + (uint32_t)kst * (kChunkBytes >> 4);
-            const uint32_t b_lo = dT_lo + (uint32_t)(2 * c) * kBAtom16;
+            const uint32_t b_lo = dT_lo + (uint32_t)(2 * c) * kTAtom16;
 #pragma unroll
             for (int a = 0; a < 2; ++a) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                tc_mma_ss(d, a_lo + ((a * kAtomBytes + ks * 32) >> 4), dK_hi, b_lo + a * kBAtom16 + ks * 2, dT_hi,
+                tc_mma_ss(d, a_lo + ((a * kAtomBytes + ks * 32) >> 4), dK_hi, b_lo + a * kTAtom16 + ks * 2, dT_hi,
                           idesc_eta, (c | a | ks) != 0 ? 1u : 0u);
               }
             }
@@ -488,8 +495,9 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
       if (k > 0 && (k % kStatFlush) == 0) hand_over();
       mbar_wait(bEtaFull + 8 * b, (uint32_t)((k >> 1) & 1));
       tc_fence_after();
-      uint32_t v[NS];
-      tc_ld_row<NS>(tmem + lane_base + col_eta + b * NS, v);
+      uint32_t v[NS], vlo[NS];
+      tc_ld_row<NS>(tmem + lane_base + col_eta + b * (2 * NS), v);
+      tc_ld_row<NS>(tmem + lane_base + col_eta + b * (2 * NS) + NS, vlo);
       tc_wait_ld();
       // R buffer b was last read by the gradient product of tile k-2, which the commit behind
       // eta_full of this tile covers (tcgen05.commit tracks every earlier MMA of the issuer)
@@ -498,7 +506,7 @@ dense_tcr_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_constan
       const uint32_t chunk = (uint32_t)lane >> 2;
 #pragma unroll
       for (int n = 0; n < NS; ++n) {
-        float eta = __uint_as_float(v[n]);
+        float eta = __uint_as_float(v[n]) + __uint_as_float(vlo[n]);
         if (ICPT) eta += icpt[ICPT ? n : 0];
         float score;
         if (FAMILY == MNF_NORMAL) {

@@ -3,6 +3,7 @@
 #pragma once
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>

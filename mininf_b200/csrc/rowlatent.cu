@@ -18,7 +18,7 @@ int launch_rowlatent_inst(const mnf_rowlatent_t& d, const float* z, int S, int D
   MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel<<<grid, kRowThreads, smem, stream>>>(d, z, S, D, s_begin, first_pass, seed, offset, offset_dev,
                                                with_entropy, partial, status);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   return MNF_OK;
 }
 

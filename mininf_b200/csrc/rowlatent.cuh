@@ -190,7 +190,7 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
     } else {
 #pragma unroll
       for (int q = 0; q < SP / 4; ++q) {
-        Philox rng(seed, offset, ((uint64_t)e << 8) | (uint64_t)((s_begin >> 2) + q));
+        Philox rng(seed, offset, kPhiloxRowLatent | ((uint64_t)e << 8) | (uint64_t)((s_begin >> 2) + q));
         const uint4 r = rng.next();
         const float2 n0 = box_muller_fast(r.x, r.y), n1 = box_muller_fast(r.z, r.w);
         eps_r[4 * q + 0] = n0.x; eps_r[4 * q + 1] = n0.y; eps_r[4 * q + 2] = n1.x; eps_r[4 * q + 3] = n1.y;

@@ -31,7 +31,7 @@ int launch_site_sweep(const mnf_site_t* sites, const float* z, int S, int D, flo
     MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kernel<<<grid, kSweepThreads, smem, stream>>>(args, z, S, D, partial, status);
   }
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   return MNF_OK;
 }
 
@@ -43,7 +43,7 @@ int launch_poisson_exp_q(const mnf_site_t& site, const float* z, int S, int D, f
   const size_t smem = poisson_exp_smem_bytes<Q>();
   MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel<<<grid, kSweepThreads, smem, stream>>>(site, z, S, D, partial, status, need_exact);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   return MNF_OK;
 }
 
@@ -86,12 +86,12 @@ int launch_poisson_moments(const mnf_site_t& site, const float* z, int S, int D,
   auto moment_kernel = poisson_moment_kernel;
   MNF_CUDA_CHECK(cudaFuncSetAttribute(moment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   poisson_range_kernel<<<range_grid, kChebThreads, 0, stream>>>(site, range_partial);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   moment_kernel<<<moment_grid, kChebThreads, smem, stream>>>(site, range_partial, range_grid, z, S, D, rows, status);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   poisson_moment_finish_kernel<<<1, kChebThreads, 0, stream>>>(site, rows, moment_grid, range_partial, range_grid,
                                                               z, S, D, acc, need_exact);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   *need_exact_out = need_exact;
   return MNF_OK;
 }
@@ -115,14 +115,14 @@ int launch_normal_stats(const mnf_site_t& site, bool vec, int grid, double* cta_
                         cudaStream_t stream) {
   if (vec) normal_stats_kernel<true><<<grid, kStatThreads, 0, stream>>>(site, cta_stats, status);
   else normal_stats_kernel<false><<<grid, kStatThreads, 0, stream>>>(site, cta_stats, status);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   return MNF_OK;
 }
 
 int launch_normal_finish(const mnf_site_t& site, const double* cta_stats, int grid, const float* z, int S, int D,
                          double* acc, uint32_t* status, cudaStream_t stream) {
   normal_stats_finish_kernel<<<1, 32 * kStatCols, 0, stream>>>(site, cta_stats, grid, z, S, D, acc, status);
-  MNF_CUDA_CHECK(cudaGetLastError());
+  MNF_LAUNCH_CHECK();
   return MNF_OK;
 }
 
@@ -168,7 +168,7 @@ extern "C" {
 
 int mnf_site_sweep(const mnf_site_t* sites, int n_sites, const float* z, int n_particles,
                    int n_latent_total, double* acc, void* workspace, size_t workspace_bytes,
-                   uint32_t* status, void* stream_) {
+                   uint32_t flags, uint32_t* status, void* stream_) {
   if (!sites || !z || !acc || !workspace || !status)
     return fail(MNF_E_INVALID, "mnf_site_sweep: null pointer%s%s");
   if (n_sites < 1 || n_sites > MNF_MAX_FUSED_SITES)
@@ -202,8 +202,12 @@ int mnf_site_sweep(const mnf_site_t* sites, int n_sites, const float* z, int n_p
   mnf_site_t generic[MNF_MAX_FUSED_SITES];
   int n_generic = 0, n_normal = 0, n_poisson = 0;
   int normal_idx[MNF_MAX_FUSED_SITES], poisson_idx[MNF_MAX_FUSED_SITES];
+  // Without MNF_SWEEP_CLOSED_FORM every site is evaluated once per (particle, element): Normal
+  // sites stay in the fused per-particle kernel and the Poisson moment path is off.
+  const bool closed_form = (flags & MNF_SWEEP_CLOSED_FORM) != 0;
   for (int i = 0; i < n_sites; ++i) {
-    const int kind = site_fast_kind(sites[i]);
+    int kind = site_fast_kind(sites[i]);
+    if (kind == kFastNormalId && !closed_form) kind = kFastNone;
     if (kind == kFastNone) generic[n_generic++] = sites[i];
     else if (kind == kFastNormalId) normal_idx[n_normal++] = i;
     else poisson_idx[n_poisson++] = i;
@@ -251,9 +255,10 @@ int mnf_site_sweep(const mnf_site_t* sites, int n_sites, const float* z, int n_p
     // data-only moment path first; the per-particle kernel runs only if its check fails (device flag)
     uint32_t* need_exact = nullptr;
     const size_t scratch_bytes = back - exact_bytes;
-    if (int rc = launch_poisson_moments(site, z, S, D, acc, static_cast<char*>(workspace) + exact_bytes,
-                                        scratch_bytes, status, c->sm_count, stream, &need_exact))
-      return rc;
+    if (closed_form)
+      if (int rc = launch_poisson_moments(site, z, S, D, acc, static_cast<char*>(workspace) + exact_bytes,
+                                          scratch_bytes, status, c->sm_count, stream, &need_exact))
+        return rc;
     if (int rc = launch_poisson_exp(site, z, S, D, partial, status, need_exact, pgrid, stream)) return rc;
     ColMap fast_map;
     fast_map.n_vec = 0;

@@ -16,7 +16,7 @@ __device__ inline float philox_standard_gamma(float alpha, uint64_t seed, uint64
   float scale = 1.0f;
   uint32_t round = 0;
   if (alpha < 1.0f) {
-    Philox rng(seed, offset, (index << 8) | 0xFFu);
+    Philox rng(seed, offset, kPhiloxGamma | (index << 8) | 0xFFu);
     const uint4 r = rng.next();
     const float u = ((float)(r.x >> 8) + 1.0f) * (1.0f / 16777216.0f);
     scale = powf(u, 1.0f / alpha);
@@ -25,7 +25,7 @@ __device__ inline float philox_standard_gamma(float alpha, uint64_t seed, uint64
   const float d = alpha - 1.0f / 3.0f;
   const float c = rsqrtf(9.0f * d);
   for (; round < 64; ++round) {
-    Philox rng(seed, offset, (index << 8) | round);
+    Philox rng(seed, offset, kPhiloxGamma | (index << 8) | round);
     const uint4 r = rng.next();
     const float x = box_muller(r.x, r.y).x;
     const float t = 1.0f + c * x;
@@ -49,11 +49,22 @@ __device__ __forceinline__ int find_latent(const mnf_latent_t* lat, int n, int c
 // -------------------------------------------------------------------------------------------
 // rsample: z[s][d] from noise, FactorizedDistribution.rsample (mininf/nn.py:133-145)
 // -------------------------------------------------------------------------------------------
+// value of a constrained parameter from its unconstrained storage (ParameterizedDistribution.forward,
+// mininf/nn.py:88-96: transform_to(real) is the identity, transform_to(positive) is exp)
+__device__ __forceinline__ float apply_transform(uint8_t code, float raw) {
+  return (code & MNF_T_MASK) == MNF_T_EXP ? expf(raw) : raw;
+}
+
+// `raw` != NULL (fused SVI step): the constrained parameters are computed here from the
+// unconstrained ones, raw[d] -> p0 of column d, raw[D + d] -> p1, and written to `constrained`
+// [2D] (where the latent table's p0 / p1 pointers point) for the later kernels of the step.
 __global__ void rsample_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
                                const float* __restrict__ noise_in, uint64_t seed, uint64_t offset,
                                const uint64_t* __restrict__ offset_dev,
                                float* __restrict__ z, float* __restrict__ noise_out,
-                               double* __restrict__ acc, uint32_t* __restrict__ status) {
+                               double* __restrict__ acc, uint32_t* __restrict__ status,
+                               const float* __restrict__ raw, const uint8_t* __restrict__ tcode,
+                               float* __restrict__ constrained) {
   if (offset_dev != nullptr) offset += *offset_dev;   // device-side call index (CUDA-graph replays)
   const int64_t n_z = (int64_t)S * D;
   const int64_t n_acc = (int64_t)S * (D + 1);
@@ -65,14 +76,25 @@ __global__ void rsample_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, 
     const int d = (int)(i % D);
     const mnf_latent_t L = lat[find_latent(lat, n_lat, d)];
     const int e = d - L.offset;
-    const float p0 = L.p0[e], p1 = L.p1[e];
+    float p0, p1;
+    if (raw != nullptr) {
+      p0 = apply_transform(tcode[d], raw[d]);
+      p1 = apply_transform(tcode[D + d], raw[D + d]);
+      if (i < D) {             // particle 0 publishes the constrained values
+        constrained[d] = p0;
+        constrained[D + d] = p1;
+      }
+    } else {
+      p0 = L.p0[e];
+      p1 = L.p1[e];
+    }
     float nz, val;
     if (L.family == MNF_NORMAL) {
       // Normal.rsample: loc + eps * scale                       TORCH normal.py:82-85
       if (noise_in != nullptr) {
         nz = noise_in[i];
       } else {
-        Philox rng(seed, offset, (uint64_t)i);
+        Philox rng(seed, offset, kPhiloxNormal | (uint64_t)i);
         const uint4 r = rng.next();
         nz = box_muller(r.x, r.y).x;
       }
@@ -90,7 +112,7 @@ __global__ void rsample_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, 
         nz = noise_in[i];
       } else {
         const float g1 = philox_standard_gamma(p0, seed, offset, (uint64_t)(2 * i));
-        const float g0 = philox_standard_gamma(p1, seed, offset, (uint64_t)(2 * i + 1) | ((uint64_t)1 << 40));
+        const float g0 = philox_standard_gamma(p1, seed, offset, (uint64_t)(2 * i + 1) | (kPhiloxBeta0 >> 8));
         nz = fminf(fmaxf(g1 / (g1 + g0), kFloatEps), 1.0f - kFloatEps);
       }
       val = nz;
@@ -109,25 +131,22 @@ __global__ void rsample_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, 
 // -------------------------------------------------------------------------------------------
 constexpr int kSmallThreads = 128;
 
-__global__ void __launch_bounds__(kSmallThreads)
-small_sites_kernel(const mnf_site_t* __restrict__ sites, const float* __restrict__ z, int S, int D,
-                   double* __restrict__ acc, uint32_t* __restrict__ status) {
-  const mnf_site_t site = sites[blockIdx.y];
-  const int s = blockIdx.z;
-  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  if ((int64_t)blockIdx.x * blockDim.x >= site.numel) return;
+// Sums of one thread over its elements of one (site, particle) pair; element-wise latent targets
+// are added to acc directly (distinct addresses within a site; other sites may touch the same
+// column, hence atomics).
+struct SmallSums {
+  double lp;
+  float gA0, gB0, gA1, gB1;
+};
+
+__device__ inline SmallSums small_site_elements(const mnf_site_t& site, const float* zs, double* as, int64_t i0,
+                                                int64_t stride, uint32_t& bad) {
   const bool g0 = link_has_latent(site.param[0]);
   const bool g1 = link_has_latent(site.param[1]);
   const bool two = site.family <= MNF_BETA;  // families with a second parameter
   const float w = (float)site.scale;
-  const float* zs = z + (int64_t)s * D;
-  double* as = acc + (int64_t)s * (D + 1);
-  uint32_t bad = 0;
-
-  double lp_sum = 0.0;
-  // gradient sums of this thread for scalar-latent (stride-0) targets
-  float gA0 = 0.f, gB0 = 0.f, gA1 = 0.f, gB1 = 0.f;
+  SmallSums o;
+  o.lp = 0.0; o.gA0 = 0.f; o.gB0 = 0.f; o.gA1 = 0.f; o.gB1 = 0.f;
   for (int64_t i = i0; i < site.numel; i += stride) {
     if (site.mask != nullptr && site.mask[i] == 0) continue;
     const float v = site.value_lat >= 0 ? zs[site.value_lat + i] : site.value[i];
@@ -137,44 +156,88 @@ small_sites_kernel(const mnf_site_t* __restrict__ sites, const float* __restrict
     const Dens dn = density(site.family, v, l0.value, l1.value, g0 || g1);
     if (dn.bad_param) bad |= MNF_ST_BAD_PARAM;
     if (dn.bad_value) bad |= MNF_ST_BAD_VALUE;
-    lp_sum += (double)dn.lp;
-    // element-wise latent targets are distinct addresses within a site; other sites may touch
-    // the same column, hence atomics
+    o.lp += (double)dn.lp;
     if (site.value_lat >= 0) atomicAdd(as + 1 + site.value_lat + i, (double)(w * dn.dv));
     if (g0) {
       const float du = dn.d0 * l0.du;
       const mnf_link_t& L = site.param[0];
-      if (L.a_lat >= 0) { if (L.a_stride) atomicAdd(as + 1 + L.a_lat + L.a_stride * i, (double)(w * du)); else gA0 += du; }
-      if (L.b_lat >= 0) { if (L.b_stride) atomicAdd(as + 1 + L.b_lat + L.b_stride * i, (double)(w * du * l0.x)); else gB0 += du * l0.x; }
+      if (L.a_lat >= 0) { if (L.a_stride) atomicAdd(as + 1 + L.a_lat + L.a_stride * i, (double)(w * du)); else o.gA0 += du; }
+      if (L.b_lat >= 0) { if (L.b_stride) atomicAdd(as + 1 + L.b_lat + L.b_stride * i, (double)(w * du * l0.x)); else o.gB0 += du * l0.x; }
     }
     if (two && g1) {
       const float du = dn.d1 * l1.du;
       const mnf_link_t& L = site.param[1];
-      if (L.a_lat >= 0) { if (L.a_stride) atomicAdd(as + 1 + L.a_lat + L.a_stride * i, (double)(w * du)); else gA1 += du; }
-      if (L.b_lat >= 0) { if (L.b_stride) atomicAdd(as + 1 + L.b_lat + L.b_stride * i, (double)(w * du * l1.x)); else gB1 += du * l1.x; }
+      if (L.a_lat >= 0) { if (L.a_stride) atomicAdd(as + 1 + L.a_lat + L.a_stride * i, (double)(w * du)); else o.gA1 += du; }
+      if (L.b_lat >= 0) { if (L.b_stride) atomicAdd(as + 1 + L.b_lat + L.b_stride * i, (double)(w * du * l1.x)); else o.gB1 += du * l1.x; }
     }
   }
+  return o;
+}
+
+// acc column of sum `k` (0 log-density, 1..4 scalar-latent gradients) of a site, or -1
+__device__ __forceinline__ int small_site_target(const mnf_site_t& site, int k) {
+  const bool g0 = link_has_latent(site.param[0]);
+  const bool g1 = link_has_latent(site.param[1]);
+  const bool two = site.family <= MNF_BETA;
+  const mnf_link_t& L0 = site.param[0];
+  const mnf_link_t& L1 = site.param[1];
+  if (k == 0) return 0;
+  if (k == 1 && g0 && L0.a_lat >= 0 && L0.a_stride == 0) return 1 + L0.a_lat;
+  if (k == 2 && g0 && L0.b_lat >= 0 && L0.b_stride == 0) return 1 + L0.b_lat;
+  if (k == 3 && two && g1 && L1.a_lat >= 0 && L1.a_stride == 0) return 1 + L1.a_lat;
+  if (k == 4 && two && g1 && L1.b_lat >= 0 && L1.b_stride == 0) return 1 + L1.b_lat;
+  return -1;
+}
+
+__global__ void __launch_bounds__(kSmallThreads)
+small_sites_kernel(const mnf_site_t* __restrict__ sites, const float* __restrict__ z, int S, int D,
+                   double* __restrict__ acc, uint32_t* __restrict__ status) {
+  const mnf_site_t site = sites[blockIdx.y];
+  const int s = blockIdx.z;
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if ((int64_t)blockIdx.x * blockDim.x >= site.numel) return;
+  const float* zs = z + (int64_t)s * D;
+  double* as = acc + (int64_t)s * (D + 1);
+  uint32_t bad = 0;
+  SmallSums t = small_site_elements(site, zs, as, i0, stride, bad);
   // block reduction: warp shuffles, then one warp finishes through shared memory
   __shared__ double s_red[kSmallThreads / 32][5];
-  lp_sum = warp_sum(lp_sum);
-  gA0 = warp_sum(gA0); gB0 = warp_sum(gB0); gA1 = warp_sum(gA1); gB1 = warp_sum(gB1);
+  t.lp = warp_sum(t.lp);
+  t.gA0 = warp_sum(t.gA0); t.gB0 = warp_sum(t.gB0); t.gA1 = warp_sum(t.gA1); t.gB1 = warp_sum(t.gB1);
   if ((threadIdx.x & 31) == 0) {
     double* row = s_red[threadIdx.x >> 5];
-    row[0] = lp_sum; row[1] = gA0; row[2] = gB0; row[3] = gA1; row[4] = gB1;
+    row[0] = t.lp; row[1] = t.gA0; row[2] = t.gB0; row[3] = t.gA1; row[4] = t.gB1;
   }
   __syncthreads();
   if (threadIdx.x < 5) {
-    double t = 0.0;
-    for (int k = 0; k < kSmallThreads / 32; ++k) t += s_red[k][threadIdx.x];
-    const mnf_link_t& L0 = site.param[0];
-    const mnf_link_t& L1 = site.param[1];
-    int target = -1;
-    if (threadIdx.x == 0) target = 0;
-    else if (threadIdx.x == 1 && g0 && L0.a_lat >= 0 && L0.a_stride == 0) target = 1 + L0.a_lat;
-    else if (threadIdx.x == 2 && g0 && L0.b_lat >= 0 && L0.b_stride == 0) target = 1 + L0.b_lat;
-    else if (threadIdx.x == 3 && two && g1 && L1.a_lat >= 0 && L1.a_stride == 0) target = 1 + L1.a_lat;
-    else if (threadIdx.x == 4 && two && g1 && L1.b_lat >= 0 && L1.b_stride == 0) target = 1 + L1.b_lat;
-    if (target >= 0 && t != 0.0) atomicAdd(as + target, site.scale * t);
+    double total = 0.0;
+    for (int k = 0; k < kSmallThreads / 32; ++k) total += s_red[k][threadIdx.x];
+    const int target = small_site_target(site, threadIdx.x);
+    if (target >= 0 && total != 0.0) atomicAdd(as + target, site.scale * total);
+  }
+  if (bad) atomicOr(status, bad);
+}
+
+// The same evaluation inside a single block (the fused tail kernel below): one warp per
+// (site, particle) pair, lanes over the elements.
+__device__ inline void small_sites_block(const mnf_site_t* __restrict__ sites, int n_sites, const float* __restrict__ z,
+                                         int S, int D, double* __restrict__ acc, uint32_t* __restrict__ status) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  uint32_t bad = 0;
+  for (int task = warp; task < n_sites * S; task += n_warps) {
+    const mnf_site_t site = sites[task / S];
+    const int s = task % S;
+    const float* zs = z + (int64_t)s * D;
+    double* as = acc + (int64_t)s * (D + 1);
+    SmallSums t = small_site_elements(site, zs, as, lane, 32, bad);
+    double sums[5] = {t.lp, (double)t.gA0, (double)t.gB0, (double)t.gA1, (double)t.gB1};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const double total = warp_sum(sums[k]);
+      const int target = small_site_target(site, k);
+      if (lane == 0 && target >= 0 && total != 0.0) atomicAdd(as + target, site.scale * total);
+    }
   }
   if (bad) atomicOr(status, bad);
 }
@@ -216,19 +279,53 @@ reduce_partials_kernel(const float* __restrict__ partial, int n_cta, int S, int 
 // -------------------------------------------------------------------------------------------
 constexpr int kFinalThreads = 512;
 
+// torch.optim.Adam (defaults: no weight decay, no amsgrad) over the unconstrained parameters of
+// the packed latent sites, fused into the last kernel of the step (README.md:63-69's
+// `optimizer.step()`; ParameterizedDistribution's transforms, mininf/nn.py:88-96, are chained
+// here instead of by autograd). Passed by value; `raw == nullptr` means "no optimiser".
+struct AdamArgs {
+  float lr, beta1, beta2, eps;
+  float* raw;                 // [2D]
+  const uint8_t* transform;   // [2D] MNF_T_* (| MNF_T_FROZEN)
+  float* m;                   // [2D]
+  float* v;                   // [2D]
+  int64_t* step;              // device: updates applied so far
+};
+
+__device__ __forceinline__ void adam_update(const AdamArgs& ad, int idx, float constrained, double grad_constrained,
+                                            double bc1, double bc2_sqrt) {
+  const uint8_t code = ad.transform[idx];
+  if (code & MNF_T_FROZEN) return;
+  // chain rule through the transform: d exp(raw)/d raw = the constrained value itself
+  const float g = (float)((code & MNF_T_MASK) == MNF_T_EXP ? grad_constrained * (double)constrained : grad_constrained);
+  const float m = ad.beta1 * ad.m[idx] + (1.0f - ad.beta1) * g;
+  const float v = ad.beta2 * ad.v[idx] + (1.0f - ad.beta2) * g * g;
+  ad.m[idx] = m;
+  ad.v[idx] = v;
+  const float denom = (float)((double)sqrtf(v) / bc2_sqrt) + ad.eps;
+  ad.raw[idx] -= (float)((double)ad.lr / bc1) * (m / denom);
+}
+
 // One warp per latent column: the lanes walk the particles (the implicit Gamma / Beta gradients
 // are ~100 fp64 operations per particle), a fixed butterfly combines them, lane 0 adds the
-// entropy terms. Sums run in the same order on every launch.
-__global__ void __launch_bounds__(kFinalThreads)
-finalize_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
-                const float* __restrict__ z, const float* __restrict__ noise,
-                const double* __restrict__ acc, int with_entropy, float* __restrict__ out,
-                uint64_t* __restrict__ step_counter, uint32_t* __restrict__ status) {
-  constexpr int kWarps = kFinalThreads / 32;
-  __shared__ double red[kWarps];
+// entropy terms. Sums run in the same order on every launch. Works for any block size that is a
+// multiple of 32 (<= 1024); acc is read past L1 (the fused tail kernel updates it with atomics).
+__device__ inline void finalize_block(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
+                                      const float* __restrict__ z, const float* __restrict__ noise,
+                                      const double* __restrict__ acc, int with_entropy, float* __restrict__ out,
+                                      uint64_t* __restrict__ step_counter, uint32_t* __restrict__ status,
+                                      const AdamArgs& adam) {
+  __shared__ double red[32];
+  const int kWarps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // last kernel of a step: the next replay of a captured step draws with the next call index
   if (step_counter != nullptr && threadIdx.x == 0) *step_counter += 1;
+  double bc1 = 1.0, bc2_sqrt = 1.0;
+  if (adam.raw != nullptr) {
+    const double t = (double)(*adam.step + 1);
+    bc1 = 1.0 - pow((double)adam.beta1, t);
+    bc2_sqrt = sqrt(1.0 - pow((double)adam.beta2, t));
+  }
   const double invS = 1.0 / (double)S;
   double ent = 0.0;        // lane 0 of each warp: entropy of its columns
   bool nonfinite = false;
@@ -240,7 +337,7 @@ finalize_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
     if (L.family == MNF_NORMAL) {
       // z = loc + eps*scale
       for (int s = lane; s < S; s += 32) {
-        const double g = acc[(int64_t)s * (D + 1) + 1 + d];
+        const double g = __ldcg(acc + (int64_t)s * (D + 1) + 1 + d);
         g0 += g;
         g1 += g * (double)noise[(int64_t)s * D + d];
       }
@@ -248,7 +345,7 @@ finalize_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
       // z = g/rate: dz/dalpha = standard_gamma_grad(alpha, g)/rate, dz/drate = -g/rate^2
       // (the clamp_ at tiny is outside autograd: gradients as if unclamped)
       for (int s = lane; s < S; s += 32) {
-        const double g = acc[(int64_t)s * (D + 1) + 1 + d];
+        const double g = __ldcg(acc + (int64_t)s * (D + 1) + 1 + d);
         const double gam = (double)noise[(int64_t)s * D + d];
         g0 += g * standard_gamma_grad(p0, gam) / p1;
         g1 += g * (-gam / (p1 * p1));
@@ -258,7 +355,7 @@ finalize_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
       // grad_k = dirichlet_grad(x_k, c_k, total) * (go_k - sum_j x_j go_j) with go = (g, 0).
       const double tot = p0 + p1;
       for (int s = lane; s < S; s += 32) {
-        const double g = acc[(int64_t)s * (D + 1) + 1 + d];
+        const double g = __ldcg(acc + (int64_t)s * (D + 1) + 1 + d);
         const double x = (double)noise[(int64_t)s * D + d];
         g0 += dirichlet_grad(x, p0, tot) * g * (1.0 - x);
         g1 += dirichlet_grad(1.0 - x, p1, tot) * (-x * g);
@@ -294,12 +391,16 @@ finalize_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
       if (!isfinite(o0) || !isfinite(o1)) nonfinite = true;
       out[1 + d] = (float)o0;
       out[1 + D + d] = (float)o1;
+      if (adam.raw != nullptr) {
+        adam_update(adam, d, (float)p0, o0, bc1, bc2_sqrt);
+        adam_update(adam, D + d, (float)p1, o1, bc1, bc2_sqrt);
+      }
     }
   }
   // total log joint over particles: warp 0's lanes, added to its entropy share
   if (warp == 0) {
     double lj = 0.0;
-    for (int s = lane; s < S; s += 32) lj += acc[(int64_t)s * (D + 1)];
+    for (int s = lane; s < S; s += 32) lj += __ldcg(acc + (int64_t)s * (D + 1));
     lj = warp_sum(lj);
     ent += lj * invS;
   }
@@ -311,8 +412,108 @@ finalize_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
     const double loss = -total;
     out[0] = (float)loss;
     if (!isfinite(loss)) nonfinite = true;
+    if (adam.raw != nullptr) *adam.step += 1;
   }
   if (nonfinite) atomicOr(status, MNF_ST_NONFINITE);
+}
+
+__global__ void __launch_bounds__(kFinalThreads)
+finalize_kernel(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
+                const float* __restrict__ z, const float* __restrict__ noise,
+                const double* __restrict__ acc, int with_entropy, float* __restrict__ out,
+                uint64_t* __restrict__ step_counter, uint32_t* __restrict__ status) {
+  AdamArgs none;
+  none.raw = nullptr;
+  finalize_block(lat, n_lat, S, D, z, noise, acc, with_entropy, out, step_counter, status, none);
+}
+
+// -------------------------------------------------------------------------------------------
+// Cross-rank exchange of the step accumulator over peer memory (NVLink / NVSwitch), replacing the
+// ncclAllReduce of SURVEY §8e: every rank PUSHES its partial accumulator into a per-source inbox
+// on each peer and raises that peer's arrival flag; the tail kernel of each rank then waits for
+// its W - 1 flags and adds the inboxes in rank order - the same order on every rank, so all
+// ranks hold bit-identical totals and parameters stay replicated without a broadcast. Inboxes
+// are double-buffered by the parity of the exchange epoch: a rank can write into a peer's slot
+// of epoch k + 2 only after that peer signalled epoch k + 1, i.e. after it finished reading
+// epoch k. No host call, no NCCL launch: the step stays capturable in a CUDA graph.
+// -------------------------------------------------------------------------------------------
+struct XrankArgs {
+  int world, rank;
+  int64_t n;                    // doubles per accumulator
+  double* inbox;                // local [2][world][n]
+  uint64_t* flags;              // local [world], flags[r] = last epoch rank r delivered
+  double* const* peer_inbox;    // device array [world]: inbox base on every rank
+  uint64_t* const* peer_flags;  // device array [world]
+  uint64_t* epoch;              // local device word: exchanges completed so far
+};
+
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+constexpr int kXrankThreads = 512;
+
+// grid = world: block b delivers this rank's accumulator to rank b
+__global__ void __launch_bounds__(kXrankThreads)
+xrank_push_kernel(XrankArgs xr, const double* __restrict__ acc) {
+  const int peer = blockIdx.x;
+  if (peer == xr.rank) return;
+  const uint64_t epoch = *xr.epoch + 1;
+  double* dst = xr.peer_inbox[peer] + ((epoch & 1) * (uint64_t)xr.world + (uint64_t)xr.rank) * (uint64_t)xr.n;
+  for (int64_t i = threadIdx.x; i < xr.n; i += kXrankThreads) dst[i] = acc[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) st_release_sys(xr.peer_flags[peer] + xr.rank, epoch);
+}
+
+// wait for every peer's delivery of this epoch, then acc += inboxes in rank order (one block)
+__device__ inline void xrank_gather_block(const XrankArgs& xr, double* __restrict__ acc, uint32_t* __restrict__ status) {
+  const uint64_t epoch = *xr.epoch + 1;
+  if ((int)threadIdx.x < xr.world && (int)threadIdx.x != xr.rank) {
+    // bounded wait (about two seconds): a dead peer must not hang the GPU
+    const long long start = clock64();
+    while (ld_acquire_sys(xr.flags + threadIdx.x) < epoch) {
+      if (clock64() - start > 4000000000LL) {
+        atomicOr(status, MNF_ST_XRANK_TIMEOUT);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  const double* slot = xr.inbox + (epoch & 1) * (uint64_t)xr.world * (uint64_t)xr.n;
+  for (int64_t i = threadIdx.x; i < xr.n; i += blockDim.x) {
+    double total = 0.0;
+    for (int r = 0; r < xr.world; ++r)
+      total += r == xr.rank ? acc[i] : __ldcv(slot + (uint64_t)r * (uint64_t)xr.n + i);
+    acc[i] = total;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *xr.epoch = epoch;
+}
+
+// -------------------------------------------------------------------------------------------
+// Tail of a step in ONE launch: [cross-rank gather] -> [latent-valued (prior) sites] -> finalize
+// [-> Adam]. A single block: the work is O(S * D).
+// -------------------------------------------------------------------------------------------
+constexpr int kTailThreads = 1024;
+
+__global__ void __launch_bounds__(kTailThreads)
+tail_kernel(XrankArgs xr, const mnf_site_t* __restrict__ global_sites, int n_global,
+            const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D, const float* __restrict__ z,
+            const float* __restrict__ noise, double* __restrict__ acc, int with_entropy, float* __restrict__ out,
+            uint64_t* __restrict__ step_counter, uint32_t* __restrict__ status, AdamArgs adam) {
+  if (xr.world > 1) xrank_gather_block(xr, acc, status);
+  if (n_global > 0) {
+    small_sites_block(global_sites, n_global, z, S, D, acc, status);
+    __threadfence();
+    __syncthreads();
+  }
+  finalize_block(lat, n_lat, S, D, z, noise, acc, with_entropy, out, step_counter, status, adam);
 }
 
 // -------------------------------------------------------------------------------------------

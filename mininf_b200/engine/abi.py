@@ -11,14 +11,19 @@ from pathlib import Path
 
 from . import build as _build
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # families (include/mininf_b200.h)
 NORMAL, GAMMA, BETA, BERNOULLI_PROBS, BERNOULLI_LOGITS, POISSON = range(6)
 T_ID, T_EXP = 0, 1
-DENSE_FP32, DENSE_TF32 = 0, 1
-ST_BAD_PARAM, ST_BAD_VALUE, ST_NONFINITE = 1, 2, 4
+T_FROZEN = 0x80
+DENSE_FP32, DENSE_TF32, DENSE_TF32_CLOSED_FORM = 0, 1, 2
+SWEEP_CLOSED_FORM = 1
+ST_BAD_PARAM, ST_BAD_VALUE, ST_NONFINITE, ST_XRANK_TIMEOUT = 1, 2, 4, 8
+STEP_ENTROPY, STEP_PRE, STEP_POST = 1, 2, 4
+STEP_ALL = STEP_PRE | STEP_POST
 MAX_FUSED_SITES = 4
+XRANK_HANDLE_BYTES = 64
 
 E_INVALID, E_UNSUPPORTED, E_CUDA = -1, -2, -3
 
@@ -70,6 +75,41 @@ class RowLatent(C.Structure):
     ]
 
 
+class PlanDesc(C.Structure):
+    _fields_ = [
+        ("n_particles", C.c_int32), ("n_latent_total", C.c_int32), ("n_latents", C.c_int32),
+        ("n_dense", C.c_int32), ("n_groups", C.c_int32), ("n_small_observed", C.c_int32),
+        ("n_small_global", C.c_int32), ("n_rowlatent", C.c_int32),
+        ("latents", C.POINTER(Latent)), ("dense", C.POINTER(DenseSite)), ("dense_mode", C.POINTER(C.c_int32)),
+        ("group_sites", C.POINTER(Site)), ("group_sizes", C.POINTER(C.c_int32)),
+        ("small_observed", C.POINTER(Site)), ("small_global", C.POINTER(Site)),
+        ("rowlatent", C.POINTER(RowLatent)),
+        ("flags", C.c_uint32), ("device", C.c_int32),
+    ]
+
+
+class RowBuffers(C.Structure):
+    _fields_ = [("loc", C.c_void_p), ("scale", C.c_void_p), ("grad_loc", C.c_void_p),
+                ("grad_scale", C.c_void_p), ("eps", C.c_void_p)]
+
+
+class Buffers(C.Structure):
+    _fields_ = [
+        ("z", C.c_void_p), ("noise", C.c_void_p), ("acc", C.c_void_p), ("out", C.c_void_p),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("status", C.c_void_p),
+        ("noise_in", C.c_void_p), ("step_counter", C.c_void_p),
+        ("rows", C.POINTER(RowBuffers)), ("xrank", C.c_void_p),
+    ]
+
+
+class Adam(C.Structure):
+    _fields_ = [
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+        ("raw", C.c_void_p), ("transform", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+        ("constrained", C.c_void_p), ("step", C.c_void_p),
+    ]
+
+
 class DeviceInfo(C.Structure):
     _fields_ = [
         ("sm_count", C.c_int32), ("cc_major", C.c_int32), ("cc_minor", C.c_int32),
@@ -94,7 +134,7 @@ EXPORTS = {
     "mnf_dense_sweep": (C.c_int, [C.POINTER(DenseSite), C.c_int, C.c_void_p, C.c_int, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "mnf_site_sweep": (C.c_int, [C.POINTER(Site), C.c_int, C.c_void_p, C.c_int, C.c_int,
-                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+                                 C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_void_p, C.c_void_p]),
     "mnf_rowlatent_sweep": (C.c_int, [C.POINTER(RowLatent), C.c_void_p, C.c_int, C.c_int, C.c_uint64,
                                       C.c_uint64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
                                       C.c_void_p, C.c_void_p]),
@@ -103,6 +143,17 @@ EXPORTS = {
     "mnf_finalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mnf_masked_count": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "mnf_plan_create": (C.c_int, [C.POINTER(PlanDesc), C.POINTER(C.c_void_p)]),
+    "mnf_plan_update": (C.c_int, [C.c_void_p, C.POINTER(PlanDesc), C.c_void_p]),
+    "mnf_plan_workspace_bytes": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t)]),
+    "mnf_plan_launches": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "mnf_plan_destroy": (C.c_int, [C.c_void_p]),
+    "mnf_elbo_fwd_bwd": (C.c_int, [C.c_void_p, C.POINTER(Buffers), C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "mnf_svi_step": (C.c_int, [C.c_void_p, C.POINTER(Buffers), C.POINTER(Adam), C.c_uint64, C.c_uint64,
+                               C.c_uint32, C.c_void_p]),
+    "mnf_xrank_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "mnf_xrank_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mnf_xrank_destroy": (C.c_int, [C.c_void_p]),
 }
 
 
@@ -152,9 +203,16 @@ _LIBRARY: Library | None = None
 
 
 def load(build_if_missing: bool = False) -> Library:
-    """Load the native library. Raises ``RuntimeError`` if it has not been built."""
+    """Load the native library. Raises ``RuntimeError`` if it has not been built, or if it was
+    built from other sources than the ones in ``csrc/`` now (a stale binary with the same ABI
+    version would otherwise load silently). ``MNF_LIB=/path/to/lib.so`` loads a developer build."""
     global _LIBRARY
     if _LIBRARY is None:
+        import os
+        override = os.environ.get("MNF_LIB")
+        if override:
+            _LIBRARY = Library(Path(override))
+            return _LIBRARY
         if not _build.LIB_PATH.exists():
             if build_if_missing:
                 _build.build()
@@ -163,5 +221,9 @@ def load(build_if_missing: bool = False) -> Library:
                     f"the mininf_b200 CUDA library is missing ({_build.LIB_PATH}); build it with "
                     "`python -m mininf_b200.engine.build` - there is no CPU fallback for the ELBO "
                     "path")
+        if _build.STAMP_PATH.exists() and _build.CSRC_DIR.exists() and not _build.is_current():
+            raise RuntimeError(
+                f"{_build.LIB_PATH} was built from different sources than mininf_b200/csrc holds now; "
+                "rebuild it with `python -m mininf_b200.engine.build`")
         _LIBRARY = Library(_build.LIB_PATH)
     return _LIBRARY

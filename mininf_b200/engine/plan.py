@@ -8,7 +8,6 @@ count) and then only enqueues kernels: ``mnf_rsample`` -> sweeps over the observ
 from __future__ import annotations
 
 import ctypes as C
-import os
 import dataclasses
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -95,8 +94,12 @@ class Plan:
 
     def __init__(self, sites: Sequence[SiteRecord], latents: Sequence[LatentSpec],
                  n_particles: int, device: torch.device, dense_mode: str = "auto",
-                 dry_run: bool = False) -> None:
-        """``dry_run`` lowers the site table without touching the GPU (host-logic tests)."""
+                 dry_run: bool = False, closed_form: bool = False) -> None:
+        """``dry_run`` lowers the site table without touching the GPU (host-logic tests).
+        ``closed_form`` lets sites whose log-density is a closed form of data-only sufficient
+        statistics skip the per-(particle, observation) evaluation (Gram statistics of a Normal
+        dense site with p <= 64, six sums / Chebyshev moments of scalar-link Normal / Poisson
+        sites); off, every site is swept once per particle and observation."""
         if device.type != "cuda" and not dry_run:
             raise RuntimeError("the mininf_b200 ELBO engine runs on CUDA tensors only; move the "
                                "approximation parameters and the conditioned data to the GPU")
@@ -111,13 +114,16 @@ class Plan:
         if self.S < 1 or self.D < 1:
             raise ValueError("need at least one particle and one latent element")
         self.dense_mode = dense_mode
+        self.closed_form = bool(closed_form)
         self.keepalive: List[torch.Tensor] = []
         self.all_normal = all(spec.family == abi.NORMAL for spec in self.latents)
 
         S, D = self.S, self.D
         f32 = dict(device=device, dtype=torch.float32)
-        self.P0 = torch.zeros(D, **f32)
-        self.P1 = torch.ones(D, **f32)
+        # constrained parameters of the packed latents, [p0 columns | p1 columns] in one buffer
+        # (the fused SVI step writes transform(raw) here, include/mininf_b200.h::mnf_adam_t)
+        self.P = torch.cat([torch.zeros(D, **f32), torch.ones(D, **f32)])
+        self.P0, self.P1 = self.P[:D], self.P[D:]
         self.z = torch.empty(S, D, **f32)
         self.noise = torch.empty(S, D, **f32)
         self.noise_in = torch.empty(S, D, **f32)
@@ -125,21 +131,20 @@ class Plan:
         self.status = torch.zeros(1, device=device, dtype=torch.int32)
         self.step_counter = torch.zeros(1, device=device, dtype=torch.int64)   # graph replays (see step)
         self.out = torch.empty(1 + 2 * D, **f32)
-        if dry_run:
-            self.workspace_bytes = 0
-            self.workspace = torch.empty(0, device=device, dtype=torch.uint8)
-        else:
-            with torch.cuda.device(device):
-                widest = max([D] + [spec.numel // spec.shape[0] + 3 for spec in self.row_latents])
-                self.workspace_bytes = max(self.lib.workspace_bytes(S, widest), 1 << 20)
-            self.workspace = torch.empty(self.workspace_bytes, device=device, dtype=torch.uint8)
+        self.dry_run = dry_run
+        self.workspace_bytes = 0
+        self.workspace = torch.empty(0, device=device, dtype=torch.uint8)
 
         table = (abi.Latent * len(self.latents))()
         for i, spec in enumerate(self.latents):
             table[i] = abi.Latent(family=spec.family, numel=spec.numel, offset=spec.offset, reserved=0,
                                   p0=self.P0.data_ptr() + 4 * spec.offset,
                                   p1=self.P1.data_ptr() + 4 * spec.offset)
+        self._latent_host = table
         self.latent_table = _bytes_to_device(table, device)
+        self.handle: Optional[C.c_void_p] = None      # mnf_plan_t*, created after lowering
+        self.xrank: Optional[Any] = None              # peer-memory exchange (sharded evaluations)
+        self.launches_last_step = 0
 
         # optional instrumentation: CUDA event pairs around every dense sweep (bench.py roofline)
         self.record_sweep_events = False
@@ -180,17 +185,71 @@ class Plan:
         for name, desc in self.row_groups.items():
             if not desc._has_prior:
                 raise NotImplementedError(f"row latent '{name}' has no prior site in the model")
+        self._small_observed_host = small_observed
+        self._small_global_host = small_global
+        self._create_native()
+
+    # ------------------------------------------------------------------------------------------
+    # the native plan (include/mininf_b200.h::mnf_plan_create): one C call per step
+    # ------------------------------------------------------------------------------------------
+    def _describe(self) -> abi.PlanDesc:
+        """The flat tables as one ``mnf_plan_desc_t`` (host arrays are kept alive on ``self``)."""
+        dense = (abi.DenseSite * max(len(self.dense_sites), 1))(*[site for site, _ in self.dense_sites])
+        modes = (C.c_int32 * max(len(self.dense_sites), 1))(*[mode for _, mode in self.dense_sites])
+        grouped = [group[i] for group in self.sweep_groups for i in range(len(group))]
+        group_sites = (abi.Site * max(len(grouped), 1))(*grouped)
+        group_sizes = (C.c_int32 * max(len(self.sweep_groups), 1))(*[len(group) for group in self.sweep_groups])
+        observed = self.small_observed[3] if self.small_observed is not None else (abi.Site * 1)()
+        priors = self.small_global[3] if self.small_global is not None else (abi.Site * 1)()
+        rows = (abi.RowLatent * max(len(self.row_groups), 1))(*self.row_groups.values())
+        self._desc_arrays = (dense, modes, group_sites, group_sizes, observed, priors, rows)
+        return abi.PlanDesc(
+            n_particles=self.S, n_latent_total=self.D, n_latents=len(self.latents),
+            n_dense=len(self.dense_sites), n_groups=len(self.sweep_groups),
+            n_small_observed=self.small_observed[1] if self.small_observed is not None else 0,
+            n_small_global=self.small_global[1] if self.small_global is not None else 0,
+            n_rowlatent=len(self.row_groups), latents=self._latent_host, dense=dense, dense_mode=modes,
+            group_sites=group_sites, group_sizes=group_sizes, small_observed=observed, small_global=priors,
+            rowlatent=rows, flags=abi.SWEEP_CLOSED_FORM if self.closed_form else 0, device=-1)
+
+    def _create_native(self) -> None:
+        if not self.dry_run:
+            with torch.cuda.device(self.device):
+                handle = C.c_void_p()
+                desc = self._describe()
+                self.lib.call("mnf_plan_create", C.byref(desc), C.byref(handle))
+                self.handle = handle
+                size = C.c_size_t()
+                self.lib.call("mnf_plan_workspace_bytes", handle, C.byref(size))
+            self.workspace_bytes = int(size.value)
+            self.workspace = torch.empty(self.workspace_bytes, device=self.device, dtype=torch.uint8)
+        self._row_buffers = (abi.RowBuffers * max(len(self.row_groups), 1))()
+        self.buffers = abi.Buffers(
+            z=self.z.data_ptr(), noise=self.noise.data_ptr(), acc=self.acc.data_ptr(), out=self.out.data_ptr(),
+            workspace=self.workspace.data_ptr(), workspace_bytes=self.workspace_bytes,
+            status=self.status.data_ptr(), noise_in=None, step_counter=None, rows=self._row_buffers, xrank=None)
+
+    def __del__(self) -> None:
+        try:
+            if getattr(self, "handle", None):
+                self.lib.raw("mnf_plan_destroy")(self.handle)
+                self.handle = None
+            if getattr(self, "xrank", None):
+                self.lib.raw("mnf_xrank_destroy")(self.xrank)
+                self.xrank = None
+        except Exception:  # noqa: BLE001  interpreter shutdown
+            pass
 
     # ------------------------------------------------------------------------------------------
     # lowering
     # ------------------------------------------------------------------------------------------
-    def _site_table(self, sites: List[abi.Site]) -> Optional[Tuple[torch.Tensor, int, int]]:
+    def _site_table(self, sites: List[abi.Site]) -> Optional[Tuple[torch.Tensor, int, int, Any]]:
         if not sites:
             return None
         array = (abi.Site * len(sites))(*sites)
         table = _bytes_to_device(array, self.device)
         self._host_tables.append((array, table))
-        return table, len(sites), max(s.numel for s in sites)
+        return table, len(sites), max(s.numel for s in sites), array
 
     def _latent_column(self, ref: LatentRef, numel: int, what: str) -> Tuple[int, int]:
         """(column, stride) of a latent reference inside a site of ``numel`` elements."""
@@ -423,13 +482,16 @@ class Plan:
                              theta_lat=theta.offset, icpt_lat=icpt_lat, icpt_const=expr.icpt_const,
                              reserved=0, scale=scale_link, weight=float(record.scale))
         has_icpt = icpt_lat >= 0 or expr.icpt_const != 0.0
-        tf32_ok = self.lib.raw("mnf_dense_tf32_kernel")(dense_family, p, self.S) != 0 and X.data_ptr() % 16 == 0 and \
-            X.stride(0) % 4 == 0 and n < 2 ** 31
+        kernel = self.lib.raw("mnf_dense_tf32_kernel")(dense_family, p, self.S)
+        if kernel == 3 and not self.closed_form:
+            kernel = 0          # only the Gram closed form covers this shape
+        tf32_ok = kernel != 0 and X.data_ptr() % 16 == 0 and X.stride(0) % 4 == 0 and n < 2 ** 31
         if self.dense_mode == "tf32" and not tf32_ok:
             raise NotImplementedError(f"{what}: the tcgen05 TF32 kernels need p == 64 with at most 64 "
                                       "particles, or p a multiple of 4 with at most 128 particles, "
                                       "and 16-byte aligned rows")
-        mode = abi.DENSE_TF32 if (self.dense_mode in ("auto", "tf32") and tf32_ok) else abi.DENSE_FP32
+        tf32 = abi.DENSE_TF32_CLOSED_FORM if self.closed_form else abi.DENSE_TF32
+        mode = tf32 if (self.dense_mode in ("auto", "tf32") and tf32_ok) else abi.DENSE_FP32
         self.dense_sites.append((site, mode))
 
     # ------------------------------------------------------------------------------------------
@@ -510,7 +572,7 @@ class Plan:
 
         # the tcgen05 kernels need 16-byte aligned rows; check before anything is modified
         for site, mode in self.dense_sites:
-            if mode == abi.DENSE_TF32 and translate(site.X) % 16:
+            if mode != abi.DENSE_FP32 and translate(site.X) % 16:
                 return False
         before = [bytes(array) for array, _ in self._host_tables]
         for struct in self._host_structs():
@@ -519,6 +581,10 @@ class Plan:
             if bytes(array) != old_bytes:       # tables of latent-valued sites hold no data pointers
                 table.copy_(torch.frombuffer(bytearray(bytes(array)), dtype=torch.uint8))
         self._sources = new
+        if self.handle:
+            desc = self._describe()
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            self.lib.call("mnf_plan_update", self.handle, C.byref(desc), stream)
         return True
 
     # ------------------------------------------------------------------------------------------
@@ -526,25 +592,33 @@ class Plan:
     # ------------------------------------------------------------------------------------------
     @property
     def gpu_launches_per_step(self) -> int:
-        """Kernels of this library launched by one :meth:`step` (sweeps come with a reduction)."""
-        count = 2  # rsample + finalize
-        for site, mode in self.dense_sites:
-            # the wide tcgen05 kernel takes at most 32 particles per sweep (csrc/abi.cu::tcr_shape)
-            kernel = self.lib.raw("mnf_dense_tf32_kernel")(site.family, site.p, self.S) if mode == abi.DENSE_TF32 else 0
-            if kernel != 0 and site.p <= 64 and site.family == abi.NORMAL and \
-                    os.environ.get("MNF_DENSE_NO_GRAM", "0") in ("", "0"):
-                count += 4      # Gram statistics, their fp64 totals, closed forms per particle, reduction
-            else:
-                count += 2 * (-(-self.S // 32) if kernel == 2 else 1)
-        for group in self.sweep_groups:
-            # sites with a specialised kernel run on their own (csrc/site_sweep.cuh::site_fast_kind)
-            fast = sum(1 for i in range(len(group)) if _has_fast_sweep(group[i]))
-            count += 2 * fast + (2 if fast < len(group) else 0)
-            # range + moment + finish kernels in front of the (skipped) per-particle kernel
-            count += 3 * sum(1 for i in range(len(group)) if _has_moment_path(group[i]))
-        count += sum(1 + -(-self.S // 32) for _ in self.row_groups)
-        count += (self.small_observed is not None) + (self.small_global is not None)
-        return count
+        """Kernels of this library the most recent :meth:`step` enqueued (counted by the library
+        itself, include/mininf_b200.h::mnf_plan_launches)."""
+        return self.launches_last_step
+
+    def enable_peer_exchange(self, group: Any = None) -> None:
+        """Sharded evaluations: every observed site is this rank's row shard, and the partial
+        [S][1+D] accumulators of all ranks are combined by the engine itself over peer memory
+        (``mnf_xrank_*``: push to every peer's inbox over NVLink, fixed-order sum in the tail
+        kernel) - no NCCL call on the step path, so a sharded step is CUDA-graph capturable. The
+        CUDA-IPC handles are exchanged once, here, through ``torch.distributed``."""
+        import torch.distributed as dist
+        if self.xrank is not None:
+            return
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world < 2:
+            return
+        with torch.cuda.device(self.device):
+            handle = C.c_void_p()
+            mine = C.create_string_buffer(abi.XRANK_HANDLE_BYTES)
+            self.lib.call("mnf_xrank_create", world, rank, self.S * (self.D + 1), C.byref(handle), mine)
+            gathered: List[Any] = [None] * world
+            dist.all_gather_object(gathered, bytes(mine.raw), group=group)
+            everyone = C.create_string_buffer(b"".join(gathered), world * abi.XRANK_HANDLE_BYTES)
+            self.lib.call("mnf_xrank_connect", handle, everyone)
+            dist.barrier(group)          # every rank has mapped every inbox before the first push
+        self.xrank = handle
+        self.buffers.xrank = handle
 
     def step(self, noise: Optional[torch.Tensor], seed: int, offset: int, with_entropy: bool = True,
              reduce_fn: Optional[Callable[[torch.Tensor], None]] = None,
@@ -553,23 +627,56 @@ class Plan:
         (loss, d loss / d p0, d loss / d p1). Parameters must already be in ``P0`` / ``P1``.
         ``device_counter``: the Philox call index is ``offset`` plus a device-resident counter that
         the last kernel of the step increments - for steps recorded into a CUDA graph, whose
-        arguments are frozen at capture time."""
+        arguments are frozen at capture time. ``reduce_fn`` (e.g. an NCCL all-reduce) combines the
+        accumulators of row-sharded ranks between the two halves of the step; with
+        :meth:`enable_peer_exchange` the engine does that itself and the step is a single call."""
         lib, S, D = self.lib, self.S, self.D
-        counter = self.step_counter.data_ptr() if device_counter else None
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        status = self.status.data_ptr()
-        noise_ptr = None
+        stream = 0 if self.dry_run else torch.cuda.current_stream(self.device).cuda_stream
+        buffers = self.buffers
+        buffers.step_counter = self.step_counter.data_ptr() if device_counter else None
+        buffers.noise_in = None
         if noise is not None:
             self.noise_in.copy_(noise.reshape(S, D))
-            noise_ptr = self.noise_in.data_ptr()
-        lib.call("mnf_rsample", self.latent_table.data_ptr(), len(self.latents), S, D, noise_ptr,
+            buffers.noise_in = self.noise_in.data_ptr()
+        for i, desc in enumerate(self.row_groups.values()):
+            row = self._row_buffers[i]
+            row.loc, row.scale, row.grad_loc, row.grad_scale, row.eps = \
+                desc.loc, desc.scale, desc.grad_loc, desc.grad_scale, desc.eps
+        flags = abi.STEP_ENTROPY if with_entropy else 0
+        if self.record_sweep_events:
+            # instrumented: the observed-site half through the phase-level entry points with CUDA
+            # events around every sweep call (bench.py's roofline numerator), then the second half
+            self._step_phases(seed, offset, with_entropy, stream)
+            if reduce_fn is not None:
+                reduce_fn(self.acc)
+            lib.call("mnf_elbo_fwd_bwd", self.handle, C.byref(buffers), seed, offset, flags | abi.STEP_POST, stream)
+        elif reduce_fn is not None:
+            lib.call("mnf_elbo_fwd_bwd", self.handle, C.byref(buffers), seed, offset, flags | abi.STEP_PRE, stream)
+            launched = self._launches()
+            reduce_fn(self.acc)   # observed sites are row shards: sum the partial accumulators
+            lib.call("mnf_elbo_fwd_bwd", self.handle, C.byref(buffers), seed, offset, flags | abi.STEP_POST, stream)
+            self.launches_last_step = launched + self._launches()
+            return self.out
+        else:
+            lib.call("mnf_elbo_fwd_bwd", self.handle, C.byref(buffers), seed, offset, flags | abi.STEP_ALL, stream)
+        self.launches_last_step = self._launches()
+        return self.out
+
+    def _launches(self) -> int:
+        count = C.c_int()
+        self.lib.call("mnf_plan_launches", self.handle, C.byref(count))
+        return int(count.value)
+
+    def _step_phases(self, seed: int, offset: int, with_entropy: bool, stream: int) -> None:
+        """rsample and every sweep over observed sites through the phase-level C-ABI."""
+        lib, S, D = self.lib, self.S, self.D
+        counter = self.buffers.step_counter
+        status = self.status.data_ptr()
+        lib.call("mnf_rsample", self.latent_table.data_ptr(), len(self.latents), S, D, self.buffers.noise_in,
                  seed, offset, counter, self.z.data_ptr(), self.noise.data_ptr(), self.acc.data_ptr(),
                  status, stream)
+
         def timed(kind: str, call: Callable[[], None]) -> None:
-            """CUDA events around one sweep call on its stream (bench.py's roofline numerator)."""
-            if not self.record_sweep_events:
-                call()
-                return
             begin, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             begin.record(torch.cuda.current_stream(self.device))
             call()
@@ -584,9 +691,10 @@ class Plan:
         for group in self.sweep_groups:
             timed("site", lambda: lib.call(
                 "mnf_site_sweep", group, len(group), self.z.data_ptr(), S, D, self.acc.data_ptr(),
-                self.workspace.data_ptr(), self.workspace_bytes, status, stream))
+                self.workspace.data_ptr(), self.workspace_bytes,
+                abi.SWEEP_CLOSED_FORM if self.closed_form else 0, status, stream))
         if self.small_observed is not None:
-            table, count, longest = self.small_observed
+            table, count, longest, _ = self.small_observed
             lib.call("mnf_small_sites", table.data_ptr(), count, longest, self.z.data_ptr(), S, D,
                      self.acc.data_ptr(), status, stream)
         for name, desc in self.row_groups.items():
@@ -594,16 +702,6 @@ class Plan:
                 "mnf_rowlatent_sweep", C.byref(desc), self.z.data_ptr(), S, D, seed, offset, counter,
                 int(with_entropy), self.acc.data_ptr(), self.workspace.data_ptr(), self.workspace_bytes,
                 status, stream))
-        if reduce_fn is not None:
-            reduce_fn(self.acc)   # observed sites are row shards: sum the partial accumulators
-        if self.small_global is not None:
-            table, count, longest = self.small_global
-            lib.call("mnf_small_sites", table.data_ptr(), count, longest, self.z.data_ptr(), S, D,
-                     self.acc.data_ptr(), status, stream)
-        lib.call("mnf_finalize", self.latent_table.data_ptr(), len(self.latents), S, D,
-                 self.z.data_ptr(), self.noise.data_ptr(), self.acc.data_ptr(), int(with_entropy),
-                 self.out.data_ptr(), counter, status, stream)
-        return self.out
 
 
 def status_message(bits: int) -> str:
@@ -614,4 +712,6 @@ def status_message(bits: int) -> str:
         parts.append("an observed value is not in the support of its distribution")
     if bits & abi.ST_NONFINITE:
         parts.append("the loss or a gradient is not finite")
+    if bits & abi.ST_XRANK_TIMEOUT:
+        parts.append("a peer rank did not deliver its partial sums in time (sharded evaluation)")
     return "; ".join(parts)

@@ -120,19 +120,59 @@ class LinkTensor(torch.Tensor):
     @classmethod
     def __torch_function__(cls, func, types, args=(), kwargs=None):  # type: ignore[override]
         kwargs = kwargs or {}
+        name = getattr(func, "__name__", "")
+        if name in _HOST_READS and any(isinstance(a, LinkTensor) and a.is_floating_point()
+                                       for a in _flatten_args(args)):
+            # float(z), z.item(), z.tolist(): the trace-time draw would be frozen into the plan as a
+            # constant and the site's dependence on the latent silently lost
+            raise NotImplementedError(
+                f"`{name}` reads the value of a latent-dependent tensor on the host; the model is "
+                "traced once, so the value would be baked into the plan as a constant")
         with torch._C.DisableTorchFunctionSubclass():
             raw = func(*args, **kwargs)
-        name = getattr(func, "__name__", "")
+        if _is_inplace(name) or kwargs.get("out") is not None:
+            # values were modified behind an existing expression: every tensor involved is opaque
+            for target in _flatten_args(args)[:1] + [kwargs.get("out")]:
+                if isinstance(target, LinkTensor):
+                    target._expr = None
+            return _wrap_opaque(raw)
         rule = _RULES.get(name)
         if isinstance(raw, (tuple, list)):
             if name == "broadcast_tensors":
                 return type(raw)(_rewrap(r, _shape_rule(a, r)) if isinstance(a, LinkTensor)
                                  else _strip(r) for a, r in zip(_flatten_args(args), raw))
-            return type(raw)(_strip(r) for r in raw)
+            if name == "unbind":
+                return type(raw)(_rule_unbind(args, kwargs, raw))
+            # split / chunk / max(dim) / ...: pieces of a latent-dependent tensor stay marked (opaque),
+            # so a site that uses one raises instead of freezing the trace-time draw
+            return _retuple(raw, [_wrap_opaque(r) for r in raw])
         if not isinstance(raw, torch.Tensor) or not raw.is_floating_point():
             return _strip(raw)
         expr = rule(args, kwargs, raw) if rule is not None else None
         return _rewrap(raw, expr)
+
+
+_HOST_READS = {"item", "__float__", "__int__", "__index__", "__complex__", "tolist", "numpy", "__array__"}
+
+
+def _is_inplace(name: str) -> bool:
+    return (name.endswith("_") and not name.endswith("__")) or (name.startswith("__i") and name.endswith("__")
+                                                                   and name not in ("__iter__", "__index__",
+                                                                                    "__int__", "__invert__"))
+
+
+def _wrap_opaque(value: Any) -> Any:
+    """Floating tensors derived from a LinkTensor without a rule: opaque, but still marked."""
+    if isinstance(value, torch.Tensor) and value.is_floating_point():
+        return _rewrap(value, None)
+    return _strip(value)
+
+
+def _retuple(raw: Any, items: List[Any]) -> Any:
+    try:
+        return type(raw)(items)
+    except TypeError:          # structseq / namedtuple variants that want positional fields
+        return tuple(items)
 
 
 def _strip(value: Any) -> Any:
@@ -310,6 +350,24 @@ def _rule_getitem(args, kwargs, raw):
     for i, size in zip(index, source.shape):
         flat = flat * size + (i % size)
     return Affine(a_lat=LatentRef(expr.a_lat.name, flat))
+
+
+def _rule_unbind(args, kwargs, raw):
+    """Pieces of `unbind` (and of `Tensor.__iter__`, which calls it): the elements of a 1-D
+    element-wise latent are scalar references; anything else is opaque."""
+    source = args[0]
+    expr = _expr_of(source)
+    scalar_pieces = isinstance(expr, Affine) and expr.is_pure_latent and not expr.a_lat.is_scalar and \
+        source.ndim == 1
+    out = []
+    for i, piece in enumerate(raw):
+        if not (isinstance(piece, torch.Tensor) and piece.is_floating_point()):
+            out.append(_strip(piece))
+        elif scalar_pieces:
+            out.append(_rewrap(piece, Affine(a_lat=LatentRef(expr.a_lat.name, i))))
+        else:
+            out.append(_rewrap(piece, None))
+    return out
 
 
 def _rule_select(args, kwargs, raw):

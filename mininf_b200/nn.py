@@ -113,6 +113,19 @@ def _unwrap_conditioning(model: Callable) -> Tuple[Callable, List[Tuple[str, Any
     return model, pinned
 
 
+def _callable_key(model: Callable) -> Tuple:
+    """Identity of a model callable that survives re-creation of thin wrappers: a bound method
+    (``obj.model``) is a new object on every attribute access and a ``functools.partial`` is often
+    rebuilt per step, so keying the plan cache on ``id(model)`` would retrace every step."""
+    import functools
+    if isinstance(model, functools.partial):
+        frozen = tuple(id(a) for a in model.args) + tuple((k, id(v)) for k, v in sorted(model.keywords.items()))
+        return ("partial", _callable_key(model.func), frozen)
+    if hasattr(model, "__func__") and hasattr(model, "__self__"):
+        return ("method", id(model.__func__), id(model.__self__))
+    return ("callable", id(model))
+
+
 def _layout_key(value: Any) -> Tuple:
     """What a plan depends on structurally: the layout of a conditioned value, not its address."""
     if isinstance(value, torch.masked.MaskedTensor):
@@ -196,23 +209,40 @@ class EvidenceLowerBoundLoss(nn.Module):
         cache: reuse the traced plan while the model, conditioned tensors and approximation
             structure are unchanged (the reference re-runs the model every step).
         process_group: ``True`` / a ``torch.distributed`` group to treat every observed site as
-            this rank's row shard and all-reduce the partial sums (one collective per step).
+            this rank's row shard and combine the partial sums of all ranks once per step.
+        reduce: how sharded ranks combine their partial sums. ``"peer"`` (default): the engine
+            pushes its [S][1+D] accumulator into every peer's inbox over NVLink and each rank adds
+            the inboxes in rank order inside the step's last kernel - no NCCL call, bit-identical
+            totals on every rank, CUDA-graph capturable. ``"nccl"``: one ``all_reduce`` between
+            the two halves of the step. Every rank must evaluate the same sequence of losses; the
+            Philox seed is taken from rank 0 when the exchange is set up.
+        closed_form: let sites whose log-density is a closed form of data-only sufficient
+            statistics skip the per-(particle, observation) sweep (Gram statistics of a Normal
+            dense site with p <= 64; six sums / Chebyshev moments for scalar-link Normal / Poisson
+            sites). Off (default), every site is evaluated once per particle and observation -
+            the black-box estimator the reference implements.
         check: ``"lazy"`` validates the device status word of the previous step at the next call
             (no extra synchronisation), ``"sync"`` synchronises every call, ``"off"`` never.
     """
 
     def __init__(self, n_particles: int = 1, *, dense_precision: str = "auto", cache: bool = True,
-                 process_group: Any = None, check: str = "lazy") -> None:
+                 process_group: Any = None, check: str = "lazy", closed_form: bool = False,
+                 reduce: str = "peer") -> None:
         super().__init__()
         if dense_precision not in ("auto", "tf32", "fp32"):
             raise ValueError("dense_precision must be 'auto', 'tf32' or 'fp32'")
         if check not in ("lazy", "sync", "off"):
             raise ValueError("check must be 'lazy', 'sync' or 'off'")
+        if reduce not in ("peer", "nccl"):
+            raise ValueError("reduce must be 'peer' or 'nccl'")
         self.n_particles = int(n_particles)
         self.dense_precision = dense_precision
         self.cache = cache
         self.process_group = process_group
         self.check = check
+        self.closed_form = bool(closed_form)
+        self.reduce = reduce
+        self._shared_seed: Optional[int] = None
         self._plans: Dict[Tuple, Any] = {}
         self._pending: List[Tuple[Any, torch.Tensor, torch.cuda.Event]] = []
         self._free_slots: List[torch.Tensor] = []
@@ -309,7 +339,7 @@ class EvidenceLowerBoundLoss(nn.Module):
         # latent draws the model never scores still take part in the entropy term; that mirrors
         # the reference, where `condition` silently accepts unused names
         return Plan(tracer.sites, assign_offsets(entries), self.n_particles, device,
-                    dense_mode=self.dense_precision)
+                    dense_mode=self.dense_precision, closed_form=self.closed_form)
 
     def _plan_for(self, model: Callable, approximation: DistributionDict) -> Any:
         """Cached plan for this model, data layout and approximation structure. The same tensors
@@ -321,10 +351,10 @@ class EvidenceLowerBoundLoss(nn.Module):
         base, pinned = _unwrap_conditioning(model)
         values = [val for _, val in pinned]
         leaves = _leaves(values)
-        key = (id(base), tuple((name, _layout_key(val)) for name, val in pinned),
+        key = (_callable_key(base), tuple((name, _layout_key(val)) for name, val in pinned),
                tuple((name, type(factor).__name__, tuple(factor.batch_shape))
                      for name, factor in approximation.items()),
-               self.n_particles, self.dense_precision)
+               self.n_particles, self.dense_precision, self.closed_form)
         bound = tuple((leaf.data_ptr(), leaf._version) for leaf in leaves)
         plan = self._plans.get(key)
         if plan is not None:
@@ -393,7 +423,24 @@ class EvidenceLowerBoundLoss(nn.Module):
         if self.process_group is not None:
             import torch.distributed as dist
             group = None if self.process_group is True else self.process_group
-            reduce_fn = lambda acc: dist.all_reduce(acc, group=group)  # noqa: E731
+            if self._shared_seed is None:
+                # every rank must draw the same z: the partial sums of all ranks are added, and the
+                # priors / entropy / optimiser update are computed redundantly on every rank. Rank
+                # 0's generator seed and call count become everyone's (once, outside any capture).
+                if capturing:
+                    raise RuntimeError("evaluate a sharded loss once eagerly before capturing it in a CUDA graph")
+                shared = [int(seed), self._calls]
+                dist.broadcast_object_list(shared, src=dist.get_global_rank(group, 0) if group is not None else 0,
+                                           group=group)
+                self._shared_seed, self._calls = int(shared[0]), int(shared[1])
+            seed = self._shared_seed
+            if self.reduce == "peer":
+                if plan.xrank is None:
+                    if capturing:
+                        raise RuntimeError("evaluate a sharded loss once eagerly before capturing it in a CUDA graph")
+                    plan.enable_peer_exchange(group)
+            else:
+                reduce_fn = lambda acc: dist.all_reduce(acc, group=group)  # noqa: E731
         offset = self._calls + (1 << 40 if capturing else 0)    # replays count on from here on the device
         return _EngineFunction.apply(self, plan, noise, row_noise, int(seed) & (2 ** 63 - 1), offset,
                                      reduce_fn, bool(_with_entropy), capturing, *params)
@@ -409,7 +456,9 @@ class GraphedStep:
     Conditioned tensors are read in place on every replay: refill them with ``copy_`` to feed the
     next minibatch. Every replay draws fresh Philox noise (the call index lives on the device).
     ``loss`` holds the value of the most recent replay; ``loss_module.synchronize()`` reports
-    invalid values flagged by the kernels.
+    invalid values flagged by the kernels. A sharded loss (``process_group=...``, peer exchange)
+    is capturable too: evaluate it once eagerly first (the warm-up steps here do).
+    :class:`FusedSVIStep` is the fully native variant (transforms and Adam inside the engine).
     """
 
     def __init__(self, loss_module: "EvidenceLowerBoundLoss", model: Callable, approximation: Callable[[], Any],
@@ -450,6 +499,138 @@ class GraphedStep:
     def __call__(self) -> torch.Tensor:
         self.graph.replay()
         return self.loss
+
+
+_PARAMETER_NAMES = {distributions.Normal: ("loc", "scale"), distributions.Gamma: ("concentration", "rate"),
+                    distributions.Beta: ("concentration1", "concentration0")}
+
+
+class FusedSVIStep:
+    """The whole SVI step of README.md:63-69 - ``zero_grad``, loss, ``backward``,
+    ``optimizer.step()`` - as ONE native call (``mnf_svi_step``, include/mininf_b200.h) that
+    enqueues 4-6 kernels: parameter transforms + reparameterised draws, the sweeps over the
+    observed sites, [the peer exchange of a sharded run], and a single tail kernel with the prior
+    sites, the entropy, the pathwise gradients, the chain rule through
+    ``ParameterizedDistribution``'s transforms (mininf/nn.py:88-96) and Adam
+    (``torch.optim.Adam`` semantics: no weight decay, no amsgrad). With ``graph=True`` the call is
+    recorded once into a CUDA graph and replayed.
+
+    ``approximation`` maps latent names to :class:`ParameterizedDistribution` modules (or is a
+    :class:`ParameterizedFactorizedDistribution`). Their ``nn.Parameter`` objects are re-pointed at
+    views of one packed buffer that the kernels update in place, so the modules keep working as
+    usual (``module()``, ``state_dict()``). Supported: Normal / Gamma / Beta factors whose
+    parameters are real (identity transform) or positive (exp transform); per-observation
+    ("row") latents are not part of the fused step.
+    """
+
+    def __init__(self, loss_module: "EvidenceLowerBoundLoss", model: Callable,
+                 approximation: Dict[str, ParameterizedDistribution] | ParameterizedFactorizedDistribution,
+                 lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 graph: bool = True, share_with: Optional["FusedSVIStep"] = None) -> None:
+        """``share_with``: another step over the same approximation whose parameters and Adam state
+        this one updates too - one step object per resident minibatch buffer (conditioned tensors
+        are baked into a recorded step by address), all training the same parameters."""
+        import ctypes as C
+        from .engine import abi
+        self._C, self._abi = C, abi
+        self.loss_module, self.model = loss_module, model
+        self.modules: Dict[str, ParameterizedDistribution] = dict(approximation.items())
+        with torch.no_grad():
+            factors = {name: module() for name, module in self.modules.items()}
+        # one eager evaluation builds the plan (and, for a sharded loss, the peer exchange)
+        loss_module(model, factors)
+        loss_module.synchronize()
+        plan = self.plan = loss_module.last_plan
+        if plan.row_latents:
+            raise NotImplementedError("FusedSVIStep does not cover per-observation latents; use "
+                                      "GraphedStep with a torch optimizer for those models")
+        D, device = plan.D, plan.device
+        raw = torch.zeros(2 * D, device=device)
+        codes = torch.zeros(2 * D, dtype=torch.uint8)
+        if share_with is not None and share_with.raw.numel() != 2 * D:
+            raise ValueError("share_with: the two steps train different approximations")
+        for spec in (plan.latents if share_with is None else []):
+            module = self.modules[spec.name]
+            names = _PARAMETER_NAMES.get(module.distribution_cls)
+            if names is None:
+                raise NotImplementedError(f"FusedSVIStep: unsupported approximation family for '{spec.name}'")
+            for half, name in enumerate(names):
+                lo = half * D + spec.offset
+                hi = lo + spec.numel
+                if name in module.distribution_parameters:
+                    parameter = module.distribution_parameters[name]
+                    transform = distributions.transform_to(module.distribution_cls.arg_constraints[name])
+                    if _is_identity_transform(transform):
+                        code = abi.T_ID
+                    elif isinstance(transform, distributions.ExpTransform):
+                        code = abi.T_EXP
+                    else:
+                        raise NotImplementedError(f"FusedSVIStep: transform {transform} of '{spec.name}.{name}'")
+                    if parameter.numel() != spec.numel:
+                        raise NotImplementedError(f"FusedSVIStep: '{spec.name}.{name}' is broadcast over the site; "
+                                                  "give it the site's shape")
+                    raw[lo:hi].copy_(parameter.detach().reshape(-1))
+                    # the packed buffer becomes the parameter's storage: in-place kernel updates are
+                    # visible through the module
+                    parameter.data = raw[lo:hi].view(parameter.shape)
+                    codes[lo:hi] = code
+                else:
+                    constant = torch.as_tensor(module.distribution_constants[name], dtype=torch.float32)
+                    raw[lo:hi].copy_(constant.to(device).expand(spec.shape if len(spec.shape) else (1,)).reshape(-1))
+                    codes[lo:hi] = abi.T_ID | abi.T_FROZEN
+        if share_with is None:
+            self.raw, self.codes = raw, codes.to(device)
+            self.m, self.v = torch.zeros_like(raw), torch.zeros_like(raw)
+            self.steps = torch.zeros(1, dtype=torch.int64, device=device)
+        else:
+            self.raw, self.codes, self.m, self.v, self.steps = \
+                share_with.raw, share_with.codes, share_with.m, share_with.v, share_with.steps
+        raw = self.raw
+        self.adam = abi.Adam(lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, raw=raw.data_ptr(),
+                             transform=self.codes.data_ptr(), m=self.m.data_ptr(), v=self.v.data_ptr(),
+                             constrained=plan.P.data_ptr(), step=self.steps.data_ptr())
+        self.loss = plan.out[0]
+        generator = torch.cuda.default_generators[device.index or 0]
+        self._seed = (loss_module._shared_seed if loss_module._shared_seed is not None
+                      else generator.initial_seed()) & (2 ** 63 - 1)
+        FusedSVIStep._instances += 1       # every step object draws from its own Philox call range
+        self._offset = (1 << 41) + (FusedSVIStep._instances << 34) + loss_module._calls
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        if graph:
+            side = torch.cuda.Stream(device)
+            side.wait_stream(torch.cuda.current_stream(device))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self._enqueue()
+            torch.cuda.current_stream(device).wait_stream(side)
+            torch.cuda.synchronize(device)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._enqueue()
+        loss_module._graphed_plans[id(plan)] = plan       # status word is read by synchronize()
+
+    _instances = 0
+
+    def _enqueue(self) -> None:
+        plan, C = self.plan, self._C
+        stream = torch.cuda.current_stream(plan.device).cuda_stream
+        plan.buffers.noise_in = None                       # an eager loss call on the same plan resets these
+        plan.buffers.step_counter = plan.step_counter.data_ptr()
+        plan.lib.call("mnf_svi_step", plan.handle, C.byref(plan.buffers), C.byref(self.adam), self._seed,
+                      self._offset, self._abi.STEP_ENTROPY | self._abi.STEP_ALL, stream)
+        plan.launches_last_step = plan._launches()
+
+    def __call__(self) -> torch.Tensor:
+        """Run one step; returns the (device-resident) loss of the parameters BEFORE the update."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+        return self.loss
+
+    @property
+    def kernels_per_step(self) -> int:
+        return self.plan.launches_last_step
 
 
 class LogLikelihoodLoss(nn.Module):

@@ -91,6 +91,10 @@ class HostBatchStream:
     def __iter__(self) -> Iterator[Dict[str, torch.Tensor]]:
         ready: List[Optional[torch.cuda.Event]] = [None] * self.depth
         free: List[Optional[torch.cuda.Event]] = [None] * self.depth
+        # A new epoch (or a new iterator after an early `break`) refills slots whose last
+        # consumers - the asynchronous sweeps of the previous epoch - may still be running on the
+        # caller's stream: nothing of this epoch may be copied before they have finished.
+        self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
         for position in range(min(self.depth - 1, self.n_batches)):
             ready[position % self.depth] = self._enqueue(position, position % self.depth, None)
         for position in range(self.n_batches):

@@ -44,6 +44,12 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mnf_link_t), sizeof(mnf_latent_t), sizeof(mnf_site_t),
          sizeof(mnf_dense_site_t), sizeof(mnf_device_info_t), offsetof(mnf_site_t, param),
          offsetof(mnf_dense_site_t, scale), offsetof(mnf_dense_site_t, weight));
+  printf("%zu %zu %zu %zu %zu\\n", sizeof(mnf_rowlatent_t), offsetof(mnf_rowlatent_t, prior_loc),
+         offsetof(mnf_rowlatent_t, feat), offsetof(mnf_rowlatent_t, beta_lat), offsetof(mnf_rowlatent_t, resp_scale));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mnf_plan_desc_t), offsetof(mnf_plan_desc_t, latents),
+         offsetof(mnf_plan_desc_t, flags), sizeof(mnf_row_buffers_t), sizeof(mnf_buffers_t),
+         offsetof(mnf_buffers_t, workspace_bytes), offsetof(mnf_buffers_t, xrank), sizeof(mnf_adam_t),
+         offsetof(mnf_adam_t, raw));
   return 0;
 }''')
     binary = tmp_path / "sizes"
@@ -51,7 +57,12 @@ int main(void) {
     sizes = [int(v) for v in subprocess.run([str(binary)], capture_output=True, text=True, check=True).stdout.split()]
     assert sizes == [ctypes.sizeof(abi.Link), ctypes.sizeof(abi.Latent), ctypes.sizeof(abi.Site),
                      ctypes.sizeof(abi.DenseSite), ctypes.sizeof(abi.DeviceInfo), abi.Site.param.offset,
-                     abi.DenseSite.scale.offset, abi.DenseSite.weight.offset]
+                     abi.DenseSite.scale.offset, abi.DenseSite.weight.offset,
+                     ctypes.sizeof(abi.RowLatent), abi.RowLatent.prior_loc.offset, abi.RowLatent.feat.offset,
+                     abi.RowLatent.beta_lat.offset, abi.RowLatent.resp_scale.offset,
+                     ctypes.sizeof(abi.PlanDesc), abi.PlanDesc.latents.offset, abi.PlanDesc.flags.offset,
+                     ctypes.sizeof(abi.RowBuffers), ctypes.sizeof(abi.Buffers), abi.Buffers.workspace_bytes.offset,
+                     abi.Buffers.xrank.offset, ctypes.sizeof(abi.Adam), abi.Adam.raw.offset]
 
 
 def test_argument_errors_do_not_need_a_gpu(library):
@@ -60,7 +71,16 @@ def test_argument_errors_do_not_need_a_gpu(library):
     assert code == abi.E_INVALID
     assert b"mnf_finalize" in library.raw("mnf_last_error")()
     with pytest.raises(abi.NativeError, match="mnf_site_sweep"):
-        library.call("mnf_site_sweep", None, 1, None, 1, 1, None, None, 0, None, None)
+        library.call("mnf_site_sweep", None, 1, None, 1, 1, None, None, 0, 0, None, None)
+    # the one-call step API validates its tables before touching the device
+    handle = ctypes.c_void_p()
+    assert library.raw("mnf_plan_create")(None, ctypes.byref(handle)) == abi.E_INVALID
+    empty = abi.PlanDesc(n_particles=4, n_latent_total=2, n_latents=0)
+    assert library.raw("mnf_plan_create")(ctypes.byref(empty), ctypes.byref(handle)) == abi.E_INVALID
+    assert b"latent" in library.raw("mnf_last_error")()
+    assert library.raw("mnf_elbo_fwd_bwd")(None, None, 0, 0, 0, None) == abi.E_INVALID
+    assert library.raw("mnf_svi_step")(None, None, None, 0, 0, 0, None) == abi.E_INVALID
+    assert library.raw("mnf_xrank_create")(1, 0, 10, ctypes.byref(handle), None) == abi.E_INVALID
 
 
 def test_dense_kernel_query_is_host_only(library, monkeypatch):

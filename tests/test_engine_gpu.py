@@ -14,10 +14,11 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def engine_eval(config, noise, n_particles, precision="fp32", approx=None, leaves=None):
+def engine_eval(config, noise, n_particles, precision="fp32", approx=None, leaves=None, closed_form=False):
     if approx is None:
         approx, leaves = config.approximation(device=DEV)
-    loss_module = mininf.nn.EvidenceLowerBoundLoss(n_particles, dense_precision=precision, check="sync")
+    loss_module = mininf.nn.EvidenceLowerBoundLoss(n_particles, dense_precision=precision, check="sync",
+                                                   closed_form=closed_form)
     conditioned = mininf.condition(lambda: config.model(mininf), **config.data)
     loss = loss_module(conditioned, approx, _noise=noise)
     loss.backward()
@@ -29,12 +30,14 @@ def rel(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
+@pytest.mark.parametrize("closed_form", [False, True])
 @pytest.mark.parametrize("case", list(GOLDEN_CASES))
-def test_matches_reference_golden(case):
-    """fp32 mode against values produced by the unmodified reference (tests/golden)."""
+def test_matches_reference_golden(case, closed_form):
+    """fp32 mode against values produced by the unmodified reference (tests/golden): the default
+    per-(particle, observation) sweeps and the closed-form statistics paths."""
     config, golden = load_golden(case, device=DEV)
     S = int(golden["n_particles"])
-    loss, leaves, _ = engine_eval(config, golden_noise(config, golden, DEV), S)
+    loss, leaves, _ = engine_eval(config, golden_noise(config, golden, DEV), S, closed_form=closed_form)
     assert loss.ndim == 0 and loss.dtype == torch.float32
     assert abs(float(loss) - float(golden["loss"])) <= 1e-5 * abs(float(golden["loss"]))  # north-star tolerance
     for key, leaf in leaves.items():
@@ -100,8 +103,9 @@ def test_tf32_error_shrinks_with_rows():
     assert rel(leaves["theta.scale"].grad.cpu().numpy(), scale.grad.cpu().numpy()) < 2e-4
 
 
+@pytest.mark.parametrize("closed_form", [False, True])
 @pytest.mark.parametrize("n,S", [(1, 1), (31, 2), (2048, 64), (50_000, 17)])
-def test_missing_observations_against_oracle(n, S):
+def test_missing_observations_against_oracle(n, S, closed_form):
     """Masked Poisson + Normal sites sharing a covariate (small-site kernel below 2048 rows,
     fused site sweep from there on)."""
     torch.manual_seed(n)
@@ -111,7 +115,7 @@ def test_missing_observations_against_oracle(n, S):
     noise = {name: elbo.draw_noise(dist, S) for name, dist in approx_c.items()}
     expected = elbo.neg_elbo(cpu.model, cpu.data, approx_c, noise, S)
     expected.backward()
-    loss, leaves, module = engine_eval(gpu, {k: v.to(DEV) for k, v in noise.items()}, S)
+    loss, leaves, module = engine_eval(gpu, {k: v.to(DEV) for k, v in noise.items()}, S, closed_form=closed_form)
     assert (len(module.last_plan.sweep_groups) == 1) == (n >= 2048)
     assert abs(float(loss) - float(expected)) <= 1e-5 * abs(float(expected))
     for key, leaf in leaves.items():
@@ -348,6 +352,36 @@ def test_host_batch_stream_feeds_the_rebound_plan():
         assert all(plan is full_plans[0] for plan in full_plans)      # full batches share one rebound plan
 
 
+def test_host_batch_stream_epochs_do_not_overtake_their_consumers():
+    """Several asynchronous epochs over an odd number of batches (depth 2): the first copies of an
+    epoch reuse slots whose consumers - the previous epoch's last sweeps - may still be running;
+    nothing synchronises inside the loop, losses are compared at the end."""
+    from mininf_b200.stream import HostBatchStream
+    S, p, rows, total = 8, 256, 60_000, 3 * 60_000
+    full = configs.logistic(total, total, p=p, device="cpu")
+    host = {k: v for k, v in full.data.items()}
+    torch.manual_seed(6)
+    approx, _ = full.approximation(device=DEV)
+    noise = {name: elbo.draw_noise(dist, S).to(DEV) for name, dist in approx.items()}
+
+    def model():
+        return full.model(mininf)
+
+    reference = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+    expected = []
+    for lo in range(0, total, rows):
+        data = {k: v[lo:lo + rows].to(DEV) for k, v in host.items()}
+        expected.append(float(reference(mininf.condition(model, **data), approx, _noise=noise)))
+    feed = HostBatchStream(host, rows, device=DEV, depth=2)
+    module = mininf.nn.EvidenceLowerBoundLoss(S, check="lazy")
+    losses = []
+    for _ in range(4):
+        for batch in feed:
+            losses.append(module(mininf.condition(model, **batch), approx, _noise=noise).detach())
+    module.synchronize()
+    assert [float(value) for value in losses] == expected * 4
+
+
 def test_graphed_step_trains_like_the_eager_loop():
     """`GraphedStep` replays the whole SVI step from one CUDA graph: every replay draws new Philox
     noise (device-side call index), parameters move, and the fit matches the eager README loop."""
@@ -578,6 +612,81 @@ def test_full_size_tensor_core_kernel_agrees_with_exact_kernel():
     assert out.tolist() == [n, n]
 
 
+def _fp64_oracle(config, noise, S):
+    """float64 evaluation of the reference algorithm (oracle/elbo.py) on the CPU."""
+    data64 = {k: v.double().cpu() for k, v in config.data.items()}
+    approx64, leaves64 = config.approximation(dtype=torch.float64)
+    expected = elbo.neg_elbo(config.model, data64, approx64, {k: v.double().cpu() for k, v in noise.items()}, S,
+                             validate=False)
+    expected.backward()
+    return float(expected), {k: v.grad.numpy() for k, v in leaves64.items()}
+
+
+@pytest.mark.parametrize("rows", [200_000, 2_000_000])
+def test_c2_black_box_kernel_meets_the_north_star_tolerance_against_the_fp64_oracle(rows):
+    """BASELINE.json config[1] (p = 64, S = 64) through the per-(particle, observation) tcgen05
+    kernel (csrc/dense_tc.cuh, the default `closed_form=False` path) on seeded row subsamples of
+    the benchmark's data recipe, against a float64 evaluation of the reference algorithm: 1e-5
+    relative on the loss (the north-star tolerance), 1e-4 relative L2 on the gradients. The error
+    that is left is the unbiased TF32 rounding of X (it shrinks as 1/sqrt(N)); theta enters the
+    tensor core as hi + lo TF32 pairs, so nothing systematic per particle remains."""
+    S = 64
+    torch.manual_seed(rows)
+    config = configs.regression(rows, 64, device=DEV)          # chunk-seeded recipe, device generator
+    approx, leaves = config.approximation(device=DEV)
+    noise = {name: elbo.draw_noise(dist, S) for name, dist in config.approximation()[0].items()}
+    module = mininf.nn.EvidenceLowerBoundLoss(S, dense_precision="tf32", check="sync")
+    loss = module(mininf.condition(lambda: config.model(mininf), **config.data), approx,
+                  _noise={k: v.to(DEV) for k, v in noise.items()})
+    loss.backward()
+    (site, mode), = module.last_plan.dense_sites
+    assert mode == abi.DENSE_TF32 and abi.load().raw("mnf_dense_tf32_kernel")(site.family, site.p, S) == 1
+    expected, grads64 = _fp64_oracle(config, noise, S)
+    assert abs(float(loss) - expected) <= 1e-5 * abs(expected)
+    for key, leaf in leaves.items():
+        assert rel(leaf.grad.cpu().numpy(), grads64[key]) < 1e-4, key
+
+
+def test_c3_black_box_kernel_meets_the_north_star_tolerance_against_the_fp64_oracle():
+    """BASELINE.json config[2] shape (p = 256, S = 16, Bernoulli logits under `batch` scaling)
+    through the wide tcgen05 kernel (csrc/dense_tcr.cuh) on a seeded 500 000-row batch against the
+    float64 oracle: 1e-5 on the loss, 1e-4 on the gradients."""
+    S, rows = 16, 500_000
+    torch.manual_seed(3)
+    config = configs.logistic(1_000_000_000, rows, p=256, device=DEV)
+    approx, leaves = config.approximation(device=DEV)
+    noise = {name: elbo.draw_noise(dist, S) for name, dist in config.approximation()[0].items()}
+    module = mininf.nn.EvidenceLowerBoundLoss(S, dense_precision="tf32", check="sync")
+    loss = module(mininf.condition(lambda: config.model(mininf), **config.data), approx,
+                  _noise={k: v.to(DEV) for k, v in noise.items()})
+    loss.backward()
+    (site, mode), = module.last_plan.dense_sites
+    assert mode == abi.DENSE_TF32 and abi.load().raw("mnf_dense_tf32_kernel")(site.family, site.p, S) == 2
+    expected, grads64 = _fp64_oracle(config, noise, S)
+    assert abs(float(loss) - expected) <= 1e-5 * abs(expected)
+    for key, leaf in leaves.items():
+        assert rel(leaf.grad.cpu().numpy(), grads64[key]) < 1e-4, key
+
+
+def test_full_size_wide_kernel_agrees_with_exact_kernel():
+    """The C3 batch at full size (1e7 x 256, S = 16): TF32 tcgen05 kernel against the exact fp32
+    SIMT kernel, 1e-5 on the loss and 1e-4 on the gradients."""
+    S, rows = 16, 10_000_000
+    config = configs.logistic(1_000_000_000, rows, p=256, device=DEV)
+    noise = {"theta": torch.randn(S, 256, generator=torch.Generator().manual_seed(8)).to(DEV)}
+    results = {}
+    for precision in ("tf32", "fp32"):
+        approx, leaves = config.approximation(device=DEV)
+        module = mininf.nn.EvidenceLowerBoundLoss(S, dense_precision=precision, check="sync")
+        loss = module(mininf.condition(lambda: config.model(mininf), **config.data), approx, _noise=noise)
+        loss.backward()
+        results[precision] = (float(loss), {k: v.grad.clone() for k, v in leaves.items()})
+    assert abs(results["tf32"][0] - results["fp32"][0]) <= 1e-5 * abs(results["fp32"][0])
+    for key, grad in results["tf32"][1].items():
+        exact = results["fp32"][1][key]
+        assert float((grad - exact).norm() / exact.norm()) < 1e-4, key
+
+
 def test_row_permutation_invariance_and_determinism():
     """The joint is a sum over rows: permuting (X, y) jointly changes nothing beyond fp32
     reassociation, and repeating a call is bit-identical (fixed-order reductions)."""
@@ -603,7 +712,7 @@ def test_gram_statistics_kernel_against_exact_and_per_particle_kernels(n, S, p, 
     """Raw C-ABI, Normal(a + X theta, exp(s)) with a latent + constant intercept, a latent scale,
     features with non-zero means (the sums of squares do not cancel in the Gram form) and no row
     mask: the Gram path (TF32 X, exact products, fp32/fp64 sums) and the per-particle tcgen05
-    kernel (MNF_DENSE_NO_GRAM=1; three passes of the wide kernel at S = 100, where the Gram path still
+    kernel (mode MNF_DENSE_TF32; four passes of the wide kernel at S = 100, where the Gram path still
     reads X once) against the exact fp32 SIMT kernel. Ragged and one-row tiles; feature counts below
     64 (columns past p are zero-filled by the TMA unit); with a row mask (30 % of the rows missing, their
     responses NaN, at an address that is not 4-byte aligned) the masked rows must leave every sum."""
@@ -642,16 +751,16 @@ def test_gram_statistics_kernel_against_exact_and_per_particle_kernels(n, S, p, 
 
     exact = sweep(abi.DENSE_FP32)
     monkeypatch.delenv("MNF_DENSE_NO_GRAM", raising=False)
-    gram = sweep(abi.DENSE_TF32)
-    assert np.array_equal(gram, sweep(abi.DENSE_TF32))                  # fixed-order reductions
-    monkeypatch.setenv("MNF_DENSE_NO_GRAM", "1")
+    gram = sweep(abi.DENSE_TF32_CLOSED_FORM)
+    assert np.array_equal(gram, sweep(abi.DENSE_TF32_CLOSED_FORM))      # fixed-order reductions
     if S > 128:                                        # beyond the per-particle kernels: only the Gram path
+        assert lib.raw("mnf_dense_tf32_kernel")(abi.NORMAL, p, S) == 3
+        monkeypatch.setenv("MNF_DENSE_NO_GRAM", "1")
         assert lib.raw("mnf_dense_tf32_kernel")(abi.NORMAL, p, S) == 0
         monkeypatch.delenv("MNF_DENSE_NO_GRAM")
-        assert lib.raw("mnf_dense_tf32_kernel")(abi.NORMAL, p, S) == 3
         per_particle = exact
     else:
-        per_particle = sweep(abi.DENSE_TF32)
+        per_particle = sweep(abi.DENSE_TF32)           # the black-box mode never takes the closed form
     assert not np.array_equal(gram, per_particle)                        # the switch selects another kernel (or: not the exact one)
     for name, fast in (("gram", gram), ("per-particle", per_particle)):
         # TF32 rounding of X is unbiased: few rows state the loose tolerance, 1e6 rows the tight one
@@ -762,7 +871,7 @@ def test_normal_site_sufficient_statistics(n, offset, masked, covariate, misalig
 
     model32, cond32 = make(*data32, DEV)
     approx, leaves = cpu.approximation(device=DEV)
-    loss_module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+    loss_module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync", closed_form=True)
     loss = loss_module(mininf.condition(lambda: model32(mininf), **cond32), approx,
                        _noise={k: v.float().to(DEV) for k, v in noise.items()})
     loss.backward()
@@ -812,7 +921,7 @@ def _poisson_site_eval(make, x64, x32, families, S, seed):
     expected.backward()
     model32, cond32 = make(x32, DEV, torch.float32)
     approx, leaves = cpu.approximation(device=DEV)
-    loss_module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+    loss_module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync", closed_form=True)
     loss = loss_module(mininf.condition(lambda: model32(mininf), **cond32), approx,
                        _noise={k: v.float().to(DEV) for k, v in noise.items()})
     loss.backward()
@@ -842,29 +951,28 @@ def test_poisson_site_moment_sweep_against_float64_oracle(n, kwargs):
         np.testing.assert_allclose(grads[key], grads64[key], rtol=3e-4, atol=2e-3 + 1e-6 * abs(expected))
 
 
-def test_poisson_site_moment_sweep_agrees_with_per_particle_kernel(monkeypatch):
-    """A/B on identical inputs: the moment path against the MUFU kernel (MNF_POISSON_EXACT=1),
-    N = 3e6, S = 64, both within 2e-6 of each other on the loss and 2e-5 on the gradients."""
+def test_poisson_site_moment_sweep_agrees_with_per_particle_kernel():
+    """A/B on identical inputs: the moment path (closed_form=True) against the per-particle MUFU
+    kernel (the default), N = 3e6, S = 64, both within 2e-6 of each other on the loss and 2e-5 on
+    the gradients."""
     make, x64, x32, families = _poisson_site_case(3_000_000, seed=5)
 
-    def run():
+    def run(closed_form):
         torch.manual_seed(11)
         cfg = configs.Config("poisson_site", None, {}, families)
         approx, leaves = cfg.approximation(device=DEV)
         gen = torch.Generator().manual_seed(3)
         noise = {k: torch.randn(64, generator=gen).to(DEV) for k in families}
         model32, cond32 = make(x32, DEV, torch.float32)
-        loss = mininf.nn.EvidenceLowerBoundLoss(64, check="sync")(
+        loss = mininf.nn.EvidenceLowerBoundLoss(64, check="sync", closed_form=closed_form)(
             mininf.condition(lambda: model32(mininf), **cond32), approx, _noise=noise)
         loss.backward()
         return float(loss), torch.stack([v.grad for v in leaves.values()]).double().cpu()
 
-    monkeypatch.delenv("MNF_POISSON_EXACT", raising=False)
-    fast = run()
-    again = run()
+    fast = run(True)
+    again = run(True)
     assert fast[0] == again[0] and torch.equal(fast[1], again[1])          # fixed-order reductions
-    monkeypatch.setenv("MNF_POISSON_EXACT", "1")
-    exact = run()
+    exact = run(False)
     assert abs(fast[0] - exact[0]) <= 2e-6 * abs(exact[0])
     assert float((fast[1] - exact[1]).norm() / exact[1].norm()) < 2e-5
 
@@ -885,7 +993,7 @@ def test_poisson_site_moment_sweep_flags_invalid_counts_and_propagates_nan_covar
         b = mininf.sample("b", Normal(0, 1))
         mininf.sample("counts", Poisson((a + b * x).exp()))
 
-    module = mininf.nn.EvidenceLowerBoundLoss(8, check="sync")
+    module = mininf.nn.EvidenceLowerBoundLoss(8, check="sync", closed_form=True)
     assert torch.isfinite(module(mininf.condition(model, counts=counts), approx))
     counts[17] = 2.5                  # same tensors (cached plan), now with a non-integer count
     with pytest.raises(ValueError, match="support"):
@@ -931,7 +1039,7 @@ def test_full_size_site_sweeps_permutation_invariance_determinism_and_counts():
         gen = torch.Generator().manual_seed(9)
         noise = {k: torch.randn(S, generator=gen).to(DEV) for k in "abcd"}
         noise["sigma"] = torch._standard_gamma(torch.full((S,), 2.0), generator=gen).to(DEV)
-        module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+        module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync", closed_form=True)
         loss = module(mininf.condition(model, counts=torch.masked.as_masked_tensor(counts, m_counts),
                                        w=torch.masked.as_masked_tensor(w, m_w)), approx, _noise=noise)
         loss.backward()
@@ -997,3 +1105,89 @@ def test_full_size_row_latent_sweep_is_seeded_and_its_gradients_are_consistent()
     h = 0.03     # fp32 loss resolution (~2e2 of 2e9) and the cubic term both stay near 1e-3 of the slope
     numeric = (evaluate(0.4 + h, backward=False) - evaluate(0.4 - h, backward=False)) / (2 * h)
     assert abs(numeric - first[1]) <= 5e-3 * abs(first[1]), (numeric, first[1])
+
+
+# ---------------------------------------------------------------------------------------------
+# one native call per step: mnf_plan_create / mnf_elbo_fwd_bwd / mnf_svi_step (include/mininf_b200.h)
+# ---------------------------------------------------------------------------------------------
+def test_a_step_is_one_native_call_with_few_kernels():
+    """The drop-in loss enqueues its whole evaluation through mnf_elbo_fwd_bwd: for the regression
+    model that is rsample, the dense sweep, its partial reduction and ONE tail kernel (priors +
+    finalize), as counted by the library itself."""
+    torch.manual_seed(0)
+    config = configs.regression(5000, 64, sigma_latent=True, device=DEV, gen_device="cpu")
+    approx, _ = config.approximation(device=DEV)
+    module = mininf.nn.EvidenceLowerBoundLoss(16, dense_precision="tf32", check="sync")
+    loss = module(mininf.condition(lambda: config.model(mininf), **config.data), approx)
+    assert torch.isfinite(loss)
+    assert module.last_plan.gpu_launches_per_step == 4
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_svi_step_matches_the_torch_adam_loop(graph):
+    """FusedSVIStep (mnf_svi_step: transforms, ELBO + gradient kernels, chain rule and Adam inside
+    the engine) against the reference-style loop `zero_grad; loss.backward(); Adam.step()` on the
+    same model with the same Philox draws: parameters after 25 steps agree to fp32 round-off."""
+    from torch.distributions import Gamma, Normal
+    PD = mininf.nn.ParameterizedDistribution
+    config = configs.regression(3000, 64, sigma_latent=True, device=DEV, gen_device="cpu")
+    conditioned = mininf.condition(lambda: config.model(mininf), **config.data)
+
+    def modules():
+        return {"theta": PD(Normal, loc=torch.zeros(64, device=DEV), scale=0.1 * torch.ones(64, device=DEV)),
+                "sigma": PD(Gamma, concentration=torch.tensor(2.0, device=DEV), rate=torch.tensor(2.0, device=DEV))}
+
+    steps, lr = 25, 0.02
+    torch.manual_seed(7)
+    fused_modules = modules()
+    fused_loss = mininf.nn.EvidenceLowerBoundLoss(8, dense_precision="fp32")
+    fused = mininf.nn.FusedSVIStep(fused_loss, conditioned, fused_modules, lr=lr, graph=graph)
+    first_offset, seed = fused._offset, fused._seed
+    losses = [float(fused()) for _ in range(steps)]
+    fused_loss.synchronize()
+    assert fused.kernels_per_step == 4 and int(fused.steps) == steps + (2 if graph else 0)
+
+    # the same loop with torch: replay the fused step's Philox stream through the plan directly
+    torch.manual_seed(7)
+    ref_modules = modules()
+    optimizer = torch.optim.Adam([p for m in ref_modules.values() for p in m.parameters()], lr=lr)
+    ref_loss = mininf.nn.EvidenceLowerBoundLoss(8, dense_precision="fp32", check="off")
+    reference_losses = []
+    warm = 2 if graph else 0              # graph capture ran two warm-up steps that also updated the parameters
+    for step in range(steps + warm):
+        optimizer.zero_grad()
+        approx = {name: module() for name, module in ref_modules.items()}
+        plan = ref_loss._plan_for(conditioned, approx)
+        from mininf_b200.nn import _EngineFunction
+        from mininf_b200.engine.plan import latent_parameters
+        params = []
+        for spec in plan.all_latents:
+            _, p0, p1 = latent_parameters(approx[spec.name])
+            params += [p0.expand(spec.shape if len(spec.shape) else torch.Size([])),
+                       p1.expand(spec.shape if len(spec.shape) else torch.Size([]))]
+        loss = _EngineFunction.apply(ref_loss, plan, None, {}, seed, first_offset + step, None, True, False, *params)
+        loss.backward()
+        optimizer.step()
+        reference_losses.append(float(loss))
+    np.testing.assert_allclose(losses, reference_losses[warm:], rtol=2e-5)
+    for name in ref_modules:
+        for key, parameter in ref_modules[name].distribution_parameters.items():
+            np.testing.assert_allclose(fused_modules[name].distribution_parameters[key].detach().cpu().numpy(),
+                                       parameter.detach().cpu().numpy(), rtol=2e-4, atol=2e-6, err_msg=f"{name}.{key}")
+
+
+def test_c_program_runs_a_step_from_host_tables_without_python(tmp_path):
+    """tests/c/plan_step.c: a plain C consumer of include/mininf_b200.h builds the flat tables of a
+    regression model, calls mnf_plan_create / mnf_elbo_fwd_bwd / mnf_svi_step and checks the loss
+    against its own double-precision evaluation (no Python, no torch in the process)."""
+    import subprocess
+    from mininf_b200.engine import build
+    root = build.PACKAGE_DIR.parent
+    binary = tmp_path / "plan_step"
+    subprocess.run(["gcc", "-O1", "-std=c11", "-I", str(root / "include"), "-I", "/usr/local/cuda/include",
+                    str(root / "tests" / "c" / "plan_step.c"), "-o", str(binary), str(build.LIB_PATH),
+                    "-L/usr/local/cuda/lib64", "-lcudart", "-lm", f"-Wl,-rpath,{build.LIB_DIR}",
+                    "-Wl,-rpath,/usr/local/cuda/lib64"], check=True)
+    result = subprocess.run([str(binary)], capture_output=True, text=True)
+    assert result.returncode == 0, result.stdout + result.stderr
+    assert "OK" in result.stdout

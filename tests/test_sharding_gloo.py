@@ -99,3 +99,48 @@ def test_two_ranks_reproduce_the_single_process_elbo():
         np.testing.assert_allclose(grad_loc, loc.grad.numpy(), rtol=2e-4, atol=1e-3)
         np.testing.assert_allclose(grad_scale, scale.grad.numpy(), rtol=2e-4, atol=1e-3)
     assert results[0][1] == results[1][1]                 # ranks agree bit for bit after the reduce
+
+
+class _RecordingLibrary:
+    """Stands in for the native library: records the order of the C-ABI calls of a step."""
+
+    def __init__(self, log):
+        self.log = log
+
+    def call(self, name, *args):
+        if name == "mnf_elbo_fwd_bwd":
+            self.log.append((name, int(args[4])))          # the step flags
+        elif name == "mnf_plan_launches":
+            args[1]._obj.value = 2
+        else:
+            self.log.append((name,))
+
+    def raw(self, name):
+        raise AssertionError(f"unexpected raw call {name}")
+
+
+def test_plan_step_orders_the_reduction_between_the_two_halves_of_the_step():
+    """Product code on the CPU (no kernels): ``Plan.step(reduce_fn=...)`` must enqueue the sweeps over
+    the rank's observed rows, THEN reduce the [S][1+D] accumulator across ranks, THEN add the
+    latent-valued (prior) sites and finalize - exactly once each; without a reduction (one rank, or
+    the engine's own peer exchange) the step is a single native call."""
+    import mininf_b200 as mininf
+    from mininf_b200.engine import abi
+    from mininf_b200.engine.plan import LatentSpec, Plan
+    from mininf_b200.engine.trace import Affine, LatentRef, LinkTensor, SiteTableTracer
+
+    config = configs.regression(N, P)
+    draws = {"theta": LinkTensor.wrap(torch.randn(P), Affine(a_lat=LatentRef("theta")))}
+    with SiteTableTracer() as tracer:
+        mininf.condition(mininf.condition(lambda: config.model(mininf), **config.data), **draws)()
+    plan = Plan(tracer.sites, [LatentSpec("theta", abi.NORMAL, torch.Size([P]), P, 0)], S, torch.device("cpu"),
+                dense_mode="fp32", dry_run=True)
+    log = []
+    plan.lib = _RecordingLibrary(log)
+    plan.step(None, seed=1, offset=2, reduce_fn=lambda acc: log.append(("reduce", tuple(acc.shape))))
+    assert log == [("mnf_elbo_fwd_bwd", abi.STEP_ENTROPY | abi.STEP_PRE), ("reduce", (S, 1 + P)),
+                   ("mnf_elbo_fwd_bwd", abi.STEP_ENTROPY | abi.STEP_POST)]
+    assert plan.gpu_launches_per_step == 4                 # both halves are counted
+    log.clear()
+    plan.step(None, seed=1, offset=3, with_entropy=False)
+    assert log == [("mnf_elbo_fwd_bwd", abi.STEP_ALL)]

@@ -37,8 +37,12 @@ def test_regression_lowers_to_one_dense_site_and_two_priors():
     assert mode == abi.DENSE_TF32 and site.family == abi.NORMAL and (site.p, site.n_rows) == (64, 3000)
     assert site.theta_lat == 0 and site.icpt_lat == -1 and site.scale.a_lat == 64 and site.weight == 1.0
     assert plan.small_global[1] == 2 and plan.small_observed is None
-    # rsample, Gram statistics + totals + closed forms + row reduction (csrc/dense_gram.cuh), priors, finalize
-    assert plan.gpu_launches_per_step == 7
+    # the closed-form switch selects the Gram-statistics mode of the same site
+    closed = Plan(sites, specs, 64, CPU, dense_mode="auto", dry_run=True, closed_form=True)
+    assert closed.dense_sites[0][1] == abi.DENSE_TF32_CLOSED_FORM
+    # more than 128 particles: only the closed form has a tensor-core kernel
+    assert Plan(sites, specs, 200, CPU, dry_run=True).dense_sites[0][1] == abi.DENSE_FP32
+    assert Plan(sites, specs, 200, CPU, dry_run=True, closed_form=True).dense_sites[0][1] == abi.DENSE_TF32_CLOSED_FORM
 
 
 def test_shapes_outside_the_tensor_core_kernel_use_fp32_or_raise():
@@ -56,7 +60,7 @@ def test_shapes_outside_the_tensor_core_kernel_use_fp32_or_raise():
     config = configs.regression(100, 24)
     sites, specs = trace(lambda: config.model(mininf), {"theta": (abi.NORMAL, torch.randn(24))}, config.data)
     plan = Plan(sites, specs, 40, CPU, dry_run=True)
-    assert plan.dense_sites[0][1] == abi.DENSE_TF32 and plan.gpu_launches_per_step == 2 + 2 * 2 + 1
+    assert plan.dense_sites[0][1] == abi.DENSE_TF32
 
 
 def test_minibatch_weight_and_logits_family():
@@ -225,3 +229,42 @@ def test_plans_with_converted_copies_are_not_rebindable():
     plan.bind_sources(_leaves(data))
     assert not plan.rebindable and not plan.rebind(_leaves(data | {"y": data["y"].clone()}))
     assert plan.rebind(_leaves(data)) is False
+
+
+def test_tuple_unpacking_a_latent_keeps_the_link_to_it():
+    """`a, b = sample(...)` goes through Tensor.__iter__ -> unbind: the pieces must stay scalar
+    references to the latent (a stripped tensor would freeze the trace-time draw into the plan and
+    the gradient with respect to 'ab' would silently be zero)."""
+    x, y = torch.randn(4000), torch.randn(4000)
+
+    def model():
+        a, b = mininf.sample("ab", Normal(0, 1), [2])
+        mininf.sample("y", Normal(a + b * x, 1.0))
+
+    sites, specs = trace(model, {"ab": (abi.NORMAL, torch.randn(2))}, {"y": y})
+    plan = Plan(sites, specs, 4, CPU, dry_run=True)
+    (site,) = plan.sweep_groups[0]
+    assert (site.param[0].a_lat, site.param[0].b_lat) == (0, 1)
+
+
+@pytest.mark.parametrize("how", ["split", "inplace", "item", "max"])
+def test_untracked_uses_of_a_latent_raise_instead_of_freezing_the_draw(how):
+    x, y = torch.randn(300), torch.randn(300)
+
+    def model():
+        ab = mininf.sample("ab", Normal(0, 1), [2])
+        if how == "split":
+            a, b = ab.split(1)
+            loc = a + b * x
+        elif how == "inplace":
+            loc = ab[0] + ab[1] * x
+            loc.add_(1.0)
+        elif how == "item":
+            loc = ab[0].item() + x
+        else:
+            loc = ab.max(dim=0).values + x
+        mininf.sample("y", Normal(loc, 1.0))
+
+    with pytest.raises(NotImplementedError):
+        sites, specs = trace(model, {"ab": (abi.NORMAL, torch.randn(2))}, {"y": y})
+        Plan(sites, specs, 4, CPU, dry_run=True)

@@ -11,7 +11,8 @@ from mininf_b200.engine import abi  # noqa: E402
 
 torch.manual_seed(0)
 dev = torch.device("cuda:0")
-lib = abi.load()
+import os
+lib = abi.Library(os.environ["MNF_LIB"]) if os.environ.get("MNF_LIB") else abi.load()
 info = lib.device_info()
 print("device", info.sm_count, info.cc_major, info.cc_minor, info.max_smem_optin)
 

@@ -127,6 +127,7 @@ int main() {
     run("A TMEM      B K/SW128", {64, 64, 0, 2, 0, 2, 1, R, nacc, 16, 1024, 16, 1024});
     run("A TMEM      B K/SW128", {128, 64, 0, 2, 0, 2, 1, R, nacc, 16, 1024, 16, 1024});
     run("A TMEM      B K/SW128", {64, 128, 0, 2, 0, 2, 1, R, nacc, 16, 1024, 16, 1024});
+    run("A TMEM      B K/SW128", {128, 128, 0, 2, 0, 2, 1, R, nacc, 16, 1024, 16, 1024});   // hi/lo particle slots
     run("A TMEM      B MN/SW32B", {64, 64, 0, 2, 1, 1, 1, R, nacc, 16, 1024, 16384, 512});
     run("A TMEM      B MN/SW32B", {128, 64, 0, 2, 1, 1, 1, R, nacc, 16, 1024, 16384, 512});
     run("A TMEM      B MN/SW32B", {64, 128, 0, 2, 1, 1, 1, R, nacc, 16, 1024, 16384, 512});
