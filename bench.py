@@ -20,7 +20,8 @@ per-observation latent feature vector (p = 32), S = 32 (the row-latent kernel; i
 S = 64 (site sweeps; closed-form statistics by default for this workload, black-box beside it).
 A step is one full SVI step: parameter transforms, reparameterised draws, ELBO + gradient kernels,
 chain rule, Adam - `mininf_b200.nn.FusedSVIStep` (one native call, replayed from a CUDA graph);
-models with per-observation latents (c4) use `GraphedStep` with torch's fused Adam. The metric is
+per-observation latents (c4) are trained inside the row-latent sweep. `--torch-adam` runs
+`GraphedStep` with torch's fused Adam instead. The metric is
 particle-observation log-density evaluations per second: rows * S / time, whole job.
 
 `--impl reference` times the UNMODIFIED reference (baseline/_ref, installed from /root/reference)
@@ -64,8 +65,8 @@ class Workload:
 
 WORKLOADS = {
     "c2": Workload("c2", "bayesian_linear_regression_p64_N1e8_S64", 64, 64, 100_000_000, "normal", None, 1,
-                   "mnf::tc::dense_tc_kernel<Normal> (+ its partial-sum reduction, ~8 us)",
-                   "dense_tc_traffic.json",
+                   "mnf::th::dense_th_kernel<Normal> (fp16 operands; + its partial-sum reduction, ~8 us)",
+                   "dense_th_traffic.json",
                    closed_form_kernel="mnf::gram::dense_gram_kernel (+ gram_reduce / gram_finish / reduce_partials)"),
     "c3": Workload("c3", "minibatch_logistic_regression_p256_batch1e7_of_N1e9_S16", 256, 16, 10_000_000,
                    "bernoulli", 1_000_000_000, 2,
@@ -105,12 +106,34 @@ def parse_args():
                     help="let sites with closed-form sufficient statistics skip the per-particle sweep")
     ap.add_argument("--black-box", action="store_true", help="force the per-particle sweep (c5 defaults to closed form)")
     ap.add_argument("--weak", action="store_true", help="weak scaling: the full configuration on every rank")
+    ap.add_argument("--torch-adam", action="store_true",
+                    help="GraphedStep with torch.optim.Adam(fused=True) instead of the native FusedSVIStep")
+    ap.add_argument("--precision", default="auto", choices=["auto", "f16", "tf32", "fp32"],
+                    help="tensor-core operand format of dense sites (auto: fp16 operands for p = 64 / S <= 64, else TF32)")
     ap.add_argument("--reduce", default="peer", choices=["peer", "nccl"], help="how sharded ranks combine partial sums")
     ap.add_argument("--sustain", type=float, default=1.0, help="seconds of back-to-back steps for the sustained figure")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary objects (closed form, reference on CUDA)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
+
+
+def dense_dtype(plan):
+    """The arithmetic type of the dense sweep that ran (engine/abi.py DENSE_* modes)."""
+    from mininf_b200.engine import abi
+    modes = {mode for _, mode in plan.dense_sites}
+    if modes == {abi.DENSE_F16}:
+        return "f16 operands (11-bit significand; theta as hi + lo pairs) / f32 accumulate"
+    if modes <= {abi.DENSE_TF32, abi.DENSE_TF32_CLOSED_FORM}:
+        return "tf32 operands (theta as hi + lo pairs) / f32 accumulate"
+    return "f32"
+
+
+def dense_kernel_name(w, plan):
+    from mininf_b200.engine import abi
+    if w.key == "c2" and {mode for _, mode in plan.dense_sites} == {abi.DENSE_TF32}:
+        return "mnf::tc::dense_tc_kernel<Normal> (TF32 operands; + its partial-sum reduction)"
+    return w.kernel
 
 
 def measured_peak_gbs():
@@ -474,13 +497,13 @@ def run_b200(args):
     batches = [make_data(w, n_total, device, SEED0 + b * 256, rows=(lo, hi)) for b in range(w.n_batches)]
     modules = make_approximation(mininf, w, n_rows, batches[0], device)
     streaming = w.n_batches > 1
-    fused = w.family != "rowlatent"                    # per-observation latents: GraphedStep + torch Adam
+    fused = not args.torch_adam                        # FusedSVIStep (native transforms + Adam) unless asked otherwise
     graphed = not args.eager
     model = model_factory(mininf, w, n_rows, batches[0], declared)
 
     def make_loss(closed):
-        return mininf.nn.EvidenceLowerBoundLoss(S, dense_precision="tf32", closed_form=closed, reduce=args.reduce,
-                                                process_group=True if distributed else None)
+        return mininf.nn.EvidenceLowerBoundLoss(S, dense_precision=args.precision, closed_form=closed,
+                                                reduce=args.reduce, process_group=True if distributed else None)
 
     def approximation():
         return {name: module() for name, module in modules.items()}
@@ -529,6 +552,8 @@ def run_b200(args):
         return run()
 
     plan = loss_modules[0].last_plan
+    step()
+    kernels_per_step = plan.gpu_launches_per_step      # counted by the library during the step just enqueued
 
     # Roofline numerator: per-launch duration of the workload's sweep call from CUDA events recorded
     # around the launch on its stream (Plan.step with `record_sweep_events`: the same kernels with the
@@ -540,9 +565,10 @@ def run_b200(args):
         plan.sweep_event_kinds.clear()
         plan.record_sweep_events = True
         for i in range(repeats):
-            if fused:
+            if fused and not plan.row_latents:
                 plan.step(None, 1234, 1 << 50 | i)
-            else:      # row latents: the loss call binds this step's parameter / gradient buffers
+            else:      # row latents: the loss call binds this step's parameter / gradient buffers (the
+                       # gradient-only variant of the sweep: the fused optimiser adds traffic, not instructions)
                 with torch.no_grad():
                     loss_modules[0](condition_on(mininf, model, w, batches[0]), approximation())
         fence()
@@ -605,7 +631,7 @@ def run_b200(args):
 
     # ---- secondary objects (rank 0 prints; every rank takes part in sharded evaluations) ----------
     secondary = {}
-    if not args.no_secondary and fused and (w.closed_form_kernel or w.black_box_kernel):
+    if not args.no_secondary and fused and not plan.row_latents and (w.closed_form_kernel or w.black_box_kernel):
         other = not closed_form
         other_loss = make_loss(other)
         other_step = mininf.nn.FusedSVIStep(other_loss, condition_on(mininf, model, w, batches[0]), modules, lr=0.01,
@@ -664,7 +690,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
-            "dtype": "tf32 operands / f32 accumulate" if w.event_kind == "dense" else "f32 (f64 sums)",
+            "dtype": dense_dtype(plan) if w.event_kind == "dense" else "f32 (f64 sums)",
             "data": "synthetic",
             "config": {"workload": w.name, "rows_total": n_total, "rows_per_gpu": n_rows,
                        "features": P, "particles": S,
@@ -681,11 +707,12 @@ def run_b200(args):
                        "final_loss": final_loss},
             "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": plan.gpu_launches_per_step * args.steps,
-            "kernels_per_step": plan.gpu_launches_per_step,
+            "gpu_launches": kernels_per_step * args.steps,
+            "kernels_per_step": kernels_per_step,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_source,
-                         "kernel": (w.closed_form_kernel if closed_form and w.closed_form_kernel else w.kernel),
+                         "kernel": (w.closed_form_kernel if closed_form and w.closed_form_kernel else
+                                    dense_kernel_name(w, plan)),
                          "kernel_ms": kernel_ms, "algorithmic_bytes": algorithmic_bytes,
                          "kernel_ms_before_after": [kernel_ms_before, kernel_ms_after],
                          "kernel_timing": f"CUDA events around each launch, {args.steps} eager launches right "

@@ -63,6 +63,8 @@ extern "C" {
 #define MNF_ST_BAD_VALUE 2u     /* an unmasked value left the support of its distribution      */
 #define MNF_ST_NONFINITE 4u     /* the loss or a gradient is NaN/Inf                           */
 #define MNF_ST_XRANK_TIMEOUT 8u /* a peer rank did not deliver its accumulator within ~2 s      */
+#define MNF_ST_RANGE 16u        /* MNF_DENSE_F16: a design-matrix entry is NaN/Inf or >= 2^15: outside */
+                                /* the range the fp16 operand format is used for (use MNF_DENSE_TF32)  */
 
 /*
  * One distribution parameter as a scalar link:  value_i = T(A_i + B_i * x_i)  with
@@ -166,6 +168,10 @@ typedef struct mnf_rowlatent {
                            /* TF32 pairs, fp32 accumulate in TMEM; shapes: mnf_dense_tf32_kernel   */
 #define MNF_DENSE_TF32_CLOSED_FORM 2 /* as 1, but a Normal site with p <= 64 may be reduced to its  */
                            /* Gram statistics (no per-particle work; csrc/dense_gram.cuh)          */
+
+#define MNF_DENSE_F16 3    /* as 1 with fp16 operands (the same 11-bit significand as TF32, K = 16 per */
+                           /* MMA: half the tensor-pipe time; csrc/dense_th.cuh). p == 64, S <= 64;    */
+                           /* |X| must stay below 2^15 (checked per step -> MNF_ST_RANGE)              */
 
 /* flags of mnf_site_sweep / mnf_plan_desc_t */
 #define MNF_SWEEP_CLOSED_FORM 1u /* allow the data-only sufficient-statistics paths (six sums for   */
@@ -316,6 +322,17 @@ typedef struct mnf_row_buffers {
   float* grad_loc;
   float* grad_scale;
   const float* eps;                    /* optional external noise [S][n_rows][p] */
+  /* mnf_svi_step only: the N*p variational parameters are trained INSIDE the row-latent sweep
+   * (transform, chain rule and Adam per element, in place; csrc/rowlatent.cuh). `loc_rw` is the
+   * unconstrained location (identity transform, == loc), `raw_scale` the unconstrained scale
+   * (scale = exp(raw_scale); `scale`, `grad_loc`, `grad_scale` are then unused), m / v the Adam
+   * moments, all [n_rows][p]. Single-pass sweeps only (at most 32 particles). */
+  float* loc_rw;
+  float* raw_scale;
+  float* m_loc;
+  float* v_loc;
+  float* m_scale;
+  float* v_scale;
 } mnf_row_buffers_t;
 
 /* Caller-owned device buffers of a step; every pointer is borrowed for the enqueued work. */
@@ -381,6 +398,33 @@ int mnf_svi_step(mnf_plan_t* plan, const mnf_buffers_t* buffers, const mnf_adam_
 int mnf_xrank_create(int world, int rank, int64_t n_doubles, mnf_xrank_t** out, void* handle_out);
 int mnf_xrank_connect(mnf_xrank_t* xr, const void* handles /* world x MNF_XRANK_HANDLE_BYTES */);
 int mnf_xrank_destroy(mnf_xrank_t* xr);
+
+/*
+ * Batched posterior predictive (`broadcast_samples`, mininf/core.py:548-584): for each of B
+ * posterior samples, walk the traced sites in model order; `value` sites are evaluated from their
+ * link, sites the samples do not provide are drawn from their distribution. z is [B][n_columns]:
+ * the given samples occupy their columns, every site writes its result to out_col .. out_col+numel.
+ * One launch for all samples (csrc/predict.cuh); Philox stream (seed, offset).
+ */
+#define MNF_PRED_DRAW 0
+#define MNF_PRED_VALUE 1
+typedef struct mnf_pred_site {
+  int32_t kind;          /* MNF_PRED_DRAW | MNF_PRED_VALUE (then param[0] / the dense link IS the value) */
+  int32_t family;        /* MNF_* of a drawn site */
+  int64_t numel;
+  int32_t out_col;       /* first column of this site's values in z */
+  int32_t transform;     /* dense link only: MNF_T_* applied to icpt + X theta */
+  mnf_link_t param[2];   /* scalar links (X == NULL) */
+  const float* X;        /* dense link of the first parameter: [numel][ldx], or NULL */
+  int64_t ldx;
+  int32_t p;
+  int32_t theta_lat;
+  int32_t icpt_lat;
+  float icpt_const;
+} mnf_pred_site_t;
+
+int mnf_predictive(const mnf_pred_site_t* sites_dev, int n_sites, int n_samples, int n_columns, float* z,
+                   uint64_t seed, uint64_t offset, uint32_t* status, void* stream);
 
 /* Counting scan used by the integer-exact parity checks: out[0]=sum(mask), out[1]=sum(mask*value)
  * as int64 (value must hold integers); mask may be NULL (all ones). */

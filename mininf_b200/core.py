@@ -377,10 +377,16 @@ def transpose_states(states: Any) -> Any:
 
 def broadcast_samples(model: Callable, states: State | None = None,
                       **params: torch.Tensor) -> State:
-    """Run ``model`` once per leading-dimension slice of the given samples and stack the results
-    (posterior-predictive helper, mininf/core.py:548-584)."""
+    """Apply ``model`` to every leading-dimension slice of the given samples and stack the results
+    (posterior-predictive helper, mininf/core.py:548-584). CUDA samples are broadcast by the
+    engine - the model is traced once and ``mnf_predictive`` evaluates / draws every site for all
+    samples in one launch (engine/predictive.py); CPU samples take the reference's per-sample
+    loop."""
     states = states or State()
     states.update(params)
+    if states and any(isinstance(v, torch.Tensor) and v.is_cuda for v in states.values()):
+        from .engine.predictive import broadcast_samples as _broadcast_on_device
+        return _broadcast_on_device(model, states)
     results = []
     for single in transpose_states(states):
         with single:

@@ -133,3 +133,15 @@ int mnf_masked_count(const float* value, const uint8_t* mask, int64_t numel, int
 }  // extern "C"
 
 #include "plan.cuh"
+#include "predict.cuh"
+
+extern "C" int mnf_predictive(const mnf_pred_site_t* sites_dev, int n_sites, int n_samples, int n_columns, float* z,
+                              uint64_t seed, uint64_t offset, uint32_t* status, void* stream) {
+  if (!sites_dev || !z || !status || n_sites < 0 || n_samples < 0 || n_columns < 1)
+    return mnf::fail(MNF_E_INVALID, "mnf_predictive: null pointer or bad size%s%s");
+  if (n_sites == 0 || n_samples == 0) return MNF_OK;
+  mnf::predictive_kernel<<<n_samples, mnf::kPredictThreads, 0, (cudaStream_t)stream>>>(sites_dev, n_sites, n_columns, z,
+                                                                                     seed, offset, status);
+  MNF_LAUNCH_CHECK();
+  return MNF_OK;
+}

@@ -46,6 +46,21 @@ inline thread_local int g_launches = 0;
                                                  cudaGetErrorString(err__));                  \
   } while (0)
 
+// mnf_svi_step: the row latent's own parameters are trained inside the sweep (README.md:63-69's
+// optimizer.step() and ParameterizedDistribution's exp transform, mininf/nn.py:88-96, per element).
+// `enabled == 0` leaves the kernel as a pure gradient evaluation.
+struct RowAdam {
+  int enabled;
+  float lr, beta1, beta2, eps;
+  const int64_t* step;          // device: updates applied so far (the tail kernel increments it)
+  float* loc_rw;                // unconstrained location (identity transform)
+  float* raw_scale;             // unconstrained scale, scale = exp(raw)
+  float* m_loc;
+  float* v_loc;
+  float* m_scale;
+  float* v_scale;
+};
+
 // ---------------------------------------------------------------------------------------------
 // warp / block reductions (fixed butterfly order => run-to-run deterministic)
 // ---------------------------------------------------------------------------------------------
@@ -125,6 +140,8 @@ constexpr uint64_t kPhiloxNormal = (uint64_t)1 << 56;
 constexpr uint64_t kPhiloxGamma = (uint64_t)2 << 56;
 constexpr uint64_t kPhiloxBeta0 = (uint64_t)3 << 56;
 constexpr uint64_t kPhiloxRowLatent = (uint64_t)4 << 56;
+constexpr uint64_t kPhiloxPredict = (uint64_t)5 << 56;        // posterior-predictive draws (predict.cuh)
+constexpr uint64_t kPhiloxPredictGamma = (uint64_t)4 << 48;   // | into the gamma sampler's index (tag 2 stays on top)
 
 struct Philox {
   uint32_t c[4];

@@ -5,6 +5,7 @@
 #include "dense_tc.cuh"
 #include "dense_tcr.cuh"
 #include "dense_gram.cuh"
+#include "dense_th.cuh"
 
 using namespace mnf;
 
@@ -35,14 +36,15 @@ int tensor_map_encoder(TensorMapEncodeFn* out) {
 
 // X [n_rows][ldx] fp32 as a 2-D tensor (features fastest), boxes of 32 features x 128 rows,
 // data type TFLOAT32: the TMA unit rounds to tf32 (nearest even) while copying.
-int make_x_map(const mnf_dense_site_t& site, CUtensorMapSwizzle swizzle, CUtensorMap* map) {
+int make_x_map(const mnf_dense_site_t& site, CUtensorMapSwizzle swizzle, CUtensorMap* map,
+               CUtensorMapDataType type = CU_TENSOR_MAP_DATA_TYPE_TFLOAT32) {
   TensorMapEncodeFn encode;
   if (int rc = tensor_map_encoder(&encode)) return rc;
   const cuuint64_t dims[2] = {(cuuint64_t)site.p, (cuuint64_t)site.n_rows};
   const cuuint64_t strides[1] = {(cuuint64_t)site.ldx * sizeof(float)};
   const cuuint32_t box[2] = {32, (cuuint32_t)tc::kTileM};
   const cuuint32_t elem_strides[2] = {1, 1};
-  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(site.X), dims,
+  const CUresult r = encode(map, type, 2, const_cast<float*>(site.X), dims,
                             strides, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MNF_E_CUDA, "cuTensorMapEncodeTiled failed%s%s");
@@ -59,6 +61,19 @@ int launch_dense_tc(const mnf_dense_site_t& site, const float* z, int S, int D, 
   MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)tc::kSmemBytes));
   kernel<<<grid, tc::kThreads, tc::kSmemBytes, stream>>>(map_k, map_mn, site, z, S, D, partial, status);
+  MNF_LAUNCH_CHECK();
+  return MNF_OK;
+}
+
+// fp16-operand kernel (dense_th.cuh): one fp32 staging image per tile, converted in shared memory
+template <int FAMILY, bool ICPT>
+int launch_dense_th(const mnf_dense_site_t& site, const float* z, int S, int D, float* partial,
+                    uint32_t* status, int grid, cudaStream_t stream) {
+  CUtensorMap map_x;
+  if (int rc = make_x_map(site, CU_TENSOR_MAP_SWIZZLE_128B, &map_x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return rc;
+  auto kernel = th::dense_th_kernel<FAMILY, ICPT>;
+  MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)th::kSmemBytes));
+  kernel<<<grid, th::kThreads, th::kSmemBytes, stream>>>(map_x, site, z, S, D, partial, status);
   MNF_LAUNCH_CHECK();
   return MNF_OK;
 }
@@ -233,7 +248,29 @@ int mnf_dense_sweep(const mnf_dense_site_t* site, int mode, const float* z, int 
   // gradient w.r.t. the scale link's pre-transform value u goes to its latent scalar
   map.scalar_lat[1] = s.family == MNF_NORMAL ? s.scale.a_lat : -1;
 
-  if (mode == MNF_DENSE_TF32 || mode == MNF_DENSE_TF32_CLOSED_FORM) {
+  if (mode == MNF_DENSE_F16) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(s.X) % 16 == 0) && (s.ldx % 4 == 0) &&
+                         s.n_rows < (int64_t)1 << 31;
+    if (!aligned || c->cc_major != 10 || p != th::kP || S > th::kNS)
+      return fail(MNF_E_UNSUPPORTED, "mnf_dense_sweep: F16 mode needs p == 64, S <= 64, 16-byte aligned rows and an "
+                                     "sm_100 device%s%s");
+    const bool has_icpt = s.icpt_lat >= 0 || s.icpt_const != 0.0f;
+    const int64_t n_tiles = (s.n_rows + th::kTileM - 1) / th::kTileM;
+    grid = (int)std::min<int64_t>(n_tiles, c->sm_count);
+    if ((size_t)grid * S * ncol * sizeof(float) > workspace_bytes)
+      return fail(MNF_E_INVALID, "mnf_dense_sweep: workspace too small%s%s");
+    int rc;
+    if (s.family == MNF_NORMAL)
+      rc = has_icpt ? launch_dense_th<MNF_NORMAL, true>(s, z, S, D, partial, status, grid, stream)
+                    : launch_dense_th<MNF_NORMAL, false>(s, z, S, D, partial, status, grid, stream);
+    else if (s.family == MNF_BERNOULLI_LOGITS)
+      rc = has_icpt ? launch_dense_th<MNF_BERNOULLI_LOGITS, true>(s, z, S, D, partial, status, grid, stream)
+                    : launch_dense_th<MNF_BERNOULLI_LOGITS, false>(s, z, S, D, partial, status, grid, stream);
+    else
+      rc = has_icpt ? launch_dense_th<MNF_POISSON, true>(s, z, S, D, partial, status, grid, stream)
+                    : launch_dense_th<MNF_POISSON, false>(s, z, S, D, partial, status, grid, stream);
+    if (rc) return rc;
+  } else if (mode == MNF_DENSE_TF32 || mode == MNF_DENSE_TF32_CLOSED_FORM) {
     const bool closed_form = mode == MNF_DENSE_TF32_CLOSED_FORM && gram_shape(s.family, p);
     const bool aligned = (reinterpret_cast<uintptr_t>(s.X) % 16 == 0) && (s.ldx % 4 == 0) &&
                          s.n_rows < (int64_t)1 << 31;

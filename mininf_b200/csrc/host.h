@@ -40,4 +40,9 @@ struct ColMap {
 int launch_reduce(const float* partial, int n_cta, int S, int ncol, const ColMap& map, double weight,
                   int D, double* acc, cudaStream_t stream);
 
+// row-latent sweep with an optional fused optimiser (rowlatent.cu; RowAdam in common.cuh)
+int rowlatent_sweep(const mnf_rowlatent_t* desc, const float* z, int n_particles, int n_latent_total, uint64_t seed,
+                    uint64_t offset, const uint64_t* offset_dev, int with_entropy, double* acc, void* workspace,
+                    size_t workspace_bytes, uint32_t* status, void* stream, const RowAdam& adam);
+
 }  // namespace mnf

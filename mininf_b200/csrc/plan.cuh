@@ -179,8 +179,20 @@ int run_step(mnf_plan* p, const mnf_buffers_t* b, const mnf_adam_t* adam, uint64
       desc.grad_loc = b->rows[i].grad_loc;
       desc.grad_scale = b->rows[i].grad_scale;
       desc.eps = b->rows[i].eps;
-      if (int rc = mnf_rowlatent_sweep(&desc, b->z, S, D, seed, offset, b->step_counter, with_entropy, b->acc,
-                                       b->workspace, b->workspace_bytes, b->status, stream))
+      RowAdam ra;
+      std::memset(&ra, 0, sizeof(ra));
+      if (adam != nullptr) {
+        // the N*p variational parameters are trained inside the sweep, element by element
+        const mnf_row_buffers_t& rb = b->rows[i];
+        ra.enabled = 1;
+        ra.lr = adam->lr; ra.beta1 = adam->beta1; ra.beta2 = adam->beta2; ra.eps = adam->eps;
+        ra.step = adam->step;
+        ra.loc_rw = rb.loc_rw; ra.raw_scale = rb.raw_scale;
+        ra.m_loc = rb.m_loc; ra.v_loc = rb.v_loc; ra.m_scale = rb.m_scale; ra.v_scale = rb.v_scale;
+        desc.loc = rb.loc_rw;
+      }
+      if (int rc = rowlatent_sweep(&desc, b->z, S, D, seed, offset, b->step_counter, with_entropy, b->acc,
+                                   b->workspace, b->workspace_bytes, b->status, stream, ra))
         return rc;
     }
   }
@@ -303,8 +315,6 @@ int mnf_elbo_fwd_bwd(mnf_plan_t* plan, const mnf_buffers_t* buffers, uint64_t se
 int mnf_svi_step(mnf_plan_t* plan, const mnf_buffers_t* buffers, const mnf_adam_t* adam, uint64_t seed, uint64_t offset,
                  uint32_t flags, void* stream) {
   if (!adam) return fail(MNF_E_INVALID, "mnf_svi_step: adam is null%s%s");
-  if (plan && !plan->rowlatent.empty())
-    return fail(MNF_E_UNSUPPORTED, "mnf_svi_step: plans with row latents update their parameters outside the fused step%s%s");
   return run_step(plan, buffers, adam, seed, offset, flags | MNF_STEP_ALL, (cudaStream_t)stream);
 }
 

@@ -12,12 +12,13 @@ bool host_link_has_latent(const mnf_link_t& L) { return L.a_lat >= 0 || L.b_lat 
 template <int SP, bool FULL>
 int launch_rowlatent_inst(const mnf_rowlatent_t& d, const float* z, int S, int D, int s_begin,
                           int first_pass, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
-                          int with_entropy, float* partial, uint32_t* status, int grid, cudaStream_t stream) {
+                          int with_entropy, float* partial, uint32_t* status, int grid, cudaStream_t stream,
+                          const RowAdam& adam) {
   auto kernel = rowlatent_kernel<SP, FULL>;
   const size_t smem = rowlatent_smem_bytes<SP>();
   MNF_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kernel<<<grid, kRowThreads, smem, stream>>>(d, z, S, D, s_begin, first_pass, seed, offset, offset_dev,
-                                               with_entropy, partial, status);
+                                               with_entropy, partial, status, adam);
   MNF_LAUNCH_CHECK();
   return MNF_OK;
 }
@@ -41,28 +42,38 @@ int rowlatent_resident(int* out) {
 template <int SP>
 int launch_rowlatent(const mnf_rowlatent_t& d, const float* z, int S, int D, int s_begin,
                      int first_pass, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
-                     int with_entropy, float* partial, uint32_t* status, int grid, cudaStream_t stream) {
+                     int with_entropy, float* partial, uint32_t* status, int grid, cudaStream_t stream,
+                     const RowAdam& adam) {
   if (S - s_begin >= SP)
     return launch_rowlatent_inst<SP, true>(d, z, S, D, s_begin, first_pass, seed, offset, offset_dev,
-                                           with_entropy, partial, status, grid, stream);
+                                           with_entropy, partial, status, grid, stream, adam);
   return launch_rowlatent_inst<SP, false>(d, z, S, D, s_begin, first_pass, seed, offset, offset_dev,
-                                          with_entropy, partial, status, grid, stream);
+                                          with_entropy, partial, status, grid, stream, adam);
 }
 
 
 }  // namespace
 
-extern "C" {
+namespace mnf {
 
-int mnf_rowlatent_sweep(const mnf_rowlatent_t* desc, const float* z, int n_particles,
-                        int n_latent_total, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
-                        int with_entropy, double* acc, void* workspace, size_t workspace_bytes,
-                        uint32_t* status, void* stream_) {
+// the sweep with an optional fused optimiser (mnf_svi_step, plan.cuh); `adam.enabled == 0`: gradients only
+int rowlatent_sweep(const mnf_rowlatent_t* desc, const float* z, int n_particles, int n_latent_total, uint64_t seed,
+                    uint64_t offset, const uint64_t* offset_dev, int with_entropy, double* acc, void* workspace,
+                    size_t workspace_bytes, uint32_t* status, void* stream_, const RowAdam& adam) {
   if (!desc || !z || !acc || !workspace || !status)
     return fail(MNF_E_INVALID, "mnf_rowlatent_sweep: null pointer%s%s");
   const mnf_rowlatent_t d = *desc;
   const int S = n_particles, D = n_latent_total;
-  if (!d.loc || !d.scale || !d.grad_loc || !d.grad_scale || d.n_rows < 0 || S <= 0)
+  if (adam.enabled) {
+    if (!adam.loc_rw || !adam.raw_scale || !adam.m_loc || !adam.v_loc || !adam.m_scale || !adam.v_scale || !adam.step)
+      return fail(MNF_E_INVALID, "mnf_svi_step: a row latent's optimiser buffers are missing%s%s");
+    if (S > 32 || d.eps != nullptr)
+      return fail(MNF_E_UNSUPPORTED, "mnf_svi_step: row latents are trained in the sweep only for single-pass "
+                                     "sweeps (at most 32 particles) with in-kernel draws%s%s");
+  } else if (!d.scale || !d.grad_loc || !d.grad_scale) {
+    return fail(MNF_E_INVALID, "mnf_rowlatent_sweep: bad descriptor%s%s");
+  }
+  if (!d.loc || d.n_rows < 0 || S <= 0)
     return fail(MNF_E_INVALID, "mnf_rowlatent_sweep: bad descriptor%s%s");
   if (d.p < 1 || d.p > 32)
     return fail(MNF_E_UNSUPPORTED, "mnf_rowlatent_sweep: 1..32 features per row in this build%s%s");
@@ -98,10 +109,10 @@ int mnf_rowlatent_sweep(const mnf_rowlatent_t* desc, const float* z, int n_parti
   float* partial = static_cast<float*>(workspace);
   for (int s_begin = 0, pass = 0; s_begin < S; s_begin += sp, ++pass) {
     int rc;
-    if (sp == 4) rc = launch_rowlatent<4>(d, z, S, D, s_begin, pass == 0, seed, offset, offset_dev, with_entropy, partial, status, grid, stream);
-    else if (sp == 8) rc = launch_rowlatent<8>(d, z, S, D, s_begin, pass == 0, seed, offset, offset_dev, with_entropy, partial, status, grid, stream);
-    else if (sp == 16) rc = launch_rowlatent<16>(d, z, S, D, s_begin, pass == 0, seed, offset, offset_dev, with_entropy, partial, status, grid, stream);
-    else rc = launch_rowlatent<32>(d, z, S, D, s_begin, pass == 0, seed, offset, offset_dev, with_entropy, partial, status, grid, stream);
+    if (sp == 4) rc = launch_rowlatent<4>(d, z, S, D, s_begin, pass == 0, seed, offset, offset_dev, with_entropy, partial, status, grid, stream, adam);
+    else if (sp == 8) rc = launch_rowlatent<8>(d, z, S, D, s_begin, pass == 0, seed, offset, offset_dev, with_entropy, partial, status, grid, stream, adam);
+    else if (sp == 16) rc = launch_rowlatent<16>(d, z, S, D, s_begin, pass == 0, seed, offset, offset_dev, with_entropy, partial, status, grid, stream, adam);
+    else rc = launch_rowlatent<32>(d, z, S, D, s_begin, pass == 0, seed, offset, offset_dev, with_entropy, partial, status, grid, stream, adam);
     if (rc) return rc;
   }
   // physical partial layout: 0 log-density, 1..p beta gradient (zeros without a response), then
@@ -117,6 +128,20 @@ int mnf_rowlatent_sweep(const mnf_rowlatent_t* desc, const float* z, int n_parti
   map.scalar_lat[3] = -1;                     // feature scale: constant
   map.scalar_lat[4] = (d.resp && d.resp_family == MNF_NORMAL) ? d.resp_scale.a_lat : -1;
   return launch_reduce(partial, grid, S, ncol, map, 1.0, D, acc, stream);
+}
+
+}  // namespace mnf
+
+extern "C" {
+
+int mnf_rowlatent_sweep(const mnf_rowlatent_t* desc, const float* z, int n_particles,
+                        int n_latent_total, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                        int with_entropy, double* acc, void* workspace, size_t workspace_bytes,
+                        uint32_t* status, void* stream_) {
+  RowAdam none;
+  std::memset(&none, 0, sizeof(none));
+  return rowlatent_sweep(desc, z, n_particles, n_latent_total, seed, offset, offset_dev, with_entropy, acc, workspace,
+                         workspace_bytes, status, stream_, none);
 }
 
 }  // extern "C"

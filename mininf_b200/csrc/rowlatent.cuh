@@ -76,7 +76,7 @@ template <int SP, bool FULL>
 __global__ void __launch_bounds__(kRowThreads)
 rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, int s_begin,
                  int first_pass, uint64_t seed, uint64_t offset, const uint64_t* __restrict__ offset_dev,
-                 int with_entropy, float* __restrict__ partial, uint32_t* __restrict__ status) {
+                 int with_entropy, float* __restrict__ partial, uint32_t* __restrict__ status, RowAdam adam) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   RowSmem<SP>& sm = *reinterpret_cast<RowSmem<SP>*>(smem_raw);
   constexpr int BS = RowSmem<SP>::kBetaStride;
@@ -146,13 +146,21 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
   const RowParticle rp_l = sm.par[sl];      // the particle this lane owns after the butterfly
   const bool lane_live = sl < s_count;
 
+  // fused optimiser: bias corrections of this step (torch.optim.Adam), the scale read through exp
+  float adam_step_size = 0.f, adam_inv_bc2_sqrt = 0.f;
+  if (adam.enabled) {
+    const double t = (double)(*adam.step + 1);
+    adam_step_size = (float)((double)adam.lr / (1.0 - pow((double)adam.beta1, t)));
+    adam_inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow((double)adam.beta2, t)));
+  }
+  const float* scale_src = adam.enabled ? adam.raw_scale : d.scale;
   const int64_t warp_global = (int64_t)blockIdx.x * kRowWarps + warp;
   const int64_t warps_total = (int64_t)gridDim.x * kRowWarps;
   // the next row's operands are fetched while the current row is being worked on
   float n_loc = prior_loc, n_scale = 1.f, n_x = 0.f, n_y = 0.f;
   if (warp_global < d.n_rows) {
     const int64_t e0 = warp_global * p + lane;
-    if (active) { n_loc = __ldg(d.loc + e0); n_scale = __ldg(d.scale + e0); }
+    if (active) { n_loc = d.loc[e0]; n_scale = scale_src[e0]; }
     if (active && has_feat) n_x = __ldg(d.feat + e0);
     if (has_resp) n_y = __ldg(d.resp + warp_global);
   }
@@ -160,7 +168,8 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
     const int64_t e = row * p + lane;
     // inactive lanes (feature index >= p) are inert: z == prior_loc == x, scale 0, beta 0
     const float loc = active ? n_loc : prior_loc;
-    const float scale_raw = active ? n_scale : 1.f;
+    const float raw_scale = n_scale;                       // unconstrained value (fused optimiser only)
+    const float scale_raw = active ? (adam.enabled ? expf(n_scale) : n_scale) : 1.f;
     const float scale = active ? scale_raw : 0.f;
     const float x = (active && has_feat) ? n_x : loc;
     const float y = n_y;
@@ -168,7 +177,9 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
       const int64_t row_n = row + warps_total;
       if (row_n < d.n_rows) {
         const int64_t en = row_n * p + lane;
-        if (active) { n_loc = __ldg(d.loc + en); n_scale = __ldg(d.scale + en); }
+        // plain loads: with the fused optimiser these arrays are written by this kernel (every
+        // element exactly once, by the thread that read it)
+        if (active) { n_loc = d.loc[en]; n_scale = scale_src[en]; }
         if (active && has_feat) n_x = __ldg(d.feat + en);
         if (has_resp) n_y = __ldg(d.resp + row_n);
       }
@@ -298,7 +309,17 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
       const float e_w = with_entropy ? 1.0f : 0.0f;
       const float out_l = -gl * invS;
       const float out_s = -(gs * invS + (first_pass ? __fdividef(e_w, scale) : 0.0f));
-      if (first_pass) { d.grad_loc[e] = out_l; d.grad_scale[e] = out_s; }
+      if (adam.enabled) {
+        // chain rule through scale = exp(raw): d/d raw = d/d scale * scale; then Adam, in place
+        const float g_l = out_l, g_s = out_s * scale;
+        const float m_l = adam.beta1 * adam.m_loc[e] + (1.0f - adam.beta1) * g_l;
+        const float v_l = adam.beta2 * adam.v_loc[e] + (1.0f - adam.beta2) * g_l * g_l;
+        const float m_s = adam.beta1 * adam.m_scale[e] + (1.0f - adam.beta1) * g_s;
+        const float v_s = adam.beta2 * adam.v_scale[e] + (1.0f - adam.beta2) * g_s * g_s;
+        adam.m_loc[e] = m_l; adam.v_loc[e] = v_l; adam.m_scale[e] = m_s; adam.v_scale[e] = v_s;
+        adam.loc_rw[e] = loc - adam_step_size * __fdividef(m_l, fmaf(sqrtf(v_l), adam_inv_bc2_sqrt, adam.eps));
+        adam.raw_scale[e] = raw_scale - adam_step_size * __fdividef(m_s, fmaf(sqrtf(v_s), adam_inv_bc2_sqrt, adam.eps));
+      } else if (first_pass) { d.grad_loc[e] = out_l; d.grad_scale[e] = out_s; }
       else { d.grad_loc[e] += out_l; d.grad_scale[e] += out_s; }
       // added to every particle's log-density column (only the mean over particles is used), so
       // every pass over a particle range accumulates it

@@ -320,12 +320,19 @@ __device__ inline void finalize_block(const mnf_latent_t* __restrict__ lat, int 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // last kernel of a step: the next replay of a captured step draws with the next call index
   if (step_counter != nullptr && threadIdx.x == 0) *step_counter += 1;
-  double bc1 = 1.0, bc2_sqrt = 1.0;
-  if (adam.raw != nullptr) {
-    const double t = (double)(*adam.step + 1);
-    bc1 = 1.0 - pow((double)adam.beta1, t);
-    bc2_sqrt = sqrt(1.0 - pow((double)adam.beta2, t));
+  // Adam's bias corrections of this step: one thread computes them (fp64 pow), everyone reads them
+  __shared__ double bias[2];
+  if (threadIdx.x == 0) {
+    bias[0] = 1.0;
+    bias[1] = 1.0;
+    if (adam.raw != nullptr) {
+      const double t = (double)(*adam.step + 1);
+      bias[0] = 1.0 - pow((double)adam.beta1, t);
+      bias[1] = sqrt(1.0 - pow((double)adam.beta2, t));
+    }
   }
+  __syncthreads();
+  const double bc1 = bias[0], bc2_sqrt = bias[1];
   const double invS = 1.0 / (double)S;
   double ent = 0.0;        // lane 0 of each warp: entropy of its columns
   bool nonfinite = false;
@@ -500,7 +507,7 @@ __device__ inline void xrank_gather_block(const XrankArgs& xr, double* __restric
 // Tail of a step in ONE launch: [cross-rank gather] -> [latent-valued (prior) sites] -> finalize
 // [-> Adam]. A single block: the work is O(S * D).
 // -------------------------------------------------------------------------------------------
-constexpr int kTailThreads = 1024;
+constexpr int kTailThreads = 512;    // 128 registers per thread for the fp64 implicit-gradient code
 
 __global__ void __launch_bounds__(kTailThreads)
 tail_kernel(XrankArgs xr, const mnf_site_t* __restrict__ global_sites, int n_global,

@@ -17,9 +17,9 @@ ABI_VERSION = 7
 NORMAL, GAMMA, BETA, BERNOULLI_PROBS, BERNOULLI_LOGITS, POISSON = range(6)
 T_ID, T_EXP = 0, 1
 T_FROZEN = 0x80
-DENSE_FP32, DENSE_TF32, DENSE_TF32_CLOSED_FORM = 0, 1, 2
+DENSE_FP32, DENSE_TF32, DENSE_TF32_CLOSED_FORM, DENSE_F16 = 0, 1, 2, 3
 SWEEP_CLOSED_FORM = 1
-ST_BAD_PARAM, ST_BAD_VALUE, ST_NONFINITE, ST_XRANK_TIMEOUT = 1, 2, 4, 8
+ST_BAD_PARAM, ST_BAD_VALUE, ST_NONFINITE, ST_XRANK_TIMEOUT, ST_RANGE = 1, 2, 4, 8, 16
 STEP_ENTROPY, STEP_PRE, STEP_POST = 1, 2, 4
 STEP_ALL = STEP_PRE | STEP_POST
 MAX_FUSED_SITES = 4
@@ -90,7 +90,9 @@ class PlanDesc(C.Structure):
 
 class RowBuffers(C.Structure):
     _fields_ = [("loc", C.c_void_p), ("scale", C.c_void_p), ("grad_loc", C.c_void_p),
-                ("grad_scale", C.c_void_p), ("eps", C.c_void_p)]
+                ("grad_scale", C.c_void_p), ("eps", C.c_void_p), ("loc_rw", C.c_void_p),
+                ("raw_scale", C.c_void_p), ("m_loc", C.c_void_p), ("v_loc", C.c_void_p),
+                ("m_scale", C.c_void_p), ("v_scale", C.c_void_p)]
 
 
 class Buffers(C.Structure):
@@ -108,6 +110,17 @@ class Adam(C.Structure):
         ("raw", C.c_void_p), ("transform", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
         ("constrained", C.c_void_p), ("step", C.c_void_p),
     ]
+
+
+class PredSite(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("family", C.c_int32), ("numel", C.c_int64), ("out_col", C.c_int32),
+        ("transform", C.c_int32), ("param", Link * 2), ("X", C.c_void_p), ("ldx", C.c_int64),
+        ("p", C.c_int32), ("theta_lat", C.c_int32), ("icpt_lat", C.c_int32), ("icpt_const", C.c_float),
+    ]
+
+
+PRED_DRAW, PRED_VALUE = 0, 1
 
 
 class DeviceInfo(C.Structure):
@@ -154,6 +167,8 @@ EXPORTS = {
     "mnf_xrank_create": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
     "mnf_xrank_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mnf_xrank_destroy": (C.c_int, [C.c_void_p]),
+    "mnf_predictive": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, C.c_uint64,
+                                 C.c_void_p, C.c_void_p]),
 }
 
 

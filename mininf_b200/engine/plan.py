@@ -74,6 +74,20 @@ def _f32(tensor: torch.Tensor, device: torch.device) -> torch.Tensor:
     return tensor.detach().to(torch.float32).contiguous()
 
 
+def _fits_f16_operands(X: torch.Tensor) -> bool:
+    """Whether a design matrix may be fed to the tensor cores as IEEE half precision: no entry at
+    or above 2^15 (the kernel re-checks that on every step, MNF_ST_RANGE), and no non-zero column
+    whose root-mean-square is below 2^-8 - below 2^-14 fp16 spacing is an absolute 2^-24, which
+    would no longer be small against such a column's entries (TF32 has the fp32 exponent range)."""
+    if X.numel() == 0:
+        return True
+    lo, hi = torch.aminmax(X)
+    if not (max(abs(float(lo)), abs(float(hi))) < 2.0 ** 15):      # also False for NaN
+        return False
+    rms = torch.linalg.vector_norm(X, dim=0) / X.shape[0] ** 0.5
+    return bool(((rms == 0) | (rms >= 2.0 ** -8)).all())
+
+
 def _has_fast_sweep(site: abi.Site) -> bool:
     first, second = site.param[0], site.param[1]
     return (site.family == abi.POISSON and first.transform == abi.T_EXP) or \
@@ -295,7 +309,10 @@ class Plan:
             return link
         tensor = torch.as_tensor(param)
         if tensor.numel() == 1 or bool((tensor == tensor.reshape(-1)[0]).all()):
-            self._folded_constant = self._folded_constant or tensor.numel() > 1
+            # an expanded scalar (all strides 0, e.g. `Normal(eta, 1.0)` after broadcast_all) IS a
+            # constant; a materialised tensor that merely holds equal values could differ in the next batch
+            expanded = all(stride == 0 or size == 1 for stride, size in zip(tensor.stride(), tensor.shape))
+            self._folded_constant = self._folded_constant or (tensor.numel() > 1 and not expanded)
             return abi.const_link(float(tensor.reshape(-1)[0]))
         data = _f32(tensor.expand(shape), self.device).reshape(-1)
         self.keepalive.append(data)
@@ -491,7 +508,19 @@ class Plan:
                                       "particles, or p a multiple of 4 with at most 128 particles, "
                                       "and 16-byte aligned rows")
         tf32 = abi.DENSE_TF32_CLOSED_FORM if self.closed_form else abi.DENSE_TF32
-        mode = tf32 if (self.dense_mode in ("auto", "tf32") and tf32_ok) else abi.DENSE_FP32
+        # fp16 operands (csrc/dense_th.cuh: the same 11-bit significand as TF32 at half the tensor-pipe
+        # cost) for the p = 64 / S <= 64 black-box shape, when the design matrix fits fp16's range
+        f16_shape = p == 64 and self.S <= 64 and not self.closed_form and X.data_ptr() % 16 == 0 and \
+            X.stride(0) % 4 == 0 and n < 2 ** 31
+        f16_ok = f16_shape and self.dense_mode in ("auto", "f16") and _fits_f16_operands(X)
+        if self.dense_mode == "f16" and not f16_ok:
+            raise NotImplementedError(f"{what}: the fp16-operand kernel needs p == 64, at most 64 particles, the "
+                                      "black-box estimator, 16-byte aligned rows and a design matrix inside fp16's "
+                                      "range (|x| < 2^15, no column with a root-mean-square below 2^-8)")
+        if f16_ok:
+            mode = abi.DENSE_F16
+        else:
+            mode = tf32 if (self.dense_mode in ("auto", "tf32") and tf32_ok) else abi.DENSE_FP32
         self.dense_sites.append((site, mode))
 
     # ------------------------------------------------------------------------------------------
@@ -712,6 +741,9 @@ def status_message(bits: int) -> str:
         parts.append("an observed value is not in the support of its distribution")
     if bits & abi.ST_NONFINITE:
         parts.append("the loss or a gradient is not finite")
+    if bits & abi.ST_RANGE:
+        parts.append("a design-matrix entry is NaN/Inf or at least 2^15: outside the range of the fp16-operand "
+                     "kernel (use dense_precision='tf32')")
     if bits & abi.ST_XRANK_TIMEOUT:
         parts.append("a peer rank did not deliver its partial sums in time (sharded evaluation)")
     return "; ".join(parts)

@@ -204,8 +204,12 @@ class EvidenceLowerBoundLoss(nn.Module):
 
     Args (all optional, all beyond the reference's zero-argument constructor):
         n_particles: reparameterised draws averaged per evaluation (default 1 = the reference).
-        dense_precision: ``"auto"`` (tcgen05 TF32 kernel where its shape constraints hold, fp32
-            SIMT otherwise), ``"tf32"`` (require it) or ``"fp32"``.
+        dense_precision: operand format of dense-link sites (``X @ theta``) on the tensor cores.
+            ``"auto"``: fp16 operands (11-bit significand like TF32, half the tensor-pipe time)
+            for p = 64 / S <= 64 when the design matrix fits fp16's range, else TF32 operands
+            where a tcgen05 kernel covers the shape, else fp32 SIMT; ``"f16"`` / ``"tf32"`` require
+            that format, ``"fp32"`` forces the exact SIMT kernel. In every tensor-core mode theta
+            enters as hi + lo pairs (22 bits) and accumulation is fp32.
         cache: reuse the traced plan while the model, conditioned tensors and approximation
             structure are unchanged (the reference re-runs the model every step).
         process_group: ``True`` / a ``torch.distributed`` group to treat every observed site as
@@ -229,8 +233,8 @@ class EvidenceLowerBoundLoss(nn.Module):
                  process_group: Any = None, check: str = "lazy", closed_form: bool = False,
                  reduce: str = "peer") -> None:
         super().__init__()
-        if dense_precision not in ("auto", "tf32", "fp32"):
-            raise ValueError("dense_precision must be 'auto', 'tf32' or 'fp32'")
+        if dense_precision not in ("auto", "f16", "tf32", "fp32"):
+            raise ValueError("dense_precision must be 'auto', 'f16', 'tf32' or 'fp32'")
         if check not in ("lazy", "sync", "off"):
             raise ValueError("check must be 'lazy', 'sync' or 'off'")
         if reduce not in ("peer", "nccl"):
@@ -505,6 +509,24 @@ _PARAMETER_NAMES = {distributions.Normal: ("loc", "scale"), distributions.Gamma:
                     distributions.Beta: ("concentration1", "concentration0")}
 
 
+def _transform_code(transform: distributions.Transform) -> Optional[int]:
+    """MNF_T_* code of a constraint transform, recognised by what it computes (torch wraps the
+    transform of `positive` as ComposeTransform([ExpTransform(), AffineTransform(0, 1)]))."""
+    from .engine import abi
+    probe = torch.tensor([-1.5, 0.0, 0.75, 2.0], dtype=torch.float64)
+    try:
+        image = transform(probe)
+    except Exception:  # noqa: BLE001  shape-changing transforms (simplex, cholesky, ...)
+        return None
+    if image.shape != probe.shape:
+        return None
+    if torch.equal(image, probe):
+        return abi.T_ID
+    if torch.allclose(image, probe.exp(), rtol=1e-12, atol=0.0):
+        return abi.T_EXP
+    return None
+
+
 class FusedSVIStep:
     """The whole SVI step of README.md:63-69 - ``zero_grad``, loss, ``backward``,
     ``optimizer.step()`` - as ONE native call (``mnf_svi_step``, include/mininf_b200.h) that
@@ -541,9 +563,10 @@ class FusedSVIStep:
         loss_module(model, factors)
         loss_module.synchronize()
         plan = self.plan = loss_module.last_plan
-        if plan.row_latents:
-            raise NotImplementedError("FusedSVIStep does not cover per-observation latents; use "
-                                      "GraphedStep with a torch optimizer for those models")
+        if plan.row_latents and (plan.S > 32 or share_with is not None):
+            raise NotImplementedError("FusedSVIStep trains per-observation latents inside the row-latent sweep for "
+                                      "single-pass sweeps only (at most 32 particles, one resident data set); use "
+                                      "GraphedStep with a torch optimizer otherwise")
         D, device = plan.D, plan.device
         raw = torch.zeros(2 * D, device=device)
         codes = torch.zeros(2 * D, dtype=torch.uint8)
@@ -560,11 +583,8 @@ class FusedSVIStep:
                 if name in module.distribution_parameters:
                     parameter = module.distribution_parameters[name]
                     transform = distributions.transform_to(module.distribution_cls.arg_constraints[name])
-                    if _is_identity_transform(transform):
-                        code = abi.T_ID
-                    elif isinstance(transform, distributions.ExpTransform):
-                        code = abi.T_EXP
-                    else:
+                    code = _transform_code(transform)
+                    if code is None:
                         raise NotImplementedError(f"FusedSVIStep: transform {transform} of '{spec.name}.{name}'")
                     if parameter.numel() != spec.numel:
                         raise NotImplementedError(f"FusedSVIStep: '{spec.name}.{name}' is broadcast over the site; "
@@ -589,6 +609,26 @@ class FusedSVIStep:
         self.adam = abi.Adam(lr=lr, beta1=betas[0], beta2=betas[1], eps=eps, raw=raw.data_ptr(),
                              transform=self.codes.data_ptr(), m=self.m.data_ptr(), v=self.v.data_ptr(),
                              constrained=plan.P.data_ptr(), step=self.steps.data_ptr())
+        # per-observation ("row") latents: the N*p location / log-scale parameters are read, updated
+        # and written back by the row-latent sweep itself (csrc/rowlatent.cuh, RowAdam)
+        self._row_state: List[torch.Tensor] = []
+        for index, spec in enumerate(plan.row_latents):
+            module = self.modules[spec.name]
+            if module.distribution_cls is not distributions.Normal or \
+                    set(module.distribution_parameters) != {"loc", "scale"}:
+                raise NotImplementedError(f"FusedSVIStep: row latent '{spec.name}' needs a Normal approximation with "
+                                          "trainable loc and scale")
+            loc, raw_scale = module.distribution_parameters["loc"], module.distribution_parameters["scale"]
+            for parameter in (loc, raw_scale):
+                if tuple(parameter.shape) != tuple(spec.shape) or not parameter.is_contiguous():
+                    raise NotImplementedError(f"FusedSVIStep: parameters of '{spec.name}' must be contiguous and have "
+                                              "the site's shape")
+            moments = [torch.zeros_like(loc) for _ in range(4)]
+            self._row_state += moments
+            row = plan._row_buffers[index]
+            row.loc, row.loc_rw, row.raw_scale = loc.data_ptr(), loc.data_ptr(), raw_scale.data_ptr()
+            row.scale, row.grad_loc, row.grad_scale, row.eps = None, None, None, None
+            row.m_loc, row.v_loc, row.m_scale, row.v_scale = (t.data_ptr() for t in moments)
         self.loss = plan.out[0]
         generator = torch.cuda.default_generators[device.index or 0]
         self._seed = (loss_module._shared_seed if loss_module._shared_seed is not None

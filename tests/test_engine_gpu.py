@@ -75,11 +75,15 @@ def test_regression_against_oracle(n, p, S, sigma, precision):
     expected = elbo.neg_elbo(cpu.model, cpu.data, approx_c, noise, S)
     expected.backward()
     loss, leaves, module = engine_eval(gpu, {k: v.to(DEV) for k, v in noise.items()}, S, precision)
-    tf32 = module.last_plan.dense_sites[0][1] == abi.DENSE_TF32
-    assert tf32 == (precision == "auto" and p == 64)
-    assert abs(float(loss) - float(expected)) <= (2e-4 if tf32 else 1e-5) * abs(float(expected))
+    mode = module.last_plan.dense_sites[0][1]
+    # "auto": fp16 operands for p = 64 with at most 64 particles, the fp32 kernel for the other shapes here
+    assert mode == (abi.DENSE_F16 if precision == "auto" and p == 64 else abi.DENSE_FP32)
+    tensor_core = mode != abi.DENSE_FP32
+    # tensor-core operands at a few hundred rows: what is left is the unbiased 11-bit rounding of X,
+    # which shrinks as 1/sqrt(N) (1e-5 / 1e-4 from ~2e5 rows on, see the fp64-oracle tests below)
+    assert abs(float(loss) - float(expected)) <= (1e-4 if tensor_core else 1e-5) * abs(float(expected))
     for key, leaf in leaves.items():
-        assert rel(leaf.grad.cpu().numpy(), leaves_c[key].grad.numpy()) < (5e-3 if tf32 else 1e-4), key
+        assert rel(leaf.grad.cpu().numpy(), leaves_c[key].grad.numpy()) < (3e-3 if tensor_core else 1e-4), key
 
 
 def test_tf32_error_shrinks_with_rows():
@@ -224,8 +228,8 @@ def test_wide_tensor_core_kernel_against_oracle(n, p, S, intercept):
 @pytest.mark.parametrize("p,S", [(128, 24), (64, 64)])
 def test_tensor_core_kernels_normal_and_poisson_families_with_intercept(p, S):
     """The Normal (latent sigma, exp link) and Poisson (exp link) epilogues with a latent plus
-    constant intercept and a row mask, dense_tcr.cuh (p = 128) and dense_tc.cuh (p = 64), against
-    the exact fp32 kernel on the same inputs (raw C-ABI, 20000 rows)."""
+    constant intercept and a row mask, dense_tcr.cuh (p = 128), dense_tc.cuh and the fp16-operand
+    dense_th.cuh (p = 64), against the exact fp32 kernel on the same inputs (raw C-ABI, 20000 rows)."""
     import ctypes
     lib = abi.load()
     torch.manual_seed(9)
@@ -246,19 +250,20 @@ def test_tensor_core_kernels_normal_and_poisson_families_with_intercept(p, S):
                              mask=mask.data_ptr(), theta_lat=0, icpt_lat=p, icpt_const=0.25, reserved=0,
                              scale=scale, weight=3.0)
         results = []
-        for mode in (abi.DENSE_FP32, abi.DENSE_TF32):
+        for mode in (abi.DENSE_FP32, abi.DENSE_TF32) + ((abi.DENSE_F16,) if p == 64 else ()):
             acc = torch.zeros(S, D + 1, device=DEV, dtype=torch.float64)
             lib.call("mnf_dense_sweep", ctypes.byref(site), mode, z.data_ptr(), S, D, acc.data_ptr(), ws.data_ptr(),
                      ws_bytes, status.data_ptr(), stream)
             torch.cuda.synchronize()
             results.append(acc.cpu().numpy())
-        exact, fast = results
+        exact = results[0]
         assert int(status.item()) == 0
-        assert np.max(np.abs(fast[:, 0] - exact[:, 0]) / np.abs(exact[:, 0])) < 2e-4, family
-        assert rel(fast[:, 1:1 + p], exact[:, 1:1 + p]) < 5e-3, family          # theta
-        assert rel(fast[:, 1 + p], exact[:, 1 + p]) < 5e-3, family              # intercept
-        if family == abi.NORMAL:
-            assert rel(fast[:, 2 + p], exact[:, 2 + p]) < 1e-3                    # log-sigma
+        for fast in results[1:]:
+            assert np.max(np.abs(fast[:, 0] - exact[:, 0]) / np.abs(exact[:, 0])) < 2e-4, family
+            assert rel(fast[:, 1:1 + p], exact[:, 1:1 + p]) < 5e-3, family          # theta
+            assert rel(fast[:, 1 + p], exact[:, 1 + p]) < 5e-3, family              # intercept
+            if family == abi.NORMAL:
+                assert rel(fast[:, 2 + p], exact[:, 2 + p]) < 1e-3                    # log-sigma
 
 
 @pytest.mark.parametrize("batch_rows", [400, 1, 4097])
@@ -593,17 +598,18 @@ def _evaluate(model, X, y, noise, precision, S=64):
 
 
 def test_full_size_tensor_core_kernel_agrees_with_exact_kernel():
-    """N = 1e8, p = 64, S = 64 (BASELINE.json config[1]): the tcgen05 TF32 path against the exact
-    fp32 SIMT kernel (itself pinned to the reference at small N): the north-star 1e-5 on the loss,
-    1e-4 relative L2 on gradients."""
+    """N = 1e8, p = 64, S = 64 (BASELINE.json config[1]): the tcgen05 paths (fp16 operands - the
+    default - and TF32 operands) against the exact fp32 SIMT kernel (itself pinned to the reference
+    at small N): the north-star 1e-5 on the loss, 1e-4 relative L2 on gradients."""
     n = 100_000_000
     model, X, y = _bench_regression(n, 123)
     noise = torch.randn(64, 64, generator=torch.Generator(device=DEV).manual_seed(5), device=DEV)
-    loss_tc, gl_tc, gs_tc = _evaluate(model, X, y, noise, "tf32")
     loss_ex, gl_ex, gs_ex = _evaluate(model, X, y, noise, "fp32")
-    assert abs(loss_tc - loss_ex) <= 1e-5 * abs(loss_ex)
-    assert float((gl_tc - gl_ex).norm() / gl_ex.norm()) < 1e-4
-    assert float((gs_tc - gs_ex).norm() / gs_ex.norm()) < 1e-4
+    for precision in ("auto", "tf32"):
+        loss_tc, gl_tc, gs_tc = _evaluate(model, X, y, noise, precision)
+        assert abs(loss_tc - loss_ex) <= 1e-5 * abs(loss_ex), precision
+        assert float((gl_tc - gl_ex).norm() / gl_ex.norm()) < 1e-4, precision
+        assert float((gs_tc - gs_ex).norm() / gs_ex.norm()) < 1e-4, precision
     # integer-exact row accounting at full size: every row is live exactly once
     out = torch.zeros(2, dtype=torch.int64, device=DEV)
     ones = torch.ones(n, device=DEV)
@@ -622,10 +628,12 @@ def _fp64_oracle(config, noise, S):
     return float(expected), {k: v.grad.numpy() for k, v in leaves64.items()}
 
 
+@pytest.mark.parametrize("precision", ["f16", "tf32"])
 @pytest.mark.parametrize("rows", [200_000, 2_000_000])
-def test_c2_black_box_kernel_meets_the_north_star_tolerance_against_the_fp64_oracle(rows):
+def test_c2_black_box_kernel_meets_the_north_star_tolerance_against_the_fp64_oracle(rows, precision):
     """BASELINE.json config[1] (p = 64, S = 64) through the per-(particle, observation) tcgen05
-    kernel (csrc/dense_tc.cuh, the default `closed_form=False` path) on seeded row subsamples of
+    kernels (csrc/dense_th.cuh with fp16 operands - the default - and csrc/dense_tc.cuh with TF32
+    operands; the default `closed_form=False` path) on seeded row subsamples of
     the benchmark's data recipe, against a float64 evaluation of the reference algorithm: 1e-5
     relative on the loss (the north-star tolerance), 1e-4 relative L2 on the gradients. The error
     that is left is the unbiased TF32 rounding of X (it shrinks as 1/sqrt(N)); theta enters the
@@ -635,12 +643,13 @@ def test_c2_black_box_kernel_meets_the_north_star_tolerance_against_the_fp64_ora
     config = configs.regression(rows, 64, device=DEV)          # chunk-seeded recipe, device generator
     approx, leaves = config.approximation(device=DEV)
     noise = {name: elbo.draw_noise(dist, S) for name, dist in config.approximation()[0].items()}
-    module = mininf.nn.EvidenceLowerBoundLoss(S, dense_precision="tf32", check="sync")
+    module = mininf.nn.EvidenceLowerBoundLoss(S, dense_precision=precision, check="sync")
     loss = module(mininf.condition(lambda: config.model(mininf), **config.data), approx,
                   _noise={k: v.to(DEV) for k, v in noise.items()})
     loss.backward()
     (site, mode), = module.last_plan.dense_sites
-    assert mode == abi.DENSE_TF32 and abi.load().raw("mnf_dense_tf32_kernel")(site.family, site.p, S) == 1
+    assert mode == (abi.DENSE_F16 if precision == "f16" else abi.DENSE_TF32)
+    assert abi.load().raw("mnf_dense_tf32_kernel")(site.family, site.p, S) == 1
     expected, grads64 = _fp64_oracle(config, noise, S)
     assert abs(float(loss) - expected) <= 1e-5 * abs(expected)
     for key, leaf in leaves.items():
@@ -1123,48 +1132,68 @@ def test_a_step_is_one_native_call_with_few_kernels():
     assert module.last_plan.gpu_launches_per_step == 4
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_fused_svi_step_matches_the_torch_adam_loop(graph):
-    """FusedSVIStep (mnf_svi_step: transforms, ELBO + gradient kernels, chain rule and Adam inside
-    the engine) against the reference-style loop `zero_grad; loss.backward(); Adam.step()` on the
-    same model with the same Philox draws: parameters after 25 steps agree to fp32 round-off."""
+def _svi_case(name):
     from torch.distributions import Gamma, Normal
     PD = mininf.nn.ParameterizedDistribution
-    config = configs.regression(3000, 64, sigma_latent=True, device=DEV, gen_device="cpu")
+
+    def scalar(value):
+        return torch.tensor(value, device=DEV)
+
+    if name == "regression":
+        config = configs.regression(3000, 64, sigma_latent=True, device=DEV, gen_device="cpu")
+
+        def modules():
+            return {"theta": PD(Normal, loc=torch.zeros(64, device=DEV), scale=0.1 * torch.ones(64, device=DEV)),
+                    "sigma": PD(Gamma, concentration=scalar(2.0), rate=scalar(2.0))}
+    else:       # per-observation latents (config C4): 2000 x 16 location / scale parameters
+        config = configs.feature_uncertainty(2000, 16, device=DEV, gen_device="cpu")
+
+        def modules():
+            return {"population_scale": PD(Gamma, concentration=scalar(2.0), rate=scalar(2.0)),
+                    "z": PD(Normal, loc=config.data["x"].clone(), scale=torch.ones(2000, 16, device=DEV)),
+                    "intercept": PD(Normal, loc=scalar(0.1), scale=scalar(0.2)),
+                    "slope": PD(Normal, loc=torch.zeros(16, device=DEV), scale=0.2 * torch.ones(16, device=DEV))}
+    return config, modules
+
+
+@pytest.mark.parametrize("case", ["regression", "features"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_svi_step_matches_the_torch_adam_loop(graph, case):
+    """FusedSVIStep (mnf_svi_step: transforms, ELBO + gradient kernels, chain rule and Adam inside
+    the engine; for per-observation latents inside the row-latent sweep itself) against the
+    reference-style loop `zero_grad; loss.backward(); Adam.step()` on the same model with the same
+    Philox draws: losses and parameters after 25 steps agree to fp32 round-off."""
+    config, modules = _svi_case(case)
     conditioned = mininf.condition(lambda: config.model(mininf), **config.data)
-
-    def modules():
-        return {"theta": PD(Normal, loc=torch.zeros(64, device=DEV), scale=0.1 * torch.ones(64, device=DEV)),
-                "sigma": PD(Gamma, concentration=torch.tensor(2.0, device=DEV), rate=torch.tensor(2.0, device=DEV))}
-
-    steps, lr = 25, 0.02
+    steps, lr, S = 25, 0.02, 8
     torch.manual_seed(7)
     fused_modules = modules()
-    fused_loss = mininf.nn.EvidenceLowerBoundLoss(8, dense_precision="fp32")
+    fused_loss = mininf.nn.EvidenceLowerBoundLoss(S, dense_precision="fp32")
     fused = mininf.nn.FusedSVIStep(fused_loss, conditioned, fused_modules, lr=lr, graph=graph)
     first_offset, seed = fused._offset, fused._seed
     losses = [float(fused()) for _ in range(steps)]
     fused_loss.synchronize()
-    assert fused.kernels_per_step == 4 and int(fused.steps) == steps + (2 if graph else 0)
+    warm = 2 if graph else 0              # graph capture ran two warm-up steps that also updated the parameters
+    assert int(fused.steps) == steps + warm
+    assert fused.kernels_per_step == 4      # draws, sweep, its partial reduction, tail
 
     # the same loop with torch: replay the fused step's Philox stream through the plan directly
+    from mininf_b200.engine.plan import latent_parameters
+    from mininf_b200.nn import _EngineFunction
     torch.manual_seed(7)
     ref_modules = modules()
     optimizer = torch.optim.Adam([p for m in ref_modules.values() for p in m.parameters()], lr=lr)
-    ref_loss = mininf.nn.EvidenceLowerBoundLoss(8, dense_precision="fp32", check="off")
+    ref_loss = mininf.nn.EvidenceLowerBoundLoss(S, dense_precision="fp32", check="off")
     reference_losses = []
-    warm = 2 if graph else 0              # graph capture ran two warm-up steps that also updated the parameters
     for step in range(steps + warm):
         optimizer.zero_grad()
         approx = {name: module() for name, module in ref_modules.items()}
         plan = ref_loss._plan_for(conditioned, approx)
-        from mininf_b200.nn import _EngineFunction
-        from mininf_b200.engine.plan import latent_parameters
         params = []
         for spec in plan.all_latents:
             _, p0, p1 = latent_parameters(approx[spec.name])
-            params += [p0.expand(spec.shape if len(spec.shape) else torch.Size([])),
-                       p1.expand(spec.shape if len(spec.shape) else torch.Size([]))]
+            shape = spec.shape if len(spec.shape) else torch.Size([])
+            params += [p0.expand(shape), p1.expand(shape)]
         loss = _EngineFunction.apply(ref_loss, plan, None, {}, seed, first_offset + step, None, True, False, *params)
         loss.backward()
         optimizer.step()
@@ -1173,7 +1202,7 @@ def test_fused_svi_step_matches_the_torch_adam_loop(graph):
     for name in ref_modules:
         for key, parameter in ref_modules[name].distribution_parameters.items():
             np.testing.assert_allclose(fused_modules[name].distribution_parameters[key].detach().cpu().numpy(),
-                                       parameter.detach().cpu().numpy(), rtol=2e-4, atol=2e-6, err_msg=f"{name}.{key}")
+                                       parameter.detach().cpu().numpy(), rtol=5e-4, atol=5e-6, err_msg=f"{name}.{key}")
 
 
 def test_c_program_runs_a_step_from_host_tables_without_python(tmp_path):
@@ -1191,3 +1220,130 @@ def test_c_program_runs_a_step_from_host_tables_without_python(tmp_path):
     result = subprocess.run([str(binary)], capture_output=True, text=True)
     assert result.returncode == 0, result.stdout + result.stderr
     assert "OK" in result.stdout
+
+
+def test_fp16_operand_kernel_reports_entries_outside_its_range():
+    """MNF_DENSE_F16 is selected per plan only when the design matrix fits fp16; a plan REBOUND to a
+    batch with an entry at or above 2^15 is caught by the kernel's per-step check (MNF_ST_RANGE)."""
+    torch.manual_seed(1)
+    n, p, S = 4096, 64, 8
+    config = configs.regression(n, p, device=DEV, gen_device="cpu")
+    approx, _ = config.approximation(device=DEV)
+    module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+    model = lambda: config.model(mininf)  # noqa: E731
+    assert torch.isfinite(module(mininf.condition(model, **config.data), approx))
+    assert module.last_plan.dense_sites[0][1] == abi.DENSE_F16
+    other = {k: v.clone() for k, v in config.data.items()}
+    other["X"][17, 3] = 1.0e5
+    with pytest.raises(ValueError, match="fp16"):
+        module(mininf.condition(model, **other), approx)          # same layout: the plan is rebound
+    # traced from scratch on such data the TF32 kernel is chosen instead
+    fresh = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+    assert torch.isfinite(fresh(mininf.condition(model, **other), approx))
+    assert fresh.last_plan.dense_sites[0][1] == abi.DENSE_TF32
+
+
+# ---------------------------------------------------------------------------------------------
+# batched posterior predictive: broadcast_samples on the site table (engine/predictive.py, csrc/predict.cuh)
+# ---------------------------------------------------------------------------------------------
+def test_broadcast_samples_on_the_device_matches_the_reference_contract():
+    """tests/test_core.py:324-333 of the reference on CUDA samples: deterministic `value` sites are
+    evaluated per sample, given samples pass through, conditioned values are replicated."""
+    def model():
+        a = mininf.value("a")
+        x = mininf.sample("x", torch.distributions.Normal(0, 1))
+        assert x.shape == ()
+        mininf.value("y", x + a)
+
+    x = torch.randn(7, device=DEV)
+    states = mininf.broadcast_samples(mininf.condition(model, a=1.3), x=x)
+    assert isinstance(states, mininf.State) and set(states) == {"a", "x", "y"}
+    torch.testing.assert_close(states["y"], x + 1.3)
+    torch.testing.assert_close(states["x"], x)
+    assert states["a"].shape == (7,) and bool((states["a"] == 1.3).all())
+
+
+def test_broadcast_samples_predictive_example_in_one_launch():
+    """examples/predictive.md:22-38 and :82-86: quadratic regression, posterior samples of theta and
+    sigma broadcast over the model conditioned on new covariates. The device path (one trace, one
+    launch) must give the per-sample loop's results: `prediction` exactly (it is deterministic), the
+    drawn `y` in distribution, every site with a leading batch dimension."""
+    from torch.distributions.constraints import nonnegative_integer
+
+    def model():
+        n = mininf.value("n", 30, support=nonnegative_integer)
+        p = mininf.value("p", 3, support=nonnegative_integer)
+        x = mininf.sample("x", torch.distributions.Normal(0, 1), n)
+        X = mininf.value("X", x[:, None] ** torch.arange(p, device=x.device))
+        theta = mininf.sample("theta", torch.distributions.Normal(0, 1), p)
+        prediction = mininf.value("prediction", X @ theta)
+        sigma = mininf.sample("sigma", torch.distributions.Gamma(2, 2))
+        mininf.sample("y", torch.distributions.Normal(prediction, sigma))
+
+    torch.manual_seed(3)
+    B, nlin = 5000, 101
+    theta = torch.randn(B, 3)
+    sigma = 0.2 + torch.rand(B)
+    lin = torch.linspace(-2.0, 2.0, nlin)
+    host = mininf.broadcast_samples(mininf.condition(model, n=nlin, x=lin), theta=theta[:50], sigma=sigma[:50])
+    device = mininf.broadcast_samples(mininf.condition(model, n=nlin, x=lin.to(DEV)), theta=theta.to(DEV), sigma=sigma.to(DEV))
+    assert set(device) == set(host) == {"n", "p", "x", "X", "theta", "prediction", "sigma", "y"}
+    for key in host:
+        assert tuple(device[key].shape) == (B,) + tuple(host[key].shape[1:]), key
+    torch.testing.assert_close(device["prediction"][:50].cpu(), host["prediction"], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(device["x"][7].cpu(), lin)
+    assert int(device["n"][0]) == nlin and device["X"].shape == (B, nlin, 3)
+    standardized = ((device["y"] - device["prediction"]) / device["sigma"][:, None]).double()
+    assert abs(float(standardized.mean())) < 5.0 / (B * nlin) ** 0.5
+    assert abs(float(standardized.var()) - 1.0) < 0.01
+    per_sample_spread = (device["y"] - device["prediction"]).std(dim=1)
+    assert float((per_sample_spread / device["sigma"] - 1).abs().mean()) < 0.08      # each sample's own sigma
+
+
+@pytest.mark.parametrize("family", ["poisson_small", "poisson_large", "bernoulli_logits", "bernoulli_probs", "gamma", "beta"])
+def test_predictive_sampler_families_have_the_right_moments(family):
+    """Every device sampler of csrc/predict.cuh against the analytic mean and variance, with
+    parameters that depend on the broadcast samples (so the link is exercised too)."""
+    from torch.distributions import Bernoulli, Beta, Gamma, Normal, Poisson
+    B, n = 4000, 64
+    torch.manual_seed(4)
+    a = (0.2 * torch.randn(B)).to(DEV)
+
+    def model():
+        a_ = mininf.sample("a", Normal(0, 1))
+        if family == "poisson_small":
+            mininf.sample("y", Poisson((1.0 + a_).exp()), n)
+        elif family == "poisson_large":
+            mininf.sample("y", Poisson((4.0 + a_).exp()), n)
+        elif family == "bernoulli_logits":
+            mininf.sample("y", Bernoulli(logits=0.5 + a_), n)
+        elif family == "bernoulli_probs":
+            mininf.sample("y", Bernoulli(probs=(a_ - 1.0).exp()), n)
+        elif family == "gamma":
+            mininf.sample("y", Gamma((1.0 + a_).exp(), 2.0), n)
+        else:       # torch's Beta stacks its concentrations (no link through that): constant parameters
+            mininf.sample("y", Beta(2.0, 3.0), n)
+
+    y = mininf.broadcast_samples(model, a=a)["y"].double()
+    assert y.shape == (B, n)
+    a64 = a.double()
+    if family.startswith("poisson"):
+        rate = ((1.0 if family == "poisson_small" else 4.0) + a64).exp()
+        mean, var = rate, rate
+        assert bool((y == y.floor()).all()) and bool((y >= 0).all())
+    elif family.startswith("bernoulli"):
+        prob = torch.sigmoid(0.5 + a64) if family == "bernoulli_logits" else (a64 - 1.0).exp()
+        mean, var = prob, prob * (1 - prob)
+        assert bool(((y == 0) | (y == 1)).all())
+    elif family == "gamma":
+        conc = (1.0 + a64).exp()
+        mean, var = conc / 2.0, conc / 4.0
+    else:
+        c1, c0 = torch.full_like(a64, 2.0), torch.full_like(a64, 3.0)
+        mean = c1 / (c1 + c0)
+        var = c1 * c0 / ((c1 + c0) ** 2 * (c1 + c0 + 1))
+    z = (y.mean(1) - mean) / (var / n).sqrt()              # per-sample standardized mean: ~ N(0, 1)
+    assert abs(float(z.mean())) < 5.0 / B ** 0.5
+    assert abs(float(z.var()) - 1.0) < 0.15
+    ratio = float((y.var(1, unbiased=True) / var).mean())   # variance of the draws themselves
+    assert abs(ratio - 1.0) < 0.05

@@ -34,7 +34,16 @@ def test_regression_lowers_to_one_dense_site_and_two_priors():
     plan = Plan(sites, specs, 64, CPU, dense_mode="auto", dry_run=True)
     assert plan.D == 65 and len(plan.dense_sites) == 1 and not plan.sweep_groups
     site, mode = plan.dense_sites[0]
-    assert mode == abi.DENSE_TF32 and site.family == abi.NORMAL and (site.p, site.n_rows) == (64, 3000)
+    # p = 64, S <= 64, N(0, 1) features: the fp16-operand tcgen05 kernel; "tf32" keeps TF32 operands
+    assert mode == abi.DENSE_F16 and site.family == abi.NORMAL and (site.p, site.n_rows) == (64, 3000)
+    assert Plan(sites, specs, 64, CPU, dense_mode="tf32", dry_run=True).dense_sites[0][1] == abi.DENSE_TF32
+    # a design matrix outside fp16's range falls back to TF32 operands; asking for fp16 raises
+    huge = dict(config.data, X=config.data["X"] * 1e6)
+    far_sites, _ = trace(lambda: config.model(mininf),
+                         {"theta": (abi.NORMAL, torch.randn(64)), "sigma": (abi.GAMMA, torch.tensor(1.3))}, huge)
+    assert Plan(far_sites, specs, 64, CPU, dry_run=True).dense_sites[0][1] == abi.DENSE_TF32
+    with pytest.raises(NotImplementedError, match="fp16"):
+        Plan(far_sites, specs, 64, CPU, dense_mode="f16", dry_run=True)
     assert site.theta_lat == 0 and site.icpt_lat == -1 and site.scale.a_lat == 64 and site.weight == 1.0
     assert plan.small_global[1] == 2 and plan.small_observed is None
     # the closed-form switch selects the Gram-statistics mode of the same site
@@ -173,7 +182,7 @@ def test_plan_rebinds_dense_site_to_a_new_batch():
     plan.bind_sources(_leaves(first.data))
     assert plan.rebindable
     site, mode = plan.dense_sites[0]
-    assert mode == abi.DENSE_TF32 and site.X == first.data["X"].data_ptr() and site.y == first.data["y"].data_ptr()
+    assert mode in (abi.DENSE_F16, abi.DENSE_TF32) and site.X == first.data["X"].data_ptr() and site.y == first.data["y"].data_ptr()
     assert plan.rebind(_leaves(second.data))
     assert site.X == second.data["X"].data_ptr() and site.y == second.data["y"].data_ptr()
     # a batch whose rows are not 16-byte aligned cannot feed the TMA path: the caller re-lowers

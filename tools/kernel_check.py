@@ -72,7 +72,7 @@ loss_ref = -((ll + prior_lp).mean() + ent)
 loss_ref.backward()
 ref = torch.cat([loss_ref.detach()[None], loc64.grad, scale64.grad])
 
-for name, mode in (("fp32", abi.DENSE_FP32), ("tf32", abi.DENSE_TF32)):
+for name, mode in (("fp32", abi.DENSE_FP32), ("tf32", abi.DENSE_TF32), ("f16", 3)):
     status.zero_()
     try:
         step(mode)
@@ -91,13 +91,13 @@ for name, mode in (("fp32", abi.DENSE_FP32), ("tf32", abi.DENSE_TF32)):
           f"scale rel-l2 {gs:.3e} | per-particle ll max rel {ll_err:.3e} | status {status.item()}")
 
 # timing
-for name, mode in (("fp32", abi.DENSE_FP32), ("tf32", abi.DENSE_TF32)):
+for name, mode in (("fp32", abi.DENSE_FP32), ("tf32", abi.DENSE_TF32), ("f16", 3)):
     try:
         for _ in range(3):
             step(mode)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 10 if mode == abi.DENSE_TF32 else 2
+        reps = 10 if mode != abi.DENSE_FP32 else 2
         e0.record()
         for _ in range(reps):
             step(mode)

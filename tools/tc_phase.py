@@ -6,6 +6,7 @@ sys.path.insert(0, ".")
 from mininf_b200.engine import abi
 dll = C.CDLL(sys.argv[1])
 N = int(float(sys.argv[2])) if len(sys.argv) > 2 else 4_000_000
+MODE = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 torch.manual_seed(0)
 dev = torch.device("cuda:0")
 p, S, D = 64, 64, 64
@@ -26,14 +27,14 @@ dll.mnf_rsample.argtypes = abi.EXPORTS["mnf_rsample"][1]
 dll.mnf_dense_sweep.argtypes = abi.EXPORTS["mnf_dense_sweep"][1]
 assert dll.mnf_debug_buffer(dbg.data_ptr()) == 0
 st = torch.cuda.current_stream().cuda_stream
-dll.mnf_rsample(lat_dev.data_ptr(), 1, S, D, eps.data_ptr(), 0, 0, z.data_ptr(), noise.data_ptr(), acc.data_ptr(), status.data_ptr(), st)
+dll.mnf_rsample(lat_dev.data_ptr(), 1, S, D, eps.data_ptr(), 0, 0, None, z.data_ptr(), noise.data_ptr(), acc.data_ptr(), status.data_ptr(), st)
 for _ in range(2):
-    dll.mnf_dense_sweep(C.byref(dense), 1, z.data_ptr(), S, D, acc.data_ptr(), ws.data_ptr(), ws.numel(), status.data_ptr(), st)
+    dll.mnf_dense_sweep(C.byref(dense), MODE, z.data_ptr(), S, D, acc.data_ptr(), ws.data_ptr(), ws.numel(), status.data_ptr(), st)
 torch.cuda.synchronize()
 dbg.zero_()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-dll.mnf_dense_sweep(C.byref(dense), 1, z.data_ptr(), S, D, acc.data_ptr(), ws.data_ptr(), ws.numel(), status.data_ptr(), st)
+dll.mnf_dense_sweep(C.byref(dense), MODE, z.data_ptr(), S, D, acc.data_ptr(), ws.data_ptr(), ws.numel(), status.data_ptr(), st)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
@@ -41,7 +42,7 @@ tiles = (N + 127) // 128
 per_cta = tiles / 148
 cnt = dbg[16384:].view(torch.int64).tolist()
 names = ["-", "-", "-", "-", "mma: wait operands", "mma: issue eta", "mma: wait r_ready", "mma: issue G",
-         "epi: wait eta_full", "epi: compute"]
+         "epi: wait eta_full", "epi: compute", "conv: wait", "conv: convert"]
 print(f"N={N} {ms:.3f} ms, {N*260/ms/1e6:.0f} GB/s, tiles/CTA {per_cta:.0f}, ~{ms*1e-3/per_cta*1e9:.0f} ns/tile")
 for i, n in enumerate(names):
     div = per_cta
