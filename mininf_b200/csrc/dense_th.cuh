@@ -95,7 +95,7 @@ __device__ __forceinline__ int conv_index(int warp) { return warp == 6 ? 0 : (wa
 constexpr uint32_t kAtomBytes = kTileM * 128;            // 128 rows x 32 fp32
 constexpr uint32_t kStgBytes = 2 * kAtomBytes;           // fp32 tile: two 32-feature atoms
 constexpr uint32_t kImgBytes = kTileM * 128;             // fp16 tile: 128 rows x 64 halves
-constexpr uint32_t kYBytes = 2 * kTileM * 4;             // interleaved (y, live) pairs per row
+constexpr uint32_t kYBytes = kTileM * 4;                 // one float per row (NaN = masked out), permuted per 32-row chunk
 
 constexpr uint32_t kOffStg = 0;
 constexpr uint32_t kOffImg = kOffStg + kStgStages * kStgBytes;
@@ -358,23 +358,28 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
         if (k < my_tiles) {
           mbar_wait(bImgEmpty + 8 * i, (uint32_t)(((k / kImgStages) & 1) ^ 1));
           const float yr[4] = {yq[i].x, yq[i].y, yq[i].z, yq[i].w};
-          float yv[4], lv[4];
+          float yv[4];
           float lgam = 0.f;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const bool live = ((mq[i] >> (8 * q)) & 0xFFu) != 0;
-            yv[q] = live ? yr[q] : 0.f;
-            lv[q] = live ? 1.f : 0.f;
+            yv[q] = live ? yr[q] : __int_as_float(0x7fc00000);    // NaN marks a masked-out row
             if (live) {
               ++live_total;
-              if (!in_support(FAMILY, yr[q])) bad_value = true;
+              if (!in_support(FAMILY, yr[q])) bad_value = true;     // a live NaN is reported, not scored
               if (FAMILY == MNF_POISSON) lgam += log_factorial(yr[q]);
             }
           }
           if (FAMILY == MNF_POISSON) lgam_total += (double)lgam;
-          const uint32_t dst = sY + (uint32_t)i * kYBytes + lane * 32;
-          sts128(dst, __float_as_uint(yv[0]), __float_as_uint(lv[0]), __float_as_uint(yv[1]), __float_as_uint(lv[1]));
-          sts128(dst + 16, __float_as_uint(yv[2]), __float_as_uint(lv[2]), __float_as_uint(yv[3]), __float_as_uint(lv[3]));
+          // Shared-memory bandwidth is this kernel's scarcest resource, so the responses are laid out
+          // for the epilogue's access pattern: within a 32-row chunk, row 8g + 2q + j is stored at
+          // position 8q + 2g + j - the eight rows an epilogue thread (t % 4 == q) scores are then two
+          // 16-byte words. This lane holds rows 4*lane .. 4*lane + 3 of the tile.
+          const int rc = 4 * (lane & 7);                          // first row within the chunk
+          const int g0 = rc >> 3, q0 = (rc & 7) >> 1;             // rows rc, rc+1 -> (g0, q0); rc+2, rc+3 -> (g0, q0 + 1)
+          const uint32_t chunk_base = sY + (uint32_t)i * kYBytes + (uint32_t)(lane >> 3) * 128u;
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(chunk_base + (uint32_t)(8 * q0 + 2 * g0) * 4u), "f"(yv[0]), "f"(yv[1]) : "memory");
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(chunk_base + (uint32_t)(8 * (q0 + 1) + 2 * g0) * 4u), "f"(yv[2]), "f"(yv[3]) : "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(bImgFull + 8 * i);
           if (k + kImgStages < my_tiles) fetch(k + kImgStages, yq[i], mq[i]);
@@ -505,15 +510,22 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
     // of particles A = 16q + t/4 and B = A + 8; a pair of rows is one fp16x2 word of the A operand
     auto process = [&](const uint32_t (&v)[16], const uint32_t (&l)[16], uint32_t (&w)[8], const float4* yl, int ch,
                        float& sa, float& sb, float& ra, float& rb) {
-      float4 yy[4];
+      // the eight responses this thread needs: two 16-byte words (see the y warp's layout)
+      const float4 lo4 = yl[8 * ch + 2 * (lane & 3)], hi4 = yl[8 * ch + 2 * (lane & 3) + 1];
+      const float raw[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+      float yv[8], lv[8];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) yy[g] = yl[16 * ch + 4 * g + (lane & 3)];
+      for (int i = 0; i < 8; ++i) {
+        const bool live = raw[i] == raw[i];
+        yv[i] = live ? raw[i] : 0.f;
+        lv[i] = live ? 1.f : 0.f;
+      }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const float a0 = point(v[4 * g + 0], l[4 * g + 0], yy[g].x, yy[g].y, icptA, sa, ra);
-        const float a1 = point(v[4 * g + 1], l[4 * g + 1], yy[g].z, yy[g].w, icptA, sa, ra);
-        const float b0 = point(v[4 * g + 2], l[4 * g + 2], yy[g].x, yy[g].y, icptB, sb, rb);
-        const float b1 = point(v[4 * g + 3], l[4 * g + 3], yy[g].z, yy[g].w, icptB, sb, rb);
+        const float a0 = point(v[4 * g + 0], l[4 * g + 0], yv[2 * g], lv[2 * g], icptA, sa, ra);
+        const float a1 = point(v[4 * g + 1], l[4 * g + 1], yv[2 * g + 1], lv[2 * g + 1], icptA, sa, ra);
+        const float b0 = point(v[4 * g + 2], l[4 * g + 2], yv[2 * g], lv[2 * g], icptB, sb, rb);
+        const float b1 = point(v[4 * g + 3], l[4 * g + 3], yv[2 * g + 1], lv[2 * g + 1], icptB, sb, rb);
         w[2 * g + 0] = pack_f16(a0, a1);
         w[2 * g + 1] = pack_f16(b0, b1);
       }

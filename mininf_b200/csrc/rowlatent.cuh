@@ -184,6 +184,12 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
         if (has_resp) n_y = __ldg(d.resp + row_n);
       }
     }
+    // fused optimiser: this element's Adam moments are requested now and consumed after the
+    // particle loop, ~1500 instructions later
+    float am_l = 0.f, av_l = 0.f, am_s = 0.f, av_s = 0.f;
+    if (adam.enabled && active) {
+      am_l = adam.m_loc[e]; av_l = adam.v_loc[e]; am_s = adam.m_scale[e]; av_s = adam.v_scale[e];
+    }
     if (!(scale_raw > 0.0f)) bad |= MNF_ST_BAD_PARAM;
     if (y != y || x != x) bad_value = true;
     float eps_r[SP], v[SP];
@@ -312,10 +318,10 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
       if (adam.enabled) {
         // chain rule through scale = exp(raw): d/d raw = d/d scale * scale; then Adam, in place
         const float g_l = out_l, g_s = out_s * scale;
-        const float m_l = adam.beta1 * adam.m_loc[e] + (1.0f - adam.beta1) * g_l;
-        const float v_l = adam.beta2 * adam.v_loc[e] + (1.0f - adam.beta2) * g_l * g_l;
-        const float m_s = adam.beta1 * adam.m_scale[e] + (1.0f - adam.beta1) * g_s;
-        const float v_s = adam.beta2 * adam.v_scale[e] + (1.0f - adam.beta2) * g_s * g_s;
+        const float m_l = adam.beta1 * am_l + (1.0f - adam.beta1) * g_l;
+        const float v_l = adam.beta2 * av_l + (1.0f - adam.beta2) * g_l * g_l;
+        const float m_s = adam.beta1 * am_s + (1.0f - adam.beta1) * g_s;
+        const float v_s = adam.beta2 * av_s + (1.0f - adam.beta2) * g_s * g_s;
         adam.m_loc[e] = m_l; adam.v_loc[e] = v_l; adam.m_scale[e] = m_s; adam.v_scale[e] = v_s;
         adam.loc_rw[e] = loc - adam_step_size * __fdividef(m_l, fmaf(sqrtf(v_l), adam_inv_bc2_sqrt, adam.eps));
         adam.raw_scale[e] = raw_scale - adam_step_size * __fdividef(m_s, fmaf(sqrtf(v_s), adam_inv_bc2_sqrt, adam.eps));

@@ -334,21 +334,60 @@ __device__ inline void finalize_block(const mnf_latent_t* __restrict__ lat, int 
   __syncthreads();
   const double bc1 = bias[0], bc2_sqrt = bias[1];
   const double invS = 1.0 / (double)S;
-  double ent = 0.0;        // lane 0 of each warp: entropy of its columns
+  double ent = 0.0;        // this thread's share of the entropy (+ warp 0: the log joint)
   bool nonfinite = false;
-  for (int d = warp; d < D; d += kWarps) {
+  // ---- Normal columns: one THREAD per column. The particle loop reads acc[s][1+d] and noise[s][d]
+  // coalesced across the threads of a warp and is unrolled, so the whole block pays a handful of
+  // L2 round trips instead of one dependent chain per column (the step is latency-bound here).
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
     const mnf_latent_t L = lat[find_latent(lat, n_lat, d)];
+    if (L.family != MNF_NORMAL) continue;
     const int e = d - L.offset;
     const double p0 = (double)L.p0[e], p1 = (double)L.p1[e];
     double g0 = 0.0, g1 = 0.0;
-    if (L.family == MNF_NORMAL) {
-      // z = loc + eps*scale
-      for (int s = lane; s < S; s += 32) {
-        const double g = __ldcg(acc + (int64_t)s * (D + 1) + 1 + d);
-        g0 += g;
-        g1 += g * (double)noise[(int64_t)s * D + d];
+    int s = 0;
+    for (; s + 8 <= S; s += 8) {
+      double g[8];
+      float nz[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        g[u] = __ldcg(acc + (int64_t)(s + u) * (D + 1) + 1 + d);
+        nz[u] = noise[(int64_t)(s + u) * D + d];
       }
-    } else if (L.family == MNF_GAMMA) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {          // z = loc + eps*scale
+        g0 += g[u];
+        g1 += g[u] * (double)nz[u];
+      }
+    }
+    for (; s < S; ++s) {
+      const double g = __ldcg(acc + (int64_t)s * (D + 1) + 1 + d);
+      g0 += g;
+      g1 += g * (double)noise[(int64_t)s * D + d];
+    }
+    // H = 0.5 + 0.5 log(2 pi) + log(scale)                      TORCH normal.py:114-115
+    double h = 0.5 + 0.91893853320467274178 + log(p1), dh1 = 1.0 / p1;
+    if (!with_entropy) { h = 0.0; dh1 = 0.0; }
+    ent += h;
+    const double o0 = -(g0 * invS);
+    const double o1 = -(g1 * invS + dh1);
+    if (!isfinite(o0) || !isfinite(o1)) nonfinite = true;
+    out[1 + d] = (float)o0;
+    out[1 + D + d] = (float)o1;
+    if (adam.raw != nullptr) {
+      adam_update(adam, d, (float)p0, o0, bc1, bc2_sqrt);
+      adam_update(adam, D + d, (float)p1, o1, bc1, bc2_sqrt);
+    }
+  }
+  // ---- Gamma / Beta columns: one WARP per column, lanes over the particles (the implicit
+  // reparameterisation gradients are ~100 fp64 operations per particle)
+  for (int d = warp; d < D; d += kWarps) {
+    const mnf_latent_t L = lat[find_latent(lat, n_lat, d)];
+    if (L.family == MNF_NORMAL) continue;
+    const int e = d - L.offset;
+    const double p0 = (double)L.p0[e], p1 = (double)L.p1[e];
+    double g0 = 0.0, g1 = 0.0;
+    if (L.family == MNF_GAMMA) {
       // z = g/rate: dz/dalpha = standard_gamma_grad(alpha, g)/rate, dz/drate = -g/rate^2
       // (the clamp_ at tiny is outside autograd: gradients as if unclamped)
       for (int s = lane; s < S; s += 32) {
@@ -372,11 +411,7 @@ __device__ inline void finalize_block(const mnf_latent_t* __restrict__ lat, int 
     g1 = warp_sum(g1);
     if (lane == 0) {
       double h = 0.0, dh0 = 0.0, dh1 = 0.0;
-      if (L.family == MNF_NORMAL) {
-        // H = 0.5 + 0.5 log(2 pi) + log(scale)                      TORCH normal.py:114-115
-        h = 0.5 + 0.91893853320467274178 + log(p1);
-        dh1 = 1.0 / p1;
-      } else if (L.family == MNF_GAMMA) {
+      if (L.family == MNF_GAMMA) {
         // H = alpha - log(rate) + lgamma(alpha) + (1-alpha) digamma(alpha)   TORCH gamma.py:100-106
         h = p0 - log(p1) + lgamma(p0) + (1.0 - p0) * digamma_d(p0);
         dh0 = 1.0 + (1.0 - p0) * trigamma_d(p0);
@@ -409,8 +444,9 @@ __device__ inline void finalize_block(const mnf_latent_t* __restrict__ lat, int 
     double lj = 0.0;
     for (int s = lane; s < S; s += 32) lj += __ldcg(acc + (int64_t)s * (D + 1));
     lj = warp_sum(lj);
-    ent += lj * invS;
+    if (lane == 0) ent += lj * invS;
   }
+  ent = warp_sum(ent);      // every lane may hold a share now (fixed butterfly: same order every launch)
   if (lane == 0) red[warp] = ent;
   __syncthreads();
   if (threadIdx.x == 0) {

@@ -696,6 +696,21 @@ class Plan:
         self.lib.call("mnf_plan_launches", self.handle, C.byref(count))
         return int(count.value)
 
+    def enqueue_sweeps(self) -> None:
+        """Only the sweeps over the dense and scalar-link observed sites, with the particles of the
+        last step (bench.py times a back-to-back series of these: a GPU-saturated loop sees the same
+        power state as the timed region, which per-launch events in a gappy eager loop do not)."""
+        lib, S, D = self.lib, self.S, self.D
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        status = self.status.data_ptr()
+        for site, mode in self.dense_sites:
+            lib.call("mnf_dense_sweep", C.byref(site), mode, self.z.data_ptr(), S, D, self.acc.data_ptr(),
+                     self.workspace.data_ptr(), self.workspace_bytes, status, stream)
+        for group in self.sweep_groups:
+            lib.call("mnf_site_sweep", group, len(group), self.z.data_ptr(), S, D, self.acc.data_ptr(),
+                     self.workspace.data_ptr(), self.workspace_bytes,
+                     abi.SWEEP_CLOSED_FORM if self.closed_form else 0, status, stream)
+
     def _step_phases(self, seed: int, offset: int, with_entropy: bool, stream: int) -> None:
         """rsample and every sweep over observed sites through the phase-level C-ABI."""
         lib, S, D = self.lib, self.S, self.D
