@@ -219,9 +219,18 @@ int run_step(mnf_plan* p, const mnf_buffers_t* b, const mnf_adam_t* adam, uint64
       ad.lr = adam->lr; ad.beta1 = adam->beta1; ad.beta2 = adam->beta2; ad.eps = adam->eps;
       ad.raw = adam->raw; ad.transform = adam->transform; ad.m = adam->m; ad.v = adam->v; ad.step = adam->step;
     }
-    tail_kernel<<<1, kTailThreads, 0, stream>>>(xa, p->small_global_dev, n_global_tail, p->latents_dev, (int)p->latents.size(),
-                                                S, D, b->z, b->noise, b->acc, with_entropy, b->out, b->step_counter,
-                                                b->status, ad);
+    const size_t stage = tail_stage_bytes(S, D);
+    if (stage <= (size_t)200 * 1024) {
+      if (stage > (size_t)48 * 1024)
+        MNF_CUDA_CHECK(cudaFuncSetAttribute(tail_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stage));
+      tail_kernel<true><<<1, kTailThreads, stage, stream>>>(xa, p->small_global_dev, n_global_tail, p->latents_dev,
+                                                            (int)p->latents.size(), S, D, b->z, b->noise, b->acc,
+                                                            with_entropy, b->out, b->step_counter, b->status, ad);
+    } else {
+      tail_kernel<false><<<1, kTailThreads, 0, stream>>>(xa, p->small_global_dev, n_global_tail, p->latents_dev,
+                                                         (int)p->latents.size(), S, D, b->z, b->noise, b->acc,
+                                                         with_entropy, b->out, b->step_counter, b->status, ad);
+    }
     MNF_LAUNCH_CHECK();
   }
   p->last_launches = g_launches - launches_before;
