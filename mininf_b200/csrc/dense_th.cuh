@@ -16,7 +16,7 @@
 // through L2.
 //
 //   fp32 tile [128 x 64]  --TMA-->  staging ring (SWIZZLE_128B, 32 KB)
-//   staging  --two conversion warps: LDS.128 -> cvt.rn.f16x2.f32 -> STS.128-->  fp16 image (16 KB)
+//   staging  --eight conversion warps: LDS.128 -> cvt.rn.f16x2.f32 -> STS.128-->  fp16 image (16 KB)
 //   eta^T[2S x 128] = Theta[2S x 64] . X^T      4 MMAs kind::f16, M=128 N=128 K=16, A = Theta in TMEM
 //   R^T  = score(y, eta)                        epilogue warps; packed fp16 pairs back into TMEM
 //   G^T[S x 64]   += R^T[S x 128] . X           8 MMAs kind::f16, M=64 N=64 K=16, A = R^T in TMEM
@@ -36,9 +36,9 @@
 // unbiased, averages out over rows), theta as hi + lo fp16 pairs (22 bits), exact products, fp32
 // accumulation in TMEM drained every kFlush tiles, fp32 / fp64 SIMT log-densities and sums.
 //
-// Warps (480 threads): 0-3 and 8-11 epilogue (two per TMEM lane quadrant, as dense_tc.cuh), 4 TMA
-// producer of the staging ring, 5 (y, live) pairs, 6 and 12-14 conversion (32 tile rows each),
-// 7 TMEM allocation + MMAs.
+// Warps (608 threads): 0-7 epilogue (two per TMEM lane quadrant, half a tile each), 8 TMA producer of
+// the staging ring, 9 responses, 10 TMEM allocation + MMAs, 11-18 conversion (16 tile rows each, two
+// threads per row).
 //
 // Replaces the same reference code as dense_tc.cuh: aten::mv / MvBackward of `X @ theta`
 // (tests/test_mininf.py:11, examples/minibatch.md:33) and the Normal / Bernoulli / Poisson log_prob
@@ -86,16 +86,26 @@ constexpr int kTileM = 128;
 constexpr int kStgStages = 4;    // fp32 staging ring (32 KB per stage): three in flight while one is converted
 constexpr int kImgStages = 4;    // fp16 operand images (16 KB per stage), live from eta(k) to G(k)
 constexpr int kFlush = 8;
-constexpr int kEpiWarps = 8;     // warps 0-3 (tile rows 0-63) and 8-11 (rows 64-127)
-constexpr int kWarpTma = 4, kWarpY = 5, kMmaWarp = 7;
-constexpr int kConvWarps = 4;    // warps 6, 12, 13, 14: 32 tile rows each
-constexpr int kThreads = 15 * 32;
-__device__ __forceinline__ int conv_index(int warp) { return warp == 6 ? 0 : (warp >= 12 ? warp - 11 : -1); }
+#ifndef MNF_TH_EPI_WARPS
+#define MNF_TH_EPI_WARPS 8
+#endif
+// timing experiments only (wrong results): 1 no conversion, 2 no score math, 4 no gradient MMAs,
+// 8 no eta MMAs, 16 no tcgen05.ld in the epilogue
+#ifndef MNF_TH_DEV_SKIP
+#define MNF_TH_DEV_SKIP 0
+#endif
+constexpr int kEpiWarps = MNF_TH_EPI_WARPS;   // warp w: TMEM lane quadrant w % 4, 32-row chunks (w / 4) kChunks .. + kChunks - 1
+constexpr int kChunks = 16 / kEpiWarps;       // 32-row chunks of a tile scored by one epilogue warp
+constexpr int kWarpTma = kEpiWarps, kWarpY = kEpiWarps + 1, kMmaWarp = kEpiWarps + 2;
+constexpr int kFirstConv = kEpiWarps + 3;
+constexpr int kConvWarps = 8;    // 16 tile rows each, two threads per row
+constexpr int kThreads = (kFirstConv + kConvWarps) * 32;
+static_assert(kEpiWarps == 4 || kEpiWarps == 8 || kEpiWarps == 16, "epilogue warps per TMEM lane quadrant: 1, 2 or 4");
 
 constexpr uint32_t kAtomBytes = kTileM * 128;            // 128 rows x 32 fp32
 constexpr uint32_t kStgBytes = 2 * kAtomBytes;           // fp32 tile: two 32-feature atoms
 constexpr uint32_t kImgBytes = kTileM * 128;             // fp16 tile: 128 rows x 64 halves
-constexpr uint32_t kYBytes = kTileM * 4;                 // one float per row (NaN = masked out), permuted per 32-row chunk
+constexpr uint32_t kYBytes = 2 * kTileM * 4;             // two planes of one float per row (response | liveness factor), permuted per 32-row chunk
 
 constexpr uint32_t kOffStg = 0;
 constexpr uint32_t kOffImg = kOffStg + kStgStages * kStgBytes;
@@ -105,7 +115,7 @@ constexpr uint32_t kNumBars = 2 * kStgStages + 2 * kImgStages + 8;
 constexpr uint32_t kOffMisc = kOffBar + 8 * kNumBars + (8 * kNumBars % 16 ? 8 : 0);
 constexpr uint32_t kOffGrad = kOffMisc + 64 + kNS * 16;
 constexpr uint32_t kOffStat = kOffGrad + kNS * (kP + 1) * 4;
-constexpr uint32_t kSmemBytes = kOffStat + 4 * kNS * 4 + 1024 /* alignment slack */;
+constexpr uint32_t kSmemBytes = kOffStat + (kEpiWarps / 4) * 2 * kNS * 4 + 1024 /* alignment slack */;
 static_assert(kOffMisc % 16 == 0, "misc block alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -275,13 +285,18 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
       }
     }
     __syncwarp();
-  } else if (conv_index(warp) >= 0) {
+  } else if (warp >= kFirstConv) {
     // ================= conversion warps: fp32 staging -> fp16 operand image =====================
-    // Thread handles one row of its warp's 32-row quarter. Staging: per 32-feature atom, row r is
-    // 128 B with its 16-byte chunks XOR-ed with r % 8 (TMA SWIZZLE_128B); image: row r is 128 B
-    // (64 halves) under the same swizzle, which is at once the K-major operand of the eta product
-    // and the MN-major operand of the gradient product.
-    const uint32_t r = (uint32_t)(32 * conv_index(warp) + lane);
+    // Two threads per row (a thread converts one 32-feature atom of its row: 8 LDS.128 -> 4 STS.128),
+    // a warp covers 16 rows, eight warps a tile: the stage's latency (a chain of shared-memory round
+    // trips) is on the critical path of every tile, so it is spread over many short threads.
+    // Staging: per 32-feature atom, row r is 128 B with its 16-byte chunks XOR-ed with r % 8 (TMA
+    // SWIZZLE_128B); image: row r is 128 B (64 halves) under the same swizzle, which is at once the
+    // K-major operand of the eta product and the MN-major operand of the gradient product. The two
+    // threads of a row walk their chunks in opposite halves (c ^ 4h), so the eight lanes of a
+    // quarter-warp always touch eight different 16-byte bank groups.
+    const uint32_t r = (uint32_t)(16 * (warp - kFirstConv) + (lane >> 1));
+    const uint32_t h = (uint32_t)lane & 1u;
     const uint32_t sw = r & 7u;
     float worst = 0.f;                       // largest |x| seen (NaN entries surface as a NaN loss)
     TC_DECL();
@@ -291,20 +306,23 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
       mbar_wait(bImgEmpty + 8 * ist, (uint32_t)(((k / kImgStages) & 1) ^ 1));
       mbar_wait(bStgFull + 8 * sst, (uint32_t)((k / kStgStages) & 1));
       TC_ACC(0);   // conv: wait
-      const uint32_t src = sStg + (uint32_t)sst * kStgBytes + r * 128u, dst = sImg + (uint32_t)ist * kImgBytes + r * 128u;
-      float4 x[16];
+      const uint32_t src = sStg + (uint32_t)sst * kStgBytes + h * kAtomBytes + r * 128u;
+      const uint32_t dst = sImg + (uint32_t)ist * kImgBytes + r * 128u;
+      float4 x[8];
+      if (!(MNF_TH_DEV_SKIP & 1)) {
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
+      for (int c = 0; c < 8; ++c) x[c] = lds128(src + ((((uint32_t)c ^ (h << 2)) ^ sw) << 4));   // x[c] = chunk c ^ 4h
 #pragma unroll
-        for (int c = 0; c < 8; ++c) x[8 * a + c] = lds128(src + a * kAtomBytes + (((uint32_t)c ^ sw) << 4));
-#pragma unroll
-      for (int i = 0; i < 16; i += 2) {
-        const float4 lo4 = x[i], hi4 = x[i + 1];
+      for (int i = 0; i < 4; ++i) {
+        // image chunk 4h + j holds features 32h + 8j .. + 7 = staging chunks 2j, 2j + 1 of atom h;
+        // step i handles j = i ^ 2h (again opposite halves for the two threads of a row)
+        const uint32_t j = (uint32_t)i ^ (h << 1);
+        const float4 lo4 = x[(2 * i) ^ 0], hi4 = x[(2 * i) ^ 1];   // staging chunks (2i) ^ 4h, (2i + 1) ^ 4h = 2j, 2j + 1
         worst = fmaxf(worst, fmaxf(fmaxf(fabsf(lo4.x), fabsf(lo4.y)), fmaxf(fabsf(lo4.z), fabsf(lo4.w))));
         worst = fmaxf(worst, fmaxf(fmaxf(fabsf(hi4.x), fabsf(hi4.y)), fmaxf(fabsf(hi4.z), fabsf(hi4.w))));
-        const uint32_t chunk = (uint32_t)(i / 2);             // features 8*chunk .. 8*chunk + 7
-        sts128(dst + ((chunk ^ sw) << 4), pack_f16(lo4.x, lo4.y), pack_f16(lo4.z, lo4.w), pack_f16(hi4.x, hi4.y),
+        sts128(dst + (((4u * h + j) ^ sw) << 4), pack_f16(lo4.x, lo4.y), pack_f16(lo4.z, lo4.w), pack_f16(hi4.x, hi4.y),
                pack_f16(hi4.z, hi4.w));
+      }
       }
       fence_proxy_async();                   // generic-proxy stores -> visible to the tensor core
       __syncwarp();
@@ -314,7 +332,7 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
       }
       TC_ACC(1);   // conv: convert
     }
-    TC_FLUSH(10, 2, warp == 6 && lane == 0);
+    TC_FLUSH(10, 2, warp == kFirstConv && lane == 0);
     // anything at or above 2^15 (or infinite) is outside the range this operand format is used for
     if (!(worst < 32768.0f)) atomicOr(status, MNF_ST_RANGE);
   } else if (warp == kWarpY) {
@@ -358,12 +376,16 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
         if (k < my_tiles) {
           mbar_wait(bImgEmpty + 8 * i, (uint32_t)(((k / kImgStages) & 1) ^ 1));
           const float yr[4] = {yq[i].x, yq[i].y, yq[i].z, yq[i].w};
-          float yv[4];
+          float yv[4], av[4];
           float lgam = 0.f;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const bool live = ((mq[i] >> (8 * q)) & 0xFFu) != 0;
-            yv[q] = live ? yr[q] : __int_as_float(0x7fc00000);    // NaN marks a masked-out row
+            // plane 0: the response (0 on masked-out rows); plane 1: what the epilogue multiplies eta by -
+            // Normal: -live 2^-k (the power-of-two scale of Theta folded in, so that a score is two
+            // FFMAs: y - 2^-k (hi + lo)); other families: live
+            yv[q] = live ? yr[q] : 0.f;
+            av[q] = live ? (FAMILY == MNF_NORMAL ? -down : 1.0f) : 0.f;
             if (live) {
               ++live_total;
               if (!in_support(FAMILY, yr[q])) bad_value = true;     // a live NaN is reported, not scored
@@ -380,6 +402,8 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
           const uint32_t chunk_base = sY + (uint32_t)i * kYBytes + (uint32_t)(lane >> 3) * 128u;
           asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(chunk_base + (uint32_t)(8 * q0 + 2 * g0) * 4u), "f"(yv[0]), "f"(yv[1]) : "memory");
           asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(chunk_base + (uint32_t)(8 * (q0 + 1) + 2 * g0) * 4u), "f"(yv[2]), "f"(yv[3]) : "memory");
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(chunk_base + kTileM * 4u + (uint32_t)(8 * q0 + 2 * g0) * 4u), "f"(av[0]), "f"(av[1]) : "memory");
+          asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(chunk_base + kTileM * 4u + (uint32_t)(8 * (q0 + 1) + 2 * g0) * 4u), "f"(av[2]), "f"(av[3]) : "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(bImgFull + 8 * i);
           if (k + kImgStages < my_tiles) fetch(k + kImgStages, yq[i], mq[i]);
@@ -415,7 +439,7 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
           const uint32_t d = tmem + kColEta + b * kTileM;
 #pragma unroll
           for (int ks = 0; ks < kP / 16; ++ks)      // 16 features = 32 B along the swizzled row
-            mma_ts_f16(d, tmem + kColTheta + ks * 8, lo + ks * 2, d_hi, idesc_eta, ks != 0 ? 1u : 0u);
+            if (!(MNF_TH_DEV_SKIP & 8)) mma_ts_f16(d, tmem + kColTheta + ks * 8, lo + ks * 2, d_hi, idesc_eta, ks != 0 ? 1u : 0u);
           tc_commit(bEtaFull + 8 * b);
         }
         __syncwarp();
@@ -439,10 +463,11 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
           const uint32_t a0 = tmem + kColEta + b * kTileM;
 #pragma unroll
           for (int ks = 0; ks < kTileM / 16; ++ks) {
-            // 16 tile rows per MMA: their packed scores are 8 TMEM columns (rows 0-63 at columns
-            // 0-31, rows 64-127 at columns 64-95 of the eta tile), their X rows 2048 B of the image
-            const uint32_t a_col = (uint32_t)(ks < 4 ? ks * 8 : 64 + (ks - 4) * 8);
-            mma_ts_f16(d, a0 + a_col, lo + ks * (2048 >> 4), d_hi, idesc_g, (!first || ks > 0) ? 1u : 0u);
+            // 16 tile rows per MMA: their packed scores are 8 TMEM columns (rows 32Q .. 32Q + 31 at
+            // columns 32Q .. 32Q + 15 of the eta tile: every epilogue warp writes inside the columns
+            // it read), their X rows 2048 B of the image
+            const uint32_t a_col = (uint32_t)(32 * (ks >> 1) + 8 * (ks & 1));   // chunk ks / 2
+            if (!(MNF_TH_DEV_SKIP & 4)) mma_ts_f16(d, a0 + a_col, lo + ks * (2048 >> 4), d_hi, idesc_g, (!first || ks > 0) ? 1u : 0u);
           }
           tc_commit(bImgEmpty + 8 * ist);
           if (last) tc_commit(bGFull + 8 * gb);
@@ -452,17 +477,22 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
       }
     }
     TC_FLUSH(4, 4, lane == 0);
-  } else {
-    // ================= epilogue warps: quadrant q = warp % 4, column half = warp / 8 ============
-    const int q = warp & 3, half = warp >> 3;
+  } else if (warp < kEpiWarps) {
+    // ================= epilogue warps: quadrant q = warp % 4, chunks Q kChunks .. of every tile, Q = warp / 4 ====
+    // The score stage is bound by instruction issue (8192 points per tile over 128 lanes: every
+    // instruction per point is 64 issue cycles per tile and scheduler, of ~1000-1100 available at the
+    // power-capped clock), so the per-point work of the Normal family is three FFMAs and half a
+    // conversion: score = y + nl (hi + lo) as two FFMAs with nl = -live 2^-k staged per row by the
+    // response warp, sum r^2 as one FFMA, two scores per cvt.rn.f16x2.
+    const int q = warp & 3, Q = warp >> 2;
     const int s = q * 16 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     double stA_total = 0.0, stB_total = 0.0;  // Normal: sum r^2 | others: sum log-density (w/o lgamma)
     double scA_total = 0.0, scB_total = 0.0;  // sum of scores: the intercept gradient (ICPT only)
     const float icptA = ICPT ? sPar[q * 16 + (lane >> 2)].icpt : 0.f;
     const float icptB = ICPT ? sPar[q * 16 + (lane >> 2) + 8].icpt : 0.f;
-    constexpr int kDrainCols = kP / 2;        // features drained by this warp
-    float* grad_row = reinterpret_cast<float*>(gbase + kOffGrad) + (size_t)(lane < 16 ? s : 0) * (kP + 1) + kDrainCols * half;
+    constexpr int kDrainCols = kP / (kEpiWarps / 4);   // features drained by this warp
+    float* grad_row = reinterpret_cast<float*>(gbase + kOffGrad) + (size_t)(lane < 16 ? s : 0) * (kP + 1) + kDrainCols * Q;
     if (lane < 16)
       for (int j = 0; j < kDrainCols; ++j) grad_row[j] = 0.f;
     int64_t n_drained = 0;
@@ -472,36 +502,45 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
       const uint32_t gb = (uint32_t)(grp & 1);
       mbar_wait(bGFull + 8 * gb, (uint32_t)((grp >> 1) & 1));
       tc_fence_after();
-      uint32_t v[32];     // 32x32b: thread == TMEM lane; an M = 64 accumulator lives on lanes 0-15
-      tc_ld32(tmem + lane_base + kColG + gb * kP + half * kDrainCols, v);
-      tc_wait_ld();
-      if (lane < 16) {
+      // 32x32b: thread == TMEM lane; an M = 64 accumulator lives on lanes 0-15
 #pragma unroll
-        for (int c = 0; c < 32; ++c) grad_row[c] += __uint_as_float(v[c]);
+      for (int c0 = 0; c0 < kDrainCols; c0 += 16) {
+        uint32_t v[16];
+        tc::tc_ld16(tmem + lane_base + kColG + gb * kP + Q * kDrainCols + c0, v);
+        tc_wait_ld();
+        if (lane < 16) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) grad_row[c0 + c] += __uint_as_float(v[c]);
+        }
       }
       tc_fence_before();
       mbar_arrive(bGEmpty + 8 * gb);
       ++n_drained;
     };
 
-    // one (row, particle) point: eta = (hi row + lo row) 2^-k; returns the score
-    auto point = [&](uint32_t cell, uint32_t cell_lo, float y, float live, float icpt, float& stat, float& ssum) {
-      const float eta = ICPT ? fmaf(__uint_as_float(cell) + __uint_as_float(cell_lo), down, icpt)
-                             : (__uint_as_float(cell) + __uint_as_float(cell_lo)) * down;
+    // one (row, particle) point; `aux` is the row's staged factor (Normal: -live 2^-k, others: live)
+    const float icptUpA = icptA * up, icptUpB = icptB * up;   // intercept in units of the scaled eta (2^k is exact)
+    auto point = [&](uint32_t cell, uint32_t cell_lo, float y, float aux, float icpt, float icpt_up, float& stat, float& ssum) {
       float score;
       if (FAMILY == MNF_NORMAL) {
-        score = fmaf(-live, eta, y);             // live * (y - eta); 1/sigma^2 applied at the end
+        // live * (y - icpt - 2^-k (hi + lo)); 1/sigma^2 applied at the end
+        const float t = ICPT ? fmaf(aux, icpt_up, y) : y;
+        score = fmaf(aux, __uint_as_float(cell), fmaf(aux, __uint_as_float(cell_lo), t));
         stat = fmaf(score, score, stat);
-      } else if (FAMILY == MNF_BERNOULLI_LOGITS) {
-        const float e = __expf(-fabsf(eta));
-        const float inv = __fdividef(1.0f, 1.0f + e);
-        const float sig = eta >= 0.f ? inv : e * inv;
-        score = live * (y - sig);
-        stat += live * (y * eta - (fmaxf(eta, 0.f) + __logf(1.0f + e)));   // softplus, abs. error ~1e-7
       } else {
-        const float rate = __expf(eta);
-        score = live * (y - rate);
-        stat += live * fmaf(y, eta, -rate);
+        const float eta = ICPT ? fmaf(__uint_as_float(cell) + __uint_as_float(cell_lo), down, icpt)
+                               : (__uint_as_float(cell) + __uint_as_float(cell_lo)) * down;
+        if (FAMILY == MNF_BERNOULLI_LOGITS) {
+          const float e = __expf(-fabsf(eta));
+          const float inv = __fdividef(1.0f, 1.0f + e);
+          const float sig = eta >= 0.f ? inv : e * inv;
+          score = aux * (y - sig);
+          stat += aux * (y * eta - (fmaxf(eta, 0.f) + __logf(1.0f + e)));   // softplus, abs. error ~1e-7
+        } else {
+          const float rate = __expf(eta);
+          score = aux * (y - rate);
+          stat += aux * fmaf(y, eta, -rate);
+        }
       }
       if (ICPT) ssum += score;
       return score;
@@ -510,24 +549,19 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
     // of particles A = 16q + t/4 and B = A + 8; a pair of rows is one fp16x2 word of the A operand
     auto process = [&](const uint32_t (&v)[16], const uint32_t (&l)[16], uint32_t (&w)[8], const float4* yl, int ch,
                        float& sa, float& sb, float& ra, float& rb) {
-      // the eight responses this thread needs: two 16-byte words (see the y warp's layout)
-      const float4 lo4 = yl[8 * ch + 2 * (lane & 3)], hi4 = yl[8 * ch + 2 * (lane & 3) + 1];
-      const float raw[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
-      float yv[8], lv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const bool live = raw[i] == raw[i];
-        yv[i] = live ? raw[i] : 0.f;
-        lv[i] = live ? 1.f : 0.f;
-      }
+      // the eight responses and factors this thread needs: two 16-byte words each (see the y warp's layout)
+      const float4 y0 = yl[8 * ch + 2 * (lane & 3)], y1 = yl[8 * ch + 2 * (lane & 3) + 1];
+      const float4 a0 = yl[kTileM / 4 + 8 * ch + 2 * (lane & 3)], a1 = yl[kTileM / 4 + 8 * ch + 2 * (lane & 3) + 1];
+      const float yv[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const float a0 = point(v[4 * g + 0], l[4 * g + 0], yv[2 * g], lv[2 * g], icptA, sa, ra);
-        const float a1 = point(v[4 * g + 1], l[4 * g + 1], yv[2 * g + 1], lv[2 * g + 1], icptA, sa, ra);
-        const float b0 = point(v[4 * g + 2], l[4 * g + 2], yv[2 * g], lv[2 * g], icptB, sb, rb);
-        const float b1 = point(v[4 * g + 3], l[4 * g + 3], yv[2 * g + 1], lv[2 * g + 1], icptB, sb, rb);
-        w[2 * g + 0] = pack_f16(a0, a1);
-        w[2 * g + 1] = pack_f16(b0, b1);
+        const float pa0 = point(v[4 * g + 0], l[4 * g + 0], yv[2 * g], av[2 * g], icptA, icptUpA, sa, ra);
+        const float pa1 = point(v[4 * g + 1], l[4 * g + 1], yv[2 * g + 1], av[2 * g + 1], icptA, icptUpA, sa, ra);
+        const float pb0 = point(v[4 * g + 2], l[4 * g + 2], yv[2 * g], av[2 * g], icptB, icptUpB, sb, rb);
+        const float pb1 = point(v[4 * g + 3], l[4 * g + 3], yv[2 * g + 1], av[2 * g + 1], icptB, icptUpB, sb, rb);
+        w[2 * g + 0] = pack_f16(pa0, pa1);
+        w[2 * g + 1] = pack_f16(pb0, pb1);
       }
     };
 
@@ -543,21 +577,36 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
       mbar_wait(bEtaFull + 8 * b, (uint32_t)((k >> 1) & 1));
       TC_ACC(0);   // epi: wait eta_full (+ drain)
       tc_fence_after();
-      const uint32_t t_eta = tmem + lane_base + kColEta + b * kTileM + 64 * half;
-      // this warp's half of the tile: two 32-column chunks; the packed scores of chunk c go to
-      // columns 16c .. 16c + 15 of the same half (already consumed: chunk 0 was loaded before its
-      // columns are overwritten, chunk 1's words land in columns chunk 0 occupied)
+      // this warp's chunks of the eta tile: 32 columns (tile rows) each, hi rows on lanes 0-15 and lo
+      // rows on lanes 16-31 of the quadrant; the packed scores of a chunk go back into its first 16
+      // columns (loaded before they are overwritten; no other warp touches a chunk's columns)
+      const uint32_t t_eta = tmem + lane_base + kColEta + b * kTileM + 32 * kChunks * Q;
       float sa = 0.f, sb = 0.f, ra = 0.f, rb = 0.f;
-      uint32_t v0[16], l0[16], v1[16], l1[16], w[8];
-      tc_ld_16x256b_x4(t_eta, v0);
-      tc_ld_16x256b_x4(t_eta + kLoRows, l0);
-      tc_ld_16x256b_x4(t_eta + 32, v1);
-      tc_ld_16x256b_x4(t_eta + kLoRows + 32, l1);
+      uint32_t v[kChunks][16], l[kChunks][16];
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        if (MNF_TH_DEV_SKIP & 16) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[c][i] = l[c][i] = (uint32_t)k;
+        } else {
+          tc_ld_16x256b_x4(t_eta + 32 * c, v[c]);
+          tc_ld_16x256b_x4(t_eta + kLoRows + 32 * c, l[c]);
+        }
+      }
       tc_wait_ld();
-      process(v0, l0, w, yl, 2 * half, sa, sb, ra, rb);
-      tc_st_16x128b_x4(t_eta, w);
-      process(v1, l1, w, yl, 2 * half + 1, sa, sb, ra, rb);
-      tc_st_16x128b_x4(t_eta + 16, w);
+      TC_ACC(1);   // epi: tcgen05.ld
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
+        uint32_t w[8];
+        if (MNF_TH_DEV_SKIP & 2) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) w[i] = v[c][i] ^ l[c][i];
+        } else {
+          process(v[c], l[c], w, yl, kChunks * Q + c, sa, sb, ra, rb);
+        }
+        tc_st_16x128b_x4(t_eta + 32 * c, w);
+      }
+      TC_ACC(2);   // epi: scores
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(bRReady + 8 * b);
@@ -567,9 +616,9 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
         scA_total += (double)ra;
         scB_total += (double)rb;
       }
-      TC_ACC(1);   // epi: compute
+      TC_ACC(3);   // epi: wait st, arrive
     }
-    TC_FLUSH(8, 2, tid == 0);
+    TC_FLUSH(0, 4, tid == 0);
     {
       const int64_t n_grp = (my_tiles + kFlush - 1) / kFlush;
       while (n_drained < n_grp) drain();
@@ -585,7 +634,7 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
       scB_total += __shfl_xor_sync(0xffffffffu, scB_total, 1);
       scB_total += __shfl_xor_sync(0xffffffffu, scB_total, 2);
     }
-    float* s_stat = reinterpret_cast<float*>(gbase + kOffStat) + half * 2 * kNS;   // [half][2][kNS]
+    float* s_stat = reinterpret_cast<float*>(gbase + kOffStat) + Q * 2 * kNS;   // [kEpiWarps / 4][2][kNS]
     if ((lane & 3) == 0) {
       s_stat[q * 16 + (lane >> 2)] = (float)stA_total;
       s_stat[q * 16 + (lane >> 2) + 8] = (float)stB_total;
@@ -597,13 +646,16 @@ dense_th_kernel(const __grid_constant__ CUtensorMap map_x, mnf_dense_site_t site
     // every epilogue warp's statistics and gradient columns, and the y warp's counters, are final
     asm volatile("bar.sync 1, %0;" ::"n"((kEpiWarps + 1) * 32) : "memory");
     const float* s_all = reinterpret_cast<const float*>(gbase + kOffStat);
-    const bool owner_thread = half == 0 && lane < 16;
+    const bool owner_thread = Q == 0 && lane < 16;
     float st0 = 0.f, sc0 = 0.f;
     if (owner_thread) {
-      st0 = s_all[s] + s_all[2 * kNS + s];
-      if (ICPT) sc0 = s_all[kNS + s] + s_all[3 * kNS + s];
+#pragma unroll
+      for (int i = 0; i < kEpiWarps / 4; ++i) {
+        st0 += s_all[2 * i * kNS + s];
+        if (ICPT) sc0 += s_all[(2 * i + 1) * kNS + s];
+      }
     }
-    grad_row -= kDrainCols * half;
+    grad_row -= kDrainCols * Q;
 
     // ---- per-particle results: this thread is the only owner of particle s --------------------
     if (owner_thread && s < S) {

@@ -21,13 +21,13 @@ __global__ void stream(const float4* __restrict__ src, size_t n_vec, float* sink
   if (acc == 123.456f) sink[0] = acc;
 }
 template <int U>
-void run(const float4* d, size_t n_vec, float* sink, int warps) {
+void run(const float4* d, size_t n_vec, float* sink, int warps, int reps = 3) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   stream<U><<<148, warps * 32>>>(d, n_vec, sink);
   cudaEventRecord(e0);
-  for (int i = 0; i < 3; ++i) stream<U><<<148, warps * 32>>>(d, n_vec, sink);
+  for (int i = 0; i < reps; ++i) stream<U><<<148, warps * 32>>>(d, n_vec, sink);
   cudaEventRecord(e1); cudaEventSynchronize(e1);
-  float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= 3;
+  float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
   printf("warps/SM %2d  x  %2d LDG.128/thread (%3d KB requested per SM per round): %7.1f GB/s\n", warps, U, warps * 32 * U * 16 / 1024, n_vec * 16.0 / ms / 1e6);
 }
 int main() {
@@ -39,5 +39,11 @@ int main() {
   run<8>(d, n_vec, sink, 16); run<4>(d, n_vec, sink, 16); run<16>(d, n_vec, sink, 16);
   run<4>(d, n_vec, sink, 32); run<8>(d, n_vec, sink, 32); run<2>(d, n_vec, sink, 32);
   run<16>(d, n_vec, sink, 12); run<8>(d, n_vec, sink, 12); run<12>(d, n_vec, sink, 12);
+  // the same loads against an L2-resident buffer (64 MB of the 126 MB L2): what register-staged
+  // loads could sustain behind an L2 prefetch
+  printf("--- 64 MB buffer (L2-resident)\n");
+  const size_t small = (64ull << 20) / 16;
+  run<4>(d, small, sink, 8, 200); run<8>(d, small, sink, 8, 200); run<2>(d, small, sink, 16, 200);
+  run<4>(d, small, sink, 16, 200); run<8>(d, small, sink, 16, 200); run<4>(d, small, sink, 32, 200);
   return 0;
 }
