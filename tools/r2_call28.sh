@@ -1,0 +1,23 @@
+#!/bin/bash
+# dense_th with three eta tiles in tensor memory (eta(k) issued before G(k - 2)), register drain
+mkdir -p gpurun_out
+export MNF_DENSE_NO_GRAM=1
+L=gpurun_out/r2c28_check.log
+: > $L
+echo "== th 3 eta tiles (main lib)" >> $L
+timeout 200 python tools/kernel_check.py 100000 2>&1 | grep f16 >> $L
+timeout 200 python tools/kernel_check.py 1000 2>&1 | grep f16 >> $L
+timeout 200 python tools/kernel_check.py 129 2>&1 | grep f16 >> $L
+timeout 200 python tools/kernel_check.py 3000000 2>&1 | grep f16 >> $L
+timeout 300 python tools/dense_time.py 1e8 3 30 >> $L 2>&1
+echo "== previous commit (2 eta tiles)" >> $L
+MNF_LIB=tools/_dbg/lib_th_skip0.so timeout 300 python tools/dense_time.py 1e8 3 30 2>&1 | tail -2 >> $L
+echo "== main again; families" >> $L
+timeout 300 python tools/dense_time.py 1e8 3 30 2>&1 | tail -2 >> $L
+timeout 300 python tools/dense_time.py 1e8 3 30 bernoulli 2>&1 | tail -1 >> $L
+timeout 300 python tools/dense_time.py 1e8 3 30 poisson 2>&1 | tail -1 >> $L
+echo "== phases" >> $L
+timeout 200 python tools/tc_phase.py tools/_dbg/lib_th_dbg.so 4e7 3 >> $L 2>&1
+timeout 900 python -m pytest tests/test_engine_gpu.py -x -q -m gpu > gpurun_out/r2c28_pytest.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2c28_pytest.log
+echo done

@@ -41,7 +41,7 @@ ms = e0.elapsed_time(e1)
 tiles = (N + 127) // 128
 per_cta = tiles / 148
 cnt = dbg[16384:].view(torch.int64).tolist()
-names = ["epi(th): wait eta_full", "epi(th): tcgen05.ld", "epi(th): scores + st issue", "epi(th): wait st + arrive", "mma: wait operands", "mma: issue eta", "mma: wait r_ready", "mma: issue G",
+names = ["epi(th): wait eta_full", "epi(th): tcgen05.ld + scores + st issue", "epi(th): wait st + arrive", "epi(th): drain", "mma: wait operands", "mma: issue eta", "mma: wait r_ready", "mma: issue G",
          "epi: wait eta_full", "epi: compute", "conv: wait", "conv: convert"]
 print(f"N={N} {ms:.3f} ms, {N*260/ms/1e6:.0f} GB/s, tiles/CTA {per_cta:.0f}, ~{ms*1e-3/per_cta*1e9:.0f} ns/tile")
 for i, n in enumerate(names):
