@@ -64,6 +64,47 @@ bool poisson_moments_disabled() {
 // (after the exact kernel's partial rows) holds the range partials, the per-CTA moment rows and
 // the need_exact word the finish kernel sets; returns that word's address, or NULL when this
 // site's layout does not qualify (no covariate, strided or misaligned data, scratch too small).
+// Range slots (site_sweep.cuh::RangeSlot): 64 per device, keyed by (covariate, mask, element count).
+// The array is allocated and a new key registered only outside stream captures (cudaMalloc and the
+// slot's reset are not capturable); a site met for the first time inside a capture runs uncached.
+struct RangeSlots {
+  static constexpr int kSlots = 64;
+  RangeSlot* dev = nullptr;
+  int used = 0;
+  struct Key { const void* x; const void* mask; int64_t n; } keys[kSlots];
+};
+RangeSlots g_range_slots[16];
+std::mutex g_range_mutex;
+
+bool range_cache_disabled() {
+  const char* v = std::getenv("MNF_POISSON_NO_RANGE_CACHE");   // developer A/B switch
+  return v != nullptr && v[0] != '\0' && v[0] != '0';
+}
+
+RangeSlot* range_slot(const mnf_site_t& site, cudaStream_t stream) {
+  if (range_cache_disabled()) return nullptr;
+  int device = 0;
+  if (cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 16) return nullptr;
+  std::lock_guard<std::mutex> lock(g_range_mutex);
+  RangeSlots& rs = g_range_slots[device];
+  for (int i = 0; i < rs.used; ++i)
+    if (rs.keys[i].x == site.param[0].x && rs.keys[i].mask == site.mask && rs.keys[i].n == site.numel) return rs.dev + i;
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &capturing) != cudaSuccess || capturing != cudaStreamCaptureStatusNone) return nullptr;
+  if (rs.dev == nullptr) {
+    if (cudaMalloc(&rs.dev, sizeof(RangeSlot) * RangeSlots::kSlots) != cudaSuccess) { rs.dev = nullptr; return nullptr; }
+    if (cudaMemset(rs.dev, 0, sizeof(RangeSlot) * RangeSlots::kSlots) != cudaSuccess) return nullptr;
+  }
+  if (rs.used == RangeSlots::kSlots) {      // full: start over (the slots revalidate themselves)
+    if (cudaMemset(rs.dev, 0, sizeof(RangeSlot) * RangeSlots::kSlots) != cudaSuccess) return nullptr;
+    rs.used = 0;
+  }
+  const int i = rs.used++;
+  rs.keys[i] = {site.param[0].x, site.mask, site.numel};
+  if (cudaMemsetAsync(rs.dev + i, 0, sizeof(RangeSlot), stream) != cudaSuccess) return nullptr;
+  return rs.dev + i;
+}
+
 int launch_poisson_moments(const mnf_site_t& site, const float* z, int S, int D, double* acc, char* scratch,
                            size_t scratch_bytes, uint32_t* status, int sm_count, cudaStream_t stream,
                            uint32_t** need_exact_out) {
@@ -78,19 +119,23 @@ int launch_poisson_moments(const mnf_site_t& site, const float* z, int S, int D,
   const int moment_grid = (int)std::max<int64_t>(1, std::min<int64_t>(groups, 3 * (int64_t)sm_count));
   const size_t rows_bytes = sizeof(double) * kChebCols * (size_t)moment_grid;
   const size_t range_bytes = (sizeof(float) * 2 * (size_t)range_grid + 15) / 16 * 16;
-  if (rows_bytes + range_bytes + 16 > scratch_bytes) return MNF_OK;
+  const size_t tmax_bytes = (sizeof(float) * (size_t)moment_grid + 15) / 16 * 16;
+  if (rows_bytes + range_bytes + tmax_bytes + 16 > scratch_bytes) return MNF_OK;
   double* rows = reinterpret_cast<double*>(scratch);
   float* range_partial = reinterpret_cast<float*>(scratch + rows_bytes);
-  uint32_t* need_exact = reinterpret_cast<uint32_t*>(scratch + rows_bytes + range_bytes);
+  float* tmax_partial = reinterpret_cast<float*>(scratch + rows_bytes + range_bytes);
+  uint32_t* need_exact = reinterpret_cast<uint32_t*>(scratch + rows_bytes + range_bytes + tmax_bytes);
+  RangeSlot* slot = range_slot(site, stream);
   const size_t smem = poisson_moment_smem_bytes();
   auto moment_kernel = poisson_moment_kernel;
   MNF_CUDA_CHECK(cudaFuncSetAttribute(moment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  poisson_range_kernel<<<range_grid, kChebThreads, 0, stream>>>(site, range_partial);
+  poisson_range_kernel<<<range_grid, kChebThreads, 0, stream>>>(site, range_partial, slot);
   MNF_LAUNCH_CHECK();
-  moment_kernel<<<moment_grid, kChebThreads, smem, stream>>>(site, range_partial, range_grid, z, S, D, rows, status);
+  moment_kernel<<<moment_grid, kChebThreads, smem, stream>>>(site, range_partial, range_grid, slot, z, S, D, rows,
+                                                             tmax_partial, status);
   MNF_LAUNCH_CHECK();
-  poisson_moment_finish_kernel<<<1, kChebThreads, 0, stream>>>(site, rows, moment_grid, range_partial, range_grid,
-                                                              z, S, D, acc, need_exact);
+  poisson_moment_finish_kernel<<<1, kChebThreads, 0, stream>>>(site, rows, moment_grid, range_partial, range_grid, slot,
+                                                              tmax_partial, z, S, D, acc, need_exact);
   MNF_LAUNCH_CHECK();
   *need_exact_out = need_exact;
   return MNF_OK;

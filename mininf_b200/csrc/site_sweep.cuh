@@ -474,11 +474,33 @@ constexpr double kChebMaxTrunc = 1e-9;
 
 struct ChebRange {
   float mid, inv;     // t = (x - mid) * inv
+  float lo, hi;       // the covariate range it was built from
+  bool cached;        // taken from the range slot (not from this step's range pass)
+};
+
+// The covariate range of a site, kept across steps in library-owned device memory (site.cu keys the
+// slots by the covariate / mask addresses and the element count). The covariate is data: it does not
+// change from step to step, so re-reading all of it every step just to find its range was 5 of the
+// 23 bytes per element this path moved. A valid slot makes the range pass return at once; the moment
+// pass then verifies the slot against every live element it reads (max |t|), and the finish kernel
+// drops the slot - and hands the step to the exact kernel - if the data no longer fit (a plan
+// re-bound to other rows), or refreshes it if the data use less than half of it.
+struct RangeSlot {
+  float lo, hi;
+  uint32_t valid;
+  uint32_t pad;
 };
 
 // every CTA reduces the range partials the same way => identical (mid, inv) everywhere
-__device__ __forceinline__ ChebRange cheb_range(const float* __restrict__ range_partial, int n_range, float* s_tmp) {
+__device__ __forceinline__ ChebRange cheb_range(const float* __restrict__ range_partial, int n_range, float* s_tmp,
+                                                const RangeSlot* __restrict__ slot = nullptr) {
   float lo = INFINITY, hi = -INFINITY;
+  const bool cached = slot != nullptr && *reinterpret_cast<const volatile uint32_t*>(&slot->valid) != 0u;
+  if (cached) {
+    lo = *reinterpret_cast<const volatile float*>(&slot->lo);
+    hi = *reinterpret_cast<const volatile float*>(&slot->hi);
+    n_range = 0;
+  }
   for (int b = threadIdx.x; b < n_range; b += blockDim.x) {
     lo = fminf(lo, range_partial[2 * b]);
     hi = fmaxf(hi, range_partial[2 * b + 1]);
@@ -495,6 +517,7 @@ __device__ __forceinline__ ChebRange cheb_range(const float* __restrict__ range_
   for (int w = 0; w < nw; ++w) { lo = fminf(lo, s_tmp[2 * w]); hi = fmaxf(hi, s_tmp[2 * w + 1]); }
   __syncthreads();
   ChebRange r;
+  r.lo = lo; r.hi = hi; r.cached = cached;
   if (!(lo <= hi)) { r.mid = 0.0f; r.inv = 0.0f; return r; }      // no live element
   r.mid = 0.5f * lo + 0.5f * hi;
   const float half = fmaxf(hi - r.mid, r.mid - lo);
@@ -504,7 +527,8 @@ __device__ __forceinline__ ChebRange cheb_range(const float* __restrict__ range_
 
 // min / max of the covariate over the live elements; 128-bit loads (the launcher checks alignment)
 __global__ void __launch_bounds__(kChebThreads)
-poisson_range_kernel(mnf_site_t st, float* __restrict__ range_partial) {
+poisson_range_kernel(mnf_site_t st, float* __restrict__ range_partial, const RangeSlot* __restrict__ slot) {
+  if (slot != nullptr && *reinterpret_cast<const volatile uint32_t*>(&slot->valid) != 0u) return;   // range known
   const int64_t n = st.numel;
   const float* __restrict__ xp = st.param[0].x;
   const uint8_t* __restrict__ mask = st.mask;
@@ -580,8 +604,8 @@ __device__ __noinline__ float poisson_log_factorial_slow(float v) { return log_f
 // cost a third of the occupancy (445 us against 394 us at N = 1e8).
 __global__ void __launch_bounds__(kChebThreads, 3)
 poisson_moment_kernel(mnf_site_t st, const float* __restrict__ range_partial, int n_range,
-                      const float* __restrict__ z, int S, int D,
-                      double* __restrict__ cta_out, uint32_t* __restrict__ status) {
+                      const RangeSlot* __restrict__ slot, const float* __restrict__ z, int S, int D,
+                      double* __restrict__ cta_out, float* __restrict__ tmax_out, uint32_t* __restrict__ status) {
   extern __shared__ double s_mom[];                     // [kChebMoments + 3][kChebThreads] fp64 running sums
   __shared__ float s_tmp[2 * kChebThreads / 32];
   __shared__ float s_logfact[64];
@@ -592,8 +616,9 @@ poisson_moment_kernel(mnf_site_t st, const float* __restrict__ range_partial, in
   const uint8_t* __restrict__ mask = st.mask;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < 64) s_logfact[threadIdx.x] = kLogFactorial[threadIdx.x];
-  const ChebRange range = cheb_range(range_partial, n_range, s_tmp);   // has the block barriers
+  const ChebRange range = cheb_range(range_partial, n_range, s_tmp, slot);   // has the block barriers
   const float mid = range.mid, inv = range.inv;
+  float tmax = 0.0f;                                    // max |t| over the live elements: verifies a cached range
   const int n_moments = cheb_moments_needed(st.param[0], z, S, D, inv, s_tmp);
 #pragma unroll
   for (int j = 0; j < kChebMoments + 3; ++j) s_mom[j * kChebThreads + threadIdx.x] = 0.0;
@@ -635,6 +660,7 @@ poisson_moment_kernel(mnf_site_t st, const float* __restrict__ range_partial, in
         const float t = live ? (x[e] - mid) * inv : 0.0f;
         w0[e] = live ? 1.0f : 0.0f;
         w1[e] = t;
+        tmax = fmaxf(tmax, fabsf(t));
         tp[e] = t + t;
         cnt += live ? 1u : 0u;
         f_v += cv[e];
@@ -714,12 +740,15 @@ poisson_moment_kernel(mnf_site_t st, const float* __restrict__ range_partial, in
     if (lane == 0) out[j] = t;
   }
   const double c = warp_sum((double)cnt);
-  if (lane == 0) s_red[warp] = c;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+  if (lane == 0) { s_red[warp] = c; s_tmp[warp] = tmax; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int w = 0; w < kChebThreads / 32; ++w) t += s_red[w];
+    for (int w = 0; w < kChebThreads / 32; ++w) { t += s_red[w]; tmax = fmaxf(tmax, s_tmp[w]); }
     out[kChebMoments + 3] = t;
+    tmax_out[blockIdx.x] = tmax == tmax ? tmax : INFINITY;    // a NaN covariate must not pass the check
   }
   if (bad_value) atomicOr(status, MNF_ST_BAD_VALUE);
 }
@@ -757,13 +786,24 @@ __device__ inline void bessel_i(double b, int jmax, double* out) {
 // either add the site to the step accumulator (need_exact = 0) or leave it to the exact kernel.
 __global__ void __launch_bounds__(kChebThreads)
 poisson_moment_finish_kernel(mnf_site_t st, const double* __restrict__ cta_rows, int n_cta,
-                             const float* __restrict__ range_partial, int n_range,
+                             const float* __restrict__ range_partial, int n_range, RangeSlot* __restrict__ slot,
+                             const float* __restrict__ tmax_partial,
                              const float* __restrict__ z, int S, int D, double* __restrict__ acc,
                              uint32_t* __restrict__ need_exact) {
   __shared__ double s_tot[kChebCols];
   __shared__ float s_tmp[2 * kChebThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const ChebRange range = cheb_range(range_partial, n_range, s_tmp);
+  const ChebRange range = cheb_range(range_partial, n_range, s_tmp, slot);
+  // the largest |t| the moment pass saw: 1 (up to rounding) when the range is this step's own
+  float tmax = 0.0f;
+  for (int b = threadIdx.x; b < n_cta; b += blockDim.x) tmax = fmaxf(tmax, tmax_partial[b]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+  if (lane == 0) s_tmp[warp] = tmax;
+  __syncthreads();
+  for (int w = 0; w < kChebThreads / 32; ++w) tmax = fmaxf(tmax, s_tmp[w]);
+  __syncthreads();
+  const bool range_ok = tmax <= 1.0f + 1e-5f;
   const int nm = cheb_moments_needed(st.param[0], z, S, D, range.inv, s_tmp);     // moments the sweep kept
   for (int c = warp; c < kChebCols; c += kChebThreads / 32) {
     double t = 0.0;
@@ -810,8 +850,19 @@ poisson_moment_finish_kernel(mnf_site_t st, const double* __restrict__ cta_rows,
       dB = Vx - Rx;
     }
   }
-  const int any_bad = __syncthreads_or(ok ? 0 : 1);
-  if (threadIdx.x == 0) *need_exact = any_bad ? 1u : 0u;
+  const int any_bad = __syncthreads_or(ok && range_ok ? 0 : 1);
+  if (threadIdx.x == 0) {
+    *need_exact = any_bad ? 1u : 0u;
+    if (slot != nullptr) {
+      if (!range.cached) {            // this step ran the range pass: keep its result for the next steps
+        slot->lo = range.lo;
+        slot->hi = range.hi;
+        slot->valid = range.lo <= range.hi ? 1u : 0u;
+      } else if (any_bad || (tmax < 0.5f && range.inv > 0.0f)) {
+        slot->valid = 0u;             // the data left the range (or use little of it): measure it again next step
+      }
+    }
+  }
   if (any_bad || s >= S) return;
   const double w = st.scale;
   double* as = acc + (int64_t)s * (D + 1);

@@ -1014,6 +1014,70 @@ def test_poisson_site_moment_sweep_flags_invalid_counts_and_propagates_nan_covar
         module(mininf.condition(model, counts=counts), approx)
 
 
+def test_poisson_site_moment_sweep_keeps_the_covariate_range_across_steps():
+    """The covariate range of the moment path is kept in a device slot across steps and verified
+    against every live element: repeated steps on the same data are bit-identical to the first
+    (which measured the range), data that leave the cached range are served exactly in the step
+    that meets them and by a freshly measured range afterwards, and data that shrink into a
+    fraction of the range make the next step measure it again. Every value is held to a float64
+    evaluation of the reference algorithm."""
+    from torch.distributions import Normal, Poisson
+    n, S = 200_000, 16
+    g = torch.Generator(device=DEV).manual_seed(123)
+    x = torch.rand(n, generator=g, device=DEV) * 2 - 1
+    counts = torch.poisson(torch.exp(0.2 + 0.4 * x), generator=g)
+    mask = torch.rand(n, generator=g, device=DEV) > 0.3
+    loc = {k: torch.tensor(v, device=DEV) for k, v in (("a", 0.2), ("b", 0.4))}
+    approx = {k: Normal(v, torch.tensor(0.05, device=DEV)) for k, v in loc.items()}
+    gen = torch.Generator().manual_seed(4)
+    noise = {k: torch.randn(S, generator=gen).to(DEV) for k in approx}
+
+    def model():
+        a = mininf.sample("a", Normal(0, 1))
+        b = mininf.sample("b", Normal(0, 1))
+        mininf.sample("counts", Poisson((a + b * x).exp()))
+
+    module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync", closed_form=True)
+
+    def step():
+        return float(module(mininf.condition(model, counts=torch.masked.as_masked_tensor(counts, mask)), approx,
+                            _noise=noise))
+
+    def expected():
+        x64, c64, m = x.double().cpu(), counts.double().cpu(), mask.cpu()
+        total = 0.0
+        for s in range(S):
+            z = {k: float(loc[k]) + 0.05 * float(noise[k][s]) for k in loc}
+            eta = z["a"] + z["b"] * x64[m]
+            total += float((c64[m] * eta - eta.exp() - torch.lgamma(c64[m] + 1)).sum())
+            total += sum(float(Normal(0.0, 1.0).log_prob(torch.tensor(v, dtype=torch.float64))) for v in z.values())
+        entropy = sum(float(d.entropy()) for d in approx.values())
+        return -(total / S + entropy)
+
+    first = step()
+    assert abs(first - expected()) <= 1e-5 * abs(expected())
+    assert step() == first and step() == first                  # cached range: same (mid, 1 / half), same sums
+    x[7] = 3.0                                                   # same tensors, one live element outside the range
+    mask[7] = True
+    counts[7] = 4.0
+    outside = step()                                             # served by the per-particle kernel
+    assert abs(outside - expected()) <= 1e-5 * abs(expected())
+    again = step()                                               # range measured again
+    assert abs(again - expected()) <= 1e-5 * abs(expected())
+    assert step() == again
+    x.mul_(0.1)                                                  # the data now use a tenth of the cached range
+    narrow = step()
+    assert abs(narrow - expected()) <= 1e-5 * abs(expected())
+    assert abs(step() - expected()) <= 1e-5 * abs(expected())
+    # the developer switch gives the uncached path on identical inputs
+    import os
+    os.environ["MNF_POISSON_NO_RANGE_CACHE"] = "1"
+    try:
+        assert abs(step() - expected()) <= 1e-5 * abs(expected())
+    finally:
+        del os.environ["MNF_POISSON_NO_RANGE_CACHE"]
+
+
 # ---------------------------------------------------------------------------------------------
 # full-size properties of the site sweeps (config C5) and the row-latent sweep (config C4)
 # ---------------------------------------------------------------------------------------------
