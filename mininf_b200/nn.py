@@ -113,17 +113,56 @@ def _unwrap_conditioning(model: Callable) -> Tuple[Callable, List[Tuple[str, Any
     return model, pinned
 
 
+def _constant_key(value: Any) -> Tuple:
+    """Fingerprint of something a model function captured: plain Python constants by value (a
+    hyper-parameter changed between steps must retrace - the reference re-runs the model every
+    step, ``mininf/nn.py:223-225``), everything else by identity (tensors are read in place)."""
+    if value is None or isinstance(value, (bool, int, float, complex, str, bytes)):
+        return ("v", type(value).__name__, value)
+    if isinstance(value, (tuple, list)) and len(value) <= 16 and \
+            all(v is None or isinstance(v, (bool, int, float, str)) for v in value):
+        return ("s", type(value).__name__, tuple(value))
+    return ("o", id(value))
+
+
+def _captured_key(function: Any) -> Tuple:
+    """Closure cells, defaults and the plain-constant globals a function names: what the trace of
+    a model depends on besides its conditioned values."""
+    code = getattr(function, "__code__", None)
+    if code is None:
+        return ()
+    captured = []
+    for cell in getattr(function, "__closure__", None) or ():
+        try:
+            captured.append(_constant_key(cell.cell_contents))
+        except ValueError:            # empty cell
+            captured.append(("e",))
+    for default in getattr(function, "__defaults__", None) or ():
+        captured.append(_constant_key(default))
+    for name, default in sorted((getattr(function, "__kwdefaults__", None) or {}).items()):
+        captured.append((name,) + _constant_key(default))
+    namespace = getattr(function, "__globals__", {})
+    for name in code.co_names:
+        value = namespace.get(name, _callable_key)      # sentinel: not a module-level name
+        if value is None or isinstance(value, (bool, int, float, complex, str)):
+            captured.append((name,) + _constant_key(value))
+    return tuple(captured)
+
+
 def _callable_key(model: Callable) -> Tuple:
     """Identity of a model callable that survives re-creation of thin wrappers: a bound method
     (``obj.model``) is a new object on every attribute access and a ``functools.partial`` is often
-    rebuilt per step, so keying the plan cache on ``id(model)`` would retrace every step."""
+    rebuilt per step, so keying the plan cache on ``id(model)`` would retrace every step. Python
+    constants the function captured (closure cells, defaults, module-level scalars it names) are
+    part of the key by VALUE, so changing one between steps traces the model again."""
     import functools
     if isinstance(model, functools.partial):
-        frozen = tuple(id(a) for a in model.args) + tuple((k, id(v)) for k, v in sorted(model.keywords.items()))
+        frozen = tuple(_constant_key(a) for a in model.args) + \
+            tuple((k,) + _constant_key(v) for k, v in sorted(model.keywords.items()))
         return ("partial", _callable_key(model.func), frozen)
     if hasattr(model, "__func__") and hasattr(model, "__self__"):
-        return ("method", id(model.__func__), id(model.__self__))
-    return ("callable", id(model))
+        return ("method", id(model.__func__), id(model.__self__), _captured_key(model.__func__))
+    return ("callable", id(model), _captured_key(model))
 
 
 def _layout_key(value: Any) -> Tuple:

@@ -1014,6 +1014,41 @@ def test_poisson_site_moment_sweep_flags_invalid_counts_and_propagates_nan_covar
         module(mininf.condition(model, counts=counts), approx)
 
 
+def test_python_hyperparameter_changed_between_steps_takes_effect():
+    """The reference re-runs the model every step (mininf/nn.py:223-225); the cached plan must not
+    freeze a Python constant the model captured: the prior scale below is a closure variable."""
+    from torch.distributions import Normal
+    x = torch.randn(500, device=DEV)
+    y = 0.5 * x + torch.randn(500, device=DEV)
+    approx = {"b": Normal(torch.tensor(0.4, device=DEV), torch.tensor(0.2, device=DEV))}
+    noise = {"b": torch.linspace(-1, 1, 8).to(DEV)}
+    prior_scale = 1.0
+
+    def model():
+        b = mininf.sample("b", Normal(0.0, prior_scale))
+        mininf.sample("y", Normal(b * x, 1.0))
+
+    module = mininf.nn.EvidenceLowerBoundLoss(8, check="sync")
+
+    def step():
+        return float(module(mininf.condition(model, y=y), approx, _noise=noise))
+
+    def expected(scale):
+        b = 0.4 + 0.2 * noise["b"].double().cpu()
+        log_prior = Normal(0.0, scale).log_prob(b)
+        resid = y.double().cpu()[None, :] - b[:, None] * x.double().cpu()[None, :]
+        log_lik = Normal(0.0, 1.0).log_prob(resid).sum(1)
+        return -float((log_prior + log_lik).mean() + approx["b"].entropy().double().cpu())
+
+    first = step()
+    assert abs(first - expected(1.0)) <= 1e-5 * abs(expected(1.0))
+    assert step() == first
+    prior_scale = 0.1
+    changed = step()
+    assert abs(changed - expected(0.1)) <= 1e-5 * abs(expected(0.1))
+    assert abs(changed - first) > 1.0
+
+
 def test_poisson_site_moment_sweep_keeps_the_covariate_range_across_steps():
     """The covariate range of the moment path is kept in a device slot across steps and verified
     against every live element: repeated steps on the same data are bit-identical to the first
