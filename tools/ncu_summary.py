@@ -38,8 +38,11 @@ KEEP = [
 def main() -> None:
     report, out_prefix, title = sys.argv[1], sys.argv[2], sys.argv[3]
     command = sys.argv[4] if len(sys.argv) > 4 else ""
-    raw = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"], capture_output=True, text=True,
-                         check=True).stdout
+    if report.endswith(".csv"):       # the raw page, already exported on the GPU box (reports are ~18 MB each)
+        raw = open(report).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"], capture_output=True, text=True,
+                             check=True).stdout
     open(out_prefix + "_ncu_raw.csv", "w").write(raw)
     rows = list(csv.reader(raw.splitlines()))
     header, units, values = rows[0], rows[1], rows[2]
