@@ -76,7 +76,7 @@ __device__ __forceinline__ T warp_sum(T v) {
 // ---------------------------------------------------------------------------------------------
 // digamma / trigamma by upward recurrence to x >= 6 and the asymptotic series. Evaluated in fp64
 // when called from the O(D) kernels (entropy, implicit gradients), fp32-accurate either way.
-__device__ inline double digamma_d(double x) {
+static __device__ __noinline__ double digamma_d(double x) {
   if (x <= 0.0 && floor(x) == x) return INFINITY;
   double r = 0.0;
   if (x < 0.0) {  // reflection
@@ -94,7 +94,7 @@ __device__ inline double digamma_d(double x) {
   return r + log(x) - 0.5 / x + t;
 }
 
-__device__ inline double trigamma_d(double x) {
+static __device__ __noinline__ double trigamma_d(double x) {
   double r = 0.0;
   while (x < 6.0) {
     r += 1.0 / (x * x);

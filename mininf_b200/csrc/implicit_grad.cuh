@@ -15,7 +15,7 @@
 namespace mnf {
 
 // d/dalpha of a standard Gamma(alpha, 1) draw x.   ATen Distributions.h:303-369
-__device__ inline double standard_gamma_grad(double alpha, double x) {
+static __device__ __noinline__ double standard_gamma_grad(double alpha, double x) {
   if (x < 0.8) {
     // Taylor series of the lower incomplete gamma function around x = 0.
     double term = 1.0, a = alpha;
@@ -133,7 +133,7 @@ __device__ inline double beta_grad_a_mid(double x, double a, double b) {
 
 // Scaled gradient  -(dCDF/dalpha)/pdf/(1-x)  of a Beta(alpha, total-alpha) draw x, the quantity
 // `torch._dirichlet_grad` returns element-wise.                  ATen Distributions.h:453-511
-__device__ inline double dirichlet_grad(double x, double alpha, double total) {
+static __device__ __noinline__ double dirichlet_grad(double x, double alpha, double total) {
   const double beta = total - alpha;
   const double boundary = total * x * (1.0 - x);
   if (x <= 0.5 && boundary < 2.5) return beta_grad_a_small(x, alpha, beta);

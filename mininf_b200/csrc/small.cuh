@@ -316,6 +316,82 @@ __device__ __forceinline__ double load_acc(const double* p) {
   else return __ldcg(p);
 }
 
+// Gamma / Beta columns of finalize_block, kept OUT OF LINE: the tail kernel runs once per step with a
+// cold instruction cache, and its time follows its code size (22 K instructions: 32 us at C2; with the
+// fp64 special functions and this block out of line: 13 K and 24 us). One WARP per column, lanes over
+// the particles (the implicit reparameterisation gradients are ~100 fp64 operations per particle).
+template <bool STAGED>
+static __device__ __noinline__ void finalize_other_columns(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
+                                                           const float* noise, const double* acc, int with_entropy,
+                                                           float* __restrict__ out, const AdamArgs& adam, double bc1,
+                                                           double bc2_sqrt, double* ent_io, bool* nonfinite_io) {
+  const int kWarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double invS = 1.0 / (double)S;
+  double ent = 0.0;
+  bool nonfinite = false;
+  for (int d = warp; d < D; d += kWarps) {
+    const mnf_latent_t L = lat[find_latent(lat, n_lat, d)];
+    if (L.family == MNF_NORMAL) continue;
+    const int e = d - L.offset;
+    const double p0 = (double)L.p0[e], p1 = (double)L.p1[e];
+    double g0 = 0.0, g1 = 0.0;
+    if (L.family == MNF_GAMMA) {
+      // z = g/rate: dz/dalpha = standard_gamma_grad(alpha, g)/rate, dz/drate = -g/rate^2
+      // (the clamp_ at tiny is outside autograd: gradients as if unclamped)
+      for (int s = lane; s < S; s += 32) {
+        const double g = load_acc<STAGED>(acc + (int64_t)s * (D + 1) + 1 + d);
+        const double gam = (double)noise[(int64_t)s * D + d];
+        g0 += g * standard_gamma_grad(p0, gam) / p1;
+        g1 += g * (-gam / (p1 * p1));
+      }
+    } else {
+      // Beta(c1 = p0, c0 = p1) as a 2-simplex Dirichlet; _Dirichlet backward dirichlet.py:16-35:
+      // grad_k = dirichlet_grad(x_k, c_k, total) * (go_k - sum_j x_j go_j) with go = (g, 0).
+      const double tot = p0 + p1;
+      for (int s = lane; s < S; s += 32) {
+        const double g = load_acc<STAGED>(acc + (int64_t)s * (D + 1) + 1 + d);
+        const double x = (double)noise[(int64_t)s * D + d];
+        g0 += dirichlet_grad(x, p0, tot) * g * (1.0 - x);
+        g1 += dirichlet_grad(1.0 - x, p1, tot) * (-x * g);
+      }
+    }
+    g0 = warp_sum(g0);
+    g1 = warp_sum(g1);
+    if (lane == 0) {
+      double h = 0.0, dh0 = 0.0, dh1 = 0.0;
+      if (L.family == MNF_GAMMA) {
+        // H = alpha - log(rate) + lgamma(alpha) + (1-alpha) digamma(alpha)   TORCH gamma.py:100-106
+        h = p0 - log(p1) + lgamma(p0) + (1.0 - p0) * digamma_d(p0);
+        dh0 = 1.0 + (1.0 - p0) * trigamma_d(p0);
+        dh1 = -1.0 / p1;
+      } else {
+        // Dirichlet entropy with k = 2                                TORCH dirichlet.py:122-130
+        const double tot = p0 + p1;
+        const double dt = digamma_d(tot);
+        h = lgamma(p0) + lgamma(p1) - lgamma(tot) - (p0 - 1.0) * digamma_d(p0) -
+            (p1 - 1.0) * digamma_d(p1) + (tot - 2.0) * dt;
+        const double tt = trigamma_d(tot);
+        dh0 = -(p0 - 1.0) * trigamma_d(p0) + (tot - 2.0) * tt;
+        dh1 = -(p1 - 1.0) * trigamma_d(p1) + (tot - 2.0) * tt;
+      }
+      if (!with_entropy) { h = 0.0; dh0 = 0.0; dh1 = 0.0; }
+      ent += h;
+      const double o0 = -(g0 * invS + dh0);
+      const double o1 = -(g1 * invS + dh1);
+      if (!isfinite(o0) || !isfinite(o1)) nonfinite = true;
+      out[1 + d] = (float)o0;
+      out[1 + D + d] = (float)o1;
+      if (adam.raw != nullptr) {
+        adam_update(adam, d, (float)p0, o0, bc1, bc2_sqrt);
+        adam_update(adam, D + d, (float)p1, o1, bc1, bc2_sqrt);
+      }
+    }
+  }
+  *ent_io += ent;
+  *nonfinite_io = *nonfinite_io || nonfinite;
+}
+
 template <bool STAGED>
 __device__ inline void finalize_block(const mnf_latent_t* __restrict__ lat, int n_lat, int S, int D,
                                       const float* z, const float* noise,
@@ -389,65 +465,12 @@ __device__ inline void finalize_block(const mnf_latent_t* __restrict__ lat, int 
       adam_update(adam, D + d, (float)p1, o1, bc1, bc2_sqrt);
     }
   }
-  // ---- Gamma / Beta columns: one WARP per column, lanes over the particles (the implicit
-  // reparameterisation gradients are ~100 fp64 operations per particle)
-  for (int d = warp; d < D; d += kWarps) {
-    const mnf_latent_t L = lat[find_latent(lat, n_lat, d)];
-    if (L.family == MNF_NORMAL) continue;
-    const int e = d - L.offset;
-    const double p0 = (double)L.p0[e], p1 = (double)L.p1[e];
-    double g0 = 0.0, g1 = 0.0;
-    if (L.family == MNF_GAMMA) {
-      // z = g/rate: dz/dalpha = standard_gamma_grad(alpha, g)/rate, dz/drate = -g/rate^2
-      // (the clamp_ at tiny is outside autograd: gradients as if unclamped)
-      for (int s = lane; s < S; s += 32) {
-        const double g = load_acc<STAGED>(acc + (int64_t)s * (D + 1) + 1 + d);
-        const double gam = (double)noise[(int64_t)s * D + d];
-        g0 += g * standard_gamma_grad(p0, gam) / p1;
-        g1 += g * (-gam / (p1 * p1));
-      }
-    } else {
-      // Beta(c1 = p0, c0 = p1) as a 2-simplex Dirichlet; _Dirichlet backward dirichlet.py:16-35:
-      // grad_k = dirichlet_grad(x_k, c_k, total) * (go_k - sum_j x_j go_j) with go = (g, 0).
-      const double tot = p0 + p1;
-      for (int s = lane; s < S; s += 32) {
-        const double g = load_acc<STAGED>(acc + (int64_t)s * (D + 1) + 1 + d);
-        const double x = (double)noise[(int64_t)s * D + d];
-        g0 += dirichlet_grad(x, p0, tot) * g * (1.0 - x);
-        g1 += dirichlet_grad(1.0 - x, p1, tot) * (-x * g);
-      }
-    }
-    g0 = warp_sum(g0);
-    g1 = warp_sum(g1);
-    if (lane == 0) {
-      double h = 0.0, dh0 = 0.0, dh1 = 0.0;
-      if (L.family == MNF_GAMMA) {
-        // H = alpha - log(rate) + lgamma(alpha) + (1-alpha) digamma(alpha)   TORCH gamma.py:100-106
-        h = p0 - log(p1) + lgamma(p0) + (1.0 - p0) * digamma_d(p0);
-        dh0 = 1.0 + (1.0 - p0) * trigamma_d(p0);
-        dh1 = -1.0 / p1;
-      } else {
-        // Dirichlet entropy with k = 2                                TORCH dirichlet.py:122-130
-        const double tot = p0 + p1;
-        const double dt = digamma_d(tot);
-        h = lgamma(p0) + lgamma(p1) - lgamma(tot) - (p0 - 1.0) * digamma_d(p0) -
-            (p1 - 1.0) * digamma_d(p1) + (tot - 2.0) * dt;
-        const double tt = trigamma_d(tot);
-        dh0 = -(p0 - 1.0) * trigamma_d(p0) + (tot - 2.0) * tt;
-        dh1 = -(p1 - 1.0) * trigamma_d(p1) + (tot - 2.0) * tt;
-      }
-      if (!with_entropy) { h = 0.0; dh0 = 0.0; dh1 = 0.0; }
-      ent += h;
-      const double o0 = -(g0 * invS + dh0);
-      const double o1 = -(g1 * invS + dh1);
-      if (!isfinite(o0) || !isfinite(o1)) nonfinite = true;
-      out[1 + d] = (float)o0;
-      out[1 + D + d] = (float)o1;
-      if (adam.raw != nullptr) {
-        adam_update(adam, d, (float)p0, o0, bc1, bc2_sqrt);
-        adam_update(adam, D + d, (float)p1, o1, bc1, bc2_sqrt);
-      }
-    }
+  // ---- Gamma / Beta columns (out of line, skipped when every latent is Normal)
+  {
+    bool any_other = false;
+    for (int i = 0; i < n_lat; ++i) any_other = any_other || lat[i].family != MNF_NORMAL;
+    if (any_other)
+      finalize_other_columns<STAGED>(lat, n_lat, S, D, noise, acc, with_entropy, out, adam, bc1, bc2_sqrt, &ent, &nonfinite);
   }
   // total log joint over particles: warp 0's lanes, added to its entropy share
   if (warp == 0) {
