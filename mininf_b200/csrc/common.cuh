@@ -162,10 +162,15 @@ struct Philox {
     const uint32_t n2 = hi0 ^ c[3] ^ k[1];
     c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
   }
+  // ROUNDS = 10 is the standard generator (and torch's); 7 is the smallest round count of Salmon et
+  // al. (SC'11, table 2) that passes BigCrush ("Crush-resistant"), offered by Random123 as
+  // philox4x32_7. The row-latent sweep draws S * N * p = 1e10 normals per step and is bound by
+  // instruction issue, a fifth of it Philox rounds: it uses 7 (rowlatent.cuh); everything else 10.
+  template <int ROUNDS = 10>
   __device__ __forceinline__ uint4 next() {
     uint32_t k0 = k[0], k1 = k[1];
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
       round_once();
       k[0] += 0x9E3779B9u;
       k[1] += 0xBB67AE85u;

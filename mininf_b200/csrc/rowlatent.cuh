@@ -7,7 +7,7 @@
 // the entropy of q(Z) (TORCH normal.py:114-115) and autograd's n*p-sized gradient passes.
 //
 // Mapping: a warp owns a row, lane j owns feature j. Per row a lane keeps loc, scale and feature
-// in registers and loops over the particles in groups of four (one Philox4x32-10 call -> two
+// in registers and loops over the particles in groups of four (one Philox4x32-7 call -> two
 // Box-Muller pairs). The kernel is instruction-bound, so the per-(element, particle)
 // work is cut to what cannot be shared:
 //   * with z = loc + scale eps the feature site needs only E1 = sum_s eps, E2 = sum_s eps^2 per
@@ -27,6 +27,12 @@
 #include "common.cuh"
 
 namespace mnf {
+
+#ifndef MNF_ROWLATENT_PHILOX_ROUNDS
+#define MNF_ROWLATENT_PHILOX_ROUNDS 7
+#endif
+constexpr int kRowLatentPhiloxRounds = MNF_ROWLATENT_PHILOX_ROUNDS;   // see common.cuh::Philox::next
+
 
 constexpr int kRowThreads = 128;
 constexpr int kRowWarps = kRowThreads / 32;
@@ -208,7 +214,7 @@ rowlatent_kernel(mnf_rowlatent_t d, const float* __restrict__ z, int S, int D, i
 #pragma unroll
       for (int q = 0; q < SP / 4; ++q) {
         Philox rng(seed, offset, kPhiloxRowLatent | ((uint64_t)e << 8) | (uint64_t)((s_begin >> 2) + q));
-        const uint4 r = rng.next();
+        const uint4 r = rng.next<kRowLatentPhiloxRounds>();
         const float2 n0 = box_muller_fast(r.x, r.y), n1 = box_muller_fast(r.z, r.w);
         eps_r[4 * q + 0] = n0.x; eps_r[4 * q + 1] = n0.y; eps_r[4 * q + 2] = n1.x; eps_r[4 * q + 3] = n1.y;
       }
