@@ -89,19 +89,23 @@ RangeSlot* range_slot(const mnf_site_t& site, cudaStream_t stream) {
   RangeSlots& rs = g_range_slots[device];
   for (int i = 0; i < rs.used; ++i)
     if (rs.keys[i].x == site.param[0].x && rs.keys[i].mask == site.mask && rs.keys[i].n == site.numel) return rs.dev + i;
+  // the cache is an optimisation: any failure below means "run uncached" and must not leave an error
+  // behind for the launch checks of the sweep
+  auto uncached = [] { (void)cudaGetLastError(); return static_cast<RangeSlot*>(nullptr); };
   cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
-  if (cudaStreamIsCapturing(stream, &capturing) != cudaSuccess || capturing != cudaStreamCaptureStatusNone) return nullptr;
+  if (cudaStreamIsCapturing(stream, &capturing) != cudaSuccess) return uncached();
+  if (capturing != cudaStreamCaptureStatusNone) return nullptr;
   if (rs.dev == nullptr) {
-    if (cudaMalloc(&rs.dev, sizeof(RangeSlot) * RangeSlots::kSlots) != cudaSuccess) { rs.dev = nullptr; return nullptr; }
-    if (cudaMemset(rs.dev, 0, sizeof(RangeSlot) * RangeSlots::kSlots) != cudaSuccess) return nullptr;
+    if (cudaMalloc(&rs.dev, sizeof(RangeSlot) * RangeSlots::kSlots) != cudaSuccess) { rs.dev = nullptr; return uncached(); }
+    if (cudaMemset(rs.dev, 0, sizeof(RangeSlot) * RangeSlots::kSlots) != cudaSuccess) return uncached();
   }
   if (rs.used == RangeSlots::kSlots) {      // full: start over (the slots revalidate themselves)
-    if (cudaMemset(rs.dev, 0, sizeof(RangeSlot) * RangeSlots::kSlots) != cudaSuccess) return nullptr;
+    if (cudaMemset(rs.dev, 0, sizeof(RangeSlot) * RangeSlots::kSlots) != cudaSuccess) return uncached();
     rs.used = 0;
   }
+  if (cudaMemsetAsync(rs.dev + rs.used, 0, sizeof(RangeSlot), stream) != cudaSuccess) return uncached();
   const int i = rs.used++;
   rs.keys[i] = {site.param[0].x, site.mask, site.numel};
-  if (cudaMemsetAsync(rs.dev + i, 0, sizeof(RangeSlot), stream) != cudaSuccess) return nullptr;
   return rs.dev + i;
 }
 
