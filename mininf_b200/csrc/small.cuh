@@ -225,8 +225,27 @@ __device__ inline void small_sites_block(const mnf_site_t* __restrict__ sites, i
                                          int S, int D, double* __restrict__ acc, uint32_t* __restrict__ status) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   uint32_t bad = 0;
+  // Short sites (the scalar priors of most models): one THREAD per (site, particle), all pairs at once.
+  // A warp per pair left 31 lanes idle and walked the pairs in rounds of n_warps, each round a chain of
+  // dependent loads and five fp64 shuffle reductions: 5 scalar priors x 64 particles took 38 us of the
+  // C5 tail kernel (75 000 cycles); this pass takes one round.
+  constexpr int64_t kShortSite = 4;
+  for (int task = threadIdx.x; task < n_sites * S; task += blockDim.x) {
+    const mnf_site_t site = sites[task / S];
+    if (site.numel > kShortSite) continue;
+    const int s = task % S;
+    double* as = acc + (int64_t)s * (D + 1);
+    SmallSums t = small_site_elements(site, z + (int64_t)s * D, as, 0, 1, bad);
+    const double sums[5] = {t.lp, (double)t.gA0, (double)t.gB0, (double)t.gA1, (double)t.gB1};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int target = small_site_target(site, k);
+      if (target >= 0 && sums[k] != 0.0) atomicAdd(as + target, site.scale * sums[k]);
+    }
+  }
   for (int task = warp; task < n_sites * S; task += n_warps) {
     const mnf_site_t site = sites[task / S];
+    if (site.numel <= kShortSite) continue;
     const int s = task % S;
     const float* zs = z + (int64_t)s * D;
     double* as = acc + (int64_t)s * (D + 1);
@@ -409,11 +428,12 @@ __device__ inline void finalize_block(const mnf_latent_t* __restrict__ lat, int 
     bias[0] = 1.0;
     bias[1] = 1.0;
     if (adam.raw != nullptr) {
-      // 1 - beta^t through expm1 / log in fp32 pieces would lose the small-t digits; one fp64 exp of
-      // t * log(beta) (log taken once, in fp64) is exact enough and a fraction of two fp64 pow calls
-      const double t = (double)(*adam.step + 1);
-      bias[0] = -expm1(t * log((double)adam.beta1));
-      bias[1] = sqrt(-expm1(t * log((double)adam.beta2)));
+      // 1 - beta^t = -expm1(t log beta): expm1f keeps the small-t digits (relative error ~2e-7, far
+      // below what a step of lr * m / sqrt(v) resolves); the fp64 versions were ~3000 dependent cycles
+      // in front of a block-wide barrier
+      const float t = (float)(*adam.step + 1);
+      bias[0] = (double)-expm1f(t * logf(adam.beta1));
+      bias[1] = (double)sqrtf(-expm1f(t * logf(adam.beta2)));
     }
   }
   __syncthreads();
@@ -600,6 +620,9 @@ tail_kernel(XrankArgs xr, const mnf_site_t* __restrict__ global_sites, int n_glo
     double* acc_s = reinterpret_cast<double*>(tail_smem);
     float* noise_s = reinterpret_cast<float*>(acc_s + (size_t)S * (D + 1));
     float* z_s = noise_s + (size_t)S * D;
+#ifdef MNF_TAIL_DEBUG
+    const long long t0 = clock64();
+#endif
     if (xr.world > 1) {
       xrank_gather_block(xr, acc, acc_s, status);
     } else {
@@ -610,11 +633,21 @@ tail_kernel(XrankArgs xr, const mnf_site_t* __restrict__ global_sites, int n_glo
       z_s[i] = z[i];
     }
     __syncthreads();
+#ifdef MNF_TAIL_DEBUG
+    const long long t1 = clock64();
+#endif
     if (n_global > 0) {
       small_sites_block(global_sites, n_global, z_s, S, D, acc_s, status);
       __syncthreads();
     }
+#ifdef MNF_TAIL_DEBUG
+    const long long t2 = clock64();
+#endif
     finalize_block<true>(lat, n_lat, S, D, z_s, noise_s, acc_s, with_entropy, out, step_counter, status, adam);
+#ifdef MNF_TAIL_DEBUG
+    __syncthreads();
+    if (threadIdx.x == 0) printf("tail: stage %lld  prior sites %lld  finalize %lld cycles (n_global %d, n_lat %d, S %d, D %d)\n", t1 - t0, t2 - t1, clock64() - t2, n_global, n_lat, S, D);
+#endif
   } else {
     if (xr.world > 1) xrank_gather_block(xr, acc, acc, status);
     if (n_global > 0) {
