@@ -344,21 +344,27 @@ static __device__ __noinline__ void finalize_other_columns(const mnf_latent_t* _
                                                            const float* noise, const double* acc, int with_entropy,
                                                            float* __restrict__ out, const AdamArgs& adam, double bc1,
                                                            double bc2_sqrt, double* ent_io, bool* nonfinite_io) {
+  // One column at a time, the whole block on it: the particles spread over the threads (one fp64
+  // implicit-gradient evaluation per thread instead of S / 32 in a row per lane: the three regimes of
+  // standard_gamma_grad diverge inside a warp, so a warp pays for all of them per round), the entropy
+  // terms (lgamma / digamma / trigamma) on the last warp at the same time. Fixed-order sums.
+  __shared__ double s_part[32][2];
+  __shared__ double s_h[3];
   const int kWarps = blockDim.x >> 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double invS = 1.0 / (double)S;
   double ent = 0.0;
   bool nonfinite = false;
-  for (int d = warp; d < D; d += kWarps) {
+  for (int d = 0; d < D; ++d) {
     const mnf_latent_t L = lat[find_latent(lat, n_lat, d)];
-    if (L.family == MNF_NORMAL) continue;
+    if (L.family == MNF_NORMAL) continue;          // uniform over the block
     const int e = d - L.offset;
     const double p0 = (double)L.p0[e], p1 = (double)L.p1[e];
     double g0 = 0.0, g1 = 0.0;
     if (L.family == MNF_GAMMA) {
       // z = g/rate: dz/dalpha = standard_gamma_grad(alpha, g)/rate, dz/drate = -g/rate^2
       // (the clamp_ at tiny is outside autograd: gradients as if unclamped)
-      for (int s = lane; s < S; s += 32) {
+      for (int s = threadIdx.x; s < S; s += blockDim.x) {
         const double g = load_acc<STAGED>(acc + (int64_t)s * (D + 1) + 1 + d);
         const double gam = (double)noise[(int64_t)s * D + d];
         g0 += g * standard_gamma_grad(p0, gam) / p1;
@@ -368,7 +374,7 @@ static __device__ __noinline__ void finalize_other_columns(const mnf_latent_t* _
       // Beta(c1 = p0, c0 = p1) as a 2-simplex Dirichlet; _Dirichlet backward dirichlet.py:16-35:
       // grad_k = dirichlet_grad(x_k, c_k, total) * (go_k - sum_j x_j go_j) with go = (g, 0).
       const double tot = p0 + p1;
-      for (int s = lane; s < S; s += 32) {
+      for (int s = threadIdx.x; s < S; s += blockDim.x) {
         const double g = load_acc<STAGED>(acc + (int64_t)s * (D + 1) + 1 + d);
         const double x = (double)noise[(int64_t)s * D + d];
         g0 += dirichlet_grad(x, p0, tot) * g * (1.0 - x);
@@ -377,7 +383,8 @@ static __device__ __noinline__ void finalize_other_columns(const mnf_latent_t* _
     }
     g0 = warp_sum(g0);
     g1 = warp_sum(g1);
-    if (lane == 0) {
+    if (lane == 0) { s_part[warp][0] = g0; s_part[warp][1] = g1; }
+    if (warp == kWarps - 1 && lane == 0) {
       double h = 0.0, dh0 = 0.0, dh1 = 0.0;
       if (L.family == MNF_GAMMA) {
         // H = alpha - log(rate) + lgamma(alpha) + (1-alpha) digamma(alpha)   TORCH gamma.py:100-106
@@ -395,9 +402,15 @@ static __device__ __noinline__ void finalize_other_columns(const mnf_latent_t* _
         dh1 = -(p1 - 1.0) * trigamma_d(p1) + (tot - 2.0) * tt;
       }
       if (!with_entropy) { h = 0.0; dh0 = 0.0; dh1 = 0.0; }
-      ent += h;
-      const double o0 = -(g0 * invS + dh0);
-      const double o1 = -(g1 * invS + dh1);
+      s_h[0] = h; s_h[1] = dh0; s_h[2] = dh1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      g0 = 0.0; g1 = 0.0;
+      for (int w = 0; w < kWarps; ++w) { g0 += s_part[w][0]; g1 += s_part[w][1]; }
+      ent += s_h[0];
+      const double o0 = -(g0 * invS + s_h[1]);
+      const double o1 = -(g1 * invS + s_h[2]);
       if (!isfinite(o0) || !isfinite(o1)) nonfinite = true;
       out[1 + d] = (float)o0;
       out[1 + D + d] = (float)o1;
@@ -406,6 +419,7 @@ static __device__ __noinline__ void finalize_other_columns(const mnf_latent_t* _
         adam_update(adam, D + d, (float)p1, o1, bc1, bc2_sqrt);
       }
     }
+    __syncthreads();     // s_part / s_h are reused by the next column
   }
   *ent_io += ent;
   *nonfinite_io = *nonfinite_io || nonfinite;
@@ -437,6 +451,9 @@ __device__ inline void finalize_block(const mnf_latent_t* __restrict__ lat, int 
     }
   }
   __syncthreads();
+#ifdef MNF_TAIL_DEBUG
+  const long long f0 = clock64();
+#endif
   const double bc1 = bias[0], bc2_sqrt = bias[1];
   const double invS = 1.0 / (double)S;
   double ent = 0.0;        // this thread's share of the entropy (+ warp 0: the log joint)
@@ -485,6 +502,10 @@ __device__ inline void finalize_block(const mnf_latent_t* __restrict__ lat, int 
       adam_update(adam, D + d, (float)p1, o1, bc1, bc2_sqrt);
     }
   }
+#ifdef MNF_TAIL_DEBUG
+  __syncthreads();
+  const long long f1 = clock64();
+#endif
   // ---- Gamma / Beta columns (out of line, skipped when every latent is Normal)
   {
     bool any_other = false;
@@ -492,6 +513,11 @@ __device__ inline void finalize_block(const mnf_latent_t* __restrict__ lat, int 
     if (any_other)
       finalize_other_columns<STAGED>(lat, n_lat, S, D, noise, acc, with_entropy, out, adam, bc1, bc2_sqrt, &ent, &nonfinite);
   }
+#ifdef MNF_TAIL_DEBUG
+  __syncthreads();
+  const long long f2 = clock64();
+  if (threadIdx.x == 0) printf("finalize: normal columns %lld  other columns %lld cycles\n", f1 - f0, f2 - f1);
+#endif
   // total log joint over particles: warp 0's lanes, added to its entropy share
   if (warp == 0) {
     double lj = 0.0;
@@ -616,6 +642,14 @@ tail_kernel(XrankArgs xr, const mnf_site_t* __restrict__ global_sites, int n_glo
             const float* __restrict__ noise, double* __restrict__ acc, int with_entropy, float* __restrict__ out,
             uint64_t* __restrict__ step_counter, uint32_t* __restrict__ status, AdamArgs adam) {
   extern __shared__ __align__(16) unsigned char tail_smem[];
+  // the latent table is read with dependent loads by every phase below (find_latent walks it): a copy
+  // in shared memory takes those round trips to L2 off the kernel's latency chain
+  constexpr int kLatStaged = 32;
+  __shared__ mnf_latent_t s_lat[kLatStaged];
+  if (n_lat <= kLatStaged) {
+    for (int i = threadIdx.x; i < n_lat; i += kTailThreads) s_lat[i] = lat[i];
+    lat = s_lat;      // visible after the first barrier below (every path has one before the table is read)
+  }
   if constexpr (STAGED) {
     double* acc_s = reinterpret_cast<double*>(tail_smem);
     float* noise_s = reinterpret_cast<float*>(acc_s + (size_t)S * (D + 1));
