@@ -162,7 +162,12 @@ def _callable_key(model: Callable) -> Tuple:
         return ("partial", _callable_key(model.func), frozen)
     if hasattr(model, "__func__") and hasattr(model, "__self__"):
         return ("method", id(model.__func__), id(model.__self__), _captured_key(model.__func__))
-    return ("callable", id(model), _captured_key(model))
+    code = getattr(model, "__code__", None)
+    if code is not None:
+        # a plain function or lambda: the code object plus what it captured. A lambda re-created in every
+        # loop iteration (`condition(lambda: model(x), ...)`) keeps its code object, so it does not retrace.
+        return ("function", id(code), _captured_key(model))
+    return ("callable", id(model))
 
 
 def _layout_key(value: Any) -> Tuple:

@@ -72,3 +72,18 @@ def test_recreated_wrappers_keep_the_key_and_objects_enter_by_identity():
     assert _callable_key(functools.partial(model, payload, big, flag=False)) != _callable_key(a)
     assert _callable_key(functools.partial(model, [1.0, "b"], big, flag=True)) != _callable_key(a)
     assert _callable_key(functools.partial(model, payload, object(), flag=True)) != _callable_key(a)
+
+
+def test_a_lambda_recreated_per_step_keeps_the_key():
+    payload = object()
+
+    def make():
+        return lambda: payload
+
+    assert _callable_key(make()) == _callable_key(make())        # same code object, same captured object
+    other = object()
+
+    def make_other():
+        return lambda: other
+
+    assert _callable_key(make()) != _callable_key(make_other())
