@@ -293,6 +293,10 @@ class Plan:
                 raise NotImplementedError(
                     f"{what} is not a supported link of the latent variables (supported: a latent "
                     "itself, constants, data, `c + d*x`, `exp(a + b*x)`, `X @ theta`)")
+            if expr.transform not in ("id", "exp"):
+                raise NotImplementedError(
+                    f"{what}: `{expr.transform}` of a latent-dependent tensor is not a supported link "
+                    "here (sigmoid only as Bernoulli(probs=sigmoid(...)))")
             link = abi.Link(a_const=expr.a_const, b_const=expr.b_const, a_lat=-1, b_lat=-1,
                             a_stride=0, b_stride=0, x=None, x_stride=0,
                             transform=abi.T_EXP if expr.transform == "exp" else abi.T_ID)
@@ -343,6 +347,14 @@ class Plan:
                                       "(supported: Normal, Gamma, Beta, Bernoulli, Poisson)")
         if dist.event_shape:
             raise NotImplementedError(f"{what}: event-shaped distributions are not supported")
+        if family == abi.BERNOULLI_PROBS and isinstance(params[0], LinkTensor) and \
+                getattr(params[0]._expr, "transform", None) == "sigmoid":
+            # Bernoulli(probs=sigmoid(eta)) is Bernoulli(logits=eta). The reference goes through
+            # probs_to_logits (TORCH distributions/utils.py: clamp to [eps, 1 - eps], log p - log1p(-p)),
+            # which agrees with the logits form to fp32 rounding for |eta| < 15 and saturates beyond.
+            family = abi.BERNOULLI_LOGITS
+            params = (LinkTensor.wrap(params[0].unwrap(),
+                                      dataclasses.replace(params[0]._expr, transform="id")),)
 
         if self._lower_row_latent(record, family, params, what):
             return
@@ -445,7 +457,8 @@ class Plan:
             desc = self.row_groups[spec.name]
             if beta.numel != desc.p or value.numel() != desc.n_rows:
                 raise NotImplementedError(f"{what}: shapes of Z, beta and the response do not match")
-            ok = (family == abi.POISSON) or (family in (abi.NORMAL, abi.BERNOULLI_LOGITS) and expr.transform == "id")
+            ok = (family == abi.POISSON and expr.transform in ("id", "exp")) or \
+                (family in (abi.NORMAL, abi.BERNOULLI_LOGITS) and expr.transform == "id")
             if not ok:
                 raise NotImplementedError(f"{what}: `Z @ beta` supports Poisson, Normal(loc) and Bernoulli(logits)")
             data = _f32(value, self.device)

@@ -14,6 +14,7 @@ CUDA tensors only; the host loop of :func:`mininf_b200.core.broadcast_samples` s
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 from typing import Any, Callable, Dict, List, Optional, Tuple
 
 import torch
@@ -165,6 +166,14 @@ def broadcast_samples(model: Callable, states: Dict[str, torch.Tensor]) -> State
                            for p in params)
             first = params[0]
         expr = getattr(first, "_expr", None) if isinstance(first, LinkTensor) else None
+        if kind == "draw" and site.family == abi.BERNOULLI_PROBS and getattr(expr, "transform", None) == "sigmoid":
+            # Bernoulli(probs=sigmoid(eta)) draws as Bernoulli(logits=eta), like Plan._lower scores it
+            site.family = abi.BERNOULLI_LOGITS
+            expr = dataclasses.replace(expr, transform="id")
+            first = LinkTensor.wrap(first.unwrap(), expr)
+        if getattr(expr, "transform", "id") not in ("id", "exp"):
+            raise NotImplementedError(f"{what}: `{expr.transform}` of a sample-dependent tensor is not a supported "
+                                      "link here (sigmoid only as Bernoulli(probs=sigmoid(...)))")
         if isinstance(expr, Dense):
             X = expr.X.detach().to(device=device, dtype=torch.float32).contiguous()
             lower.keepalive.append(X)

@@ -9,7 +9,9 @@ expression* describing how the value was built from latents and data. The closed
 forms is what the CUDA kernels implement (include/mininf_b200.h):
 
 * ``Affine``:  ``T(a_const + a_lat + (b_const + b_lat) * x)`` - constants, data tensors, a latent
-  itself, ``c + d*x``, ``exp(a + b*x)``;
+  itself, ``c + d*x``, ``exp(a + b*x)``, and what reduces to it: ``-z``, ``c*z``, ``z/c``, ``z/x``,
+  ``a - b*x``, ``c - x``, ``(c + z)*x`` (a scaled latent moves to the slope, the constant or the
+  product of data tensors becomes its covariate);
 * ``Dense``:   ``T(icpt + X @ theta)`` - ``X @ theta`` with an optional scalar intercept;
 * ``RowDot``:  ``T(icpt + Z @ beta)`` - a per-observation latent matrix times a latent vector.
 
@@ -279,13 +281,54 @@ def _rule_add(args, kwargs, raw):
     return _combine_add(_lift(args[0], raw), _lift(args[1], raw), raw.shape)
 
 
+def _scale_const(expr: Expr, c: float, raw: torch.Tensor) -> Expr:
+    """c * expr for a Python constant. The link form has no coefficient on ``a_lat``, so a scaled
+    latent moves to the slope with the constant as its covariate: ``c * z = z * full(c)``."""
+    if not isinstance(expr, Affine) or expr.transform != "id":
+        return None
+    if c == 1.0:
+        return expr
+    with torch._C.DisableTorchFunctionSubclass():
+        if expr.a_lat is not None:
+            if expr.has_x_term:
+                return None
+            x = torch.full(raw.shape, c, dtype=raw.dtype, device=raw.device)
+            return Affine(a_const=expr.a_const * c + 0.0, b_lat=expr.a_lat, x=x)
+        if expr.b_lat is not None:
+            return Affine(a_const=expr.a_const * c + 0.0, b_const=expr.b_const, b_lat=expr.b_lat,
+                          x=expr.x.expand(raw.shape) * c)
+    return Affine(a_const=expr.a_const * c + 0.0, b_const=expr.b_const * c + 0.0, x=expr.x)
+
+
+def _scale_data(expr: Expr, weight: torch.Tensor, raw: torch.Tensor) -> Expr:
+    """expr * w for a plain data tensor w (element-wise, broadcast to the result)."""
+    if not isinstance(expr, Affine) or expr.transform != "id":
+        return None
+    with torch._C.DisableTorchFunctionSubclass():
+        w = weight.to(raw.dtype).expand(raw.shape)
+        if not expr.has_x_term:
+            # (a_const + z) * w: intercept and latent become the slope of the covariate w
+            return Affine(b_const=expr.a_const, b_lat=expr.a_lat, x=w)
+        if expr.a_const == 0.0 and expr.a_lat is None:
+            return Affine(b_const=expr.b_const, b_lat=expr.b_lat, x=expr.x.expand(raw.shape) * w)
+    return None
+
+
 def _rule_sub(args, kwargs, raw):
     if kwargs.get("alpha", 1) != 1:
         return None
-    const = _as_const(args[1])
-    if const is None:
-        return None                       # subtracting data or latents needs a coefficient of -1
-    return _combine_add(_lift(args[0], raw), Affine(a_const=-const), raw.shape)
+    return _combine_add(_lift(args[0], raw), _scale_const(_lift(args[1], raw), -1.0, raw), raw.shape)
+
+
+def _rule_rsub(args, kwargs, raw):
+    """``other - self`` (``Tensor.__rsub__`` / ``torch.rsub``)."""
+    if kwargs.get("alpha", 1) != 1:
+        return None
+    return _combine_add(_lift(args[1], raw), _scale_const(_lift(args[0], raw), -1.0, raw), raw.shape)
+
+
+def _rule_neg(args, kwargs, raw):
+    return _scale_const(_expr_of(args[0]), -1.0, raw)
 
 
 def _rule_mul(args, kwargs, raw):
@@ -296,14 +339,33 @@ def _rule_mul(args, kwargs, raw):
     if expr is None or isinstance(right, LinkTensor):
         return None
     if isinstance(right, numbers.Number):
-        # `1 * x` is how ParameterizedDistribution hides raw parameters (mininf/nn.py:92-94)
-        return _shape_rule(left, raw) if float(right) == 1.0 else None
-    if isinstance(expr, Affine) and expr.is_pure_latent and _plain(right):
-        if not expr.a_lat.is_scalar and left.numel() != raw.numel():
+        if float(right) == 1.0:
+            # `1 * x` is how ParameterizedDistribution hides raw parameters (mininf/nn.py:92-94)
+            return _shape_rule(left, raw)
+        return _scale_const(expr, float(right), raw)
+    if _plain(right) and isinstance(expr, Affine):
+        whole = [ref for ref in (expr.a_lat, expr.b_lat) if ref is not None and not ref.is_scalar]
+        if whole and left.numel() != raw.numel():
+            return None
+        return _scale_data(expr, right, raw)
+    return None
+
+
+def _rule_div(args, kwargs, raw):
+    """``expr / c`` and ``expr / data``; a latent in the denominator is outside the link forms."""
+    left, right = args[0], args[1]
+    if kwargs.get("rounding_mode") is not None or not isinstance(left, LinkTensor) or \
+            isinstance(right, LinkTensor):
+        return None
+    expr = _expr_of(left)
+    if isinstance(right, numbers.Number):
+        return _scale_const(expr, 1.0 / float(right), raw) if float(right) != 0.0 else None
+    if _plain(right) and isinstance(expr, Affine):
+        whole = [ref for ref in (expr.a_lat, expr.b_lat) if ref is not None and not ref.is_scalar]
+        if whole and left.numel() != raw.numel():
             return None
         with torch._C.DisableTorchFunctionSubclass():
-            x = right.to(raw.dtype).expand(raw.shape)
-        return Affine(b_lat=expr.a_lat, x=x)
+            return _scale_data(expr, right.to(raw.dtype).reciprocal(), raw)
     return None
 
 
@@ -312,6 +374,15 @@ def _rule_exp(args, kwargs, raw):
     if expr is None or expr.transform != "id":
         return None
     return dataclasses.replace(expr, transform="exp")
+
+
+def _rule_sigmoid(args, kwargs, raw):
+    """Only meaningful as ``Bernoulli(probs=sigmoid(eta))``, which the plan lowers as
+    ``Bernoulli(logits=eta)``; anywhere else the lowering raises."""
+    expr = _expr_of(args[0])
+    if expr is None or expr.transform != "id":
+        return None
+    return dataclasses.replace(expr, transform="sigmoid")
 
 
 def _rule_matmul(args, kwargs, raw):
@@ -381,8 +452,11 @@ def _rule_select(args, kwargs, raw):
 _RULES: Dict[str, Any] = {
     "add": _rule_add, "__add__": _rule_add, "__radd__": _rule_add,
     "sub": _rule_sub, "__sub__": _rule_sub, "subtract": _rule_sub,
+    "rsub": _rule_rsub, "__rsub__": _rule_rsub,
+    "neg": _rule_neg, "__neg__": _rule_neg, "negative": _rule_neg,
     "mul": _rule_mul, "__mul__": _rule_mul, "__rmul__": _rule_mul, "multiply": _rule_mul,
-    "exp": _rule_exp,
+    "div": _rule_div, "__truediv__": _rule_div, "true_divide": _rule_div, "divide": _rule_div,
+    "exp": _rule_exp, "sigmoid": _rule_sigmoid,
     "matmul": _rule_matmul, "__matmul__": _rule_matmul, "mv": _rule_matmul,
     "__getitem__": _rule_getitem, "select": _rule_select,
     "expand": _rule_identity, "expand_as": _rule_identity, "broadcast_to": _rule_identity,

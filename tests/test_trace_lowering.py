@@ -119,7 +119,7 @@ def test_link_algebra():
     # real values ride along, so torch.distributions validates as usual
     torch.testing.assert_close((a + b * x).unwrap(), 0.5 + 2.0 * x)
     # outside the closed set: opaque
-    for opaque in (torch.sin(a), a * b, x - a, theta @ X.T @ X[:, 0], 2.0 * theta):
+    for opaque in (torch.sin(a), a * b, x - a, theta @ X.T @ X[:, 0], 2.0 / a, (a + b * x) * 2.0, (X @ theta) * 2.0):
         assert opaque._expr is None
 
 
@@ -277,3 +277,96 @@ def test_untracked_uses_of_a_latent_raise_instead_of_freezing_the_draw(how):
     with pytest.raises(NotImplementedError):
         sites, specs = trace(model, {"ab": (abi.NORMAL, torch.randn(2))}, {"y": y})
         Plan(sites, specs, 4, CPU, dry_run=True)
+
+
+def _evaluate(expr, latents, shape):
+    """The link form ``T(a_const + a_lat + (b_const + b_lat) * x)`` evaluated on the host."""
+    def value(ref):
+        if ref is None:
+            return torch.zeros(())
+        return latents[ref.name].reshape(-1)[ref.index] if ref.is_scalar else latents[ref.name]
+    out = expr.a_const + value(expr.a_lat) + torch.zeros(shape)
+    if expr.x is not None:
+        out = out + (expr.b_const + value(expr.b_lat)) * expr.x
+    return {"id": lambda t: t, "exp": torch.exp, "sigmoid": torch.sigmoid}[expr.transform](out)
+
+
+def test_widened_link_algebra_evaluates_to_the_traced_values():
+    # negation, scaling, division and differences reduce to the one affine form the kernels read
+    # (SURVEY 8 a10); every expression must reproduce the real values that ride along
+    torch.manual_seed(3)
+    latents = {"a": torch.tensor(0.5), "b": torch.tensor(-2.0), "theta": torch.randn(6)}
+    a = LinkTensor.wrap(latents["a"], Affine(a_lat=LatentRef("a", 0)))
+    b = LinkTensor.wrap(latents["b"], Affine(a_lat=LatentRef("b", 0)))
+    theta = LinkTensor.wrap(latents["theta"], Affine(a_lat=LatentRef("theta")))
+    x, w = torch.randn(6), torch.rand(6) + 0.5
+    built = {
+        "-a": -a, "2 * theta": 2.0 * theta, "theta * -0.5": theta * -0.5, "a - b * x": a - b * x,
+        "1 - x * b": 1.0 - x * b, "a / 2": a / 2, "theta / w": theta / w, "(1 + a) * x": (1 + a) * x,
+        "(b * x) * w": (b * x) * w, "(b * x) / w": (b * x) / w, "a - b": a - b, "3 - a": 3 - a,
+        "rsub": torch.rsub(a, 2.0), "a * x - 1": a * x - 1, "-(b * x)": -(b * x), "theta - x": theta - x,
+        "a - x": a - x, "0.5 * x + a": 0.5 * x + a, "exp(a - b * x)": torch.exp(a - b * x),
+        "neg of a data product": torch.neg(b * x) + 2.0, "x / 4 + theta": x / 4 + theta,
+        "sigmoid": torch.sigmoid(a + b * x),
+    }
+    for name, tensor in built.items():
+        expr = tensor._expr
+        assert isinstance(expr, Affine), name
+        torch.testing.assert_close(_evaluate(expr, latents, tensor.shape), tensor.unwrap(), msg=name)
+    # a coefficient on the intercept latent next to a slope term, a latent denominator: opaque
+    for name, tensor in {"x - a": x - a, "2 * (a + b * x)": 2 * (a + b * x), "x / a": x / a,
+                         "floor division": torch.div(a, 2.0, rounding_mode="floor"),
+                         "sigmoid of exp": torch.sigmoid(torch.exp(a))}.items():
+        assert tensor._expr is None, name
+
+
+def test_widened_links_lower_to_the_site_table():
+    x = torch.randn(5000)
+    y = torch.randn(5000)
+
+    def model():
+        a = mininf.sample("a", Normal(0, 1))
+        b = mininf.sample("b", Normal(0, 1))
+        mininf.sample("y", Normal(a - b * x / 2, 1.0))
+
+    sites, specs = trace(model, {"a": (abi.NORMAL, torch.tensor(0.1)), "b": (abi.NORMAL, torch.tensor(0.2))}, {"y": y})
+    plan = Plan(sites, specs, 8, CPU, dry_run=True)
+    (site,) = plan.sweep_groups[0]
+    link = site.param[0]
+    assert (link.a_lat, link.b_lat, link.a_const, link.b_const, link.transform) == (0, 1, 0.0, 0.0, abi.T_ID)
+    covariate = next(t for t in plan.keepalive if t.data_ptr() == link.x)
+    torch.testing.assert_close(covariate, -x / 2)
+    # a covariate built at trace time is not one of the conditioned tensors: a new batch retraces
+    plan.bind_sources([y])
+    assert not plan.rebindable
+
+
+def test_bernoulli_probs_of_a_sigmoid_is_lowered_as_logits():
+    config = configs.logistic(2000, 2000, p=64)
+    X, y = config.data["X"], config.data["y"]
+
+    def dense():
+        theta = mininf.sample("theta", Normal(0, 1), [64])
+        mininf.sample("y", Bernoulli(probs=torch.sigmoid(X @ theta)))
+
+    sites, specs = trace(dense, {"theta": (abi.NORMAL, 0.05 * torch.randn(64))}, {"y": y})
+    site, _ = Plan(sites, specs, 16, CPU, dry_run=True).dense_sites[0]
+    assert site.family == abi.BERNOULLI_LOGITS and site.n_rows == 2000
+
+    def scalar():
+        a = mininf.sample("a", Normal(0, 1))
+        mininf.sample("y", Bernoulli(probs=torch.sigmoid(a + 0.5 * X[:, 0])))
+
+    sites, specs = trace(scalar, {"a": (abi.NORMAL, torch.tensor(0.1))}, {"y": y})
+    table = Plan(sites, specs, 16, CPU, dry_run=True)._small_observed_host
+    assert len(table) == 1 and table[0].family == abi.BERNOULLI_LOGITS
+    assert (table[0].param[0].a_lat, table[0].param[0].b_const, table[0].param[0].transform) == (0, 1.0, abi.T_ID)   # 0.5 * X[:, 0] is data
+
+    # a sigmoid anywhere else is not a link the kernels evaluate
+    def elsewhere():
+        a = mininf.sample("a", Normal(0, 1))
+        mininf.sample("y", Normal(torch.sigmoid(a + 0.5 * X[:, 0]), 1.0))
+
+    sites, specs = trace(elsewhere, {"a": (abi.NORMAL, torch.tensor(0.1))}, {"y": y.float()})
+    with pytest.raises(NotImplementedError, match="sigmoid"):
+        Plan(sites, specs, 16, CPU, dry_run=True)
