@@ -1,0 +1,170 @@
+"""What the lowered site table MEANS, checked without a GPU: a float64 host interpreter of the
+C-ABI structures (``mnf_site_t`` / ``mnf_dense_site_t`` with their ``mnf_link_t`` parameters,
+include/mininf_b200.h) evaluates the log-joint the kernels are asked to compute and is compared
+with the oracle's restatement of the reference (oracle/handlers.py following mininf/core.py:211-273)
+on the same latent values. This pins the host half of the drop-in boundary (trace -> link algebra
+-> tables); the device half (tables -> numbers) is the `-m gpu` parity suite."""
+import ctypes
+
+import pytest
+import torch
+from torch.distributions import Bernoulli, Beta, Gamma, Normal, Poisson
+
+import mininf_b200 as mininf
+from mininf_b200.engine import abi
+from mininf_b200.engine.plan import LatentSpec, Plan
+from mininf_b200.engine.trace import Affine, LatentRef, LinkTensor, SiteTableTracer
+from oracle import configs, handlers
+
+from test_widened_links_gpu import make_data, make_model
+
+CPU = torch.device("cpu")
+FAMILY = {Normal: abi.NORMAL, Gamma: abi.GAMMA, Beta: abi.BETA}
+
+
+def lower(model, data, latents, n_particles=4):
+    """Trace ``model`` with the latent values wrapped as links and lower it (dry run)."""
+    draws, specs, offset = {}, [], 0
+    for name, (family, value) in latents.items():
+        numel = max(value.numel(), 1)
+        ref = LatentRef(name, 0) if numel == 1 else LatentRef(name)
+        draws[name] = LinkTensor.wrap(value.float(), Affine(a_lat=ref))
+        specs.append(LatentSpec(name, family, value.shape, numel, offset))
+        offset += numel
+    with SiteTableTracer() as tracer:
+        mininf.condition(mininf.condition(lambda: model(mininf), **data), **draws)()
+    return Plan(tracer.sites, specs, n_particles, CPU, dry_run=True), specs
+
+
+class Interpreter:
+    """Evaluates the tables for one packed latent vector z[D] in float64."""
+
+    def __init__(self, plan, z):
+        self.plan, self.z = plan, z.double()
+
+    def buffer(self, pointer, count, stride=1):
+        for tensor in self.plan.keepalive:
+            size = tensor.numel() * tensor.element_size()
+            if tensor.data_ptr() <= pointer < tensor.data_ptr() + max(size, 1):
+                offset = (pointer - tensor.data_ptr()) // tensor.element_size()
+                flat = tensor.reshape(-1)
+                index = offset + stride * torch.arange(count)
+                return flat[index]
+        raise AssertionError("a table points outside every tensor the plan keeps alive")
+
+    def link(self, L, count):
+        i = torch.arange(count)
+        a = torch.full((count,), float(L.a_const), dtype=torch.float64)
+        if L.a_lat >= 0:
+            a = a + self.z[L.a_lat + L.a_stride * i]
+        b = torch.full((count,), float(L.b_const), dtype=torch.float64)
+        if L.b_lat >= 0:
+            b = b + self.z[L.b_lat + L.b_stride * i]
+        x = self.buffer(L.x, count, L.x_stride).double() if L.x else torch.ones(count, dtype=torch.float64)
+        eta = a + b * x                              # csrc/common.cuh: x = 1 without a covariate
+        return eta.exp() if L.transform == abi.T_EXP else eta
+
+    @staticmethod
+    def log_density(family, value, p0, p1):
+        dist = {abi.NORMAL: lambda: Normal(p0, p1), abi.GAMMA: lambda: Gamma(p0, p1), abi.BETA: lambda: Beta(p0, p1),
+                abi.BERNOULLI_PROBS: lambda: Bernoulli(probs=p0), abi.BERNOULLI_LOGITS: lambda: Bernoulli(logits=p0),
+                abi.POISSON: lambda: Poisson(p0)}[family]()
+        return dist.log_prob(value)
+
+    def site(self, site):
+        count = site.numel
+        if site.value_lat >= 0:
+            value = self.z[site.value_lat + torch.arange(count)]
+        else:
+            value = self.buffer(site.value, count).double()
+        lp = self.log_density(site.family, value, self.link(site.param[0], count), self.link(site.param[1], count))
+        if site.mask:
+            lp = torch.where(self.buffer(site.mask, count), lp, torch.zeros_like(lp))
+        return site.scale * lp.sum()
+
+    def dense(self, site):
+        X = self.buffer(site.X, site.n_rows * site.ldx).double().reshape(site.n_rows, site.ldx)[:, :site.p]
+        eta = X @ self.z[site.theta_lat:site.theta_lat + site.p] + float(site.icpt_const)
+        if site.icpt_lat >= 0:
+            eta = eta + self.z[site.icpt_lat]
+        y = self.buffer(site.y, site.n_rows).double()
+        scale = self.link(site.scale, site.n_rows)
+        lp = self.log_density(site.family, y, eta.exp() if site.family == abi.POISSON else eta, scale)
+        if site.mask:
+            lp = torch.where(self.buffer(site.mask, site.n_rows), lp, torch.zeros_like(lp))
+        return site.weight * lp.sum()
+
+    def total(self):
+        plan = self.plan
+        out = sum(self.site(group[i]) for group in plan.sweep_groups for i in range(len(group)))
+        out = out + sum(self.site(s) for s in plan._small_observed_host + plan._small_global_host)
+        return out + sum(self.dense(site) for site, _ in plan.dense_sites)
+
+
+def oracle_log_joint(model, data, values):
+    data64 = {}
+    for name, value in data.items():
+        if isinstance(value, torch.masked.MaskedTensor):
+            data64[name] = torch.masked.as_masked_tensor(value.get_data().double(), value.get_mask())
+        else:
+            data64[name] = value.double()
+    conditioned = handlers.condition(handlers.condition(lambda: model(handlers), **data64),
+                                     **{k: v.double() for k, v in values.items()})
+    return sum(handlers.evaluate(conditioned, {}, validate=False).values())
+
+
+def packed(specs, values):
+    return torch.cat([values[spec.name].reshape(-1).double() for spec in specs])
+
+
+def check(model64, model32, data, latents):
+    plan, specs = lower(model32, data, latents)
+    values = {name: value for name, (_, value) in latents.items()}
+    got = Interpreter(plan, packed(specs, values)).total()
+    expected = oracle_log_joint(model64, data, values)
+    torch.testing.assert_close(got, expected.double(), rtol=2e-6, atol=1e-6)   # data are stored as float32
+    return plan
+
+
+def test_widened_links_mean_what_the_reference_scores():
+    # the model of tests/test_widened_links_gpu.py: a - b*x/2, (c + a)*x/2, Bernoulli(probs=sigmoid(c - b*x))
+    for n in (100, 5000):
+        x, data = make_data(n, 17 + n)
+        latents = {"a": (abi.NORMAL, torch.tensor(0.23)), "b": (abi.NORMAL, torch.tensor(-0.41)),
+                   "sigma": (abi.GAMMA, torch.tensor(0.9))}
+        plan = check(make_model(x.double()), make_model(x), data, latents)
+        assert (len(plan.sweep_groups) == 1) == (n >= 2048)
+
+
+@pytest.mark.parametrize("n", [50, 4000])
+def test_missing_observations_table(n):
+    config = configs.missing(n)
+    latents = {k: (abi.NORMAL, torch.tensor(v)) for k, v in zip("abcd", (0.3, 0.5, -0.2, 0.8))}
+    latents["sigma"] = (abi.GAMMA, torch.tensor(0.7))
+    check(config.model, config.model, config.data, latents)
+
+
+def test_coin_and_regression_tables():
+    config = configs.coin()
+    check(config.model, config.model, config.data, {"theta": (abi.BETA, torch.tensor(0.6))})
+    torch.manual_seed(0)
+    config = configs.regression(300, 24, sigma_latent=True)
+    check(config.model, config.model, config.data,
+          {"theta": (abi.NORMAL, 0.1 * torch.randn(24)), "sigma": (abi.GAMMA, torch.tensor(1.3))})
+    config = configs.logistic(100_000, 500, p=64, intercept=True)          # `batch` scaling: weight 200
+    latents = {name: (FAMILY[cls], 0.1 * torch.randn(params["loc"].shape)) for name, (cls, params) in config.families.items()}
+    check(config.model, config.model, config.data, latents)
+
+
+def test_element_wise_latents_and_scaled_vectors():
+    # a vector latent with a coefficient, against a data vector of the same length
+    torch.manual_seed(1)
+    w = torch.rand(7) + 0.5
+    y = torch.randn(7)
+
+    def model(m):
+        t = m.sample("t", Normal(0, 1), [7])
+        m.sample("y", Normal(2.0 * t / w - 1.0, 0.5))
+
+    check(model, model, {"y": y}, {"t": (abi.NORMAL, torch.randn(7))})
+    assert ctypes.sizeof(abi.Link) == 40          # the layout the interpreter reads (tests/test_abi.py holds it to gcc)
