@@ -5,7 +5,7 @@
 (mininf/__init__.py:1-14); ``nn.EvidenceLowerBoundLoss`` runs on hand-written sm_100a kernels
 (see DESIGN.md).
 """
-from . import core, nn, stream, util  # noqa: F401
+from . import core, distributions, nn, stream, util  # noqa: F401
 from .core import State, batch, broadcast_samples, condition, no_log_prob, sample, value  # noqa: F401
 
 __all__ = ["batch", "broadcast_samples", "condition", "nn", "no_log_prob", "value", "sample",

@@ -295,3 +295,9 @@ def test_no_log_prob_and_broadcast():
     x = torch.randn(7)
     states = mininf.broadcast_samples(mininf.condition(other, a=1.3), x=x)
     torch.testing.assert_close(states["y"], x + 1.3)
+
+
+def test_inverse_gamma_is_importable_like_the_reference() -> None:
+    # tests/test_distributions.py:5-6 of the reference
+    from mininf_b200.distributions import InverseGamma
+    assert InverseGamma(torch.rand(3, 1), torch.rand(4)).sample([7]).shape == (7, 3, 4)
