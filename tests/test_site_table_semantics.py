@@ -12,7 +12,7 @@ from torch.distributions import Bernoulli, Beta, Gamma, Normal, Poisson
 
 import mininf_b200 as mininf
 from mininf_b200.engine import abi
-from mininf_b200.engine.plan import LatentSpec, Plan
+from mininf_b200.engine.plan import ROW_LATENT, LatentSpec, Plan
 from mininf_b200.engine.trace import Affine, LatentRef, LinkTensor, SiteTableTracer
 from oracle import configs, handlers
 
@@ -29,6 +29,9 @@ def lower(model, data, latents, n_particles=4):
         numel = max(value.numel(), 1)
         ref = LatentRef(name, 0) if numel == 1 else LatentRef(name)
         draws[name] = LinkTensor.wrap(value.float(), Affine(a_lat=ref))
+        if numel > ROW_LATENT and family == abi.NORMAL:      # as assign_offsets: never packed into z
+            specs.append(LatentSpec(name, family, value.shape, numel, -1, True))
+            continue
         specs.append(LatentSpec(name, family, value.shape, numel, offset))
         offset += numel
     with SiteTableTracer() as tracer:
@@ -39,8 +42,8 @@ def lower(model, data, latents, n_particles=4):
 class Interpreter:
     """Evaluates the tables for one packed latent vector z[D] in float64."""
 
-    def __init__(self, plan, z):
-        self.plan, self.z = plan, z.double()
+    def __init__(self, plan, z, rows=None):
+        self.plan, self.z, self.rows = plan, z.double(), rows or {}
 
     def buffer(self, pointer, count, stride=1):
         for tensor in self.plan.keepalive:
@@ -94,10 +97,30 @@ class Interpreter:
             lp = torch.where(self.buffer(site.mask, site.n_rows), lp, torch.zeros_like(lp))
         return site.weight * lp.sum()
 
+    def row_latent(self, desc, Z):
+        """``mnf_rowlatent_t``: prior of the latent matrix, its observed noisy copy, the response."""
+        n, p = desc.n_rows, desc.p
+        Z = Z.double().reshape(n, p)
+        scalar = lambda L: self.link(L, 1)[0]                                      # noqa: E731
+        out = Normal(scalar(desc.prior_loc), scalar(desc.prior_scale)).log_prob(Z).sum()
+        if desc.feat:
+            feat = self.buffer(desc.feat, n * p).double().reshape(n, p)
+            out = out + Normal(Z, scalar(desc.feat_scale)).log_prob(feat).sum()
+        if desc.resp:
+            eta = Z @ self.z[desc.beta_lat:desc.beta_lat + p] + float(desc.icpt_const)
+            if desc.icpt_lat >= 0:
+                eta = eta + self.z[desc.icpt_lat]
+            if desc.resp_transform == abi.T_EXP:
+                eta = eta.exp()
+            resp = self.buffer(desc.resp, n).double()
+            out = out + self.log_density(desc.resp_family, resp, eta, scalar(desc.resp_scale)).sum()
+        return out
+
     def total(self):
         plan = self.plan
         out = sum(self.site(group[i]) for group in plan.sweep_groups for i in range(len(group)))
         out = out + sum(self.site(s) for s in plan._small_observed_host + plan._small_global_host)
+        out = out + sum(self.row_latent(desc, self.rows[name]) for name, desc in plan.row_groups.items())
         return out + sum(self.dense(site) for site, _ in plan.dense_sites)
 
 
@@ -114,13 +137,14 @@ def oracle_log_joint(model, data, values):
 
 
 def packed(specs, values):
-    return torch.cat([values[spec.name].reshape(-1).double() for spec in specs])
+    return torch.cat([values[spec.name].reshape(-1).double() for spec in specs if not spec.row_latent])
 
 
 def check(model64, model32, data, latents):
     plan, specs = lower(model32, data, latents)
     values = {name: value for name, (_, value) in latents.items()}
-    got = Interpreter(plan, packed(specs, values)).total()
+    rows = {spec.name: values[spec.name] for spec in specs if spec.row_latent}
+    got = Interpreter(plan, packed(specs, values), rows).total()
     expected = oracle_log_joint(model64, data, values)
     torch.testing.assert_close(got, expected.double(), rtol=2e-6, atol=1e-6)   # data are stored as float32
     return plan
@@ -168,3 +192,17 @@ def test_element_wise_latents_and_scaled_vectors():
 
     check(model, model, {"y": y}, {"t": (abi.NORMAL, torch.randn(7))})
     assert ctypes.sizeof(abi.Link) == 40          # the layout the interpreter reads (tests/test_abi.py holds it to gcc)
+
+
+def test_row_latent_descriptor():
+    # C4 (examples/regression-with-feature-uncertainty.md:28-38 widened to p features): the 300 x 32
+    # latent matrix is a row latent - prior, noisy features and the Poisson response in one descriptor
+    torch.manual_seed(2)
+    config = configs.feature_uncertainty(300, 32)
+    latents = {"population_scale": (abi.GAMMA, torch.tensor(1.1)),
+               "z": (abi.NORMAL, config.data["x"] + 0.3 * torch.randn(300, 32)),
+               "intercept": (abi.NORMAL, torch.tensor(0.4)), "slope": (abi.NORMAL, 0.1 * torch.randn(32))}
+    plan = check(config.model, config.model, config.data, latents)
+    (desc,) = plan.row_groups.values()
+    assert (desc.n_rows, desc.p, desc.resp_family, desc.resp_transform) == (300, 32, abi.POISSON, abi.T_EXP)
+    assert not plan.sweep_groups and not plan.dense_sites
