@@ -107,17 +107,13 @@ def _distribution_parameters(dist: Distribution, what: str) -> Tuple[int, Tuple[
 _calls = 0
 
 
-def broadcast_samples(model: Callable, states: Dict[str, torch.Tensor]) -> State:
-    """``broadcast_samples`` for CUDA samples: one trace, one launch, B samples."""
-    global _calls
-    lib = abi.load()
-    B = _assert_same_batch_size(states)
-    device = next(iter(states.values())).device
-    given = {name: maybe_as_tensor(value) for name, value in states.items()}
-    for name, value in given.items():
-        if value.device != device:
-            raise ValueError(f"all samples must live on {device}; '{name}' is on {value.device}")
-
+def lower_predictive(model: Callable, given: Dict[str, torch.Tensor], B: int, device: torch.device
+                     ) -> Tuple[List[abi.PredSite], Dict[str, LatentSpec], List[str], State, torch.Tensor, "_Lowering"]:
+    """The host half of :func:`broadcast_samples`: trace ``model`` once and lower every site the
+    samples do not provide to a ``mnf_pred_site_t``. Touches no CUDA API, so the lowering is
+    testable without a GPU. Returns the site table, the column layout, the site order, the traced
+    state, the sample matrix ``z`` [B, columns] with the given samples filled in, and the lowering
+    object that keeps the tables' data tensors alive."""
     # ---- trace once, with sample 0 standing in for every sample --------------------------------------
     symbolic = {}
     for name, value in given.items():
@@ -190,6 +186,22 @@ def broadcast_samples(model: Callable, states: Dict[str, torch.Tensor]) -> State
         if len(params) > 1:
             site.param[1] = lower._link(params[1], torch.Size([spec.numel]) if len(shape) == 0 else shape, what)
         sites.append(site)
+
+    return sites, specs, order, traced, z, lower
+
+
+def broadcast_samples(model: Callable, states: Dict[str, torch.Tensor]) -> State:
+    """``broadcast_samples`` for CUDA samples: one trace, one launch, B samples."""
+    global _calls
+    lib = abi.load()
+    B = _assert_same_batch_size(states)
+    device = next(iter(states.values())).device
+    given = {name: maybe_as_tensor(value) for name, value in states.items()}
+    for name, value in given.items():
+        if value.device != device:
+            raise ValueError(f"all samples must live on {device}; '{name}' is on {value.device}")
+    sites, specs, order, traced, z, lower = lower_predictive(model, given, B, device)
+    n_columns = z.shape[1]
 
     # ---- one launch ------------------------------------------------------------------------------------
     if sites:
