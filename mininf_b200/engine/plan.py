@@ -587,7 +587,12 @@ class Plan:
 
         for struct in self._host_structs():
             self._walk_pointers(struct, visit)
-        self.rebindable = contiguous and disjoint and resolved[0] and not self._folded_constant
+        # a one-element conditioned tensor may have been folded into a link constant by the tracer
+        # (`a + scale0`, `Normal(eta, scale0)`): its VALUE is in the tables, not its address, so new
+        # contents - in place or behind a new pointer - need a fresh trace
+        scalar_leaf = any(t.numel() == 1 and t.is_floating_point() for t in leaves)
+        self.rebindable = contiguous and disjoint and resolved[0] and not self._folded_constant and \
+            not scalar_leaf
 
     def rebind(self, leaves: Sequence[torch.Tensor]) -> bool:
         """Point the plan at new conditioned tensors (same order and layout as the ones given to

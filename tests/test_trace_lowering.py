@@ -370,3 +370,30 @@ def test_bernoulli_probs_of_a_sigmoid_is_lowered_as_logits():
     sites, specs = trace(elsewhere, {"a": (abi.NORMAL, torch.tensor(0.1))}, {"y": y.float()})
     with pytest.raises(NotImplementedError, match="sigmoid"):
         Plan(sites, specs, 16, CPU, dry_run=True)
+
+
+def test_one_element_conditioned_tensors_make_the_plan_retrace():
+    # a scalar tensor handed to `condition` is folded into a link constant; a plan that kept it
+    # across batches would silently score the old value (the reference re-reads it every step)
+    x = torch.randn(3000)
+    y = torch.randn(3000)
+    noise_scale = torch.tensor(0.5)
+
+    def model():
+        a = mininf.sample("a", Normal(0, 1))
+        scale = mininf.value("noise_scale")
+        mininf.sample("y", Normal(a + x, scale))
+
+    sites, specs = trace(model, {"a": (abi.NORMAL, torch.tensor(0.1))}, {"y": y, "noise_scale": noise_scale})
+    plan = Plan(sites, specs, 4, CPU, dry_run=True)
+    (site,) = plan.sweep_groups[0]
+    assert site.param[1].a_const == 0.5 and not site.param[1].x        # folded
+    plan.bind_sources([y, noise_scale])
+    assert not plan.rebindable and not plan.rebind([torch.randn(3000), torch.tensor(0.7)])
+    plan.bind_sources([y])                                                 # without the scalar leaf: pointers only
+    assert not plan.rebindable                                             # x is captured, not conditioned
+    sites, specs = trace(lambda: mininf.sample("y", Normal(mininf.sample("a", Normal(0, 1)), 1.0), [3000]),
+                         {"a": (abi.NORMAL, torch.tensor(0.1))}, {"y": y})
+    plan = Plan(sites, specs, 4, CPU, dry_run=True)
+    plan.bind_sources([y])
+    assert plan.rebindable
