@@ -47,13 +47,26 @@ class LatentSpec:
     row_latent: bool = False
 
 
-def assign_offsets(entries: Sequence[Tuple[str, int, torch.Size]]) -> List[LatentSpec]:
+def row_latent_names(sites: Sequence[SiteRecord]) -> set:
+    """Latents a model uses as the per-observation matrix of a ``Z @ beta`` / ``z * slope`` link:
+    whatever their size, they are swept by the row-latent kernel (the packed-latent sweeps have no
+    link that is bilinear in two latents)."""
+    names = set()
+    for record in sites:
+        for value in vars(record.distribution).values():
+            if isinstance(value, LinkTensor) and isinstance(value._expr, RowDot):
+                names.add(value._expr.Z)
+    return names
+
+
+def assign_offsets(entries: Sequence[Tuple[str, int, torch.Size]], rows: Sequence[str] = ()) -> List[LatentSpec]:
     """Latent specs for (name, family, shape) triples: small sites are packed into z[S][D] in
-    order; large Normal sites become row latents that are never materialised."""
+    order; large Normal sites - and those named in ``rows`` (:func:`row_latent_names`) - become row
+    latents that are never materialised."""
     specs, offset = [], 0
     for name, family, shape in entries:
         numel = max(shape.numel(), 1)
-        if numel > ROW_LATENT and family == abi.NORMAL and len(shape) in (1, 2):
+        if (numel > ROW_LATENT or name in rows) and family == abi.NORMAL and len(shape) in (1, 2):
             specs.append(LatentSpec(name, family, shape, numel, -1, True))
         else:
             specs.append(LatentSpec(name, family, shape, numel, offset))

@@ -336,7 +336,9 @@ def _rule_mul(args, kwargs, raw):
     if isinstance(right, LinkTensor) and not isinstance(left, LinkTensor):
         left, right = right, left
     expr = _expr_of(left)
-    if expr is None or isinstance(right, LinkTensor):
+    if isinstance(right, LinkTensor):
+        return _rule_latent_product(left, right, raw)
+    if expr is None:
         return None
     if isinstance(right, numbers.Number):
         if float(right) == 1.0:
@@ -348,6 +350,20 @@ def _rule_mul(args, kwargs, raw):
         if whole and left.numel() != raw.numel():
             return None
         return _scale_data(expr, right, raw)
+    return None
+
+
+def _rule_latent_product(left: "LinkTensor", right: "LinkTensor", raw: torch.Tensor) -> Expr:
+    """``z * slope``: an element-wise latent vector times a one-element latent is ``Z @ beta`` with
+    one feature per row (examples/regression-with-feature-uncertainty.md:38). Which latent the
+    scalar reference belongs to is checked when the site is lowered (``beta`` must hold exactly p = 1
+    element); every other product of two latent-dependent tensors is outside the link forms."""
+    for vector, scalar in ((left, right), (right, left)):
+        ve, se = _expr_of(vector), _expr_of(scalar)
+        if isinstance(ve, Affine) and ve.is_pure_latent and not ve.a_lat.is_scalar and vector.ndim == 1 and \
+                isinstance(se, Affine) and se.is_pure_latent and se.a_lat.is_scalar and se.a_lat.index == 0 and \
+                scalar.numel() == 1 and raw.shape == vector.shape:
+            return RowDot(Z=ve.a_lat.name, beta=se.a_lat.name)
     return None
 
 

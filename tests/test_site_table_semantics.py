@@ -12,7 +12,7 @@ from torch.distributions import Bernoulli, Beta, Gamma, Normal, Poisson
 
 import mininf_b200 as mininf
 from mininf_b200.engine import abi
-from mininf_b200.engine.plan import ROW_LATENT, LatentSpec, Plan
+from mininf_b200.engine.plan import Plan, assign_offsets, row_latent_names
 from mininf_b200.engine.trace import Affine, LatentRef, LinkTensor, SiteTableTracer
 from oracle import configs, handlers
 
@@ -29,13 +29,11 @@ def lower(model, data, latents, n_particles=4):
         numel = max(value.numel(), 1)
         ref = LatentRef(name, 0) if numel == 1 else LatentRef(name)
         draws[name] = LinkTensor.wrap(value.float(), Affine(a_lat=ref))
-        if numel > ROW_LATENT and family == abi.NORMAL:      # as assign_offsets: never packed into z
-            specs.append(LatentSpec(name, family, value.shape, numel, -1, True))
-            continue
-        specs.append(LatentSpec(name, family, value.shape, numel, offset))
-        offset += numel
     with SiteTableTracer() as tracer:
         mininf.condition(mininf.condition(lambda: model(mininf), **data), **draws)()
+    # as EvidenceLowerBoundLoss._build_plan: large Normal latents and the Z of a `Z @ beta` link are row latents
+    entries = [(name, family, value.shape) for name, (family, value) in latents.items()]
+    specs = assign_offsets(entries, row_latent_names(tracer.sites))
     return Plan(tracer.sites, specs, n_particles, CPU, dry_run=True), specs
 
 
@@ -206,3 +204,33 @@ def test_row_latent_descriptor():
     (desc,) = plan.row_groups.values()
     assert (desc.n_rows, desc.p, desc.resp_family, desc.resp_transform) == (300, 32, abi.POISSON, abi.T_EXP)
     assert not plan.sweep_groups and not plan.dense_sites
+
+
+def test_the_feature_uncertainty_example_as_written():
+    # examples/regression-with-feature-uncertainty.md:28-38 literally: ONE latent feature per row,
+    # n = 30, `intercept + z * slope`, the noise scale conditioned on as a known value. The product of
+    # the latent vector and the scalar latent is `Z @ beta` with p = 1, and z becomes a row latent
+    # although it is small.
+    torch.manual_seed(13)
+    n = 30
+
+    def model(m):
+        population_scale = m.sample("population_scale", Gamma(2, 2))
+        z = m.sample("z", Normal(0, population_scale), n)
+        noise_scale = m.sample("noise_scale", Gamma(2, 2))
+        m.sample("x", Normal(z, noise_scale))
+        intercept = m.sample("intercept", Normal(0, 1))
+        slope = m.sample("slope", Normal(0, 1))
+        m.sample("y", Poisson((intercept + z * slope).exp()))
+
+    z_true = torch.randn(n)
+    data = {"x": z_true + 0.3 * torch.randn(n), "y": torch.poisson(torch.exp(0.2 + 0.7 * z_true)),
+            "noise_scale": torch.tensor(0.3)}
+    latents = {"population_scale": (abi.GAMMA, torch.tensor(1.2)), "z": (abi.NORMAL, z_true + 0.1 * torch.randn(n)),
+               "intercept": (abi.NORMAL, torch.tensor(0.25)), "slope": (abi.NORMAL, torch.tensor(0.6))}
+    plan = check(model, model, data, latents)
+    (desc,) = plan.row_groups.values()
+    assert (desc.n_rows, desc.p, desc.resp_family, desc.resp_transform) == (n, 1, abi.POISSON, abi.T_EXP)
+    assert desc.feat_scale.a_const == pytest.approx(0.3) and desc.beta_lat >= 0 and desc.icpt_lat >= 0
+    # the Gamma(2, 2) density of the conditioned noise scale is a small observed site of its own
+    assert len(plan._small_observed_host) == 1 and plan._small_observed_host[0].family == abi.GAMMA

@@ -397,3 +397,38 @@ def test_one_element_conditioned_tensors_make_the_plan_retrace():
     plan = Plan(sites, specs, 4, CPU, dry_run=True)
     plan.bind_sources([y])
     assert plan.rebindable
+
+
+def test_latent_vector_times_scalar_latent_is_a_one_feature_row_dot():
+    from mininf_b200.engine.plan import assign_offsets, row_latent_names
+    from mininf_b200.engine.trace import RowDot
+    n = 40
+    x, y = torch.randn(n), torch.poisson(torch.ones(n))
+
+    def model(slope_of):
+        def run():
+            z = mininf.sample("z", Normal(0, 1), n)
+            mininf.sample("x", Normal(z, 0.5))
+            theta = mininf.sample("theta", Normal(0, 1), 3)
+            slope = mininf.sample("slope", Normal(0, 1))
+            mininf.sample("y", Poisson((0.5 + slope_of(theta, slope) * z).exp()))
+        return run
+
+    latents = {"z": (abi.NORMAL, torch.randn(n)), "theta": (abi.NORMAL, torch.randn(3)),
+               "slope": (abi.NORMAL, torch.tensor(0.4))}
+    sites, _ = trace(model(lambda theta, slope: slope), latents, {"x": x, "y": y})
+    expr = sites[-1].distribution.rate._expr
+    assert isinstance(expr, RowDot) and (expr.Z, expr.beta, expr.icpt_const, expr.transform) == ("z", "slope", 0.5, "exp")
+    assert row_latent_names(sites) == {"z"}
+    specs = assign_offsets([(k, f, v.shape) for k, (f, v) in latents.items()], row_latent_names(sites))
+    assert [s.row_latent for s in specs] == [True, False, False]
+    plan = Plan(sites, specs, 4, CPU, dry_run=True)
+    assert plan.row_groups["z"].p == 1 and plan.row_groups["z"].beta_lat == specs[2].offset
+    # an element of a longer vector is not a coefficient vector of p = 1 elements
+    sites, _ = trace(model(lambda theta, slope: theta[0]), latents, {"x": x, "y": y})
+    specs = assign_offsets([(k, f, v.shape) for k, (f, v) in latents.items()], row_latent_names(sites))
+    with pytest.raises(NotImplementedError, match="do not match"):
+        Plan(sites, specs, 4, CPU, dry_run=True)
+    # without the row-latent treatment (z packed) the site is refused, not mis-scored
+    with pytest.raises(NotImplementedError):
+        Plan(*trace(model(lambda theta, slope: slope), latents, {"x": x, "y": y}), 4, CPU, dry_run=True)

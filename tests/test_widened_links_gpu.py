@@ -72,3 +72,54 @@ def test_widened_links_against_the_float64_oracle(n, S):
     assert abs(float(loss) - expected) <= 1e-5 * abs(expected)
     for key, leaf in leaves.items():
         np.testing.assert_allclose(float(leaf.grad), grads[key], rtol=2e-4, atol=1e-3, err_msg=key)
+
+
+@pytest.mark.gpu
+def test_the_feature_uncertainty_example_as_written_against_the_float64_oracle():
+    """examples/regression-with-feature-uncertainty.md:28-38 literally (one latent feature per row,
+    n = 30, `intercept + z * slope`, the noise scale conditioned on): the row-latent kernel with
+    p = 1 on a latent far below the size at which latents become row latents by themselves."""
+    torch.manual_seed(13)
+    n, S = 30, 4
+
+    def model(m):
+        population_scale = m.sample("population_scale", Gamma(2, 2))
+        z = m.sample("z", Normal(0, population_scale), n)
+        noise_scale = m.sample("noise_scale", Gamma(2, 2))
+        m.sample("x", Normal(z, noise_scale))
+        intercept = m.sample("intercept", Normal(0, 1))
+        slope = m.sample("slope", Normal(0, 1))
+        m.sample("y", Poisson((intercept + z * slope).exp()))
+
+    z_true = torch.randn(n)
+    data = {"x": z_true + 0.3 * torch.randn(n), "y": torch.poisson(torch.exp(0.2 + 0.7 * z_true)),
+            "noise_scale": torch.tensor(0.3)}
+    z_loc = data["x"].clone()
+
+    def approximation(device, dtype):
+        values = {"z.loc": z_loc, "z.scale": 0.3 * torch.ones(n), "intercept.loc": torch.tensor(0.1),
+                  "intercept.scale": torch.tensor(0.2), "slope.loc": torch.tensor(0.5), "slope.scale": torch.tensor(0.2),
+                  "population_scale.concentration": torch.tensor(2.0), "population_scale.rate": torch.tensor(2.0)}
+        leaves = {k: v.to(device=device, dtype=dtype).clone().requires_grad_() for k, v in values.items()}
+        approx = {"z": Normal(leaves["z.loc"], leaves["z.scale"]),
+                  "intercept": Normal(leaves["intercept.loc"], leaves["intercept.scale"]),
+                  "slope": Normal(leaves["slope.loc"], leaves["slope.scale"]),
+                  "population_scale": Gamma(leaves["population_scale.concentration"], leaves["population_scale.rate"])}
+        return approx, leaves
+
+    approx32, _ = approximation("cpu", torch.float32)
+    noise = {name: elbo.draw_noise(dist, S) for name, dist in approx32.items()}
+    approx64, leaves64 = approximation("cpu", torch.float64)
+    expected = elbo.neg_elbo(model, {k: v.double() for k, v in data.items()}, approx64,
+                             {k: v.double() for k, v in noise.items()}, S)
+    expected.backward()
+
+    approx, leaves = approximation(DEV, torch.float32)
+    module = mininf.nn.EvidenceLowerBoundLoss(S, check="sync")
+    conditioned = mininf.condition(lambda: model(mininf), **{k: v.to(DEV) for k, v in data.items()})
+    loss = module(conditioned, approx, _noise={k: v.to(DEV) for k, v in noise.items()})
+    loss.backward()
+    assert list(module.last_plan.row_groups) == ["z"] and module.last_plan.row_groups["z"].p == 1
+    assert abs(float(loss) - float(expected)) <= 1e-5 * abs(float(expected))
+    for key, leaf in leaves.items():
+        np.testing.assert_allclose(leaf.grad.cpu().numpy(), leaves64[key].grad.numpy(), rtol=2e-4, atol=1e-3, err_msg=key)
