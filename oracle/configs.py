@@ -246,3 +246,69 @@ def feature_uncertainty(n: int, p: int = 32, device: Any = "cpu", seed0: int = 4
         "slope": (Normal, {"loc": torch.zeros(p), "scale": 0.2 * torch.ones(p)}),
     }
     return Config("features", model, data, families, {"n": n, "p": p, "slope_true": slope_true.to(target)})
+
+
+# ---------------------------------------------------------------------------------------------
+# Beyond BASELINE.json: link forms that REDUCE to the affine link (SURVEY.md §8 a10 widened) and
+# the feature-uncertainty example exactly as the reference writes it
+# ---------------------------------------------------------------------------------------------
+def affine_links(n: int, device: Any = "cpu", seed0: int = 6000, gen_device: Any = None) -> Config:
+    """Normal, Bernoulli and Poisson sites over one covariate whose links are written with a
+    difference, a division, a scaled latent and a sigmoid: ``a - b*x/2``, ``sigmoid(1 - b*x)``
+    (as Bernoulli probs), ``exp((0.5 + a)*x/2)``. Plain torch arithmetic in the reference
+    (autograd differentiates whatever links latents to parameters, mininf/nn.py:223-225)."""
+    target, device = device, gen_device or device
+    truth = {"a": 0.3, "b": 0.5, "sigma": 0.7}
+    generator = torch.Generator(device=device)
+    generator.manual_seed(seed0)
+    x = torch.randn(n, generator=generator, device=device)
+    w = truth["a"] - truth["b"] * x / 2 + truth["sigma"] * torch.randn(n, generator=generator, device=device)
+    k = torch.bernoulli(torch.sigmoid(1.0 - truth["b"] * x), generator=generator)
+    counts = torch.poisson(torch.exp((0.5 + truth["a"]) * x / 2), generator=generator)
+    x = x.to(target)
+
+    def model(m: Any) -> None:
+        a = m.sample("a", Normal(0, 1))
+        b = m.sample("b", Normal(0, 1))
+        sigma = m.sample("sigma", Gamma(2, 2))
+        m.sample("w", Normal(a - b * x / 2, sigma))
+        m.sample("k", Bernoulli(probs=torch.sigmoid(1.0 - b * x)))
+        m.sample("counts", Poisson(torch.exp((0.5 + a) * x / 2)))
+
+    data = {"w": w.to(target), "k": k.to(target), "counts": counts.to(target)}
+    families: Dict[str, Any] = {
+        "a": (Normal, {"loc": torch.tensor(0.1), "scale": torch.tensor(0.2)}),
+        "b": (Normal, {"loc": torch.tensor(0.3), "scale": torch.tensor(0.15)}),
+        "sigma": (Gamma, {"concentration": torch.tensor(2.0), "rate": torch.tensor(2.5)}),
+    }
+    return Config("affine_links", model, data, families, {"n": n, "x": x})
+
+
+def feature_example(n: int = 30, device: Any = "cpu", seed0: int = 7000, gen_device: Any = None) -> Config:
+    """examples/regression-with-feature-uncertainty.md:28-38 as written: ONE latent feature per
+    observation, ``Poisson((intercept + z * slope).exp())``, and - as the example's text says - the
+    observation noise scale conditioned on as a known value."""
+    target, device = device, gen_device or device
+    generator = torch.Generator(device=device)
+    generator.manual_seed(seed0)
+    z_true = torch.randn(n, generator=generator, device=device)
+    x = z_true + 0.3 * torch.randn(n, generator=generator, device=device)
+    y = torch.poisson(torch.exp(0.2 + 0.7 * z_true), generator=generator)
+
+    def model(m: Any) -> None:
+        population_scale = m.sample("population_scale", Gamma(2, 2))
+        z = m.sample("z", Normal(0, population_scale), n)
+        noise_scale = m.sample("noise_scale", Gamma(2, 2))
+        m.sample("x", Normal(z, noise_scale))
+        intercept = m.sample("intercept", Normal(0, 1))
+        slope = m.sample("slope", Normal(0, 1))
+        m.sample("y", Poisson((intercept + z * slope).exp()))
+
+    data = {"x": x.to(target), "y": y.to(target), "noise_scale": torch.tensor(0.3, device=target)}
+    families: Dict[str, Any] = {
+        "population_scale": (Gamma, {"concentration": torch.tensor(2.0), "rate": torch.tensor(2.0)}),
+        "z": (Normal, {"loc": x.detach().cpu().clone(), "scale": 0.3 * torch.ones(n)}),
+        "intercept": (Normal, {"loc": torch.tensor(0.1), "scale": torch.tensor(0.2)}),
+        "slope": (Normal, {"loc": torch.tensor(0.5), "scale": torch.tensor(0.2)}),
+    }
+    return Config("feature_example", model, data, families, {"n": n})

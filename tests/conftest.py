@@ -40,6 +40,15 @@ GOLDEN_CASES = {
 }
 
 
+# not BASELINE configurations: links that reduce to the affine form, and the feature-uncertainty example
+# as the reference writes it. Held by the CPU oracle test and by tests/test_widened_links_gpu.py only.
+EXTRA_GOLDEN_CASES = {
+    "affine_links_small": lambda cfgs, **kw: cfgs.affine_links(100, **kw),
+    "affine_links": lambda cfgs, **kw: cfgs.affine_links(5000, **kw),
+    "feature_example": lambda cfgs, **kw: cfgs.feature_example(30, **kw),
+}
+
+
 def load_golden(case, device="cpu"):
     """(config on ``device`` with CPU-generated data, golden arrays)."""
     from oracle import configs
@@ -47,7 +56,7 @@ def load_golden(case, device="cpu"):
     kwargs = {"device": device}
     if case != "coin":
         kwargs["gen_device"] = "cpu"
-    config = GOLDEN_CASES[case](configs, **kwargs)
+    config = {**GOLDEN_CASES, **EXTRA_GOLDEN_CASES}[case](configs, **kwargs)
     # install the golden parameter values as the approximation's initial values
     families = {}
     for name, (cls, params) in config.families.items():

@@ -74,6 +74,10 @@ CASES = {
     "logistic_wide": (lambda: configs.logistic(50000, 333, p=128, intercept=True), 3),
     "missing": (lambda: configs.missing(600), 4),
     "features": (lambda: configs.feature_uncertainty(300, 32), 2),
+    # beyond BASELINE.json (tests/conftest.py::EXTRA_GOLDEN_CASES)
+    "affine_links_small": (lambda: configs.affine_links(100), 3),
+    "affine_links": (lambda: configs.affine_links(5000), 8),
+    "feature_example": (lambda: configs.feature_example(30), 4),
 }
 
 

@@ -16,8 +16,6 @@ from mininf_b200.engine.plan import Plan, assign_offsets, row_latent_names
 from mininf_b200.engine.trace import Affine, LatentRef, LinkTensor, SiteTableTracer
 from oracle import configs, handlers
 
-from test_widened_links_gpu import make_data, make_model
-
 CPU = torch.device("cpu")
 FAMILY = {Normal: abi.NORMAL, Gamma: abi.GAMMA, Beta: abi.BETA}
 
@@ -149,12 +147,12 @@ def check(model64, model32, data, latents):
 
 
 def test_widened_links_mean_what_the_reference_scores():
-    # the model of tests/test_widened_links_gpu.py: a - b*x/2, (c + a)*x/2, Bernoulli(probs=sigmoid(c - b*x))
+    # oracle/configs.py::affine_links: a - b*x/2, (c + a)*x/2, Bernoulli(probs=sigmoid(c - b*x))
     for n in (100, 5000):
-        x, data = make_data(n, 17 + n)
+        config = configs.affine_links(n)
         latents = {"a": (abi.NORMAL, torch.tensor(0.23)), "b": (abi.NORMAL, torch.tensor(-0.41)),
                    "sigma": (abi.GAMMA, torch.tensor(0.9))}
-        plan = check(make_model(x.double()), make_model(x), data, latents)
+        plan = check(config.model, config.model, config.data, latents)
         assert (len(plan.sweep_groups) == 1) == (n >= 2048)
 
 
@@ -207,28 +205,17 @@ def test_row_latent_descriptor():
 
 
 def test_the_feature_uncertainty_example_as_written():
-    # examples/regression-with-feature-uncertainty.md:28-38 literally: ONE latent feature per row,
-    # n = 30, `intercept + z * slope`, the noise scale conditioned on as a known value. The product of
-    # the latent vector and the scalar latent is `Z @ beta` with p = 1, and z becomes a row latent
-    # although it is small.
+    # examples/regression-with-feature-uncertainty.md:28-38 literally (oracle/configs.py::feature_example):
+    # ONE latent feature per row, n = 30, `intercept + z * slope`, the noise scale conditioned on as a
+    # known value. The product of the latent vector and the scalar latent is `Z @ beta` with p = 1, and
+    # z becomes a row latent although it is small.
     torch.manual_seed(13)
     n = 30
-
-    def model(m):
-        population_scale = m.sample("population_scale", Gamma(2, 2))
-        z = m.sample("z", Normal(0, population_scale), n)
-        noise_scale = m.sample("noise_scale", Gamma(2, 2))
-        m.sample("x", Normal(z, noise_scale))
-        intercept = m.sample("intercept", Normal(0, 1))
-        slope = m.sample("slope", Normal(0, 1))
-        m.sample("y", Poisson((intercept + z * slope).exp()))
-
-    z_true = torch.randn(n)
-    data = {"x": z_true + 0.3 * torch.randn(n), "y": torch.poisson(torch.exp(0.2 + 0.7 * z_true)),
-            "noise_scale": torch.tensor(0.3)}
-    latents = {"population_scale": (abi.GAMMA, torch.tensor(1.2)), "z": (abi.NORMAL, z_true + 0.1 * torch.randn(n)),
+    config = configs.feature_example(n)
+    latents = {"population_scale": (abi.GAMMA, torch.tensor(1.2)),
+               "z": (abi.NORMAL, config.data["x"] + 0.1 * torch.randn(n)),
                "intercept": (abi.NORMAL, torch.tensor(0.25)), "slope": (abi.NORMAL, torch.tensor(0.6))}
-    plan = check(model, model, data, latents)
+    plan = check(config.model, config.model, config.data, latents)
     (desc,) = plan.row_groups.values()
     assert (desc.n_rows, desc.p, desc.resp_family, desc.resp_transform) == (n, 1, abi.POISSON, abi.T_EXP)
     assert desc.feat_scale.a_const == pytest.approx(0.3) and desc.beta_lat >= 0 and desc.icpt_lat >= 0
