@@ -23,7 +23,7 @@ from typing import Any, Callable, Dict, List, Optional, Set, Tuple, Type
 import torch
 from torch import distributions, nn
 
-from .core import condition
+from .core import batch, condition, no_log_prob
 from .util import OptionalSize, TensorDict, _normalize_shape, maybe_as_tensor
 
 DistributionDict = Dict[str, torch.distributions.Distribution]
@@ -402,7 +402,9 @@ class EvidenceLowerBoundLoss(nn.Module):
         key = (_callable_key(base), tuple((name, _layout_key(val)) for name, val in pinned),
                tuple((name, type(factor).__name__, tuple(factor.batch_shape))
                      for name, factor in approximation.items()),
-               self.n_particles, self.dense_precision, self.closed_form)
+               self.n_particles, self.dense_precision, self.closed_form,
+               # contexts opened AROUND the loss call shape the trace like the ones inside the model
+               tuple(batch.get_shape()), no_log_prob.get_instance() is not None)
         bound = tuple((leaf.data_ptr(), leaf._version) for leaf in leaves)
         plan = self._plans.get(key)
         if plan is not None:

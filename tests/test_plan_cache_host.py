@@ -130,3 +130,26 @@ def test_a_changed_python_constant_and_a_changed_approximation_structure_retrace
         module._plan_for(mininf.condition(make(3.0 + i), y=y), approx)
     assert len(module._plans) == 8
     assert abi.ABI_VERSION >= 7
+
+
+def test_contexts_opened_around_the_loss_call_are_part_of_the_key():
+    # `with mininf.batch(N): loss(...)` declares the full size from OUTSIDE the model (every site is then
+    # batched, as in the reference); another N is another plan
+    module = host_module()
+    y = torch.randn(3000)
+
+    def model():
+        a = mininf.sample("a", Normal(0, 1), [3000])
+        mininf.sample("y", Normal(a, 1.0))
+
+    approx = {"a": Normal(torch.zeros(3000), torch.ones(3000))}
+    scales = lambda plan: {site.scale for site in plan._small_observed_host + plan._small_global_host}  # noqa: E731
+    plain = module._plan_for(mininf.condition(model, y=y), approx)
+    assert scales(plain) == {1.0}
+    with mininf.batch(9000):
+        tripled = module._plan_for(mininf.condition(model, y=y), approx)
+        assert tripled is not plain and scales(tripled) == {3.0}
+        assert module._plan_for(mininf.condition(model, y=y), approx) is tripled
+    with mininf.batch(30000):
+        assert scales(module._plan_for(mininf.condition(model, y=y), approx)) == {10.0}
+    assert module._plan_for(mininf.condition(model, y=y), approx) is plain and module.traces == 3
