@@ -221,3 +221,69 @@ def test_the_feature_uncertainty_example_as_written():
     assert desc.feat_scale.a_const == pytest.approx(0.3) and desc.beta_lat >= 0 and desc.icpt_lat >= 0
     # the Gamma(2, 2) density of the conditioned noise scale is a small observed site of its own
     assert len(plan._small_observed_host) == 1 and plan._small_observed_host[0].family == abi.GAMMA
+
+
+def test_a_gallery_of_model_forms():
+    """Shapes of models users of the reference write (eight schools, Gamma-Poisson with an exposure,
+    heteroscedastic noise, vector Beta-Bernoulli, unpacked coefficient vectors, log offsets, centred
+    covariates, negated latents): each lowers to tables that mean what the reference scores."""
+    torch.manual_seed(0)
+    J, n = 8, 3000
+    sigma_known, effects = torch.rand(J) + 0.5, 3 * torch.randn(J)
+    exposure = torch.rand(n) + 0.5
+    counts = torch.poisson(2 * exposure)
+    x, w, y = torch.randn(n), torch.rand(n) + 0.5, torch.randn(n)
+    flips = torch.bernoulli(torch.full((12,), 0.3))
+
+    def schools(m):
+        mu = m.sample("mu", Normal(0, 5))
+        tau = m.sample("tau", Gamma(2, 0.5))
+        theta = m.sample("theta", Normal(mu, tau), [J])
+        m.sample("y", Normal(theta, sigma_known))
+
+    check(schools, schools, {"y": effects}, {"mu": (abi.NORMAL, torch.tensor(0.5)), "tau": (abi.GAMMA, torch.tensor(1.5)),
+                                             "theta": (abi.NORMAL, torch.randn(J))})
+
+    def gamma_poisson(m):
+        rate = m.sample("rate", Gamma(2, 2))
+        m.sample("y", Poisson(rate * exposure))
+
+    check(gamma_poisson, gamma_poisson, {"y": counts}, {"rate": (abi.GAMMA, torch.tensor(1.7))})
+
+    def heteroscedastic(m):
+        a = m.sample("a", Normal(0, 1))
+        b = m.sample("b", Normal(0, 1))
+        log_scale = m.sample("log_scale", Normal(0, 1))
+        s = m.sample("s", Gamma(2, 2))
+        m.sample("y", Normal(a + b * x, s * w))
+        m.sample("y2", Normal(a - x, log_scale.exp()))
+
+    check(heteroscedastic, heteroscedastic, {"y": y, "y2": y + 1},
+          {"a": (abi.NORMAL, torch.tensor(0.2)), "b": (abi.NORMAL, torch.tensor(-0.3)),
+           "log_scale": (abi.NORMAL, torch.tensor(0.1)), "s": (abi.GAMMA, torch.tensor(0.8))})
+
+    def beta_bernoulli(m):
+        p = m.sample("p", Beta(2, 2), [12])
+        m.sample("k", Bernoulli(p))
+
+    check(beta_bernoulli, beta_bernoulli, {"k": flips}, {"p": (abi.BETA, 0.8 * torch.rand(12) + 0.1)})
+
+    def unpacked(m):
+        a, b = m.sample("ab", Normal(0, 1), [2])
+        m.sample("y", Normal(a + b * x, 1.0))
+
+    check(unpacked, unpacked, {"y": y}, {"ab": (abi.NORMAL, torch.tensor([0.3, -0.2]))})
+
+    def offset(m):
+        a = m.sample("a", Normal(0, 1))
+        m.sample("y", Poisson(torch.exp(a + torch.log(exposure))))
+
+    check(offset, offset, {"y": counts}, {"a": (abi.NORMAL, torch.tensor(0.4))})
+
+    def centred(m):
+        a = m.sample("a", Normal(0, 1))
+        b = m.sample("b", Gamma(2, 2))
+        m.sample("y", Normal(a - b * (x - x.mean()) / x.std(), 2.0))
+        m.sample("y2", Normal(-a, 1.0), [n])
+
+    check(centred, centred, {"y": y, "y2": y}, {"a": (abi.NORMAL, torch.tensor(0.4)), "b": (abi.GAMMA, torch.tensor(0.7))})
