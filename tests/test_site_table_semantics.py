@@ -287,3 +287,71 @@ def test_a_gallery_of_model_forms():
         m.sample("y2", Normal(-a, 1.0), [n])
 
     check(centred, centred, {"y": y, "y2": y}, {"a": (abi.NORMAL, torch.tensor(0.4)), "b": (abi.GAMMA, torch.tensor(0.7))})
+
+
+def _random_recipe(rng, depth):
+    if depth == 0 or rng.random() < 0.25:
+        return rng.choice(["a", "b", "theta", "x", "w", 2.0, -0.5, 3.0, 0.25])
+    op = rng.choice(["add", "sub", "mul", "div", "neg"])
+    if op == "neg":
+        return ("neg", _random_recipe(rng, depth - 1))
+    return (op, _random_recipe(rng, depth - 1), _random_recipe(rng, depth - 1))
+
+
+def _run_recipe(recipe, env):
+    if not isinstance(recipe, tuple):
+        return env.get(recipe, recipe)
+    args = [_run_recipe(r, env) for r in recipe[1:]]
+    if recipe[0] == "neg":
+        return -args[0]
+    left, right = args
+    if recipe[0] == "add":
+        return left + right
+    if recipe[0] == "sub":
+        return left - right
+    if recipe[0] == "mul":
+        return left * right
+    if isinstance(right, float):
+        return left / (right if abs(right) > 1e-3 else 2.0)
+    return left / right
+
+
+def test_random_links_lower_to_tables_that_score_what_the_reference_scores():
+    """The property test of tests/test_trace_lowering.py one level down: random link expressions as
+    the location of a Normal site (or, exponentiated, as a Poisson rate) go through ``Plan`` and the
+    table interpreter; what is not refused must reproduce the oracle's log-joint."""
+    import random
+    rng = random.Random(11)
+    torch.manual_seed(11)
+    n = 40
+    x, w = torch.randn(n), torch.rand(n) + 0.5
+    y, counts = torch.randn(n), torch.poisson(torch.ones(n))
+    lowered = refused = 0
+    for trial in range(250):
+        recipe = _random_recipe(rng, 3)
+        poisson = rng.random() < 0.3
+
+        def model(m, recipe=recipe, poisson=poisson):
+            env = {"a": m.sample("a", Normal(0, 1)), "b": m.sample("b", Normal(0, 1)),
+                   "theta": m.sample("theta", Normal(0, 1), [n]), "x": x, "w": w}
+            eta = _run_recipe(recipe, env)
+            if not isinstance(eta, torch.Tensor):
+                eta = torch.as_tensor(float(eta))
+            if poisson:
+                m.sample("counts", Poisson(torch.exp(0.05 * eta)), [] if eta.ndim else [n])
+            else:
+                m.sample("y", Normal(eta, 1.5), [] if eta.ndim else [n])
+
+        latents = {"a": (abi.NORMAL, torch.tensor(0.7)), "b": (abi.NORMAL, torch.tensor(-1.3)),
+                   "theta": (abi.NORMAL, 0.5 * torch.randn(n))}
+        data = {"counts": counts} if poisson else {"y": y}
+        values = {"a": latents["a"][1], "b": latents["b"][1], "theta": latents["theta"][1], "x": x, "w": w}
+        reference_eta = _run_recipe(recipe, values)
+        if isinstance(reference_eta, torch.Tensor) and not (reference_eta.abs().max() < 200.0):   # also NaN / inf
+            continue
+        try:
+            check(model, model, data, latents)
+            lowered += 1
+        except NotImplementedError:
+            refused += 1
+    assert lowered > 60 and refused > 30

@@ -432,3 +432,70 @@ def test_latent_vector_times_scalar_latent_is_a_one_feature_row_dot():
     # without the row-latent treatment (z packed) the site is refused, not mis-scored
     with pytest.raises(NotImplementedError):
         Plan(*trace(model(lambda theta, slope: slope), latents, {"x": x, "y": y}), 4, CPU, dry_run=True)
+
+
+def test_random_link_expressions_are_either_opaque_or_exact():
+    """Property test of the link algebra: random expression trees over scalar latents, an
+    element-wise latent vector, data tensors and constants. Whatever the tracer does not mark as
+    opaque must evaluate - from the recorded link form alone - to the values torch computed. A wrong
+    rule would lower a model to tables that silently score something else."""
+    import random
+    from mininf_b200.engine.trace import RowDot
+    rng = random.Random(7)
+    torch.manual_seed(7)
+    n = 6
+    latents = {"a": torch.tensor(0.7), "b": torch.tensor(-1.3), "theta": torch.randn(n)}
+    x, w = torch.randn(n), torch.rand(n) + 0.5
+
+    def leaf():
+        kind = rng.choice(["a", "b", "theta", "x", "w", "const", "const"])
+        if kind in ("a", "b"):
+            return LinkTensor.wrap(latents[kind], Affine(a_lat=LatentRef(kind, 0)))
+        if kind == "theta":
+            return LinkTensor.wrap(latents["theta"], Affine(a_lat=LatentRef("theta")))
+        if kind == "const":
+            return rng.choice([2.0, -0.5, 3, 0.25])
+        return {"x": x, "w": w}[kind]
+
+    def grow(depth):
+        if depth == 0 or rng.random() < 0.25:
+            return leaf()
+        op = rng.choice(["add", "sub", "mul", "div", "neg", "radd", "rsub"])
+        left, right = grow(depth - 1), grow(depth - 1)
+        if op == "neg":
+            return -left if isinstance(left, torch.Tensor) else -float(left)
+        if op in ("add", "radd"):
+            return left + right
+        if op in ("sub", "rsub"):
+            return left - right
+        if op == "mul":
+            return left * right
+        if isinstance(right, torch.Tensor) and not isinstance(right, LinkTensor):
+            return left / right                       # data denominators are bounded away from zero only for w
+        return left / (right if not isinstance(right, torch.Tensor) and abs(right) > 1e-3 else 2.0)
+
+    exact = opaque = 0
+    for _ in range(600):
+        tree = grow(4)
+        if rng.random() < 0.3 and isinstance(tree, LinkTensor):
+            tree = torch.exp(tree.clamp(-3, 3)) if rng.random() < 0.2 else torch.exp(0.1 * tree)
+        if not isinstance(tree, LinkTensor):
+            continue                                   # no latent involved
+        values = tree.unwrap()
+        if not torch.isfinite(values).all():
+            continue
+        if tree._expr is None:
+            opaque += 1
+            continue
+        expr = tree._expr
+        if isinstance(expr, RowDot):                  # latent vector times scalar latent: Z @ beta with p = 1
+            got = latents[expr.Z] * latents[expr.beta] + expr.icpt_const
+            if expr.icpt_lat is not None:
+                got = got + latents[expr.icpt_lat.name].reshape(-1)[expr.icpt_lat.index or 0]
+            got = got.exp() if expr.transform == "exp" else got
+        else:
+            assert isinstance(expr, Affine)
+            got = _evaluate(expr, latents, values.shape)
+        torch.testing.assert_close(got, values, rtol=1e-4, atol=1e-4)
+        exact += 1
+    assert exact > 100 and opaque > 50                 # both outcomes are exercised
