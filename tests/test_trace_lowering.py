@@ -460,8 +460,21 @@ def test_random_link_expressions_are_either_opaque_or_exact():
     def grow(depth):
         if depth == 0 or rng.random() < 0.25:
             return leaf()
-        op = rng.choice(["add", "sub", "mul", "div", "neg", "radd", "rsub"])
+        op = rng.choice(["add", "sub", "mul", "div", "neg", "radd", "rsub", "shape"])
         left, right = grow(depth - 1), grow(depth - 1)
+        if op == "shape":                              # layout-only operations keep (or drop) the link, never bend it
+            if not isinstance(left, torch.Tensor):
+                return left
+            how = rng.choice(["reshape", "unsqueeze", "expand", "clone", "contiguous", "float", "index", "detach"])
+            if how == "reshape":
+                return left.reshape(-1) if left.ndim else left.reshape(())
+            if how == "unsqueeze":
+                return left.unsqueeze(0).squeeze(0)
+            if how == "expand":
+                return left.expand(n) if left.ndim == 0 or left.shape == (n,) else left
+            if how == "index":
+                return left[rng.randrange(n)] if left.ndim == 1 else left
+            return getattr(left, how)()
         if op == "neg":
             return -left if isinstance(left, torch.Tensor) else -float(left)
         if op in ("add", "radd"):
