@@ -15,7 +15,7 @@ import torch
 from torch import distributions as td
 
 from . import abi
-from .trace import Affine, Dense, LatentRef, LinkTensor, RowDot, SiteRecord
+from .trace import Affine, Dense, LatentRef, Linear, LinkTensor, RowDot, SiteRecord
 from ..util import is_masked
 
 BIG_SITE = 2048          # observed sites at least this long go through the fused site sweep
@@ -398,7 +398,7 @@ class Plan:
 
         # dense linear predictor in the first parameter?
         first = params[0]
-        if isinstance(first, LinkTensor) and isinstance(first._expr, Dense):
+        if isinstance(first, LinkTensor) and isinstance(first._expr, (Dense, Linear)):
             self._lower_dense(record, family, params, data_ptr, mask, numel, what)
             return
 
@@ -486,6 +486,27 @@ class Plan:
             return True
         return False
 
+    def _linear_design(self, expr: Linear, numel: int, what: str) -> Tuple[torch.Tensor, int]:
+        """Design matrix and first latent column of a several-covariate link ``sum_k z[c_k] * x_k``:
+        one column per distinct latent (covariates of a repeated latent add up), ordered like the packed
+        latents, which must be adjacent there - the dense kernels read theta as one run of z."""
+        columns: Dict[int, torch.Tensor] = {}
+        names: Dict[int, str] = {}
+        for ref, x in expr.terms:
+            column, _ = self._latent_column(ref, 1, what)
+            values = _f32(x, self.device).expand(numel) if x.numel() == 1 else _f32(x, self.device).reshape(-1)
+            if values.numel() != numel:
+                raise NotImplementedError(f"{what}: a covariate with {values.numel()} elements in a site of {numel}")
+            columns[column] = columns[column] + values if column in columns else values
+            names[column] = ref.name if ref.index in (None, 0) and self.by_name[ref.name].numel == 1 \
+                else f"{ref.name}[{ref.index}]"
+        order = sorted(columns)
+        if order != list(range(order[0], order[0] + len(order))):
+            raise NotImplementedError(
+                f"{what}: the slopes of a several-covariate link must be adjacent in the approximation "
+                f"(packed columns {order} for {[names[c] for c in order]}); list these latents next to each other")
+        return torch.stack([columns[c] for c in order], dim=1).contiguous(), order[0]
+
     def _lower_dense(self, record: SiteRecord, family: int, params: Tuple[Any, ...],
                      data_ptr: Optional[int], mask: Optional[torch.Tensor], numel: int,
                      what: str) -> None:
@@ -501,14 +522,18 @@ class Plan:
         else:
             raise NotImplementedError(f"{what}: dense links are supported for Normal(loc=X@theta), "
                                       "Bernoulli(logits=X@theta) and Poisson(rate=exp(X@theta))")
-        X = _f32(expr.X, self.device)
+        if isinstance(expr, Linear):
+            X, theta_offset = self._linear_design(expr, numel, what)
+        else:
+            X = _f32(expr.X, self.device)
+            theta = self.by_name.get(expr.theta)
+            if theta is None or theta.numel != X.shape[1]:
+                raise NotImplementedError(f"{what}: coefficient vector '{expr.theta}' does not match X")
+            theta_offset = theta.offset
         self.keepalive.append(X)
         n, p = X.shape
         if n != numel:
             raise NotImplementedError(f"{what}: X has {n} rows but the site has {numel} elements")
-        theta = self.by_name.get(expr.theta)
-        if theta is None or theta.numel != p:
-            raise NotImplementedError(f"{what}: coefficient vector '{expr.theta}' does not match X")
         icpt_lat = -1
         if expr.icpt_lat is not None:
             icpt_lat, _ = self._latent_column(expr.icpt_lat, 1, what)
@@ -522,7 +547,7 @@ class Plan:
                 raise NotImplementedError(f"{what}: the scale must be a constant or a scalar latent")
         site = abi.DenseSite(family=dense_family, p=p, n_rows=n, ldx=X.stride(0), X=X.data_ptr(),
                              y=data_ptr, mask=mask.data_ptr() if mask is not None else None,
-                             theta_lat=theta.offset, icpt_lat=icpt_lat, icpt_const=expr.icpt_const,
+                             theta_lat=theta_offset, icpt_lat=icpt_lat, icpt_const=expr.icpt_const,
                              reserved=0, scale=scale_link, weight=float(record.scale))
         has_icpt = icpt_lat >= 0 or expr.icpt_const != 0.0
         kernel = self.lib.raw("mnf_dense_tf32_kernel")(dense_family, p, self.S)

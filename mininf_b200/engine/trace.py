@@ -86,7 +86,18 @@ class RowDot:
     transform: str = "id"
 
 
-Expr = Any  # Affine | Dense | RowDot | None (opaque)
+@dataclasses.dataclass
+class Linear:
+    """``T(icpt + sum_k z[ref_k] * x_k)``: several scalar latents, each with a covariate of its own
+    (``a + b1 * x1 + b2 * x2``). Lowered as a dense-link site over the design matrix ``[x_1 ... x_K]``
+    built once at trace time; the slopes must be adjacent columns of the packed latents."""
+    terms: List[Tuple[LatentRef, torch.Tensor]]
+    icpt_const: float = 0.0
+    icpt_lat: Optional[LatentRef] = None
+    transform: str = "id"
+
+
+Expr = Any  # Affine | Dense | RowDot | Linear | None (opaque)
 
 
 def _as_const(value: Any) -> Optional[float]:
@@ -209,6 +220,8 @@ def _shape_rule(source: LinkTensor, raw: torch.Tensor, reshaper=None) -> Expr:
     same_numel = raw.numel() == source.numel()
     if isinstance(expr, (Dense, RowDot)):
         return expr if same_numel and raw.ndim == 1 else None
+    if isinstance(expr, Linear):
+        return expr if raw.shape == source.shape else None
     whole = [ref for ref in (expr.a_lat, expr.b_lat) if ref is not None and not ref.is_scalar]
     if whole and not same_numel:
         return None                     # an element-wise latent cannot be broadcast periodically
@@ -238,10 +251,38 @@ def _rule_to(args, kwargs, raw):
     return _rule_identity(args, kwargs, raw)
 
 
+def _slope_terms(expr: Expr, shape: torch.Size) -> Optional[Tuple[List[Tuple[LatentRef, torch.Tensor]], float, Optional[LatentRef]]]:
+    """(terms, constant, intercept latent) of an expression that is a sum of scalar-latent slopes."""
+    if isinstance(expr, Linear):
+        return (list(expr.terms), expr.icpt_const, expr.icpt_lat) if expr.transform == "id" else None
+    if not isinstance(expr, Affine) or expr.transform != "id":
+        return None
+    if expr.a_lat is not None and not expr.a_lat.is_scalar:
+        return None
+    if not expr.has_x_term:
+        return [], expr.a_const, expr.a_lat
+    if expr.b_const != 0.0 or expr.b_lat is None or not expr.b_lat.is_scalar or expr.x is None:
+        return None                       # a data-only term has no latent column to ride on
+    with torch._C.DisableTorchFunctionSubclass():
+        return [(expr.b_lat, expr.x.expand(shape))], expr.a_const, expr.a_lat
+
+
+def _combine_linear(left: Expr, right: Expr, shape: torch.Size) -> Expr:
+    """Sum of two expressions that both carry covariates: a several-covariate link."""
+    a, b = _slope_terms(left, shape), _slope_terms(right, shape)
+    if a is None or b is None or len(shape) != 1:
+        return None
+    if a[2] is not None and b[2] is not None:
+        return None                       # two latent intercepts
+    return Linear(terms=a[0] + b[0], icpt_const=a[1] + b[1], icpt_lat=a[2] or b[2])
+
+
 def _combine_add(left: Expr, right: Expr, shape: torch.Size) -> Expr:
     """left + right for two expressions."""
     if left is None or right is None:
         return None
+    if isinstance(left, Linear) or isinstance(right, Linear):
+        return _combine_linear(left, right, shape)
     if isinstance(right, (Dense, RowDot)):
         left, right = right, left
     if isinstance(left, (Dense, RowDot)):
@@ -255,7 +296,7 @@ def _combine_add(left: Expr, right: Expr, shape: torch.Size) -> Expr:
     if left.transform != "id" or right.transform != "id":
         return None
     if left.has_x_term and right.has_x_term:
-        return None
+        return _combine_linear(left, right, shape)
     if left.a_lat is not None and right.a_lat is not None:
         return None
     carrier = left if left.has_x_term else right
@@ -284,6 +325,10 @@ def _rule_add(args, kwargs, raw):
 def _scale_const(expr: Expr, c: float, raw: torch.Tensor) -> Expr:
     """c * expr for a Python constant. The link form has no coefficient on ``a_lat``, so a scaled
     latent moves to the slope with the constant as its covariate: ``c * z = z * full(c)``."""
+    if isinstance(expr, Linear) and expr.transform == "id" and (expr.icpt_lat is None or c == 1.0):
+        with torch._C.DisableTorchFunctionSubclass():
+            return Linear(terms=[(ref, x * c) for ref, x in expr.terms], icpt_const=expr.icpt_const * c + 0.0,
+                          icpt_lat=expr.icpt_lat)
     if not isinstance(expr, Affine) or expr.transform != "id":
         return None
     if c == 1.0:

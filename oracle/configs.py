@@ -312,3 +312,33 @@ def feature_example(n: int = 30, device: Any = "cpu", seed0: int = 7000, gen_dev
         "slope": (Normal, {"loc": torch.tensor(0.5), "scale": torch.tensor(0.2)}),
     }
     return Config("feature_example", model, data, families, {"n": n})
+
+
+def several_covariates(n: int, device: Any = "cpu", seed0: int = 8000, gen_device: Any = None) -> Config:
+    """``a + b1*x1 - b2*x2/3`` under a Normal and ``exp(0.1*(b1*x3 + b2*x2))`` under a Poisson:
+    regression written with one named scalar coefficient per covariate instead of ``X @ theta``."""
+    target, device = device, gen_device or device
+    generator = torch.Generator(device=device)
+    generator.manual_seed(seed0)
+    x1, x2 = (torch.randn(n, generator=generator, device=device) for _ in range(2))
+    x3 = torch.rand(n, generator=generator, device=device) + 0.5
+    y = 0.2 + 0.5 * x1 - 0.3 * x2 / 3 + 0.8 * torch.randn(n, generator=generator, device=device)
+    k = torch.poisson(torch.exp(0.1 * (0.5 * x3 + 0.3 * x2)), generator=generator)
+    x1, x2, x3 = x1.to(target), x2.to(target), x3.to(target)
+
+    def model(m: Any) -> None:
+        a = m.sample("a", Normal(0, 1))
+        b1 = m.sample("b1", Normal(0, 1))
+        b2 = m.sample("b2", Normal(0, 1))
+        s = m.sample("s", Gamma(2, 2))
+        m.sample("y", Normal(a + b1 * x1 - b2 * x2 / 3, s))
+        m.sample("k", Poisson(torch.exp(0.1 * (b1 * x3 + b2 * x2))))
+
+    data = {"y": y.to(target), "k": k.to(target)}
+    families: Dict[str, Any] = {
+        "a": (Normal, {"loc": torch.tensor(0.1), "scale": torch.tensor(0.2)}),
+        "b1": (Normal, {"loc": torch.tensor(0.4), "scale": torch.tensor(0.1)}),
+        "b2": (Normal, {"loc": torch.tensor(0.2), "scale": torch.tensor(0.15)}),
+        "s": (Gamma, {"concentration": torch.tensor(2.0), "rate": torch.tensor(2.5)}),
+    }
+    return Config("several_covariates", model, data, families, {"n": n})

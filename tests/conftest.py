@@ -46,6 +46,7 @@ EXTRA_GOLDEN_CASES = {
     "affine_links_small": lambda cfgs, **kw: cfgs.affine_links(100, **kw),
     "affine_links": lambda cfgs, **kw: cfgs.affine_links(5000, **kw),
     "feature_example": lambda cfgs, **kw: cfgs.feature_example(30, **kw),
+    "several_covariates": lambda cfgs, **kw: cfgs.several_covariates(4000, **kw),
 }
 
 

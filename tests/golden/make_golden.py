@@ -78,6 +78,7 @@ CASES = {
     "affine_links_small": (lambda: configs.affine_links(100), 3),
     "affine_links": (lambda: configs.affine_links(5000), 8),
     "feature_example": (lambda: configs.feature_example(30), 4),
+    "several_covariates": (lambda: configs.several_covariates(4000), 5),
 }
 
 

@@ -280,6 +280,21 @@ def test_a_gallery_of_model_forms():
 
     check(offset, offset, {"y": counts}, {"a": (abi.NORMAL, torch.tensor(0.4))})
 
+    x2 = torch.randn(n)
+
+    def several_covariates(m):                       # a + b1 x1 + b2 x2: a dense site over [x1 x2], built at trace time
+        a = m.sample("a", Normal(0, 1))
+        b1 = m.sample("b1", Normal(0, 1))
+        b2 = m.sample("b2", Normal(0, 1))
+        s = m.sample("s", Gamma(2, 2))
+        m.sample("y", Normal(a + b1 * x - b2 * x2 / 3, s))
+        m.sample("k", Poisson(torch.exp(0.1 * (b1 * w + b2 * x2))))
+
+    plan = check(several_covariates, several_covariates, {"y": y, "k": counts},
+                 {"a": (abi.NORMAL, torch.tensor(0.2)), "b1": (abi.NORMAL, torch.tensor(-0.3)),
+                  "b2": (abi.NORMAL, torch.tensor(0.6)), "s": (abi.GAMMA, torch.tensor(0.8))})
+    assert [(site.p, site.theta_lat) for site, _ in plan.dense_sites] == [(2, 1), (2, 1)]
+
     def centred(m):
         a = m.sample("a", Normal(0, 1))
         b = m.sample("b", Gamma(2, 2))

@@ -401,7 +401,7 @@ def test_one_element_conditioned_tensors_make_the_plan_retrace():
 
 def test_latent_vector_times_scalar_latent_is_a_one_feature_row_dot():
     from mininf_b200.engine.plan import assign_offsets, row_latent_names
-    from mininf_b200.engine.trace import RowDot
+    from mininf_b200.engine.trace import Linear, RowDot
     n = 40
     x, y = torch.randn(n), torch.poisson(torch.ones(n))
 
@@ -440,7 +440,7 @@ def test_random_link_expressions_are_either_opaque_or_exact():
     opaque must evaluate - from the recorded link form alone - to the values torch computed. A wrong
     rule would lower a model to tables that silently score something else."""
     import random
-    from mininf_b200.engine.trace import RowDot
+    from mininf_b200.engine.trace import Linear, RowDot
     rng = random.Random(7)
     torch.manual_seed(7)
     n = 6
@@ -487,7 +487,7 @@ def test_random_link_expressions_are_either_opaque_or_exact():
             return left / right                       # data denominators are bounded away from zero only for w
         return left / (right if not isinstance(right, torch.Tensor) and abs(right) > 1e-3 else 2.0)
 
-    exact = opaque = 0
+    exact = opaque = linear = 0
     for _ in range(600):
         tree = grow(4)
         if rng.random() < 0.3 and isinstance(tree, LinkTensor):
@@ -506,9 +506,63 @@ def test_random_link_expressions_are_either_opaque_or_exact():
             if expr.icpt_lat is not None:
                 got = got + latents[expr.icpt_lat.name].reshape(-1)[expr.icpt_lat.index or 0]
             got = got.exp() if expr.transform == "exp" else got
+        elif isinstance(expr, Linear):                # several scalar latents, each with its own covariate
+            scalar = lambda ref: latents[ref.name].reshape(-1)[ref.index or 0]     # noqa: E731
+            got = expr.icpt_const + sum(scalar(ref) * cov for ref, cov in expr.terms) + torch.zeros(values.shape)
+            if expr.icpt_lat is not None:
+                got = got + scalar(expr.icpt_lat)
+            got = got.exp() if expr.transform == "exp" else got
+            linear += 1
         else:
             assert isinstance(expr, Affine)
             got = _evaluate(expr, latents, values.shape)
         torch.testing.assert_close(got, values, rtol=1e-4, atol=1e-4)
         exact += 1
-    assert exact > 100 and opaque > 50                 # both outcomes are exercised
+    assert exact > 100 and opaque > 50                 # both outcomes are exercised (Linear: the test below)
+
+
+def test_several_covariates_lower_to_a_dense_site_over_a_design_matrix_built_at_trace_time():
+    from mininf_b200.engine.trace import Linear
+    n = 3000
+    torch.manual_seed(5)
+    x1, x2, x3, y = torch.randn(n), torch.randn(n), torch.rand(n), torch.randn(n)
+
+    def model():
+        a = mininf.sample("a", Normal(0, 1))
+        b1 = mininf.sample("b1", Normal(0, 1))
+        b2 = mininf.sample("b2", Normal(0, 1))
+        beta = mininf.sample("beta", Normal(0, 1), [2])
+        sigma = mininf.sample("sigma", Gamma(2, 2))
+        eta = 0.5 + a + b1 * x1 - b2 * x2 / 2 + beta[0] * x3 + b1 * x3        # b1 rides on two covariates
+        mininf.sample("y", Normal(eta, sigma))
+
+    latents = {"a": (abi.NORMAL, torch.tensor(0.1)), "b1": (abi.NORMAL, torch.tensor(0.2)),
+               "b2": (abi.NORMAL, torch.tensor(0.3)), "beta": (abi.NORMAL, torch.tensor([0.4, 0.5])),
+               "sigma": (abi.GAMMA, torch.tensor(1.1))}
+    sites, specs = trace(model, latents, {"y": y})
+    expr = sites[-1].distribution.loc._expr
+    assert isinstance(expr, Linear) and len(expr.terms) == 4 and expr.icpt_const == 0.5 and expr.icpt_lat.name == "a"
+    plan = Plan(sites, specs, 8, CPU, dry_run=True)
+    (site, mode), = plan.dense_sites
+    assert (site.family, site.p, site.n_rows, site.theta_lat, site.icpt_lat) == (abi.NORMAL, 3, n, 1, 0)   # b1, b2, beta[0]
+    assert mode == abi.DENSE_FP32 and site.scale.a_lat == 5
+    X = next(t for t in plan.keepalive if t.data_ptr() == site.X)
+    torch.testing.assert_close(X, torch.stack([x1 + x3, -x2 / 2, x3], dim=1))
+    plan.bind_sources([y])
+    assert not plan.rebindable                              # the design matrix is derived, a new batch retraces
+
+    # slopes that are not neighbours in the packed latents are refused with a hint, not mis-read
+    def gapped():
+        b1 = mininf.sample("b1", Normal(0, 1))
+        mininf.sample("a", Normal(0, 1))
+        beta = mininf.sample("beta", Normal(0, 1), [2])
+        mininf.sample("y", Normal(b1 * x1 + beta[1] * x2, 1.0))
+
+    sites, specs = trace(gapped, latents, {"y": y})
+    with pytest.raises(NotImplementedError, match="next to each other"):
+        Plan(sites, specs, 8, CPU, dry_run=True)
+    # a data-only term or two latent intercepts have no place in the form: opaque
+    a = LinkTensor.wrap(torch.tensor(0.5), Affine(a_lat=LatentRef("a", 0)))
+    b = LinkTensor.wrap(torch.tensor(2.0), Affine(a_lat=LatentRef("b", 0)))
+    assert (a * x1 + b * x2 + x3)._expr is None and (a + a * x1 + b + b * x2)._expr is None
+    assert isinstance(torch.exp(a * x1 + b * x2)._expr, Linear) and torch.exp(a * x1 + b * x2)._expr.transform == "exp"

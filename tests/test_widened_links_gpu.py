@@ -1,8 +1,9 @@
 """Beyond the BASELINE configurations, through the CUDA engine: links the tracer reduces to the
 affine form (`a - b*x/2`, `(c + a)*x/2`, `Bernoulli(probs=sigmoid(c - b*x))`) and
 the feature-uncertainty example exactly as the reference writes it (`intercept + z * slope`, one
-latent feature per row, n = 30). Each case is held to values the UNMODIFIED reference produced on
-the same data and noise (tests/golden/{affine_links_small,affine_links,feature_example}.npz, made by
+latent feature per row, n = 30), and regression written with one named scalar slope per covariate
+(`a + b1*x1 - b2*x2/3`: a dense site over a design matrix built at trace time). Each case is held to values the UNMODIFIED reference produced on
+the same data and noise (tests/golden/{affine_links_small,affine_links,feature_example,several_covariates}.npz, made by
 tests/golden/make_golden.py) and to a float64 evaluation of the reference algorithm with other
 noise (oracle/elbo.py). The host half - trace, link algebra, tables - is covered without a GPU in
 tests/test_trace_lowering.py and tests/test_site_table_semantics.py. Needs a B200."""
@@ -35,6 +36,8 @@ def rel(a, b):
 def check_plan(case, plan):
     if case == "feature_example":
         assert list(plan.row_groups) == ["z"] and plan.row_groups["z"].p == 1      # a row latent although small
+    elif case == "several_covariates":
+        assert [(site.p, site.theta_lat) for site, _ in plan.dense_sites] == [(2, 1), (2, 1)]  # [x1 x2], [x3 x2]
     else:
         assert (len(plan.sweep_groups) == 1) == (case == "affine_links") and not plan.row_groups
 
@@ -53,7 +56,8 @@ def test_matches_reference_golden(case):
         assert rel(leaf.grad.cpu().numpy(), golden[f"grad/{key}"]) < 1e-4, key
 
 
-@pytest.mark.parametrize("case,S", [("affine_links_small", 5), ("affine_links", 16), ("feature_example", 7)])
+@pytest.mark.parametrize("case,S", [("affine_links_small", 5), ("affine_links", 16), ("feature_example", 7),
+                                     ("several_covariates", 6)])
 def test_against_the_float64_oracle(case, S):
     """Other particle counts and fresh noise, against float64 on the CPU."""
     from oracle import configs
