@@ -59,19 +59,59 @@ def row_latent_names(sites: Sequence[SiteRecord]) -> set:
     return names
 
 
-def assign_offsets(entries: Sequence[Tuple[str, int, torch.Size]], rows: Sequence[str] = ()) -> List[LatentSpec]:
+def slope_groups(sites: Sequence[SiteRecord]) -> List[List[str]]:
+    """Names of the latents whose columns a several-covariate link (``trace.Linear``) reads as ONE
+    run of the packed latents, per site, in term order."""
+    groups = []
+    for record in sites:
+        for value in vars(record.distribution).values():
+            if isinstance(value, LinkTensor) and isinstance(value._expr, Linear):
+                names: List[str] = []
+                for ref, _ in value._expr.terms:
+                    if ref.name not in names:
+                        names.append(ref.name)
+                groups.append(names)
+    return groups
+
+
+def _packing_order(names: List[str], together: Sequence[Sequence[str]]) -> List[str]:
+    """``names`` reordered so that the members of every group in ``together`` are neighbours (groups
+    that share a member are chained in order of appearance). The caller's order is kept otherwise;
+    a layout no order satisfies is caught when the site is lowered (`Plan._linear_design`)."""
+    clusters: List[List[str]] = []
+    for group in together:
+        touching = [c for c in clusters if any(name in c for name in group)]
+        merged = [name for c in touching for name in c]
+        merged += [name for name in group if name not in merged]
+        clusters = [c for c in clusters if c not in touching] + [merged]
+    placed: List[str] = []
+    for name in names:
+        if name in placed:
+            continue
+        cluster = next((c for c in clusters if name in c), None)
+        placed.extend([n for n in cluster if n in names] if cluster else [name])
+    return placed
+
+
+def assign_offsets(entries: Sequence[Tuple[str, int, torch.Size]], rows: Sequence[str] = (),
+                   together: Sequence[Sequence[str]] = ()) -> List[LatentSpec]:
     """Latent specs for (name, family, shape) triples: small sites are packed into z[S][D] in
     order; large Normal sites - and those named in ``rows`` (:func:`row_latent_names`) - become row
-    latents that are never materialised."""
-    specs, offset = [], 0
-    for name, family, shape in entries:
+    latents that are never materialised. ``together`` (:func:`slope_groups`) lists latents that must
+    sit in neighbouring columns; the specs come back in packing order (the caller's, unless a group moved)."""
+    by_name = {name: (name, family, shape) for name, family, shape in entries}
+    order = _packing_order([name for name, _, _ in entries], together) if together else list(by_name)
+    packed: Dict[str, LatentSpec] = {}
+    offset = 0
+    for name in order:
+        _, family, shape = by_name[name]
         numel = max(shape.numel(), 1)
         if (numel > ROW_LATENT or name in rows) and family == abi.NORMAL and len(shape) in (1, 2):
-            specs.append(LatentSpec(name, family, shape, numel, -1, True))
+            packed[name] = LatentSpec(name, family, shape, numel, -1, True)
         else:
-            specs.append(LatentSpec(name, family, shape, numel, offset))
+            packed[name] = LatentSpec(name, family, shape, numel, offset)
             offset += numel
-    return specs
+    return [packed[name] for name in order]          # packing order: the latent table stays sorted by column
 
 
 def _bytes_to_device(struct_array: Any, device: torch.device) -> torch.Tensor:

@@ -358,7 +358,7 @@ class EvidenceLowerBoundLoss(nn.Module):
 
     # -- tracing ----------------------------------------------------------------------------
     def _build_plan(self, model: Callable, approximation: DistributionDict) -> Any:
-        from .engine.plan import Plan, assign_offsets, latent_parameters, row_latent_names
+        from .engine.plan import Plan, assign_offsets, latent_parameters, row_latent_names, slope_groups
         from .engine.trace import Affine, LatentRef, LinkTensor, SiteTableTracer
 
         entries = []
@@ -386,7 +386,8 @@ class EvidenceLowerBoundLoss(nn.Module):
             condition(model, **draws)()
         # latent draws the model never scores still take part in the entropy term; that mirrors
         # the reference, where `condition` silently accepts unused names
-        return Plan(tracer.sites, assign_offsets(entries, row_latent_names(tracer.sites)), self.n_particles, device,
+        specs = assign_offsets(entries, row_latent_names(tracer.sites), slope_groups(tracer.sites))
+        return Plan(tracer.sites, specs, self.n_particles, device,
                     dense_mode=self.dense_precision, closed_form=self.closed_form)
 
     def _plan_for(self, model: Callable, approximation: DistributionDict) -> Any:

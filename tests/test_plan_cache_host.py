@@ -7,7 +7,7 @@ from torch.distributions import Normal
 
 import mininf_b200 as mininf
 from mininf_b200.engine import abi
-from mininf_b200.engine.plan import Plan, assign_offsets, latent_parameters, row_latent_names
+from mininf_b200.engine.plan import Plan, assign_offsets, latent_parameters, row_latent_names, slope_groups
 from mininf_b200.engine.trace import Affine, LatentRef, LinkTensor, SiteTableTracer
 
 CPU = torch.device("cpu")
@@ -28,7 +28,7 @@ def host_module(n_particles=4):
             draws[name] = LinkTensor.wrap(factor.sample(), Affine(a_lat=ref))
         with SiteTableTracer() as tracer:
             mininf.condition(model, **draws)()
-        return Plan(tracer.sites, assign_offsets(entries, row_latent_names(tracer.sites)), n_particles, CPU,
+        return Plan(tracer.sites, assign_offsets(entries, row_latent_names(tracer.sites), slope_groups(tracer.sites)), n_particles, CPU,
                     dry_run=True)
 
     module._build_plan = build

@@ -12,7 +12,7 @@ from torch.distributions import Bernoulli, Beta, Gamma, Normal, Poisson
 
 import mininf_b200 as mininf
 from mininf_b200.engine import abi
-from mininf_b200.engine.plan import Plan, assign_offsets, row_latent_names
+from mininf_b200.engine.plan import Plan, assign_offsets, row_latent_names, slope_groups
 from mininf_b200.engine.trace import Affine, LatentRef, LinkTensor, SiteTableTracer
 from oracle import configs, handlers
 
@@ -31,7 +31,7 @@ def lower(model, data, latents, n_particles=4):
         mininf.condition(mininf.condition(lambda: model(mininf), **data), **draws)()
     # as EvidenceLowerBoundLoss._build_plan: large Normal latents and the Z of a `Z @ beta` link are row latents
     entries = [(name, family, value.shape) for name, (family, value) in latents.items()]
-    specs = assign_offsets(entries, row_latent_names(tracer.sites))
+    specs = assign_offsets(entries, row_latent_names(tracer.sites), slope_groups(tracer.sites))
     return Plan(tracer.sites, specs, n_particles, CPU, dry_run=True), specs
 
 

@@ -566,3 +566,30 @@ def test_several_covariates_lower_to_a_dense_site_over_a_design_matrix_built_at_
     b = LinkTensor.wrap(torch.tensor(2.0), Affine(a_lat=LatentRef("b", 0)))
     assert (a * x1 + b * x2 + x3)._expr is None and (a + a * x1 + b + b * x2)._expr is None
     assert isinstance(torch.exp(a * x1 + b * x2)._expr, Linear) and torch.exp(a * x1 + b * x2)._expr.transform == "exp"
+
+
+def test_slopes_of_a_several_covariate_link_are_packed_next_to_each_other():
+    from mininf_b200.engine.plan import _packing_order, assign_offsets, slope_groups
+    n = 3000
+    x1, x2, y = torch.randn(n), torch.randn(n), torch.randn(n)
+
+    def model():
+        b1 = mininf.sample("b1", Normal(0, 1))
+        a = mininf.sample("a", Normal(0, 1))
+        sigma = mininf.sample("sigma", Gamma(2, 2))
+        b2 = mininf.sample("b2", Normal(0, 1))
+        mininf.sample("y", Normal(a + b1 * x1 + b2 * x2, sigma))
+
+    latents = {"b1": (abi.NORMAL, torch.tensor(0.2)), "a": (abi.NORMAL, torch.tensor(0.1)),
+               "sigma": (abi.GAMMA, torch.tensor(1.1)), "b2": (abi.NORMAL, torch.tensor(0.3))}
+    sites, in_order = trace(model, latents, {"y": y})
+    with pytest.raises(NotImplementedError, match="next to each other"):       # the caller's order: b1 | a sigma | b2
+        Plan(sites, in_order, 4, CPU, dry_run=True)
+    assert slope_groups(sites) == [["b1", "b2"]]
+    specs = assign_offsets([(k, f, v.shape) for k, (f, v) in latents.items()], (), slope_groups(sites))
+    assert [(s.name, s.offset) for s in specs] == [("b1", 0), ("b2", 1), ("a", 2), ("sigma", 3)]
+    (site, _), = Plan(sites, specs, 4, CPU, dry_run=True).dense_sites
+    assert (site.p, site.theta_lat, site.icpt_lat, site.scale.a_lat) == (2, 0, 2, 3)
+    # without groups nothing moves; chained groups end up in one run
+    assert [s.name for s in assign_offsets([(k, f, v.shape) for k, (f, v) in latents.items()])] == list(latents)
+    assert _packing_order(list("abcdef"), [["b", "e"], ["e", "c"], ["f", "a"]]) == ["f", "a", "b", "e", "c", "d"]
