@@ -345,7 +345,8 @@ class Plan:
             if not isinstance(expr, Affine):
                 raise NotImplementedError(
                     f"{what} is not a supported link of the latent variables (supported: a latent "
-                    "itself, constants, data, `c + d*x`, `exp(a + b*x)`, `X @ theta`)")
+                    "itself, constants, data, `c + d*x` and what reduces to it, `exp(a + b*x)`, `X @ theta`, "
+                    "`a + b1*x1 + b2*x2` with scalar latents; see README.md)")
             if expr.transform not in ("id", "exp"):
                 raise NotImplementedError(
                     f"{what}: `{expr.transform}` of a latent-dependent tensor is not a supported link "

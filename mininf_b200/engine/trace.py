@@ -13,7 +13,10 @@ forms is what the CUDA kernels implement (include/mininf_b200.h):
   ``a - b*x``, ``c - x``, ``(c + z)*x`` (a scaled latent moves to the slope, the constant or the
   product of data tensors becomes its covariate);
 * ``Dense``:   ``T(icpt + X @ theta)`` - ``X @ theta`` with an optional scalar intercept;
-* ``RowDot``:  ``T(icpt + Z @ beta)`` - a per-observation latent matrix times a latent vector.
+* ``RowDot``:  ``T(icpt + Z @ beta)`` - a per-observation latent matrix times a latent vector
+  (``z * slope`` for one latent feature per row);
+* ``Linear``:  ``T(icpt + b1*x1 + b2*x2 + ...)`` - one scalar latent per covariate; lowered like
+  ``Dense`` over the design matrix ``[x1 x2 ...]`` built once at trace time.
 
 Anything else makes the tensor *opaque*; an opaque tensor reaching a distribution parameter of a
 site that contributes to the log-density raises ``NotImplementedError`` (no fallback).
