@@ -23,7 +23,7 @@ from torch.distributions import Distribution
 
 from . import abi
 from .plan import LatentSpec, Plan
-from .trace import Affine, Dense, LatentRef, LinkTensor
+from .trace import Affine, Dense, LatentRef, Linear, LinkTensor
 from ..core import State, TracerMixin, Value, _assert_same_batch_size
 from ..util import OptionalSize, _normalize_shape, maybe_as_tensor
 
@@ -170,13 +170,17 @@ def lower_predictive(model: Callable, given: Dict[str, torch.Tensor], B: int, de
         if getattr(expr, "transform", "id") not in ("id", "exp"):
             raise NotImplementedError(f"{what}: `{expr.transform}` of a sample-dependent tensor is not a supported "
                                       "link here (sigmoid only as Bernoulli(probs=sigmoid(...)))")
-        if isinstance(expr, Dense):
-            X = expr.X.detach().to(device=device, dtype=torch.float32).contiguous()
+        if isinstance(expr, (Dense, Linear)):
+            if isinstance(expr, Linear):               # b1*x1 + b2*x2 + ...: a design matrix built here, as in Plan
+                X, theta_offset = lower._linear_design(expr, spec.numel, what)
+            else:
+                X = expr.X.detach().to(device=device, dtype=torch.float32).contiguous()
+                theta = specs.get(expr.theta)
+                if theta is None or theta.numel != X.shape[1] or X.shape[0] != spec.numel:
+                    raise NotImplementedError(f"{what}: `X @ theta` does not match the site")
+                theta_offset = theta.offset
             lower.keepalive.append(X)
-            theta = specs.get(expr.theta)
-            if theta is None or theta.numel != X.shape[1] or X.shape[0] != spec.numel:
-                raise NotImplementedError(f"{what}: `X @ theta` does not match the site")
-            site.X, site.ldx, site.p, site.theta_lat = X.data_ptr(), X.stride(0), X.shape[1], theta.offset
+            site.X, site.ldx, site.p, site.theta_lat = X.data_ptr(), X.stride(0), X.shape[1], theta_offset
             site.icpt_const = expr.icpt_const
             if expr.icpt_lat is not None:
                 site.icpt_lat, _ = lower._latent_column(expr.icpt_lat, 1, what)

@@ -109,3 +109,23 @@ def test_widened_links_and_the_sigmoid_rewrite_in_the_predictive_lowering():
 
     with pytest.raises(NotImplementedError, match="sigmoid"):
         lower_predictive(sigmoid_value, {"a": a}, 4, CPU)
+
+
+def test_several_covariates_in_the_predictive_lowering():
+    x1, x2 = torch.linspace(-1.0, 1.0, 9), torch.linspace(0.0, 2.0, 9) ** 2
+
+    def model():
+        a = mininf.sample("a", Normal(0, 1))
+        b1 = mininf.sample("b1", Normal(0, 1))
+        b2 = mininf.sample("b2", Normal(0, 1))
+        mean = mininf.value("mean", a + b1 * x1 - b2 * x2 / 3)
+        mininf.sample("y", Normal(mean, 0.5))
+
+    a, b1, b2 = torch.randn(5), torch.randn(5), torch.randn(5)
+    sites, specs, order, traced, z, lower = lower_predictive(model, {"a": a, "b1": b1, "b2": b2}, 5, CPU)
+    mean, y = sites
+    assert (mean.kind, mean.p, mean.theta_lat, mean.icpt_lat) == (abi.PRED_VALUE, 2, specs["b1"].offset, specs["a"].offset)
+    filled = evaluate_value_sites(sites, lower, z)
+    lo = specs["mean"].offset
+    torch.testing.assert_close(filled[:, lo:lo + 9], a[:, None] + b1[:, None] * x1 - b2[:, None] * x2 / 3)
+    assert (y.kind, y.family, y.param[0].a_lat, y.param[0].a_stride) == (abi.PRED_DRAW, abi.NORMAL, lo, 1)
