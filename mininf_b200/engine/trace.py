@@ -465,11 +465,25 @@ def _rule_matmul(args, kwargs, raw):
     return None
 
 
+_MAX_INDICATOR_ELEMENTS = 1 << 28     # rows x groups of an `alpha[group]` indicator matrix (1 GiB of fp32)
+
+
 def _rule_getitem(args, kwargs, raw):
     source, index = args[0], args[1]
     expr = _expr_of(source)
     if not isinstance(expr, Affine) or not expr.is_pure_latent or expr.a_lat.is_scalar:
         return None
+    if isinstance(index, torch.Tensor) and not isinstance(index, LinkTensor) and index.ndim == 1 and \
+            index.numel() > 1 and index.dtype in (torch.int64, torch.int32) and source.ndim == 1 and raw.ndim == 1:
+        # `alpha[group]` - a coefficient per group picked by an integer data vector (random effects) - is
+        # one_hot(group) @ alpha: a dense link over an indicator design matrix built once at trace time
+        groups = source.numel()
+        if index.numel() * groups > _MAX_INDICATOR_ELEMENTS:
+            return None
+        with torch._C.DisableTorchFunctionSubclass():
+            wrapped = torch.where(index < 0, index + groups, index).long()
+            indicator = torch.nn.functional.one_hot(wrapped, groups).to(source.dtype)
+        return Dense(X=indicator, theta=expr.a_lat.name)
     if raw.numel() != 1:
         return None
     if isinstance(index, torch.Tensor):

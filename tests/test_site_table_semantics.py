@@ -295,6 +295,22 @@ def test_a_gallery_of_model_forms():
                   "b2": (abi.NORMAL, torch.tensor(0.6)), "s": (abi.GAMMA, torch.tensor(0.8))})
     assert [(site.p, site.theta_lat) for site, _ in plan.dense_sites] == [(2, 1), (2, 1)]
 
+    G = 7
+    group = torch.randint(0, G, (n,))
+
+    def random_intercepts(m):                        # alpha[group]: a dense site over an indicator matrix
+        mu = m.sample("mu", Normal(0, 1))
+        tau = m.sample("tau", Gamma(2, 2))
+        alpha = m.sample("alpha", Normal(0, tau), [G])
+        s = m.sample("s", Gamma(2, 2))
+        m.sample("y", Normal(mu + alpha[group], s))
+        m.sample("k", Poisson(torch.exp(alpha[group - G])))          # negative indices wrap like torch's
+
+    plan = check(random_intercepts, random_intercepts, {"y": y, "k": counts},
+                 {"mu": (abi.NORMAL, torch.tensor(0.2)), "tau": (abi.GAMMA, torch.tensor(0.9)),
+                  "alpha": (abi.NORMAL, 0.3 * torch.randn(G)), "s": (abi.GAMMA, torch.tensor(0.8))})
+    assert [(site.p, site.theta_lat, site.icpt_lat) for site, _ in plan.dense_sites] == [(G, 2, 0), (G, 2, -1)]
+
     def centred(m):
         a = m.sample("a", Normal(0, 1))
         b = m.sample("b", Gamma(2, 2))

@@ -593,3 +593,19 @@ def test_slopes_of_a_several_covariate_link_are_packed_next_to_each_other():
     # without groups nothing moves; chained groups end up in one run
     assert [s.name for s in assign_offsets([(k, f, v.shape) for k, (f, v) in latents.items()])] == list(latents)
     assert _packing_order(list("abcdef"), [["b", "e"], ["e", "c"], ["f", "a"]]) == ["f", "a", "b", "e", "c", "d"]
+
+
+def test_indexing_a_latent_vector_with_group_labels_is_a_dense_link_over_an_indicator_matrix():
+    alpha = LinkTensor.wrap(torch.tensor([0.1, -0.2, 0.3]), Affine(a_lat=LatentRef("alpha")))
+    mu = LinkTensor.wrap(torch.tensor(1.5), Affine(a_lat=LatentRef("mu", 0)))
+    group = torch.tensor([2, 0, 0, 1, 2, -1])
+    picked = alpha[group]
+    assert isinstance(picked._expr, Dense) and picked._expr.theta == "alpha"
+    torch.testing.assert_close(picked._expr.X @ alpha.unwrap(), picked.unwrap())       # one_hot(group) @ alpha
+    shifted = (mu + picked)._expr
+    assert isinstance(shifted, Dense) and shifted.icpt_lat == LatentRef("mu", 0)
+    # one element stays a scalar reference; float or boolean indices and 2-D sources are not this form
+    assert alpha[torch.tensor(1)]._expr.a_lat == LatentRef("alpha", 1)
+    assert alpha[torch.tensor([1])]._expr is None or alpha[torch.tensor([1])]._expr.a_lat == LatentRef("alpha", 1)
+    assert alpha[torch.tensor([True, False, True])]._expr is None
+    assert (alpha[group] * 2.0)._expr is None
