@@ -534,6 +534,17 @@ class Plan:
         columns: Dict[int, torch.Tensor] = {}
         names: Dict[int, str] = {}
         for ref, x in expr.terms:
+            spec = self.by_name.get(ref.name)
+            if spec is not None and not ref.is_scalar and spec.numel > 1:
+                # a whole coefficient vector with its block X[n, G] (`X @ theta`, `alpha[group]`)
+                first, _ = self._latent_column(LatentRef(ref.name, 0), 1, what)
+                block = _f32(x, self.device)
+                if block.ndim != 2 or tuple(block.shape) != (numel, spec.numel):
+                    raise NotImplementedError(f"{what}: the block of '{ref.name}' does not match the site")
+                for g in range(spec.numel):
+                    columns[first + g] = columns[first + g] + block[:, g] if first + g in columns else block[:, g]
+                    names[first + g] = f"{ref.name}[{g}]"
+                continue
             column, _ = self._latent_column(ref, 1, what)
             values = _f32(x, self.device).expand(numel) if x.numel() == 1 else _f32(x, self.device).reshape(-1)
             if values.numel() != numel:

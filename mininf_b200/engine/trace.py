@@ -94,7 +94,7 @@ class Linear:
     """``T(icpt + sum_k z[ref_k] * x_k)``: several scalar latents, each with a covariate of its own
     (``a + b1 * x1 + b2 * x2``). Lowered as a dense-link site over the design matrix ``[x_1 ... x_K]``
     built once at trace time; the slopes must be adjacent columns of the packed latents."""
-    terms: List[Tuple[LatentRef, torch.Tensor]]
+    terms: List[Tuple[LatentRef, torch.Tensor]]     # (scalar reference, x[n]) or (whole vector latent, X[n, G])
     icpt_const: float = 0.0
     icpt_lat: Optional[LatentRef] = None
     transform: str = "id"
@@ -258,6 +258,11 @@ def _slope_terms(expr: Expr, shape: torch.Size) -> Optional[Tuple[List[Tuple[Lat
     """(terms, constant, intercept latent) of an expression that is a sum of scalar-latent slopes."""
     if isinstance(expr, Linear):
         return (list(expr.terms), expr.icpt_const, expr.icpt_lat) if expr.transform == "id" else None
+    if isinstance(expr, Dense):
+        # `X @ theta` / `alpha[group]` joining other covariates: its block is copied into the design matrix
+        if expr.transform != "id" or expr.X.numel() > _MAX_INDICATOR_ELEMENTS:
+            return None
+        return [(LatentRef(expr.theta), expr.X)], expr.icpt_const, expr.icpt_lat
     if not isinstance(expr, Affine) or expr.transform != "id":
         return None
     if expr.a_lat is not None and not expr.a_lat.is_scalar:
@@ -288,6 +293,8 @@ def _combine_add(left: Expr, right: Expr, shape: torch.Size) -> Expr:
         return _combine_linear(left, right, shape)
     if isinstance(right, (Dense, RowDot)):
         left, right = right, left
+    if isinstance(left, Dense) and (isinstance(right, Dense) or (isinstance(right, Affine) and right.has_x_term)):
+        return _combine_linear(left, right, shape)       # mixed model: a block of coefficients plus named slopes
     if isinstance(left, (Dense, RowDot)):
         if not isinstance(right, Affine) or right.has_x_term or right.transform != "id" or \
                 left.transform != "id":

@@ -311,6 +311,24 @@ def test_a_gallery_of_model_forms():
                   "alpha": (abi.NORMAL, 0.3 * torch.randn(G)), "s": (abi.GAMMA, torch.tensor(0.8))})
     assert [(site.p, site.theta_lat, site.icpt_lat) for site, _ in plan.dense_sites] == [(G, 2, 0), (G, 2, -1)]
 
+    X4 = torch.randn(n, 4)
+
+    def mixed(m):                                    # random intercepts + a named slope; a coefficient block + a named slope
+        mu = m.sample("mu", Normal(0, 1))
+        alpha = m.sample("alpha", Normal(0, 1), [G])
+        s = m.sample("s", Gamma(2, 2))
+        b = m.sample("b", Normal(0, 1))
+        theta = m.sample("theta", Normal(0, 1), [4])
+        m.sample("y", Normal(mu + alpha[group] + b * x, s))
+        m.sample("k", Poisson(torch.exp(0.2 * (X4.to(theta.dtype) @ theta - b * w))))
+
+    plan = check(mixed, mixed, {"y": y, "k": counts},
+                 {"mu": (abi.NORMAL, torch.tensor(0.2)), "alpha": (abi.NORMAL, 0.3 * torch.randn(G)),
+                  "s": (abi.GAMMA, torch.tensor(0.8)), "b": (abi.NORMAL, torch.tensor(-0.4)),
+                  "theta": (abi.NORMAL, 0.2 * torch.randn(4))})
+    # packed as mu | alpha b theta | s: both sites read one run of columns (alpha b, b theta)
+    assert [(site.p, site.theta_lat) for site, _ in plan.dense_sites] == [(G + 1, 1), (5, 1 + G)]
+
     def centred(m):
         a = m.sample("a", Normal(0, 1))
         b = m.sample("b", Gamma(2, 2))
