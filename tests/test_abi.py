@@ -121,3 +121,21 @@ def test_build_units_track_their_own_headers():
     assert {"dense_tc.cuh", "dense_tcr.cuh", "dense_simt.cuh"} <= closures["dense"]
     assert "rowlatent.cuh" in closures["rowlatent"] and "small.cuh" in closures["abi"]
     assert len({build.unit_digest(unit) for unit in build.UNITS}) == len(build.UNITS)
+
+
+def test_the_c_consumer_compiles_and_links_against_the_header_and_the_library(tmp_path):
+    """tests/c/plan_step.c (run on a B200 by tests/test_engine_gpu.py) must at least build here: a
+    plain C11 translation unit over include/mininf_b200.h, linked against the in-tree library."""
+    import shutil
+    import subprocess
+    from mininf_b200.engine import build
+    if shutil.which("gcc") is None or not build.LIB_PATH.exists():
+        pytest.skip("needs gcc and the built library")
+    root = build.PACKAGE_DIR.parent
+    binary = tmp_path / "plan_step"
+    result = subprocess.run(["gcc", "-O1", "-std=c11", "-Wall", "-I", str(root / "include"), "-I", "/usr/local/cuda/include",
+                             str(root / "tests" / "c" / "plan_step.c"), "-o", str(binary), str(build.LIB_PATH),
+                             "-L/usr/local/cuda/lib64", "-lcudart", "-lm", f"-Wl,-rpath,{build.LIB_DIR}",
+                             "-Wl,-rpath,/usr/local/cuda/lib64"], capture_output=True, text=True)
+    assert result.returncode == 0, result.stderr
+    assert binary.exists()
